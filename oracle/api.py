@@ -1,0 +1,118 @@
+"""Reference-shaped facade over :mod:`oracle.hp_oracle` (TEST INFRASTRUCTURE).
+
+Gives the oracle the same names and call signatures as the reference modules (and as the
+CUDA package), so one parity case in ``oracle/cases.py`` can be evaluated against the real
+reference, the oracle restatement and the B200 path interchangeably."""
+from __future__ import annotations
+
+import types
+
+import torch.nn as nn
+
+from . import hp_oracle as O
+
+
+class JointsMSELoss(nn.Module):                      # uda/model/loss.py:27-65
+    def __init__(self, reduction="mean"):
+        super().__init__()
+        self.reduction = reduction
+
+    def forward(self, output, target, target_weight=None):
+        return O.joints_mse_loss(output, target, target_weight, self.reduction)
+
+
+class JointsKLLoss(nn.Module):                       # uda/model/loss.py:115-158
+    def __init__(self, reduction="mean", epsilon=0.0):
+        super().__init__()
+        self.reduction = reduction
+        self.epsilon = epsilon
+
+    def forward(self, output, target, target_weight=None):
+        return O.joints_kl_loss(output, target, target_weight, self.reduction, self.epsilon)
+
+
+class _PLG(nn.Module):
+    variant = "base"
+
+    def __init__(self, num_keypoints, height=64, width=64, sigma=2):
+        super().__init__()
+        self.height, self.width, self.sigma = height, width, sigma
+
+    def forward(self, y):
+        return O.pseudo_label(y, self.variant, self.sigma)
+
+
+class PseudoLabelGenerator(_PLG):                    # uda/model/regda_4.py:17-86
+    variant = "base"
+
+
+class PseudoLabelGenerator02(_PLG):                  # uda/model/regda_7.py:3044-3114 (copy of base)
+    variant = "base"
+
+
+class PseudoLabelGenerator01(_PLG):                  # uda/model/regda_7.py:2956-3039
+    variant = "01"
+
+    def __init__(self, num_keypoints, height=16, width=16, sigma=2):
+        super().__init__(num_keypoints, height, width, sigma)
+
+
+class PseudoLabelGenerator03(_PLG):                  # uda/model/regda_7.py:3118-3201
+    variant = "03"
+
+    def __init__(self, num_keypoints, height=32, width=32, sigma=2):
+        super().__init__(num_keypoints, height, width, sigma)
+
+
+class _RD(nn.Module):
+    variant = "base"
+
+    def __init__(self, pseudo_label_generator, criterion):
+        super().__init__()
+        self.pseudo_label_generator = pseudo_label_generator
+        self.criterion = criterion
+
+    def _run(self, y, y_adv, y_adv2, weight, mode):
+        assert mode in ["min", "max"]
+        gt, gf = O.ground_maps(self.variant, y.detach(), y_adv2)
+        self.ground_truth, self.ground_false = gt, gf
+        return self.criterion(y_adv, gt if mode == "min" else gf, weight)
+
+
+class RegressionDisparity(_RD):                      # uda/model/regda_4.py:89-143
+    variant = "base"
+
+    def forward(self, y, y_adv, weight=None, mode="min"):
+        return self._run(y, y_adv, None, weight, mode)
+
+
+class RegressionDisparityx1(_RD):                    # uda/model/regda_7.py:3206-3268
+    variant = "x1"
+
+    def forward(self, y, y_adv, weight=None, mode="min"):
+        return self._run(y, y_adv, None, weight, mode)
+
+
+class RegressionDisparityx5(_RD):                    # uda/model/regda_7.py:3485-3561
+    variant = "x5"
+
+    def forward(self, y, y_adv, y_adv2, weight=None, mode="min"):
+        return self._run(y, y_adv, y_adv2, weight, mode)
+
+
+class RegressionDisparityx6(_RD):                    # uda/model/regda_7.py:3564-3632
+    variant = "x6"
+
+    def forward(self, y, y_adv, y_adv2, weight=None, mode="min"):
+        return self._run(y, y_adv, y_adv2, weight, mode)
+
+
+def namespace():
+    return types.SimpleNamespace(
+        get_max_preds=O.get_max_preds, accuracy=O.accuracy, generate_target=O.generate_target,
+        JointsMSELoss=JointsMSELoss, JointsKLLoss=JointsKLLoss,
+        PseudoLabelGenerator=PseudoLabelGenerator, PseudoLabelGenerator01=PseudoLabelGenerator01,
+        PseudoLabelGenerator02=PseudoLabelGenerator02, PseudoLabelGenerator03=PseudoLabelGenerator03,
+        RegressionDisparity=RegressionDisparity, RegressionDisparityx1=RegressionDisparityx1,
+        RegressionDisparityx5=RegressionDisparityx5, RegressionDisparityx6=RegressionDisparityx6,
+    )
