@@ -1,0 +1,48 @@
+// hp_api.cu - library-level entry points and the error plumbing of libhp_b200.so.
+#include <cstdarg>
+#include <cstdio>
+
+#include "hp_common.cuh"
+
+namespace hp {
+
+static thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int launch_status(const char* what) {
+    const cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) return HP_OK;
+    snprintf(g_err, sizeof(g_err), "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+    return static_cast<int>(e);
+}
+
+}  // namespace hp
+
+extern "C" HP_API int hp_version(void) { return 100; /* 0.1.0 */ }
+
+extern "C" HP_API const char* hp_last_error(void) { return hp::g_err; }
+
+extern "C" HP_API int hp_device_sm_count(void) {
+    int dev = 0, sms = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) {
+        hp::fail(-1, "hp_device_sm_count: %s", cudaGetErrorString(e));
+        return -static_cast<int>(e);
+    }
+    return sms;
+}
+
+extern "C" HP_API size_t hp_workspace_bytes(int n_maps, int K) {
+    (void)K;
+    // Workspace header + one float64 partial slot per map for deterministic fixed-order sums
+    const size_t n = n_maps > 0 ? static_cast<size_t>(n_maps) : 0;
+    return sizeof(hp::Workspace) + 256 + 2 * sizeof(double) * n;
+}

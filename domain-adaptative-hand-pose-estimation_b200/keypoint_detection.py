@@ -1,0 +1,104 @@
+"""Decode + PCK on the GPU behind the reference's signatures.
+
+Mirror of ``utils/keypoint_detection.py:7-92`` (``get_max_preds``, ``accuracy``).  The reference
+functions take **numpy** arrays (``train1.py:464-475`` passes ``y.detach().cpu().numpy()``); these
+take numpy arrays *or* CUDA tensors.  numpy in -> numpy out (same dtypes/shapes as the reference);
+CUDA tensor in -> tensors out with no host hop for the heatmaps.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _device():
+    if not torch.cuda.is_available():
+        raise RuntimeError("no CUDA device: the B200 heatmap path has no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _as_cuda_heatmaps(x, what):
+    """-> (cuda float32 contiguous tensor, was_numpy, numpy dtype or None)"""
+    if isinstance(x, np.ndarray):
+        if x.dtype == np.float64:
+            raise TypeError(f"{what}: float64 heatmaps are not supported (argmax ties would change "
+                            "under a cast); pass float32 like train1.py/test.py do")
+        if x.dtype not in (np.float32, np.float16):
+            raise TypeError(f"{what}: unsupported dtype {x.dtype}")
+        t = torch.from_numpy(np.ascontiguousarray(x)).to(_device(), non_blocking=False)
+        return _lib.require_cuda(t, what), True, x.dtype
+    if isinstance(x, torch.Tensor):
+        return _lib.require_cuda(x.detach(), what), False, None
+    raise AssertionError("batch_heatmaps should be numpy.ndarray")  # keypoint_detection.py:12-13
+
+
+def decode(heat: torch.Tensor):
+    """CUDA tensor [B,K,H,W] -> (preds float32 [B,K,2] as (x,y), maxvals float32 [B,K,1]) on device.
+    utils/keypoint_detection.py:16-35 semantics (first index on ties, NaN wins, masked by max>0)."""
+    heat = _lib.require_cuda(heat, "decode")
+    B, K, H, W = heat.shape
+    if H * W == 0:
+        raise ValueError("attempt to get argmax of an empty sequence")
+    preds = torch.empty((B, K, 2), dtype=torch.float32, device=heat.device)
+    maxvals = torch.empty((B, K, 1), dtype=torch.float32, device=heat.device)
+    with torch.cuda.device(heat.device):
+        _lib.call("hp_argmax_decode", _lib.ptr(heat), B * K, H, W, _lib.ptr(preds), _lib.ptr(maxvals), None,
+                  _lib.stream_ptr(heat.device))
+    return preds, maxvals
+
+
+def get_max_preds(batch_heatmaps):
+    """utils/keypoint_detection.py:7-35.  numpy [B,K,H,W] -> (preds float32 [B,K,2], maxvals [B,K,1])."""
+    if not isinstance(batch_heatmaps, (np.ndarray, torch.Tensor)):
+        raise AssertionError("batch_heatmaps should be numpy.ndarray")
+    assert batch_heatmaps.ndim == 4, "batch_images should be 4-ndim"
+    heat, was_numpy, np_dtype = _as_cuda_heatmaps(batch_heatmaps, "get_max_preds")
+    preds, maxvals = decode(heat)
+    if was_numpy:
+        return preds.cpu().numpy(), maxvals.cpu().numpy().astype(np_dtype, copy=False)
+    return preds, maxvals
+
+
+def pck(output: torch.Tensor, target: torch.Tensor, thr: float = 0.5):
+    """Device-side accuracy: -> (acc_vec float64 [K+2] = acc[K], avg_acc, cnt ; pred_xy float32 [B,K,2] ;
+    counts int32 [2K] = hits, valid), all CUDA tensors, one launch, no synchronisation."""
+    output = _lib.require_cuda(output, "accuracy(output)")
+    target = _lib.require_cuda(target, "accuracy(target)")
+    if output.shape != target.shape or output.ndim != 4:
+        raise ValueError(f"accuracy: output {tuple(output.shape)} vs target {tuple(target.shape)}")
+    B, K, H, W = output.shape
+    if K > _lib.MAX_K:
+        raise ValueError(f"accuracy: K={K} exceeds HP_MAX_K={_lib.MAX_K}")
+    dev = output.device
+    pred_xy = torch.empty((B, K, 2), dtype=torch.float32, device=dev)
+    counts = torch.empty((2 * K,), dtype=torch.int32, device=dev)
+    acc = torch.empty((K + 2,), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        ws = _lib.workspace(dev, B * K, K)
+        _lib.call("hp_accuracy", _lib.ptr(output), _lib.ptr(target), B, K, H, W, C.c_double(thr), _lib.ptr(pred_xy),
+                  _lib.ptr(counts), _lib.ptr(acc), _lib.ptr(ws), _lib.stream_ptr(dev))
+    return acc, pred_xy, counts
+
+
+def accuracy(output, target, hm_type="gaussian", thr=0.5):
+    """utils/keypoint_detection.py:63-92.  -> (acc float64[K], avg_acc, cnt, pred [B,K,2]).
+
+    ``pred`` is a numpy array when ``output`` was one, else a CUDA tensor; ``acc``/``avg_acc``/``cnt``
+    are host values like the reference's (one 8*(K+2)-byte device->host read)."""
+    if hm_type != "gaussian":
+        # the reference leaves `pred` undefined in this case (keypoint_detection.py:72-78)
+        raise NameError("accuracy: only hm_type='gaussian' is defined by the reference")
+    out_t, was_numpy, _ = _as_cuda_heatmaps(output, "accuracy(output)")
+    tgt_t, _, _ = _as_cuda_heatmaps(target, "accuracy(target)")
+    acc_vec, pred_xy, _ = pck(out_t, tgt_t, thr)
+    host = acc_vec.cpu().numpy()
+    K = out_t.shape[1]
+    acc = host[:K].copy()
+    cnt = int(host[K + 1])
+    avg_acc = float(host[K]) if cnt != 0 else 0
+    pred = pred_xy.cpu().numpy() if was_numpy else pred_xy
+    return acc, avg_acc, cnt, pred

@@ -1,0 +1,129 @@
+"""``JointsMSELoss`` / ``JointsKLLoss`` with the reference's constructor and ``forward`` signatures
+(``uda/model/loss.py:27-65, 115-158``), each a single fused CUDA pass forward and backward.
+
+Gradients flow to ``output`` only (what ``train1.py:392,433,449`` needs); ``target`` and
+``target_weight`` are treated as constants, as they are everywhere in the reference's drivers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+
+def _flat_weight(w, B, K, device):
+    if w is None:
+        return None
+    w = _lib.require_cuda(w.detach(), "target_weight")
+    if w.numel() != B * K:
+        raise ValueError(f"target_weight has {w.numel()} elements, expected {B}*{K}")
+    return w.reshape(B * K)
+
+
+class _MSE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, output, target, weight, reduction):
+        out = _lib.require_cuda(output.detach(), "JointsMSELoss(output)")
+        tgt = _lib.require_cuda(target.detach(), "JointsMSELoss(target)")
+        if out.shape != tgt.shape or out.ndim != 4:
+            raise ValueError(f"JointsMSELoss: output {tuple(out.shape)} vs target {tuple(tgt.shape)}")
+        B, K, H, W = out.shape
+        dev = out.device
+        w = _flat_weight(weight, B, K, dev)
+        per_map = torch.empty((B, K), dtype=torch.float32, device=dev)
+        mean = torch.empty((), dtype=torch.float32, device=dev) if reduction == "mean" else None
+        with torch.cuda.device(dev):
+            ws = _lib.workspace(dev, B * K, K)
+            _lib.call("hp_mse_fwd", _lib.ptr(out), _lib.ptr(tgt), _lib.ptr(w), B, K, H * W, _lib.ptr(per_map),
+                      _lib.ptr(mean), _lib.ptr(ws), _lib.stream_ptr(dev))
+        ctx.save_for_backward(out, tgt, w if w is not None else torch.empty(0, device=dev))
+        ctx.has_w = w is not None
+        ctx.reduction = reduction
+        return mean if reduction == "mean" else per_map
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        out, tgt, w = ctx.saved_tensors
+        w = w if ctx.has_w else None
+        B, K, H, W = out.shape
+        dev = out.device
+        go = grad_out.detach().to(torch.float32).contiguous()
+        kind = _lib.GRAD_SCALAR if ctx.reduction == "mean" else _lib.GRAD_PER_MAP
+        grad_in = torch.empty_like(out)
+        with torch.cuda.device(dev):
+            _lib.call("hp_mse_bwd", _lib.ptr(out), _lib.ptr(tgt), _lib.ptr(w), _lib.ptr(go), kind, B, K, H * W,
+                      _lib.ptr(grad_in), _lib.stream_ptr(dev))
+        return grad_in, None, None, None
+
+
+class _KL(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, output, target, weight, reduction, epsilon):
+        out = _lib.require_cuda(output.detach(), "JointsKLLoss(output)")
+        tgt = _lib.require_cuda(target.detach(), "JointsKLLoss(target)")
+        if out.shape != tgt.shape or out.ndim != 4:
+            raise ValueError(f"JointsKLLoss: output {tuple(out.shape)} vs target {tuple(tgt.shape)}")
+        B, K, H, W = out.shape
+        dev = out.device
+        w = _flat_weight(weight, B, K, dev)
+        per_map = torch.empty((B, K), dtype=torch.float32, device=dev)
+        stats = torch.empty((B * K, 2), dtype=torch.float32, device=dev)
+        mean = torch.empty((), dtype=torch.float32, device=dev) if reduction == "mean" else None
+        per_sample = torch.empty((B,), dtype=torch.float32, device=dev) if reduction == "none" else None
+        with torch.cuda.device(dev):
+            ws = _lib.workspace(dev, B * K, K)
+            _lib.call("hp_kl_fwd", _lib.ptr(out), _lib.ptr(tgt), _lib.ptr(w), C.c_float(epsilon), B, K, H * W,
+                      _lib.ptr(per_map), _lib.ptr(per_sample), _lib.ptr(mean), _lib.ptr(stats), _lib.ptr(ws),
+                      _lib.stream_ptr(dev))
+        ctx.save_for_backward(out, tgt, w if w is not None else torch.empty(0, device=dev), stats)
+        ctx.has_w = w is not None
+        ctx.reduction = reduction
+        ctx.epsilon = float(epsilon)
+        return mean if reduction == "mean" else per_sample
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        out, tgt, w, stats = ctx.saved_tensors
+        w = w if ctx.has_w else None
+        B, K, H, W = out.shape
+        dev = out.device
+        go = grad_out.detach().to(torch.float32).contiguous()
+        kind = _lib.GRAD_SCALAR if ctx.reduction == "mean" else _lib.GRAD_PER_SAMPLE
+        grad_in = torch.empty_like(out)
+        with torch.cuda.device(dev):
+            _lib.call("hp_kl_bwd", _lib.ptr(out), _lib.ptr(tgt), _lib.ptr(w), C.c_float(ctx.epsilon), _lib.ptr(stats),
+                      _lib.ptr(go), kind, B, K, H * W, _lib.ptr(grad_in), _lib.stream_ptr(dev))
+        return grad_in, None, None, None, None
+
+
+class JointsMSELoss(nn.Module):
+    """uda/model/loss.py:27-65.  ``0.5*(pred-gt)^2*w``; ``'mean'`` over all elements (zero-weight joints
+    stay in the denominator), ``'none'`` -> mean over HW -> ``[B,K]``."""
+
+    def __init__(self, reduction="mean"):
+        super().__init__()
+        self.reduction = reduction
+
+    def forward(self, output, target, target_weight=None):
+        if self.reduction not in ("mean", "none"):
+            return None                       # the reference falls off the if/elif (loss.py:62-65)
+        return _MSE.apply(output, target, target_weight, self.reduction)
+
+
+class JointsKLLoss(nn.Module):
+    """uda/model/loss.py:115-158.  KL(q || softmax(pred)) per map, q = (gt+eps)/sum(gt+eps);
+    ``'mean'`` over B*K, ``'none'`` -> mean over K -> ``[B]`` (the reference docstring says [B,K];
+    its code returns [B], and so does this)."""
+
+    def __init__(self, reduction="mean", epsilon=0.0):
+        super().__init__()
+        self.reduction = reduction
+        self.epsilon = epsilon
+
+    def forward(self, output, target, target_weight=None):
+        if self.reduction not in ("mean", "none"):
+            return None
+        return _KL.apply(output, target, target_weight, self.reduction, float(self.epsilon))

@@ -1,0 +1,213 @@
+"""The fused hot path as one object: Gaussian target generation + JointsMSELoss + JointsKLLoss +
+decode + PCK in a single pass over the prediction tensor (BASELINE.json metric), and the multiscale
+fuse + decode + PCK evaluation of configs[3].
+
+What it replaces per batch in the reference (``validate()``, ``train1.py:495-536``, plus the
+dataset-side ``generate_target``)::
+
+    target, weight = zip(*[generate_target(j, v, (W,H), sigma, image) for each sample])   # util.py:9-68
+    mse  = JointsMSELoss()(y, target, weight)                                            # loss.py:55-65
+    kl   = JointsKLLoss(epsilon=eps)(y, target, weight)                                  # loss.py:145-158
+    acc, avg_acc, cnt, pred = accuracy(y.cpu().numpy(), target.cpu().numpy())            # keypoint_detection.py:63-92
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import dist as hpdist
+
+_LOSS_BITS = {"mse": _lib.LOSS_MSE, "kl": _lib.LOSS_KL}
+
+
+@dataclass
+class PipelineResult:
+    """Device-resident outputs; ``host()`` does the one small device->host read."""
+    result: torch.Tensor      # float64 [4+K] = mse, kl, avg_acc, cnt, acc[K]
+    partial: torch.Tensor     # float64 [4+2K] = mse_sum, kl_sum, n_maps, n_elems, hits[K], valid[K]
+    pred_xy: torch.Tensor     # float32 [B,K,2]
+    maxvals: torch.Tensor     # float32 [B,K,1]
+    weight: torch.Tensor      # float32 [B,K,1]  (target_weight of generate_target)
+    K: int
+
+    def host(self):
+        r = self.result.cpu().numpy() if isinstance(self.result, torch.Tensor) else np.asarray(self.result)
+        K = self.K
+        return dict(mse=float(r[0]), kl=float(r[1]), avg_acc=float(r[2]) if int(r[3]) else 0, cnt=int(r[3]),
+                    acc=r[4:4 + K].copy())
+
+
+class HeatmapPipeline:
+    """gen + loss + decode + PCK, one kernel launch per batch (one more tiny one after the
+    all-reduce when the batch is sharded over several GPUs)."""
+
+    def __init__(self, num_keypoints=21, heatmap_size=(64, 64), image_size=(256, 256), sigma=2, kl_epsilon=0.0,
+                 thr=0.5, losses=("mse", "kl"), device=None, group=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("no CUDA device: the B200 heatmap path has no CPU fallback")
+        self.K = int(num_keypoints)
+        if self.K > _lib.MAX_K:
+            raise ValueError(f"num_keypoints={self.K} exceeds HP_MAX_K={_lib.MAX_K}")
+        self.W, self.H = int(heatmap_size[0]), int(heatmap_size[1])
+        self.sigma = sigma
+        self.tmp = _lib.integer_tmp(sigma * 3)
+        stride = np.array(image_size) / np.array(heatmap_size)          # util.py:36
+        self.stride = (float(stride[0]), float(stride[1]))
+        self.kl_epsilon = float(kl_epsilon)
+        self.thr = float(thr)
+        self.loss_mask = 0
+        for name in losses:
+            self.loss_mask |= _LOSS_BITS[name]
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.group = group
+        with torch.cuda.device(self.device):
+            self.tab = _lib.gaussian_table(sigma, self.tmp, self.device)
+        self._host_state = None
+        _lib.load()
+
+    # ------------------------------------------------------------------------------ device path
+    def __call__(self, pred, joints, vis, out=None) -> PipelineResult:
+        """pred float32 [B,K,H,W], joints float64 [B,K,2] (image px), vis float32 [B,K,1]|[B,K]: CUDA
+        tensors of THIS rank's slice of the batch.  Asynchronous on the current stream."""
+        pred = _lib.require_cuda(pred, "HeatmapPipeline(pred)")
+        joints = _lib.require_cuda(joints, "HeatmapPipeline(joints)", torch.float64)
+        vis = _lib.require_cuda(vis, "HeatmapPipeline(vis)")
+        B, K, H, W = pred.shape
+        if (K, H, W) != (self.K, self.H, self.W):
+            raise ValueError(f"pred is {tuple(pred.shape)}, pipeline was built for K={self.K} H={self.H} W={self.W}")
+        if joints.numel() != 2 * B * K or vis.numel() != B * K:
+            raise ValueError("joints must be [B,K,2] and vis [B,K,1]")
+        dev = pred.device
+        if out is None:
+            out = self.alloc_outputs(B, dev)
+        sharded = hpdist.is_distributed(self.group)
+        with torch.cuda.device(dev):
+            ws = _lib.workspace(dev, B * K, K)
+            _lib.call("hp_pipeline_fused", _lib.ptr(pred), _lib.ptr(joints), _lib.ptr(vis), B, K, H, W,
+                      C.c_double(self.stride[0]), C.c_double(self.stride[1]), self.tmp, _lib.ptr(self.tab),
+                      C.c_float(self.kl_epsilon), C.c_double(self.thr), self.loss_mask, _lib.ptr(out.pred_xy),
+                      _lib.ptr(out.maxvals), _lib.ptr(out.weight), _lib.ptr(out.partial), 0,
+                      None if sharded else _lib.ptr(out.result), _lib.ptr(ws), _lib.stream_ptr(dev))
+            if sharded:
+                hpdist.allreduce_partial(out.partial, self.group)      # the path's only collective
+                _lib.call("hp_pipeline_finalize", _lib.ptr(out.partial), K, _lib.ptr(out.result), _lib.stream_ptr(dev))
+        return out
+
+    def alloc_outputs(self, B, device=None) -> PipelineResult:
+        dev = device or self.device
+        K = self.K
+        return PipelineResult(
+            result=torch.empty((4 + K,), dtype=torch.float64, device=dev),
+            partial=torch.empty((4 + 2 * K,), dtype=torch.float64, device=dev),
+            pred_xy=torch.empty((B, K, 2), dtype=torch.float32, device=dev),
+            maxvals=torch.empty((B, K, 1), dtype=torch.float32, device=dev),
+            weight=torch.empty((B, K, 1), dtype=torch.float32, device=dev), K=K)
+
+    # -------------------------------------------------------------------------------- host path
+    def run_host(self, pred, joints, vis, slab=64, want_pred_xy=True):
+        """End-to-end form for HOST inputs (what a caller holding numpy / CPU tensors uses):
+        pinned host buffers -> slabbed H2D copies overlapped with the kernel -> one small D2H.
+        ``pred`` float32 [B,K,H,W], ``joints`` float64 [B,K,2], ``vis`` float32 [B,K,1] (numpy arrays or
+        CPU tensors; pinned tensors are used in place, anything else is staged through pinned memory).
+        Returns ``dict(mse, kl, avg_acc, cnt, acc[K], pred_xy[B,K,2] numpy)`` after synchronising."""
+        hp, hj, hv = self._pinned(pred, torch.float32), self._pinned(joints, torch.float64), self._pinned(vis, torch.float32)
+        B, K, H, W = hp.shape
+        if (K, H, W) != (self.K, self.H, self.W):
+            raise ValueError(f"pred is {tuple(hp.shape)}, pipeline was built for K={self.K} H={self.H} W={self.W}")
+        slab = max(1, min(int(slab), B))
+        st = self._host_buffers(B, slab)
+        dev = self.device
+        with torch.cuda.device(dev):
+            ws = _lib.workspace(dev, B * K, K)
+            _lib.call("hp_pipeline_fused_host", _lib.ptr(hp), _lib.ptr(hj), _lib.ptr(hv), B, K, H, W,
+                      C.c_double(self.stride[0]), C.c_double(self.stride[1]), self.tmp, _lib.ptr(self.tab),
+                      C.c_float(self.kl_epsilon), C.c_double(self.thr), self.loss_mask, slab, _lib.ptr(st["d_pred"]),
+                      _lib.ptr(st["d_joints"]), _lib.ptr(st["d_vis"]), _lib.ptr(st["d_xy"]), _lib.ptr(st["d_max"]),
+                      _lib.ptr(st["d_w"]), _lib.ptr(st["d_partial"]), _lib.ptr(st["d_result"]), _lib.ptr(ws),
+                      _lib.ptr(st["h_xy"]) if want_pred_xy else None, _lib.ptr(st["h_result"]),
+                      _lib.stream_ptr(dev), C.c_void_p(st["copy_stream"].cuda_stream))
+        r = st["h_result"].numpy()
+        out = dict(mse=float(r[0]), kl=float(r[1]), avg_acc=float(r[2]) if int(r[3]) else 0, cnt=int(r[3]),
+                   acc=r[4:4 + K].copy())
+        if want_pred_xy:
+            out["pred_xy"] = st["h_xy"][:B].numpy().copy()
+        return out
+
+    def host_bytes_per_call(self, B):
+        """(h2d, d2h) bytes moved by :meth:`run_host` for a batch of B."""
+        K = self.K
+        h2d = B * K * self.H * self.W * 4 + B * K * 2 * 8 + B * K * 4
+        d2h = (4 + K) * 8 + B * K * 2 * 4
+        return h2d, d2h
+
+    @staticmethod
+    def _pinned(x, dtype):
+        t = torch.as_tensor(x)
+        if t.is_cuda:
+            raise RuntimeError("run_host takes host arrays; call the pipeline object directly for CUDA tensors")
+        t = t.to(dtype).contiguous()
+        return t if t.is_pinned() else t.pin_memory()
+
+    def _host_buffers(self, B, slab):
+        st = self._host_state
+        if st is None or st["B"] < B or st["slab"] != slab:
+            dev, K = self.device, self.K
+            st = dict(
+                B=B, slab=slab,
+                d_pred=torch.empty((2 * slab, K, self.H, self.W), dtype=torch.float32, device=dev),
+                d_joints=torch.empty((B, K, 2), dtype=torch.float64, device=dev),
+                d_vis=torch.empty((B, K), dtype=torch.float32, device=dev),
+                d_xy=torch.empty((B, K, 2), dtype=torch.float32, device=dev),
+                d_max=torch.empty((B, K), dtype=torch.float32, device=dev),
+                d_w=torch.empty((B, K), dtype=torch.float32, device=dev),
+                d_partial=torch.empty((4 + 2 * K,), dtype=torch.float64, device=dev),
+                d_result=torch.empty((4 + K,), dtype=torch.float64, device=dev),
+                h_xy=torch.empty((B, K, 2), dtype=torch.float32).pin_memory(),
+                h_result=torch.empty((4 + K,), dtype=torch.float64).pin_memory(),
+                copy_stream=torch.cuda.Stream(device=dev),
+            )
+            self._host_state = st
+        return st
+
+
+class MultiscaleEval:
+    """BASELINE.json configs[3]: fuse three resolutions (``0.5*up(lo) + up(mid) + hi``, the rule of
+    train1.py:410-424 scaled up), decode the fused map and score PCK against label coordinates - the
+    fused map lives in registers only.  Batch-sharded like :class:`HeatmapPipeline`."""
+
+    def __init__(self, num_keypoints=21, thr=0.5, a_lo=0.5, a_mid=1.0, a_hi=1.0, group=None):
+        self.K = int(num_keypoints)
+        self.thr = float(thr)
+        self.coef = (float(a_lo), float(a_mid), float(a_hi))
+        self.group = group
+        _lib.load()
+
+    def __call__(self, lo, mid, hi, target_xy):
+        """lo/mid/hi float32 [B,K,h,w] CUDA tensors (hi may be None -> output size = 2x mid); target_xy
+        float32 [B,K,2].  -> (acc_vec float64 [K+2] = acc[K], avg_acc, cnt ; pred_xy [B,K,2] ; counts int32 [2K])."""
+        lo = _lib.require_cuda(lo, "MultiscaleEval(lo)")
+        mid = _lib.require_cuda(mid, "MultiscaleEval(mid)")
+        hi = _lib.require_cuda(hi, "MultiscaleEval(hi)")
+        tgt = _lib.require_cuda(target_xy, "MultiscaleEval(target_xy)")
+        B, K, H, W = hi.shape
+        dev = hi.device
+        pred_xy = torch.empty((B, K, 2), dtype=torch.float32, device=dev)
+        maxvals = torch.empty((B, K, 1), dtype=torch.float32, device=dev)
+        counts = torch.empty((2 * K,), dtype=torch.int32, device=dev)
+        acc = torch.empty((K + 2,), dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            ws = _lib.workspace(dev, B * K, K)
+            _lib.call("hp_fuse_decode_pck", _lib.ptr(lo), lo.shape[2], lo.shape[3], C.c_float(self.coef[0]),
+                      _lib.ptr(mid), mid.shape[2], mid.shape[3], C.c_float(self.coef[1]), _lib.ptr(hi),
+                      C.c_float(self.coef[2]), _lib.ptr(tgt), B, K, H, W, C.c_double(self.thr), _lib.ptr(pred_xy),
+                      _lib.ptr(maxvals), _lib.ptr(counts), _lib.ptr(acc), _lib.ptr(ws), _lib.stream_ptr(dev))
+            if hpdist.is_distributed(self.group):
+                c64 = counts.to(torch.float64)
+                hpdist.allreduce_partial(c64, self.group)
+                counts = c64.to(torch.int32)
+                _lib.call("hp_pck_finalize", _lib.ptr(counts), K, _lib.ptr(acc), _lib.stream_ptr(dev))
+        return acc, pred_xy, counts

@@ -1,0 +1,250 @@
+"""Pseudo-label generators and regression-disparity modules with the reference's signatures.
+
+=============================  ==========================================  ===================
+class                          reference                                   pseudo-label grid
+=============================  ==========================================  ===================
+``PseudoLabelGenerator``       uda/model/regda_4.py:17-86                  H x W of ``y``
+``PseudoLabelGenerator02``     uda/model/regda_7.py:3044-3114 (copy)       H x W of ``y``
+``PseudoLabelGenerator03``     uda/model/regda_7.py:3118-3201              32 x 32, centre = pred/2, 9x9 patch
+``PseudoLabelGenerator01``     uda/model/regda_7.py:2956-3039              16 x 16, centre = pred/4, 7x7 patch
+``RegressionDisparity``        uda/model/regda_4.py:89-143                 gf = clip(sum_{j!=k} gt_j)
+``RegressionDisparityx1``      uda/model/regda_7.py:3206-3268              gf = clip(1 - 10 gt)
+``RegressionDisparityx5``      uda/model/regda_7.py:3485-3561              + fused map, per-map max normalise
+``RegressionDisparityx6``      uda/model/regda_7.py:3564-3632              clip(sum gt) based, + fused map, normalise
+=============================  ==========================================  ===================
+
+Unlike the reference nothing leaves the GPU: ``y`` is decoded by a CUDA kernel, and when the
+criterion is this package's ``JointsKLLoss`` (what ``train1.py:135-137`` wires) the whole disparity
+term - pseudo-label, ground-false recipe, normalisation, KL - is one fused kernel that never writes
+gt / gf.  ``.ground_truth`` / ``.ground_false`` stay available (materialised on first access).
+Any other criterion gets materialised maps and is called as in the reference.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .loss import JointsKLLoss
+
+_VARIANT_CODE = {"base": _lib.RD_BASE, "x1": _lib.RD_X1, "x5": _lib.RD_X5, "x6": _lib.RD_X6}
+
+
+class _PLGBase(nn.Module):
+    #: (output side or None, shift applied to the decoded coordinate, tmp_size / sigma, C-ABI kind)
+    _spec = (None, 0, 3, _lib.PLG_BASE)
+
+    def __init__(self, num_keypoints, height=64, width=64, sigma=2):
+        super().__init__()
+        self.num_keypoints = num_keypoints
+        self.height = height
+        self.width = width
+        self.sigma = sigma
+        # regda_4.py:74 - kept for API parity; the kernels use sum-minus-self instead of the sgemm
+        self.false_matrix = 1.0 - np.eye(num_keypoints, dtype=np.float32)
+
+    # -- geometry --------------------------------------------------------------------------
+    def grid(self, H, W):
+        side, shift, tmp_factor, kind = self._spec
+        oh, ow = (H, W) if side is None else (side, side)
+        return oh, ow, shift, _lib.integer_tmp(self.sigma * tmp_factor), kind
+
+    def _check_input(self, y):
+        y = _lib.require_cuda(y.detach(), type(self).__name__ + "(y)")
+        if y.ndim != 4:
+            raise ValueError("y must be [B,K,H,W]")
+        B, K, H, W = y.shape
+        if K > _lib.MAX_K:
+            raise ValueError(f"K={K} exceeds HP_MAX_K={_lib.MAX_K}")
+        oh, ow, shift, tmp, kind = self.grid(H, W)
+        if ((H - 1) >> shift) >= oh or ((W - 1) >> shift) >= ow:
+            # the reference indexes its look-up table out of bounds here (IndexError)
+            raise IndexError(f"decoded coordinates of a {H}x{W} map do not fit the {oh}x{ow} pseudo-label grid")
+        return y, (B, K, H, W), (oh, ow, shift, tmp, kind)
+
+    def forward(self, y):
+        """-> (ground_truth, ground_false) float32 [B,K,oh,ow] on ``y.device``."""
+        y, (B, K, H, W), (oh, ow, shift, tmp, kind) = self._check_input(y)
+        dev = y.device
+        gt = torch.empty((B, K, oh, ow), dtype=torch.float32, device=dev)
+        gf = torch.empty_like(gt)
+        centres = torch.empty((B * K, 2), dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            tab = _lib.gaussian_table(self.sigma, tmp, dev)
+            _lib.call("hp_pseudo_label", _lib.ptr(y), B, K, H, W, kind, oh, ow, shift, tmp, _lib.ptr(tab), _lib.ptr(gt),
+                      _lib.ptr(gf), _lib.ptr(centres), _lib.stream_ptr(dev))
+        return gt, gf
+
+
+class PseudoLabelGenerator(_PLGBase):
+    _spec = (None, 0, 3, _lib.PLG_BASE)
+
+
+class PseudoLabelGenerator02(_PLGBase):
+    _spec = (None, 0, 3, _lib.PLG_BASE)
+
+
+class PseudoLabelGenerator03(_PLGBase):
+    _spec = (32, 1, 2, _lib.PLG_ONE_MINUS)
+
+    def __init__(self, num_keypoints, height=32, width=32, sigma=2):
+        super().__init__(num_keypoints, height, width, sigma)
+
+
+class PseudoLabelGenerator01(_PLGBase):
+    _spec = (16, 2, 1.5, _lib.PLG_ONE_MINUS)
+
+    def __init__(self, num_keypoints, height=16, width=16, sigma=2):
+        super().__init__(num_keypoints, height, width, sigma)
+
+
+# ------------------------------------------------------------------------------------------
+
+class _RegDisp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y_adv, y, fused, weight, variant, mode, epsilon, reduction, plg, holder):
+        yd, (B, K, H, W), (oh, ow, shift, tmp, _) = plg._check_input(y)
+        adv = _lib.require_cuda(y_adv.detach(), "RegressionDisparity(y_adv)")
+        if tuple(adv.shape) != (B, K, oh, ow):
+            raise ValueError(f"y_adv is {tuple(adv.shape)}, the pseudo-label grid is {(B, K, oh, ow)}")
+        dev = adv.device
+        fz = None
+        if fused is not None:
+            fz = _lib.require_cuda(fused.detach(), "RegressionDisparity(y_adv2)")
+            if tuple(fz.shape) != (B, K, oh, ow):
+                raise ValueError(f"y_adv2 is {tuple(fz.shape)}, expected {(B, K, oh, ow)}")
+        w = None
+        if weight is not None:
+            w = _lib.require_cuda(weight.detach(), "weight").reshape(-1)
+            if w.numel() != B * K:
+                raise ValueError(f"weight has {w.numel()} elements, expected {B}*{K}")
+        per_map = torch.empty((B, K), dtype=torch.float32, device=dev)
+        stats = torch.empty((B * K, 3), dtype=torch.float32, device=dev)
+        centres = torch.empty((B * K, 2), dtype=torch.int32, device=dev)
+        mean = torch.empty((), dtype=torch.float32, device=dev) if reduction == "mean" else None
+        per_sample = torch.empty((B,), dtype=torch.float32, device=dev) if reduction == "none" else None
+        with torch.cuda.device(dev):
+            tab = _lib.gaussian_table(plg.sigma, tmp, dev)
+            ws = _lib.workspace(dev, B * K, K)
+            _lib.call("hp_regdisp_fwd", _lib.ptr(yd), _lib.ptr(adv), _lib.ptr(fz), _lib.ptr(w), variant, mode,
+                      C.c_float(epsilon), B, K, H, W, oh, ow, shift, tmp, _lib.ptr(tab), _lib.ptr(per_map),
+                      _lib.ptr(per_sample), _lib.ptr(mean), _lib.ptr(stats), _lib.ptr(centres), _lib.ptr(ws),
+                      _lib.stream_ptr(dev))
+        ctx.save_for_backward(adv, centres, stats, tab)
+        ctx.fz, ctx.w = fz, w
+        ctx.cfg = (variant, mode, float(epsilon), reduction, B, K, oh, ow, tmp)
+        holder._remember(variant, fz, centres, tab, (B, K, oh, ow, tmp))
+        return mean if reduction == "mean" else per_sample
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        adv, centres, stats, tab = ctx.saved_tensors
+        variant, mode, eps, reduction, B, K, oh, ow, tmp = ctx.cfg
+        dev = adv.device
+        go = grad_out.detach().to(torch.float32).contiguous()
+        kind = _lib.GRAD_SCALAR if reduction == "mean" else _lib.GRAD_PER_SAMPLE
+        grad_in = torch.empty_like(adv)
+        with torch.cuda.device(dev):
+            _lib.call("hp_regdisp_bwd", _lib.ptr(adv), _lib.ptr(ctx.fz), _lib.ptr(ctx.w), variant, mode, C.c_float(eps),
+                      B, K, oh, ow, tmp, _lib.ptr(tab), _lib.ptr(centres), _lib.ptr(stats), _lib.ptr(go), kind,
+                      _lib.ptr(grad_in), _lib.stream_ptr(dev))
+        return (grad_in,) + (None,) * 9
+
+
+class _RDBase(nn.Module):
+    _variant = "base"
+
+    def __init__(self, pseudo_label_generator, criterion: nn.Module):
+        super().__init__()
+        self.criterion = criterion
+        self.pseudo_label_generator = pseudo_label_generator
+        self._lazy = None
+        self._gt = None
+        self._gf = None
+
+    # -- lazily materialised attributes the reference sets eagerly (regda_4.py:136-137) ------
+    def _remember(self, variant, fused, centres, tab, dims):
+        self._lazy = (variant, fused, centres, tab, dims)
+        self._gt = self._gf = None
+
+    def _materialise(self):
+        if self._gt is None:
+            if self._lazy is None:
+                raise AttributeError("ground_truth / ground_false exist only after a forward call")
+            variant, fused, centres, tab, (B, K, oh, ow, tmp) = self._lazy
+            dev = centres.device
+            gt = torch.empty((B, K, oh, ow), dtype=torch.float32, device=dev)
+            gf = torch.empty_like(gt)
+            with torch.cuda.device(dev):
+                _lib.call("hp_regdisp_materialize", _lib.ptr(fused), variant, B, K, oh, ow, tmp, _lib.ptr(tab),
+                          _lib.ptr(centres), _lib.ptr(gt), _lib.ptr(gf), _lib.stream_ptr(dev))
+            self._gt, self._gf = gt, gf
+        return self._gt, self._gf
+
+    @property
+    def ground_truth(self):
+        return self._materialise()[0]
+
+    @property
+    def ground_false(self):
+        return self._materialise()[1]
+
+    # -----------------------------------------------------------------------------------------
+    def _run(self, y, y_adv, y_adv2, weight, mode):
+        assert mode in ["min", "max"]
+        variant = _VARIANT_CODE[self._variant]
+        plg = self.pseudo_label_generator
+        if not isinstance(plg, _PLGBase):
+            raise TypeError("pseudo_label_generator must be one of this package's PseudoLabelGenerator classes")
+        mode_code = _lib.MODE_MIN if mode == "min" else _lib.MODE_MAX
+        crit = self.criterion
+        if isinstance(crit, JointsKLLoss) and crit.reduction in ("mean", "none"):
+            return _RegDisp.apply(y_adv, y, y_adv2, weight, variant, mode_code, float(crit.epsilon), crit.reduction,
+                                  plg, self)
+        # foreign criterion: materialise the maps on the GPU and call it like the reference does
+        from .keypoint_detection import decode
+        yd, (B, K, H, W), (oh, ow, shift, tmp, _) = plg._check_input(y)
+        dev = yd.device
+        fz = None if y_adv2 is None else _lib.require_cuda(y_adv2.detach(), "y_adv2")
+        preds, _ = decode(yd)
+        centres = (preds.reshape(-1, 2).to(torch.int32) >> shift).contiguous()
+        with torch.cuda.device(dev):
+            tab = _lib.gaussian_table(plg.sigma, tmp, dev)
+        self._remember(variant, fz, centres, tab, (B, K, oh, ow, tmp))
+        gt, gf = self._materialise()
+        return crit(y_adv, gt if mode == "min" else gf, weight)
+
+
+class RegressionDisparity(_RDBase):
+    """uda/model/regda_4.py:89-143: ``forward(y, y_adv, weight=None, mode='min')``."""
+    _variant = "base"
+
+    def forward(self, y, y_adv, weight=None, mode="min"):
+        return self._run(y, y_adv, None, weight, mode)
+
+
+class RegressionDisparityx1(_RDBase):
+    """uda/model/regda_7.py:3206-3268 (16x16 head): ``forward(y, y_adv, weight=None, mode='min')``."""
+    _variant = "x1"
+
+    def forward(self, y, y_adv, weight=None, mode="min"):
+        return self._run(y, y_adv, None, weight, mode)
+
+
+class RegressionDisparityx5(_RDBase):
+    """uda/model/regda_7.py:3485-3561 (32x32 head): ``forward(y, y_adv, y_adv2, weight=None, mode='min')``."""
+    _variant = "x5"
+
+    def forward(self, y, y_adv, y_adv2, weight=None, mode="min"):
+        return self._run(y, y_adv, y_adv2, weight, mode)
+
+
+class RegressionDisparityx6(_RDBase):
+    """uda/model/regda_7.py:3564-3632 (64x64 head): ``forward(y, y_adv, y_adv2, weight=None, mode='min')``."""
+    _variant = "x6"
+
+    def forward(self, y, y_adv, y_adv2, weight=None, mode="min"):
+        return self._run(y, y_adv, y_adv2, weight, mode)

@@ -1,0 +1,197 @@
+/*
+ * hp_b200.h - C ABI of libhp_b200.so: the B200 (sm_100a) heatmap keypoint hot path.
+ *
+ * This is the drop-in boundary.  The reference has no FFI - its
+ * "operator API" is a set of Python callables - so each entry point below names the
+ * reference function (file:line, relative to the reference tree) whose arithmetic it
+ * replaces; the Python layer in domain-adaptative-hand-pose-estimation_b200/ binds these
+ * through ctypes and re-exposes the reference's own signatures.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name starts with h_ (pinned host memory);
+ *   - heatmaps are contiguous NCHW float32: map (b,k) starts at ((b*K+k)*H*W);
+ *   - the caller owns all memory, including workspaces; nothing is retained after a call;
+ *   - every launch is asynchronous on the caller's stream (hp_stream_t == cudaStream_t);
+ *     only the *_host entry points synchronise (they return host-visible results);
+ *   - return 0 on success, <0 for an argument error (HP_ERR_*), >0 for a cudaError_t;
+ *     hp_last_error() returns a thread-local description; no C++ exception crosses;
+ *   - a workspace must be zero-filled once before its first use; calls leave it zeroed.
+ *   - Gaussian values come from a caller-supplied table tab[d2] = exp(-d2 / (2 sigma^2)),
+ *     d2 = 0 .. 2*tmp*tmp (float32, device memory).  The host builds it with the reference's
+ *     own numpy expression (uda/dataset/util.py:49-54) so generated maps are bit-equal to the
+ *     reference on the same host; `tmp` is the integer half-width of the pasted patch.
+ */
+#ifndef HP_B200_H
+#define HP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* hp_stream_t; /* cudaStream_t */
+
+#if defined(__GNUC__)
+#define HP_API __attribute__((visibility("default")))
+#else
+#define HP_API
+#endif
+
+#define HP_OK             0
+#define HP_ERR_NULL      -1 /* required pointer is NULL */
+#define HP_ERR_SHAPE     -2 /* non-positive or unsupported extent */
+#define HP_ERR_ALIGN     -3 /* pointer not aligned for its element type */
+#define HP_ERR_ARG       -4 /* bad enum / scalar argument */
+
+#define HP_MAX_K        64  /* joints per sample supported by the per-sample kernels */
+
+/* loss selection bits for hp_pipeline_fused */
+#define HP_LOSS_MSE      1
+#define HP_LOSS_KL       2
+
+/* pseudo-label variants (centre = decoded coordinate >> shift, on an oh x ow map) */
+#define HP_PLG_BASE      0 /* PseudoLabelGenerator   uda/model/regda_4.py:17-86 : gf = clip(sum_{j!=k} gt_j) */
+#define HP_PLG_ONE_MINUS 1 /* PseudoLabelGenerator01/03 uda/model/regda_7.py:2956-3201 : gf = clip(1-10 gt) */
+
+/* regression-disparity variants */
+#define HP_RD_BASE       0 /* RegressionDisparity    uda/model/regda_4.py:89-143  */
+#define HP_RD_X1         1 /* RegressionDisparityx1  uda/model/regda_7.py:3206-3268 */
+#define HP_RD_X5         2 /* RegressionDisparityx5  uda/model/regda_7.py:3485-3561 */
+#define HP_RD_X6         3 /* RegressionDisparityx6  uda/model/regda_7.py:3564-3632 */
+#define HP_MODE_MIN      0
+#define HP_MODE_MAX      1
+
+/* gradient layouts accepted by the backward kernels */
+#define HP_GRAD_SCALAR     0 /* upstream gradient of the 'mean' scalar                  */
+#define HP_GRAD_PER_MAP    1 /* upstream gradient [B*K] (MSE 'none')                     */
+#define HP_GRAD_PER_SAMPLE 2 /* upstream gradient [B]   (KL  'none' = mean over joints)  */
+
+/* ---- library ------------------------------------------------------------------------ */
+int         hp_version(void);            /* 10000*major + 100*minor + patch */
+const char* hp_last_error(void);
+int         hp_device_sm_count(void);    /* SMs of the current device (148 on B200), <0 on error */
+
+/* bytes of zero-initialised workspace every op below accepts (one size fits all ops) */
+size_t      hp_workspace_bytes(int n_maps, int K);
+
+/* ---- a1: decode.  utils/keypoint_detection.py:7-35 (get_max_preds) ------------------- */
+/* preds [n_maps,2] = (x,y) zeroed where max <= 0 ; maxvals [n_maps] ; first index wins ties,
+ * NaN counts as the maximum.  idx (nullable) receives the flat int32 argmax. */
+int hp_argmax_decode(const float* heat, int n_maps, int H, int W,
+                     float* preds, float* maxvals, int32_t* idx, hp_stream_t stream);
+
+/* ---- a2: PCK.  utils/keypoint_detection.py:38-92 (calc_dists, dist_acc, accuracy) ---- */
+/* From decoded coordinates: counts[0..K) += hits, counts[K..2K) += valid (int32). */
+int hp_pck_accumulate(const float* pred_xy, const float* tgt_xy, int B, int K, int H, int W,
+                      double thr, int32_t* counts, hp_stream_t stream);
+/* acc_out[0..K) = hits/valid or -1 ; acc_out[K] = avg_acc ; acc_out[K+1] = cnt  (float64). */
+int hp_pck_finalize(const int32_t* counts, int K, double* acc_out, hp_stream_t stream);
+/* accuracy(output, target): decode both tensors, count, finalise - one launch.
+ * pred_xy [B*K,2] float32 ; counts [2K] int32 (overwritten) ; acc_out [K+2] float64. */
+int hp_accuracy(const float* output, const float* target, int B, int K, int H, int W, double thr,
+                float* pred_xy, int32_t* counts, double* acc_out, void* workspace,
+                hp_stream_t stream);
+
+/* ---- a5: target generation.  uda/dataset/util.py:9-68 (generate_target), batched ------ */
+/* joints float64 [B*K,2] image px ; vis float32 [B*K] ; stride = image_size / heatmap_size
+ * (float64, computed by the host exactly as util.py:36) ; target [B*K,H,W] ; weight [B*K]. */
+int hp_gaussian_target(const double* joints, const float* vis, int n_maps, int H, int W,
+                       double stride_x, double stride_y, int tmp, const float* tab,
+                       float* target, float* weight, hp_stream_t stream);
+
+/* ---- a3: JointsMSELoss.  uda/model/loss.py:27-65 -------------------------------------- */
+/* per_map [B*K] = mean_hw(0.5 w (p-t)^2) ('none') ; mean (nullable) = mean over all elements. */
+int hp_mse_fwd(const float* output, const float* target, const float* weight /*nullable [B*K]*/,
+               int B, int K, int HW, float* per_map, float* mean, void* workspace,
+               hp_stream_t stream);
+int hp_mse_bwd(const float* output, const float* target, const float* weight,
+               const float* grad_out, int grad_kind, int B, int K, int HW, float* grad_in,
+               hp_stream_t stream);
+
+/* ---- a4: JointsKLLoss.  uda/model/loss.py:115-158 ------------------------------------- */
+/* per_map [B*K] = w * KL(q || softmax(p)) ; per_sample (nullable) [B] = mean over K ('none');
+ * mean (nullable) scalar ; stats [B*K,2] = (logsumexp, sum(t+eps)) saved for the backward. */
+int hp_kl_fwd(const float* output, const float* target, const float* weight, float epsilon,
+              int B, int K, int HW, float* per_map, float* per_sample, float* mean, float* stats,
+              void* workspace, hp_stream_t stream);
+int hp_kl_bwd(const float* output, const float* target, const float* weight, float epsilon,
+              const float* stats, const float* grad_out, int grad_kind, int B, int K, int HW,
+              float* grad_in, hp_stream_t stream);
+
+/* ---- a6/a7: pseudo labels, materialised.  regda_4.py:76-86 ; regda_7.py:3026-3039, 3188-3201 */
+/* y [B,K,H,W] -> gt, gf [B,K,oh,ow] ; centre = (decode(y) >> shift) ; centres (nullable) [B*K,2] int32 */
+int hp_pseudo_label(const float* y, int B, int K, int H, int W, int kind, int oh, int ow, int shift,
+                    int tmp, const float* tab, float* gt, float* gf, int32_t* centres,
+                    hp_stream_t stream);
+
+/* ---- a8-a11: regression disparity, fused (no gt/gf materialised).  regda_4.py:129-143 ;
+ *      regda_7.py:3250-3268, 3529-3561, 3609-3632 ; criterion = JointsKLLoss(epsilon) ------ */
+/* y [B,K,H,W] (decoded, no gradient) ; y_adv [B,K,oh,ow] ; fused (nullable) [B,K,oh,ow] is the
+ * y_adv2 argument of x5/x6 ; outputs as hp_kl_fwd plus centres [B*K,2] int32 and
+ * stats [B*K,3] = (logsumexp, sum(target+eps), per-map max M used by the x5/x6 normalisation). */
+int hp_regdisp_fwd(const float* y, const float* y_adv, const float* fused, const float* weight,
+                   int variant, int mode, float epsilon, int B, int K, int H, int W, int oh, int ow,
+                   int shift, int tmp, const float* tab, float* per_map, float* per_sample,
+                   float* mean, float* stats, int32_t* centres, void* workspace,
+                   hp_stream_t stream);
+int hp_regdisp_bwd(const float* y_adv, const float* fused, const float* weight, int variant, int mode,
+                   float epsilon, int B, int K, int oh, int ow, int tmp, const float* tab,
+                   const int32_t* centres, const float* stats, const float* grad_out, int grad_kind,
+                   float* grad_in, hp_stream_t stream);
+/* the .ground_truth / .ground_false attributes the reference classes expose, on demand */
+int hp_regdisp_materialize(const float* fused, int variant, int B, int K, int oh, int ow, int tmp,
+                           const float* tab, const int32_t* centres, float* gt, float* gf,
+                           hp_stream_t stream);
+
+/* ---- a12: multiscale fusion.  train1.py:410-424 (nn.Upsample bilinear, align_corners=False) */
+/* out[n,H,W] = a_lo * up(lo[n,hl,wl]) + a_mid * up(mid[n,hm,wm]) + a_hi * hi[n,H,W] ;
+ * mid and hi are nullable.  target5 = (0.5, 1, -) ; target0 = (1, -, -) ; 3-scale = (0.5, 1, 1). */
+int hp_fuse_multiscale(const float* lo, int hl, int wl, float a_lo,
+                       const float* mid, int hm, int wm, float a_mid,
+                       const float* hi, float a_hi, int n_maps, int H, int W, float* out,
+                       hp_stream_t stream);
+/* fuse (as above, never written to memory) + decode + PCK against target coordinates:
+ * BASELINE.json configs[3].  tgt_xy [n_maps,2] ; outputs as hp_accuracy. */
+int hp_fuse_decode_pck(const float* lo, int hl, int wl, float a_lo,
+                       const float* mid, int hm, int wm, float a_mid,
+                       const float* hi, float a_hi, const float* tgt_xy, int B, int K, int H, int W,
+                       double thr, float* pred_xy, float* maxvals, int32_t* counts, double* acc_out,
+                       void* workspace, hp_stream_t stream);
+
+/* ---- the benchmarked pipeline: gen + loss + decode + PCK in ONE pass over `pred` -------
+ * replaces generate_target xB (util.py:9-68) + JointsMSELoss (loss.py:55-65) + JointsKLLoss
+ * (loss.py:145-158) + accuracy (keypoint_detection.py:63-92); the target is generated in
+ * registers and never written.
+ *   pred [B,K,H,W] ; joints float64 [B*K,2] ; vis float32 [B*K]
+ *   pred_xy [B*K,2], maxvals [B*K], weight_out [B*K]           (per-map outputs)
+ *   partial float64 [4 + 2K] = { mse_sum, kl_sum, n_maps, n_elems, hits[K], valid[K] }
+ *       (+= semantics when accumulate != 0: batch shards / ranks add up, then finalise)
+ *   result float64 [4 + K] = { mse, kl, avg_acc, cnt, acc[K] }  (nullable: skip finalise)
+ */
+int hp_pipeline_fused(const float* pred, const double* joints, const float* vis,
+                      int B, int K, int H, int W, double stride_x, double stride_y, int tmp,
+                      const float* tab, float kl_epsilon, double thr, int loss_mask,
+                      float* pred_xy, float* maxvals, float* weight_out,
+                      double* partial, int accumulate, double* result, void* workspace,
+                      hp_stream_t stream);
+/* partial (e.g. after an NCCL all-reduce over ranks) -> result, on device */
+int hp_pipeline_finalize(const double* partial, int K, double* result, hp_stream_t stream);
+
+/* Host-buffer form (end-to-end path): h_* are pinned host arrays; the batch is cut into slabs
+ * of slab_B samples whose H2D copies (copy_stream) overlap the kernels (stream); device
+ * staging d_pred holds 2 slabs [2*slab_B,K,H,W]; returns after h_result is valid. */
+int hp_pipeline_fused_host(const float* h_pred, const double* h_joints, const float* h_vis,
+                           int B, int K, int H, int W, double stride_x, double stride_y, int tmp,
+                           const float* tab, float kl_epsilon, double thr, int loss_mask,
+                           int slab_B, float* d_pred, double* d_joints, float* d_vis,
+                           float* d_pred_xy, float* d_maxvals, float* d_weight,
+                           double* d_partial, double* d_result, void* workspace,
+                           float* h_pred_xy /*nullable*/, double* h_result,
+                           hp_stream_t stream, hp_stream_t copy_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HP_B200_H */

@@ -1,0 +1,248 @@
+"""GPU parity: the CUDA path (through the C ABI) against (a) the golden vectors frozen from the real
+reference and (b) the live CPU oracle on the same seeded inputs.  Bars are in the key prefixes of
+oracle/cases.py: ``x:`` bit-exact (coordinates, maxvals, PCK counts/acc, weights), ``c:`` rtol 1e-5
+(+ atol 1e-6 for heatmaps, scaled for gradients)."""
+import importlib
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import api, cases
+from oracle import hp_oracle as O
+from oracle.gen_golden import digest
+
+pytestmark = pytest.mark.gpu
+
+hp = importlib.import_module("domain-adaptative-hand-pose-estimation_b200")
+
+
+def _ns():
+    import types
+    return types.SimpleNamespace(
+        get_max_preds=hp.get_max_preds, accuracy=hp.accuracy, generate_target=hp.generate_target,
+        JointsMSELoss=hp.JointsMSELoss, JointsKLLoss=hp.JointsKLLoss,
+        PseudoLabelGenerator=hp.PseudoLabelGenerator, PseudoLabelGenerator01=hp.PseudoLabelGenerator01,
+        PseudoLabelGenerator02=hp.PseudoLabelGenerator02, PseudoLabelGenerator03=hp.PseudoLabelGenerator03,
+        RegressionDisparity=hp.RegressionDisparity, RegressionDisparityx1=hp.RegressionDisparityx1,
+        RegressionDisparityx5=hp.RegressionDisparityx5, RegressionDisparityx6=hp.RegressionDisparityx6,
+        fuse_multiscale=hp.fuse_multiscale)
+
+
+@pytest.fixture(scope="module")
+def cuda_outputs():
+    cache = {}
+
+    def get(name):
+        if name not in cache:
+            cache[name] = cases.CASES[name](_ns(), "cuda")
+        return cache[name]
+    return get
+
+
+@pytest.mark.parametrize("name", list(cases.CASES))
+def test_cuda_matches_reference_goldens(name, golden, cuda_outputs):
+    cases.compare(digest(cuda_outputs(name)), golden(name))
+
+
+@pytest.mark.parametrize("name", list(cases.CASES))
+def test_cuda_matches_live_oracle(name, cuda_outputs):
+    want = cases.CASES[name](api.namespace(), "cpu")
+    cases.compare(cuda_outputs(name), want)
+
+
+def test_generated_targets_are_bit_equal_to_live_oracle():
+    """Same host, same numpy: the table trick makes generated heatmaps bit-identical, not just close."""
+    joints, vis = cases.target_inputs()
+    for s in (64, 32, 128):
+        t, w = hp.generate_target_batch(joints, vis, (s, s), 2, (256, 256))
+        ot, ow = O.generate_target_batch(joints, vis, (s, s), 2, (256, 256))
+        assert np.array_equal(t.cpu().numpy(), ot)
+        assert np.array_equal(w.cpu().numpy(), ow)
+
+
+# ------------------------------------------------------------------ fused pipeline
+
+def _run_pipeline(d, eps, **kw):
+    pipe = hp.HeatmapPipeline(num_keypoints=d["pred"].shape[1], heatmap_size=(d["pred"].shape[3], d["pred"].shape[2]),
+                              kl_epsilon=eps, **kw)
+    out = pipe(torch.from_numpy(d["pred"]).cuda(), torch.from_numpy(d["joints"]).cuda(),
+               torch.from_numpy(d["vis"]).cuda())
+    return pipe, out
+
+
+@pytest.mark.parametrize("size,B,seed", [(64, 8, 801), (32, 6, 802), (16, 6, 803), (128, 2, 804)])
+def test_pipeline_matches_oracle(size, B, seed):
+    d = hp.synth.make_host_batch(seed, B, 21, size, size)
+    # edge rows: out-of-bounds joint, invisible joint, joint whose centre has x<=1 (PCK-invalid)
+    d["joints"][0, 0] = (-50.0, 10.0); d["joints"][0, 1] = (3.0, 100.0); d["vis"][0, 2] = 0.0
+    want = O.pipeline(d["pred"], d["joints"], d["vis"], kl_epsilon=1e-7)
+    _, out = _run_pipeline(d, 1e-7)
+    got = out.host()
+    part = out.partial.cpu().numpy()
+    assert np.array_equal(out.pred_xy.cpu().numpy(), want["pred_xy"])
+    assert np.array_equal(out.weight.cpu().numpy(), want["weight"])
+    assert np.array_equal(part[4:25].astype(np.int64), want["hits"])
+    assert np.array_equal(part[25:46].astype(np.int64), want["valid"])
+    assert np.array_equal(got["acc"], want["acc"]) and got["avg_acc"] == want["avg_acc"] and got["cnt"] == want["cnt"]
+    np.testing.assert_allclose(got["mse"], want["mse"], rtol=1e-5)
+    np.testing.assert_allclose(got["kl"], want["kl"], rtol=1e-5)
+    assert part[2] == B * 21 and part[3] == B * 21 * size * size
+
+
+def test_pipeline_kl_eps0_is_nan_like_reference():
+    """epsilon=0 + an invisible joint (all-zero target) -> NaN even with weight 0."""
+    d = hp.synth.make_host_batch(811, 4)
+    d["vis"][1, 3] = 0.0
+    want = O.pipeline(d["pred"], d["joints"], d["vis"], kl_epsilon=0.0)
+    _, out = _run_pipeline(d, 0.0)
+    got = out.host()
+    assert np.isnan(want["kl"]) and np.isnan(got["kl"])
+    np.testing.assert_allclose(got["mse"], want["mse"], rtol=1e-5)
+
+
+def test_pipeline_odd_sizes_scalar_walk():
+    d = hp.synth.make_host_batch(821, 3, 7, 30, 42)          # H=30, W=42: W % 4 != 0
+    want = O.pipeline(d["pred"], d["joints"], d["vis"], kl_epsilon=1e-7)
+    _, out = _run_pipeline(d, 1e-7)
+    got = out.host()
+    assert np.array_equal(out.pred_xy.cpu().numpy(), want["pred_xy"])
+    assert np.array_equal(got["acc"], want["acc"]) and got["cnt"] == want["cnt"]
+    np.testing.assert_allclose(got["mse"], want["mse"], rtol=1e-5)
+    np.testing.assert_allclose(got["kl"], want["kl"], rtol=1e-5)
+
+
+def test_pipeline_host_path_equals_device_path():
+    d = hp.synth.make_host_batch(831, 37)
+    pipe, out = _run_pipeline(d, 1e-7)
+    dev = out.host()
+    for slab in (8, 16, 64):
+        h = pipe.run_host(d["pred"], d["joints"], d["vis"], slab=slab)
+        assert np.array_equal(h["pred_xy"], out.pred_xy.cpu().numpy())
+        assert np.array_equal(h["acc"], dev["acc"]) and h["cnt"] == dev["cnt"] and h["avg_acc"] == dev["avg_acc"]
+        np.testing.assert_allclose(h["mse"], dev["mse"], rtol=1e-12)
+        np.testing.assert_allclose(h["kl"], dev["kl"], rtol=1e-12)
+
+
+def test_pipeline_full_size_properties():
+    """BASELINE configs[1] size (256x21x64x64): size-independent properties instead of the slow oracle -
+    fused == composition of the unfused CUDA ops; PCK of targets against themselves; determinism."""
+    B = 256
+    d = hp.synth.make_device_batch(841, B)
+    pipe = hp.HeatmapPipeline(kl_epsilon=1e-7)
+    out = pipe(d["pred"], d["joints"], d["vis"])
+    r1 = out.result.clone(); p1 = out.partial.clone(); xy1 = out.pred_xy.clone()
+    target, weight = hp.generate_target_batch(d["joints"], d["vis"], (64, 64), 2, (256, 256))
+    mse = hp.JointsMSELoss()(d["pred"], target, weight)
+    kl = hp.JointsKLLoss(epsilon=1e-7)(d["pred"], target, weight)
+    acc, avg, cnt, pred = hp.accuracy(d["pred"], target)
+    got = out.host()
+    assert torch.equal(pred, out.pred_xy) and torch.equal(weight, out.weight)
+    assert np.array_equal(acc, got["acc"]) and avg == got["avg_acc"] and cnt == got["cnt"]
+    np.testing.assert_allclose(got["mse"], mse.item(), rtol=1e-5)
+    np.testing.assert_allclose(got["kl"], kl.item(), rtol=1e-5)
+    # decode(generate_target(j)) is the centre: every valid joint hits when scored against itself
+    acc_t, avg_t, cnt_t, _ = hp.accuracy(target, target)
+    assert all(a in (1.0, -1.0) for a in acc_t)
+    # bitwise determinism over repeated launches (fixed-order reductions, integer counters)
+    for _ in range(3):
+        out2 = pipe(d["pred"], d["joints"], d["vis"])
+        assert torch.equal(out2.result, r1) and torch.equal(out2.partial, p1) and torch.equal(out2.pred_xy, xy1)
+
+
+# ------------------------------------------------------------------ generic shapes / edge cases
+
+@pytest.mark.parametrize("H,W,K", [(30, 42, 5), (20, 20, 21), (100, 100, 3), (7, 5, 2), (96, 72, 4), (256, 256, 2)])
+def test_decode_and_accuracy_generic_shapes(H, W, K):
+    d = hp.synth.make_host_batch(900 + H, 3, K, H, W)
+    p, mv = hp.get_max_preds(d["pred"])
+    op, omv = O.get_max_preds(d["pred"])
+    assert np.array_equal(p, op) and np.array_equal(mv, omv)
+    tgt, _ = O.generate_target_batch(d["joints"], d["vis"], (W, H), 2, (256, 256))
+    acc, avg, cnt, pred = hp.accuracy(d["pred"], tgt)
+    oacc, oavg, ocnt, opred = O.accuracy(d["pred"], tgt)
+    assert np.array_equal(acc, oacc) and avg == oavg and cnt == ocnt and np.array_equal(pred, opred)
+
+
+def test_pck_threshold_boundaries_non_power_of_two():
+    """dx,dy sweeps at sizes where 0.5*norm lands on representable distances (20, 40, 100, 50)."""
+    for S in (20, 40, 50, 100):
+        K = 21
+        o = np.zeros((4, K, S, S), np.float32); t = np.zeros((4, K, S, S), np.float32)
+        rs = np.random.RandomState(S)
+        for b in range(4):
+            for k in range(K):
+                cx, cy = rs.randint(8, S - 8, size=2)
+                dx, dy = rs.randint(-6, 7, size=2)
+                t[b, k, cy, cx] = 1.0
+                o[b, k, cy + dy, cx + dx] = 1.0
+        acc, avg, cnt, _ = hp.accuracy(o, t)
+        oacc, oavg, ocnt, _ = O.accuracy(o, t)
+        assert np.array_equal(acc, oacc) and avg == oavg and cnt == ocnt, S
+
+
+@pytest.mark.parametrize("H,W", [(30, 42), (48, 48), (24, 36)])
+def test_losses_generic_shapes(H, W):
+    d = hp.synth.make_host_batch(950 + H, 3, 6, H, W)
+    tgt, w = O.generate_target_batch(d["joints"], d["vis"], (W, H), 2, (256, 256))
+    for make_g, make_o in ((lambda: hp.JointsMSELoss(), lambda: api.JointsMSELoss()),
+                           (lambda: hp.JointsKLLoss(epsilon=1e-7), lambda: api.JointsKLLoss(epsilon=1e-7)),
+                           (lambda: hp.JointsKLLoss("none", 1e-7), lambda: api.JointsKLLoss("none", 1e-7)),
+                           (lambda: hp.JointsMSELoss("none"), lambda: api.JointsMSELoss("none"))):
+        pg = torch.from_numpy(d["pred"]).cuda().requires_grad_(True)
+        pc = torch.from_numpy(d["pred"]).requires_grad_(True)
+        lg = make_g()(pg, torch.from_numpy(tgt).cuda(), torch.from_numpy(w).cuda())
+        lc = make_o()(pc, torch.from_numpy(tgt), torch.from_numpy(w))
+        np.testing.assert_allclose(lg.detach().cpu().numpy(), lc.detach().numpy(), rtol=1e-5, atol=1e-7)
+        lg.sum().backward(); lc.sum().backward()
+        g = pc.grad.numpy()
+        np.testing.assert_allclose(pg.grad.cpu().numpy(), g, rtol=1e-5, atol=1e-6 * np.abs(g).max())
+
+
+def test_three_scale_fuse_decode_pck_matches_unfused_and_oracle():
+    rs = np.random.RandomState(77)
+    B, K = 4, 21
+    d = hp.synth.make_host_batch(78, B, K, 128, 128)
+    mid, lo = hp.synth.make_lowres_heads(79, d["pred"], (64, 32))
+    hi = (0.3 * d["pred"]).astype(np.float32)
+    tgt, _ = O.generate_target_batch(d["joints"], d["vis"], (128, 128), 2, (256, 256))
+    txy, _ = O.get_max_preds(tgt)
+    ev = hp.MultiscaleEval(K)
+    acc, pred_xy, counts = ev(torch.from_numpy(lo).cuda(), torch.from_numpy(mid).cuda(), torch.from_numpy(hi).cuda(),
+                              torch.from_numpy(txy).cuda())
+    fused_gpu = hp.fuse_three_scales(torch.from_numpy(lo).cuda(), torch.from_numpy(mid).cuda(), torch.from_numpy(hi).cuda())
+    fused_cpu = O.fuse_three_scales(torch.from_numpy(lo), torch.from_numpy(mid), torch.from_numpy(hi))
+    np.testing.assert_allclose(fused_gpu.cpu().numpy(), fused_cpu.numpy(), rtol=1e-5, atol=1e-6)
+    # in-register fusion decodes exactly like decoding the materialised CUDA fusion
+    p2, _ = hp.get_max_preds(fused_gpu)
+    assert torch.equal(pred_xy, p2)
+    hits, valid = O.pck_counts(p2.cpu().numpy(), txy, 128, 128)
+    c = counts.cpu().numpy()
+    assert np.array_equal(c[:K], hits) and np.array_equal(c[K:], valid)
+
+
+def test_foreign_criterion_gets_materialised_maps():
+    I = cases.disparity_inputs()
+    y, adv, w = (torch.from_numpy(I[k]).cuda() for k in ("y", "adv64", "w"))
+    rd_g = hp.RegressionDisparity(hp.PseudoLabelGenerator(21, 64, 64), hp.JointsMSELoss())
+    rd_o = api.RegressionDisparity(api.PseudoLabelGenerator(21, 64, 64), api.JointsMSELoss())
+    for mode in ("min", "max"):
+        lg = rd_g(y, adv, w, mode)
+        lo = rd_o(torch.from_numpy(I["y"]), torch.from_numpy(I["adv64"]), torch.from_numpy(I["w"]), mode)
+        np.testing.assert_allclose(lg.item(), lo.item(), rtol=1e-5)
+
+
+def test_no_cpu_fallback_and_argument_errors():
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        hp.JointsKLLoss()(torch.zeros(1, 2, 4, 4), torch.zeros(1, 2, 4, 4))
+    with pytest.raises(AssertionError):
+        hp.get_max_preds(np.zeros((2, 4, 4), np.float32))
+    with pytest.raises(AssertionError):
+        hp.get_max_preds([[1.0]])
+    with pytest.raises(ValueError):
+        hp.JointsMSELoss()(torch.zeros(1, 2, 4, 4).cuda(), torch.zeros(1, 2, 4, 5).cuda())
+    with pytest.raises(IndexError):
+        hp.PseudoLabelGenerator01(21)(torch.zeros(1, 21, 128, 128).cuda())
+    with pytest.raises(AssertionError):
+        hp.RegressionDisparity(hp.PseudoLabelGenerator(21), hp.JointsKLLoss())(
+            torch.zeros(1, 21, 64, 64).cuda(), torch.zeros(1, 21, 64, 64).cuda(), None, "sideways")
