@@ -67,12 +67,15 @@ class HeatmapPipeline:
         with torch.cuda.device(self.device):
             self.tab = _lib.gaussian_table(sigma, self.tmp, self.device)
         self._host_state = None
+        self._ws = None
+        self._plans = {}
         _lib.load()
 
     # ------------------------------------------------------------------------------ device path
-    def __call__(self, pred, joints, vis, out=None) -> PipelineResult:
-        """pred float32 [B,K,H,W], joints float64 [B,K,2] (image px), vis float32 [B,K,1]|[B,K]: CUDA
-        tensors of THIS rank's slice of the batch.  Asynchronous on the current stream."""
+    def plan(self, pred, joints, vis, out=None, finalize=True):
+        """Validate once and return ``(launch, out)``: ``launch()`` enqueues the fused kernel on the
+        current stream with pre-bound arguments (a ~15 us kernel leaves no room for per-call Python
+        argument checking; this is also what gets captured into CUDA graphs)."""
         pred = _lib.require_cuda(pred, "HeatmapPipeline(pred)")
         joints = _lib.require_cuda(joints, "HeatmapPipeline(joints)", torch.float64)
         vis = _lib.require_cuda(vis, "HeatmapPipeline(vis)")
@@ -82,19 +85,62 @@ class HeatmapPipeline:
         if joints.numel() != 2 * B * K or vis.numel() != B * K:
             raise ValueError("joints must be [B,K,2] and vis [B,K,1]")
         dev = pred.device
+        if dev != self.device:
+            raise ValueError(f"inputs are on {dev}, the pipeline was built for {self.device}")
         if out is None:
             out = self.alloc_outputs(B, dev)
+        ws = self._workspace(B * K)
+        fn = _lib.load().hp_pipeline_fused
+        args = (_lib.ptr(pred), _lib.ptr(joints), _lib.ptr(vis), B, K, H, W, C.c_double(self.stride[0]),
+                C.c_double(self.stride[1]), self.tmp, _lib.ptr(self.tab), C.c_float(self.kl_epsilon),
+                C.c_double(self.thr), self.loss_mask, _lib.ptr(out.pred_xy), _lib.ptr(out.maxvals), _lib.ptr(out.weight),
+                _lib.ptr(out.partial), 0, _lib.ptr(out.result) if finalize else None, _lib.ptr(ws))
+        keep = (pred, joints, vis, out, ws)            # the plan owns references: pointers stay valid
+        current_stream = torch.cuda.current_stream
+
+        def launch(_keep=keep):
+            rc = fn(*args, C.c_void_p(current_stream(dev).cuda_stream))
+            if rc != 0:
+                raise RuntimeError(f"hp_pipeline_fused failed (rc={rc}): "
+                                   f"{_lib.load().hp_last_error().decode(errors='replace')}")
+        return launch, out
+
+    def _workspace(self, n_maps):
+        """One zero-initialised workspace per pipeline object (a pipeline is used on one stream at a time)."""
+        need = int(_lib.load().hp_workspace_bytes(int(n_maps), self.K))
+        if self._ws is None or self._ws.numel() < need:
+            with torch.cuda.device(self.device):
+                self._ws = torch.zeros(max(need, 1 << 16), dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def _cached_plan(self, pred, joints, vis, out, finalize):
+        key = (pred.data_ptr(), joints.data_ptr(), vis.data_ptr(), id(out), pred.shape[0], finalize)
+        hit = self._plans.get(key)
+        if hit is None:
+            if len(self._plans) > 256:
+                self._plans.clear()
+            hit = self.plan(pred, joints, vis, out, finalize)
+            self._plans[key] = hit
+        return hit
+
+    def launch_local(self, pred, joints, vis, out=None) -> PipelineResult:
+        """This rank's kernel only (finalised locally, no collective)."""
+        launch, out = self._cached_plan(pred, joints, vis, out, True)
+        launch()
+        return out
+
+    def __call__(self, pred, joints, vis, out=None) -> PipelineResult:
+        """pred float32 [B,K,H,W], joints float64 [B,K,2] (image px), vis float32 [B,K,1]|[B,K]: CUDA
+        tensors of THIS rank's slice of the batch.  Asynchronous on the current stream.  Single process:
+        one kernel.  Sharded (torch.distributed initialised): kernel -> all-reduce of the 4+2K partial
+        doubles (the path's only collective) -> finalise kernel."""
         sharded = hpdist.is_distributed(self.group)
-        with torch.cuda.device(dev):
-            ws = _lib.workspace(dev, B * K, K)
-            _lib.call("hp_pipeline_fused", _lib.ptr(pred), _lib.ptr(joints), _lib.ptr(vis), B, K, H, W,
-                      C.c_double(self.stride[0]), C.c_double(self.stride[1]), self.tmp, _lib.ptr(self.tab),
-                      C.c_float(self.kl_epsilon), C.c_double(self.thr), self.loss_mask, _lib.ptr(out.pred_xy),
-                      _lib.ptr(out.maxvals), _lib.ptr(out.weight), _lib.ptr(out.partial), 0,
-                      None if sharded else _lib.ptr(out.result), _lib.ptr(ws), _lib.stream_ptr(dev))
-            if sharded:
-                hpdist.allreduce_partial(out.partial, self.group)      # the path's only collective
-                _lib.call("hp_pipeline_finalize", _lib.ptr(out.partial), K, _lib.ptr(out.result), _lib.stream_ptr(dev))
+        launch, out = self._cached_plan(pred, joints, vis, out, not sharded)
+        launch()
+        if sharded:
+            hpdist.allreduce_partial(out.partial, self.group)
+            _lib.call("hp_pipeline_finalize", _lib.ptr(out.partial), self.K, _lib.ptr(out.result),
+                      _lib.stream_ptr(self.device))
         return out
 
     def alloc_outputs(self, B, device=None) -> PipelineResult:
@@ -122,7 +168,7 @@ class HeatmapPipeline:
         st = self._host_buffers(B, slab)
         dev = self.device
         with torch.cuda.device(dev):
-            ws = _lib.workspace(dev, B * K, K)
+            ws = self._workspace(B * K)
             _lib.call("hp_pipeline_fused_host", _lib.ptr(hp), _lib.ptr(hj), _lib.ptr(hv), B, K, H, W,
                       C.c_double(self.stride[0]), C.c_double(self.stride[1]), self.tmp, _lib.ptr(self.tab),
                       C.c_float(self.kl_epsilon), C.c_double(self.thr), self.loss_mask, slab, _lib.ptr(st["d_pred"]),

@@ -5,7 +5,7 @@
 Evaluates every case of ``oracle/cases.py`` on the reference's own code (loaded in place by
 ``oracle/ref_loader.py``) and stores the outputs.  Inputs are regenerated from seeds by the
 tests.  Arrays above ``DIGEST_ABOVE`` elements are stored as a digest (strided sample + float64
-sum + L2 norm) to keep the fixtures small; ``digest()`` is applied to the candidate side too.
+L1 + L2 norms) to keep the fixtures small; ``digest()`` is applied to the candidate side too.
 """
 from __future__ import annotations
 
@@ -34,7 +34,7 @@ def digest(outputs: dict) -> dict:
         flat = a.reshape(-1)
         out[key + "#sample"] = flat[::DIGEST_STRIDE].copy()
         f64 = flat.astype(np.float64)
-        out["c:" + key[2:] + "#sum"] = np.asarray([f64.sum()])
+        out["c:" + key[2:] + "#l1"] = np.asarray([np.abs(f64).sum()])   # signed sums of gradients cancel to ~0
         out["c:" + key[2:] + "#l2"] = np.asarray([np.sqrt((f64 * f64).sum())])
         out["x:" + key[2:] + "#shape"] = np.asarray(a.shape, dtype=np.int64)
     return out
