@@ -266,13 +266,9 @@ def run_product_arm(args):
     value = maps_per_step * args.steps / (ms_total * 1e-3)
 
     # dominant kernel alone (identical to the step at N=1; without the collective at N>1)
-    solo = hp.HeatmapPipeline(num_keypoints=K, heatmap_size=(side, side), image_size=(4 * side, 4 * side), sigma=2,
-                              kl_epsilon=KL_EPS, device=dev, group=None)
-    solo._force_single = True
-
     def kernel_only(i):
         s = sets[i % n_sets]
-        solo.launch_local(s["pred"], s["joints"], s["vis"], outs[i % n_sets])
+        pipe.launch_local(s["pred"], s["joints"], s["vis"], outs[i % n_sets])
 
     for i in range(3):
         kernel_only(i)
