@@ -126,13 +126,14 @@ def cpu_reference_setup():
 def cpu_reference_step(O, batch, side):
     """One pass of the reference path on the host: generate_target x B + JointsMSELoss + JointsKLLoss +
     accuracy (2x get_max_preds + PCK)."""
-    return O.pipeline(batch["pred"], batch["joints"], batch["vis"], kl_epsilon=KL_EPS)
+    return O.pipeline(batch["pred"], batch["joints"], batch["vis"], kl_epsilon=KL_EPS,
+                      image_size=(4 * side, 4 * side))
 
 
 def run_cpu_baseline(side, budget_s=12.0, sample_B=32, min_reps=3, max_reps=400):
     synth = importlib.import_module(PKG + ".synth")
     O, threads = cpu_reference_setup()
-    batch = synth.make_host_batch(1234, sample_B, K_JOINTS, side, side)
+    batch = synth.make_host_batch(1234, sample_B, K_JOINTS, side, side, image_size=4 * side)
     cpu_reference_step(O, batch, side)                       # warm-up (LUT-free path, torch thread pool)
     reps, t0 = 0, time.perf_counter()
     while reps < max_reps and (reps < min_reps or time.perf_counter() - t0 < budget_s):
@@ -152,7 +153,7 @@ def run_reference_arm(args):
     synth = importlib.import_module(PKG + ".synth")
     O, threads = cpu_reference_setup()
     sample_B = 32
-    batch = synth.make_host_batch(1234, sample_B, K_JOINTS, side, side)
+    batch = synth.make_host_batch(1234, sample_B, K_JOINTS, side, side, image_size=4 * side)
     for _ in range(max(1, min(args.warmup, 3))):
         cpu_reference_step(O, batch, side)
     budget = 150.0
