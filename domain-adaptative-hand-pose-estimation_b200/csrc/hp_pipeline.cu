@@ -14,6 +14,8 @@
 // Algorithmic bytes per map: H*W*4 (pred) + 24 (joint, vis, weight) + 8 (coords) = 16,416 at 64x64.
 // Roofline: HBM.  Per element: 1 compare-select pair (argmax), 1 FFMA+MUFU+FADD (softmax),
 // 1 FADD (sum p), 1 FFMA (squared error); target terms only on the 13 rows the patch touches.
+#include <cmath>
+
 #include "hp_common.cuh"
 #include "hp_dispatch.cuh"
 
@@ -64,6 +66,12 @@ __device__ __forceinline__ void pipeline_result_from_partial(const double* p, in
     result[2] = acc[K];
     result[3] = acc[K + 1];
 }
+
+}  // namespace hp
+
+#include "hp_pipeline_stream.cuh"
+
+namespace hp {
 
 template <int TPM, int NV, int MODE, int MPB>
 __global__ void __launch_bounds__(TPM* MPB) pipeline_kernel(const PipeArgs a) {
@@ -277,6 +285,45 @@ static int launch_pipeline(const float* pred, const double* joints, const float*
     a.ws = static_cast<Workspace*>(workspace);
     a.map_vals = reinterpret_cast<float*>(static_cast<char*>(workspace) + (sizeof(Workspace) + 255) / 256 * 256);
     (void)ws_maps;
+    const int HW = H * W, side = 2 * tmp + 1;
+    // fast shape: one warp per map, register-tile streaming (hp_pipeline_stream.cuh)
+    const bool stream_ok = aligned16(pred) && (W % 4 == 0) && (HW % 256 == 0) && HW < (1 << 24) &&
+                           side * side <= 32 * kStreamMaxPatch && (sizeof(Workspace) + 255) / 256 * 256 +
+                           sizeof(double) * 2 * ((a.n_maps + kStreamWarps - 1) / kStreamWarps) <=
+                           hp_workspace_bytes(a.n_maps, K);
+    if (stream_ok) {
+        StreamArgs sa{};
+        sa.pred = pred; sa.joints = joints; sa.vis = vis; sa.n_maps = a.n_maps; sa.K = K; sa.H = H; sa.W = W; sa.HW = HW;
+        sa.wdiv = a.wdiv; sa.sdiv = FastDiv(static_cast<uint32_t>(side));
+        sa.sx = stride_x; sa.sy = stride_y; sa.inv_sx = 1.0 / stride_x; sa.inv_sy = 1.0 / stride_y;
+        int ex = 0, ey = 0;
+        sa.pow2_stride = (std::frexp(stride_x, &ex) == 0.5 && std::frexp(stride_y, &ey) == 0.5) ? 1 : 0;
+        sa.tmp = tmp; sa.tab = tab; sa.eps = kl_epsilon;
+        sa.eps_log_eps = kl_epsilon > 0.0f ? static_cast<float>(static_cast<double>(kl_epsilon) * std::log(static_cast<double>(kl_epsilon))) : 0.0f;
+        sa.thr = thr;
+        const double t2 = thr * thr;
+        sa.thr2_lo = static_cast<float>(t2 * (1.0 - 1e-4)); sa.thr2_hi = static_cast<float>(t2 * (1.0 + 1e-4));
+        sa.inv_nx = static_cast<float>(10.0 / H); sa.inv_ny = static_cast<float>(10.0 / W);  // norm = (H/10, W/10) on (x, y)
+        sa.pred_xy = pred_xy; sa.maxvals = maxvals; sa.weight_out = weight_out; sa.partial = partial;
+        sa.accumulate = accumulate; sa.result = result; sa.ws = a.ws;
+        sa.cta_vals = reinterpret_cast<double*>(a.map_vals);
+        const int grid = (a.n_maps + kStreamWarps - 1) / kStreamWarps;
+        const size_t smem = table_bytes(tmp);
+        const bool big = (HW % 1024) == 0;
+        sa.ntiles = HW / (big ? 1024 : 256);
+#define HP_STREAM_LAUNCH(NVV, LM) pipeline_stream_kernel<NVV, LM><<<grid, 32 * kStreamWarps, smem, stream>>>(sa)
+#define HP_STREAM_BY_LOSS(NVV)                                  \
+        switch (loss_mask) {                                    \
+            case 0: HP_STREAM_LAUNCH(NVV, 0); break;            \
+            case HP_LOSS_MSE: HP_STREAM_LAUNCH(NVV, 1); break;  \
+            case HP_LOSS_KL: HP_STREAM_LAUNCH(NVV, 2); break;   \
+            default: HP_STREAM_LAUNCH(NVV, 3); break;           \
+        }
+        if (big) { HP_STREAM_BY_LOSS(8) } else { HP_STREAM_BY_LOSS(2) }
+#undef HP_STREAM_BY_LOSS
+#undef HP_STREAM_LAUNCH
+        return launch_status("hp_pipeline_fused");
+    }
     PipeLaunch l{a, stream};
     dispatch_map_walk(H * W, aligned16(pred) && (W % 4 == 0), l);
     return launch_status("hp_pipeline_fused");

@@ -1,0 +1,153 @@
+"""Run the reference's own drivers (``train1.py`` / ``test.py``) UNCHANGED on top of the B200 path.
+
+    python hpb200.py --ref /path/to/reference train1.py data/H3D -t Hand3DStudio ...
+    python hpb200.py --ref /path/to/reference test.py  data/H3D -t Hand3DStudio --checkpoint ...
+
+The reference has no plugin registry: its hot-path callables are plain names imported at
+``train1.py:18-32`` from modules that also hold the models.  So the drop-in is an overlay
+(SURVEY.md §8b):
+
+1. install compatibility shims for what the reference needs but a modern stack lacks
+   (``np.int``/``np.float``; ``matplotlib``, ``webcolors``, ``prettytable`` stubs when absent;
+   ``torchvision.models.utils.load_state_dict_from_url``; ``torchvision.models.resnet.model_urls``);
+2. import the reference modules that define or re-export the hot-path names;
+3. rebind those names - in every loaded reference module that holds them - to this package's
+   implementations (same signatures);
+4. ``runpy.run_path`` the driver as ``__main__``.
+
+Nothing is copied from the reference; it executes from where it lies.
+"""
+from __future__ import annotations
+
+import importlib
+import os
+import runpy
+import sys
+import types
+
+#: hot-path name -> attribute of this package
+REPLACED = (
+    "get_max_preds", "accuracy",                                    # utils/keypoint_detection.py
+    "JointsMSELoss", "JointsKLLoss",                                # uda/model/loss.py
+    "PseudoLabelGenerator", "PseudoLabelGenerator01", "PseudoLabelGenerator02", "PseudoLabelGenerator03",
+    "RegressionDisparity", "RegressionDisparityx1", "RegressionDisparityx5", "RegressionDisparityx6",
+    "generate_target",                                              # uda/dataset/util.py
+)
+
+#: reference modules that define the names above (imported before rebinding)
+DEFINING_MODULES = ("utils.keypoint_detection", "uda.model.loss", "uda.model.regda_4", "uda.model.regda_7",
+                    "uda.dataset.util")
+
+
+_BASIC_COLOURS = {"black": (0, 0, 0), "white": (255, 255, 255), "red": (255, 0, 0), "green": (0, 128, 0),
+                  "blue": (0, 0, 255), "yellow": (255, 255, 0), "purple": (128, 0, 128), "orange": (255, 165, 0),
+                  "cyan": (0, 255, 255), "magenta": (255, 0, 255), "pink": (255, 192, 203), "brown": (165, 42, 42),
+                  "gray": (128, 128, 128), "grey": (128, 128, 128), "lime": (0, 255, 0), "navy": (0, 0, 128)}
+
+
+def _stub_module(name):
+    """Stand-in for an optional visualisation dependency that is not installed: any attribute is a
+    no-op callable; ``webcolors.name_to_rgb`` (keypoint_dataset.py:52-55, drawing only) knows the basic names."""
+    mod = types.ModuleType(name)
+    mod.__dict__["__hp_stub__"] = True
+
+    def _noop(*args, **kwargs):
+        return None
+
+    def _getattr(attr):
+        if attr.startswith("__"):
+            raise AttributeError(attr)
+        if name == "webcolors" and attr == "name_to_rgb":
+            return lambda colour, *a, **k: _BASIC_COLOURS.get(str(colour).lower(), (0, 0, 0))
+        return _noop
+    mod.__getattr__ = _getattr
+    return mod
+
+
+def install_shims():
+    import numpy as np
+
+    if not hasattr(np, "int"):
+        np.int = int
+    if not hasattr(np, "float"):
+        np.float = float
+    for name in ("matplotlib", "matplotlib.pyplot", "webcolors", "prettytable"):
+        if name in sys.modules:
+            continue
+        try:
+            importlib.import_module(name)
+        except Exception:
+            sys.modules[name] = _stub_module(name)
+    if "matplotlib" in sys.modules and "matplotlib.pyplot" in sys.modules:
+        setattr(sys.modules["matplotlib"], "pyplot", sys.modules["matplotlib.pyplot"])
+    try:
+        import torchvision.models.utils  # noqa: F401  (removed in torchvision >= 0.13)
+    except Exception:
+        try:
+            import torch.hub
+            import torchvision.models as tvm
+            shim = types.ModuleType("torchvision.models.utils")
+            shim.load_state_dict_from_url = torch.hub.load_state_dict_from_url
+            sys.modules["torchvision.models.utils"] = shim
+            tvm.utils = shim
+            import torchvision.models.resnet as tvr
+            if not hasattr(tvr, "model_urls"):
+                tvr.model_urls = {k: "" for k in ("resnet18", "resnet34", "resnet50", "resnet101", "resnet152",
+                                                  "resnext50_32x4d", "resnext101_32x8d", "wide_resnet50_2",
+                                                  "wide_resnet101_2")}
+        except Exception:
+            pass
+
+
+def install(ref_root: str, verbose: bool = False):
+    """Shim, import and rebind.  Returns ``{module_name: [rebound names]}``."""
+    ref_root = os.path.abspath(ref_root)
+    if not os.path.isfile(os.path.join(ref_root, "utils", "keypoint_detection.py")):
+        raise FileNotFoundError(f"{ref_root} does not look like the reference tree")
+    sys.dont_write_bytecode = True
+    install_shims()
+    if ref_root not in sys.path:
+        sys.path.insert(0, ref_root)
+    pkg = importlib.import_module(__package__)
+    originals = {}
+    for modname in DEFINING_MODULES:
+        mod = importlib.import_module(modname)
+        for name in REPLACED:
+            if hasattr(mod, name) and getattr(mod, name).__module__ == mod.__name__:
+                originals.setdefault(name, []).append(getattr(mod, name))   # regda_4 and regda_7 both define some
+    rebound = {}
+    for modname, mod in list(sys.modules.items()):
+        path = getattr(mod, "__file__", None) or ""
+        if not path.startswith(ref_root):
+            continue
+        for name, origs in originals.items():
+            if any(mod.__dict__.get(name) is o for o in origs):
+                setattr(mod, name, getattr(pkg, name))
+                rebound.setdefault(modname, []).append(name)
+    if verbose:
+        for m in sorted(rebound):
+            print(f"[hpb200 overlay] {m}: {', '.join(sorted(rebound[m]))}", file=sys.stderr)
+    return rebound
+
+
+def main(argv=None):
+    argv = list(sys.argv[1:] if argv is None else argv)
+    ref = os.environ.get("HP_REF_DIR", "/root/reference")
+    verbose = False
+    while argv and argv[0].startswith("--"):
+        if argv[0] == "--ref" and len(argv) > 1:
+            ref = argv[1]
+            argv = argv[2:]
+        elif argv[0] == "--verbose":
+            verbose = True
+            argv = argv[1:]
+        else:
+            break
+    if not argv:
+        print(__doc__)
+        return 2
+    script = argv[0] if os.path.isabs(argv[0]) else os.path.join(ref, argv[0])
+    install(ref, verbose=verbose)
+    sys.argv = [script] + argv[1:]
+    runpy.run_path(script, run_name="__main__")
+    return 0

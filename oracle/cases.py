@@ -322,7 +322,9 @@ def compare(got: dict, want: dict, rtol=RTOL, atol=ATOL):
             assert same.all(), f"{key}: {int((~same).sum())} of {same.size} entries differ (bit-exact bar)"
         else:
             a = atol
-            if "grad" in key and w.size:      # gradients are O(1e-5): scale the absolute slack with them
+            if "grad" in key and w.size:
+                # gradients are c*(softmax - q): both terms carry ~1e-7 relative fp32 error (the reference's
+                # too) and nearly cancel, so the bar is 1e-5 of the tensor's scale, not of each element
                 finite = np.abs(w[np.isfinite(w)])
-                a = atol * min(1.0, float(finite.max())) if finite.size else atol
+                a = 1e-5 * float(finite.max()) if finite.size else atol
             np.testing.assert_allclose(g, w, rtol=rtol, atol=a, equal_nan=True, err_msg=key)
