@@ -430,12 +430,13 @@ __device__ __forceinline__ double block_sum_f32_as_f64(const float* __restrict__
     return r;
 }
 
-// workspace layout (all ops): [0] block counter, [1] spare, [2..2+2K) int32 hits/valid, then float64 slots
+// workspace layout (all ops): block counter, spare, int32 hits/valid counters, then eight 64-bit
+// accumulators (the fused pipeline's fixed-point loss sums and non-finite counters)
 struct Workspace {
     unsigned int counter;
     unsigned int spare;
     int counts[2 * HP_MAX_K];
-    double f64[8];
+    unsigned long long acc[8];
 };
 
 }  // namespace hp

@@ -15,77 +15,33 @@
 // Roofline: HBM.  Per element: 1 compare-select pair (argmax), 1 FFMA+MUFU+FADD (softmax),
 // 1 FADD (sum p), 1 FFMA (squared error); target terms only on the 13 rows the patch touches.
 #include <cmath>
+#include <cstdlib>
 
 #include "hp_common.cuh"
 #include "hp_dispatch.cuh"
-
-namespace hp {
-
-struct PipeArgs {
-    const float* pred;
-    const double* joints;
-    const float* vis;
-    int n_maps, K, H, W;
-    FastDiv wdiv;
-    double sx, sy;
-    int tmp;
-    const float* tab;
-    float eps;
-    double thr;
-    int loss_mask;
-    float* pred_xy;
-    float* maxvals;
-    float* weight_out;
-    double* partial;
-    int accumulate;
-    double* result;
-    Workspace* ws;
-    float* map_vals;  // [2*n_maps] per-map mse / kl (workspace tail)
-};
-
-// number of in-bounds pixels of the pasted patch
-__device__ __forceinline__ int patch_area(Centre c, int tmp, int W, int H) {
-    if (c.y == kNoPaste) return 0;
-    const int nx = min(c.x + tmp, W - 1) - max(c.x - tmp, 0) + 1;
-    const int ny = min(c.y + tmp, H - 1) - max(c.y - tmp, 0) + 1;
-    return nx * ny;
-}
-
-__device__ __forceinline__ void pipeline_result_from_partial(const double* p, int K, double* result) {
-    // p = { mse_sum, kl_sum, n_maps, n_elems, hits[K], valid[K] } ; result = { mse, kl, avg_acc, cnt, acc[K] }
-    result[0] = p[0] / p[2];
-    result[1] = p[1] / p[2];
-    int hits[HP_MAX_K], valid[HP_MAX_K];
-    for (int k = 0; k < K; ++k) {
-        hits[k] = static_cast<int>(p[4 + k]);
-        valid[k] = static_cast<int>(p[4 + K + k]);
-    }
-    double acc[HP_MAX_K + 2];
-    pck_finalize_serial(hits, valid, K, acc);
-    for (int k = 0; k < K; ++k) result[4 + k] = acc[k];
-    result[2] = acc[K];
-    result[3] = acc[K + 1];
-}
-
-}  // namespace hp
-
+#include "hp_pipeline_common.cuh"
+#include "hp_pipeline_coop.cuh"
 #include "hp_pipeline_stream.cuh"
 
 namespace hp {
 
+// ---------------------------------------------------------------------------------------------
+// generic shape: any H, W (odd widths, unaligned bases), any patch size.  Block-per-map register
+// tiles with the target evaluated next to every element - correct everywhere, fast nowhere; the
+// aligned power-of-two shapes never come here.
+// ---------------------------------------------------------------------------------------------
 template <int TPM, int NV, int MODE, int MPB>
-__global__ void __launch_bounds__(TPM* MPB) pipeline_kernel(const PipeArgs a) {
+__global__ void __launch_bounds__(TPM* MPB) pipeline_generic_kernel(const PipeArgs a) {
     // per-map sums: 0 sum (p-t)^2 | 1 sum p | 2 sum_patch u*p | 3 sum_patch u*log(u) | 4 sum_patch u | 5 sum_patch p
-    // with u = t + eps; "patch" = the pixels the pasted Gaussian covers (t != 0), everything else is
-    // background where u == eps exactly, so its contribution is added in closed form at the end.
     constexpr int NS = 6;
     extern __shared__ float s_tab[];
     __shared__ Stats<NS> scratch[TPM > 32 ? TPM / 32 + 1 : 1];
     __shared__ Centre s_centre[MPB];
     __shared__ float s_weight[MPB];
-    __shared__ double s_red[TPM * MPB];
+    __shared__ double s_map[2][MPB];
+    __shared__ BlockLoss s_loss;
 
-    const int HW = a.H * a.W;
+    const int HW = a.HW;
     const int g = threadIdx.x / TPM, t = threadIdx.x % TPM;
     const int map = blockIdx.x * MPB + g;
     const bool active = map < a.n_maps;
@@ -93,14 +49,14 @@ __global__ void __launch_bounds__(TPM* MPB) pipeline_kernel(const PipeArgs a) {
     const float* pm = a.pred + static_cast<size_t>(active ? map : 0) * HW;
     const int ntiles = (MODE == WALK_EXACT) ? 1 : tiles_for<TPM, NV>(HW);
 
-    // issue the first tile's loads before anything else so they are in flight during the setup
     float4 p[NV];
     if (active) load_tile<TPM, NV, MODE>(pm, HW, 0, t, -INFINITY, p);
-
     load_table(s_tab, a.tab, a.tmp);
+    if (threadIdx.x == 0) block_loss_zero(&s_loss);
+    if (t == 0) s_map[0][g] = s_map[1][g] = 0.0;
     if (active && t == 0) {
         float w;
-        s_centre[g] = target_centre(a.joints[2 * map], a.joints[2 * map + 1], a.vis[map], a.sx, a.sy, a.W, a.H, w);
+        s_centre[g] = pipe_centre(a, a.joints[2 * map], a.joints[2 * map + 1], a.vis[map], w);
         s_weight[g] = w;
     }
     __syncthreads();
@@ -200,66 +156,39 @@ __global__ void __launch_bounds__(TPM* MPB) pipeline_kernel(const PipeArgs a) {
             const int k = map % a.K;
             if (valid) atomicAdd(&a.ws->counts[a.K + k], 1);
             if (hit) atomicAdd(&a.ws->counts[k], 1);
-            float mse = 0.f, kl = 0.f;
+            double mse = 0.0, kl = 0.0;
             if (want_mse)  // mean over HW of 0.5*w*(p-t)^2   (loss.py:59-65)
-                mse = static_cast<float>(0.5 * static_cast<double>(w) * static_cast<double>(st.sum[0]) /
-                                         static_cast<double>(HW));
+                mse = 0.5 * static_cast<double>(w) * static_cast<double>(st.sum[0]) / static_cast<double>(HW);
             if (want_kl) {
                 const double eps = static_cast<double>(a.eps);
-                const double n_bg = static_cast<double>(HW - patch_area(c, a.tmp, a.W, a.H));
+                const double n_bg = static_cast<double>(HW - pipe_patch_area(a, c));
                 const double Su = static_cast<double>(st.sum[4]) + eps * n_bg;
                 const double Sup = static_cast<double>(st.sum[2]) +
                                    eps * (static_cast<double>(st.sum[1]) - static_cast<double>(st.sum[5]));
                 const double Sulogu = static_cast<double>(st.sum[3]) + ((a.eps > 0.0f) ? n_bg * eps * log(eps) : 0.0);
                 const double lse = static_cast<double>(st.m) + log(static_cast<double>(st.s));
                 const double L = (Sulogu - Sup) / Su - log(Su) + lse;  // Su == 0 (eps 0, nothing pasted) -> NaN
-                kl = static_cast<float>(L * static_cast<double>(w));
+                kl = L * static_cast<double>(w);
             }
-            a.map_vals[map] = mse;
-            a.map_vals[a.n_maps + map] = kl;
+            s_map[0][g] = mse;
+            s_map[1][g] = kl;
         }
     }
-
-    if (last_block_arrives(&a.ws->counter, gridDim.x)) {
-        const volatile float* mv = a.map_vals;
-        double acc_m = 0.0, acc_k = 0.0;
-        for (int i = threadIdx.x; i < a.n_maps; i += TPM * MPB) {
-            acc_m += static_cast<double>(mv[i]);
-            acc_k += static_cast<double>(mv[a.n_maps + i]);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int n_here = min(MPB, a.n_maps - static_cast<int>(blockIdx.x) * MPB);
+        for (int w = 0; w < n_here; ++w) {
+            if (want_mse) block_loss_add(&s_loss, 0, s_map[0][w]);
+            if (want_kl) block_loss_add(&s_loss, 1, s_map[1][w]);
         }
-        s_red[threadIdx.x] = acc_m;
-        __syncthreads();
-        for (int o = (TPM * MPB) / 2; o > 0; o >>= 1) {
-            if (threadIdx.x < o) s_red[threadIdx.x] += s_red[threadIdx.x + o];
-            __syncthreads();
-        }
-        const double mse_sum = s_red[0];
-        __syncthreads();
-        s_red[threadIdx.x] = acc_k;
-        __syncthreads();
-        for (int o = (TPM * MPB) / 2; o > 0; o >>= 1) {
-            if (threadIdx.x < o) s_red[threadIdx.x] += s_red[threadIdx.x + o];
-            __syncthreads();
-        }
-        const double kl_sum = s_red[0];
-        if (threadIdx.x == 0) {
-            volatile int* cnt = a.ws->counts;
-            double* P = a.partial;
-            P[0] = (a.accumulate ? P[0] : 0.0) + mse_sum;
-            P[1] = (a.accumulate ? P[1] : 0.0) + kl_sum;
-            P[2] = (a.accumulate ? P[2] : 0.0) + static_cast<double>(a.n_maps);
-            P[3] = (a.accumulate ? P[3] : 0.0) + static_cast<double>(a.n_maps) * static_cast<double>(HW);
-            for (int k = 0; k < 2 * a.K; ++k) {
-                P[4 + k] = (a.accumulate ? P[4 + k] : 0.0) + static_cast<double>(cnt[k]);
-                cnt[k] = 0;
-            }
-            if (a.result) pipeline_result_from_partial(P, a.K, a.result);
-            a.ws->counter = 0;
-        }
+        block_loss_flush(&s_loss, a.ws);
+    }
+    if (pipeline_last_block(a.ws)) {
+        if (threadIdx.x == 0) pipeline_publish(a);
     }
 }
 
-__global__ void pipeline_finalize_kernel(const double* __restrict__ partial, int K, double* __restrict__ result) {
+__global__ void pipeline_finalize_kernel(const long long* __restrict__ partial, int K, double* __restrict__ result) {
     if (blockIdx.x == 0 && threadIdx.x == 0) pipeline_result_from_partial(partial, K, result);
 }
 
@@ -269,63 +198,77 @@ struct PipeLaunch {
     template <int TPM, int NV, int MODE, int MPB>
     void run() const {
         const int grid = (a.n_maps + MPB - 1) / MPB;
-        pipeline_kernel<TPM, NV, MODE, MPB><<<grid, TPM * MPB, table_bytes(a.tmp), stream>>>(a);
+        pipeline_generic_kernel<TPM, NV, MODE, MPB><<<grid, TPM * MPB, table_bytes(a.tmp), stream>>>(a);
     }
 };
 
+static int g_sm_count = 0;
+
 static int launch_pipeline(const float* pred, const double* joints, const float* vis, int B, int K, int H, int W,
                            double stride_x, double stride_y, int tmp, const float* tab, float kl_epsilon, double thr,
-                           int loss_mask, float* pred_xy, float* maxvals, float* weight_out, double* partial,
-                           int accumulate, double* result, void* workspace, int ws_maps, cudaStream_t stream) {
-    PipeArgs a{};
-    a.pred = pred; a.joints = joints; a.vis = vis; a.n_maps = B * K; a.K = K; a.H = H; a.W = W;
-    a.wdiv = FastDiv(static_cast<uint32_t>(W)); a.sx = stride_x; a.sy = stride_y; a.tmp = tmp; a.tab = tab;
-    a.eps = kl_epsilon; a.thr = thr; a.loss_mask = loss_mask; a.pred_xy = pred_xy; a.maxvals = maxvals;
-    a.weight_out = weight_out; a.partial = partial; a.accumulate = accumulate; a.result = result;
-    a.ws = static_cast<Workspace*>(workspace);
-    a.map_vals = reinterpret_cast<float*>(static_cast<char*>(workspace) + (sizeof(Workspace) + 255) / 256 * 256);
-    (void)ws_maps;
+                           int loss_mask, float* pred_xy, float* maxvals, float* weight_out, long long* partial,
+                           int accumulate, double* result, void* workspace, cudaStream_t stream) {
     const int HW = H * W, side = 2 * tmp + 1;
-    // fast shape: one warp per map, register-tile streaming (hp_pipeline_stream.cuh)
-    const bool stream_ok = aligned16(pred) && (W % 4 == 0) && (HW % 256 == 0) && HW < (1 << 24) &&
-                           side * side <= 32 * kStreamMaxPatch && (sizeof(Workspace) + 255) / 256 * 256 +
-                           sizeof(double) * 2 * ((a.n_maps + kStreamWarps - 1) / kStreamWarps) <=
-                           hp_workspace_bytes(a.n_maps, K);
-    if (stream_ok) {
-        StreamArgs sa{};
-        sa.pred = pred; sa.joints = joints; sa.vis = vis; sa.n_maps = a.n_maps; sa.K = K; sa.H = H; sa.W = W; sa.HW = HW;
-        sa.wdiv = a.wdiv; sa.sdiv = FastDiv(static_cast<uint32_t>(side));
-        sa.sx = stride_x; sa.sy = stride_y; sa.inv_sx = 1.0 / stride_x; sa.inv_sy = 1.0 / stride_y;
-        int ex = 0, ey = 0;
-        sa.pow2_stride = (std::frexp(stride_x, &ex) == 0.5 && std::frexp(stride_y, &ey) == 0.5) ? 1 : 0;
-        sa.tmp = tmp; sa.tab = tab; sa.eps = kl_epsilon;
-        sa.eps_log_eps = kl_epsilon > 0.0f ? static_cast<float>(static_cast<double>(kl_epsilon) * std::log(static_cast<double>(kl_epsilon))) : 0.0f;
-        sa.thr = thr;
-        const double t2 = thr * thr;
-        sa.thr2_lo = static_cast<float>(t2 * (1.0 - 1e-4)); sa.thr2_hi = static_cast<float>(t2 * (1.0 + 1e-4));
-        sa.inv_nx = static_cast<float>(10.0 / H); sa.inv_ny = static_cast<float>(10.0 / W);  // norm = (H/10, W/10) on (x, y)
-        sa.pred_xy = pred_xy; sa.maxvals = maxvals; sa.weight_out = weight_out; sa.partial = partial;
-        sa.accumulate = accumulate; sa.result = result; sa.ws = a.ws;
-        sa.cta_vals = reinterpret_cast<double*>(a.map_vals);
-        const int grid = (a.n_maps + kStreamWarps - 1) / kStreamWarps;
-        const size_t smem = table_bytes(tmp);
-        const bool big = (HW % 1024) == 0;
-        sa.ntiles = HW / (big ? 1024 : 256);
-#define HP_STREAM_LAUNCH(NVV, LM) pipeline_stream_kernel<NVV, LM><<<grid, 32 * kStreamWarps, smem, stream>>>(sa)
-#define HP_STREAM_BY_LOSS(NVV)                                  \
-        switch (loss_mask) {                                    \
-            case 0: HP_STREAM_LAUNCH(NVV, 0); break;            \
-            case HP_LOSS_MSE: HP_STREAM_LAUNCH(NVV, 1); break;  \
-            case HP_LOSS_KL: HP_STREAM_LAUNCH(NVV, 2); break;   \
-            default: HP_STREAM_LAUNCH(NVV, 3); break;           \
+    PipeArgs a{};
+    a.pred = pred; a.joints = joints; a.vis = vis; a.n_maps = B * K; a.K = K; a.H = H; a.W = W; a.HW = HW;
+    a.wdiv = FastDiv(static_cast<uint32_t>(W)); a.sdiv = FastDiv(static_cast<uint32_t>(side));
+    a.sx = stride_x; a.sy = stride_y; a.inv_sx = 1.0 / stride_x; a.inv_sy = 1.0 / stride_y;
+    int ex = 0, ey = 0;
+    a.pow2_stride = (std::frexp(stride_x, &ex) == 0.5 && std::frexp(stride_y, &ey) == 0.5) ? 1 : 0;
+    a.tmp = tmp; a.tab = tab; a.eps = kl_epsilon;
+    a.eps_log_eps = kl_epsilon > 0.0f
+                        ? static_cast<float>(static_cast<double>(kl_epsilon) * std::log(static_cast<double>(kl_epsilon)))
+                        : 0.0f;
+    a.thr = thr;
+    const double t2 = thr * thr;
+    a.thr2_lo = static_cast<float>(t2 * (1.0 - 1e-4)); a.thr2_hi = static_cast<float>(t2 * (1.0 + 1e-4));
+    a.inv_nx = static_cast<float>(10.0 / H); a.inv_ny = static_cast<float>(10.0 / W);  // norm = (H/10, W/10) on (x, y)
+    a.loss_mask = loss_mask; a.pred_xy = pred_xy; a.maxvals = maxvals; a.weight_out = weight_out;
+    a.partial = partial; a.accumulate = accumulate; a.result = result; a.ws = static_cast<Workspace*>(workspace);
+
+    const bool fast_ok = aligned16(pred) && (W % 4 == 0) && HW < (1 << 24) && side * side <= 32 * kCoopMaxPatch &&
+                         thr > 0.0;
+    const size_t smem = table_bytes(tmp);
+#define HP_BY_LOSS(KERNEL, GRID, ...)                                                            \
+    switch (loss_mask) {                                                                         \
+        case 0: KERNEL<__VA_ARGS__, 0><<<GRID, 128, smem, stream>>>(a); break;                   \
+        case HP_LOSS_MSE: KERNEL<__VA_ARGS__, 1><<<GRID, 128, smem, stream>>>(a); break;         \
+        case HP_LOSS_KL: KERNEL<__VA_ARGS__, 2><<<GRID, 128, smem, stream>>>(a); break;          \
+        default: KERNEL<__VA_ARGS__, 3><<<GRID, 128, smem, stream>>>(a); break;                  \
+    }
+    if (fast_ok && (HW == 4096 || HW == 1024)) {
+        // cooperative persistent shape: 4 blocks of 4 warps per SM, each block strides over the maps
+        if (g_sm_count == 0) {
+            g_sm_count = hp_device_sm_count();
+            if (g_sm_count <= 0) g_sm_count = 148;
         }
-        if (big) { HP_STREAM_BY_LOSS(8) } else { HP_STREAM_BY_LOSS(2) }
-#undef HP_STREAM_BY_LOSS
-#undef HP_STREAM_LAUNCH
+        static const int minb = []() {
+            const char* e = std::getenv("HP_COOP_BLOCKS_PER_SM");  // tuning knob: 3 (168 regs) or 4 (128 regs)
+            return (e && e[0] == '3') ? 3 : 4;
+        }();
+        int grid = g_sm_count * minb;
+        if (grid > a.n_maps) grid = a.n_maps;
+        if (HW == 4096) {
+            if (minb == 3) { HP_BY_LOSS(pipeline_coop3_kernel, grid, 8) } else { HP_BY_LOSS(pipeline_coop4_kernel, grid, 8) }
+        } else {
+            if (minb == 3) { HP_BY_LOSS(pipeline_coop3_kernel, grid, 2) } else { HP_BY_LOSS(pipeline_coop4_kernel, grid, 2) }
+        }
         return launch_status("hp_pipeline_fused");
     }
+    if (fast_ok && (HW % 256 == 0)) {
+        const int grid = (a.n_maps + kStreamWarps - 1) / kStreamWarps;
+        if (HW % 1024 == 0) {
+            a.ntiles = HW / 1024;
+            HP_BY_LOSS(pipeline_stream_kernel, grid, 8)
+        } else {
+            a.ntiles = HW / 256;
+            HP_BY_LOSS(pipeline_stream_kernel, grid, 2)
+        }
+        return launch_status("hp_pipeline_fused");
+    }
+#undef HP_BY_LOSS
     PipeLaunch l{a, stream};
-    dispatch_map_walk(H * W, aligned16(pred) && (W % 4 == 0), l);
+    dispatch_map_walk(HW, aligned16(pred) && (W % 4 == 0), l);
     return launch_status("hp_pipeline_fused");
 }
 
@@ -350,20 +293,21 @@ using namespace hp;
 extern "C" HP_API int hp_pipeline_fused(const float* pred, const double* joints, const float* vis, int B, int K, int H,
                                         int W, double stride_x, double stride_y, int tmp, const float* tab,
                                         float kl_epsilon, double thr, int loss_mask, float* pred_xy, float* maxvals,
-                                        float* weight_out, double* partial, int accumulate, double* result,
+                                        float* weight_out, int64_t* partial, int accumulate, double* result,
                                         void* workspace, hp_stream_t stream) {
     if (int rc = check_pipeline("hp_pipeline_fused", pred, joints, vis, B, K, H, W, stride_x, stride_y, tmp, tab, pred_xy,
                                 partial, workspace, loss_mask))
         return rc;
     return launch_pipeline(pred, joints, vis, B, K, H, W, stride_x, stride_y, tmp, tab, kl_epsilon, thr, loss_mask,
-                           pred_xy, maxvals, weight_out, partial, accumulate, result, workspace, B * K,
-                           static_cast<cudaStream_t>(stream));
+                           pred_xy, maxvals, weight_out, reinterpret_cast<long long*>(partial), accumulate, result,
+                           workspace, static_cast<cudaStream_t>(stream));
 }
 
-extern "C" HP_API int hp_pipeline_finalize(const double* partial, int K, double* result, hp_stream_t stream) {
+extern "C" HP_API int hp_pipeline_finalize(const int64_t* partial, int K, double* result, hp_stream_t stream) {
     HP_REQUIRE(partial && result, HP_ERR_NULL, "hp_pipeline_finalize: null pointer");
     HP_REQUIRE(K > 0 && K <= HP_MAX_K, HP_ERR_SHAPE, "hp_pipeline_finalize: K=%d", K);
-    pipeline_finalize_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(partial, K, result);
+    pipeline_finalize_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const long long*>(partial),
+                                                                              K, result);
     return launch_status("hp_pipeline_finalize");
 }
 
@@ -371,7 +315,7 @@ extern "C" HP_API int hp_pipeline_fused_host(const float* h_pred, const double* 
                                              int K, int H, int W, double stride_x, double stride_y, int tmp,
                                              const float* tab, float kl_epsilon, double thr, int loss_mask, int slab_B,
                                              float* d_pred, double* d_joints, float* d_vis, float* d_pred_xy,
-                                             float* d_maxvals, float* d_weight, double* d_partial, double* d_result,
+                                             float* d_maxvals, float* d_weight, int64_t* d_partial, double* d_result,
                                              void* workspace, float* h_pred_xy, double* h_result, hp_stream_t stream,
                                              hp_stream_t copy_stream) {
     if (int rc = check_pipeline("hp_pipeline_fused_host", h_pred, h_joints, h_vis, B, K, H, W, stride_x, stride_y, tmp,
@@ -411,8 +355,9 @@ extern "C" HP_API int hp_pipeline_fused_host(const float* h_pred, const double* 
                              H, W, stride_x, stride_y, tmp, tab, kl_epsilon, thr, loss_mask,
                              d_pred_xy + 2 * static_cast<size_t>(b0) * K,
                              d_maxvals ? d_maxvals + static_cast<size_t>(b0) * K : nullptr,
-                             d_weight ? d_weight + static_cast<size_t>(b0) * K : nullptr, d_partial, s > 0 ? 1 : 0,
-                             last ? d_result : nullptr, workspace, nb * K, cs);
+                             d_weight ? d_weight + static_cast<size_t>(b0) * K : nullptr,
+                             reinterpret_cast<long long*>(d_partial), s > 0 ? 1 : 0, last ? d_result : nullptr, workspace,
+                             cs);
         if (rc == HP_OK) e = cudaEventRecord(drained[slot], cs);
     }
     if (e == cudaSuccess && rc == HP_OK)

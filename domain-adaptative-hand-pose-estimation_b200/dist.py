@@ -1,10 +1,11 @@
 """Batch sharding across the GPUs of one box + the single collective of the hot path.
 
 Every stage is independent per sample, so ranks own contiguous slices of the batch
-and exchange nothing until the end: ONE all-reduce(sum) of the float64 partial vector
-``[mse_sum, kl_sum, n_maps, n_elems, hits[K], valid[K]]`` (4+2K doubles = 368 B at K=21; integer
-counts < 2^53 are exact in float64), after which every rank finalises exactly what
-``accuracy()`` / ``loss.mean()`` would give on the concatenated batch.  NCCL over NVLink on the
+and exchange nothing until the end: ONE all-reduce(sum) of the int64 partial vector
+``[mse_fx, kl_fx, n_maps, n_elems, hits[K], valid[K], 6 non-finite counters]`` (4+2K+6 int64 = 416 B
+at K=21; the loss sums are fixed point, value * 2**40, so the sum over ranks is exact and order
+independent), after which every rank finalises exactly what ``accuracy()`` / ``loss.mean()`` would
+give on the concatenated batch.  NCCL over NVLink on the
 GPUs; the same code runs on ``gloo`` for the CPU tests of the host logic.
 """
 from __future__ import annotations
@@ -32,13 +33,44 @@ def allreduce_partial(partial: torch.Tensor, group=None) -> torch.Tensor:
     return partial
 
 
+FX_SHIFT = 40                    # HP_LOSS_FX_SHIFT of include/hp_b200.h
+FX_LIMIT = 2097152.0             # |per-map loss| >= 2**21 counts as infinite
+
+
+def partial_len(K: int) -> int:
+    """HP_PARTIAL_LEN(K)."""
+    return 4 + 2 * K + 6
+
+
+def loss_to_fx(values):
+    """Per-map float losses -> (fixed-point int64 sum, [n_nan, n_pinf, n_ninf]) exactly like the kernels."""
+    v = np.asarray(values, dtype=np.float64).ravel()
+    nan = np.isnan(v)
+    pinf = ~nan & (v >= FX_LIMIT)
+    ninf = ~nan & (v <= -FX_LIMIT)
+    fin = ~(nan | pinf | ninf)
+    fx = np.rint(np.ldexp(v[fin], FX_SHIFT)).astype(np.int64).sum()
+    return int(fx), [int(nan.sum()), int(pinf.sum()), int(ninf.sum())]
+
+
+def _loss_from_fx(fx, n_nan, n_pinf, n_ninf, n_maps):
+    if n_nan or (n_pinf and n_ninf):
+        return float("nan")
+    if n_pinf:
+        return float("inf")
+    if n_ninf:
+        return float("-inf")
+    return float(np.ldexp(np.float64(fx), -FX_SHIFT) / np.float64(n_maps))
+
+
 def finalize_partial_host(partial, K: int):
-    """Host mirror of ``hp_pipeline_finalize`` for a partial vector already on the host:
-    -> dict(mse, kl, avg_acc, cnt, acc[K]).  Same order of float64 operations as
+    """Host mirror of ``hp_pipeline_finalize`` for an int64 partial vector already on the host:
+    -> dict(mse, kl, avg_acc, cnt, acc[K], hits, valid).  Same order of float64 operations as
     utils/keypoint_detection.py:53-60, 80-90."""
-    p = np.asarray(partial, dtype=np.float64)
+    p = np.asarray(partial, dtype=np.int64)
     hits = p[4:4 + K].astype(np.int64)
     valid = p[4 + K:4 + 2 * K].astype(np.int64)
+    cls = p[4 + 2 * K:4 + 2 * K + 6]
     acc = np.full(K, -1.0)
     total, cnt = 0.0, 0
     for k in range(K):
@@ -47,5 +79,5 @@ def finalize_partial_host(partial, K: int):
         if acc[k] >= 0:
             total = total + acc[k]
             cnt += 1
-    return dict(mse=p[0] / p[2], kl=p[1] / p[2], avg_acc=(total / cnt if cnt != 0 else 0.0), cnt=cnt, acc=acc,
-                hits=hits, valid=valid)
+    return dict(mse=_loss_from_fx(p[0], cls[0], cls[1], cls[2], p[2]), kl=_loss_from_fx(p[1], cls[3], cls[4], cls[5], p[2]),
+                avg_acc=(total / cnt if cnt != 0 else 0.0), cnt=cnt, acc=acc, hits=hits, valid=valid)

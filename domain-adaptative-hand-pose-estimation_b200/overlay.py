@@ -132,7 +132,7 @@ def install(ref_root: str, verbose: bool = False):
 
 def main(argv=None):
     argv = list(sys.argv[1:] if argv is None else argv)
-    ref = os.environ.get("HP_REF_DIR", "/root/reference")
+    ref = os.environ.get("HP_REF_DIR")
     verbose = False
     while argv and argv[0].startswith("--"):
         if argv[0] == "--ref" and len(argv) > 1:
@@ -143,8 +143,9 @@ def main(argv=None):
             argv = argv[1:]
         else:
             break
-    if not argv:
+    if not argv or ref is None:
         print(__doc__)
+        print("error: give the reference tree with --ref DIR or HP_REF_DIR", file=sys.stderr)
         return 2
     script = argv[0] if os.path.isabs(argv[0]) else os.path.join(ref, argv[0])
     install(ref, verbose=verbose)

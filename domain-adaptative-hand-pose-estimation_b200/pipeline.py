@@ -28,7 +28,8 @@ _LOSS_BITS = {"mse": _lib.LOSS_MSE, "kl": _lib.LOSS_KL}
 class PipelineResult:
     """Device-resident outputs; ``host()`` does the one small device->host read."""
     result: torch.Tensor      # float64 [4+K] = mse, kl, avg_acc, cnt, acc[K]
-    partial: torch.Tensor     # float64 [4+2K] = mse_sum, kl_sum, n_maps, n_elems, hits[K], valid[K]
+    partial: torch.Tensor     # int64 [4+2K+6] = mse_fx, kl_fx, n_maps, n_elems, hits[K], valid[K], 6 non-finite counters
+    #                           (loss sums are fixed point, value * 2**40: exact under any schedule / sharding)
     pred_xy: torch.Tensor     # float32 [B,K,2]
     maxvals: torch.Tensor     # float32 [B,K,1]
     weight: torch.Tensor      # float32 [B,K,1]  (target_weight of generate_target)
@@ -148,7 +149,7 @@ class HeatmapPipeline:
         K = self.K
         return PipelineResult(
             result=torch.empty((4 + K,), dtype=torch.float64, device=dev),
-            partial=torch.empty((4 + 2 * K,), dtype=torch.float64, device=dev),
+            partial=torch.empty((hpdist.partial_len(K),), dtype=torch.int64, device=dev),
             pred_xy=torch.empty((B, K, 2), dtype=torch.float32, device=dev),
             maxvals=torch.empty((B, K, 1), dtype=torch.float32, device=dev),
             weight=torch.empty((B, K, 1), dtype=torch.float32, device=dev), K=K)
@@ -210,7 +211,7 @@ class HeatmapPipeline:
                 d_xy=torch.empty((B, K, 2), dtype=torch.float32, device=dev),
                 d_max=torch.empty((B, K), dtype=torch.float32, device=dev),
                 d_w=torch.empty((B, K), dtype=torch.float32, device=dev),
-                d_partial=torch.empty((4 + 2 * K,), dtype=torch.float64, device=dev),
+                d_partial=torch.empty((hpdist.partial_len(K),), dtype=torch.int64, device=dev),
                 d_result=torch.empty((4 + K,), dtype=torch.float64, device=dev),
                 h_xy=torch.empty((B, K, 2), dtype=torch.float32).pin_memory(),
                 h_result=torch.empty((4 + K,), dtype=torch.float64).pin_memory(),

@@ -50,6 +50,8 @@ typedef void* hp_stream_t; /* cudaStream_t */
 /* loss selection bits for hp_pipeline_fused */
 #define HP_LOSS_MSE      1
 #define HP_LOSS_KL       2
+#define HP_PARTIAL_LEN(K) (4 + 2 * (K) + 6) /* int64 elements of the pipeline partial vector */
+#define HP_LOSS_FX_SHIFT 40 /* fixed-point scale of the loss sums: value * 2^40 */
 
 /* pseudo-label variants (centre = decoded coordinate >> shift, on an oh x ow map) */
 #define HP_PLG_BASE      0 /* PseudoLabelGenerator   uda/model/regda_4.py:17-86 : gf = clip(sum_{j!=k} gt_j) */
@@ -166,7 +168,10 @@ int hp_fuse_decode_pck(const float* lo, int hl, int wl, float a_lo,
  * registers and never written.
  *   pred [B,K,H,W] ; joints float64 [B*K,2] ; vis float32 [B*K]
  *   pred_xy [B*K,2], maxvals [B*K], weight_out [B*K]           (per-map outputs)
- *   partial float64 [4 + 2K] = { mse_sum, kl_sum, n_maps, n_elems, hits[K], valid[K] }
+ *   partial int64 [4 + 2K + 6] = { mse_fx, kl_fx, n_maps, n_elems, hits[K], valid[K],
+ *                                  mse_nan, mse_pinf, mse_ninf, kl_nan, kl_pinf, kl_ninf }
+ *       loss sums are fixed point (value * 2^40): integer sums are associative, so any block
+ *       schedule, slab split or GPU sharding gives bit-identical results.
  *       (+= semantics when accumulate != 0: batch shards / ranks add up, then finalise)
  *   result float64 [4 + K] = { mse, kl, avg_acc, cnt, acc[K] }  (nullable: skip finalise)
  */
@@ -174,10 +179,10 @@ int hp_pipeline_fused(const float* pred, const double* joints, const float* vis,
                       int B, int K, int H, int W, double stride_x, double stride_y, int tmp,
                       const float* tab, float kl_epsilon, double thr, int loss_mask,
                       float* pred_xy, float* maxvals, float* weight_out,
-                      double* partial, int accumulate, double* result, void* workspace,
+                      int64_t* partial, int accumulate, double* result, void* workspace,
                       hp_stream_t stream);
 /* partial (e.g. after an NCCL all-reduce over ranks) -> result, on device */
-int hp_pipeline_finalize(const double* partial, int K, double* result, hp_stream_t stream);
+int hp_pipeline_finalize(const int64_t* partial, int K, double* result, hp_stream_t stream);
 
 /* Host-buffer form (end-to-end path): h_* are pinned host arrays; the batch is cut into slabs
  * of slab_B samples whose H2D copies (copy_stream) overlap the kernels (stream); device
@@ -187,7 +192,7 @@ int hp_pipeline_fused_host(const float* h_pred, const double* h_joints, const fl
                            const float* tab, float kl_epsilon, double thr, int loss_mask,
                            int slab_B, float* d_pred, double* d_joints, float* d_vis,
                            float* d_pred_xy, float* d_maxvals, float* d_weight,
-                           double* d_partial, double* d_result, void* workspace,
+                           int64_t* d_partial, double* d_result, void* workspace,
                            float* h_pred_xy /*nullable*/, double* h_result,
                            hp_stream_t stream, hp_stream_t copy_stream);
 

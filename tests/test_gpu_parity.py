@@ -87,7 +87,7 @@ def test_pipeline_matches_oracle(size, B, seed):
     assert np.array_equal(got["acc"], want["acc"]) and got["avg_acc"] == want["avg_acc"] and got["cnt"] == want["cnt"]
     np.testing.assert_allclose(got["mse"], want["mse"], rtol=1e-5)
     np.testing.assert_allclose(got["kl"], want["kl"], rtol=1e-5)
-    assert part[2] == B * 21 and part[3] == B * 21 * size * size
+    assert part.dtype == np.int64 and part[2] == B * 21 and part[3] == B * 21 * size * size
 
 
 def test_pipeline_kl_eps0_is_nan_like_reference():
