@@ -42,7 +42,8 @@ extern "C" HP_API int hp_device_sm_count(void) {
 
 extern "C" HP_API size_t hp_workspace_bytes(int n_maps, int K) {
     (void)K;
-    // Workspace header + one float64 partial slot per map for deterministic fixed-order sums
+    // Workspace header, then per map: one arrival counter and up to four 32-byte tile statistics
+    // (hp_pipeline_tiles.cuh), each region 256-byte aligned
     const size_t n = n_maps > 0 ? static_cast<size_t>(n_maps) : 0;
-    return sizeof(hp::Workspace) + 256 + 2 * sizeof(double) * n;
+    return sizeof(hp::Workspace) + 3 * 256 + n * (4 + 4 * 32);
 }

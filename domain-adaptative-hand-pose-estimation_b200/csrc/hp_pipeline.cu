@@ -20,7 +20,7 @@
 #include "hp_common.cuh"
 #include "hp_dispatch.cuh"
 #include "hp_pipeline_common.cuh"
-#include "hp_pipeline_coop.cuh"
+#include "hp_pipeline_tiles.cuh"
 #include "hp_pipeline_stream.cuh"
 
 namespace hp {
@@ -183,9 +183,7 @@ __global__ void __launch_bounds__(TPM* MPB) pipeline_generic_kernel(const PipeAr
         }
         block_loss_flush(&s_loss, a.ws);
     }
-    if (pipeline_last_block(a.ws)) {
-        if (threadIdx.x == 0) pipeline_publish(a);
-    }
+    if (pipeline_last_block(a.ws)) pipeline_publish(a);
 }
 
 __global__ void pipeline_finalize_kernel(const long long* __restrict__ partial, int K, double* __restrict__ result) {
@@ -226,43 +224,42 @@ static int launch_pipeline(const float* pred, const double* joints, const float*
     a.loss_mask = loss_mask; a.pred_xy = pred_xy; a.maxvals = maxvals; a.weight_out = weight_out;
     a.partial = partial; a.accumulate = accumulate; a.result = result; a.ws = static_cast<Workspace*>(workspace);
 
-    const bool fast_ok = aligned16(pred) && (W % 4 == 0) && HW < (1 << 24) && side * side <= 32 * kCoopMaxPatch &&
+    const bool fast_ok = aligned16(pred) && (W % 4 == 0) && HW < (1 << 24) && side * side <= 32 * kTileMaxPatch &&
                          thr > 0.0;
     const size_t smem = table_bytes(tmp);
-#define HP_BY_LOSS(KERNEL, GRID, ...)                                                            \
+#define HP_BY_LOSS(KERNEL, GRID, ARG, NVV)                                                       \
     switch (loss_mask) {                                                                         \
-        case 0: KERNEL<__VA_ARGS__, 0><<<GRID, 128, smem, stream>>>(a); break;                   \
-        case HP_LOSS_MSE: KERNEL<__VA_ARGS__, 1><<<GRID, 128, smem, stream>>>(a); break;         \
-        case HP_LOSS_KL: KERNEL<__VA_ARGS__, 2><<<GRID, 128, smem, stream>>>(a); break;          \
-        default: KERNEL<__VA_ARGS__, 3><<<GRID, 128, smem, stream>>>(a); break;                  \
+        case 0: KERNEL<NVV, 0><<<GRID, 128, smem, stream>>>(ARG); break;                         \
+        case HP_LOSS_MSE: KERNEL<NVV, 1><<<GRID, 128, smem, stream>>>(ARG); break;               \
+        case HP_LOSS_KL: KERNEL<NVV, 2><<<GRID, 128, smem, stream>>>(ARG); break;                \
+        default: KERNEL<NVV, 3><<<GRID, 128, smem, stream>>>(ARG); break;                        \
     }
-    if (fast_ok && (HW == 4096 || HW == 1024)) {
-        // cooperative persistent shape: 4 blocks of 4 warps per SM, each block strides over the maps
-        if (g_sm_count == 0) {
-            g_sm_count = hp_device_sm_count();
-            if (g_sm_count <= 0) g_sm_count = 148;
-        }
-        static const int minb = []() {
-            const char* e = std::getenv("HP_COOP_BLOCKS_PER_SM");  // tuning knob: 3 (168 regs) or 4 (128 regs)
-            return (e && e[0] == '3') ? 3 : 4;
-        }();
-        int grid = g_sm_count * minb;
-        if (grid > a.n_maps) grid = a.n_maps;
-        if (HW == 4096) {
-            if (minb == 3) { HP_BY_LOSS(pipeline_coop3_kernel, grid, 8) } else { HP_BY_LOSS(pipeline_coop4_kernel, grid, 8) }
+    const int tile_elems = (HW % 1024 == 0) ? 1024 : ((HW % 256 == 0) ? 256 : 0);
+    if (fast_ok && tile_elems != 0) {
+        const int tpm = HW / tile_elems;
+        if (tpm <= kTilesMaxPerMap) {
+            // tile-granular persistent shape: 4 blocks of 4 warps per SM, static stride over the tiles
+            if (g_sm_count == 0) {
+                g_sm_count = hp_device_sm_count();
+                if (g_sm_count <= 0) g_sm_count = 148;
+            }
+            TileArgs t{};
+            t.p = a;
+            t.tiles_per_map = tpm;
+            t.n_tiles = a.n_maps * tpm;
+            t.tdiv = FastDiv(static_cast<uint32_t>(tpm));
+            char* tail = static_cast<char*>(workspace) + (sizeof(Workspace) + 255) / 256 * 256;
+            t.arrivals = reinterpret_cast<unsigned int*>(tail);
+            t.stats = reinterpret_cast<TileStat*>(tail + (static_cast<size_t>(a.n_maps) * 4 + 255) / 256 * 256);
+            int grid = g_sm_count * 4;
+            const int need = (t.n_tiles + kTileWarps - 1) / kTileWarps;
+            if (grid > need) grid = need;
+            if (tile_elems == 1024) { HP_BY_LOSS(pipeline_tiles_kernel, grid, t, 8) } else { HP_BY_LOSS(pipeline_tiles_kernel, grid, t, 2) }
         } else {
-            if (minb == 3) { HP_BY_LOSS(pipeline_coop3_kernel, grid, 2) } else { HP_BY_LOSS(pipeline_coop4_kernel, grid, 2) }
-        }
-        return launch_status("hp_pipeline_fused");
-    }
-    if (fast_ok && (HW % 256 == 0)) {
-        const int grid = (a.n_maps + kStreamWarps - 1) / kStreamWarps;
-        if (HW % 1024 == 0) {
-            a.ntiles = HW / 1024;
-            HP_BY_LOSS(pipeline_stream_kernel, grid, 8)
-        } else {
-            a.ntiles = HW / 256;
-            HP_BY_LOSS(pipeline_stream_kernel, grid, 2)
+            // many tiles per map (128x128 ...): one warp streams a whole map
+            const int grid = (a.n_maps + kStreamWarps - 1) / kStreamWarps;
+            a.ntiles = tpm;
+            if (tile_elems == 1024) { HP_BY_LOSS(pipeline_stream_kernel, grid, a, 8) } else { HP_BY_LOSS(pipeline_stream_kernel, grid, a, 2) }
         }
         return launch_status("hp_pipeline_fused");
     }

@@ -128,25 +128,61 @@ __device__ __forceinline__ void pipeline_result_from_partial(const long long* p,
     result[3] = acc[K + 1];
 }
 
-// last block, one thread: workspace -> partial (= or +=), workspace back to zero, optional finalise
+// last block, ALL threads: workspace -> partial (= or +=), workspace back to zero, optional finalise.
+// One thread per slot so the ~50 counters cost one L2 round trip instead of fifty dependent ones
+// (the single-thread version of this was a constant ~20 us tail on every launch, see profiles/).
 __device__ __forceinline__ void pipeline_publish(const PipeArgs& a) {
-    volatile int* cnt = a.ws->counts;
-    volatile unsigned long long* acc = a.ws->acc;
-    long long* P = a.partial;
+    __shared__ long long s_p[4 + 2 * HP_MAX_K + 6];
+    __shared__ double s_acc[HP_MAX_K];
+    const int K = a.K, n = 4 + 2 * K + 6;
     const bool add = a.accumulate != 0;
-    const int K = a.K;
-    P[0] = (add ? P[0] : 0) + static_cast<long long>(acc[0]);
-    P[1] = (add ? P[1] : 0) + static_cast<long long>(acc[1]);
-    P[2] = (add ? P[2] : 0) + a.n_maps;
-    P[3] = (add ? P[3] : 0) + static_cast<long long>(a.n_maps) * a.HW;
-    for (int k = 0; k < 2 * K; ++k) {
-        P[4 + k] = (add ? P[4 + k] : 0) + cnt[k];
-        cnt[k] = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        long long v;
+        if (i < 2) {
+            v = static_cast<long long>(*reinterpret_cast<volatile unsigned long long*>(&a.ws->acc[i]));
+            a.ws->acc[i] = 0;
+        } else if (i == 2) {
+            v = a.n_maps;
+        } else if (i == 3) {
+            v = static_cast<long long>(a.n_maps) * a.HW;
+        } else if (i < 4 + 2 * K) {
+            v = *reinterpret_cast<volatile int*>(&a.ws->counts[i - 4]);
+            a.ws->counts[i - 4] = 0;
+        } else {
+            const int j = 2 + (i - 4 - 2 * K);
+            v = static_cast<long long>(*reinterpret_cast<volatile unsigned long long*>(&a.ws->acc[j]));
+            a.ws->acc[j] = 0;
+        }
+        if (add) v += a.partial[i];
+        a.partial[i] = v;
+        s_p[i] = v;
     }
-    for (int i = 0; i < 6; ++i) P[4 + 2 * K + i] = (add ? P[4 + 2 * K + i] : 0) + static_cast<long long>(acc[2 + i]);
-    for (int i = 0; i < 8; ++i) acc[i] = 0;
-    if (a.result) pipeline_result_from_partial(P, K, a.result);
-    a.ws->counter = 0;
+    __syncthreads();
+    if (a.result) {
+        // acc[k] = hits/valid or -1 in parallel; the ordered average over joints serially from shared memory
+        for (int k = threadIdx.x; k < K; k += blockDim.x) {
+            const long long h = s_p[4 + k], v = s_p[4 + K + k];
+            const double acc = v > 0 ? __ddiv_rn(static_cast<double>(h) * 1.0, static_cast<double>(v)) : -1.0;
+            s_acc[k] = acc;
+            a.result[4 + k] = acc;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double total = 0.0;
+            int cnt = 0;
+            for (int k = 0; k < K; ++k)
+                if (s_acc[k] >= 0.0) {
+                    total = __dadd_rn(total, s_acc[k]);
+                    ++cnt;
+                }
+            const long long* cls = s_p + 4 + 2 * K;
+            a.result[0] = loss_from_fx(s_p[0], cls[0], cls[1], cls[2], s_p[2]);
+            a.result[1] = loss_from_fx(s_p[1], cls[3], cls[4], cls[5], s_p[2]);
+            a.result[2] = cnt != 0 ? __ddiv_rn(total, static_cast<double>(cnt)) : 0.0;
+            a.result[3] = static_cast<double>(cnt);
+        }
+    }
+    if (threadIdx.x == 0) a.ws->counter = 0;
 }
 
 // "last block done": only thread 0 fences (it is the only writer of block-level results)
