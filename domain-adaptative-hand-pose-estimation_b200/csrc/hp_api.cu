@@ -42,8 +42,8 @@ extern "C" HP_API int hp_device_sm_count(void) {
 
 extern "C" HP_API size_t hp_workspace_bytes(int n_maps, int K) {
     (void)K;
-    // Workspace header, then per map: one arrival counter and up to four 32-byte tile statistics
-    // (hp_pipeline_tiles.cuh), each region 256-byte aligned
-    const size_t n = n_maps > 0 ? static_cast<size_t>(n_maps) : 0;
-    return sizeof(hp::Workspace) + 3 * 256 + n * (4 + 4 * 32);
+    // Workspace header (block counter, PCK counters, 64-bit loss accumulators) + slack; kernels that need
+    // per-map scratch keep it in shared memory
+    (void)n_maps;
+    return sizeof(hp::Workspace) + 1024;
 }

@@ -237,7 +237,7 @@ static int launch_pipeline(const float* pred, const double* joints, const float*
     const int tile_elems = (HW % 1024 == 0) ? 1024 : ((HW % 256 == 0) ? 256 : 0);
     if (fast_ok && tile_elems != 0) {
         const int tpm = HW / tile_elems;
-        if (tpm <= kTilesMaxPerMap) {
+        if (tpm == 1 || tpm == 2 || tpm == 4) {
             // tile-granular persistent shape: 4 blocks of 4 warps per SM, static stride over the tiles
             if (g_sm_count == 0) {
                 g_sm_count = hp_device_sm_count();
@@ -248,9 +248,8 @@ static int launch_pipeline(const float* pred, const double* joints, const float*
             t.tiles_per_map = tpm;
             t.n_tiles = a.n_maps * tpm;
             t.tdiv = FastDiv(static_cast<uint32_t>(tpm));
-            char* tail = static_cast<char*>(workspace) + (sizeof(Workspace) + 255) / 256 * 256;
-            t.arrivals = reinterpret_cast<unsigned int*>(tail);
-            t.stats = reinterpret_cast<TileStat*>(tail + (static_cast<size_t>(a.n_maps) * 4 + 255) / 256 * 256);
+            // static stride n_warps = 4*grid over the tiles: with tpm | 4 the warps of a block always hold the
+            // tiles of the same map(s) in the same iteration, which the shared-memory ring relies on
             int grid = g_sm_count * 4;
             const int need = (t.n_tiles + kTileWarps - 1) / kTileWarps;
             if (grid > need) grid = need;

@@ -1,14 +1,15 @@
 // hp_pipeline_tiles.cuh - the production shape of the fused gen+loss+decode+PCK kernel.
 //
 // Work quantum = one TILE of 128*NV consecutive elements of one map (4 KB at NV = 8: a quarter of a
-// 64x64 map, 1/16 of a 128x128 map, a whole 32x32 map).  Every WARP independently walks its tiles
-// (static stride over the global tile index, so the 4 warps of a block stream the 4 quarters of the same
-// map), double-buffered in registers so the next tile is always in flight, and publishes five numbers
-// per tile - max, first index of the max, sum exp (relative to the max), sum p, sum p^2 - to a small
-// global table, then bumps the map's arrival counter.  The warp that completes a map's LAST tile
-// ("last arriver closes the door") merges the tiles, re-reads the <=169 patch pixels (L2), builds the
-// target terms, decodes, scores PCK, closes MSE / KL and publishes.  No block barrier on the data path,
-// no warp ever waits for another warp, any grid size balances to within one 4 KB tile.
+// 64x64 map, a whole 32x32 map).  Every WARP independently walks its tiles with a static stride over
+// the global tile index - which makes the 4 warps of a block stream the 4 quarters of the SAME map -
+// double-buffered in registers so the next tile is always in flight, and leaves five numbers per tile
+// (max, first index of the max, sum exp relative to the max, sum p, sum p^2) in a shared-memory ring
+// slot, then bumps the slot's arrival counter (shared-memory atomic, block-scope fence: no global
+// fence or atomic on the data path).  The warp that delivers a map's LAST tile ("last arriver closes
+// the door") merges the tiles, re-reads the <=169 patch pixels (L2), builds the target terms, decodes,
+// scores PCK, closes MSE / KL and publishes.  No block barrier in the loop, no warp waits for another
+// warp (the ring is 8 maps deep), and the grid balances to within one 4 KB tile.
 //
 // How it got here (profiles/r1_pipeline_*.md):
 //   v1 block-per-map, target math in the hot loop ... 43 instructions/element, issue-bound (13 % of HBM)
@@ -18,6 +19,8 @@
 //                                                     scalar math at each barrier
 //   all three ....................................... a single-thread last-block epilogue with ~50 dependent
 //                                                     L2 round trips: a constant ~20 us tail
+//   v4 last arriver through GLOBAL counters ......... a __threadfence + atomic round trip per tile with 31
+//                                                     lanes parked at the reconvergence point (20 % issue)
 #pragma once
 #include "hp_pipeline_common.cuh"
 
@@ -27,19 +30,24 @@ constexpr int kTileWarps = 4;       // warps per block
 constexpr int kTilesMaxPerMap = 4;  // more tiles per map than this -> warp-per-map streaming instead
 constexpr int kTileMaxPatch = 6;    // patch pixels per lane of the closing warp: (2*tmp+1)^2 <= 192
 
-struct TileStat {  // 32 bytes, one per (map, tile)
+constexpr int kTileRing = 8;        // ring depth (maps in flight per block) of the shared-memory slots
+
+struct TileStat {  // what one warp leaves per tile
     float vmax;
     int idx;
     float s, sp, spp;
-    float pad[3];
 };
 
 struct TileArgs {
     PipeArgs p;
-    int tiles_per_map, n_tiles;
-    FastDiv tdiv;             // by tiles_per_map
-    TileStat* stats;          // [n_maps * tiles_per_map]   (workspace tail)
-    unsigned int* arrivals;   // [n_maps], zero on entry, zero on exit
+    int tiles_per_map, n_tiles;  // tiles_per_map in {1, 2, 4}: the warps of a block split into 4/tpm groups
+    FastDiv tdiv;                // by tiles_per_map
+};
+
+struct TileRing {
+    TileStat stat[kTileRing][kTileWarps];
+    unsigned int count[kTileRing][kTileWarps];  // arrivals per (slot, group)
+    unsigned int gen[kTileRing][kTileWarps];    // how many times (slot, group) has been closed
 };
 
 template <int NV>
@@ -115,8 +123,8 @@ __device__ __forceinline__ void warp_loss_add(WarpLoss& w, int which, double v) 
 
 // the closing warp: merge the map's tiles, patch terms, decode, PCK, losses, publish
 template <int LOSS>
-__device__ __forceinline__ void tile_close_map(const TileArgs& t, int map, const TileStat& mine, int my_tile, int lane,
-                                               const float* s_tab, WarpLoss& wl) {
+__device__ __forceinline__ void tile_close_map(const TileArgs& t, int map, const TileStat (&ts)[kTilesMaxPerMap],
+                                               int lane, const float* s_tab, WarpLoss& wl) {
     const PipeArgs& a = t.p;
     const float* pm = a.pred + static_cast<size_t>(map) * a.HW;
     float weight;
@@ -138,43 +146,25 @@ __device__ __forceinline__ void tile_close_map(const TileArgs& t, int map, const
             tv[k] = in ? s_tab[dx * dx + dy * dy] : 0.0f;
         }
     }
-    // merge: lane l takes tiles l, l+32, ... (other warps' rows come from L2, mine from registers)
-    ArgMax am{-INFINITY, 0x7fffffff};
-    float m_run = -INFINITY, s_run = 0.f, sp = 0.f, spp = 0.f;
-    const volatile TileStat* row = t.stats + static_cast<size_t>(map) * t.tiles_per_map;
-    for (int q = lane; q < t.tiles_per_map; q += 32) {
-        TileStat ts;
-        if (q == my_tile) {
-            ts = mine;
-        } else {
-            ts.vmax = row[q].vmax;
-            ts.idx = row[q].idx;
-            ts.s = row[q].s;
-            ts.sp = row[q].sp;
-            ts.spp = row[q].spp;
+    // merge the tiles in order (every lane redundantly: same instruction count as one lane);
+    // a strict > keeps the earlier tile - and so the lower index - on equal maxima
+    ArgMax am{ts[0].vmax, ts[0].idx};
+#pragma unroll
+    for (int q = 1; q < kTilesMaxPerMap; ++q)
+        if (q < t.tiles_per_map && ts[q].vmax > am.v) {
+            am.v = ts[q].vmax;
+            am.i = ts[q].idx;
         }
-        if (ts.vmax > am.v || (ts.vmax == am.v && ts.idx < am.i)) {
-            am.v = ts.vmax;
-            am.i = ts.idx;
+    float sum_exp = 0.f, sum_p = 0.f, sum_pp = 0.f;
+    const float Ms = (am.v == -INFINITY) ? 0.0f : am.v;
+#pragma unroll
+    for (int q = 0; q < kTilesMaxPerMap; ++q)
+        if (q < t.tiles_per_map) {
+            if (LOSS & HP_LOSS_KL)
+                sum_exp += ts[q].s * ((ts[q].vmax == -INFINITY) ? 0.0f : ex2_approx((ts[q].vmax - Ms) * kLog2e));
+            sum_p += ts[q].sp;
+            sum_pp += ts[q].spp;
         }
-        if (LOSS & HP_LOSS_KL) {
-            const float mn = fmaxf(m_run, ts.vmax);
-            const float ms = (mn == -INFINITY) ? 0.0f : mn;
-            s_run = s_run * ((m_run == -INFINITY) ? 0.0f : ex2_approx((m_run - ms) * kLog2e)) +
-                    ts.s * ((ts.vmax == -INFINITY) ? 0.0f : ex2_approx((ts.vmax - ms) * kLog2e));
-            m_run = mn;
-        }
-        sp += ts.sp;
-        spp += ts.spp;
-    }
-    am = warp_argmax(am, lane);  // equal maxima: the lower index (earlier tile) wins
-    float sum_exp = 0.f;
-    if (LOSS & HP_LOSS_KL) {
-        const float Ms = (am.v == -INFINITY) ? 0.0f : am.v;
-        sum_exp = warp_sum(s_run * ((m_run == -INFINITY) ? 0.0f : ex2_approx((m_run - Ms) * kLog2e)));
-    }
-    const float sum_p = warp_sum(sp);
-    const float sum_pp = (LOSS & HP_LOSS_MSE) ? warp_sum(spp) : 0.f;
     if (sum_p != sum_p) {
         // a NaN (or +inf with -inf) is in the map: redo the argmax with numpy's exact rules from memory
         ArgMax sx = am_init();
@@ -215,27 +205,59 @@ __device__ __forceinline__ void tile_close_map(const TileArgs& t, int map, const
         const int k = map % a.K;
         if (valid) atomicAdd(&a.ws->counts[a.K + k], 1);
         if (hit) atomicAdd(&a.ws->counts[k], 1);
-        if (t.tiles_per_map > 1) t.arrivals[map] = 0;  // leave the workspace zeroed for the next launch
     }
 }
 
-// publish a tile's statistics and learn whether this warp closed the map (all lanes get the answer)
-__device__ __forceinline__ unsigned int tile_arrive(const TileArgs& t, int map, int tile_in_map, const TileStat& st,
-                                                    int lane) {
-    unsigned int prev = 0;
-    if (lane == 0) {
-        TileStat* dst = t.stats + static_cast<size_t>(map) * t.tiles_per_map + tile_in_map;
-        *reinterpret_cast<float4*>(dst) = make_float4(st.vmax, __int_as_float(st.idx), st.s, st.sp);
-        dst->spp = st.spp;
-        __threadfence();  // statistics visible before the arrival is
-        prev = atomicAdd(&t.arrivals[map], 1u);
+// one tile: statistics -> ring slot -> arrival; the last arriver of the map's group closes it
+template <int NV, int LOSS>
+__device__ __forceinline__ void tile_step(const TileArgs& t, const float4 (&v)[NV], long long tile, int iter, int warp,
+                                          int lane, const float* s_tab, TileRing* ring, WarpLoss& wl) {
+    uint32_t map, q;
+    t.tdiv.divmod(static_cast<uint32_t>(tile), map, q);
+    const int tpm = t.tiles_per_map;
+    TileStat st = tile_stats<NV, LOSS>(v, static_cast<int>(q), lane);
+    TileStat ts[kTilesMaxPerMap];
+    ts[0] = st;
+    if (tpm > 1) {
+        // the warps [g*tpm, (g+1)*tpm) of this block hold the tiles of the same map in this iteration
+        const int slot = iter & (kTileRing - 1), g = warp / tpm;
+        const unsigned int my_gen = static_cast<unsigned int>(iter / kTileRing);
+        unsigned int prev = 0;
+        if (lane == 0) {
+            volatile unsigned int* gen = &ring->gen[slot][g];
+            while (*gen != my_gen) {  // slot still being merged from 8 maps ago: practically never taken
+            }
+            ring->stat[slot][warp] = st;
+            __threadfence_block();  // statistics visible (block scope) before the arrival is
+            prev = atomicAdd(&ring->count[slot][g], 1u);
+        }
+        prev = __shfl_sync(0xffffffffu, prev, 0);
+        if (prev != static_cast<unsigned int>(tpm - 1)) return;
+        __threadfence_block();
+#pragma unroll
+        for (int k = 0; k < kTilesMaxPerMap; ++k)
+            if (k < tpm) {
+                const volatile TileStat* src = &ring->stat[slot][g * tpm + k];
+                ts[k].vmax = src->vmax;
+                ts[k].idx = src->idx;
+                ts[k].s = src->s;
+                ts[k].sp = src->sp;
+                ts[k].spp = src->spp;
+            }
+        __syncwarp();
+        if (lane == 0) {  // free the slot before the long scalar part
+            ring->count[slot][g] = 0;
+            __threadfence_block();
+            ring->gen[slot][g] = my_gen + 1;
+        }
     }
-    return __shfl_sync(0xffffffffu, prev, 0);
+    tile_close_map<LOSS>(t, static_cast<int>(map), ts, lane, s_tab, wl);
 }
 
 template <int NV, int LOSS>
 __global__ void __launch_bounds__(32 * kTileWarps, 4) pipeline_tiles_kernel(const TileArgs t) {
     extern __shared__ float s_tab[];
+    __shared__ TileRing s_ring;
     const PipeArgs& a = t.p;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long n_warps = static_cast<long long>(gridDim.x) * kTileWarps;
@@ -244,46 +266,27 @@ __global__ void __launch_bounds__(32 * kTileWarps, 4) pipeline_tiles_kernel(cons
     float4 bufA[NV], bufB[NV];
     if (tile < t.n_tiles) tile_load<NV>(a.pred, tile, lane, bufA);
     load_table(s_tab, a.tab, a.tmp);
+    for (int i = threadIdx.x; i < kTileRing * kTileWarps; i += blockDim.x) {
+        (&s_ring.count[0][0])[i] = 0;
+        (&s_ring.gen[0][0])[i] = 0;
+    }
     __syncthreads();  // the only block barrier before the epilogue
 
     WarpLoss wl;
     wl.fx[0] = wl.fx[1] = 0;
 #pragma unroll
     for (int i = 0; i < 6; ++i) wl.cls[i] = 0;
-    const FastDiv tdiv = t.tdiv;
 
     // two tiles per trip so the register buffers have static names
-    while (tile < t.n_tiles) {
+    for (int iter = 0; tile < t.n_tiles; iter += 2) {
         long long next = tile + n_warps;
         if (next < t.n_tiles) tile_load<NV>(a.pred, next, lane, bufB);
-        {
-            uint32_t map, q;
-            tdiv.divmod(static_cast<uint32_t>(tile), map, q);
-            const TileStat st = tile_stats<NV, LOSS>(bufA, static_cast<int>(q), lane);
-            const bool closes = (t.tiles_per_map == 1) ||
-                                (tile_arrive(t, static_cast<int>(map), static_cast<int>(q), st, lane) ==
-                                 static_cast<unsigned int>(t.tiles_per_map - 1));
-            if (closes) {
-                if (t.tiles_per_map > 1) __threadfence();  // acquire: the other tiles' statistics
-                tile_close_map<LOSS>(t, static_cast<int>(map), st, static_cast<int>(q), lane, s_tab, wl);
-            }
-        }
+        tile_step<NV, LOSS>(t, bufA, tile, iter, warp, lane, s_tab, &s_ring, wl);
         tile = next;
         if (tile >= t.n_tiles) break;
         next = tile + n_warps;
         if (next < t.n_tiles) tile_load<NV>(a.pred, next, lane, bufA);
-        {
-            uint32_t map, q;
-            tdiv.divmod(static_cast<uint32_t>(tile), map, q);
-            const TileStat st = tile_stats<NV, LOSS>(bufB, static_cast<int>(q), lane);
-            const bool closes = (t.tiles_per_map == 1) ||
-                                (tile_arrive(t, static_cast<int>(map), static_cast<int>(q), st, lane) ==
-                                 static_cast<unsigned int>(t.tiles_per_map - 1));
-            if (closes) {
-                if (t.tiles_per_map > 1) __threadfence();
-                tile_close_map<LOSS>(t, static_cast<int>(map), st, static_cast<int>(q), lane, s_tab, wl);
-            }
-        }
+        tile_step<NV, LOSS>(t, bufB, tile, iter + 1, warp, lane, s_tab, &s_ring, wl);
         tile = next;
     }
     // ---- epilogue: exact loss sums -> workspace, last block publishes -------------------------------------
