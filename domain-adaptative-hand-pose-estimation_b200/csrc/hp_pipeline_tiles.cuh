@@ -8,8 +8,10 @@
 // slot, then bumps the slot's arrival counter (shared-memory atomic, block-scope fence: no global
 // fence or atomic on the data path).  The warp that delivers a map's LAST tile ("last arriver closes
 // the door") merges the tiles, re-reads the <=169 patch pixels (L2), builds the target terms, decodes,
-// scores PCK, closes MSE / KL and publishes.  No block barrier in the loop, no warp waits for another
-// warp (the ring is 8 maps deep), and the grid balances to within one 4 KB tile.
+// scores PCK, closes MSE / KL and publishes.  Closing duty ROTATES over the warps (map j of a block is
+// closed by warp j mod 4 as soon as it sees all four arrivals, checked after each of its own tiles), so
+// no warp waits for another (the ring is 8 maps deep), there is no block barrier in the loop, and the
+// grid balances to within one 4 KB tile.
 //
 // How it got here (profiles/r1_pipeline_*.md):
 //   v1 block-per-map, target math in the hot loop ... 43 instructions/element, issue-bound (13 % of HBM)
@@ -21,6 +23,8 @@
 //                                                     L2 round trips: a constant ~20 us tail
 //   v4 last arriver through GLOBAL counters ......... a __threadfence + atomic round trip per tile with 31
 //                                                     lanes parked at the reconvergence point (20 % issue)
+//   v5 last arriver closes, shared-memory ring ...... the slowest warp is always last, closes every map and
+//                                                     falls further behind; the other three idle at the end
 #pragma once
 #include "hp_pipeline_common.cuh"
 
@@ -208,32 +212,24 @@ __device__ __forceinline__ void tile_close_map(const TileArgs& t, int map, const
     }
 }
 
-// one tile: statistics -> ring slot -> arrival; the last arriver of the map's group closes it
-template <int NV, int LOSS>
-__device__ __forceinline__ void tile_step(const TileArgs& t, const float4 (&v)[NV], long long tile, int iter, int warp,
-                                          int lane, const float* s_tab, TileRing* ring, WarpLoss& wl) {
-    uint32_t map, q;
-    t.tdiv.divmod(static_cast<uint32_t>(tile), map, q);
-    const int tpm = t.tiles_per_map;
-    TileStat st = tile_stats<NV, LOSS>(v, static_cast<int>(q), lane);
-    TileStat ts[kTilesMaxPerMap];
-    ts[0] = st;
-    if (tpm > 1) {
-        // the warps [g*tpm, (g+1)*tpm) of this block hold the tiles of the same map in this iteration
-        const int slot = iter & (kTileRing - 1), g = warp / tpm;
-        const unsigned int my_gen = static_cast<unsigned int>(iter / kTileRing);
-        unsigned int prev = 0;
-        if (lane == 0) {
-            volatile unsigned int* gen = &ring->gen[slot][g];
-            while (*gen != my_gen) {  // slot still being merged from 8 maps ago: practically never taken
-            }
-            ring->stat[slot][warp] = st;
-            __threadfence_block();  // statistics visible (block scope) before the arrival is
-            prev = atomicAdd(&ring->count[slot][g], 1u);
+// Close every map this warp is the designated closer of and whose tiles have all arrived.
+// Designation rotates: within its group of tpm warps, warp r closes the iterations j with j % tpm == r,
+// so closing work is spread evenly no matter which warp happens to arrive last (a last-arriver rule
+// makes the slowest warp close every map and fall ever further behind).
+template <int LOSS>
+__device__ __forceinline__ void tile_try_close(const TileArgs& t, int& next_close, int upto, bool drain,
+                                               long long tile0, long long n_warps, int warp, int lane,
+                                               const float* s_tab, TileRing* ring, WarpLoss& wl) {
+    const int tpm = t.tiles_per_map, g = warp / tpm;
+    while (next_close <= upto) {
+        const int slot = next_close & (kTileRing - 1);
+        const volatile unsigned int* cnt = &ring->count[slot][g];
+        if (*cnt != static_cast<unsigned int>(tpm)) {
+            if (!drain) return;
+            continue;  // end of the walk: the other warps of the group are still on their way
         }
-        prev = __shfl_sync(0xffffffffu, prev, 0);
-        if (prev != static_cast<unsigned int>(tpm - 1)) return;
         __threadfence_block();
+        TileStat ts[kTilesMaxPerMap];
 #pragma unroll
         for (int k = 0; k < kTilesMaxPerMap; ++k)
             if (k < tpm) {
@@ -248,10 +244,36 @@ __device__ __forceinline__ void tile_step(const TileArgs& t, const float4 (&v)[N
         if (lane == 0) {  // free the slot before the long scalar part
             ring->count[slot][g] = 0;
             __threadfence_block();
-            ring->gen[slot][g] = my_gen + 1;
+            ring->gen[slot][g] = static_cast<unsigned int>(next_close / kTileRing) + 1u;
         }
+        // the group's tiles in iteration j start at tile0_of_block + j*n_warps + g*tpm, all of one map
+        const long long first_tile = tile0 + static_cast<long long>(next_close) * n_warps + g * tpm;
+        const int map = static_cast<int>(t.tdiv.div(static_cast<uint32_t>(first_tile)));
+        tile_close_map<LOSS>(t, map, ts, lane, s_tab, wl);
+        next_close += tpm;
     }
-    tile_close_map<LOSS>(t, static_cast<int>(map), ts, lane, s_tab, wl);
+}
+
+// one tile: statistics -> ring slot -> arrival (fire and forget), then opportunistic closing
+template <int NV, int LOSS>
+__device__ __forceinline__ void tile_step(const TileArgs& t, const float4 (&v)[NV], long long tile, int iter, int warp,
+                                          int lane, const float* s_tab, TileRing* ring, WarpLoss& wl) {
+    uint32_t map, q;
+    t.tdiv.divmod(static_cast<uint32_t>(tile), map, q);
+    const int tpm = t.tiles_per_map;
+    const TileStat st = tile_stats<NV, LOSS>(v, static_cast<int>(q), lane);
+    // the warps [g*tpm, (g+1)*tpm) of this block hold the tiles of the same map in this iteration
+    const int slot = iter & (kTileRing - 1), g = warp / tpm;
+    if (lane == 0) {
+        const unsigned int my_gen = static_cast<unsigned int>(iter / kTileRing);
+        volatile unsigned int* gen = &ring->gen[slot][g];
+        while (*gen != my_gen) {  // slot still unread from 8 maps ago: practically never taken
+        }
+        ring->stat[slot][warp] = st;
+        __threadfence_block();  // statistics visible (block scope) before the arrival is
+        atomicAdd(&ring->count[slot][g], 1u);
+    }
+    __syncwarp();
 }
 
 template <int NV, int LOSS>
@@ -261,7 +283,8 @@ __global__ void __launch_bounds__(32 * kTileWarps, 4) pipeline_tiles_kernel(cons
     const PipeArgs& a = t.p;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long n_warps = static_cast<long long>(gridDim.x) * kTileWarps;
-    long long tile = static_cast<long long>(blockIdx.x) * kTileWarps + warp;
+    const long long tile0 = static_cast<long long>(blockIdx.x) * kTileWarps;
+    long long tile = tile0 + warp;
 
     float4 bufA[NV], bufB[NV];
     if (tile < t.n_tiles) tile_load<NV>(a.pred, tile, lane, bufA);
@@ -276,18 +299,33 @@ __global__ void __launch_bounds__(32 * kTileWarps, 4) pipeline_tiles_kernel(cons
     wl.fx[0] = wl.fx[1] = 0;
 #pragma unroll
     for (int i = 0; i < 6; ++i) wl.cls[i] = 0;
+    const int tpm = t.tiles_per_map;
+    int next_close = warp % tpm;  // first iteration this warp is the designated closer of
 
-    // two tiles per trip so the register buffers have static names
-    for (int iter = 0; tile < t.n_tiles; iter += 2) {
-        long long next = tile + n_warps;
-        if (next < t.n_tiles) tile_load<NV>(a.pred, next, lane, bufB);
-        tile_step<NV, LOSS>(t, bufA, tile, iter, warp, lane, s_tab, &s_ring, wl);
-        tile = next;
-        if (tile >= t.n_tiles) break;
-        next = tile + n_warps;
-        if (next < t.n_tiles) tile_load<NV>(a.pred, next, lane, bufA);
-        tile_step<NV, LOSS>(t, bufB, tile, iter + 1, warp, lane, s_tab, &s_ring, wl);
-        tile = next;
+    // Two tiles per trip so the register buffers have static names; ONE closing call site per trip so the
+    // long scalar closure is inlined once (it would otherwise triple the code and spill the tile buffers).
+    int iter = 0;
+    bool more = tile < t.n_tiles;
+    while (true) {
+        if (more) {
+            long long next = tile + n_warps;
+            if (next < t.n_tiles) tile_load<NV>(a.pred, next, lane, bufB);
+            tile_step<NV, LOSS>(t, bufA, tile, iter, warp, lane, s_tab, &s_ring, wl);
+            ++iter;
+            tile = next;
+            more = tile < t.n_tiles;
+            if (more) {
+                next = tile + n_warps;
+                if (next < t.n_tiles) tile_load<NV>(a.pred, next, lane, bufA);
+                tile_step<NV, LOSS>(t, bufB, tile, iter, warp, lane, s_tab, &s_ring, wl);
+                ++iter;
+                tile = next;
+                more = tile < t.n_tiles;
+            }
+        }
+        // close what is ready; after the last tile, wait for the rest of this warp's maps (drain)
+        tile_try_close<LOSS>(t, next_close, iter - 1, !more, tile0, n_warps, warp, lane, s_tab, &s_ring, wl);
+        if (!more) break;
     }
     // ---- epilogue: exact loss sums -> workspace, last block publishes -------------------------------------
     if (lane == 0) {
