@@ -3,48 +3,48 @@
 // Work quantum = one TILE of 128*NV consecutive elements of one map (4 KB at NV = 8: a quarter of a
 // 64x64 map, a whole 32x32 map).  Every WARP independently walks its tiles with a static stride over
 // the global tile index - which makes the 4 warps of a block stream the 4 quarters of the SAME map -
-// double-buffered in registers so the next tile is always in flight, and leaves five numbers per tile
-// (max, first index of the max, sum exp relative to the max, sum p, sum p^2) in a shared-memory ring
-// slot, then bumps the slot's arrival counter (shared-memory atomic, block-scope fence: no global
-// fence or atomic on the data path).  The warp that delivers a map's LAST tile ("last arriver closes
-// the door") merges the tiles, re-reads the <=169 patch pixels (L2), builds the target terms, decodes,
-// scores PCK, closes MSE / KL and publishes.  Closing duty ROTATES over the warps (map j of a block is
-// closed by warp j mod 4 as soon as it sees all four arrivals, checked after each of its own tiles), so
-// no warp waits for another (the ring is 8 maps deep), there is no block barrier in the loop, and the
-// grid balances to within one 4 KB tile.
+// double-buffered in registers so the next tile is always in flight, and leaves four numbers per tile
+// (max, sum exp relative to the max, sum p, sum p^2) in a shared-memory ring slot, then bumps the
+// slot's arrival counter (shared-memory RED, block-scope fence: no global fence or atomic on the data
+// path).  Closing duty ROTATES over the warps: map j of a block is closed by warp j mod 4 as soon as it
+// sees all arrivals (polled after each of its own tiles).  Closing = merge the tiles, re-read from L2
+// the one tile that holds the maximum (first-index scan) and the <=169 patch pixels, build the target
+// terms, decode, score PCK, close MSE / KL, publish.  No block barrier in the loop, no warp waits for
+// another (the ring is 8 maps deep), and the grid balances to within one 4 KB tile.
 //
-// How it got here (profiles/r1_pipeline_*.md):
+// How it got here (profiles/r1_pipeline_history.md):
 //   v1 block-per-map, target math in the hot loop ... 43 instructions/element, issue-bound (13 % of HBM)
 //   v2 warp-per-map streaming ....................... 3x fewer instructions, but a 10 us work item on a
 //                                                     2.3-wave grid leaves the SMs idle half the time
 //   v3 4 warps per map, one barrier per map ......... every warp waits ~1200 cycles for the closing warp's
 //                                                     scalar math at each barrier
-//   all three ....................................... a single-thread last-block epilogue with ~50 dependent
+//   v1-v3 ........................................... a single-thread last-block epilogue with ~50 dependent
 //                                                     L2 round trips: a constant ~20 us tail
 //   v4 last arriver through GLOBAL counters ......... a __threadfence + atomic round trip per tile with 31
 //                                                     lanes parked at the reconvergence point (20 % issue)
 //   v5 last arriver closes, shared-memory ring ...... the slowest warp is always last, closes every map and
 //                                                     falls further behind; the other three idle at the end
+//   v6 rotating closers ............................. 2730 instructions/map: spills at 127 registers, an eager
+//                                                     index scan per tile, per-pixel patch index arithmetic
+//   v7 (this) ....................................... index scan only by the closer, per-lane patch table in
+//                                                     shared memory, transposed multi-value reductions
 #pragma once
 #include "hp_pipeline_common.cuh"
 
 namespace hp {
 
 constexpr int kTileWarps = 4;       // warps per block
-constexpr int kTilesMaxPerMap = 4;  // more tiles per map than this -> warp-per-map streaming instead
+constexpr int kTilesMaxPerMap = 4;  // tiles_per_map in {1, 2, 4}; larger maps use the stream shape
 constexpr int kTileMaxPatch = 6;    // patch pixels per lane of the closing warp: (2*tmp+1)^2 <= 192
-
 constexpr int kTileRing = 8;        // ring depth (maps in flight per block) of the shared-memory slots
 
 struct TileStat {  // what one warp leaves per tile
-    float vmax;
-    int idx;
-    float s, sp, spp;
+    float vmax, s, sp, spp;
 };
 
 struct TileArgs {
     PipeArgs p;
-    int tiles_per_map, n_tiles;  // tiles_per_map in {1, 2, 4}: the warps of a block split into 4/tpm groups
+    int tiles_per_map, n_tiles;  // the warps of a block split into 4/tpm groups, one map per group
     FastDiv tdiv;                // by tiles_per_map
 };
 
@@ -52,6 +52,12 @@ struct TileRing {
     TileStat stat[kTileRing][kTileWarps];
     unsigned int count[kTileRing][kTileWarps];  // arrivals per (slot, group)
     unsigned int gen[kTileRing][kTileWarps];    // how many times (slot, group) has been closed
+};
+
+// per-lane patch slots: offset from the centre and the target terms that do not depend on the prediction
+struct PatchSlot {
+    int dx, dy;        // dx = 1<<20 for unused slots (never in bounds)
+    float t, ulogu;    // target value, (t+eps)*ln(t+eps)
 };
 
 template <int NV>
@@ -62,9 +68,27 @@ __device__ __forceinline__ void tile_load(const float* __restrict__ pred, long l
     for (int j = 0; j < NV; ++j) v[j] = ldg_stream4(p + j * 32);
 }
 
-// hot loop over one tile -> TileStat (all lanes hold the result)
+// Sum three values over the warp with 6 shuffles instead of 15: after each exchange a lane keeps half of
+// its values.  On return lanes 0-7 hold sum(a), lanes 8-15 sum(b), lanes 16-23 sum(c), lanes 24-31 zero.
+__device__ __forceinline__ float warp_sum3_scattered(float a, float b, float c, int lane) {
+    const bool hi16 = (lane & 16) != 0;
+    float k0 = hi16 ? c : a, k1 = hi16 ? 0.0f : b;  // low half keeps (a, b), high half keeps (c, 0)
+    const float s0 = hi16 ? a : c, s1 = hi16 ? b : 0.0f;
+    k0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+    k1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+    const bool hi8 = (lane & 8) != 0;
+    float k = hi8 ? k1 : k0;
+    const float s = hi8 ? k0 : k1;
+    k += __shfl_xor_sync(0xffffffffu, s, 8);
+    k += __shfl_xor_sync(0xffffffffu, k, 4);
+    k += __shfl_xor_sync(0xffffffffu, k, 2);
+    k += __shfl_xor_sync(0xffffffffu, k, 1);
+    return k;
+}
+
+// hot loop over one tile; vmax in every lane, the three sums scattered (see warp_sum3_scattered)
 template <int NV, int LOSS>
-__device__ __forceinline__ TileStat tile_stats(const float4 (&v)[NV], int tile_in_map, int lane) {
+__device__ __forceinline__ void tile_stats(const float4 (&v)[NV], int lane, float& vmax, float& scattered) {
     float tm = -INFINITY;
 #pragma unroll
     for (int j = 0; j < NV; ++j) tm = fmaxf(tm, fmaxf(fmaxf(v[j].x, v[j].y), fmaxf(v[j].z, v[j].w)));
@@ -89,28 +113,13 @@ __device__ __forceinline__ TileStat tile_stats(const float4 (&v)[NV], int tile_i
             spp2 = __ffma2_rn(hi, hi, spp2);
         }
     }
-    TileStat r;
-    r.vmax = warp_max(tm);
-    int loc = 4 * NV;  // first index of the warp maximum inside this tile: scan downwards, lowest survives
-#pragma unroll
-    for (int j = NV - 1; j >= 0; --j) {
-        loc = (v[j].w == r.vmax) ? (4 * j + 3) : loc;
-        loc = (v[j].z == r.vmax) ? (4 * j + 2) : loc;
-        loc = (v[j].y == r.vmax) ? (4 * j + 1) : loc;
-        loc = (v[j].x == r.vmax) ? (4 * j + 0) : loc;
-    }
-    const int cand = (loc < 4 * NV) ? (tile_in_map * (128 * NV) + (loc >> 2) * 128 + lane * 4 + (loc & 3)) : 0x7fffffff;
-    r.idx = warp_min_int(cand);
-    r.s = 0.f;
-    r.spp = 0.f;
+    vmax = warp_max(tm);
+    float s = 0.f;
     if (LOSS & HP_LOSS_KL) {
-        const float ws = (r.vmax == -INFINITY) ? 0.0f : r.vmax;
-        const float scale = (tm == -INFINITY) ? 0.0f : ex2_approx((tm - ws) * kLog2e);
-        r.s = warp_sum((s2.x + s2.y) * scale);
+        const float ws = (vmax == -INFINITY) ? 0.0f : vmax;
+        s = (s2.x + s2.y) * ((tm == -INFINITY) ? 0.0f : ex2_approx((tm - ws) * kLog2e));
     }
-    r.sp = warp_sum(sp2.x + sp2.y);
-    if (LOSS & HP_LOSS_MSE) r.spp = warp_sum(spp2.x + spp2.y);
-    return r;
+    scattered = warp_sum3_scattered(s, sp2.x + sp2.y, spp2.x + spp2.y, lane);
 }
 
 // per-warp exact loss accumulators (registers; every lane holds the same values)
@@ -125,42 +134,41 @@ __device__ __forceinline__ void warp_loss_add(WarpLoss& w, int which, double v) 
     else w.fx[which] += __double2ll_rn(ldexp(v, kFxShift));
 }
 
-// the closing warp: merge the map's tiles, patch terms, decode, PCK, losses, publish
-template <int LOSS>
+// the closing warp: merge the map's tiles, index scan, patch terms, decode, PCK, losses, publish
+template <int NV, int LOSS>
 __device__ __forceinline__ void tile_close_map(const TileArgs& t, int map, const TileStat (&ts)[kTilesMaxPerMap],
-                                               int lane, const float* s_tab, WarpLoss& wl) {
+                                               int lane, const PatchSlot* s_patch, WarpLoss& wl) {
     const PipeArgs& a = t.p;
     const float* pm = a.pred + static_cast<size_t>(map) * a.HW;
+    // merge the tiles in order; a strict > keeps the earlier tile - and so the lower indices - on ties
+    float M = ts[0].vmax;
+    int qstar = 0;
+#pragma unroll
+    for (int q = 1; q < kTilesMaxPerMap; ++q)
+        if (q < t.tiles_per_map && ts[q].vmax > M) {
+            M = ts[q].vmax;
+            qstar = q;
+        }
+    // everything that has to come from memory is requested now, in one go: the tile holding the maximum
+    // (L2, it was streamed microseconds ago), the patch pixels, the keypoint
+    float4 w[NV];
+    tile_load<NV>(pm, qstar, lane, w);
     float weight;
     const Centre c = pipe_centre(a, a.joints[2 * map], a.joints[2 * map + 1], a.vis[map], weight);
     const bool pasted = c.y != kNoPaste;
-    // patch pixels: issue the loads first, merge the tiles while they fly
-    float pv[kTileMaxPatch], tv[kTileMaxPatch];
-    {
-        const int side = 2 * a.tmp + 1, n_patch = side * side;
+    float pv[kTileMaxPatch], tv[kTileMaxPatch], lv[kTileMaxPatch];
 #pragma unroll
-        for (int k = 0; k < kTileMaxPatch; ++k) {
-            const int i = lane + 32 * k;
-            uint32_t ry, rx;
-            a.sdiv.divmod(static_cast<uint32_t>(i), ry, rx);
-            const int dx = static_cast<int>(rx) - a.tmp, dy = static_cast<int>(ry) - a.tmp;
-            const int x = c.x + dx, y = c.y + dy;
-            const bool in = pasted && i < n_patch && x >= 0 && x < a.W && y >= 0 && y < a.H;
-            pv[k] = in ? ldg_stream1(pm + y * a.W + x) : 0.0f;
-            tv[k] = in ? s_tab[dx * dx + dy * dy] : 0.0f;
-        }
+    for (int k = 0; k < kTileMaxPatch; ++k) {
+        const PatchSlot ps = s_patch[k * 32 + lane];
+        const int x = c.x + ps.dx, y = c.y + ps.dy;
+        const bool in = pasted && static_cast<unsigned>(x) < static_cast<unsigned>(a.W) &&
+                        static_cast<unsigned>(y) < static_cast<unsigned>(a.H);
+        pv[k] = in ? ldg_stream1(pm + y * a.W + x) : 0.0f;
+        tv[k] = in ? ps.t : 0.0f;
+        lv[k] = in ? ps.ulogu : 0.0f;
     }
-    // merge the tiles in order (every lane redundantly: same instruction count as one lane);
-    // a strict > keeps the earlier tile - and so the lower index - on equal maxima
-    ArgMax am{ts[0].vmax, ts[0].idx};
-#pragma unroll
-    for (int q = 1; q < kTilesMaxPerMap; ++q)
-        if (q < t.tiles_per_map && ts[q].vmax > am.v) {
-            am.v = ts[q].vmax;
-            am.i = ts[q].idx;
-        }
     float sum_exp = 0.f, sum_p = 0.f, sum_pp = 0.f;
-    const float Ms = (am.v == -INFINITY) ? 0.0f : am.v;
+    const float Ms = (M == -INFINITY) ? 0.0f : M;
 #pragma unroll
     for (int q = 0; q < kTilesMaxPerMap; ++q)
         if (q < t.tiles_per_map) {
@@ -169,6 +177,21 @@ __device__ __forceinline__ void tile_close_map(const TileArgs& t, int map, const
             sum_p += ts[q].sp;
             sum_pp += ts[q].spp;
         }
+    // first index of M inside tile qstar: scan downwards so the lowest survives, then min over the lanes
+    ArgMax am;
+    am.v = M;
+    {
+        int loc = 4 * NV;
+#pragma unroll
+        for (int j = NV - 1; j >= 0; --j) {
+            loc = (w[j].w == M) ? (4 * j + 3) : loc;
+            loc = (w[j].z == M) ? (4 * j + 2) : loc;
+            loc = (w[j].y == M) ? (4 * j + 1) : loc;
+            loc = (w[j].x == M) ? (4 * j + 0) : loc;
+        }
+        const int cand = (loc < 4 * NV) ? (qstar * (128 * NV) + (loc >> 2) * 128 + lane * 4 + (loc & 3)) : 0x7fffffff;
+        am.i = warp_min_int(cand);
+    }
     if (sum_p != sum_p) {
         // a NaN (or +inf with -inf) is in the map: redo the argmax with numpy's exact rules from memory
         ArgMax sx = am_init();
@@ -177,16 +200,31 @@ __device__ __forceinline__ void tile_close_map(const TileArgs& t, int map, const
         am = warp_argmax(sx, lane);
         sum_exp = __int_as_float(0x7fc00000);  // log_softmax of a map holding a NaN is NaN
     }
+    // patch terms with u = t + eps:  up = sum u p, u = sum u, p = sum p, e = sum t (t - 2p), ulogu = sum u ln u
     PatchSums ps{0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int k = 0; k < kTileMaxPatch; ++k) patch_pixel<LOSS>(ps, tv[k], pv[k], a.eps);
-    if (LOSS & HP_LOSS_KL) {
-        ps.up = warp_sum(ps.up);
-        ps.ulogu = warp_sum(ps.ulogu);
-        ps.u = warp_sum(ps.u);
-        ps.p = warp_sum(ps.p);
+    for (int k = 0; k < kTileMaxPatch; ++k) {
+        const float tk = tv[k], pk = pv[k];
+        if (LOSS & HP_LOSS_KL) {
+            const float u = (tk != 0.0f) ? tk + a.eps : 0.0f;
+            ps.up = fmaf(u, pk, ps.up);
+            ps.u += u;
+            ps.p += pk;
+            ps.ulogu += lv[k];
+        }
+        if (LOSS & HP_LOSS_MSE) ps.e = fmaf(tk, tk - 2.0f * pk, ps.e);
     }
-    if (LOSS & HP_LOSS_MSE) ps.e = warp_sum(ps.e);
+    if (LOSS & HP_LOSS_KL) {
+        const float r = warp_sum3_scattered(ps.up, ps.u, ps.p, lane);
+        ps.up = __shfl_sync(0xffffffffu, r, 0);
+        ps.u = __shfl_sync(0xffffffffu, r, 8);
+        ps.p = __shfl_sync(0xffffffffu, r, 16);
+    }
+    {
+        const float r = warp_sum3_scattered(ps.ulogu, ps.e, 0.0f, lane);
+        ps.ulogu = __shfl_sync(0xffffffffu, r, 0);
+        ps.e = __shfl_sync(0xffffffffu, r, 8);
+    }
 
     uint32_t qy, qx;
     a.wdiv.divmod(static_cast<uint32_t>(am.i), qy, qx);
@@ -216,29 +254,29 @@ __device__ __forceinline__ void tile_close_map(const TileArgs& t, int map, const
 // Designation rotates: within its group of tpm warps, warp r closes the iterations j with j % tpm == r,
 // so closing work is spread evenly no matter which warp happens to arrive last (a last-arriver rule
 // makes the slowest warp close every map and fall ever further behind).
-template <int LOSS>
+template <int NV, int LOSS>
 __device__ __forceinline__ void tile_try_close(const TileArgs& t, int& next_close, int upto, bool drain,
                                                long long tile0, long long n_warps, int warp, int lane,
-                                               const float* s_tab, TileRing* ring, WarpLoss& wl) {
+                                               const PatchSlot* s_patch, TileRing* ring, WarpLoss& wl) {
     const int tpm = t.tiles_per_map, g = warp / tpm;
     while (next_close <= upto) {
         const int slot = next_close & (kTileRing - 1);
         const volatile unsigned int* cnt = &ring->count[slot][g];
         if (*cnt != static_cast<unsigned int>(tpm)) {
             if (!drain) return;
-            continue;  // end of the walk: the other warps of the group are still on their way
+            __nanosleep(200);  // end of the walk: the other warps of the group are still on their way
+            continue;
         }
         __threadfence_block();
         TileStat ts[kTilesMaxPerMap];
 #pragma unroll
         for (int k = 0; k < kTilesMaxPerMap; ++k)
             if (k < tpm) {
-                const volatile TileStat* src = &ring->stat[slot][g * tpm + k];
-                ts[k].vmax = src->vmax;
-                ts[k].idx = src->idx;
-                ts[k].s = src->s;
-                ts[k].sp = src->sp;
-                ts[k].spp = src->spp;
+                const volatile float* r = &ring->stat[slot][g * tpm + k].vmax;
+                ts[k].vmax = r[0];
+                ts[k].s = r[1];
+                ts[k].sp = r[2];
+                ts[k].spp = r[3];
             }
         __syncwarp();
         if (lane == 0) {  // free the slot before the long scalar part
@@ -249,37 +287,40 @@ __device__ __forceinline__ void tile_try_close(const TileArgs& t, int& next_clos
         // the group's tiles in iteration j start at tile0_of_block + j*n_warps + g*tpm, all of one map
         const long long first_tile = tile0 + static_cast<long long>(next_close) * n_warps + g * tpm;
         const int map = static_cast<int>(t.tdiv.div(static_cast<uint32_t>(first_tile)));
-        tile_close_map<LOSS>(t, map, ts, lane, s_tab, wl);
+        tile_close_map<NV, LOSS>(t, map, ts, lane, s_patch, wl);
         next_close += tpm;
     }
 }
 
-// one tile: statistics -> ring slot -> arrival (fire and forget), then opportunistic closing
+// one tile: statistics -> ring slot -> arrival (fire and forget)
 template <int NV, int LOSS>
-__device__ __forceinline__ void tile_step(const TileArgs& t, const float4 (&v)[NV], long long tile, int iter, int warp,
-                                          int lane, const float* s_tab, TileRing* ring, WarpLoss& wl) {
-    uint32_t map, q;
-    t.tdiv.divmod(static_cast<uint32_t>(tile), map, q);
-    const int tpm = t.tiles_per_map;
-    const TileStat st = tile_stats<NV, LOSS>(v, static_cast<int>(q), lane);
+__device__ __forceinline__ void tile_step(const TileArgs& t, const float4 (&v)[NV], int iter, int warp, int lane,
+                                          TileRing* ring) {
+    float vmax, scattered;
+    tile_stats<NV, LOSS>(v, lane, vmax, scattered);
     // the warps [g*tpm, (g+1)*tpm) of this block hold the tiles of the same map in this iteration
-    const int slot = iter & (kTileRing - 1), g = warp / tpm;
+    const int slot = iter & (kTileRing - 1), g = warp / t.tiles_per_map;
     if (lane == 0) {
         const unsigned int my_gen = static_cast<unsigned int>(iter / kTileRing);
         volatile unsigned int* gen = &ring->gen[slot][g];
         while (*gen != my_gen) {  // slot still unread from 8 maps ago: practically never taken
         }
-        ring->stat[slot][warp] = st;
+        ring->stat[slot][warp].vmax = vmax;
+    }
+    __syncwarp();
+    // lanes 0 / 8 / 16 hold sum exp / sum p / sum p^2 (warp_sum3_scattered)
+    if ((lane & 7) == 0 && lane < 24) (&ring->stat[slot][warp].s)[lane >> 3] = scattered;
+    __syncwarp();
+    if (lane == 0) {
         __threadfence_block();  // statistics visible (block scope) before the arrival is
         atomicAdd(&ring->count[slot][g], 1u);
     }
-    __syncwarp();
 }
 
 template <int NV, int LOSS>
 __global__ void __launch_bounds__(32 * kTileWarps, 4) pipeline_tiles_kernel(const TileArgs t) {
-    extern __shared__ float s_tab[];
     __shared__ TileRing s_ring;
+    __shared__ PatchSlot s_patch[kTileMaxPatch * 32];
     const PipeArgs& a = t.p;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long n_warps = static_cast<long long>(gridDim.x) * kTileWarps;
@@ -288,10 +329,29 @@ __global__ void __launch_bounds__(32 * kTileWarps, 4) pipeline_tiles_kernel(cons
 
     float4 bufA[NV], bufB[NV];
     if (tile < t.n_tiles) tile_load<NV>(a.pred, tile, lane, bufA);
-    load_table(s_tab, a.tab, a.tmp);
     for (int i = threadIdx.x; i < kTileRing * kTileWarps; i += blockDim.x) {
         (&s_ring.count[0][0])[i] = 0;
         (&s_ring.gen[0][0])[i] = 0;
+    }
+    {  // per-lane patch table: slot k of lane l is patch pixel i = l + 32k (row-major in the patch)
+        const int side = 2 * a.tmp + 1, n_patch = side * side;
+        for (int i = threadIdx.x; i < kTileMaxPatch * 32; i += blockDim.x) {
+            PatchSlot ps;
+            ps.dx = 1 << 20;
+            ps.dy = 0;
+            ps.t = 0.f;
+            ps.ulogu = 0.f;
+            if (i < n_patch) {
+                uint32_t ry, rx;
+                a.sdiv.divmod(static_cast<uint32_t>(i), ry, rx);
+                ps.dx = static_cast<int>(rx) - a.tmp;
+                ps.dy = static_cast<int>(ry) - a.tmp;
+                ps.t = a.tab[ps.dx * ps.dx + ps.dy * ps.dy];
+                const float u = ps.t + a.eps;
+                ps.ulogu = (u != 0.0f) ? u * logf(u) : 0.0f;
+            }
+            s_patch[i] = ps;
+        }
     }
     __syncthreads();  // the only block barrier before the epilogue
 
@@ -310,21 +370,21 @@ __global__ void __launch_bounds__(32 * kTileWarps, 4) pipeline_tiles_kernel(cons
         if (more) {
             long long next = tile + n_warps;
             if (next < t.n_tiles) tile_load<NV>(a.pred, next, lane, bufB);
-            tile_step<NV, LOSS>(t, bufA, tile, iter, warp, lane, s_tab, &s_ring, wl);
+            tile_step<NV, LOSS>(t, bufA, iter, warp, lane, &s_ring);
             ++iter;
             tile = next;
             more = tile < t.n_tiles;
             if (more) {
                 next = tile + n_warps;
                 if (next < t.n_tiles) tile_load<NV>(a.pred, next, lane, bufA);
-                tile_step<NV, LOSS>(t, bufB, tile, iter, warp, lane, s_tab, &s_ring, wl);
+                tile_step<NV, LOSS>(t, bufB, iter, warp, lane, &s_ring);
                 ++iter;
                 tile = next;
                 more = tile < t.n_tiles;
             }
         }
         // close what is ready; after the last tile, wait for the rest of this warp's maps (drain)
-        tile_try_close<LOSS>(t, next_close, iter - 1, !more, tile0, n_warps, warp, lane, s_tab, &s_ring, wl);
+        tile_try_close<NV, LOSS>(t, next_close, iter - 1, !more, tile0, n_warps, warp, lane, s_patch, &s_ring, wl);
         if (!more) break;
     }
     // ---- epilogue: exact loss sums -> workspace, last block publishes -------------------------------------
