@@ -226,7 +226,7 @@ static int launch_pipeline(const float* pred, const double* joints, const float*
 
     const bool fast_ok = aligned16(pred) && (W % 4 == 0) && HW < (1 << 24) && side * side <= 32 * kTileMaxPatch &&
                          thr > 0.0;
-    const size_t smem = table_bytes(tmp);
+    const size_t smem = table_bytes(tmp);  // the generic / stream shapes stage the Gaussian table here
 #define HP_BY_LOSS(KERNEL, GRID, ARG, NVV)                                                       \
     switch (loss_mask) {                                                                         \
         case 0: KERNEL<NVV, 0><<<GRID, 128, smem, stream>>>(ARG); break;                         \
@@ -250,10 +250,22 @@ static int launch_pipeline(const float* pred, const double* joints, const float*
             t.tdiv = FastDiv(static_cast<uint32_t>(tpm));
             // static stride n_warps = 4*grid over the tiles: with tpm | 4 the warps of a block always hold the
             // tiles of the same map(s) in the same iteration, which the shared-memory ring relies on
-            int grid = g_sm_count * 4;
+            static const int variant = []() {
+                const char* e = std::getenv("HP_TILES_VARIANT");  // tuning knob: A = 2 buffers x 4 blocks/SM, B = 1 x 6
+                if (e && (e[0] == 'B' || e[0] == 'b')) return 1;
+                if (e && (e[0] == 'C' || e[0] == 'c')) return 2;
+                return 0;
+            }();
+            int grid = g_sm_count * (variant == 1 ? 6 : (variant == 2 ? 5 : 4));
             const int need = (t.n_tiles + kTileWarps - 1) / kTileWarps;
             if (grid > need) grid = need;
-            if (tile_elems == 1024) { HP_BY_LOSS(pipeline_tiles_kernel, grid, t, 8) } else { HP_BY_LOSS(pipeline_tiles_kernel, grid, t, 2) }
+            if (variant == 1) {
+                if (tile_elems == 1024) { HP_BY_LOSS(pipeline_tiles1_kernel, grid, t, 8) } else { HP_BY_LOSS(pipeline_tiles1_kernel, grid, t, 2) }
+            } else if (variant == 2) {
+                if (tile_elems == 1024) { HP_BY_LOSS(pipeline_tiles1c_kernel, grid, t, 8) } else { HP_BY_LOSS(pipeline_tiles1c_kernel, grid, t, 2) }
+            } else {
+                if (tile_elems == 1024) { HP_BY_LOSS(pipeline_tiles_kernel, grid, t, 8) } else { HP_BY_LOSS(pipeline_tiles_kernel, grid, t, 2) }
+            }
         } else {
             // many tiles per map (128x128 ...): one warp streams a whole map
             const int grid = (a.n_maps + kStreamWarps - 1) / kStreamWarps;

@@ -61,9 +61,9 @@ struct PatchSlot {
 };
 
 template <int NV>
-__device__ __forceinline__ void tile_load(const float* __restrict__ pred, long long tile, int lane, float4 (&v)[NV]) {
+__device__ __forceinline__ void tile_load(const float* __restrict__ pred, int tile, int lane, float4 (&v)[NV]) {
     // maps are contiguous and HW is a multiple of the tile size, so tile t starts at t * 128 * NV
-    const float4* p = reinterpret_cast<const float4*>(pred) + tile * (32 * NV) + lane;
+    const float4* p = reinterpret_cast<const float4*>(pred) + static_cast<size_t>(tile) * (32 * NV) + lane;
 #pragma unroll
     for (int j = 0; j < NV; ++j) v[j] = ldg_stream4(p + j * 32);
 }
@@ -122,32 +122,38 @@ __device__ __forceinline__ void tile_stats(const float4 (&v)[NV], int lane, floa
     scattered = warp_sum3_scattered(s, sp2.x + sp2.y, spp2.x + spp2.y, lane);
 }
 
-// per-warp exact loss accumulators (registers; every lane holds the same values)
+// per-warp exact loss accumulators (shared memory, touched by lane 0 of the owning warp only)
 struct WarpLoss {
     long long fx[2];
     int cls[6];
 };
-__device__ __forceinline__ void warp_loss_add(WarpLoss& w, int which, double v) {
-    if (v != v) w.cls[3 * which + 0] += 1;
-    else if (v >= kFxLimit) w.cls[3 * which + 1] += 1;
-    else if (v <= -kFxLimit) w.cls[3 * which + 2] += 1;
-    else w.fx[which] += __double2ll_rn(ldexp(v, kFxShift));
+__device__ __forceinline__ void warp_loss_add(WarpLoss* w, int which, double v) {
+    if (v != v) w->cls[3 * which + 0] += 1;
+    else if (v >= kFxLimit) w->cls[3 * which + 1] += 1;
+    else if (v <= -kFxLimit) w->cls[3 * which + 2] += 1;
+    else w->fx[which] += __double2ll_rn(ldexp(v, kFxShift));
 }
 
 // the closing warp: merge the map's tiles, index scan, patch terms, decode, PCK, losses, publish
 template <int NV, int LOSS>
-__device__ __forceinline__ void tile_close_map(const TileArgs& t, int map, const TileStat (&ts)[kTilesMaxPerMap],
-                                               int lane, const PatchSlot* s_patch, WarpLoss& wl) {
+__device__ __forceinline__ void tile_close_map(const TileArgs& t, int map, TileRing* ring, int slot, int g,
+                                               unsigned int next_gen, int lane, const PatchSlot* s_patch,
+                                               WarpLoss* wl) {
     const PipeArgs& a = t.p;
+    const int tpm = t.tiles_per_map;
     const float* pm = a.pred + static_cast<size_t>(map) * a.HW;
-    // merge the tiles in order; a strict > keeps the earlier tile - and so the lower indices - on ties
-    float M = ts[0].vmax;
+    const volatile TileStat* st = &ring->stat[slot][g * tpm];
+    // which tile holds the maximum?  a strict > keeps the earlier tile - and so the lower indices - on ties
+    float M = st[0].vmax;
     int qstar = 0;
 #pragma unroll
     for (int q = 1; q < kTilesMaxPerMap; ++q)
-        if (q < t.tiles_per_map && ts[q].vmax > M) {
-            M = ts[q].vmax;
-            qstar = q;
+        if (q < tpm) {
+            const float vq = st[q].vmax;
+            if (vq > M) {
+                M = vq;
+                qstar = q;
+            }
         }
     // everything that has to come from memory is requested now, in one go: the tile holding the maximum
     // (L2, it was streamed microseconds ago), the patch pixels, the keypoint
@@ -156,27 +162,41 @@ __device__ __forceinline__ void tile_close_map(const TileArgs& t, int map, const
     float weight;
     const Centre c = pipe_centre(a, a.joints[2 * map], a.joints[2 * map + 1], a.vis[map], weight);
     const bool pasted = c.y != kNoPaste;
-    float pv[kTileMaxPatch], tv[kTileMaxPatch], lv[kTileMaxPatch];
+    // patch terms with u = t + eps:  up = sum u p, u = sum u, p = sum p, e = sum t (t - 2p), ulogu = sum u ln u
+    PatchSums ps{0.f, 0.f, 0.f, 0.f, 0.f};
+    float pv[kTileMaxPatch], tv[kTileMaxPatch];
 #pragma unroll
     for (int k = 0; k < kTileMaxPatch; ++k) {
-        const PatchSlot ps = s_patch[k * 32 + lane];
-        const int x = c.x + ps.dx, y = c.y + ps.dy;
+        const PatchSlot sl = s_patch[k * 32 + lane];
+        const int x = c.x + sl.dx, y = c.y + sl.dy;
         const bool in = pasted && static_cast<unsigned>(x) < static_cast<unsigned>(a.W) &&
                         static_cast<unsigned>(y) < static_cast<unsigned>(a.H);
         pv[k] = in ? ldg_stream1(pm + y * a.W + x) : 0.0f;
-        tv[k] = in ? ps.t : 0.0f;
-        lv[k] = in ? ps.ulogu : 0.0f;
+        tv[k] = in ? sl.t : 0.0f;
+        if (LOSS & HP_LOSS_KL) {  // the part that does not need the prediction
+            ps.ulogu += in ? sl.ulogu : 0.0f;
+            ps.u += (tv[k] != 0.0f) ? tv[k] + a.eps : 0.0f;
+        }
     }
+    // merge the per-tile sums while the loads fly, then hand the ring slot back
     float sum_exp = 0.f, sum_p = 0.f, sum_pp = 0.f;
     const float Ms = (M == -INFINITY) ? 0.0f : M;
 #pragma unroll
     for (int q = 0; q < kTilesMaxPerMap; ++q)
-        if (q < t.tiles_per_map) {
-            if (LOSS & HP_LOSS_KL)
-                sum_exp += ts[q].s * ((ts[q].vmax == -INFINITY) ? 0.0f : ex2_approx((ts[q].vmax - Ms) * kLog2e));
-            sum_p += ts[q].sp;
-            sum_pp += ts[q].spp;
+        if (q < tpm) {
+            if (LOSS & HP_LOSS_KL) {
+                const float vq = st[q].vmax;
+                sum_exp += st[q].s * ((vq == -INFINITY) ? 0.0f : ex2_approx((vq - Ms) * kLog2e));
+            }
+            sum_p += st[q].sp;
+            if (LOSS & HP_LOSS_MSE) sum_pp += st[q].spp;
         }
+    __syncwarp();
+    if (lane == 0) {
+        ring->count[slot][g] = 0;
+        __threadfence_block();
+        ring->gen[slot][g] = next_gen;
+    }
     // first index of M inside tile qstar: scan downwards so the lowest survives, then min over the lanes
     ArgMax am;
     am.v = M;
@@ -200,17 +220,13 @@ __device__ __forceinline__ void tile_close_map(const TileArgs& t, int map, const
         am = warp_argmax(sx, lane);
         sum_exp = __int_as_float(0x7fc00000);  // log_softmax of a map holding a NaN is NaN
     }
-    // patch terms with u = t + eps:  up = sum u p, u = sum u, p = sum p, e = sum t (t - 2p), ulogu = sum u ln u
-    PatchSums ps{0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int k = 0; k < kTileMaxPatch; ++k) {
         const float tk = tv[k], pk = pv[k];
         if (LOSS & HP_LOSS_KL) {
             const float u = (tk != 0.0f) ? tk + a.eps : 0.0f;
             ps.up = fmaf(u, pk, ps.up);
-            ps.u += u;
             ps.p += pk;
-            ps.ulogu += lv[k];
         }
         if (LOSS & HP_LOSS_MSE) ps.e = fmaf(tk, tk - 2.0f * pk, ps.e);
     }
@@ -237,9 +253,9 @@ __device__ __forceinline__ void tile_close_map(const TileArgs& t, int map, const
     pipe_pck(a, px, py, tx, ty, valid, hit);
     double mse, kl;
     pipe_losses<LOSS>(a, c, weight, am.v, sum_exp, sum_p, sum_pp, ps, mse, kl);
-    if (LOSS & HP_LOSS_MSE) warp_loss_add(wl, 0, mse);
-    if (LOSS & HP_LOSS_KL) warp_loss_add(wl, 1, kl);
     if (lane == 0) {
+        if (LOSS & HP_LOSS_MSE) warp_loss_add(wl, 0, mse);
+        if (LOSS & HP_LOSS_KL) warp_loss_add(wl, 1, kl);
         a.pred_xy[2 * map + 0] = px;
         a.pred_xy[2 * map + 1] = py;
         if (a.maxvals) a.maxvals[map] = am.v;
@@ -256,8 +272,8 @@ __device__ __forceinline__ void tile_close_map(const TileArgs& t, int map, const
 // makes the slowest warp close every map and fall ever further behind).
 template <int NV, int LOSS>
 __device__ __forceinline__ void tile_try_close(const TileArgs& t, int& next_close, int upto, bool drain,
-                                               long long tile0, long long n_warps, int warp, int lane,
-                                               const PatchSlot* s_patch, TileRing* ring, WarpLoss& wl) {
+                                               int tile0, int n_warps, int warp, int lane,
+                                               const PatchSlot* s_patch, TileRing* ring, WarpLoss* wl) {
     const int tpm = t.tiles_per_map, g = warp / tpm;
     while (next_close <= upto) {
         const int slot = next_close & (kTileRing - 1);
@@ -268,26 +284,11 @@ __device__ __forceinline__ void tile_try_close(const TileArgs& t, int& next_clos
             continue;
         }
         __threadfence_block();
-        TileStat ts[kTilesMaxPerMap];
-#pragma unroll
-        for (int k = 0; k < kTilesMaxPerMap; ++k)
-            if (k < tpm) {
-                const volatile float* r = &ring->stat[slot][g * tpm + k].vmax;
-                ts[k].vmax = r[0];
-                ts[k].s = r[1];
-                ts[k].sp = r[2];
-                ts[k].spp = r[3];
-            }
-        __syncwarp();
-        if (lane == 0) {  // free the slot before the long scalar part
-            ring->count[slot][g] = 0;
-            __threadfence_block();
-            ring->gen[slot][g] = static_cast<unsigned int>(next_close / kTileRing) + 1u;
-        }
         // the group's tiles in iteration j start at tile0_of_block + j*n_warps + g*tpm, all of one map
-        const long long first_tile = tile0 + static_cast<long long>(next_close) * n_warps + g * tpm;
+        const int first_tile = tile0 + next_close * n_warps + g * tpm;
         const int map = static_cast<int>(t.tdiv.div(static_cast<uint32_t>(first_tile)));
-        tile_close_map<NV, LOSS>(t, map, ts, lane, s_patch, wl);
+        tile_close_map<NV, LOSS>(t, map, ring, slot, g, static_cast<unsigned int>(next_close / kTileRing) + 1u, lane,
+                                 s_patch, wl);
         next_close += tpm;
     }
 }
@@ -317,48 +318,67 @@ __device__ __forceinline__ void tile_step(const TileArgs& t, const float4 (&v)[N
     }
 }
 
+// shared prologue: ring + per-lane patch table (slot k of lane l is patch pixel i = l + 32k, row-major)
+__device__ __forceinline__ void tile_prologue(const PipeArgs& a, TileRing* ring, PatchSlot* s_patch) {
+    for (int i = threadIdx.x; i < kTileRing * kTileWarps; i += blockDim.x) {
+        (&ring->count[0][0])[i] = 0;
+        (&ring->gen[0][0])[i] = 0;
+    }
+    const int side = 2 * a.tmp + 1, n_patch = side * side;
+    for (int i = threadIdx.x; i < kTileMaxPatch * 32; i += blockDim.x) {
+        PatchSlot ps;
+        ps.dx = 1 << 20;
+        ps.dy = 0;
+        ps.t = 0.f;
+        ps.ulogu = 0.f;
+        if (i < n_patch) {
+            uint32_t ry, rx;
+            a.sdiv.divmod(static_cast<uint32_t>(i), ry, rx);
+            ps.dx = static_cast<int>(rx) - a.tmp;
+            ps.dy = static_cast<int>(ry) - a.tmp;
+            ps.t = a.tab[ps.dx * ps.dx + ps.dy * ps.dy];
+            const float u = ps.t + a.eps;
+            ps.ulogu = (u != 0.0f) ? u * logf(u) : 0.0f;
+        }
+        s_patch[i] = ps;
+    }
+}
+
+// shared epilogue: exact loss sums -> workspace, last block publishes
+__device__ __forceinline__ void tile_epilogue(const PipeArgs& a, const WarpLoss* wl, int lane) {
+    if (lane == 0) {
+        for (int w = 0; w < 2; ++w)
+            if (wl->fx[w] != 0) atomicAdd(&a.ws->acc[w], static_cast<unsigned long long>(wl->fx[w]));
+        for (int i = 0; i < 6; ++i)
+            if (wl->cls[i] != 0) atomicAdd(&a.ws->acc[2 + i], static_cast<unsigned long long>(wl->cls[i]));
+        __threadfence();
+    }
+    if (pipeline_last_block(a.ws)) pipeline_publish(a);
+}
+
+// Variant A: two register buffers (the next tile is requested before the current one is reduced),
+// 4 blocks = 16 warps per SM.
 template <int NV, int LOSS>
 __global__ void __launch_bounds__(32 * kTileWarps, 4) pipeline_tiles_kernel(const TileArgs t) {
     __shared__ TileRing s_ring;
     __shared__ PatchSlot s_patch[kTileMaxPatch * 32];
+    __shared__ WarpLoss s_wl[kTileWarps];
     const PipeArgs& a = t.p;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long n_warps = static_cast<long long>(gridDim.x) * kTileWarps;
-    const long long tile0 = static_cast<long long>(blockIdx.x) * kTileWarps;
-    long long tile = tile0 + warp;
+    const int n_warps = static_cast<int>(gridDim.x) * kTileWarps;
+    const int tile0 = static_cast<int>(blockIdx.x) * kTileWarps;
+    int tile = tile0 + warp;
 
     float4 bufA[NV], bufB[NV];
     if (tile < t.n_tiles) tile_load<NV>(a.pred, tile, lane, bufA);
-    for (int i = threadIdx.x; i < kTileRing * kTileWarps; i += blockDim.x) {
-        (&s_ring.count[0][0])[i] = 0;
-        (&s_ring.gen[0][0])[i] = 0;
-    }
-    {  // per-lane patch table: slot k of lane l is patch pixel i = l + 32k (row-major in the patch)
-        const int side = 2 * a.tmp + 1, n_patch = side * side;
-        for (int i = threadIdx.x; i < kTileMaxPatch * 32; i += blockDim.x) {
-            PatchSlot ps;
-            ps.dx = 1 << 20;
-            ps.dy = 0;
-            ps.t = 0.f;
-            ps.ulogu = 0.f;
-            if (i < n_patch) {
-                uint32_t ry, rx;
-                a.sdiv.divmod(static_cast<uint32_t>(i), ry, rx);
-                ps.dx = static_cast<int>(rx) - a.tmp;
-                ps.dy = static_cast<int>(ry) - a.tmp;
-                ps.t = a.tab[ps.dx * ps.dx + ps.dy * ps.dy];
-                const float u = ps.t + a.eps;
-                ps.ulogu = (u != 0.0f) ? u * logf(u) : 0.0f;
-            }
-            s_patch[i] = ps;
-        }
+    tile_prologue(a, &s_ring, s_patch);
+    if (lane == 0) {
+        s_wl[warp].fx[0] = s_wl[warp].fx[1] = 0;
+        for (int i = 0; i < 6; ++i) s_wl[warp].cls[i] = 0;
     }
     __syncthreads();  // the only block barrier before the epilogue
 
-    WarpLoss wl;
-    wl.fx[0] = wl.fx[1] = 0;
-#pragma unroll
-    for (int i = 0; i < 6; ++i) wl.cls[i] = 0;
+    WarpLoss* wl = &s_wl[warp];
     const int tpm = t.tiles_per_map;
     int next_close = warp % tpm;  // first iteration this warp is the designated closer of
 
@@ -368,7 +388,7 @@ __global__ void __launch_bounds__(32 * kTileWarps, 4) pipeline_tiles_kernel(cons
     bool more = tile < t.n_tiles;
     while (true) {
         if (more) {
-            long long next = tile + n_warps;
+            int next = tile + n_warps;
             if (next < t.n_tiles) tile_load<NV>(a.pred, next, lane, bufB);
             tile_step<NV, LOSS>(t, bufA, iter, warp, lane, &s_ring);
             ++iter;
@@ -387,15 +407,57 @@ __global__ void __launch_bounds__(32 * kTileWarps, 4) pipeline_tiles_kernel(cons
         tile_try_close<NV, LOSS>(t, next_close, iter - 1, !more, tile0, n_warps, warp, lane, s_patch, &s_ring, wl);
         if (!more) break;
     }
-    // ---- epilogue: exact loss sums -> workspace, last block publishes -------------------------------------
+    tile_epilogue(a, wl, lane);
+}
+
+// Variant B: one register buffer, memory latency hidden by residency instead of register prefetch:
+// <= 80 registers, 6 blocks = 24 warps per SM.
+template <int NV, int LOSS>
+__device__ __forceinline__ void pipeline_tiles1_body(const TileArgs& t) {
+    __shared__ TileRing s_ring;
+    __shared__ PatchSlot s_patch[kTileMaxPatch * 32];
+    __shared__ WarpLoss s_wl[kTileWarps];
+    const PipeArgs& a = t.p;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_warps = static_cast<int>(gridDim.x) * kTileWarps;
+    const int tile0 = static_cast<int>(blockIdx.x) * kTileWarps;
+    int tile = tile0 + warp;
+
+    float4 buf[NV];
+    if (tile < t.n_tiles) tile_load<NV>(a.pred, tile, lane, buf);
+    tile_prologue(a, &s_ring, s_patch);
     if (lane == 0) {
-        for (int w = 0; w < 2; ++w)
-            if (wl.fx[w] != 0) atomicAdd(&a.ws->acc[w], static_cast<unsigned long long>(wl.fx[w]));
-        for (int i = 0; i < 6; ++i)
-            if (wl.cls[i] != 0) atomicAdd(&a.ws->acc[2 + i], static_cast<unsigned long long>(wl.cls[i]));
-        __threadfence();
+        s_wl[warp].fx[0] = s_wl[warp].fx[1] = 0;
+        for (int i = 0; i < 6; ++i) s_wl[warp].cls[i] = 0;
     }
-    if (pipeline_last_block(a.ws)) pipeline_publish(a);
+    __syncthreads();
+
+    WarpLoss* wl = &s_wl[warp];
+    const int tpm = t.tiles_per_map;
+    int next_close = warp % tpm;
+    int iter = 0;
+    bool more = tile < t.n_tiles;
+    while (true) {
+        if (more) {
+            if (iter > 0) tile_load<NV>(a.pred, tile, lane, buf);
+            tile_step<NV, LOSS>(t, buf, iter, warp, lane, &s_ring);
+            ++iter;
+            tile += n_warps;
+            more = tile < t.n_tiles;
+        }
+        tile_try_close<NV, LOSS>(t, next_close, iter - 1, !more, tile0, n_warps, warp, lane, s_patch, &s_ring, wl);
+        if (!more) break;
+    }
+    tile_epilogue(a, wl, lane);
+}
+template <int NV, int LOSS>
+__global__ void __launch_bounds__(32 * kTileWarps, 6) pipeline_tiles1_kernel(const TileArgs t) {
+    pipeline_tiles1_body<NV, LOSS>(t);
+}
+// Variant C: the same single-buffer body at 5 blocks = 20 warps per SM (<= 102 registers)
+template <int NV, int LOSS>
+__global__ void __launch_bounds__(32 * kTileWarps, 5) pipeline_tiles1c_kernel(const TileArgs t) {
+    pipeline_tiles1_body<NV, LOSS>(t);
 }
 
 }  // namespace hp
