@@ -248,6 +248,7 @@ static int launch_pipeline(const float* pred, const double* joints, const float*
             t.tiles_per_map = tpm;
             t.n_tiles = a.n_maps * tpm;
             t.tdiv = FastDiv(static_cast<uint32_t>(tpm));
+            t.kdiv = FastDiv(static_cast<uint32_t>(K));
             // static stride n_warps = 4*grid over the tiles: with tpm | 4 the warps of a block always hold the
             // tiles of the same map(s) in the same iteration, which the shared-memory ring relies on
             static const int variant = []() {

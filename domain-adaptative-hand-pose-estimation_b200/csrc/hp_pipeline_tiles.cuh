@@ -46,6 +46,7 @@ struct TileArgs {
     PipeArgs p;
     int tiles_per_map, n_tiles;  // the warps of a block split into 4/tpm groups, one map per group
     FastDiv tdiv;                // by tiles_per_map
+    FastDiv kdiv;                // by K (joint index of a map)
 };
 
 struct TileRing {
@@ -260,7 +261,7 @@ __device__ __forceinline__ void tile_close_map(const TileArgs& t, int map, TileR
         a.pred_xy[2 * map + 1] = py;
         if (a.maxvals) a.maxvals[map] = am.v;
         if (a.weight_out) a.weight_out[map] = weight;
-        const int k = map % a.K;
+        const int k = map - static_cast<int>(t.kdiv.div(static_cast<uint32_t>(map))) * a.K;
         if (valid) atomicAdd(&a.ws->counts[a.K + k], 1);
         if (hit) atomicAdd(&a.ws->counts[k], 1);
     }
@@ -272,15 +273,14 @@ __device__ __forceinline__ void tile_close_map(const TileArgs& t, int map, TileR
 // makes the slowest warp close every map and fall ever further behind).
 template <int NV, int LOSS>
 __device__ __forceinline__ void tile_try_close(const TileArgs& t, int& next_close, int upto, bool drain,
-                                               int tile0, int n_warps, int warp, int lane,
+                                               int tile0, int n_warps, int tpm, int g, int lane,
                                                const PatchSlot* s_patch, TileRing* ring, WarpLoss* wl) {
-    const int tpm = t.tiles_per_map, g = warp / tpm;
     while (next_close <= upto) {
         const int slot = next_close & (kTileRing - 1);
         const volatile unsigned int* cnt = &ring->count[slot][g];
         if (*cnt != static_cast<unsigned int>(tpm)) {
             if (!drain) return;
-            __nanosleep(200);  // end of the walk: the other warps of the group are still on their way
+            __nanosleep(1000);  // end of the walk: the other warps of the group are still on their way
             continue;
         }
         __threadfence_block();
@@ -295,12 +295,11 @@ __device__ __forceinline__ void tile_try_close(const TileArgs& t, int& next_clos
 
 // one tile: statistics -> ring slot -> arrival (fire and forget)
 template <int NV, int LOSS>
-__device__ __forceinline__ void tile_step(const TileArgs& t, const float4 (&v)[NV], int iter, int warp, int lane,
-                                          TileRing* ring) {
+__device__ __forceinline__ void tile_step(const float4 (&v)[NV], int iter, int warp, int g, int lane, TileRing* ring) {
     float vmax, scattered;
     tile_stats<NV, LOSS>(v, lane, vmax, scattered);
     // the warps [g*tpm, (g+1)*tpm) of this block hold the tiles of the same map in this iteration
-    const int slot = iter & (kTileRing - 1), g = warp / t.tiles_per_map;
+    const int slot = iter & (kTileRing - 1);
     if (lane == 0) {
         const unsigned int my_gen = static_cast<unsigned int>(iter / kTileRing);
         volatile unsigned int* gen = &ring->gen[slot][g];
@@ -379,8 +378,9 @@ __global__ void __launch_bounds__(32 * kTileWarps, 4) pipeline_tiles_kernel(cons
     __syncthreads();  // the only block barrier before the epilogue
 
     WarpLoss* wl = &s_wl[warp];
-    const int tpm = t.tiles_per_map;
-    int next_close = warp % tpm;  // first iteration this warp is the designated closer of
+    const int tpm = t.tiles_per_map;              // 1, 2 or 4
+    const int g = tpm == 4 ? 0 : (tpm == 2 ? (warp >> 1) : warp);
+    int next_close = warp & (tpm - 1);  // first iteration this warp is the designated closer of
 
     // Two tiles per trip so the register buffers have static names; ONE closing call site per trip so the
     // long scalar closure is inlined once (it would otherwise triple the code and spill the tile buffers).
@@ -390,21 +390,21 @@ __global__ void __launch_bounds__(32 * kTileWarps, 4) pipeline_tiles_kernel(cons
         if (more) {
             int next = tile + n_warps;
             if (next < t.n_tiles) tile_load<NV>(a.pred, next, lane, bufB);
-            tile_step<NV, LOSS>(t, bufA, iter, warp, lane, &s_ring);
+            tile_step<NV, LOSS>(bufA, iter, warp, g, lane, &s_ring);
             ++iter;
             tile = next;
             more = tile < t.n_tiles;
             if (more) {
                 next = tile + n_warps;
                 if (next < t.n_tiles) tile_load<NV>(a.pred, next, lane, bufA);
-                tile_step<NV, LOSS>(t, bufB, iter, warp, lane, &s_ring);
+                tile_step<NV, LOSS>(bufB, iter, warp, g, lane, &s_ring);
                 ++iter;
                 tile = next;
                 more = tile < t.n_tiles;
             }
         }
         // close what is ready; after the last tile, wait for the rest of this warp's maps (drain)
-        tile_try_close<NV, LOSS>(t, next_close, iter - 1, !more, tile0, n_warps, warp, lane, s_patch, &s_ring, wl);
+        tile_try_close<NV, LOSS>(t, next_close, iter - 1, !more, tile0, n_warps, tpm, g, lane, s_patch, &s_ring, wl);
         if (!more) break;
     }
     tile_epilogue(a, wl, lane);
@@ -434,18 +434,19 @@ __device__ __forceinline__ void pipeline_tiles1_body(const TileArgs& t) {
 
     WarpLoss* wl = &s_wl[warp];
     const int tpm = t.tiles_per_map;
-    int next_close = warp % tpm;
+    const int g = tpm == 4 ? 0 : (tpm == 2 ? (warp >> 1) : warp);
+    int next_close = warp & (tpm - 1);
     int iter = 0;
     bool more = tile < t.n_tiles;
     while (true) {
         if (more) {
             if (iter > 0) tile_load<NV>(a.pred, tile, lane, buf);
-            tile_step<NV, LOSS>(t, buf, iter, warp, lane, &s_ring);
+            tile_step<NV, LOSS>(buf, iter, warp, g, lane, &s_ring);
             ++iter;
             tile += n_warps;
             more = tile < t.n_tiles;
         }
-        tile_try_close<NV, LOSS>(t, next_close, iter - 1, !more, tile0, n_warps, warp, lane, s_patch, &s_ring, wl);
+        tile_try_close<NV, LOSS>(t, next_close, iter - 1, !more, tile0, n_warps, tpm, g, lane, s_patch, &s_ring, wl);
         if (!more) break;
     }
     tile_epilogue(a, wl, lane);
