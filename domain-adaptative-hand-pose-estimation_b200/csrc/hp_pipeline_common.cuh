@@ -201,14 +201,24 @@ __device__ __forceinline__ bool pipeline_last_block(Workspace* ws) {
 // ---- per-map scalar math -----------------------------------------------------------------------------
 // centre of the generated target (uda/dataset/util.py:36-46); multiplying by the reciprocal is
 // bit-identical to the division when the stride is a power of two
+// kept out of line so the compiler cannot if-convert the (rare) slow paths into the common path
+__device__ __noinline__ void pipe_centre_divide(double jx, double jy, double sx, double sy, double& qx, double& qy) {
+    qx = __ddiv_rn(jx, sx);
+    qy = __ddiv_rn(jy, sy);
+}
+__device__ __noinline__ int pipe_pck_exact(float px, float py, float tx, float ty, int H, int W, double thr) {
+    int valid, hit;
+    pck_one(px, py, tx, ty, H, W, thr, valid, hit);
+    return hit;
+}
+
 __device__ __forceinline__ Centre pipe_centre(const PipeArgs& a, double jx, double jy, float vis, float& weight) {
     double qx, qy;
     if (a.pow2_stride) {
         qx = jx * a.inv_sx;
         qy = jy * a.inv_sy;
     } else {
-        qx = __ddiv_rn(jx, a.sx);
-        qy = __ddiv_rn(jy, a.sy);
+        pipe_centre_divide(jx, jy, a.sx, a.sy, qx, qy);
     }
     const double fx = trunc(qx + 0.5), fy = trunc(qy + 0.5);
     const bool inside = (fx >= 0.0) && (fx < static_cast<double>(a.W)) && (fy >= 0.0) && (fy < static_cast<double>(a.H));
@@ -231,8 +241,7 @@ __device__ __forceinline__ void pipe_pck(const PipeArgs& a, float px, float py, 
     if (d2 < a.thr2_lo) {
         hit = 1;
     } else if (!(d2 > a.thr2_hi)) {
-        int v2;
-        pck_one(px, py, tx, ty, a.H, a.W, a.thr, v2, hit);
+        hit = pipe_pck_exact(px, py, tx, ty, a.H, a.W, a.thr);
     }
 }
 

@@ -128,11 +128,14 @@ struct WarpLoss {
     long long fx[2];
     int cls[6];
 };
-__device__ __forceinline__ void warp_loss_add(WarpLoss* w, int which, double v) {
+__device__ __noinline__ void warp_loss_add_nonfinite(WarpLoss* w, int which, double v) {
     if (v != v) w->cls[3 * which + 0] += 1;
     else if (v >= kFxLimit) w->cls[3 * which + 1] += 1;
-    else if (v <= -kFxLimit) w->cls[3 * which + 2] += 1;
-    else w->fx[which] += __double2ll_rn(ldexp(v, kFxShift));
+    else w->cls[3 * which + 2] += 1;
+}
+__device__ __forceinline__ void warp_loss_add(WarpLoss* w, int which, double v) {
+    if (fabs(v) < kFxLimit) w->fx[which] += __double2ll_rn(v * 1099511627776.0);  // * 2^40, exact scaling
+    else warp_loss_add_nonfinite(w, which, v);
 }
 
 // the closing warp: merge the map's tiles, index scan, patch terms, decode, PCK, losses, publish
@@ -300,16 +303,15 @@ __device__ __forceinline__ void tile_step(const float4 (&v)[NV], int iter, int w
     tile_stats<NV, LOSS>(v, lane, vmax, scattered);
     // the warps [g*tpm, (g+1)*tpm) of this block hold the tiles of the same map in this iteration
     const int slot = iter & (kTileRing - 1);
-    if (lane == 0) {
-        const unsigned int my_gen = static_cast<unsigned int>(iter / kTileRing);
-        volatile unsigned int* gen = &ring->gen[slot][g];
-        while (*gen != my_gen) {  // slot still unread from 8 maps ago: practically never taken
+    if (iter >= kTileRing) {  // the slot was used 8 maps ago: make sure that map has been read out
+        const unsigned int my_gen = static_cast<unsigned int>(iter) / kTileRing;
+        const volatile unsigned int* gen = &ring->gen[slot][g];
+        while (*gen != my_gen) {  // practically never taken
         }
-        ring->stat[slot][warp].vmax = vmax;
     }
-    __syncwarp();
-    // lanes 0 / 8 / 16 hold sum exp / sum p / sum p^2 (warp_sum3_scattered)
-    if ((lane & 7) == 0 && lane < 24) (&ring->stat[slot][warp].s)[lane >> 3] = scattered;
+    // lanes 0 / 8 / 16 hold sum exp / sum p / sum p^2 (warp_sum3_scattered); lane 24 carries the max
+    float* dst = &ring->stat[slot][warp].vmax;
+    if ((lane & 7) == 0) dst[lane == 24 ? 0 : 1 + (lane >> 3)] = (lane == 24) ? vmax : scattered;
     __syncwarp();
     if (lane == 0) {
         __threadfence_block();  // statistics visible (block scope) before the arrival is
