@@ -400,6 +400,8 @@ __device__ __forceinline__ double kl_finish(float m, float s, float Su, float Su
 }
 
 // "last block done" election.  counter must be zero on entry; it is reset by the winner.
+// Every thread that published block results fences its own writes (cheap when it wrote nothing),
+// then one atomic per block.
 __device__ __forceinline__ bool last_block_arrives(unsigned int* counter, unsigned int n_blocks) {
     __shared__ bool s_last;
     __threadfence();
@@ -407,9 +409,9 @@ __device__ __forceinline__ bool last_block_arrives(unsigned int* counter, unsign
     if (threadIdx.x == 0) {
         const unsigned int prev = atomicAdd(counter, 1u);
         s_last = (prev == n_blocks - 1);
+        if (s_last) __threadfence();
     }
     __syncthreads();
-    if (s_last) __threadfence();
     return s_last;
 }
 

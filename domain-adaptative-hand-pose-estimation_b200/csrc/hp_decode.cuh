@@ -64,21 +64,37 @@ __device__ __forceinline__ ArgMax decode_map(const float* __restrict__ map, int 
     return decode_tiles<TPM, NV, MODE>(ld, HW, t, scratch);
 }
 
-// finalise PCK by the last block: copy + clear the workspace counters, write acc/avg/cnt
+// finalise PCK by the last block, ALL threads: one thread per counter (one L2 round trip instead of 2K
+// dependent ones - the single-thread version cost ~15 us), then the ordered average from shared memory
 __device__ __forceinline__ void pck_publish(Workspace* ws, int K, int32_t* counts_out, double* acc_out) {
-    volatile int* c = ws->counts;
-    int hits[HP_MAX_K], valid[HP_MAX_K];
-    for (int k = 0; k < K; ++k) {
-        hits[k] = c[k];
-        valid[k] = c[K + k];
-        if (counts_out) {
-            counts_out[k] = hits[k];
-            counts_out[K + k] = valid[k];
-        }
-        c[k] = 0;
-        c[K + k] = 0;
+    __shared__ int s_cnt[2 * HP_MAX_K];
+    __shared__ double s_acc[HP_MAX_K];
+    for (int i = threadIdx.x; i < 2 * K; i += blockDim.x) {
+        const int v = *reinterpret_cast<volatile int*>(&ws->counts[i]);
+        ws->counts[i] = 0;
+        s_cnt[i] = v;
+        if (counts_out) counts_out[i] = v;
     }
-    pck_finalize_serial(hits, valid, K, acc_out);
+    __syncthreads();
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        const int h = s_cnt[k], v = s_cnt[K + k];
+        const double acc = v > 0 ? __ddiv_rn(static_cast<double>(h) * 1.0, static_cast<double>(v)) : -1.0;
+        s_acc[k] = acc;
+        acc_out[k] = acc;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double total = 0.0;
+        int cnt = 0;
+        for (int k = 0; k < K; ++k)
+            if (s_acc[k] >= 0.0) {
+                total = __dadd_rn(total, s_acc[k]);
+                ++cnt;
+            }
+        acc_out[K] = cnt != 0 ? __ddiv_rn(total, static_cast<double>(cnt)) : 0.0;
+        acc_out[K + 1] = static_cast<double>(cnt);
+        ws->counter = 0;
+    }
 }
 
 }  // namespace hp

@@ -157,12 +157,7 @@ __global__ void __launch_bounds__(TPM* MPB)
             if (hit) atomicAdd(&ws->counts[k], 1);
         }
     }
-    if (last_block_arrives(&ws->counter, gridDim.x)) {
-        if (threadIdx.x == 0) {
-            pck_publish(ws, K, counts_out, acc_out);
-            ws->counter = 0;
-        }
-    }
+    if (last_block_arrives(&ws->counter, gridDim.x)) pck_publish(ws, K, counts_out, acc_out);
 }
 
 struct FuseDecodeLaunch {
