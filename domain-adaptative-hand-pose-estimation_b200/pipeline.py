@@ -34,8 +34,16 @@ class PipelineResult:
     maxvals: torch.Tensor     # float32 [B,K,1]
     weight: torch.Tensor      # float32 [B,K,1]  (target_weight of generate_target)
     K: int
+    ready: object = None      # CUDA event recorded after the last op that writes `result` (sharded path)
+
+    def wait(self):
+        """Make the current stream wait for `result` (only needed when the collective ran on a side stream)."""
+        if self.ready is not None:
+            torch.cuda.current_stream(self.result.device).wait_event(self.ready)
+        return self
 
     def host(self):
+        self.wait()
         r = self.result.cpu().numpy() if isinstance(self.result, torch.Tensor) else np.asarray(self.result)
         K = self.K
         return dict(mse=float(r[0]), kl=float(r[1]), avg_acc=float(r[2]) if int(r[3]) else 0, cnt=int(r[3]),
@@ -70,6 +78,7 @@ class HeatmapPipeline:
         self._host_state = None
         self._ws = None
         self._plans = {}
+        self._comm_stream = None
         _lib.load()
 
     # ------------------------------------------------------------------------------ device path
@@ -139,10 +148,26 @@ class HeatmapPipeline:
         launch, out = self._cached_plan(pred, joints, vis, out, not sharded)
         launch()
         if sharded:
-            hpdist.allreduce_partial(out.partial, self.group)
-            _lib.call("hp_pipeline_finalize", _lib.ptr(out.partial), self.K, _lib.ptr(out.result),
-                      _lib.stream_ptr(self.device))
+            # The collective and the finalise run on a side stream so that they overlap the NEXT step's
+            # kernel (steps are independent; `out.ready` / `out.wait()` order consumers after them).
+            main = torch.cuda.current_stream(self.device)
+            if self._comm_stream is None:
+                self._comm_stream = torch.cuda.Stream(device=self.device)
+            comm = self._comm_stream
+            comm.wait_stream(main)
+            with torch.cuda.stream(comm):
+                hpdist.allreduce_partial(out.partial, self.group)
+                _lib.call("hp_pipeline_finalize", _lib.ptr(out.partial), self.K, _lib.ptr(out.result),
+                          C.c_void_p(comm.cuda_stream))
+                if out.ready is None:
+                    out.ready = torch.cuda.Event()
+                out.ready.record(comm)
         return out
+
+    def join(self):
+        """Order the current stream after every outstanding collective of this pipeline."""
+        if self._comm_stream is not None:
+            torch.cuda.current_stream(self.device).wait_stream(self._comm_stream)
 
     def alloc_outputs(self, B, device=None) -> PipelineResult:
         dev = device or self.device

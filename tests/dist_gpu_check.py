@@ -1,0 +1,57 @@
+"""Run under torchrun on >= 2 GPUs: the batch-sharded pipeline (kernel -> NCCL all-reduce of the int64
+partial vector -> finalise) must equal the single-GPU pipeline on the concatenated batch BIT FOR BIT, and
+match the CPU oracle.  Launched by tests/test_gpu_parity.py::test_sharded_pipeline_two_gpus."""
+import importlib
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+hp = importlib.import_module("domain-adaptative-hand-pose-estimation_b200")
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    B = 37
+    d = hp.synth.make_host_batch(9001, B)
+    lo, hi = hp.dist.shard_bounds(B, rank, world)
+    pipe = hp.HeatmapPipeline(kl_epsilon=1e-7, device=dev)
+    assert hp.dist.is_distributed()
+    outs = []
+    for rep in range(3):    # several steps in flight: exercises the side-stream overlap
+        outs.append(pipe(torch.from_numpy(d["pred"][lo:hi]).to(dev), torch.from_numpy(d["joints"][lo:hi]).to(dev),
+                         torch.from_numpy(d["vis"][lo:hi]).to(dev)))
+    got = [o.host() for o in outs]
+    part = outs[-1].wait().partial.cpu().numpy()
+    # single-GPU reference on the whole batch (group of one rank)
+    solo_group = dist.new_group(ranks=[rank]) if False else None
+    dist.barrier()
+    dist.destroy_process_group()
+    solo = hp.HeatmapPipeline(kl_epsilon=1e-7, device=dev)
+    ref = solo(torch.from_numpy(d["pred"]).to(dev), torch.from_numpy(d["joints"]).to(dev),
+               torch.from_numpy(d["vis"]).to(dev))
+    want = ref.host()
+    wpart = ref.partial.cpu().numpy()
+    assert np.array_equal(part, wpart), (part, wpart)                      # every entry is an exact integer
+    for g in got:
+        assert g["mse"] == want["mse"] and g["kl"] == want["kl"], (g, want)
+        assert np.array_equal(g["acc"], want["acc"]) and g["cnt"] == want["cnt"] and g["avg_acc"] == want["avg_acc"]
+    if rank == 0:
+        from oracle import hp_oracle as O
+        o = O.pipeline(d["pred"], d["joints"], d["vis"], kl_epsilon=1e-7)
+        assert np.array_equal(want["acc"], o["acc"]) and want["cnt"] == o["cnt"]
+        np.testing.assert_allclose(want["mse"], o["mse"], rtol=1e-5)
+        np.testing.assert_allclose(want["kl"], o["kl"], rtol=1e-5)
+    print(f"rank {rank}: sharded == single-GPU bit for bit")
+
+
+if __name__ == "__main__":
+    main()

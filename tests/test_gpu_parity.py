@@ -246,3 +246,15 @@ def test_no_cpu_fallback_and_argument_errors():
     with pytest.raises(AssertionError):
         hp.RegressionDisparity(hp.PseudoLabelGenerator(21), hp.JointsKLLoss())(
             torch.zeros(1, 21, 64, 64).cuda(), torch.zeros(1, 21, 64, 64).cuda(), None, "sideways")
+
+
+def test_sharded_pipeline_two_gpus():
+    """N>1 on real GPUs (skipped on a single-GPU box): torchrun 2 ranks, NCCL all-reduce of the partials."""
+    import os, subprocess, sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29633",
+                        os.path.join(root, "tests", "dist_gpu_check.py")], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
