@@ -213,6 +213,8 @@ def run_product_arm(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"      # the version banner goes to stdout and would precede the JSON line
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     n_gpus = world
     if args.gpus != n_gpus and rank == 0:
@@ -270,44 +272,8 @@ def run_product_arm(args):
     pipe.join()
     barrier()
 
-    # Sharded steps are launch-bound on the host (kernel + NCCL all-reduce + finalise per 28 us step), so the
-    # n_sets-step sequence is captured once into a CUDA graph and replayed; eager launches cover the
-    # remainder (and everything, if capture is unavailable).  Single-GPU steps are one ctypes call: eager.
-    graph, graph_note = None, "eager launches"
-    use_graph = args.graph == "on" or (args.graph == "auto" and world > 1)
-    if use_graph and args.steps >= n_sets:
-        try:
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                for s_i in range(n_sets):
-                    step(s_i)
-                pipe.join()
-            for _ in range(3):
-                graph.replay()
-            torch.cuda.synchronize()
-            graph_note = f"CUDA graph of {n_sets} steps (kernel + all-reduce + finalise each), replayed"
-        except Exception as exc:  # noqa: BLE001 - fall back to eager launches, say so in the line
-            graph = None
-            graph_note = f"eager launches (graph capture failed: {type(exc).__name__})"
-            torch.cuda.synchronize()
-    barrier()
-
-    if graph is not None:
-        n_replays, rest = divmod(args.steps, n_sets)
-
-        def run_steps(i):
-            if i < n_replays:
-                graph.replay()
-            elif i == n_replays:
-                for r in range(rest):
-                    step(r)
-                pipe.join()
-        ms_total = timed(run_steps, n_replays + 1)
-    else:
-        ms_total = timed(steps_then_join, args.steps)
-    maps_per_step = per_gpu_B * K * n_gpus
-    value = maps_per_step * args.steps / (ms_total * 1e-3)
-
+    graph_note = "eager launches"
+    ms_total = timed(steps_then_join, args.steps)
     # dominant kernel alone (identical to the step at N=1; without the collective at N>1)
     def kernel_only(i):
         s = sets[i % n_sets]
@@ -389,8 +355,6 @@ def main():
     ap.add_argument("--workload", default="pipeline64", choices=sorted(WORKLOADS))
     ap.add_argument("--slab", type=int, default=32, help="samples per H2D slab in the end-to-end path")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
-                    help="replay the step sequence from a CUDA graph (auto: only when sharded)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
