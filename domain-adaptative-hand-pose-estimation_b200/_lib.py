@@ -52,6 +52,13 @@ PROTOTYPES = {
     "hp_pipeline_fused": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _d, _d, _i, _vp, _f, _d, _i,
                                _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "hp_pipeline_finalize": (_i, [_vp, _i, _vp, _vp]),
+    "hp_peer_mailbox_bytes": (_sz, [_i]),
+    "hp_peer_alloc": (_i, [_i, _vp]),
+    "hp_peer_free": (_i, [_vp]),
+    "hp_peer_export": (_i, [_vp, _vp]),
+    "hp_peer_import": (_i, [_vp, _vp]),
+    "hp_peer_close": (_i, [_vp]),
+    "hp_pipeline_finalize_peer": (_i, [_vp, _vp, _i, _i, _i, C.c_int64, _vp, _vp, _vp]),
     "hp_pipeline_fused_host": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _d, _d, _i, _vp, _f, _d, _i, _i,
                                     _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }

@@ -202,11 +202,11 @@ __device__ __forceinline__ bool pipeline_last_block(Workspace* ws) {
 // centre of the generated target (uda/dataset/util.py:36-46); multiplying by the reciprocal is
 // bit-identical to the division when the stride is a power of two
 // kept out of line so the compiler cannot if-convert the (rare) slow paths into the common path
-__device__ __noinline__ void pipe_centre_divide(double jx, double jy, double sx, double sy, double& qx, double& qy) {
+static __device__ __noinline__ void pipe_centre_divide(double jx, double jy, double sx, double sy, double& qx, double& qy) {
     qx = __ddiv_rn(jx, sx);
     qy = __ddiv_rn(jy, sy);
 }
-__device__ __noinline__ int pipe_pck_exact(float px, float py, float tx, float ty, int H, int W, double thr) {
+static __device__ __noinline__ int pipe_pck_exact(float px, float py, float tx, float ty, int H, int W, double thr) {
     int valid, hit;
     pck_one(px, py, tx, ty, H, W, thr, valid, hit);
     return hit;

@@ -128,7 +128,7 @@ struct WarpLoss {
     long long fx[2];
     int cls[6];
 };
-__device__ __noinline__ void warp_loss_add_nonfinite(WarpLoss* w, int which, double v) {
+static __device__ __noinline__ void warp_loss_add_nonfinite(WarpLoss* w, int which, double v) {
     if (v != v) w->cls[3 * which + 0] += 1;
     else if (v >= kFxLimit) w->cls[3 * which + 1] += 1;
     else w->cls[3 * which + 2] += 1;

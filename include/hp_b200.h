@@ -184,6 +184,22 @@ int hp_pipeline_fused(const float* pred, const double* joints, const float* vis,
 /* partial (e.g. after an NCCL all-reduce over ranks) -> result, on device */
 int hp_pipeline_finalize(const int64_t* partial, int K, double* result, hp_stream_t stream);
 
+/* ---- the path's single collective over NVLink peer memory (no NCCL on the per-step path) ----
+ * Setup (once; the only entry points that own memory): every rank allocates a mailbox, exports its
+ * 64-byte CUDA IPC handle, exchanges handles with the other ranks of the node (any transport) and maps
+ * theirs.  Per step: hp_pipeline_finalize_peer replaces [all-reduce(partial) ; hp_pipeline_finalize]:
+ * it writes this rank's partial into every mailbox, waits (bounded) for all ranks' step `seq`, sums in
+ * rank order and finalises.  mailboxes[r] = rank r's mailbox as mapped here (own pointer for r == rank).
+ * `seq` = 1, 2, 3, ... identical on all ranks.  On a timeout result[0] and result[1] are NaN. */
+size_t hp_peer_mailbox_bytes(int world);
+int hp_peer_alloc(int world, void** mailbox);
+int hp_peer_free(void* mailbox);
+int hp_peer_export(void* mailbox, void* handle64);
+int hp_peer_import(const void* handle64, void** mapped);
+int hp_peer_close(void* mapped);
+int hp_pipeline_finalize_peer(const int64_t* partial, void* const* mailboxes, int rank, int world, int K,
+                              int64_t seq, int64_t* partial_out, double* result, hp_stream_t stream);
+
 /* Host-buffer form (end-to-end path): h_* are pinned host arrays; the batch is cut into slabs
  * of slab_B samples whose H2D copies (copy_stream) overlap the kernels (stream); device
  * staging d_pred holds 2 slabs [2*slab_B,K,H,W]; returns after h_result is valid. */
