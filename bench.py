@@ -257,9 +257,13 @@ def run_product_arm(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    # steps are independent resident batches with their own output buffers: consecutive launches may overlap
+    # (programmatic dependent launch, HP_PIPE_OVERLAP_PREV); --no-overlap serialises them
+    overlap = not args.no_overlap
+
     def step(i):
         s = sets[i % n_sets]
-        pipe(s["pred"], s["joints"], s["vis"], out=outs[i % n_sets])
+        pipe(s["pred"], s["joints"], s["vis"], out=outs[i % n_sets], overlap=overlap)
 
     def steps_then_join(i):
         step(i)
@@ -274,10 +278,12 @@ def run_product_arm(args):
 
     graph_note = "eager launches"
     ms_total = timed(steps_then_join, args.steps)
+    maps_per_step = per_gpu_B * K * n_gpus
+    value = maps_per_step * args.steps / (ms_total * 1e-3)
     # dominant kernel alone (identical to the step at N=1; without the collective at N>1)
     def kernel_only(i):
         s = sets[i % n_sets]
-        pipe.launch_local(s["pred"], s["joints"], s["vis"], outs[i % n_sets])
+        pipe.launch_local(s["pred"], s["joints"], s["vis"], outs[i % n_sets], overlap=overlap)
 
     for i in range(3):
         kernel_only(i)
@@ -334,7 +340,9 @@ def run_product_arm(args):
                              f"({n_sets * per_gpu_B * K * map_bytes / 1e6:.0f} MB > 126 MB L2)",
                        "parallelism": f"batch-sharded dp{n_gpus}; one NCCL all-reduce of {4 + 2 * K + 6} int64 per step"
                                       if n_gpus > 1 else "single GPU, no collective",
-                       "launch": graph_note},
+                       "launch": graph_note + (", consecutive steps overlap by programmatic dependent launch "
+                                               "(independent resident batches, separate outputs)" if overlap else
+                                               ", fully serialised")},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": clocks,
             "gpu_launches": args.steps * (2 if n_gpus > 1 else 1),
         }
@@ -355,6 +363,8 @@ def main():
     ap.add_argument("--workload", default="pipeline64", choices=sorted(WORKLOADS))
     ap.add_argument("--slab", type=int, default=32, help="samples per H2D slab in the end-to-end path")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true",
+                    help="launch every step fully serialised after the previous one (no programmatic dependent launch)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

@@ -18,6 +18,7 @@ LIB_PATH = os.path.join(_HERE, "libhp_b200.so")
 
 # enums of include/hp_b200.h
 LOSS_MSE, LOSS_KL = 1, 2
+PIPE_OVERLAP_PREV = 1          # HP_PIPE_OVERLAP_PREV (include/hp_b200.h)
 PLG_BASE, PLG_ONE_MINUS = 0, 1
 RD_BASE, RD_X1, RD_X5, RD_X6 = 0, 1, 2, 3
 MODE_MIN, MODE_MAX = 0, 1
@@ -51,6 +52,8 @@ PROTOTYPES = {
                                 _vp, _vp, _vp, _vp, _vp, _vp]),
     "hp_pipeline_fused": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _d, _d, _i, _vp, _f, _d, _i,
                                _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
+    "hp_pipeline_fused_ex": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _d, _d, _i, _vp, _f, _d, _i,
+                                  _vp, _vp, _vp, _vp, _i, _vp, _vp, C.c_uint, _vp]),
     "hp_pipeline_finalize": (_i, [_vp, _i, _vp, _vp]),
     "hp_peer_mailbox_bytes": (_sz, [_i]),
     "hp_peer_alloc": (_i, [_i, _vp]),

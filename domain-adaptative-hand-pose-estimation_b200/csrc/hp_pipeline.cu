@@ -21,6 +21,7 @@
 #include "hp_dispatch.cuh"
 #include "hp_pipeline_common.cuh"
 #include "hp_pipeline_tiles.cuh"
+#include "hp_pipeline_bulk.cuh"
 #include "hp_pipeline_stream.cuh"
 
 namespace hp {
@@ -202,10 +203,56 @@ struct PipeLaunch {
 
 static int g_sm_count = 0;
 
+// ---- TMA-staged shape (hp_pipeline_bulk.cuh) ---------------------------------------------------------------------
+template <int NITC, int LOSS, bool MULTI, int W, int KST>
+static cudaError_t launch_bulk_one(const BulkArgs& t, int grid, cudaStream_t stream) {
+    constexpr size_t smem = static_cast<size_t>(W) * KST * NITC * 512 + sizeof(uint64_t) * W * KST;
+    static bool configured[16] = {};  // per device: opt in to > 48 KB of dynamic shared memory once
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 16 || !configured[dev]) {
+        const cudaError_t e = cudaFuncSetAttribute(pipeline_bulk_kernel<NITC, LOSS, MULTI, W, KST>,
+                                                   cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 16) configured[dev] = true;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(static_cast<unsigned>(grid));
+    cfg.blockDim = dim3(32 * W);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = t.overlap ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, pipeline_bulk_kernel<NITC, LOSS, MULTI, W, KST>, t);
+}
+template <int NITC, bool MULTI, int W, int KST>
+static cudaError_t launch_bulk(const BulkArgs& t, int grid, cudaStream_t stream) {
+    switch (t.p.loss_mask) {
+        case 0: return launch_bulk_one<NITC, 0, MULTI, W, KST>(t, grid, stream);
+        case HP_LOSS_MSE: return launch_bulk_one<NITC, 1, MULTI, W, KST>(t, grid, stream);
+        case HP_LOSS_KL: return launch_bulk_one<NITC, 2, MULTI, W, KST>(t, grid, stream);
+        default: return launch_bulk_one<NITC, 3, MULTI, W, KST>(t, grid, stream);
+    }
+}
+// 0 = tiles/stream shapes, 1.. = bulk shape with (warps, stages per warp) variants for 64x64
+static int pipeline_shape_choice() {
+    static const int choice = []() {
+        const char* e = std::getenv("HP_PIPE_SHAPE");
+        if (!e) return 1;
+        if (e[0] == 't' || e[0] == 'T') return 0;       // "tiles": the register-tile kernels
+        if (e[0] >= '1' && e[0] <= '5') return e[0] - '0';
+        return 1;
+    }();
+    return choice;
+}
+
 static int launch_pipeline(const float* pred, const double* joints, const float* vis, int B, int K, int H, int W,
                            double stride_x, double stride_y, int tmp, const float* tab, float kl_epsilon, double thr,
                            int loss_mask, float* pred_xy, float* maxvals, float* weight_out, long long* partial,
-                           int accumulate, double* result, void* workspace, cudaStream_t stream) {
+                           int accumulate, double* result, void* workspace, cudaStream_t stream, unsigned flags = 0) {
     const int HW = H * W, side = 2 * tmp + 1;
     PipeArgs a{};
     a.pred = pred; a.joints = joints; a.vis = vis; a.n_maps = B * K; a.K = K; a.H = H; a.W = W; a.HW = HW;
@@ -233,6 +280,34 @@ static int launch_pipeline(const float* pred, const double* joints, const float*
         case HP_LOSS_MSE: KERNEL<NVV, 1><<<GRID, 128, smem, stream>>>(ARG); break;               \
         case HP_LOSS_KL: KERNEL<NVV, 2><<<GRID, 128, smem, stream>>>(ARG); break;                \
         default: KERNEL<NVV, 3><<<GRID, 128, smem, stream>>>(ARG); break;                        \
+    }
+    if (fast_ok && pipeline_shape_choice() != 0 &&
+        (HW == 256 || HW == 1024 || (HW % 4096 == 0 && HW / 4096 <= 64))) {
+        if (g_sm_count == 0) {
+            g_sm_count = hp_device_sm_count();
+            if (g_sm_count <= 0) g_sm_count = 148;
+        }
+        BulkArgs t{};
+        t.p = a;
+        t.kdiv = FastDiv(static_cast<uint32_t>(K));
+        t.n_chunks = HW > 4096 ? HW / 4096 : 1;
+        t.overlap = (flags & HP_PIPE_OVERLAP_PREV) ? 1 : 0;
+        const int grid = a.n_maps < g_sm_count ? a.n_maps : g_sm_count;  // one persistent block per SM
+        cudaError_t e;
+        if (HW == 256) e = launch_bulk<2, false, 12, 8>(t, grid, stream);
+        else if (HW == 1024) e = launch_bulk<8, false, 12, 4>(t, grid, stream);
+        else if (HW > 4096) e = launch_bulk<32, true, 6, 2>(t, grid, stream);
+        else {
+            switch (pipeline_shape_choice()) {
+                case 2: e = launch_bulk<32, false, 6, 2>(t, grid, stream); break;
+                case 3: e = launch_bulk<32, false, 4, 3>(t, grid, stream); break;
+                case 4: e = launch_bulk<32, false, 8, 1>(t, grid, stream); break;
+                case 5: e = launch_bulk<32, false, 13, 1>(t, grid, stream); break;
+                default: e = launch_bulk<32, false, 12, 1>(t, grid, stream); break;
+            }
+        }
+        if (e != cudaSuccess) return fail(static_cast<int>(e), "hp_pipeline_fused: %s", cudaGetErrorString(e));
+        return launch_status("hp_pipeline_fused");
     }
     const int tile_elems = (HW % 1024 == 0) ? 1024 : ((HW % 256 == 0) ? 256 : 0);
     if (fast_ok && tile_elems != 0) {
@@ -310,6 +385,20 @@ extern "C" HP_API int hp_pipeline_fused(const float* pred, const double* joints,
     return launch_pipeline(pred, joints, vis, B, K, H, W, stride_x, stride_y, tmp, tab, kl_epsilon, thr, loss_mask,
                            pred_xy, maxvals, weight_out, reinterpret_cast<long long*>(partial), accumulate, result,
                            workspace, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" HP_API int hp_pipeline_fused_ex(const float* pred, const double* joints, const float* vis, int B, int K, int H,
+                                           int W, double stride_x, double stride_y, int tmp, const float* tab,
+                                           float kl_epsilon, double thr, int loss_mask, float* pred_xy, float* maxvals,
+                                           float* weight_out, int64_t* partial, int accumulate, double* result,
+                                           void* workspace, unsigned int flags, hp_stream_t stream) {
+    if (int rc = check_pipeline("hp_pipeline_fused_ex", pred, joints, vis, B, K, H, W, stride_x, stride_y, tmp, tab,
+                                pred_xy, partial, workspace, loss_mask))
+        return rc;
+    HP_REQUIRE((flags & ~HP_PIPE_OVERLAP_PREV) == 0, HP_ERR_ARG, "hp_pipeline_fused_ex: unknown flags 0x%x", flags);
+    return launch_pipeline(pred, joints, vis, B, K, H, W, stride_x, stride_y, tmp, tab, kl_epsilon, thr, loss_mask,
+                           pred_xy, maxvals, weight_out, reinterpret_cast<long long*>(partial), accumulate, result,
+                           workspace, static_cast<cudaStream_t>(stream), flags);
 }
 
 extern "C" HP_API int hp_pipeline_finalize(const int64_t* partial, int K, double* result, hp_stream_t stream) {

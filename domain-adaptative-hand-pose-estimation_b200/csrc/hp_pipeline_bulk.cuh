@@ -1,0 +1,423 @@
+// hp_pipeline_bulk.cuh - the production shape of the fused gen+loss+decode+PCK kernel on sm_100a:
+// maps are staged in shared memory by the TMA engine (cp.async.bulk + mbarrier complete_tx), one
+// persistent block per SM, every warp owns a PRIVATE ring of stages.
+//
+// Why this shape (profiles/r1_pipeline_history.md): the register-tile kernels needed the warps themselves
+// to keep HBM busy, so memory-level parallelism was tied to occupancy and to 128-register tile buffers
+// (spills), and a map's four tiles had to be merged through a cross-warp ring.  Here
+//   * bytes in flight are decoupled from the instruction stream: the copy engine keeps W*KST stages
+//     (12 x 16 KB = 192 KB per SM) requested, the warps only ever touch shared memory;
+//   * a warp owns a whole map: no cross-warp protocol, no block barrier, no atomics in the loop; the
+//     stage's barrier is armed and re-filled by the same warp that drained it (no empty-barrier, no
+//     phase hazards between warps);
+//   * the map sits in shared memory, so a two-pass exact softmax (max+argmax, then sums against the true
+//     max), the first-index resolution and the <=169 patch pixels are cheap LDS traffic, not L2 re-reads;
+//   * everything that does not need the prediction (centre, patch offsets, target-only sums) runs before
+//     the wait on the stage, the float64 closure after the refill has been issued.
+// Large maps (128x128 = 64 KB) go through the same loop in 16 KB chunks with an online softmax merge.
+//
+// Algorithmic bytes per map: H*W*4 + 24 + 8; the map is read from HBM exactly once.
+#pragma once
+#include "hp_pipeline_common.cuh"
+#include "hp_pipeline_tiles.cuh"  // PatchSlot, WarpLoss, warp_sum3_scattered, kTileMaxPatch
+
+namespace hp {
+
+struct BulkArgs {
+    PipeArgs p;
+    FastDiv kdiv;   // by K (joint index of a map)
+    int n_chunks;   // chunks per map (1 unless the map is larger than a stage)
+    int overlap;    // launched with programmatic stream serialization (HP_PIPE_OVERLAP_PREV)
+};
+
+// ---- mbarrier / bulk-copy primitives (PTX; SASS: SYNCS.*, UBLKCP) ---------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+// global -> shared bulk copy, completion counted in bytes on `bar`
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t pol) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+        "l"(src), "r"(bytes), "r"(bar), "l"(pol)
+        : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// bounded: a copy that never lands (bad pointer) traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    unsigned int spins = 0;
+    while (!mbar_try_wait(bar, parity))
+        if (++spins > (1u << 24)) __trap();
+}
+
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+__device__ __forceinline__ float warp_max_f32(float x) {
+    float r;
+    asm("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// ---- per-lane accumulators of one map ------------------------------------------------------------------
+struct BulkAcc {
+    float M;      // maximum so far (all lanes agree)
+    int idx;      // its first flat index
+    float2 s2;    // per-lane partial sum exp(p - M)
+    float2 sp2;   // per-lane partial sum p
+    float2 spp2;  // per-lane partial sum p^2
+};
+
+// One chunk of NITC*128 elements sitting in shared memory.  Element e of the chunk is component (e & 3) of
+// float4 number (e >> 2); lane l reads float4 number it*32 + l in iteration it (conflict-free LDS.128).
+template <int NITC, int LOSS, bool MULTI>
+__device__ __forceinline__ void bulk_chunk(BulkAcc& A, const float4* __restrict__ buf, int chunk, int lane) {
+    // pass A: maximum, and per lane the first iteration that reached the lane's maximum
+    float run = -INFINITY;
+    int best_it = 0;
+#pragma unroll 8
+    for (int it = 0; it < NITC; ++it) {
+        const float4 v = buf[it * 32 + lane];
+        const float t = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+        best_it = (t > run) ? it : best_it;  // strict: the earlier iteration keeps ties
+        run = fmaxf(run, t);
+    }
+    const float cm = warp_max_f32(run);
+    if (!MULTI || chunk == 0 || cm > A.M) {
+        // first flat index of cm: smallest (iteration, lane) among the lanes that hold it, then the component
+        const unsigned key = (run == cm) ? static_cast<unsigned>(best_it * 32 + lane) : 0x7fffffffu;
+        const unsigned kmin = __reduce_min_sync(0xffffffffu, key);
+        const float4 v = buf[kmin];
+        const int comp = (v.x == cm) ? 0 : ((v.y == cm) ? 1 : ((v.z == cm) ? 2 : 3));
+        A.idx = chunk * (NITC * 128) + static_cast<int>(kmin) * 4 + comp;
+        if (MULTI && (LOSS & HP_LOSS_KL)) {  // re-base the sums collected so far on the new maximum
+            const float scale = (A.M == -INFINITY) ? 0.0f : ex2_approx((A.M - cm) * kLog2e);
+            A.s2.x *= scale;
+            A.s2.y *= scale;
+        }
+        A.M = cm;
+    }
+    // pass B: the sums, against the true maximum
+    const float ms = (A.M == -INFINITY) ? 0.0f : A.M;
+    const float2 l2 = make_float2(kLog2e, kLog2e), mb2 = make_float2(-ms * kLog2e, -ms * kLog2e);
+    float2 s2 = A.s2, sp2 = A.sp2, spp2 = A.spp2;
+#pragma unroll 8
+    for (int it = 0; it < NITC; ++it) {
+        const float4 v = buf[it * 32 + lane];
+        const float2 lo = make_float2(v.x, v.y), hi = make_float2(v.z, v.w);
+        if (LOSS & HP_LOSS_KL) {
+            const float2 a0 = __ffma2_rn(lo, l2, mb2);
+            const float2 a1 = __ffma2_rn(hi, l2, mb2);
+            const float2 e0 = make_float2(ex2_approx(a0.x), ex2_approx(a0.y));
+            const float2 e1 = make_float2(ex2_approx(a1.x), ex2_approx(a1.y));
+            s2 = __fadd2_rn(s2, __fadd2_rn(e0, e1));
+        }
+        sp2 = __fadd2_rn(sp2, __fadd2_rn(lo, hi));
+        if (LOSS & HP_LOSS_MSE) {
+            spp2 = __ffma2_rn(lo, lo, spp2);
+            spp2 = __ffma2_rn(hi, hi, spp2);
+        }
+    }
+    A.s2 = s2;
+    A.sp2 = sp2;
+    A.spp2 = spp2;
+}
+
+// shared memory of the kernel besides the stages
+struct BulkShared {
+    PatchSlot patch[kTileMaxPatch * 32];
+    int counts[2 * HP_MAX_K];       // PCK hits / valid of this block
+    unsigned long long acc[8];      // loss sums (fixed point) and non-finite counters of this block
+};
+
+// NITC: iterations (of 128 elements) per chunk;  MULTI: maps span several chunks;
+// W warps per block, KST private stages per warp.
+template <int NITC, int LOSS, bool MULTI, int W, int KST>
+__global__ void __launch_bounds__(32 * W, 1) pipeline_bulk_kernel(const BulkArgs t) {
+    extern __shared__ __align__(128) unsigned char s_dyn[];
+    __shared__ BulkShared sh;
+    __shared__ WarpLoss s_wl[W];
+    constexpr int kChunkBytes = NITC * 512;
+    constexpr int kChunkElems = NITC * 128;
+    const PipeArgs& a = t.p;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_chunks = MULTI ? t.n_chunks : 1;
+    // maps of this block: blockIdx.x + j*gridDim.x ; of this warp: j = warp + jj*W
+    const int n_local = (a.n_maps - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+    const int n_mine = (n_local > warp) ? (n_local - warp + W - 1) / W : 0;
+    const int q_total = n_mine * n_chunks;  // chunk loads of this warp, in order q = jj*n_chunks + c
+
+    unsigned char* my_stage = s_dyn + static_cast<size_t>(warp) * KST * kChunkBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_dyn + static_cast<size_t>(W) * KST * kChunkBytes) + warp * KST;
+    const uint32_t stage_u32 = smem_addr(my_stage), bar_u32 = smem_addr(bars);
+    const uint64_t pol = l2_evict_first_policy();
+    const size_t map_stride = static_cast<size_t>(gridDim.x) * W * a.HW;  // between consecutive maps of this warp
+    const float* my_first = a.pred + (static_cast<size_t>(blockIdx.x) + static_cast<size_t>(warp) * gridDim.x) * a.HW;
+
+    // Programmatic dependent launch (no-ops unless the launch carries the attribute): the next launch on the
+    // stream may start filling SMs as soon as this grid's blocks retire; nothing of a launch is WRITTEN (and
+    // the shared workspace is not touched) before griddep_wait() has seen the previous grid complete.
+    griddep_launch_dependents();
+    // ---- prologue ----------------------------------------------------------------------------------------------
+    // The small global loads are ISSUED first and consumed after the bulk copies have been requested: once
+    // 148 x 192 KB of bulk traffic is queued, a plain load waits microseconds behind it (the first version
+    // of this kernel loaded each map's keypoint right before use and spent a third of its time there).
+    // Keypoints are lane-distributed: lane l of a warp holds the keypoint of the warp's map 32*batch + l.
+    const bool joints16 = (reinterpret_cast<uintptr_t>(a.joints) & 15u) == 0;
+    double jx_cur = 0.0, jy_cur = 0.0, jx_nxt = 0.0, jy_nxt = 0.0;
+    float vis_cur = 0.0f, vis_nxt = 0.0f;
+    auto load_keypoints = [&](int batch, double& jx, double& jy, float& vis) {
+        const int jj = batch * 32 + lane;
+        if (jj < n_mine) {
+            const int m = static_cast<int>(blockIdx.x) + (warp + jj * W) * static_cast<int>(gridDim.x);
+            const double* jp = a.joints + 2 * static_cast<size_t>(m);
+            if (joints16) {
+                const double2 j2 = *reinterpret_cast<const double2*>(jp);
+                jx = j2.x;
+                jy = j2.y;
+            } else {
+                jx = jp[0];
+                jy = jp[1];
+            }
+            vis = a.vis[m];
+        }
+    };
+    load_keypoints(0, jx_cur, jy_cur, vis_cur);
+    const int side = 2 * a.tmp + 1, n_patch = side * side;
+    // per-lane patch table: slot k of lane l is patch pixel l + 32k (row-major); thread t fills slots t, t + 32W, ...
+    constexpr int kSlotsPerThread = (kTileMaxPatch * 32 + 32 * W - 1) / (32 * W);
+    PatchSlot my_slot[kSlotsPerThread];
+#pragma unroll
+    for (int r = 0; r < kSlotsPerThread; ++r) {
+        const int i = static_cast<int>(threadIdx.x) + r * 32 * W;
+        my_slot[r].dx = 1 << 20;
+        my_slot[r].dy = 0;
+        my_slot[r].t = 0.f;
+        my_slot[r].ulogu = 0.f;
+        if (i < n_patch) {
+            uint32_t ry, rx;
+            a.sdiv.divmod(static_cast<uint32_t>(i), ry, rx);
+            my_slot[r].dx = static_cast<int>(rx) - a.tmp;
+            my_slot[r].dy = static_cast<int>(ry) - a.tmp;
+            my_slot[r].t = a.tab[my_slot[r].dx * my_slot[r].dx + my_slot[r].dy * my_slot[r].dy];
+        }
+    }
+    // arm the private ring and request the first KST chunks
+    int q_load = 0, load_jj = 0, load_c = 0;  // next chunk to request
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < KST; ++s) mbar_init(bar_u32 + 8 * s, 1);
+        mbar_init_fence();
+#pragma unroll
+        for (int s = 0; s < KST; ++s) {
+            if (q_load < q_total) {
+                mbar_arrive_expect_tx(bar_u32 + 8 * s, kChunkBytes);
+                bulk_load(stage_u32 + s * kChunkBytes, my_first + load_jj * map_stride + load_c * kChunkElems, kChunkBytes,
+                          bar_u32 + 8 * s, pol);
+                ++q_load;
+                if (++load_c == n_chunks) {
+                    load_c = 0;
+                    ++load_jj;
+                }
+            }
+        }
+    }
+    load_keypoints(1, jx_nxt, jy_nxt, vis_nxt);
+    // patch table and block accumulators
+#pragma unroll
+    for (int r = 0; r < kSlotsPerThread; ++r) {
+        const int i = static_cast<int>(threadIdx.x) + r * 32 * W;
+        if (i < kTileMaxPatch * 32) {
+            if (i < n_patch) {
+                const float u = my_slot[r].t + a.eps;
+                my_slot[r].ulogu = (u != 0.0f) ? u * logf(u) : 0.0f;
+            }
+            sh.patch[i] = my_slot[r];
+        }
+    }
+    for (int i = threadIdx.x; i < 2 * HP_MAX_K; i += blockDim.x) sh.counts[i] = 0;
+    if (threadIdx.x < 8) sh.acc[threadIdx.x] = 0;
+    if (lane == 0) {
+        s_wl[warp].fx[0] = s_wl[warp].fx[1] = 0;
+        for (int i = 0; i < 6; ++i) s_wl[warp].cls[i] = 0;
+    }
+    __syncthreads();  // the only block barrier before the epilogue
+
+    WarpLoss* wl = &s_wl[warp];
+    int q = 0;  // chunk being consumed
+    for (int jj = 0; jj < n_mine; ++jj) {
+        const int map = static_cast<int>(blockIdx.x) + (warp + jj * W) * static_cast<int>(gridDim.x);
+        // ---- everything that does not need the prediction, while the chunk is in flight ----------------------
+        if (jj != 0 && (jj & 31) == 0) {  // next batch of 32 keypoints: requested 32 maps ago
+            jx_cur = jx_nxt;
+            jy_cur = jy_nxt;
+            vis_cur = vis_nxt;
+            load_keypoints((jj >> 5) + 1, jx_nxt, jy_nxt, vis_nxt);
+        }
+        float weight;
+        const Centre c = pipe_centre(a, __shfl_sync(0xffffffffu, jx_cur, jj & 31), __shfl_sync(0xffffffffu, jy_cur, jj & 31),
+                                     __shfl_sync(0xffffffffu, vis_cur, jj & 31), weight);
+        const bool pasted = c.y != kNoPaste;
+        PatchSums ps{0.f, 0.f, 0.f, 0.f, 0.f};
+        int off[kTileMaxPatch];
+        float tv[kTileMaxPatch];
+        if (LOSS != 0) {
+#pragma unroll
+            for (int k = 0; k < kTileMaxPatch; ++k) {
+                const PatchSlot sl = sh.patch[k * 32 + lane];
+                const int x = c.x + sl.dx, y = c.y + sl.dy;
+                const bool in = pasted && static_cast<unsigned>(x) < static_cast<unsigned>(a.W) &&
+                                static_cast<unsigned>(y) < static_cast<unsigned>(a.H);
+                off[k] = in ? y * a.W + x : -1;
+                tv[k] = in ? sl.t : 0.0f;
+                if (LOSS & HP_LOSS_KL) {
+                    ps.ulogu += in ? sl.ulogu : 0.0f;
+                    ps.u += (tv[k] != 0.0f) ? tv[k] + a.eps : 0.0f;
+                }
+            }
+            if (LOSS & HP_LOSS_KL) {
+                const float r = warp_sum3_scattered(ps.u, ps.ulogu, 0.0f, lane);
+                ps.u = __shfl_sync(0xffffffffu, r, 0);
+                ps.ulogu = __shfl_sync(0xffffffffu, r, 8);
+            }
+        }
+        BulkAcc A;
+        A.M = -INFINITY;
+        A.idx = 0;
+        A.s2 = A.sp2 = A.spp2 = make_float2(0.f, 0.f);
+        // ---- the map, chunk by chunk, from shared memory ----------------------------------------------------------
+        for (int ch = 0; ch < n_chunks; ++ch, ++q) {
+            const int s = q % KST;
+            const uint32_t parity = static_cast<uint32_t>(q / KST) & 1u;
+            const float* buf = reinterpret_cast<const float*>(my_stage + s * kChunkBytes);
+            mbar_wait(bar_u32 + 8 * s, parity);
+            bulk_chunk<NITC, LOSS, MULTI>(A, reinterpret_cast<const float4*>(buf), ch, lane);
+            if (LOSS != 0) {
+#pragma unroll
+                for (int k = 0; k < kTileMaxPatch; ++k) {
+                    const int rel = off[k] - ch * kChunkElems;
+                    const bool here = MULTI ? (static_cast<unsigned>(rel) < static_cast<unsigned>(kChunkElems)) : (rel >= 0);
+                    const float pk = here ? buf[rel] : 0.0f;
+                    const float tk = here ? tv[k] : 0.0f;
+                    if (LOSS & HP_LOSS_KL) {
+                        const float u = (tk != 0.0f) ? tk + a.eps : 0.0f;
+                        ps.up = fmaf(u, pk, ps.up);
+                        ps.p += pk;
+                    }
+                    if (LOSS & HP_LOSS_MSE) ps.e = fmaf(tk, tk - 2.0f * pk, ps.e);
+                }
+            }
+            // the stage has been read out (every lane's values are in registers): request the chunk KST ahead
+            __syncwarp();
+            if (lane == 0 && q_load < q_total) {
+                mbar_arrive_expect_tx(bar_u32 + 8 * s, kChunkBytes);
+                bulk_load(stage_u32 + s * kChunkBytes, my_first + load_jj * map_stride + load_c * kChunkElems, kChunkBytes,
+                          bar_u32 + 8 * s, pol);
+                ++q_load;
+                if (++load_c == n_chunks) {
+                    load_c = 0;
+                    ++load_jj;
+                }
+            }
+        }
+        // ---- warp reductions ---------------------------------------------------------------------------------------
+        float sum_exp, sum_p, sum_pp;
+        {
+            const float r = warp_sum3_scattered(A.s2.x + A.s2.y, A.sp2.x + A.sp2.y, A.spp2.x + A.spp2.y, lane);
+            sum_exp = __shfl_sync(0xffffffffu, r, 0);
+            sum_p = __shfl_sync(0xffffffffu, r, 8);
+            sum_pp = __shfl_sync(0xffffffffu, r, 16);
+        }
+        if (LOSS != 0) {
+            const float r = warp_sum3_scattered(ps.up, ps.p, ps.e, lane);
+            ps.up = __shfl_sync(0xffffffffu, r, 0);
+            ps.p = __shfl_sync(0xffffffffu, r, 8);
+            ps.e = __shfl_sync(0xffffffffu, r, 16);
+        }
+        ArgMax am;
+        am.v = A.M;
+        am.i = A.idx;
+        if (sum_p != sum_p) {
+            // a NaN (or +inf with -inf) is in the map: redo the argmax with numpy's exact rules from memory (L2)
+            ArgMax sx = am_init();
+            const float4* m4 = reinterpret_cast<const float4*>(a.pred + static_cast<size_t>(map) * a.HW);
+            for (int e4 = lane; e4 < a.HW / 4; e4 += 32) am_scan4<true>(sx, ldg_stream4(m4 + e4), e4 * 4);
+            am = warp_argmax(sx, lane);
+            sum_exp = __int_as_float(0x7fc00000);  // log_softmax of a map holding a NaN is NaN
+        }
+        // ---- closure: decode, PCK, losses (float64), publish -------------------------------------------------------
+        uint32_t qy, qx;
+        a.wdiv.divmod(static_cast<uint32_t>(am.i), qy, qx);
+        const float keep = (am.v > 0.0f) ? 1.0f : 0.0f;  // NaN -> 0 (keypoint_detection.py:31-34)
+        const float px = static_cast<float>(qx) * keep, py = static_cast<float>(qy) * keep;
+        // decoding the generated target: its unique maximum (exactly 1.0) sits on the centre when pasted;
+        // the all-zero map decodes to the masked (0,0)   
+        const float tx = pasted ? static_cast<float>(c.x) : 0.0f, ty = pasted ? static_cast<float>(c.y) : 0.0f;
+        int valid, hit;
+        pipe_pck(a, px, py, tx, ty, valid, hit);
+        double mse, kl;
+        pipe_losses<LOSS>(a, c, weight, am.v, sum_exp, sum_p, sum_pp, ps, mse, kl);
+        griddep_wait();  // first global write of this launch comes next (returns at once when already satisfied)
+        if (lane == 0) {
+            if (LOSS & HP_LOSS_MSE) warp_loss_add(wl, 0, mse);
+            if (LOSS & HP_LOSS_KL) warp_loss_add(wl, 1, kl);
+            a.pred_xy[2 * map + 0] = px;
+            a.pred_xy[2 * map + 1] = py;
+            if (a.maxvals) a.maxvals[map] = am.v;
+            if (a.weight_out) a.weight_out[map] = weight;
+            const int k = map - static_cast<int>(t.kdiv.div(static_cast<uint32_t>(map))) * a.K;
+            if (valid) atomicAdd(&sh.counts[a.K + k], 1);
+            if (hit) atomicAdd(&sh.counts[k], 1);
+        }
+    }
+
+    // ---- epilogue: block sums -> workspace (integer atomics: exact, order-free), last block publishes ---------
+    if (lane == 0) {
+        for (int w = 0; w < 2; ++w)
+            if (wl->fx[w] != 0) atomicAdd(&sh.acc[w], static_cast<unsigned long long>(wl->fx[w]));
+        for (int i = 0; i < 6; ++i)
+            if (wl->cls[i] != 0) atomicAdd(&sh.acc[2 + i], static_cast<unsigned long long>(wl->cls[i]));
+    }
+    __syncthreads();
+    griddep_wait();
+    for (int i = threadIdx.x; i < 8 + 2 * a.K; i += blockDim.x) {
+        if (i < 8) {
+            const unsigned long long v = sh.acc[i];
+            if (v != 0) atomicAdd(&a.ws->acc[i], v);
+        } else {
+            const int v = sh.counts[i - 8];
+            if (v != 0) atomicAdd(&a.ws->counts[i - 8], v);
+        }
+        __threadfence();
+    }
+    if (pipeline_last_block(a.ws)) pipeline_publish(a);
+}
+
+}  // namespace hp

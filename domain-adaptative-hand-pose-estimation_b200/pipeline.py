@@ -82,10 +82,14 @@ class HeatmapPipeline:
         _lib.load()
 
     # ------------------------------------------------------------------------------ device path
-    def plan(self, pred, joints, vis, out=None, finalize=True):
+    def plan(self, pred, joints, vis, out=None, finalize=True, overlap=False):
         """Validate once and return ``(launch, out)``: ``launch()`` enqueues the fused kernel on the
         current stream with pre-bound arguments (a ~15 us kernel leaves no room for per-call Python
-        argument checking; this is also what gets captured into CUDA graphs)."""
+        argument checking; this is also what gets captured into CUDA graphs).
+
+        ``overlap=True`` (HP_PIPE_OVERLAP_PREV): the launch may start while the previous kernel on the
+        stream is still draining.  Only for steps over batches that are already resident: ``pred``,
+        ``joints`` and ``vis`` must not be written by the kernel launched right before this one."""
         pred = _lib.require_cuda(pred, "HeatmapPipeline(pred)")
         joints = _lib.require_cuda(joints, "HeatmapPipeline(joints)", torch.float64)
         vis = _lib.require_cuda(vis, "HeatmapPipeline(vis)")
@@ -100,18 +104,19 @@ class HeatmapPipeline:
         if out is None:
             out = self.alloc_outputs(B, dev)
         ws = self._workspace(B * K)
-        fn = _lib.load().hp_pipeline_fused
+        fn = _lib.load().hp_pipeline_fused_ex
         args = (_lib.ptr(pred), _lib.ptr(joints), _lib.ptr(vis), B, K, H, W, C.c_double(self.stride[0]),
                 C.c_double(self.stride[1]), self.tmp, _lib.ptr(self.tab), C.c_float(self.kl_epsilon),
                 C.c_double(self.thr), self.loss_mask, _lib.ptr(out.pred_xy), _lib.ptr(out.maxvals), _lib.ptr(out.weight),
-                _lib.ptr(out.partial), 0, _lib.ptr(out.result) if finalize else None, _lib.ptr(ws))
+                _lib.ptr(out.partial), 0, _lib.ptr(out.result) if finalize else None, _lib.ptr(ws),
+                C.c_uint(_lib.PIPE_OVERLAP_PREV if overlap else 0))
         keep = (pred, joints, vis, out, ws)            # the plan owns references: pointers stay valid
         current_stream = torch.cuda.current_stream
 
         def launch(_keep=keep):
             rc = fn(*args, C.c_void_p(current_stream(dev).cuda_stream))
             if rc != 0:
-                raise RuntimeError(f"hp_pipeline_fused failed (rc={rc}): "
+                raise RuntimeError(f"hp_pipeline_fused_ex failed (rc={rc}): "
                                    f"{_lib.load().hp_last_error().decode(errors='replace')}")
         return launch, out
 
@@ -123,29 +128,29 @@ class HeatmapPipeline:
                 self._ws = torch.zeros(max(need, 1 << 16), dtype=torch.uint8, device=self.device)
         return self._ws
 
-    def _cached_plan(self, pred, joints, vis, out, finalize):
-        key = (pred.data_ptr(), joints.data_ptr(), vis.data_ptr(), id(out), pred.shape[0], finalize)
+    def _cached_plan(self, pred, joints, vis, out, finalize, overlap=False):
+        key = (pred.data_ptr(), joints.data_ptr(), vis.data_ptr(), id(out), pred.shape[0], finalize, overlap)
         hit = self._plans.get(key)
         if hit is None:
             if len(self._plans) > 256:
                 self._plans.clear()
-            hit = self.plan(pred, joints, vis, out, finalize)
+            hit = self.plan(pred, joints, vis, out, finalize, overlap)
             self._plans[key] = hit
         return hit
 
-    def launch_local(self, pred, joints, vis, out=None) -> PipelineResult:
+    def launch_local(self, pred, joints, vis, out=None, overlap=False) -> PipelineResult:
         """This rank's kernel only (finalised locally, no collective)."""
-        launch, out = self._cached_plan(pred, joints, vis, out, True)
+        launch, out = self._cached_plan(pred, joints, vis, out, True, overlap)
         launch()
         return out
 
-    def __call__(self, pred, joints, vis, out=None) -> PipelineResult:
+    def __call__(self, pred, joints, vis, out=None, overlap=False) -> PipelineResult:
         """pred float32 [B,K,H,W], joints float64 [B,K,2] (image px), vis float32 [B,K,1]|[B,K]: CUDA
         tensors of THIS rank's slice of the batch.  Asynchronous on the current stream.  Single process:
         one kernel.  Sharded (torch.distributed initialised): kernel -> all-reduce of the 4+2K partial
         doubles (the path's only collective) -> finalise kernel."""
         sharded = hpdist.is_distributed(self.group)
-        launch, out = self._cached_plan(pred, joints, vis, out, not sharded)
+        launch, out = self._cached_plan(pred, joints, vis, out, not sharded, overlap)
         launch()
         if sharded:
             # The collective and the finalise run on a side stream so that they overlap the NEXT step's

@@ -181,6 +181,20 @@ int hp_pipeline_fused(const float* pred, const double* joints, const float* vis,
                       float* pred_xy, float* maxvals, float* weight_out,
                       int64_t* partial, int accumulate, double* result, void* workspace,
                       hp_stream_t stream);
+/* Same, with launch flags.
+ *   HP_PIPE_OVERLAP_PREV: the launch may begin (programmatic dependent launch) while the previous kernel
+ *   on `stream` is still draining: blocks of this launch read pred / joints / vis / tab as soon as SMs
+ *   free up, but write nothing and do not touch `workspace` until the previous kernel has completed.
+ *   Contract: pred, joints, vis and tab must NOT be produced by the kernel launched right before this
+ *   one on `stream` (steps over independent, already resident batches - e.g. back-to-back calls of this
+ *   function); everything else is as hp_pipeline_fused. */
+#define HP_PIPE_OVERLAP_PREV 1u
+int hp_pipeline_fused_ex(const float* pred, const double* joints, const float* vis,
+                         int B, int K, int H, int W, double stride_x, double stride_y, int tmp,
+                         const float* tab, float kl_epsilon, double thr, int loss_mask,
+                         float* pred_xy, float* maxvals, float* weight_out,
+                         int64_t* partial, int accumulate, double* result, void* workspace,
+                         unsigned int flags, hp_stream_t stream);
 /* partial (e.g. after an NCCL all-reduce over ranks) -> result, on device */
 int hp_pipeline_finalize(const int64_t* partial, int K, double* result, hp_stream_t stream);
 

@@ -150,6 +150,86 @@ def test_pipeline_full_size_properties():
         assert torch.equal(out2.result, r1) and torch.equal(out2.partial, p1) and torch.equal(out2.pred_xy, xy1)
 
 
+def _assert_pipeline_equals_oracle(d, out, want, K):
+    got = out.host()
+    part = out.partial.cpu().numpy()
+    assert np.array_equal(out.pred_xy.cpu().numpy(), want["pred_xy"])
+    _, want_max = O.get_max_preds(d["pred"])
+    assert np.array_equal(out.maxvals.cpu().numpy().reshape(-1), want_max.reshape(-1), equal_nan=True)
+    assert np.array_equal(out.weight.cpu().numpy(), want["weight"])
+    assert np.array_equal(part[4:4 + K].astype(np.int64), want["hits"])
+    assert np.array_equal(part[4 + K:4 + 2 * K].astype(np.int64), want["valid"])
+    assert np.array_equal(got["acc"], want["acc"]) and got["avg_acc"] == want["avg_acc"] and got["cnt"] == want["cnt"]
+    return got
+
+
+@pytest.mark.parametrize("size", [64, 32, 16, 128])
+def test_pipeline_argmax_edge_maps(size):
+    """Ties in every (iteration, lane, component) position, all<=0, -inf, +inf and NaN maps through the
+    TMA-staged kernel: coordinates / maxvals / PCK bit-exact against the oracle (numpy: first index wins,
+    NaN beats everything and is masked to (0,0))."""
+    B, K = 6, 21
+    d = hp.synth.make_host_batch(861 + size, B, K, size, size)
+    rs = np.random.RandomState(5)
+    flat = d["pred"].reshape(B * K, -1)
+    HW = size * size
+    for m in range(0, 60):                       # duplicated maxima at random positions
+        pos = np.sort(rs.choice(HW, size=3, replace=False))
+        flat[m, pos] = flat[m].max() + 1.0
+    flat[60, :] = -1.0                           # all <= 0 -> (0,0)
+    flat[62, :] = 0.25; flat[62, HW - 1] = 0.25  # constant map: index 0
+    flat[66, HW - 1] = flat[66].max() + 2.0      # maximum in the very last element
+    flat[67, 0] = flat[67].max() + 2.0           # and in the very first
+    want = O.pipeline(d["pred"], d["joints"], d["vis"], kl_epsilon=1e-7)
+    _, out = _run_pipeline(d, 1e-7)
+    got = _assert_pipeline_equals_oracle(d, out, want, K)
+    np.testing.assert_allclose(got["mse"], want["mse"], rtol=1e-5)
+    np.testing.assert_allclose(got["kl"], want["kl"], rtol=1e-5)
+    # non-finite maps: the losses become NaN / inf exactly like the reference's
+    flat[61, :] = -np.inf                        # all -inf
+    flat[63, rs.randint(HW)] = np.inf            # +inf
+    flat[64, HW // 2 + 3] = np.nan               # one NaN
+    flat[65, 5] = np.nan; flat[65, 4] = np.inf   # NaN after a larger value: NaN still wins
+    want = O.pipeline(d["pred"], d["joints"], d["vis"], kl_epsilon=1e-7)
+    _, out = _run_pipeline(d, 1e-7)
+    got = _assert_pipeline_equals_oracle(d, out, want, K)
+    for name in ("mse", "kl"):
+        assert not np.isfinite(want[name])
+        assert np.isnan(got[name]) == np.isnan(want[name]) and (np.isnan(want[name]) or got[name] == want[name])
+
+
+def test_pipeline_many_maps_per_warp():
+    """More than 32 maps per warp (second batch of lane-distributed keypoints) and a wrapped stage ring:
+    2800 x 21 maps of 16x16 and 40 x 21 maps of 128x128 against the oracle."""
+    for size, B, seed in ((16, 2800, 871), (128, 40, 872)):
+        d = hp.synth.make_host_batch(seed, B, 21, size, size)
+        want = O.pipeline(d["pred"], d["joints"], d["vis"], kl_epsilon=1e-7)
+        _, out = _run_pipeline(d, 1e-7)
+        got = _assert_pipeline_equals_oracle(d, out, want, 21)
+        np.testing.assert_allclose(got["mse"], want["mse"], rtol=1e-5)
+        np.testing.assert_allclose(got["kl"], want["kl"], rtol=1e-5)
+
+
+def test_pipeline_overlapped_launches_are_bit_identical():
+    """HP_PIPE_OVERLAP_PREV (programmatic dependent launch): a train of back-to-back launches over resident
+    batches with separate outputs gives exactly the results of fully serialised launches."""
+    B, n = 256, 6
+    sets = [hp.synth.make_device_batch(881 + i, B) for i in range(n)]
+    pipe = hp.HeatmapPipeline(kl_epsilon=1e-7)
+    ref = []
+    for s in sets:
+        o = pipe(s["pred"], s["joints"], s["vis"])
+        ref.append((o.result.clone(), o.partial.clone(), o.pred_xy.clone(), o.maxvals.clone(), o.weight.clone()))
+    outs = [pipe.alloc_outputs(B) for _ in range(n)]
+    for rep in range(5):
+        for s, o in zip(sets, outs):
+            pipe(s["pred"], s["joints"], s["vis"], out=o, overlap=True)
+    torch.cuda.synchronize()
+    for o, r in zip(outs, ref):
+        assert torch.equal(o.result, r[0]) and torch.equal(o.partial, r[1]) and torch.equal(o.pred_xy, r[2])
+        assert torch.equal(o.maxvals, r[3]) and torch.equal(o.weight, r[4])
+
+
 # ------------------------------------------------------------------ generic shapes / edge cases
 
 @pytest.mark.parametrize("H,W,K", [(30, 42, 5), (20, 20, 21), (100, 100, 3), (7, 5, 2), (96, 72, 4), (256, 256, 2)])
