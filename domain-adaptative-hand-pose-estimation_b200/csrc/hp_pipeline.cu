@@ -202,16 +202,20 @@ struct PipeLaunch {
 };
 
 static int g_sm_count = 0;
+// profiling only (hp_debug_pipeline_trace): two launch slots, alternating
+static unsigned long long* g_trace = nullptr;
+static size_t g_trace_words = 0;
+static unsigned long long g_trace_seq = 0;
 
 // ---- TMA-staged shape (hp_pipeline_bulk.cuh) ---------------------------------------------------------------------
-template <int NITC, int LOSS, bool MULTI, int W, int KST>
+template <int NITC, int LOSS, bool MULTI, int W, int KST, int BPS>
 static cudaError_t launch_bulk_one(const BulkArgs& t, int grid, cudaStream_t stream) {
     constexpr size_t smem = static_cast<size_t>(W) * KST * NITC * 512 + sizeof(uint64_t) * W * KST;
     static bool configured[16] = {};  // per device: opt in to > 48 KB of dynamic shared memory once
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 16 || !configured[dev]) {
-        const cudaError_t e = cudaFuncSetAttribute(pipeline_bulk_kernel<NITC, LOSS, MULTI, W, KST>,
+        const cudaError_t e = cudaFuncSetAttribute(pipeline_bulk_kernel<NITC, LOSS, MULTI, W, KST, BPS>,
                                                    cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < 16) configured[dev] = true;
@@ -226,15 +230,16 @@ static cudaError_t launch_bulk_one(const BulkArgs& t, int grid, cudaStream_t str
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = t.overlap ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, pipeline_bulk_kernel<NITC, LOSS, MULTI, W, KST>, t);
+    return cudaLaunchKernelEx(&cfg, pipeline_bulk_kernel<NITC, LOSS, MULTI, W, KST, BPS>, t);
 }
-template <int NITC, bool MULTI, int W, int KST>
-static cudaError_t launch_bulk(const BulkArgs& t, int grid, cudaStream_t stream) {
+template <int NITC, bool MULTI, int W, int KST, int BPS>
+static cudaError_t launch_bulk(const BulkArgs& t, int sms, cudaStream_t stream) {
+    const int grid = t.p.n_maps < sms * BPS ? t.p.n_maps : sms * BPS;  // persistent: BPS blocks per SM
     switch (t.p.loss_mask) {
-        case 0: return launch_bulk_one<NITC, 0, MULTI, W, KST>(t, grid, stream);
-        case HP_LOSS_MSE: return launch_bulk_one<NITC, 1, MULTI, W, KST>(t, grid, stream);
-        case HP_LOSS_KL: return launch_bulk_one<NITC, 2, MULTI, W, KST>(t, grid, stream);
-        default: return launch_bulk_one<NITC, 3, MULTI, W, KST>(t, grid, stream);
+        case 0: return launch_bulk_one<NITC, 0, MULTI, W, KST, BPS>(t, grid, stream);
+        case HP_LOSS_MSE: return launch_bulk_one<NITC, 1, MULTI, W, KST, BPS>(t, grid, stream);
+        case HP_LOSS_KL: return launch_bulk_one<NITC, 2, MULTI, W, KST, BPS>(t, grid, stream);
+        default: return launch_bulk_one<NITC, 3, MULTI, W, KST, BPS>(t, grid, stream);
     }
 }
 // 0 = tiles/stream shapes, 1.. = bulk shape with (warps, stages per warp) variants for 64x64
@@ -243,7 +248,7 @@ static int pipeline_shape_choice() {
         const char* e = std::getenv("HP_PIPE_SHAPE");
         if (!e) return 1;
         if (e[0] == 't' || e[0] == 'T') return 0;       // "tiles": the register-tile kernels
-        if (e[0] >= '1' && e[0] <= '5') return e[0] - '0';
+        if (e[0] >= '1' && e[0] <= '4') return e[0] - '0';
         return 1;
     }();
     return choice;
@@ -292,18 +297,19 @@ static int launch_pipeline(const float* pred, const double* joints, const float*
         t.kdiv = FastDiv(static_cast<uint32_t>(K));
         t.n_chunks = HW > 4096 ? HW / 4096 : 1;
         t.overlap = (flags & HP_PIPE_OVERLAP_PREV) ? 1 : 0;
-        const int grid = a.n_maps < g_sm_count ? a.n_maps : g_sm_count;  // one persistent block per SM
+        const size_t trace_words = static_cast<size_t>(kTraceBlockWords) * static_cast<size_t>(g_sm_count);
+        if (g_trace && g_trace_words >= 2 * trace_words) t.trace = g_trace + (g_trace_seq++ & 1) * trace_words;
+        const int sms = g_sm_count;
         cudaError_t e;
-        if (HW == 256) e = launch_bulk<2, false, 12, 8>(t, grid, stream);
-        else if (HW == 1024) e = launch_bulk<8, false, 12, 4>(t, grid, stream);
-        else if (HW > 4096) e = launch_bulk<32, true, 6, 2>(t, grid, stream);
+        if (HW == 256) e = launch_bulk<2, false, 6, 8, 2>(t, sms, stream);
+        else if (HW == 1024) e = launch_bulk<8, false, 6, 4, 2>(t, sms, stream);
+        else if (HW > 4096) e = launch_bulk<32, true, 3, 2, 2>(t, sms, stream);
         else {
             switch (pipeline_shape_choice()) {
-                case 2: e = launch_bulk<32, false, 6, 2>(t, grid, stream); break;
-                case 3: e = launch_bulk<32, false, 4, 3>(t, grid, stream); break;
-                case 4: e = launch_bulk<32, false, 8, 1>(t, grid, stream); break;
-                case 5: e = launch_bulk<32, false, 13, 1>(t, grid, stream); break;
-                default: e = launch_bulk<32, false, 12, 1>(t, grid, stream); break;
+                case 2: e = launch_bulk<32, false, 12, 1, 1>(t, sms, stream); break;
+                case 3: e = launch_bulk<32, false, 4, 1, 3>(t, sms, stream); break;
+                case 4: e = launch_bulk<32, false, 3, 2, 2>(t, sms, stream); break;
+                default: e = launch_bulk<32, false, 6, 1, 2>(t, sms, stream); break;
             }
         }
         if (e != cudaSuccess) return fail(static_cast<int>(e), "hp_pipeline_fused: %s", cudaGetErrorString(e));
@@ -399,6 +405,22 @@ extern "C" HP_API int hp_pipeline_fused_ex(const float* pred, const double* join
     return launch_pipeline(pred, joints, vis, B, K, H, W, stride_x, stride_y, tmp, tab, kl_epsilon, thr, loss_mask,
                            pred_xy, maxvals, weight_out, reinterpret_cast<long long*>(partial), accumulate, result,
                            workspace, static_cast<cudaStream_t>(stream), flags);
+}
+
+/* profiling aid: blocks of the TMA-staged pipeline kernel stamp their timeline into `buf` (device memory,
+ * uint64 words; two alternating launch slots of hp_debug_pipeline_trace_words() words each).  NULL switches it off. */
+extern "C" HP_API size_t hp_debug_pipeline_trace_words(void) {
+    if (g_sm_count == 0) {
+        g_sm_count = hp_device_sm_count();
+        if (g_sm_count <= 0) g_sm_count = 148;
+    }
+    return static_cast<size_t>(kTraceBlockWords) * static_cast<size_t>(g_sm_count);
+}
+extern "C" HP_API int hp_debug_pipeline_trace(void* buf, size_t words) {
+    g_trace = static_cast<unsigned long long*>(buf);
+    g_trace_words = buf ? words : 0;
+    g_trace_seq = 0;
+    return HP_OK;
 }
 
 extern "C" HP_API int hp_pipeline_finalize(const int64_t* partial, int K, double* result, hp_stream_t stream) {

@@ -28,6 +28,8 @@ struct BulkArgs {
     FastDiv kdiv;   // by K (joint index of a map)
     int n_chunks;   // chunks per map (1 unless the map is larger than a stage)
     int overlap;    // launched with programmatic stream serialization (HP_PIPE_OVERLAP_PREV)
+    unsigned long long* trace;  // nullable profiling buffer (hp_debug_pipeline_trace): per block a header
+                                // {globaltimer, clock64} at entry and exit, per warp and map 4 clock64 stamps
 };
 
 // ---- mbarrier / bulk-copy primitives (PTX; SASS: SYNCS.*, UBLKCP) ---------------------------------------
@@ -84,6 +86,17 @@ __device__ __forceinline__ float warp_max_f32(float x) {
     float r;
     asm("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(x));
     return r;
+}
+
+// trace buffer layout (uint64): block b at b * kTraceBlockWords: [0] globaltimer in, [1] clock in, [2] globaltimer out,
+// [3] clock out, then per warp w (<= 16) and map jj (< kTraceMaps): 4 stamps {wait begins, data landed, refill issued,
+// map closed}
+constexpr int kTraceMaps = 8;
+constexpr int kTraceBlockWords = 4 + 16 * kTraceMaps * 4;
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
 }
 
 // ---- per-lane accumulators of one map ------------------------------------------------------------------
@@ -150,17 +163,102 @@ __device__ __forceinline__ void bulk_chunk(BulkAcc& A, const float4* __restrict_
     A.spp2 = spp2;
 }
 
+// per-map losses from the reduced sums, float32 closure (a per-map loss only has float32 accuracy anyway; the
+// exact part - the accumulation over maps - is the 64-bit fixed-point sum).  Same algebra as pipe_losses.
+template <int LOSS>
+__device__ __forceinline__ void bulk_losses(const PipeArgs& a, Centre c, float weight, float inv_hw, float vmax,
+                                            float sum_exp, float sum_p, float sum_pp, const PatchSums& ps, float& mse,
+                                            float& kl) {
+    mse = 0.0f;
+    kl = 0.0f;
+    if (LOSS & HP_LOSS_MSE)  // mean over HW of 0.5*w*(p-t)^2 (loss.py:59-65); sum (p-t)^2 = sum p^2 + sum_patch t(t-2p)
+        mse = 0.5f * weight * ((sum_pp + ps.e) * inv_hw);
+    if (LOSS & HP_LOSS_KL) {
+        const float n_bg = static_cast<float>(a.HW - pipe_patch_area(a, c));
+        const float Su = fmaf(a.eps, n_bg, ps.u);
+        const float Sup = fmaf(a.eps, sum_p - ps.p, ps.up);
+        const float Sulogu = fmaf(n_bg, a.eps_log_eps, ps.ulogu);
+        const float lse = fmaf(lg2_approx(sum_exp), kLn2, vmax);
+        // Su == 0 (eps 0 and nothing pasted) -> 0/0 = NaN, like the reference
+        const float L = __fdividef(Sulogu - Sup, Su) - lg2_approx(Su) * kLn2 + lse;
+        kl = L * weight;
+    }
+}
+// fixed-point accumulate of a float32 per-map loss: v * 2^40 is an exact scaling, the conversion is exact
+__device__ __forceinline__ void warp_loss_add_f32(WarpLoss* w, int which, float v) {
+    if (fabsf(v) < static_cast<float>(kFxLimit)) w->fx[which] += __float2ll_rn(v * 1099511627776.0f);
+    else warp_loss_add_nonfinite(w, which, static_cast<double>(v));
+}
+
 // shared memory of the kernel besides the stages
+constexpr int kBulkOutCap = 64;  // per-map outputs of a block that wait in shared memory for the previous grid
 struct BulkShared {
     PatchSlot patch[kTileMaxPatch * 32];
     int counts[2 * HP_MAX_K];       // PCK hits / valid of this block
     unsigned long long acc[8];      // loss sums (fixed point) and non-finite counters of this block
+    float4 out[kBulkOutCap];        // {x, y, maxval, weight} of the block's first maps
+    long long pub[4 + 2 * HP_MAX_K + 6];
+    double pub_acc[HP_MAX_K];
 };
 
+// last block, ONE warp: workspace -> partial (= or +=), workspace back to zero, optional finalise
+// (same results as pipeline_publish, without block barriers)
+__device__ __forceinline__ void bulk_publish_warp(const PipeArgs& a, BulkShared& sh, int lane) {
+    const int K = a.K, n = 4 + 2 * K + 6;
+    const bool add = a.accumulate != 0;
+    for (int i = lane; i < n; i += 32) {
+        long long v;
+        if (i < 2) {
+            v = static_cast<long long>(*reinterpret_cast<volatile unsigned long long*>(&a.ws->acc[i]));
+            a.ws->acc[i] = 0;
+        } else if (i == 2) {
+            v = a.n_maps;
+        } else if (i == 3) {
+            v = static_cast<long long>(a.n_maps) * a.HW;
+        } else if (i < 4 + 2 * K) {
+            v = *reinterpret_cast<volatile int*>(&a.ws->counts[i - 4]);
+            a.ws->counts[i - 4] = 0;
+        } else {
+            const int j = 2 + (i - 4 - 2 * K);
+            v = static_cast<long long>(*reinterpret_cast<volatile unsigned long long*>(&a.ws->acc[j]));
+            a.ws->acc[j] = 0;
+        }
+        if (add) v += a.partial[i];
+        a.partial[i] = v;
+        sh.pub[i] = v;
+    }
+    __syncwarp();
+    if (a.result) {
+        for (int k = lane; k < K; k += 32) {
+            const long long h = sh.pub[4 + k], v = sh.pub[4 + K + k];
+            const double acc = v > 0 ? __ddiv_rn(static_cast<double>(h) * 1.0, static_cast<double>(v)) : -1.0;
+            sh.pub_acc[k] = acc;
+            a.result[4 + k] = acc;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            double total = 0.0;
+            int cnt = 0;
+            for (int k = 0; k < K; ++k)
+                if (sh.pub_acc[k] >= 0.0) {
+                    total = __dadd_rn(total, sh.pub_acc[k]);
+                    ++cnt;
+                }
+            const long long* cls = sh.pub + 4 + 2 * K;
+            a.result[0] = loss_from_fx(sh.pub[0], cls[0], cls[1], cls[2], sh.pub[2]);
+            a.result[1] = loss_from_fx(sh.pub[1], cls[3], cls[4], cls[5], sh.pub[2]);
+            a.result[2] = cnt != 0 ? __ddiv_rn(total, static_cast<double>(cnt)) : 0.0;
+            a.result[3] = static_cast<double>(cnt);
+        }
+    }
+    if (lane == 0) a.ws->counter = 0;
+}
+
 // NITC: iterations (of 128 elements) per chunk;  MULTI: maps span several chunks;
-// W warps per block, KST private stages per warp.
-template <int NITC, int LOSS, bool MULTI, int W, int KST>
-__global__ void __launch_bounds__(32 * W, 1) pipeline_bulk_kernel(const BulkArgs t) {
+// W warps per block, KST private stages per warp, BPS blocks per SM (W*BPS warps and W*KST*BPS stages per SM:
+// several small blocks per SM let the blocks of the NEXT launch take over an SM piecewise while this launch drains).
+template <int NITC, int LOSS, bool MULTI, int W, int KST, int BPS>
+__global__ void __launch_bounds__(32 * W, BPS) pipeline_bulk_kernel(const BulkArgs t) {
     extern __shared__ __align__(128) unsigned char s_dyn[];
     __shared__ BulkShared sh;
     __shared__ WarpLoss s_wl[W];
@@ -177,19 +275,31 @@ __global__ void __launch_bounds__(32 * W, 1) pipeline_bulk_kernel(const BulkArgs
     unsigned char* my_stage = s_dyn + static_cast<size_t>(warp) * KST * kChunkBytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_dyn + static_cast<size_t>(W) * KST * kChunkBytes) + warp * KST;
     const uint32_t stage_u32 = smem_addr(my_stage), bar_u32 = smem_addr(bars);
-    const uint64_t pol = l2_evict_first_policy();
     const size_t map_stride = static_cast<size_t>(gridDim.x) * W * a.HW;  // between consecutive maps of this warp
     const float* my_first = a.pred + (static_cast<size_t>(blockIdx.x) + static_cast<size_t>(warp) * gridDim.x) * a.HW;
 
     // Programmatic dependent launch (no-ops unless the launch carries the attribute): the next launch on the
-    // stream may start filling SMs as soon as this grid's blocks retire; nothing of a launch is WRITTEN (and
-    // the shared workspace is not touched) before griddep_wait() has seen the previous grid complete.
+    // stream may start filling SMs as soon as this grid's blocks retire; nothing of a launch is WRITTEN to
+    // global memory (and the shared workspace is not touched) before griddep_wait() has seen the previous grid
+    // complete - per-map outputs wait in shared memory until then.
     griddep_launch_dependents();
+    unsigned long long* trace = t.trace ? t.trace + static_cast<size_t>(blockIdx.x) * kTraceBlockWords : nullptr;
+    if (trace && threadIdx.x == 0) {
+        trace[0] = global_timer_ns();
+        trace[1] = static_cast<unsigned long long>(clock64());
+    }
+    unsigned long long* wtrace = (trace && lane == 0 && warp < 16) ? trace + 4 + warp * (kTraceMaps * 4) : nullptr;
     // ---- prologue ----------------------------------------------------------------------------------------------
-    // The small global loads are ISSUED first and consumed after the bulk copies have been requested: once
-    // 148 x 192 KB of bulk traffic is queued, a plain load waits microseconds behind it (the first version
-    // of this kernel loaded each map's keypoint right before use and spent a third of its time there).
-    // Keypoints are lane-distributed: lane l of a warp holds the keypoint of the warp's map 32*batch + l.
+    // Order matters: (1) arm the ring (the init fence would otherwise wait for the loads below), (2) ISSUE the
+    // small global loads, (3) request the bulk copies, (4) consume the small loads.  Once 148 x 192 KB of bulk
+    // traffic is queued a plain load waits microseconds behind it (the first version of this kernel loaded each
+    // map's keypoint right before use and spent a third of its time there).
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < KST; ++s) mbar_init(bar_u32 + 8 * s, 1);
+        mbar_init_fence();
+    }
+    // keypoints are lane-distributed: lane l of a warp holds the keypoint of the warp's map 32*batch + l
     const bool joints16 = (reinterpret_cast<uintptr_t>(a.joints) & 15u) == 0;
     double jx_cur = 0.0, jy_cur = 0.0, jx_nxt = 0.0, jy_nxt = 0.0;
     float vis_cur = 0.0f, vis_nxt = 0.0f;
@@ -229,12 +339,10 @@ __global__ void __launch_bounds__(32 * W, 1) pipeline_bulk_kernel(const BulkArgs
             my_slot[r].t = a.tab[my_slot[r].dx * my_slot[r].dx + my_slot[r].dy * my_slot[r].dy];
         }
     }
-    // arm the private ring and request the first KST chunks
+    // request the first KST chunks
+    const uint64_t pol = l2_evict_first_policy();
     int q_load = 0, load_jj = 0, load_c = 0;  // next chunk to request
     if (lane == 0) {
-#pragma unroll
-        for (int s = 0; s < KST; ++s) mbar_init(bar_u32 + 8 * s, 1);
-        mbar_init_fence();
 #pragma unroll
         for (int s = 0; s < KST; ++s) {
             if (q_load < q_total) {
@@ -271,9 +379,12 @@ __global__ void __launch_bounds__(32 * W, 1) pipeline_bulk_kernel(const BulkArgs
     __syncthreads();  // the only block barrier before the epilogue
 
     WarpLoss* wl = &s_wl[warp];
-    int q = 0;  // chunk being consumed
+    const float inv_hw = 1.0f / static_cast<float>(a.HW);
+    bool dep_ok = false;  // griddep_wait() already executed by this warp
+    int q = 0;            // chunk being consumed
     for (int jj = 0; jj < n_mine; ++jj) {
-        const int map = static_cast<int>(blockIdx.x) + (warp + jj * W) * static_cast<int>(gridDim.x);
+        const int j = warp + jj * W;
+        const int map = static_cast<int>(blockIdx.x) + j * static_cast<int>(gridDim.x);
         // ---- everything that does not need the prediction, while the chunk is in flight ----------------------
         if (jj != 0 && (jj & 31) == 0) {  // next batch of 32 keypoints: requested 32 maps ago
             jx_cur = jx_nxt;
@@ -317,7 +428,9 @@ __global__ void __launch_bounds__(32 * W, 1) pipeline_bulk_kernel(const BulkArgs
             const int s = q % KST;
             const uint32_t parity = static_cast<uint32_t>(q / KST) & 1u;
             const float* buf = reinterpret_cast<const float*>(my_stage + s * kChunkBytes);
+            if (wtrace && jj < kTraceMaps && ch == 0) wtrace[jj * 4 + 0] = static_cast<unsigned long long>(clock64());
             mbar_wait(bar_u32 + 8 * s, parity);
+            if (wtrace && jj < kTraceMaps && ch == 0) wtrace[jj * 4 + 1] = static_cast<unsigned long long>(clock64());
             bulk_chunk<NITC, LOSS, MULTI>(A, reinterpret_cast<const float4*>(buf), ch, lane);
             if (LOSS != 0) {
 #pragma unroll
@@ -346,6 +459,7 @@ __global__ void __launch_bounds__(32 * W, 1) pipeline_bulk_kernel(const BulkArgs
                     ++load_jj;
                 }
             }
+            if (wtrace && jj < kTraceMaps && ch == n_chunks - 1) wtrace[jj * 4 + 2] = static_cast<unsigned long long>(clock64());
         }
         // ---- warp reductions ---------------------------------------------------------------------------------------
         float sum_exp, sum_p, sum_pp;
@@ -372,7 +486,7 @@ __global__ void __launch_bounds__(32 * W, 1) pipeline_bulk_kernel(const BulkArgs
             am = warp_argmax(sx, lane);
             sum_exp = __int_as_float(0x7fc00000);  // log_softmax of a map holding a NaN is NaN
         }
-        // ---- closure: decode, PCK, losses (float64), publish -------------------------------------------------------
+        // ---- closure: decode, PCK, losses, results -----------------------------------------------------------------
         uint32_t qy, qx;
         a.wdiv.divmod(static_cast<uint32_t>(am.i), qy, qx);
         const float keep = (am.v > 0.0f) ? 1.0f : 0.0f;  // NaN -> 0 (keypoint_detection.py:31-34)
@@ -382,20 +496,27 @@ __global__ void __launch_bounds__(32 * W, 1) pipeline_bulk_kernel(const BulkArgs
         const float tx = pasted ? static_cast<float>(c.x) : 0.0f, ty = pasted ? static_cast<float>(c.y) : 0.0f;
         int valid, hit;
         pipe_pck(a, px, py, tx, ty, valid, hit);
-        double mse, kl;
-        pipe_losses<LOSS>(a, c, weight, am.v, sum_exp, sum_p, sum_pp, ps, mse, kl);
-        griddep_wait();  // first global write of this launch comes next (returns at once when already satisfied)
+        float mse, kl;
+        bulk_losses<LOSS>(a, c, weight, inv_hw, am.v, sum_exp, sum_p, sum_pp, ps, mse, kl);
+        if (j >= kBulkOutCap && !dep_ok) {  // results beyond the shared-memory buffer go straight to global memory
+            griddep_wait();
+            dep_ok = true;
+        }
         if (lane == 0) {
-            if (LOSS & HP_LOSS_MSE) warp_loss_add(wl, 0, mse);
-            if (LOSS & HP_LOSS_KL) warp_loss_add(wl, 1, kl);
-            a.pred_xy[2 * map + 0] = px;
-            a.pred_xy[2 * map + 1] = py;
-            if (a.maxvals) a.maxvals[map] = am.v;
-            if (a.weight_out) a.weight_out[map] = weight;
+            if (LOSS & HP_LOSS_MSE) warp_loss_add_f32(wl, 0, mse);
+            if (LOSS & HP_LOSS_KL) warp_loss_add_f32(wl, 1, kl);
+            if (j < kBulkOutCap) {
+                sh.out[j] = make_float4(px, py, am.v, weight);
+            } else {
+                *reinterpret_cast<float2*>(a.pred_xy + 2 * static_cast<size_t>(map)) = make_float2(px, py);
+                if (a.maxvals) a.maxvals[map] = am.v;
+                if (a.weight_out) a.weight_out[map] = weight;
+            }
             const int k = map - static_cast<int>(t.kdiv.div(static_cast<uint32_t>(map))) * a.K;
             if (valid) atomicAdd(&sh.counts[a.K + k], 1);
             if (hit) atomicAdd(&sh.counts[k], 1);
         }
+        if (wtrace && jj < kTraceMaps) wtrace[jj * 4 + 3] = static_cast<unsigned long long>(clock64());
     }
 
     // ---- epilogue: block sums -> workspace (integer atomics: exact, order-free), last block publishes ---------
@@ -406,18 +527,41 @@ __global__ void __launch_bounds__(32 * W, 1) pipeline_bulk_kernel(const BulkArgs
             if (wl->cls[i] != 0) atomicAdd(&sh.acc[2 + i], static_cast<unsigned long long>(wl->cls[i]));
     }
     __syncthreads();
-    griddep_wait();
-    for (int i = threadIdx.x; i < 8 + 2 * a.K; i += blockDim.x) {
-        if (i < 8) {
-            const unsigned long long v = sh.acc[i];
-            if (v != 0) atomicAdd(&a.ws->acc[i], v);
-        } else {
-            const int v = sh.counts[i - 8];
-            if (v != 0) atomicAdd(&a.ws->counts[i - 8], v);
+    griddep_wait();  // the previous grid on the stream is complete: outputs and workspace may be written now
+    if (warp == 0) {
+        for (int i = lane; i < 8 + 2 * a.K; i += 32) {
+            if (i < 8) {
+                const unsigned long long v = sh.acc[i];
+                if (v != 0) atomicAdd(&a.ws->acc[i], v);
+            } else {
+                const int v = sh.counts[i - 8];
+                if (v != 0) atomicAdd(&a.ws->counts[i - 8], v);
+            }
         }
-        __threadfence();
+        __threadfence();  // every lane: its own atomics before the ticket
+        __syncwarp();
+        int last = 0;
+        if (lane == 0) {
+            last = (atomicAdd(&a.ws->counter, 1u) == gridDim.x - 1) ? 1 : 0;
+            if (last) __threadfence();
+        }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last) bulk_publish_warp(a, sh, lane);
+    } else {
+        // the other warps deliver the buffered per-map outputs meanwhile
+        const int n_buf = n_local < kBulkOutCap ? n_local : kBulkOutCap;
+        for (int jb = static_cast<int>(threadIdx.x) - 32; jb < n_buf; jb += 32 * (W - 1)) {
+            const int map = static_cast<int>(blockIdx.x) + jb * static_cast<int>(gridDim.x);
+            const float4 o = sh.out[jb];
+            *reinterpret_cast<float2*>(a.pred_xy + 2 * static_cast<size_t>(map)) = make_float2(o.x, o.y);
+            if (a.maxvals) a.maxvals[map] = o.z;
+            if (a.weight_out) a.weight_out[map] = o.w;
+        }
     }
-    if (pipeline_last_block(a.ws)) pipeline_publish(a);
+    if (trace && threadIdx.x == 0) {
+        trace[2] = global_timer_ns();
+        trace[3] = static_cast<unsigned long long>(clock64());
+    }
 }
 
 }  // namespace hp

@@ -195,6 +195,12 @@ int hp_pipeline_fused_ex(const float* pred, const double* joints, const float* v
                          float* pred_xy, float* maxvals, float* weight_out,
                          int64_t* partial, int accumulate, double* result, void* workspace,
                          unsigned int flags, hp_stream_t stream);
+/* Profiling aid (not part of the reference-facing path): when a buffer is set, the blocks of the TMA-staged
+ * pipeline kernel stamp their timeline (entry/exit, and per warp and map: wait begins, data landed, refill
+ * issued, map closed) into it; launches alternate between two slots of hp_debug_pipeline_trace_words()
+ * uint64 words.  buf = NULL switches it off.  Read by profiles/trace_pipeline.py. */
+size_t hp_debug_pipeline_trace_words(void);
+int hp_debug_pipeline_trace(void* buf, size_t words);
 /* partial (e.g. after an NCCL all-reduce over ranks) -> result, on device */
 int hp_pipeline_finalize(const int64_t* partial, int K, double* result, hp_stream_t stream);
 
