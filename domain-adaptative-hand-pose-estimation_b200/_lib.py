@@ -19,6 +19,19 @@ LIB_PATH = os.path.join(_HERE, "libhp_b200.so")
 # enums of include/hp_b200.h
 LOSS_MSE, LOSS_KL = 1, 2
 PIPE_OVERLAP_PREV = 1          # HP_PIPE_OVERLAP_PREV (include/hp_b200.h)
+
+
+def pipe_flags(overlap):
+    """False/0 -> serialised launch; True -> overlapped at the library's default depth; int d in 1..8 ->
+    HP_PIPE_OVERLAP_PREV | HP_PIPE_DEPTH(d)."""
+    if overlap is True:
+        return PIPE_OVERLAP_PREV
+    d = int(overlap or 0)
+    if d == 0:
+        return 0
+    if not 1 <= d <= 8:
+        raise ValueError(f"overlap depth must be 1..8, got {overlap!r}")
+    return PIPE_OVERLAP_PREV | (d << 8)
 PLG_BASE, PLG_ONE_MINUS = 0, 1
 RD_BASE, RD_X1, RD_X5, RD_X6 = 0, 1, 2, 3
 MODE_MIN, MODE_MAX = 0, 1

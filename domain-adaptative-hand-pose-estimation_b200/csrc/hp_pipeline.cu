@@ -207,6 +207,15 @@ static unsigned long long* g_trace = nullptr;
 static size_t g_trace_words = 0;
 static unsigned long long g_trace_seq = 0;
 
+// experiments: HP_PIPE_GRID_DIV overrides the depth requested through the flags (0 = no override)
+static int pipeline_grid_div_override() {
+    static const int div = []() {
+        const char* e = std::getenv("HP_PIPE_GRID_DIV");
+        const int v = e ? std::atoi(e) : 0;
+        return (v >= 1 && v <= 8) ? v : 0;
+    }();
+    return div;
+}
 // ---- TMA-staged shape (hp_pipeline_bulk.cuh) ---------------------------------------------------------------------
 template <int NITC, int LOSS, bool MULTI, int W, int KST, int BPS>
 static cudaError_t launch_bulk_one(const BulkArgs& t, int grid, cudaStream_t stream) {
@@ -229,12 +238,16 @@ static cudaError_t launch_bulk_one(const BulkArgs& t, int grid, cudaStream_t str
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = t.overlap ? 1 : 0;
+    cfg.numAttrs = t.overlap > 0 ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, pipeline_bulk_kernel<NITC, LOSS, MULTI, W, KST, BPS>, t);
 }
 template <int NITC, bool MULTI, int W, int KST, int BPS>
 static cudaError_t launch_bulk(const BulkArgs& t, int sms, cudaStream_t stream) {
-    const int grid = t.p.n_maps < sms * BPS ? t.p.n_maps : sms * BPS;  // persistent: BPS blocks per SM
+    // persistent: BPS blocks per SM.  An overlapped launch may take only 1/div of the slots so that `div`
+    // consecutive launches are resident at once, out of phase (their start-up and drain bubbles interleave).
+    int slots = sms * BPS;
+    if (t.overlap > 1) slots = (slots + t.overlap - 1) / t.overlap;
+    const int grid = t.p.n_maps < slots ? t.p.n_maps : slots;
     switch (t.p.loss_mask) {
         case 0: return launch_bulk_one<NITC, 0, MULTI, W, KST, BPS>(t, grid, stream);
         case HP_LOSS_MSE: return launch_bulk_one<NITC, 1, MULTI, W, KST, BPS>(t, grid, stream);
@@ -296,20 +309,26 @@ static int launch_pipeline(const float* pred, const double* joints, const float*
         t.p = a;
         t.kdiv = FastDiv(static_cast<uint32_t>(K));
         t.n_chunks = HW > 4096 ? HW / 4096 : 1;
-        t.overlap = (flags & HP_PIPE_OVERLAP_PREV) ? 1 : 0;
-        const size_t trace_words = static_cast<size_t>(kTraceBlockWords) * static_cast<size_t>(g_sm_count);
+        if (flags & HP_PIPE_OVERLAP_PREV) {  // depth of the launch train: 0 -> library default
+            const int depth = static_cast<int>((flags >> 8) & 15u);
+            t.overlap = pipeline_grid_div_override() ? pipeline_grid_div_override() : (depth ? depth : 4);
+        }
+        const size_t trace_words = static_cast<size_t>(kTraceBlockWords) * kTraceMaxBlocksPerSM * static_cast<size_t>(g_sm_count);
         if (g_trace && g_trace_words >= 2 * trace_words) t.trace = g_trace + (g_trace_seq++ & 1) * trace_words;
         const int sms = g_sm_count;
         cudaError_t e;
-        if (HW == 256) e = launch_bulk<2, false, 6, 8, 2>(t, sms, stream);
-        else if (HW == 1024) e = launch_bulk<8, false, 6, 4, 2>(t, sms, stream);
-        else if (HW > 4096) e = launch_bulk<32, true, 3, 2, 2>(t, sms, stream);
-        else {
+        // default: 3 blocks of 4 warps per SM, one 16 KB stage per warp (12 stages = 192 KB in flight per SM)
+        if (HW == 256) e = launch_bulk<2, false, 4, 8, 3>(t, sms, stream);
+        else if (HW == 1024) e = launch_bulk<8, false, 4, 4, 3>(t, sms, stream);
+        else if (HW > 4096) {
+            if (pipeline_shape_choice() == 2) e = launch_bulk<32, true, 3, 2, 2>(t, sms, stream);
+            else e = launch_bulk<32, true, 4, 1, 3>(t, sms, stream);
+        } else {
             switch (pipeline_shape_choice()) {
-                case 2: e = launch_bulk<32, false, 12, 1, 1>(t, sms, stream); break;
-                case 3: e = launch_bulk<32, false, 4, 1, 3>(t, sms, stream); break;
-                case 4: e = launch_bulk<32, false, 3, 2, 2>(t, sms, stream); break;
-                default: e = launch_bulk<32, false, 6, 1, 2>(t, sms, stream); break;
+                case 2: e = launch_bulk<32, false, 6, 1, 2>(t, sms, stream); break;
+                case 3: e = launch_bulk<32, false, 12, 1, 1>(t, sms, stream); break;
+                case 4: e = launch_bulk<32, false, 3, 1, 4>(t, sms, stream); break;
+                default: e = launch_bulk<32, false, 4, 1, 3>(t, sms, stream); break;
             }
         }
         if (e != cudaSuccess) return fail(static_cast<int>(e), "hp_pipeline_fused: %s", cudaGetErrorString(e));
@@ -401,7 +420,8 @@ extern "C" HP_API int hp_pipeline_fused_ex(const float* pred, const double* join
     if (int rc = check_pipeline("hp_pipeline_fused_ex", pred, joints, vis, B, K, H, W, stride_x, stride_y, tmp, tab,
                                 pred_xy, partial, workspace, loss_mask))
         return rc;
-    HP_REQUIRE((flags & ~HP_PIPE_OVERLAP_PREV) == 0, HP_ERR_ARG, "hp_pipeline_fused_ex: unknown flags 0x%x", flags);
+    HP_REQUIRE((flags & ~(HP_PIPE_OVERLAP_PREV | HP_PIPE_DEPTH(15u))) == 0 && ((flags >> 8) & 15u) <= 8u, HP_ERR_ARG,
+               "hp_pipeline_fused_ex: bad flags 0x%x", flags);
     return launch_pipeline(pred, joints, vis, B, K, H, W, stride_x, stride_y, tmp, tab, kl_epsilon, thr, loss_mask,
                            pred_xy, maxvals, weight_out, reinterpret_cast<long long*>(partial), accumulate, result,
                            workspace, static_cast<cudaStream_t>(stream), flags);
@@ -414,7 +434,7 @@ extern "C" HP_API size_t hp_debug_pipeline_trace_words(void) {
         g_sm_count = hp_device_sm_count();
         if (g_sm_count <= 0) g_sm_count = 148;
     }
-    return static_cast<size_t>(kTraceBlockWords) * static_cast<size_t>(g_sm_count);
+    return static_cast<size_t>(kTraceBlockWords) * kTraceMaxBlocksPerSM * static_cast<size_t>(g_sm_count);
 }
 extern "C" HP_API int hp_debug_pipeline_trace(void* buf, size_t words) {
     g_trace = static_cast<unsigned long long*>(buf);

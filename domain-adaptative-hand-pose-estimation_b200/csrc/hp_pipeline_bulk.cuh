@@ -27,7 +27,8 @@ struct BulkArgs {
     PipeArgs p;
     FastDiv kdiv;   // by K (joint index of a map)
     int n_chunks;   // chunks per map (1 unless the map is larger than a stage)
-    int overlap;    // launched with programmatic stream serialization (HP_PIPE_OVERLAP_PREV)
+    int overlap;    // 0: serialised launch; d >= 1: programmatic dependent launch on 1/d of the block slots, so that
+                    // d consecutive launches are resident at once (HP_PIPE_OVERLAP_PREV | HP_PIPE_DEPTH(d))
     unsigned long long* trace;  // nullable profiling buffer (hp_debug_pipeline_trace): per block a header
                                 // {globaltimer, clock64} at entry and exit, per warp and map 4 clock64 stamps
 };
@@ -89,10 +90,12 @@ __device__ __forceinline__ float warp_max_f32(float x) {
 }
 
 // trace buffer layout (uint64): block b at b * kTraceBlockWords: [0] globaltimer in, [1] clock in, [2] globaltimer out,
-// [3] clock out, then per warp w (<= 16) and map jj (< kTraceMaps): 4 stamps {wait begins, data landed, refill issued,
-// map closed}
+// [3] clock out, [4] SM id, [5] clock when the block's last warp left the map loop, [6..7] spare, then per warp w
+// (< 16) and map jj (< kTraceMaps): 4 stamps {wait begins, data landed, refill issued, map closed}
 constexpr int kTraceMaps = 8;
-constexpr int kTraceBlockWords = 4 + 16 * kTraceMaps * 4;
+constexpr int kTraceHdr = 8;
+constexpr int kTraceBlockWords = kTraceHdr + 16 * kTraceMaps * 4;
+constexpr int kTraceMaxBlocksPerSM = 4;
 __device__ __forceinline__ unsigned long long global_timer_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -287,8 +290,11 @@ __global__ void __launch_bounds__(32 * W, BPS) pipeline_bulk_kernel(const BulkAr
     if (trace && threadIdx.x == 0) {
         trace[0] = global_timer_ns();
         trace[1] = static_cast<unsigned long long>(clock64());
+        unsigned int smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        trace[4] = smid;
     }
-    unsigned long long* wtrace = (trace && lane == 0 && warp < 16) ? trace + 4 + warp * (kTraceMaps * 4) : nullptr;
+    unsigned long long* wtrace = (trace && lane == 0 && warp < 16) ? trace + kTraceHdr + warp * (kTraceMaps * 4) : nullptr;
     // ---- prologue ----------------------------------------------------------------------------------------------
     // Order matters: (1) arm the ring (the init fence would otherwise wait for the loads below), (2) ISSUE the
     // small global loads, (3) request the bulk copies, (4) consume the small loads.  Once 148 x 192 KB of bulk
@@ -527,7 +533,8 @@ __global__ void __launch_bounds__(32 * W, BPS) pipeline_bulk_kernel(const BulkAr
             if (wl->cls[i] != 0) atomicAdd(&sh.acc[2 + i], static_cast<unsigned long long>(wl->cls[i]));
     }
     __syncthreads();
-    griddep_wait();  // the previous grid on the stream is complete: outputs and workspace may be written now
+    if (trace && threadIdx.x == 0) trace[5] = static_cast<unsigned long long>(clock64());
+    if (!dep_ok) griddep_wait();  // (warps without maps) previous grid complete: outputs and workspace may be written
     if (warp == 0) {
         for (int i = lane; i < 8 + 2 * a.K; i += 32) {
             if (i < 8) {

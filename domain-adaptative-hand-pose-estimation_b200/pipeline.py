@@ -87,9 +87,11 @@ class HeatmapPipeline:
         current stream with pre-bound arguments (a ~15 us kernel leaves no room for per-call Python
         argument checking; this is also what gets captured into CUDA graphs).
 
-        ``overlap=True`` (HP_PIPE_OVERLAP_PREV): the launch may start while the previous kernel on the
-        stream is still draining.  Only for steps over batches that are already resident: ``pred``,
-        ``joints`` and ``vis`` must not be written by the kernel launched right before this one."""
+        ``overlap`` (HP_PIPE_OVERLAP_PREV): ``True`` or a depth 1..8 - the launch is part of a train of
+        launches over batches that are already resident and may run concurrently with the previous
+        ``depth - 1`` launches on the stream (it writes nothing before they have completed; results are
+        bit-identical).  ``pred``, ``joints`` and ``vis`` must not be written by the kernel launched right
+        before this one, and consecutive launches need different ``out`` buffers."""
         pred = _lib.require_cuda(pred, "HeatmapPipeline(pred)")
         joints = _lib.require_cuda(joints, "HeatmapPipeline(joints)", torch.float64)
         vis = _lib.require_cuda(vis, "HeatmapPipeline(vis)")
@@ -109,7 +111,7 @@ class HeatmapPipeline:
                 C.c_double(self.stride[1]), self.tmp, _lib.ptr(self.tab), C.c_float(self.kl_epsilon),
                 C.c_double(self.thr), self.loss_mask, _lib.ptr(out.pred_xy), _lib.ptr(out.maxvals), _lib.ptr(out.weight),
                 _lib.ptr(out.partial), 0, _lib.ptr(out.result) if finalize else None, _lib.ptr(ws),
-                C.c_uint(_lib.PIPE_OVERLAP_PREV if overlap else 0))
+                C.c_uint(_lib.pipe_flags(overlap)))
         keep = (pred, joints, vis, out, ws)            # the plan owns references: pointers stay valid
         current_stream = torch.cuda.current_stream
 
@@ -129,7 +131,7 @@ class HeatmapPipeline:
         return self._ws
 
     def _cached_plan(self, pred, joints, vis, out, finalize, overlap=False):
-        key = (pred.data_ptr(), joints.data_ptr(), vis.data_ptr(), id(out), pred.shape[0], finalize, overlap)
+        key = (pred.data_ptr(), joints.data_ptr(), vis.data_ptr(), id(out), pred.shape[0], finalize, int(overlap))
         hit = self._plans.get(key)
         if hit is None:
             if len(self._plans) > 256:

@@ -182,13 +182,18 @@ int hp_pipeline_fused(const float* pred, const double* joints, const float* vis,
                       int64_t* partial, int accumulate, double* result, void* workspace,
                       hp_stream_t stream);
 /* Same, with launch flags.
- *   HP_PIPE_OVERLAP_PREV: the launch may begin (programmatic dependent launch) while the previous kernel
- *   on `stream` is still draining: blocks of this launch read pred / joints / vis / tab as soon as SMs
- *   free up, but write nothing and do not touch `workspace` until the previous kernel has completed.
- *   Contract: pred, joints, vis and tab must NOT be produced by the kernel launched right before this
- *   one on `stream` (steps over independent, already resident batches - e.g. back-to-back calls of this
- *   function); everything else is as hp_pipeline_fused. */
+ *   HP_PIPE_OVERLAP_PREV: this launch belongs to a train of launches over independent, already resident
+ *   batches (back-to-back calls of this function on one stream).  It is issued as a programmatic dependent
+ *   launch on 1/depth of the kernel's block slots, so that `depth` consecutive launches are resident at
+ *   once and one launch's start-up and drain overlap the streaming of its neighbours.  Its blocks read
+ *   pred / joints / vis / tab as soon as they get a slot, keep their per-map outputs in shared memory, and
+ *   write nothing (outputs, partial, result, workspace) until the previous kernel on the stream has
+ *   completed - results are bit-identical to serialised launches.
+ *   Contract: pred, joints, vis and tab must NOT be produced by the kernel launched right before this one
+ *   on `stream`; consecutive launches of a train use different output buffers.
+ *   HP_PIPE_DEPTH(d), d = 1..8: launches resident at once (1 = hand-over only); 0/absent = library default. */
 #define HP_PIPE_OVERLAP_PREV 1u
+#define HP_PIPE_DEPTH(d) (((unsigned int)(d) & 15u) << 8)
 int hp_pipeline_fused_ex(const float* pred, const double* joints, const float* vis,
                          int B, int K, int H, int W, double stride_x, double stride_y, int tmp,
                          const float* tab, float kl_epsilon, double thr, int loss_mask,

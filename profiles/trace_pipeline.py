@@ -46,13 +46,17 @@ torch.cuda.synchronize()
 L.call("hp_debug_pipeline_trace", None, 0)
 us_per_launch = 1e3 * e0.elapsed_time(e1) / args.launches
 t = buf.cpu().numpy().astype(np.uint64).reshape(2, -1)
-n_blocks = words // (4 + 16 * 8 * 4)
+HDR = 8
+BW = HDR + 16 * 8 * 4
+n_blocks = words // BW
 last, prev = (args.launches - 1) & 1, (args.launches - 2) & 1
 
 def unpack(slot):
-    b = t[slot].reshape(n_blocks, 4 + 16 * 8 * 4)
-    hdr = b[:, :4].astype(np.int64)
-    maps = b[:, 4:].reshape(n_blocks, 16, 8, 4).astype(np.int64)
+    b = t[slot].reshape(n_blocks, BW)
+    used = b[:, 0] != 0                      # blocks that ran (grid <= n_blocks)
+    b = b[used]
+    hdr = b[:, :HDR].astype(np.int64)
+    maps = b[:, HDR:].reshape(-1, 16, 8, 4).astype(np.int64)
     return hdr, maps
 
 hdr, maps = unpack(last)
@@ -82,6 +86,20 @@ first_ready = (maps[:, :, 0, 1] - hdr[:, 1][:, None])[valid[:, :, 0]]
 rep["first_data_after_entry_ns"] = stats(first_ready)
 last_close = np.where(valid, maps[..., 3], 0).max(axis=(1, 2)) 
 rep["exit_after_last_close_ns"] = stats(hdr[:, 3] - last_close)
+rep["barrier_after_last_close_ns"] = stats(hdr[:, 5] - last_close)
+rep["exit_after_barrier_ns"] = stats(hdr[:, 3] - hdr[:, 5])
+rep["blocks"] = int(hdr.shape[0])
+# hand-over between launches: how many blocks of the last launch began before the previous launch had fully exited
+prev_end = int(hdr_p[:, 2].max())
+rep["blocks_started_before_prev_launch_ended"] = int((hdr[:, 0] < prev_end).sum())
+rep["entry_minus_prev_launch_end_ns"] = {"min": int((hdr[:, 0] - prev_end).min()), "median": float(np.median(hdr[:, 0] - prev_end)), "max": int((hdr[:, 0] - prev_end).max())}
+# per SM: idle time between a block of the previous launch leaving and a block of this launch entering
+gaps = []
+for sm in np.unique(hdr[:, 4]):
+    ex = np.sort(hdr_p[hdr_p[:, 4] == sm, 2]); en = np.sort(hdr[hdr[:, 4] == sm, 0])
+    for a_, b_ in zip(ex, en):
+        gaps.append(b_ - a_)
+rep["per_sm_slot_handover_ns"] = {"n": len(gaps), "median": float(np.median(gaps)), "p90": float(np.percentile(gaps, 90)), "max": int(max(gaps))} if gaps else {}
 per_round = {}
 for jj in range(8):
     v = valid[:, :, jj]

@@ -220,14 +220,29 @@ def test_pipeline_overlapped_launches_are_bit_identical():
     for s in sets:
         o = pipe(s["pred"], s["joints"], s["vis"])
         ref.append((o.result.clone(), o.partial.clone(), o.pred_xy.clone(), o.maxvals.clone(), o.weight.clone()))
-    outs = [pipe.alloc_outputs(B) for _ in range(n)]
-    for rep in range(5):
-        for s, o in zip(sets, outs):
-            pipe(s["pred"], s["joints"], s["vis"], out=o, overlap=True)
-    torch.cuda.synchronize()
-    for o, r in zip(outs, ref):
-        assert torch.equal(o.result, r[0]) and torch.equal(o.partial, r[1]) and torch.equal(o.pred_xy, r[2])
-        assert torch.equal(o.maxvals, r[3]) and torch.equal(o.weight, r[4])
+    for depth in (True, 1, 2, 3, 8):
+        outs = [pipe.alloc_outputs(B) for _ in range(n)]
+        for rep in range(5):
+            for s, o in zip(sets, outs):
+                pipe(s["pred"], s["joints"], s["vis"], out=o, overlap=depth)
+        torch.cuda.synchronize()
+        for o, r in zip(outs, ref):
+            assert torch.equal(o.result, r[0]) and torch.equal(o.partial, r[1]) and torch.equal(o.pred_xy, r[2])
+            assert torch.equal(o.maxvals, r[3]) and torch.equal(o.weight, r[4])
+    # a small batch (fewer maps than block slots) and a big one (outputs beyond the shared-memory buffer)
+    for Bx, size in ((3, 64), (1200, 16)):
+        d = hp.synth.make_device_batch(891 + Bx, Bx, 21, size, size)
+        p2 = hp.HeatmapPipeline(heatmap_size=(size, size), kl_epsilon=1e-7)
+        o = p2(d["pred"], d["joints"], d["vis"])
+        want = (o.result.clone(), o.partial.clone(), o.pred_xy.clone(), o.maxvals.clone(), o.weight.clone())
+        outs = [p2.alloc_outputs(Bx) for _ in range(4)]
+        for rep in range(3):
+            for o in outs:
+                p2(d["pred"], d["joints"], d["vis"], out=o, overlap=True)
+        torch.cuda.synchronize()
+        for o in outs:
+            assert torch.equal(o.result, want[0]) and torch.equal(o.partial, want[1]) and torch.equal(o.pred_xy, want[2])
+            assert torch.equal(o.maxvals, want[3]) and torch.equal(o.weight, want[4])
 
 
 # ------------------------------------------------------------------ generic shapes / edge cases
