@@ -223,7 +223,7 @@ def run_product_arm(args):
     per_gpu_B, side, desc = WORKLOADS[args.workload]
     K = K_JOINTS
     pipe = hp.HeatmapPipeline(num_keypoints=K, heatmap_size=(side, side), image_size=(4 * side, 4 * side),
-                              sigma=2, kl_epsilon=KL_EPS, device=dev)
+                              sigma=2, kl_epsilon=KL_EPS, device=dev, collective=args.collective)
     map_bytes = side * side * 4
     n_sets = max(4, min(N_SETS, int(8e9 // (per_gpu_B * K * map_bytes)) or 1))
     sets = [hp.synth.make_device_batch(1234 + 1000 * 1 + 97 * rank + 7919 * s, per_gpu_B, K, side, side,
@@ -276,8 +276,39 @@ def run_product_arm(args):
     pipe.join()
     barrier()
 
-    graph_note = "eager launches"
-    ms_total = timed(steps_then_join, args.steps)
+    # Optional: replay the n_sets-step train from a CUDA graph (--graph on).  Measured on B200: slower than eager
+    # launches (15.5 vs 12.6 us per step at N=1) because a graph does not keep the programmatic overlap between
+    # consecutive launches across replays; kept as an experiment switch, off by default.
+    graph, graph_note = None, "eager launches"
+    use_graph = args.graph == "on"
+    if use_graph and args.steps >= n_sets:
+        try:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                for s_i in range(n_sets):
+                    step(s_i)
+            for _ in range(3):
+                graph.replay()
+            torch.cuda.synchronize()
+            graph_note = f"CUDA graph of {n_sets} steps, replayed"
+        except Exception as exc:  # noqa: BLE001 - fall back to eager launches and say so in the line
+            graph = None
+            graph_note = f"eager launches (graph capture failed: {type(exc).__name__})"
+            torch.cuda.synchronize()
+    barrier()
+    if graph is not None:
+        n_replays, rest = divmod(args.steps, n_sets)
+
+        def run_steps(i):
+            if i < n_replays:
+                graph.replay()
+            else:
+                for r in range(rest):
+                    step(r)
+                pipe.join()
+        ms_total = timed(run_steps, n_replays + 1)
+    else:
+        ms_total = timed(steps_then_join, args.steps)
     maps_per_step = per_gpu_B * K * n_gpus
     value = maps_per_step * args.steps / (ms_total * 1e-3)
     # dominant kernel alone (identical to the step at N=1; without the collective at N>1)
@@ -288,12 +319,27 @@ def run_product_arm(args):
     for i in range(3):
         kernel_only(i)
     ms_kernel = timed(kernel_only, args.steps) / args.steps
+
+    # the same launches fully serialised (no programmatic dependent launch): the latency of ONE launch incl. its
+    # start-up, drain and the launch gap - reported beside the throughput figure, not instead of it
+    def kernel_serial(i):
+        s = sets[i % n_sets]
+        pipe.launch_local(s["pred"], s["joints"], s["vis"], outs[i % n_sets], overlap=False)
+
+    for i in range(3):
+        kernel_serial(i)
+    ms_serial = timed(kernel_serial, max(100, args.steps // 4)) / max(100, args.steps // 4)
     peak, peak_src = measured_hbm_peak()
     alg_bytes = algorithmic_bytes_per_map(side) * per_gpu_B * K
     achieved = alg_bytes / (ms_kernel * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": recorded_traffic(args.workload), "kernel": "hp::pipeline_kernel",
-                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": ms_kernel, "peak_source": peak_src}
+                "traffic": recorded_traffic(args.workload), "kernel": "hp::pipeline_bulk_kernel",
+                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": ms_kernel, "peak_source": peak_src,
+                "kernel_ms_note": "average over the timed train of launches (CUDA events on the launching stream)"
+                                  + ("; up to 4 launches of the train are resident at once" if overlap else ""),
+                "serialised": {"kernel_ms": ms_serial, "achieved": alg_bytes / (ms_serial * 1e-3) / 1e9,
+                               "frac": alg_bytes / (ms_serial * 1e-3) / 1e9 / peak,
+                               "note": "one launch at a time (launch gap, start-up and drain exposed)"}}
 
     # end to end through the public host-buffer API
     host_sets = []
@@ -338,17 +384,21 @@ def run_product_arm(args):
                        "losses": "mse+kl", "kl_epsilon": KL_EPS,
                        "l2": f"{n_sets} rotating input sets of {per_gpu_B * K * map_bytes / 1e6:.0f} MB "
                              f"({n_sets * per_gpu_B * K * map_bytes / 1e6:.0f} MB > 126 MB L2)",
-                       "parallelism": f"batch-sharded dp{n_gpus}; one NCCL all-reduce of {4 + 2 * K + 6} int64 per step"
+                       "parallelism": (f"batch-sharded dp{n_gpus}; per step one exchange of {4 + 2 * K + 6} int64 "
+                                       + ("over NVLink peer memory inside the fused kernel's last block (one kernel per step, "
+                                          "no NCCL on the step path)"
+                                          if args.collective == "peer" else "by NCCL all-reduce"))
                                       if n_gpus > 1 else "single GPU, no collective",
                        "launch": graph_note + (", consecutive steps overlap by programmatic dependent launch "
                                                "(independent resident batches, separate outputs)" if overlap else
                                                ", fully serialised")},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": clocks,
-            "gpu_launches": args.steps * (2 if n_gpus > 1 else 1),
+            "gpu_launches": args.steps * (2 if (n_gpus > 1 and args.collective == "nccl") else 1),
         }
         sys.stdout.write(json.dumps(line) + "\n")
         sys.stdout.flush()
     if world > 1:
+        pipe.close()
         dist.barrier()
         dist.destroy_process_group()
     return 0
@@ -363,6 +413,10 @@ def main():
     ap.add_argument("--workload", default="pipeline64", choices=sorted(WORKLOADS))
     ap.add_argument("--slab", type=int, default=32, help="samples per H2D slab in the end-to-end path")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", default="off", choices=["on", "off"],
+                    help="replay the step train from a CUDA graph (measured slower: a graph serialises the launch train)")
+    ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
+                    help="N>1: how the ranks' partial vectors are summed each step")
     ap.add_argument("--no-overlap", action="store_true",
                     help="launch every step fully serialised after the previous one (no programmatic dependent launch)")
     args = ap.parse_args()

@@ -67,6 +67,12 @@ PROTOTYPES = {
                                _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "hp_pipeline_fused_ex": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _d, _d, _i, _vp, _f, _d, _i,
                                   _vp, _vp, _vp, _vp, _i, _vp, _vp, C.c_uint, _vp]),
+    "hp_pipeline_fused_peer": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _d, _d, _i, _vp, _f, _d, _i,
+                                    _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, C.c_int64, C.c_uint, _vp]),
+    "hp_pipeline_plan_create": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _d, _d, _i, _vp, _f, _d, _i,
+                                     _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, C.c_uint, _vp]),
+    "hp_pipeline_plan_launch": (_i, [_vp, _vp]),
+    "hp_pipeline_plan_destroy": (_i, [_vp]),
     "hp_debug_pipeline_trace_words": (_sz, []),
     "hp_debug_pipeline_trace": (_i, [_vp, _sz]),
     "hp_pipeline_finalize": (_i, [_vp, _i, _vp, _vp]),

@@ -10,19 +10,18 @@
 //   * it then waits (bounded spin, volatile system-scope loads) until all `world` flags of its own mailbox
 //     show this sequence number, sums the `world` vectors in rank order and finalises exactly like
 //     hp_pipeline_finalize.  Every entry is an integer, so all ranks get bit-identical results.
-// Two parities suffice: a rank can be at most one step ahead of the slowest rank (it cannot finish step
+// The step number is either passed by the host or (seq = 0) counted on the device, which makes a captured CUDA
+// graph of steps replayable.  Two parities suffice: a rank can be at most one step ahead of the slowest rank (it cannot finish step
 // s+1 before it has received everybody's step-(s+1) vector).  Ranks run on different GPUs, so the kernels
 // that wait for one another always execute concurrently; the spin is bounded (~2 s) and reports a timeout
 // through the result vector instead of hanging.
 #include <cstring>
 
 #include "hp_common.cuh"
+#include "hp_internal.cuh"
 #include "hp_pipeline_common.cuh"
 
 namespace hp {
-
-constexpr int kPeerWords = 64;          // int64 words per (parity, source) slot; word 63 is the flag
-constexpr int kPeerMaxWorld = 16;
 
 struct PeerArgs {
     const long long* partial;           // this rank's partial vector [4+2K+6]
@@ -33,15 +32,21 @@ struct PeerArgs {
     double* result;                     // [4+K]
 };
 
-__device__ __forceinline__ long long* peer_slot(long long* base, int world, int parity, int src) {
-    return base + (static_cast<size_t>(parity) * world + src) * kPeerWords;
-}
-
-__global__ void __launch_bounds__(256) pipeline_finalize_peer_kernel(const PeerArgs a) {
+// 64 threads, a few registers, 1.2 KB of shared memory: always fits beside the resident pipeline blocks of a train
+__global__ void __launch_bounds__(64) pipeline_finalize_peer_kernel(const PeerArgs a) {
     __shared__ long long s_total[4 + 2 * HP_MAX_K + 6];
     __shared__ int s_timeout;
     const int n = 4 + 2 * a.K + 6;
-    const int parity = static_cast<int>(a.seq & 1);
+    // Programmatic dependent launch (no-ops without the launch attribute): the next pipeline launch of the train
+    // may start right away; this kernel reads `partial` only once the pipeline launch before it has completed.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    // (the counter is read only now: the previous step's exchange kernel, which writes it, has completed)
+    // step number: given by the host, or (seq == 0) counted on the device in the rank's own mailbox so that a
+    // captured CUDA graph of steps can be replayed - all ranks run the same steps in the same order
+    long long* counter = peer_counter(a.mailbox[a.rank], a.world);
+    const long long seq = a.seq != 0 ? a.seq : *reinterpret_cast<volatile long long*>(counter) + 1;
+    const int parity = static_cast<int>(seq & 1);
     if (threadIdx.x == 0) s_timeout = 0;
     // ---- send: my vector into slot[parity][rank] of every mailbox ------------------------------------
     for (int i = threadIdx.x; i < a.world * n; i += blockDim.x) {
@@ -52,13 +57,13 @@ __global__ void __launch_bounds__(256) pipeline_finalize_peer_kernel(const PeerA
     if (threadIdx.x < a.world) {
         __threadfence_system();  // payload before flag, at system scope (peer GPUs)
         volatile long long* flag = peer_slot(a.mailbox[threadIdx.x], a.world, parity, a.rank) + (kPeerWords - 1);
-        *flag = a.seq;
+        *flag = seq;
     }
     // ---- receive: wait for every source's flag in MY mailbox ---------------------------------------------
     if (threadIdx.x < a.world) {
         volatile long long* flag = peer_slot(a.mailbox[a.rank], a.world, parity, threadIdx.x) + (kPeerWords - 1);
         const long long t0 = clock64();
-        while (*flag != a.seq) {
+        while (*flag != seq) {
             if (clock64() - t0 > 4000000000ll) {  // ~2 s at 2 GHz: a peer never arrived
                 s_timeout = 1;
                 break;
@@ -77,6 +82,7 @@ __global__ void __launch_bounds__(256) pipeline_finalize_peer_kernel(const PeerA
     }
     __syncthreads();
     if (threadIdx.x == 0) {
+        *counter = seq;  // every thread has read it (barriers above)
         pipeline_result_from_partial(s_total, a.K, a.result);
         if (s_timeout) a.result[0] = a.result[1] = __longlong_as_double(0x7ff8000000000000ll);
     }
@@ -88,7 +94,7 @@ using namespace hp;
 
 // ---- setup-time helpers (the only entry points of the library that own memory) -------------------------------
 extern "C" HP_API size_t hp_peer_mailbox_bytes(int world) {
-    return sizeof(long long) * 2 * static_cast<size_t>(world > 0 ? world : 1) * kPeerWords;
+    return sizeof(long long) * (2 * static_cast<size_t>(world > 0 ? world : 1) * kPeerWords + 8);  // + step counter
 }
 
 extern "C" HP_API int hp_peer_alloc(int world, void** mailbox) {
@@ -132,22 +138,41 @@ extern "C" HP_API int hp_peer_close(void* mapped) {
 }
 
 // ---- per step -----------------------------------------------------------------------------------------------------
-extern "C" HP_API int hp_pipeline_finalize_peer(const int64_t* partial, void* const* mailboxes, int rank, int world,
-                                                int K, int64_t seq, int64_t* partial_out, double* result,
-                                                hp_stream_t stream) {
+namespace hp {
+int launch_finalize_peer(const long long* partial, void* const* mailboxes, int rank, int world, int K, long long seq,
+                         long long* partial_out, double* result, int overlap, cudaStream_t stream) {
     HP_REQUIRE(partial && mailboxes && result, HP_ERR_NULL, "hp_pipeline_finalize_peer: null pointer");
-    HP_REQUIRE(world > 0 && world <= kPeerMaxWorld && rank >= 0 && rank < world && K > 0 && K <= HP_MAX_K && seq > 0 &&
+    HP_REQUIRE(world > 0 && world <= kPeerMaxWorld && rank >= 0 && rank < world && K > 0 && K <= HP_MAX_K && seq >= 0 &&
                    4 + 2 * K + 6 < kPeerWords,
-               HP_ERR_ARG, "hp_pipeline_finalize_peer: rank=%d world=%d K=%d seq=%lld", rank, world, K,
-               static_cast<long long>(seq));
+               HP_ERR_ARG, "hp_pipeline_finalize_peer: rank=%d world=%d K=%d seq=%lld", rank, world, K, seq);
     PeerArgs a{};
-    a.partial = reinterpret_cast<const long long*>(partial);
+    a.partial = partial;
     for (int r = 0; r < world; ++r) {
         HP_REQUIRE(mailboxes[r], HP_ERR_NULL, "hp_pipeline_finalize_peer: mailbox %d is null", r);
         a.mailbox[r] = static_cast<long long*>(mailboxes[r]);
     }
     a.rank = rank; a.world = world; a.K = K; a.seq = seq;
-    a.partial_out = reinterpret_cast<long long*>(partial_out); a.result = result;
-    pipeline_finalize_peer_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    a.partial_out = partial_out; a.result = result;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(1);
+    cfg.blockDim = dim3(64);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = overlap ? 1 : 0;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, pipeline_finalize_peer_kernel, a);
+    if (e != cudaSuccess) return fail(static_cast<int>(e), "hp_pipeline_finalize_peer: %s", cudaGetErrorString(e));
     return launch_status("hp_pipeline_finalize_peer");
+}
+}  // namespace hp
+
+extern "C" HP_API int hp_pipeline_finalize_peer(const int64_t* partial, void* const* mailboxes, int rank, int world,
+                                                int K, int64_t seq, int64_t* partial_out, double* result,
+                                                hp_stream_t stream) {
+    return launch_finalize_peer(reinterpret_cast<const long long*>(partial), mailboxes, rank, world, K,
+                                static_cast<long long>(seq), reinterpret_cast<long long*>(partial_out), result, 0,
+                                static_cast<cudaStream_t>(stream));
 }

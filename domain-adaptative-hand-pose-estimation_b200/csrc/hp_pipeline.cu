@@ -16,9 +16,11 @@
 // 1 FADD (sum p), 1 FFMA (squared error); target terms only on the 13 rows the patch touches.
 #include <cmath>
 #include <cstdlib>
+#include <new>
 
 #include "hp_common.cuh"
 #include "hp_dispatch.cuh"
+#include "hp_internal.cuh"
 #include "hp_pipeline_common.cuh"
 #include "hp_pipeline_tiles.cuh"
 #include "hp_pipeline_bulk.cuh"
@@ -245,8 +247,15 @@ template <int NITC, bool MULTI, int W, int KST, int BPS>
 static cudaError_t launch_bulk(const BulkArgs& t, int sms, cudaStream_t stream) {
     // persistent: BPS blocks per SM.  An overlapped launch may take only 1/div of the slots so that `div`
     // consecutive launches are resident at once, out of phase (their start-up and drain bubbles interleave).
+    // The depth only pays while a launch is a few rounds long (its start-up and drain are then a third of its
+    // life); it is capped so that a block's per-map outputs still fit its shared-memory buffer - beyond that a
+    // block has to wait for the previous launch in mid-stream, which serialises the train on 1/depth of the SMs.
     int slots = sms * BPS;
-    if (t.overlap > 1) slots = (slots + t.overlap - 1) / t.overlap;
+    if (t.overlap > 1) {
+        const long long fit = static_cast<long long>(kBulkOutCap) * slots / (t.p.n_maps > 0 ? t.p.n_maps : 1);
+        const int depth = fit < 1 ? 1 : (fit < t.overlap ? static_cast<int>(fit) : t.overlap);
+        slots = (slots + depth - 1) / depth;
+    }
     const int grid = t.p.n_maps < slots ? t.p.n_maps : slots;
     switch (t.p.loss_mask) {
         case 0: return launch_bulk_one<NITC, 0, MULTI, W, KST, BPS>(t, grid, stream);
@@ -270,7 +279,9 @@ static int pipeline_shape_choice() {
 static int launch_pipeline(const float* pred, const double* joints, const float* vis, int B, int K, int H, int W,
                            double stride_x, double stride_y, int tmp, const float* tab, float kl_epsilon, double thr,
                            int loss_mask, float* pred_xy, float* maxvals, float* weight_out, long long* partial,
-                           int accumulate, double* result, void* workspace, cudaStream_t stream, unsigned flags = 0) {
+                           int accumulate, double* result, void* workspace, cudaStream_t stream, unsigned flags = 0,
+                           const PeerLink* link = nullptr, bool* exchanged = nullptr) {
+    if (exchanged) *exchanged = false;
     const int HW = H * W, side = 2 * tmp + 1;
     PipeArgs a{};
     a.pred = pred; a.joints = joints; a.vis = vis; a.n_maps = B * K; a.K = K; a.H = H; a.W = W; a.HW = HW;
@@ -312,6 +323,10 @@ static int launch_pipeline(const float* pred, const double* joints, const float*
         if (flags & HP_PIPE_OVERLAP_PREV) {  // depth of the launch train: 0 -> library default
             const int depth = static_cast<int>((flags >> 8) & 15u);
             t.overlap = pipeline_grid_div_override() ? pipeline_grid_div_override() : (depth ? depth : 4);
+        }
+        if (link && link->world > 1 && accumulate == 0) {  // the kernel's last block does the exchange itself
+            t.link = *link;
+            if (exchanged) *exchanged = true;
         }
         const size_t trace_words = static_cast<size_t>(kTraceBlockWords) * kTraceMaxBlocksPerSM * static_cast<size_t>(g_sm_count);
         if (g_trace && g_trace_words >= 2 * trace_words) t.trace = g_trace + (g_trace_seq++ & 1) * trace_words;
@@ -425,6 +440,114 @@ extern "C" HP_API int hp_pipeline_fused_ex(const float* pred, const double* join
     return launch_pipeline(pred, joints, vis, B, K, H, W, stride_x, stride_y, tmp, tab, kl_epsilon, thr, loss_mask,
                            pred_xy, maxvals, weight_out, reinterpret_cast<long long*>(partial), accumulate, result,
                            workspace, static_cast<cudaStream_t>(stream), flags);
+}
+
+/* one sharded step: the fused kernel on this rank's slice, then the exchange + finalise kernel, both on `stream`
+ * (with HP_PIPE_OVERLAP_PREV both are programmatic dependent launches: a train of steps stays overlapped) */
+extern "C" HP_API int hp_pipeline_fused_peer(const float* pred, const double* joints, const float* vis, int B, int K,
+                                             int H, int W, double stride_x, double stride_y, int tmp, const float* tab,
+                                             float kl_epsilon, double thr, int loss_mask, float* pred_xy,
+                                             float* maxvals, float* weight_out, int64_t* partial, double* result,
+                                             void* workspace, void* const* mailboxes, int rank, int world,
+                                             int64_t seq, unsigned int flags, hp_stream_t stream) {
+    if (int rc = check_pipeline("hp_pipeline_fused_peer", pred, joints, vis, B, K, H, W, stride_x, stride_y, tmp, tab,
+                                pred_xy, partial, workspace, loss_mask))
+        return rc;
+    HP_REQUIRE((flags & ~(HP_PIPE_OVERLAP_PREV | HP_PIPE_DEPTH(15u))) == 0 && ((flags >> 8) & 15u) <= 8u, HP_ERR_ARG,
+               "hp_pipeline_fused_peer: bad flags 0x%x", flags);
+    HP_REQUIRE(result && mailboxes, HP_ERR_NULL, "hp_pipeline_fused_peer: null pointer");
+    HP_REQUIRE(world > 0 && world <= kPeerMaxWorld && rank >= 0 && rank < world && seq == 0, HP_ERR_ARG,
+               "hp_pipeline_fused_peer: rank=%d world=%d seq=%lld (the step is counted on the device: pass 0)", rank,
+               world, static_cast<long long>(seq));
+    PeerLink link{};
+    for (int r = 0; r < world; ++r) {
+        HP_REQUIRE(mailboxes[r], HP_ERR_NULL, "hp_pipeline_fused_peer: mailbox %d is null", r);
+        link.mailbox[r] = static_cast<long long*>(mailboxes[r]);
+    }
+    link.rank = rank;
+    link.world = world;
+    bool exchanged = false;
+    // shapes served by the TMA-staged kernel: its last block exchanges and finalises in place (ONE kernel per step)
+    if (int rc = launch_pipeline(pred, joints, vis, B, K, H, W, stride_x, stride_y, tmp, tab, kl_epsilon, thr, loss_mask,
+                                 pred_xy, maxvals, weight_out, reinterpret_cast<long long*>(partial), 0, result,
+                                 workspace, static_cast<cudaStream_t>(stream), flags, &link, &exchanged))
+        return rc;
+    if (exchanged || world == 1) return HP_OK;
+    // other shapes: the separate exchange + finalise kernel
+    return launch_finalize_peer(reinterpret_cast<const long long*>(partial), mailboxes, rank, world, K, 0,
+                                reinterpret_cast<long long*>(partial), result,
+                                (flags & HP_PIPE_OVERLAP_PREV) ? 1 : 0, static_cast<cudaStream_t>(stream));
+}
+
+/* ---- pre-bound steps -------------------------------------------------------------------------------------------
+ * A step of the pipeline is a ~12 us kernel; marshalling two dozen arguments through an FFI per step costs about
+ * as much on the host.  A plan validates and stores the arguments of hp_pipeline_fused_ex / hp_pipeline_fused_peer
+ * once; launching it is a two-argument call.  The plan holds the caller's pointers until it is destroyed. */
+struct hp_plan {
+    const float* pred; const double* joints; const float* vis;
+    int B, K, H, W; double sx, sy; int tmp; const float* tab; float eps; double thr; int loss_mask;
+    float* pred_xy; float* maxvals; float* weight_out; long long* partial; int accumulate; double* result;
+    void* workspace; unsigned flags;
+    PeerLink link;                       // world <= 1: single rank
+    void* mailboxes[kPeerMaxWorld];
+};
+
+extern "C" HP_API int hp_pipeline_plan_create(const float* pred, const double* joints, const float* vis, int B, int K,
+                                              int H, int W, double stride_x, double stride_y, int tmp, const float* tab,
+                                              float kl_epsilon, double thr, int loss_mask, float* pred_xy,
+                                              float* maxvals, float* weight_out, int64_t* partial, int accumulate,
+                                              double* result, void* workspace, void* const* mailboxes, int rank,
+                                              int world, unsigned int flags, hp_plan** plan) {
+    HP_REQUIRE(plan, HP_ERR_NULL, "hp_pipeline_plan_create: null plan pointer");
+    *plan = nullptr;
+    if (int rc = check_pipeline("hp_pipeline_plan_create", pred, joints, vis, B, K, H, W, stride_x, stride_y, tmp, tab,
+                                pred_xy, partial, workspace, loss_mask))
+        return rc;
+    HP_REQUIRE((flags & ~(HP_PIPE_OVERLAP_PREV | HP_PIPE_DEPTH(15u))) == 0 && ((flags >> 8) & 15u) <= 8u, HP_ERR_ARG,
+               "hp_pipeline_plan_create: bad flags 0x%x", flags);
+    HP_REQUIRE(world >= 0 && world <= kPeerMaxWorld && (world <= 1 || (mailboxes && rank >= 0 && rank < world && result &&
+                                                                      accumulate == 0)),
+               HP_ERR_ARG, "hp_pipeline_plan_create: rank=%d world=%d", rank, world);
+    hp_plan* p = new (std::nothrow) hp_plan{};
+    HP_REQUIRE(p, HP_ERR_ARG, "hp_pipeline_plan_create: out of host memory");
+    p->pred = pred; p->joints = joints; p->vis = vis; p->B = B; p->K = K; p->H = H; p->W = W;
+    p->sx = stride_x; p->sy = stride_y; p->tmp = tmp; p->tab = tab; p->eps = kl_epsilon; p->thr = thr;
+    p->loss_mask = loss_mask; p->pred_xy = pred_xy; p->maxvals = maxvals; p->weight_out = weight_out;
+    p->partial = reinterpret_cast<long long*>(partial); p->accumulate = accumulate; p->result = result;
+    p->workspace = workspace; p->flags = flags;
+    p->link.rank = rank; p->link.world = world > 1 ? world : 0;
+    for (int r = 0; r < p->link.world; ++r) {
+        if (!mailboxes[r]) {
+            delete p;
+            return fail(HP_ERR_NULL, "hp_pipeline_plan_create: mailbox %d is null", r);
+        }
+        p->mailboxes[r] = mailboxes[r];
+        p->link.mailbox[r] = static_cast<long long*>(mailboxes[r]);
+    }
+    *plan = p;
+    return HP_OK;
+}
+
+extern "C" HP_API int hp_pipeline_plan_launch(const hp_plan* p, hp_stream_t stream) {
+    HP_REQUIRE(p, HP_ERR_NULL, "hp_pipeline_plan_launch: null plan");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (p->link.world <= 1)
+        return launch_pipeline(p->pred, p->joints, p->vis, p->B, p->K, p->H, p->W, p->sx, p->sy, p->tmp, p->tab, p->eps,
+                               p->thr, p->loss_mask, p->pred_xy, p->maxvals, p->weight_out, p->partial, p->accumulate,
+                               p->result, p->workspace, st, p->flags);
+    bool exchanged = false;
+    if (int rc = launch_pipeline(p->pred, p->joints, p->vis, p->B, p->K, p->H, p->W, p->sx, p->sy, p->tmp, p->tab, p->eps,
+                                 p->thr, p->loss_mask, p->pred_xy, p->maxvals, p->weight_out, p->partial, 0, p->result,
+                                 p->workspace, st, p->flags, &p->link, &exchanged))
+        return rc;
+    if (exchanged) return HP_OK;
+    return launch_finalize_peer(p->partial, p->mailboxes, p->link.rank, p->link.world, p->K, 0, p->partial, p->result,
+                                (p->flags & HP_PIPE_OVERLAP_PREV) ? 1 : 0, st);
+}
+
+extern "C" HP_API int hp_pipeline_plan_destroy(hp_plan* p) {
+    delete p;
+    return HP_OK;
 }
 
 /* profiling aid: blocks of the TMA-staged pipeline kernel stamp their timeline into `buf` (device memory,

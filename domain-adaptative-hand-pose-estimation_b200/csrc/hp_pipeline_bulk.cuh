@@ -18,6 +18,7 @@
 //
 // Algorithmic bytes per map: H*W*4 + 24 + 8; the map is read from HBM exactly once.
 #pragma once
+#include "hp_internal.cuh"
 #include "hp_pipeline_common.cuh"
 #include "hp_pipeline_tiles.cuh"  // PatchSlot, WarpLoss, warp_sum3_scattered, kTileMaxPatch
 
@@ -29,6 +30,7 @@ struct BulkArgs {
     int n_chunks;   // chunks per map (1 unless the map is larger than a stage)
     int overlap;    // 0: serialised launch; d >= 1: programmatic dependent launch on 1/d of the block slots, so that
                     // d consecutive launches are resident at once (HP_PIPE_OVERLAP_PREV | HP_PIPE_DEPTH(d))
+    PeerLink link;  // world > 1: the last block sums the partial vector over the ranks itself (NVLink peer memory)
     unsigned long long* trace;  // nullable profiling buffer (hp_debug_pipeline_trace): per block a header
                                 // {globaltimer, clock64} at entry and exit, per warp and map 4 clock64 stamps
 };
@@ -206,9 +208,16 @@ struct BulkShared {
 
 // last block, ONE warp: workspace -> partial (= or +=), workspace back to zero, optional finalise
 // (same results as pipeline_publish, without block barriers)
-__device__ __forceinline__ void bulk_publish_warp(const PipeArgs& a, BulkShared& sh, int lane) {
+// When the batch is sharded over GPUs (link.world > 1) the same warp then performs the path's one collective
+// in place: it stores the vector into every rank's mailbox over NVLink, flags it with the step number, waits
+// (bounded) for the other ranks' vectors of the same step and sums them in rank order - compute and collective
+// in ONE kernel, no NCCL launch and no second kernel on the step path.  All entries are integers, so every rank
+// ends with bit-identical totals.
+__device__ __forceinline__ void bulk_publish_warp(const PipeArgs& a, const PeerLink& link, BulkShared& sh, int lane) {
     const int K = a.K, n = 4 + 2 * K + 6;
     const bool add = a.accumulate != 0;
+    const bool exchange = link.world > 1;
+    int timeout = 0;
     for (int i = lane; i < n; i += 32) {
         long long v;
         if (i < 2) {
@@ -227,10 +236,45 @@ __device__ __forceinline__ void bulk_publish_warp(const PipeArgs& a, BulkShared&
             a.ws->acc[j] = 0;
         }
         if (add) v += a.partial[i];
-        a.partial[i] = v;
+        if (!exchange) a.partial[i] = v;
         sh.pub[i] = v;
     }
     __syncwarp();
+    if (exchange) {
+        const int world = link.world, rank = link.rank;
+        long long* counter = peer_counter(link.mailbox[rank], world);
+        // step number, counted on the device (the previous launch, which wrote it, is complete: griddep_wait)
+        const long long seq = *reinterpret_cast<volatile long long*>(counter) + 1;
+        const int parity = static_cast<int>(seq & 1);
+        for (int dst = 0; dst < world; ++dst) {
+            long long* slot = peer_slot(link.mailbox[dst], world, parity, rank);
+            for (int i = lane; i < n; i += 32) slot[i] = sh.pub[i];
+        }
+        __threadfence_system();  // payload before flag, at system scope (peer GPUs)
+        __syncwarp();
+        if (lane < world) {
+            *reinterpret_cast<volatile long long*>(peer_slot(link.mailbox[lane], world, parity, rank) + (kPeerWords - 1)) = seq;
+            volatile long long* flag = peer_slot(link.mailbox[rank], world, parity, lane) + (kPeerWords - 1);
+            const long long t0 = clock64();
+            while (*flag != seq) {
+                if (clock64() - t0 > 4000000000ll) {  // ~2 s: a peer never arrived
+                    timeout = 1;
+                    break;
+                }
+            }
+            __threadfence_system();
+        }
+        timeout = __any_sync(0xffffffffu, timeout);
+        for (int i = lane; i < n; i += 32) {
+            long long tot = 0;
+            for (int src = 0; src < world; ++src)
+                tot += *reinterpret_cast<volatile long long*>(peer_slot(link.mailbox[rank], world, parity, src) + i);
+            sh.pub[i] = tot;
+            a.partial[i] = tot;
+        }
+        if (lane == 0) *counter = seq;
+        __syncwarp();
+    }
     if (a.result) {
         for (int k = lane; k < K; k += 32) {
             const long long h = sh.pub[4 + k], v = sh.pub[4 + K + k];
@@ -252,6 +296,7 @@ __device__ __forceinline__ void bulk_publish_warp(const PipeArgs& a, BulkShared&
             a.result[1] = loss_from_fx(sh.pub[1], cls[3], cls[4], cls[5], sh.pub[2]);
             a.result[2] = cnt != 0 ? __ddiv_rn(total, static_cast<double>(cnt)) : 0.0;
             a.result[3] = static_cast<double>(cnt);
+            if (timeout) a.result[0] = a.result[1] = __longlong_as_double(0x7ff8000000000000ll);
         }
     }
     if (lane == 0) a.ws->counter = 0;
@@ -553,7 +598,7 @@ __global__ void __launch_bounds__(32 * W, BPS) pipeline_bulk_kernel(const BulkAr
             if (last) __threadfence();
         }
         last = __shfl_sync(0xffffffffu, last, 0);
-        if (last) bulk_publish_warp(a, sh, lane);
+        if (last) bulk_publish_warp(a, t.link, sh, lane);
     } else {
         // the other warps deliver the buffered per-map outputs meanwhile
         const int n_buf = n_local < kBulkOutCap ? n_local : kBulkOutCap;

@@ -33,6 +33,69 @@ def allreduce_partial(partial: torch.Tensor, group=None) -> torch.Tensor:
     return partial
 
 
+class PeerExchange:
+    """The path's single collective without NCCL on the per-step path: every rank owns a mailbox in device
+    memory (``hp_peer_alloc``), exported with CUDA IPC and mapped by all ranks of the node; per step ONE small
+    kernel (``hp_pipeline_finalize_peer``) stores this rank's int64 partial vector into every mailbox over
+    NVLink, waits (bounded) for the other ranks' vectors of the same step, sums them in rank order and
+    finalises - all ranks get bit-identical results, with no collective launch latency on the host.
+
+    Setup uses ``torch.distributed`` once (all-gather of the 64-byte IPC handles).  Single node only."""
+
+    def __init__(self, device, group=None):
+        import ctypes as C
+        from . import _lib
+        self._lib, self._C = _lib, C
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.device = torch.device(device)
+        self._mapped = []
+        with torch.cuda.device(self.device):
+            own = C.c_void_p()
+            _lib.call("hp_peer_alloc", self.world, C.byref(own))
+            self._own = own
+            handle = (C.c_ubyte * 64)()
+            _lib.call("hp_peer_export", own, handle)
+            mine = torch.tensor(list(bytes(handle)), dtype=torch.uint8, device=self.device)
+            every = [torch.empty_like(mine) for _ in range(self.world)]
+            dist.all_gather(every, mine, group=group)
+            ptrs = []
+            for r, h in enumerate(every):
+                if r == self.rank:
+                    ptrs.append(own.value)
+                    continue
+                raw = (C.c_ubyte * 64)(*h.cpu().tolist())
+                mapped = C.c_void_p()
+                _lib.call("hp_peer_import", raw, C.byref(mapped))
+                self._mapped.append(mapped)
+                ptrs.append(mapped.value)
+            self._table = (C.c_void_p * self.world)(*ptrs)
+            torch.cuda.synchronize(self.device)
+        dist.barrier(group=group)          # every mailbox is mapped (and zeroed) before the first step
+
+    def finalize(self, partial, K, result, partial_out=None, stream=None):
+        """Enqueue the exchange + finalise of this step on ``stream`` (default: current)."""
+        C, _lib = self._C, self._lib
+        st = C.c_void_p(stream.cuda_stream) if stream is not None else _lib.stream_ptr(self.device)
+        _lib.call("hp_pipeline_finalize_peer", _lib.ptr(partial), self._table, self.rank, self.world, int(K),
+                  C.c_int64(0), _lib.ptr(partial_out), _lib.ptr(result), st)      # 0: step counted on the device
+
+    def close(self):
+        if self._own is None:
+            return
+        try:
+            torch.cuda.synchronize(self.device)
+            if dist.is_initialized():
+                dist.barrier(group=self.group)     # nobody unmaps while a peer may still write
+            with torch.cuda.device(self.device):
+                for m in self._mapped:
+                    self._lib.call("hp_peer_close", m)
+                self._lib.call("hp_peer_free", self._own)
+        finally:
+            self._mapped, self._own = [], None
+
+
 FX_SHIFT = 40                    # HP_LOSS_FX_SHIFT of include/hp_b200.h
 FX_LIMIT = 2097152.0             # |per-map loss| >= 2**21 counts as infinite
 

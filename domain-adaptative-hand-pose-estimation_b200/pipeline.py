@@ -50,12 +50,27 @@ class PipelineResult:
                     acc=r[4:4 + K].copy())
 
 
+class _Plan:
+    """Owner of one C-side plan handle (``hp_plan_t``) and of the tensors whose pointers it stores."""
+
+    def __init__(self, handle, keep):
+        self.handle, self.keep = handle, keep
+
+    def __del__(self):
+        try:
+            if self.handle:
+                _lib.load().hp_pipeline_plan_destroy(self.handle)
+        except Exception:  # interpreter shutdown
+            pass
+        self.handle = None
+
+
 class HeatmapPipeline:
     """gen + loss + decode + PCK, one kernel launch per batch (one more tiny one after the
     all-reduce when the batch is sharded over several GPUs)."""
 
     def __init__(self, num_keypoints=21, heatmap_size=(64, 64), image_size=(256, 256), sigma=2, kl_epsilon=0.0,
-                 thr=0.5, losses=("mse", "kl"), device=None, group=None):
+                 thr=0.5, losses=("mse", "kl"), device=None, group=None, collective="nccl"):
         if not torch.cuda.is_available():
             raise RuntimeError("no CUDA device: the B200 heatmap path has no CPU fallback")
         self.K = int(num_keypoints)
@@ -78,7 +93,12 @@ class HeatmapPipeline:
         self._host_state = None
         self._ws = None
         self._plans = {}
+        self._fast = {}
         self._comm_stream = None
+        if collective not in ("nccl", "peer"):
+            raise ValueError("collective must be 'nccl' or 'peer'")
+        self.collective = collective      # how the sharded path sums the partial vectors (dist.PeerExchange / NCCL)
+        self._peer = None
         _lib.load()
 
     # ------------------------------------------------------------------------------ device path
@@ -106,21 +126,53 @@ class HeatmapPipeline:
         if out is None:
             out = self.alloc_outputs(B, dev)
         ws = self._workspace(B * K)
-        fn = _lib.load().hp_pipeline_fused_ex
-        args = (_lib.ptr(pred), _lib.ptr(joints), _lib.ptr(vis), B, K, H, W, C.c_double(self.stride[0]),
-                C.c_double(self.stride[1]), self.tmp, _lib.ptr(self.tab), C.c_float(self.kl_epsilon),
-                C.c_double(self.thr), self.loss_mask, _lib.ptr(out.pred_xy), _lib.ptr(out.maxvals), _lib.ptr(out.weight),
-                _lib.ptr(out.partial), 0, _lib.ptr(out.result) if finalize else None, _lib.ptr(ws),
-                C.c_uint(_lib.pipe_flags(overlap)))
-        keep = (pred, joints, vis, out, ws)            # the plan owns references: pointers stay valid
-        current_stream = torch.cuda.current_stream
+        return self._bind(pred, joints, vis, out, ws, finalize, overlap, None), out
 
-        def launch(_keep=keep):
-            rc = fn(*args, C.c_void_p(current_stream(dev).cuda_stream))
+    def _bind(self, pred, joints, vis, out, ws, finalize, overlap, peer):
+        """Arguments validated and stored once on the C side (``hp_pipeline_plan_create``); the returned ``launch()``
+        is a two-argument FFI call (a step is a ~12 us kernel: per-call marshalling of 25 arguments costs as much)."""
+        lib = _lib.load()
+        B, K, H, W = pred.shape
+        dev = pred.device
+        handle = C.c_void_p()
+        _lib.call("hp_pipeline_plan_create", _lib.ptr(pred), _lib.ptr(joints), _lib.ptr(vis), B, K, H, W,
+                  C.c_double(self.stride[0]), C.c_double(self.stride[1]), self.tmp, _lib.ptr(self.tab),
+                  C.c_float(self.kl_epsilon), C.c_double(self.thr), self.loss_mask, _lib.ptr(out.pred_xy),
+                  _lib.ptr(out.maxvals), _lib.ptr(out.weight), _lib.ptr(out.partial), 0,
+                  _lib.ptr(out.result) if finalize else None, _lib.ptr(ws),
+                  peer._table if peer is not None else None, peer.rank if peer is not None else 0,
+                  peer.world if peer is not None else 1, C.c_uint(_lib.pipe_flags(overlap)), C.byref(handle))
+        plan = _Plan(handle, (pred, joints, vis, out, ws, peer, self.tab))   # the plan owns references: pointers stay valid
+        fn = lib.hp_pipeline_plan_launch
+        current_stream = torch.cuda.current_stream
+        last_error = lib.hp_last_error
+
+        def launch(_plan=plan, _h=handle):
+            rc = fn(_h, current_stream(dev).cuda_stream)
             if rc != 0:
-                raise RuntimeError(f"hp_pipeline_fused_ex failed (rc={rc}): "
-                                   f"{_lib.load().hp_last_error().decode(errors='replace')}")
-        return launch, out
+                raise RuntimeError(f"hp_pipeline_plan_launch failed (rc={rc}): {last_error().decode(errors='replace')}")
+        return launch
+
+    def plan_peer(self, pred, joints, vis, out=None, overlap=False):
+        """Sharded step with the peer-memory exchange as ONE call (``hp_pipeline_fused_peer``): the fused kernel on
+        this rank's slice, then the exchange + finalise kernel, both on the current stream."""
+        pred = _lib.require_cuda(pred, "HeatmapPipeline(pred)")
+        joints = _lib.require_cuda(joints, "HeatmapPipeline(joints)", torch.float64)
+        vis = _lib.require_cuda(vis, "HeatmapPipeline(vis)")
+        B, K, H, W = pred.shape
+        if (K, H, W) != (self.K, self.H, self.W):
+            raise ValueError(f"pred is {tuple(pred.shape)}, pipeline was built for K={self.K} H={self.H} W={self.W}")
+        if joints.numel() != 2 * B * K or vis.numel() != B * K:
+            raise ValueError("joints must be [B,K,2] and vis [B,K,1]")
+        dev = pred.device
+        if dev != self.device:
+            raise ValueError(f"inputs are on {dev}, the pipeline was built for {self.device}")
+        if out is None:
+            out = self.alloc_outputs(B, dev)
+        if self._peer is None:
+            self._peer = hpdist.PeerExchange(self.device, self.group)
+        ws = self._workspace(B * K)
+        return self._bind(pred, joints, vis, out, ws, True, overlap, self._peer), out
 
     def _workspace(self, n_maps):
         """One zero-initialised workspace per pipeline object (a pipeline is used on one stream at a time)."""
@@ -150,12 +202,29 @@ class HeatmapPipeline:
         """pred float32 [B,K,H,W], joints float64 [B,K,2] (image px), vis float32 [B,K,1]|[B,K]: CUDA
         tensors of THIS rank's slice of the batch.  Asynchronous on the current stream.  Single process:
         one kernel.  Sharded (torch.distributed initialised): kernel -> all-reduce of the 4+2K partial
-        doubles (the path's only collective) -> finalise kernel."""
+        doubles (the path's only collective) -> finalise kernel; with ``collective="peer"`` the exchange over
+        NVLink peer memory happens inside the kernel's last block instead (one kernel per step, no NCCL)."""
+        fkey = (id(pred), id(joints), id(vis), id(out), overlap)
+        fast = self._fast.get(fkey)
+        if fast is not None:             # same tensors as an earlier call: the pre-bound launch, nothing else
+            fast[0]()
+            return fast[1]
         sharded = hpdist.is_distributed(self.group)
+        if not sharded or self.collective == "peer":
+            hit = self.plan_peer(pred, joints, vis, out, overlap) if sharded else self.plan(pred, joints, vis, out, True, overlap)
+            if len(self._fast) > 256:
+                self._fast.clear()
+            self._fast[fkey] = (hit[0], hit[1], (pred, joints, vis, out))   # the tensors stay alive: ids stay unique
+            hit[0]()
+            return hit[1]
+        # NCCL collective: kernel on this stream, all-reduce + finalise on a side stream
         launch, out = self._cached_plan(pred, joints, vis, out, not sharded, overlap)
+        if sharded and out.ready is not None:
+            # `out` is being reused: its previous collective (side stream) must have consumed it first
+            torch.cuda.current_stream(self.device).wait_event(out.ready)
         launch()
         if sharded:
-            # The collective and the finalise run on a side stream so that they overlap the NEXT step's
+            # NCCL: the collective and the finalise run on a side stream so that they overlap the NEXT step's
             # kernel (steps are independent; `out.ready` / `out.wait()` order consumers after them).
             main = torch.cuda.current_stream(self.device)
             if self._comm_stream is None:
@@ -170,6 +239,15 @@ class HeatmapPipeline:
                     out.ready = torch.cuda.Event()
                 out.ready.record(comm)
         return out
+
+    def close(self):
+        """Release the peer mailboxes (collective; call on every rank before destroying the process group)."""
+        self._fast.clear()
+        self._plans.clear()
+        if self._peer is not None:
+            self.join()
+            self._peer.close()
+            self._peer = None
 
     def join(self):
         """Order the current stream after every outstanding collective of this pipeline."""

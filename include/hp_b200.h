@@ -215,7 +215,9 @@ int hp_pipeline_finalize(const int64_t* partial, int K, double* result, hp_strea
  * theirs.  Per step: hp_pipeline_finalize_peer replaces [all-reduce(partial) ; hp_pipeline_finalize]:
  * it writes this rank's partial into every mailbox, waits (bounded) for all ranks' step `seq`, sums in
  * rank order and finalises.  mailboxes[r] = rank r's mailbox as mapped here (own pointer for r == rank).
- * `seq` = 1, 2, 3, ... identical on all ranks.  On a timeout result[0] and result[1] are NaN. */
+ * `seq` = 1, 2, 3, ... identical on all ranks, or 0: the step number is counted on the device (in the rank's own
+ * mailbox), which makes a captured CUDA graph of steps replayable.  Do not mix the two on one mailbox.
+ * On a timeout result[0] and result[1] are NaN. */
 size_t hp_peer_mailbox_bytes(int world);
 int hp_peer_alloc(int world, void** mailbox);
 int hp_peer_free(void* mailbox);
@@ -224,6 +226,35 @@ int hp_peer_import(const void* handle64, void** mapped);
 int hp_peer_close(void* mapped);
 int hp_pipeline_finalize_peer(const int64_t* partial, void* const* mailboxes, int rank, int world, int K,
                               int64_t seq, int64_t* partial_out, double* result, hp_stream_t stream);
+
+/* One batch-sharded step in a single call and - for the shapes served by the TMA-staged kernel (H*W = 256,
+ * 1024 or a multiple of 4096 floats, aligned) - in a single KERNEL: the last block of the fused kernel stores
+ * this rank's partial vector into every rank's mailbox over NVLink, waits (bounded) for the others, sums in rank
+ * order and finalises; `partial` and `result` hold the totals over all ranks on return (stream order).  Other
+ * shapes run hp_pipeline_fused_ex + hp_pipeline_finalize_peer.  `seq` must be 0 (step counted on the device).
+ * With HP_PIPE_OVERLAP_PREV a train of sharded steps stays overlapped. */
+int hp_pipeline_fused_peer(const float* pred, const double* joints, const float* vis,
+                           int B, int K, int H, int W, double stride_x, double stride_y, int tmp,
+                           const float* tab, float kl_epsilon, double thr, int loss_mask,
+                           float* pred_xy, float* maxvals, float* weight_out,
+                           int64_t* partial, double* result, void* workspace,
+                           void* const* mailboxes, int rank, int world, int64_t seq,
+                           unsigned int flags, hp_stream_t stream);
+
+/* Pre-bound steps.  A step is a ~12 us kernel; marshalling two dozen arguments through an FFI costs about as much
+ * on the host, so a plan validates and stores the arguments of hp_pipeline_fused_ex (world <= 1, mailboxes NULL) or
+ * hp_pipeline_fused_peer (world > 1) once and is launched with a two-argument call.  The plan keeps the caller's
+ * pointers (it owns none of the memory) until hp_pipeline_plan_destroy. */
+typedef struct hp_plan hp_plan_t;
+int hp_pipeline_plan_create(const float* pred, const double* joints, const float* vis,
+                            int B, int K, int H, int W, double stride_x, double stride_y, int tmp,
+                            const float* tab, float kl_epsilon, double thr, int loss_mask,
+                            float* pred_xy, float* maxvals, float* weight_out,
+                            int64_t* partial, int accumulate, double* result, void* workspace,
+                            void* const* mailboxes, int rank, int world, unsigned int flags,
+                            hp_plan_t** plan);
+int hp_pipeline_plan_launch(const hp_plan_t* plan, hp_stream_t stream);
+int hp_pipeline_plan_destroy(hp_plan_t* plan);
 
 /* Host-buffer form (end-to-end path): h_* are pinned host arrays; the batch is cut into slabs
  * of slab_B samples whose H2D copies (copy_stream) overlap the kernels (stream); device

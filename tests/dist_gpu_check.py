@@ -31,6 +31,30 @@ def main():
                          torch.from_numpy(d["vis"][lo:hi]).to(dev)))
     got = [o.host() for o in outs]
     part = outs[-1].wait().partial.cpu().numpy()
+    # the same steps with the NVLink peer-memory exchange instead of NCCL (one kernel per step): 40 steps in flight,
+    # separate outputs, overlapped launches - must be bit-identical on every rank
+    peer = hp.HeatmapPipeline(kl_epsilon=1e-7, device=dev, collective="peer")
+    x = [torch.from_numpy(d[k][lo:hi]).to(dev) for k in ("pred", "joints", "vis")]
+    pouts = [peer.alloc_outputs(hi - lo, dev) for _ in range(8)]
+    for overlap in (False, True, 2):
+        for o in pouts:
+            o.partial.zero_(); o.result.zero_()
+        for rep in range(40):
+            peer(x[0], x[1], x[2], out=pouts[rep % 8], overlap=overlap)
+        peer.join()
+        torch.cuda.synchronize()
+        for o in pouts:
+            assert np.array_equal(o.partial.cpu().numpy(), part), (overlap, o.partial.cpu().numpy(), part)
+            assert torch.equal(o.result, outs[-1].result), (overlap, o.result, outs[-1].result)
+    peer.close()
+    # NCCL path with reused outputs and overlapped launches
+    nouts = [pipe.alloc_outputs(hi - lo, dev) for _ in range(3)]
+    for rep in range(30):
+        pipe(x[0], x[1], x[2], out=nouts[rep % 3], overlap=True)
+    pipe.join()
+    torch.cuda.synchronize()
+    for o in nouts:
+        assert np.array_equal(o.partial.cpu().numpy(), part), ("nccl", o.partial.cpu().numpy(), part)
     # single-GPU reference on the whole batch (group of one rank)
     solo_group = dist.new_group(ranks=[rank]) if False else None
     dist.barrier()
@@ -50,7 +74,7 @@ def main():
         assert np.array_equal(want["acc"], o["acc"]) and want["cnt"] == o["cnt"]
         np.testing.assert_allclose(want["mse"], o["mse"], rtol=1e-5)
         np.testing.assert_allclose(want["kl"], o["kl"], rtol=1e-5)
-    print(f"rank {rank}: sharded == single-GPU bit for bit")
+    print(f"rank {rank}: sharded (NCCL and peer-memory exchange) == single-GPU bit for bit")
 
 
 if __name__ == "__main__":
