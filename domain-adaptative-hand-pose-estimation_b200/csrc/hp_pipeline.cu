@@ -462,7 +462,7 @@ extern "C" HP_API int hp_pipeline_fused_peer(const float* pred, const double* jo
     PeerLink link{};
     for (int r = 0; r < world; ++r) {
         HP_REQUIRE(mailboxes[r], HP_ERR_NULL, "hp_pipeline_fused_peer: mailbox %d is null", r);
-        link.mailbox[r] = static_cast<long long*>(mailboxes[r]);
+        link.mailbox[r] = static_cast<unsigned long long*>(mailboxes[r]);
     }
     link.rank = rank;
     link.world = world;
@@ -522,7 +522,7 @@ extern "C" HP_API int hp_pipeline_plan_create(const float* pred, const double* j
             return fail(HP_ERR_NULL, "hp_pipeline_plan_create: mailbox %d is null", r);
         }
         p->mailboxes[r] = mailboxes[r];
-        p->link.mailbox[r] = static_cast<long long*>(mailboxes[r]);
+        p->link.mailbox[r] = static_cast<unsigned long long*>(mailboxes[r]);
     }
     *plan = p;
     return HP_OK;

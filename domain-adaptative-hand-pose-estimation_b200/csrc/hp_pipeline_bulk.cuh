@@ -209,7 +209,7 @@ struct BulkShared {
 // last block, ONE warp: workspace -> partial (= or +=), workspace back to zero, optional finalise
 // (same results as pipeline_publish, without block barriers)
 // When the batch is sharded over GPUs (link.world > 1) the same warp then performs the path's one collective
-// in place: it stores the vector into every rank's mailbox over NVLink, flags it with the step number, waits
+// in place: it stores the vector into every rank's mailbox over NVLink as step-tagged 8-byte entries, polls
 // (bounded) for the other ranks' vectors of the same step and sums them in rank order - compute and collective
 // in ONE kernel, no NCCL launch and no second kernel on the step path.  All entries are integers, so every rank
 // ends with bit-identical totals.
@@ -241,38 +241,8 @@ __device__ __forceinline__ void bulk_publish_warp(const PipeArgs& a, const PeerL
     }
     __syncwarp();
     if (exchange) {
-        const int world = link.world, rank = link.rank;
-        long long* counter = peer_counter(link.mailbox[rank], world);
-        // step number, counted on the device (the previous launch, which wrote it, is complete: griddep_wait)
-        const long long seq = *reinterpret_cast<volatile long long*>(counter) + 1;
-        const int parity = static_cast<int>(seq & 1);
-        for (int dst = 0; dst < world; ++dst) {
-            long long* slot = peer_slot(link.mailbox[dst], world, parity, rank);
-            for (int i = lane; i < n; i += 32) slot[i] = sh.pub[i];
-        }
-        __threadfence_system();  // payload before flag, at system scope (peer GPUs)
-        __syncwarp();
-        if (lane < world) {
-            *reinterpret_cast<volatile long long*>(peer_slot(link.mailbox[lane], world, parity, rank) + (kPeerWords - 1)) = seq;
-            volatile long long* flag = peer_slot(link.mailbox[rank], world, parity, lane) + (kPeerWords - 1);
-            const long long t0 = clock64();
-            while (*flag != seq) {
-                if (clock64() - t0 > 4000000000ll) {  // ~2 s: a peer never arrived
-                    timeout = 1;
-                    break;
-                }
-            }
-            __threadfence_system();
-        }
-        timeout = __any_sync(0xffffffffu, timeout);
-        for (int i = lane; i < n; i += 32) {
-            long long tot = 0;
-            for (int src = 0; src < world; ++src)
-                tot += *reinterpret_cast<volatile long long*>(peer_slot(link.mailbox[rank], world, parity, src) + i);
-            sh.pub[i] = tot;
-            a.partial[i] = tot;
-        }
-        if (lane == 0) *counter = seq;
+        timeout = peer_exchange_warp(link, sh.pub, n, lane);   // sh.pub: this rank's vector -> totals over the ranks
+        for (int i = lane; i < n; i += 32) a.partial[i] = sh.pub[i];
         __syncwarp();
     }
     if (a.result) {
