@@ -28,52 +28,87 @@ __device__ __forceinline__ unsigned long long* peer_slot(unsigned long long* bas
 __device__ __forceinline__ unsigned long long* peer_counter(unsigned long long* base, int world) {
     return base + static_cast<size_t>(2) * world * kPeerSlotEntries;
 }
+__device__ __forceinline__ void peer_store2(unsigned long long* p, unsigned long long a, unsigned long long b) {
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+}
 __device__ __forceinline__ void peer_store(unsigned long long* p, unsigned long long v) {
     asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ ulonglong2 peer_load2(const unsigned long long* p) {
+    ulonglong2 v;
+    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
+    return v;
 }
 __device__ __forceinline__ unsigned long long peer_load(const unsigned long long* p) {
     unsigned long long v;
     asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
+constexpr int kPeerScratchWords = kPeerMaxWorld * (kPeerSlotEntries / 2);  // int64 words of shared-memory scratch
 // ONE warp: vec[0..n) (shared memory; this rank's int64 vector) -> sum over all ranks, in rank order, in place.
+// `scratch`: kPeerScratchWords int64 of shared memory.  The (source, word) pairs are spread over the lanes and
+// polled eight at a time, so a pass over all sources costs one or two memory round trips however many ranks
+// there are (polling source after source cost a round trip per rank: 5.6 us at 8 GPUs).
 // The step number is counted on the device (the rank's own mailbox), so captured graphs of steps replay.
 // Returns non-zero in every lane if a peer did not arrive within ~2 s.
-__device__ __forceinline__ int peer_exchange_warp(const PeerLink& link, long long* vec, int n, int lane) {
+__device__ __forceinline__ int peer_exchange_warp(const PeerLink& link, long long* vec, long long* scratch, int n, int lane) {
     const int world = link.world, rank = link.rank;
     unsigned long long* counter = peer_counter(link.mailbox[rank], world);
     const unsigned long long seq = peer_load(counter) + 1ull;
     const unsigned long long tag = (seq & 0xffffffffull) << 32;
+    const unsigned long long tag_mask = 0xffffffff00000000ull;
     const int parity = static_cast<int>(seq & 1ull);
+    // ---- send: a word travels as two tagged 8-byte entries, written with one 16-byte store ---------------------
     for (int dst = 0; dst < world; ++dst) {
         unsigned long long* slot = peer_slot(link.mailbox[dst], world, parity, rank);
         for (int w = lane; w < n; w += 32) {
             const unsigned long long v = static_cast<unsigned long long>(vec[w]);
-            peer_store(slot + 2 * w, tag | (v & 0xffffffffull));
-            peer_store(slot + 2 * w + 1, tag | (v >> 32));
+            peer_store2(slot + 2 * w, tag | (v & 0xffffffffull), tag | (v >> 32));
         }
     }
+    // ---- receive: pair p = src * n + w lives in lane p % 32, bit p / 32 of `pending` ------------------------------
+    const int total = world * n;
+    const int kcount = (total + 31) >> 5;  // <= 32
+    unsigned pending = 0;
+    for (int k = 0; k < kcount; ++k)
+        if (lane + 32 * k < total) pending |= 1u << k;
+    const unsigned long long* mine = peer_slot(link.mailbox[rank], world, parity, 0);
     int timeout = 0;
     const long long t0 = clock64();
-    for (int w = lane; w < n; w += 32) {
-        long long tot = 0;
-        for (int src = 0; src < world; ++src) {
-            const unsigned long long* slot = peer_slot(link.mailbox[rank], world, parity, src);
-            unsigned long long lo, hi;
-            while (true) {
-                lo = peer_load(slot + 2 * w);
-                hi = peer_load(slot + 2 * w + 1);
-                if ((lo & 0xffffffff00000000ull) == tag && (hi & 0xffffffff00000000ull) == tag) break;
-                if (clock64() - t0 > 4000000000ll) {  // ~2 s: a peer never arrived
-                    timeout = 1;
-                    break;
+    while (__any_sync(0xffffffffu, pending != 0)) {
+        for (int kb = 0; kb < kcount; kb += 8) {
+            ulonglong2 v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int k = kb + j, p = lane + 32 * k;
+                if ((pending >> k) & 1u) {
+                    const int src = p / n, w = p - src * n;
+                    v[j] = peer_load2(mine + static_cast<size_t>(src) * kPeerSlotEntries + 2 * w);
                 }
             }
-            tot += static_cast<long long>((hi << 32) | (lo & 0xffffffffull));
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int k = kb + j, p = lane + 32 * k;
+                if (((pending >> k) & 1u) && (v[j].x & tag_mask) == tag && (v[j].y & tag_mask) == tag) {
+                    scratch[p] = static_cast<long long>((v[j].y << 32) | (v[j].x & 0xffffffffull));
+                    pending &= ~(1u << k);
+                }
+            }
         }
-        vec[w] = tot;
+        if (clock64() - t0 > 4000000000ll) {  // ~2 s: a peer never arrived
+            timeout = pending != 0;
+            for (int k = 0; k < kcount; ++k)
+                if ((pending >> k) & 1u) scratch[lane + 32 * k] = 0;
+            pending = 0;
+        }
     }
     timeout = __any_sync(0xffffffffu, timeout);
+    __syncwarp();
+    for (int w = lane; w < n; w += 32) {
+        long long tot = 0;
+        for (int src = 0; src < world; ++src) tot += scratch[src * n + w];  // rank order
+        vec[w] = tot;
+    }
     if (lane == 0) peer_store(counter, seq);
     __syncwarp();
     return timeout;

@@ -29,9 +29,10 @@ struct PeerArgs {
     double* result;                     // [4+K]
 };
 
-// one warp, a few registers, 1.2 KB of shared memory: always fits beside the resident pipeline blocks of a train
+// one warp, a few registers, 9 KB of shared memory: always fits beside the resident pipeline blocks of a train
 __global__ void __launch_bounds__(32) pipeline_finalize_peer_kernel(const PeerArgs a) {
     __shared__ long long s_total[4 + 2 * HP_MAX_K + 6];
+    __shared__ long long s_scratch[kPeerScratchWords];
     const int n = 4 + 2 * a.K + 6, lane = threadIdx.x;
     // Programmatic dependent launch (no-ops without the launch attribute): the next pipeline launch of the train
     // may start right away; this kernel reads `partial` only once the pipeline launch before it has completed.
@@ -39,7 +40,7 @@ __global__ void __launch_bounds__(32) pipeline_finalize_peer_kernel(const PeerAr
     asm volatile("griddepcontrol.wait;" ::: "memory");
     for (int w = lane; w < n; w += 32) s_total[w] = a.partial[w];
     __syncwarp();
-    const int timeout = peer_exchange_warp(a.link, s_total, n, lane);
+    const int timeout = peer_exchange_warp(a.link, s_total, s_scratch, n, lane);
     if (a.partial_out)
         for (int w = lane; w < n; w += 32) a.partial_out[w] = s_total[w];
     if (lane == 0) {

@@ -213,7 +213,8 @@ struct BulkShared {
 // (bounded) for the other ranks' vectors of the same step and sums them in rank order - compute and collective
 // in ONE kernel, no NCCL launch and no second kernel on the step path.  All entries are integers, so every rank
 // ends with bit-identical totals.
-__device__ __forceinline__ void bulk_publish_warp(const PipeArgs& a, const PeerLink& link, BulkShared& sh, int lane) {
+__device__ __forceinline__ void bulk_publish_warp(const PipeArgs& a, const PeerLink& link, BulkShared& sh,
+                                                  long long* scratch, int lane) {
     const int K = a.K, n = 4 + 2 * K + 6;
     const bool add = a.accumulate != 0;
     const bool exchange = link.world > 1;
@@ -241,7 +242,7 @@ __device__ __forceinline__ void bulk_publish_warp(const PipeArgs& a, const PeerL
     }
     __syncwarp();
     if (exchange) {
-        timeout = peer_exchange_warp(link, sh.pub, n, lane);   // sh.pub: this rank's vector -> totals over the ranks
+        timeout = peer_exchange_warp(link, sh.pub, scratch, n, lane);  // sh.pub: this rank's vector -> totals over the ranks
         for (int i = lane; i < n; i += 32) a.partial[i] = sh.pub[i];
         __syncwarp();
     }
@@ -568,7 +569,9 @@ __global__ void __launch_bounds__(32 * W, BPS) pipeline_bulk_kernel(const BulkAr
             if (last) __threadfence();
         }
         last = __shfl_sync(0xffffffffu, last, 0);
-        if (last) bulk_publish_warp(a, t.link, sh, lane);
+        // (the block's stages are idle by now - every copy was consumed before the barrier above - and serve as the
+        // exchange's scratch space)
+        if (last) bulk_publish_warp(a, t.link, sh, reinterpret_cast<long long*>(s_dyn), lane);
     } else {
         // the other warps deliver the buffered per-map outputs meanwhile
         const int n_buf = n_local < kBulkOutCap ? n_local : kBulkOutCap;
