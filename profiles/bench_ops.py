@@ -1,0 +1,129 @@
+#!/usr/bin/env python
+"""Per-operator rates of the hot path on one B200 against each kernel's HBM roofline, through
+the public Python API (the call a user of the reference makes).  Not the headline bench (bench.py): these are
+the BASELINE.json parity configs C2..C5 measured per GPU, for DESIGN.md / BASELINE.md.
+
+    python profiles/bench_ops.py [--out gpurun_out/ops.json] [--reps 30]
+
+Timing: CUDA events around `reps` back-to-back calls on rotating input sets (>= 3 sets, each larger than or
+rotating past the 126 MB L2), after 5 warm-up calls.  bytes = algorithmic bytes per call as listed per row."""
+import argparse, importlib, json, os, sys
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+hp = importlib.import_module("domain-adaptative-hand-pose-estimation_b200")
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--out", default=None)
+ap.add_argument("--reps", type=int, default=30)
+args = ap.parse_args()
+dev = torch.device("cuda", 0)
+PEAK = 6450.3
+try:
+    PEAK = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+except Exception:
+    pass
+K = 21
+rows = []
+
+
+def timed(name, fn, n_sets, bytes_per_call, maps_per_call, note=""):
+    for i in range(5):
+        fn(i % n_sets)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.reps):
+        fn(i % n_sets)
+    e1.record()
+    torch.cuda.synchronize()
+    us = 1e3 * e0.elapsed_time(e1) / args.reps
+    gbs = bytes_per_call / (us * 1e-6) / 1e9
+    rows.append({"op": name, "us_per_call": us, "GBps": gbs, "frac_of_measured_hbm": gbs / PEAK,
+                 "heatmaps_per_s": maps_per_call / (us * 1e-6), "algorithmic_bytes": bytes_per_call, "note": note})
+    print(f"{name:58s} {us:9.1f} us  {gbs:8.1f} GB/s  {gbs / PEAK:5.2f} of HBM  {maps_per_call / (us * 1e-6) / 1e6:8.1f} M maps/s  {note}")
+
+
+def batch(seed, B, side):
+    return hp.synth.make_device_batch(seed, B, K, side, side, image_size=4 * side, device=dev)
+
+
+with torch.no_grad():
+    # ---- C2 shapes: 256 x 21 x 64 x 64 -----------------------------------------------------------------------
+    B, S = 256, 64
+    sets = [batch(10 + i, B, S) for i in range(4)]
+    tg = [hp.generate_target_batch(s["joints"], s["vis"], (S, S), 2, (4 * S, 4 * S)) for s in sets]
+    n, hw4 = B * K, S * S * 4
+    timed("get_max_preds (decode) 256x21x64x64", lambda i: hp.decode(sets[i]["pred"]), 4, n * (hw4 + 12), n)
+    timed("accuracy (2x decode + PCK) 256x21x64x64", lambda i: hp.pck(sets[i]["pred"], tg[i][0]), 4, n * (2 * hw4 + 8), n)
+    timed("generate_target_batch 256x21x64x64", lambda i: hp.generate_target_batch(sets[i]["joints"], sets[i]["vis"], (S, S), 2, (4 * S, 4 * S)),
+          4, n * (hw4 + 24), n, "write-only")
+    mse, kl = hp.JointsMSELoss(), hp.JointsKLLoss(epsilon=1e-7)
+    timed("JointsMSELoss fwd 256x21x64x64", lambda i: mse(sets[i]["pred"], tg[i][0], tg[i][1]), 4, n * 2 * hw4, n)
+    timed("JointsKLLoss fwd 256x21x64x64", lambda i: kl(sets[i]["pred"], tg[i][0], tg[i][1]), 4, n * 2 * hw4, n)
+
+# backward (autograd) -------------------------------------------------------------------------------------------
+preds = [s["pred"].clone().requires_grad_(True) for s in sets]
+
+
+def fwd_bwd(crit, i):
+    preds[i].grad = None
+    crit(preds[i], tg[i][0], tg[i][1]).backward()
+
+
+timed("JointsMSELoss fwd+bwd 256x21x64x64", lambda i: fwd_bwd(mse, i), 4, n * 5 * hw4, n, "fwd 2 reads; bwd 2 reads + 1 write")
+timed("JointsKLLoss fwd+bwd 256x21x64x64", lambda i: fwd_bwd(kl, i), 4, n * 5 * hw4, n, "fwd 2 reads; bwd 2 reads + 1 write")
+del preds, sets, tg
+torch.cuda.empty_cache()
+
+with torch.no_grad():
+    # ---- C3: 512 x 21 x 64 x 64 pseudo-label + KL regression disparity (x6) -------------------------------
+    B = 512
+    n = B * K
+    ys = [batch(20 + i, B, S)["pred"] for i in range(3)]
+    advs = [batch(30 + i, B, S)["pred"] for i in range(3)]
+    f32 = [torch.nn.functional.avg_pool2d(a, 2) for a in advs]
+    f16 = [torch.nn.functional.avg_pool2d(a, 4) for a in advs]
+    rd6 = hp.RegressionDisparityx6(hp.PseudoLabelGenerator(K, S, S), hp.JointsKLLoss(epsilon=1e-7))
+    timed("RegressionDisparityx6 'min' 512x21x64x64", lambda i: rd6(ys[i], advs[i], None, None, "min"), 3, n * 2 * hw4, n,
+          "read y + y_adv; gt/gf never written")
+    timed("RegressionDisparityx6 'max' (no fused map)", lambda i: rd6(ys[i], advs[i], None, None, "max"), 3, n * 2 * hw4, n)
+    t5 = [hp.fuse_multiscale(f16[i], f32[i], 64, 32)[0] for i in range(3)]
+    timed("RegressionDisparityx6 'max' + pre-fused target5", lambda i: rd6(ys[i], advs[i], t5[i], None, "max"), 3, n * 3 * hw4, n)
+    timed("fuse_multiscale 16+32 -> 64 and 16 -> 32 (512x21)", lambda i: hp.fuse_multiscale(f16[i], f32[i], 64, 32), 3,
+          n * (1024 + 4096 + hw4 + 4096), n, "reads 16^2 + 32^2, writes 64^2 + 32^2")
+    rd5 = hp.RegressionDisparityx5(hp.PseudoLabelGenerator03(K), hp.JointsKLLoss(epsilon=1e-7))
+    rd1 = hp.RegressionDisparityx1(hp.PseudoLabelGenerator01(K), hp.JointsKLLoss(epsilon=1e-7))
+    timed("RegressionDisparityx5 'min' (32x32 head)", lambda i: rd5(ys[i], f32[i], None, None, "min"), 3, n * (hw4 + 4096), n)
+    timed("RegressionDisparityx1 'min' (16x16 head)", lambda i: rd1(ys[i], f16[i], None, "min"), 3, n * (hw4 + 1024), n)
+    del ys, advs, f32, f16, t5
+    torch.cuda.empty_cache()
+
+    # ---- C4 per GPU: 256 samples, fuse 32/64/128 + decode + PCK ---------------------------------------------
+    B = 256
+    n = B * K
+    hi = [batch(40 + i, B, 128)["pred"] for i in range(3)]
+    mid = [torch.nn.functional.avg_pool2d(h, 2) for h in hi]
+    lo = [torch.nn.functional.avg_pool2d(h, 4) for h in hi]
+    tgt = [torch.randint(0, 128, (B, K, 2), device=dev).float() for _ in range(3)]
+    ev = hp.MultiscaleEval(K)
+    timed("MultiscaleEval fuse 32/64/128 + decode + PCK (256x21)", lambda i: ev(lo[i], mid[i], hi[i], tgt[i]), 3,
+          n * (4096 + 16384 + 65536 + 16), n, "fused map never written")
+    del hi, mid, lo
+    torch.cuda.empty_cache()
+
+    # ---- C5 per GPU: 1024 x 21 x 128 x 128 end-to-end pipeline ------------------------------------------------
+    B = 1024
+    n = B * K
+    p128 = [batch(50 + i, B, 128) for i in range(3)]
+    pipe = hp.HeatmapPipeline(num_keypoints=K, heatmap_size=(128, 128), image_size=(512, 512), kl_epsilon=1e-7, device=dev)
+    outs = [pipe.alloc_outputs(B, dev) for _ in range(3)]
+    timed("HeatmapPipeline 1024x21x128x128 (serialised launches)",
+          lambda i: pipe(p128[i]["pred"], p128[i]["joints"], p128[i]["vis"], out=outs[i]), 3, n * (65536 + 32), n)
+    timed("HeatmapPipeline 1024x21x128x128 (launch train)",
+          lambda i: pipe(p128[i]["pred"], p128[i]["joints"], p128[i]["vis"], out=outs[i], overlap=True), 3, n * (65536 + 32), n)
+
+if args.out:
+    with open(args.out, "w") as f:
+        json.dump({"hbm_peak_gbs": PEAK, "rows": rows}, f, indent=1)
