@@ -15,6 +15,19 @@
 
 namespace hp {
 
+
+// warp-level argmax with the numpy tie rule (lowest index, NaN wins); every lane gets the result
+__device__ __forceinline__ ArgMax warp_argmax_rows(ArgMax am, int lane) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        ArgMax b;
+        b.v = __shfl_xor_sync(0xffffffffu, am.v, o);
+        b.i = __shfl_xor_sync(0xffffffffu, am.i, o);
+        am = ((lane & o) == 0) ? am_merge(am, b) : am_merge(b, am);
+    }
+    return am;
+}
+
 struct Tap {
     int i0, i1;
     float l0, l1;
@@ -160,6 +173,228 @@ __global__ void __launch_bounds__(TPM* MPB)
     if (last_block_arrives(&ws->counter, gridDim.x)) pck_publish(ws, K, counts_out, acc_out);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Row-walking shape (the production path for W in {4, 8, ..., 128}, W % 4 == 0):
+// the first version above re-derived four bilinear taps and gathered eight source values for EVERY output
+// element (~250 instructions per float4: 0.07-0.14 of HBM).  Bilinear interpolation is separable,
+//     out(y, x) = l0y * T(i0y, x) + l1y * T(i1y, x),   T(r, x) = l0x * src[r][i0x] + l1x * src[r][i1x],
+// so here a lane owns four output columns for a strip of consecutive rows: its column taps are computed once,
+// the row taps once per block (shared-memory table), and the horizontally interpolated source rows T live in
+// registers and are refreshed only when the source row changes (every 2nd / 4th output row at x2 / x4).
+// Per output float4 that leaves: one 128-bit load of `hi` (the HBM stream), ~30 FMA-pipe instructions and the
+// argmax bookkeeping.  The blend uses fused multiply-adds; the materialising kernel and the decode kernel
+// share this code, so decoding in registers equals decoding the materialised map bit for bit.
+// ---------------------------------------------------------------------------------------------
+struct RowTap {
+    int i0, i1;
+    float l0, l1;
+};
+constexpr int kRowWarps = 4;
+
+struct RowSource {  // one low-resolution source as seen by a lane
+    const float* base;  // current map
+    int w;
+    Tap tx[4];
+    int cur0, cur1;     // source rows held in t0 / t1 (-1: none)
+    float t0[4], t1[4];
+};
+
+__device__ __forceinline__ void row_source_init(RowSource& s, int x0, float sx, int in_w, int out_w) {
+    s.w = in_w;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) s.tx[c] = make_tap(x0 + c, sx, in_w, out_w);
+    s.cur0 = s.cur1 = -1;
+}
+__device__ __forceinline__ void row_source_load(const RowSource& s, int r, float (&t)[4]) {
+    const float* row = s.base + r * s.w;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) t[c] = fmaf(s.tx[c].l1, __ldg(row + s.tx[c].i1), s.tx[c].l0 * __ldg(row + s.tx[c].i0));
+}
+// vertical blend of the source at an output row with taps ty (refreshing the cached rows as needed)
+__device__ __forceinline__ void row_source_at(RowSource& s, const RowTap ty, float (&v)[4]) {
+    if (ty.i0 != s.cur0) {
+        if (ty.i0 == s.cur1) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) s.t0[c] = s.t1[c];
+        } else {
+            row_source_load(s, ty.i0, s.t0);
+        }
+        s.cur0 = ty.i0;
+    }
+    if (ty.i1 != s.cur1) {
+        if (ty.i1 == s.cur0) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) s.t1[c] = s.t0[c];
+        } else {
+            row_source_load(s, ty.i1, s.t1);
+        }
+        s.cur1 = ty.i1;
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) v[c] = fmaf(ty.l1, s.t1[c], ty.l0 * s.t0[c]);
+}
+
+struct RowWalk {  // geometry of a block's walk over one map
+    int cpr;      // float4 per output row
+    int rps;      // output rows covered by a warp per step
+    int strip;    // rows per warp
+};
+
+// fused float4 of output row `row` for this lane (hi4: the lane's four `hi` values or zeros)
+__device__ __forceinline__ float4 fused_row4(const FuseSrc& f, RowSource& lo, RowSource& mid, const RowTap* s_rows, int row,
+                                             float4 hi4) {
+    float vl[4], r[4];
+    row_source_at(lo, s_rows[row], vl);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) r[c] = f.a_lo * vl[c];
+    if (f.mid) {
+        float vm[4];
+        row_source_at(mid, s_rows[f.H + row], vm);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) r[c] = fmaf(f.a_mid, vm[c], r[c]);
+    }
+    if (f.hi) {
+        r[0] = fmaf(f.a_hi, hi4.x, r[0]);
+        r[1] = fmaf(f.a_hi, hi4.y, r[1]);
+        r[2] = fmaf(f.a_hi, hi4.z, r[2]);
+        r[3] = fmaf(f.a_hi, hi4.w, r[3]);
+    }
+    return make_float4(r[0], r[1], r[2], r[3]);
+}
+
+template <bool DECODE>
+__global__ void __launch_bounds__(32 * kRowWarps)
+    fuse_rows_kernel(const FuseSrc f, const RowWalk g, int n_maps, float* __restrict__ out, const float* __restrict__ tgt_xy,
+                     int K, double thr, float* __restrict__ pred_xy, float* __restrict__ maxvals,
+                     int32_t* __restrict__ counts_out, double* __restrict__ acc_out, Workspace* __restrict__ ws) {
+    extern __shared__ RowTap s_rows[];  // [H] taps into lo, then [H] taps into mid
+    __shared__ ArgMax s_am[kRowWarps];
+    __shared__ int s_nan;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int HW = f.H * f.W;
+    for (int r = threadIdx.x; r < f.H; r += blockDim.x) {
+        const Tap tl = make_tap(r, f.sy_lo, f.hl, f.H);
+        s_rows[r] = RowTap{tl.i0, tl.i1, tl.l0, tl.l1};
+        if (f.mid) {
+            const Tap tm = make_tap(r, f.sy_mid, f.hm, f.H);
+            s_rows[f.H + r] = RowTap{tm.i0, tm.i1, tm.l0, tm.l1};
+        }
+    }
+    const int x0 = (lane % g.cpr) * 4, ro = lane / g.cpr;
+    RowSource lo, mid;
+    row_source_init(lo, x0, f.sx_lo, f.wl, f.W);
+    row_source_init(mid, x0, f.mid ? f.sx_mid : 1.0f, f.mid ? f.wm : f.W, f.W);
+    const int row_begin = warp * g.strip + ro, row_end = min(f.H, (warp + 1) * g.strip);
+    __syncthreads();
+
+    for (int map = blockIdx.x; map < n_maps; map += gridDim.x) {
+        lo.base = f.lo + static_cast<size_t>(map) * f.hl * f.wl;
+        lo.cur0 = lo.cur1 = -1;
+        if (f.mid) {
+            mid.base = f.mid + static_cast<size_t>(map) * f.hm * f.wm;
+            mid.cur0 = mid.cur1 = -1;
+        }
+        const float* hi = f.hi ? f.hi + static_cast<size_t>(map) * HW + x0 : nullptr;
+        float* o = DECODE ? nullptr : out + static_cast<size_t>(map) * HW + x0;
+        float best = -INFINITY, witness = 0.0f;
+        int best_row = row_begin;
+        for (int row = row_begin; row < row_end; row += 4 * g.rps) {
+            float4 h[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {  // four rows of the HBM stream in flight
+                const int r = row + u * g.rps;
+                h[u] = (hi && r < row_end) ? ldg_stream4(reinterpret_cast<const float4*>(hi + r * f.W)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int r = row + u * g.rps;
+                if (r < row_end) {
+                    const float4 v = fused_row4(f, lo, mid, s_rows, r, h[u]);
+                    if (DECODE) {
+                        const float m4 = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+                        best_row = (m4 > best) ? r : best_row;  // strict: the earlier row keeps ties
+                        best = fmaxf(best, m4);
+                        witness += (v.x + v.y) + (v.z + v.w);    // NaN / inf-inf witness
+                    } else {
+                        stg_stream4(reinterpret_cast<float4*>(o + r * f.W), v);
+                    }
+                }
+            }
+        }
+        if (DECODE) {
+            // the lane's first maximum: recompute its row (same code, same bits) and pick the component
+            ArgMax am = am_init();
+            if (row_begin < row_end) {
+                const float4 hb = hi ? ldg_stream4(reinterpret_cast<const float4*>(hi + best_row * f.W)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 v = fused_row4(f, lo, mid, s_rows, best_row, hb);
+                const int comp = (v.x == best) ? 0 : ((v.y == best) ? 1 : ((v.z == best) ? 2 : 3));
+                am.v = best;
+                am.i = best_row * f.W + x0 + comp;
+            }
+            am = warp_argmax_rows(am, lane);
+            const bool bad = __any_sync(0xffffffffu, witness != witness);
+            if (threadIdx.x == 0) s_nan = 0;
+            __syncthreads();
+            if (lane == 0) {
+                s_am[warp] = am;
+                if (bad) s_nan = 1;
+            }
+            __syncthreads();
+            if (s_nan) {
+                // a NaN (or +inf with -inf) somewhere in the fused map: element-wise scan with numpy's exact rules
+                ArgMax sx = am_init();
+                for (int r = row_begin; r < row_end; r += g.rps) {
+                    const float4 hb = hi ? ldg_stream4(reinterpret_cast<const float4*>(hi + r * f.W)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    am_scan4<true>(sx, fused_row4(f, lo, mid, s_rows, r, hb), r * f.W + x0);
+                }
+                sx = warp_argmax_rows(sx, lane);
+                __syncthreads();
+                if (lane == 0) s_am[warp] = sx;
+                __syncthreads();
+            }
+            if (threadIdx.x == 0) {
+                ArgMax a = s_am[0];
+#pragma unroll
+                for (int w = 1; w < kRowWarps; ++w) a = am_merge(a, s_am[w]);
+                float px, py;
+                decode_xy(a, f.W, px, py);
+                pred_xy[2 * map + 0] = px;
+                pred_xy[2 * map + 1] = py;
+                if (maxvals) maxvals[map] = a.v;
+                int valid, hit;
+                pck_one(px, py, tgt_xy[2 * map], tgt_xy[2 * map + 1], f.H, f.W, thr, valid, hit);
+                const int k = map % K;
+                if (valid) atomicAdd(&ws->counts[K + k], 1);
+                if (hit) atomicAdd(&ws->counts[k], 1);
+            }
+            __syncthreads();  // s_am / s_nan are reused by the next map
+        }
+    }
+    if (DECODE) {
+        if (last_block_arrives(&ws->counter, gridDim.x)) pck_publish(ws, K, counts_out, acc_out);
+    }
+}
+
+// rows kernel applicable?  W a multiple of 4 with W/4 dividing 32, 16-byte aligned streams, table fits
+static bool rows_geometry(const FuseSrc& f, const float* out, RowWalk& g) {
+    if (f.W % 4 != 0 || f.W > 128 || (32 % (f.W / 4)) != 0) return false;
+    if (f.hi && !aligned16(f.hi)) return false;
+    if (out && !aligned16(out)) return false;
+    if (f.H > 1024) return false;
+    g.cpr = f.W / 4;
+    g.rps = 32 / g.cpr;
+    const int steps = (f.H + kRowWarps * g.rps - 1) / (kRowWarps * g.rps);
+    g.strip = steps * g.rps;
+    return true;
+}
+static int rows_grid(int n_maps) {
+    int sms = hp_device_sm_count();
+    if (sms <= 0) sms = 148;
+    const int cap = sms * 4;  // 4 blocks of 4 warps per SM (128 registers per thread): persistent, grid-stride over the maps
+    return n_maps < cap ? n_maps : cap;
+}
+
 struct FuseDecodeLaunch {
     FuseSrc f;
     const float* tgt_xy;
@@ -208,12 +443,19 @@ extern "C" HP_API int hp_fuse_multiscale(const float* lo, int hl, int wl, float 
     HP_REQUIRE(out, HP_ERR_NULL, "hp_fuse_multiscale: out is null");
     HP_REQUIRE(n_maps >= 0, HP_ERR_SHAPE, "hp_fuse_multiscale: n_maps=%d", n_maps);
     if (n_maps == 0) return HP_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    RowWalk g;
+    if (rows_geometry(f, out, g)) {
+        const size_t smem = sizeof(RowTap) * 2 * static_cast<size_t>(H);
+        fuse_rows_kernel<false><<<rows_grid(n_maps), 32 * kRowWarps, smem, s>>>(f, g, n_maps, out, nullptr, 0, 0.0, nullptr,
+                                                                                nullptr, nullptr, nullptr, nullptr);
+        return launch_status("hp_fuse_multiscale");
+    }
     const bool vec = (W % 4 == 0) && aligned16(out) && (!hi || aligned16(hi));
     const size_t total = static_cast<size_t>(n_maps) * H * W / (vec ? 4 : 1);
     size_t blocks = (total + 255) / 256;
     const size_t cap = 148u * 8u * 16u;
     const int grid = static_cast<int>(blocks < cap ? blocks : cap);
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (vec) fuse_kernel<true><<<grid, 256, 0, s>>>(f, n_maps, out);
     else fuse_kernel<false><<<grid, 256, 0, s>>>(f, n_maps, out);
     return launch_status("hp_fuse_multiscale");
@@ -227,6 +469,13 @@ extern "C" HP_API int hp_fuse_decode_pck(const float* lo, int hl, int wl, float 
     if (int rc = make_src("hp_fuse_decode_pck", lo, hl, wl, a_lo, mid, hm, wm, a_mid, hi, a_hi, H, W, f)) return rc;
     HP_REQUIRE(tgt_xy && pred_xy && acc_out && workspace, HP_ERR_NULL, "hp_fuse_decode_pck: null pointer");
     HP_REQUIRE(B > 0 && K > 0 && K <= HP_MAX_K, HP_ERR_SHAPE, "hp_fuse_decode_pck: bad B=%d K=%d", B, K);
+    RowWalk g;
+    if (rows_geometry(f, nullptr, g)) {
+        const size_t smem = sizeof(RowTap) * 2 * static_cast<size_t>(H);
+        fuse_rows_kernel<true><<<rows_grid(B * K), 32 * kRowWarps, smem, static_cast<cudaStream_t>(stream)>>>(
+            f, g, B * K, nullptr, tgt_xy, K, thr, pred_xy, maxvals, counts, acc_out, static_cast<Workspace*>(workspace));
+        return launch_status("hp_fuse_decode_pck");
+    }
     FuseDecodeLaunch l{f, tgt_xy, B * K, K, thr, pred_xy, maxvals, counts, acc_out, static_cast<Workspace*>(workspace),
                        static_cast<cudaStream_t>(stream)};
     dispatch_map_walk(H * W, !hi || aligned16(hi), l);
