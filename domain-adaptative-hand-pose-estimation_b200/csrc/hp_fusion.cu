@@ -12,6 +12,7 @@
 #include "hp_common.cuh"
 #include "hp_decode.cuh"
 #include "hp_dispatch.cuh"
+#include "hp_tma.cuh"
 
 namespace hp {
 
@@ -192,47 +193,85 @@ struct RowTap {
 };
 constexpr int kRowWarps = 4;
 
-struct RowSource {  // one low-resolution source as seen by a lane
-    const float* base;  // current map
-    int w;
-    Tap tx[4];
-    int cur0, cur1;     // source rows held in t0 / t1 (-1: none)
-    float t0[4], t1[4];
+struct RowSource {  // one low-resolution source as seen by a lane (values in pairs: packed FMUL2 / FFMA2)
+    const float* base;   // current map in global memory (rows kernel)
+    uint32_t base_s;     // current map in shared memory (staged kernel), shared-window byte address
+    int w;               // source width (elements)
+    int off0[4], off1[4];        // element offsets of the two column taps of each output column
+    float2 l0[2], l1[2];         // column weights, columns (0,1) and (2,3)
+    int cur0, cur1;              // source rows held in t0 / t1 (-1: none)
+    float2 t0[2], t1[2];
 };
 
 __device__ __forceinline__ void row_source_init(RowSource& s, int x0, float sx, int in_w, int out_w) {
     s.w = in_w;
+    float l0[4], l1[4];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) s.tx[c] = make_tap(x0 + c, sx, in_w, out_w);
+    for (int c = 0; c < 4; ++c) {
+        const Tap t = make_tap(x0 + c, sx, in_w, out_w);
+        s.off0[c] = t.i0;
+        s.off1[c] = t.i1;
+        l0[c] = t.l0;
+        l1[c] = t.l1;
+    }
+    s.l0[0] = make_float2(l0[0], l0[1]); s.l0[1] = make_float2(l0[2], l0[3]);
+    s.l1[0] = make_float2(l1[0], l1[1]); s.l1[1] = make_float2(l1[2], l1[3]);
     s.cur0 = s.cur1 = -1;
+    s.base = nullptr;
+    s.base_s = 0;
 }
-__device__ __forceinline__ void row_source_load(const RowSource& s, int r, float (&t)[4]) {
-    const float* row = s.base + r * s.w;
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+template <bool STAGED>
+__device__ __forceinline__ void row_source_load(const RowSource& s, int r, float2 (&t)[2]) {
+    float a[4], b[4];
+    if (STAGED) {  // the map sits in shared memory: 32-bit addresses, one add per load
+        const uint32_t row = s.base_s + 4u * static_cast<uint32_t>(r * s.w);
 #pragma unroll
-    for (int c = 0; c < 4; ++c) t[c] = fmaf(s.tx[c].l1, __ldg(row + s.tx[c].i1), s.tx[c].l0 * __ldg(row + s.tx[c].i0));
+        for (int c = 0; c < 4; ++c) {
+            a[c] = lds_f32(row + 4u * static_cast<uint32_t>(s.off0[c]));
+            b[c] = lds_f32(row + 4u * static_cast<uint32_t>(s.off1[c]));
+        }
+    } else {
+        const float* row = s.base + r * s.w;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            a[c] = __ldg(row + s.off0[c]);
+            b[c] = __ldg(row + s.off1[c]);
+        }
+    }
+    t[0] = __ffma2_rn(s.l1[0], make_float2(b[0], b[1]), __fmul2_rn(s.l0[0], make_float2(a[0], a[1])));
+    t[1] = __ffma2_rn(s.l1[1], make_float2(b[2], b[3]), __fmul2_rn(s.l0[1], make_float2(a[2], a[3])));
 }
 // vertical blend of the source at an output row with taps ty (refreshing the cached rows as needed)
-__device__ __forceinline__ void row_source_at(RowSource& s, const RowTap ty, float (&v)[4]) {
-    if (ty.i0 != s.cur0) {
-        if (ty.i0 == s.cur1) {
-#pragma unroll
-            for (int c = 0; c < 4; ++c) s.t0[c] = s.t1[c];
-        } else {
-            row_source_load(s, ty.i0, s.t0);
+template <bool STAGED>
+__device__ __forceinline__ void row_source_at(RowSource& s, const RowTap ty, float2 (&v)[2]) {
+    if (ty.i1 != s.cur1 || ty.i0 != s.cur0) {
+        if (ty.i0 != s.cur0) {
+            if (ty.i0 == s.cur1) {
+                s.t0[0] = s.t1[0];
+                s.t0[1] = s.t1[1];
+            } else {
+                row_source_load<STAGED>(s, ty.i0, s.t0);
+            }
+            s.cur0 = ty.i0;
         }
-        s.cur0 = ty.i0;
-    }
-    if (ty.i1 != s.cur1) {
-        if (ty.i1 == s.cur0) {
-#pragma unroll
-            for (int c = 0; c < 4; ++c) s.t1[c] = s.t0[c];
-        } else {
-            row_source_load(s, ty.i1, s.t1);
+        if (ty.i1 != s.cur1) {
+            if (ty.i1 == s.cur0) {
+                s.t1[0] = s.t0[0];
+                s.t1[1] = s.t0[1];
+            } else {
+                row_source_load<STAGED>(s, ty.i1, s.t1);
+            }
+            s.cur1 = ty.i1;
         }
-        s.cur1 = ty.i1;
     }
-#pragma unroll
-    for (int c = 0; c < 4; ++c) v[c] = fmaf(ty.l1, s.t1[c], ty.l0 * s.t0[c]);
+    const float2 l0 = make_float2(ty.l0, ty.l0), l1 = make_float2(ty.l1, ty.l1);
+    v[0] = __ffma2_rn(l1, s.t1[0], __fmul2_rn(l0, s.t0[0]));
+    v[1] = __ffma2_rn(l1, s.t1[1], __fmul2_rn(l0, s.t0[1]));
 }
 
 struct RowWalk {  // geometry of a block's walk over one map
@@ -242,25 +281,27 @@ struct RowWalk {  // geometry of a block's walk over one map
 };
 
 // fused float4 of output row `row` for this lane (hi4: the lane's four `hi` values or zeros)
+template <bool STAGED = false>
 __device__ __forceinline__ float4 fused_row4(const FuseSrc& f, RowSource& lo, RowSource& mid, const RowTap* s_rows, int row,
                                              float4 hi4) {
-    float vl[4], r[4];
-    row_source_at(lo, s_rows[row], vl);
-#pragma unroll
-    for (int c = 0; c < 4; ++c) r[c] = f.a_lo * vl[c];
+    float2 vl[2], r[2];
+    row_source_at<STAGED>(lo, s_rows[row], vl);
+    const float2 al = make_float2(f.a_lo, f.a_lo);
+    r[0] = __fmul2_rn(al, vl[0]);
+    r[1] = __fmul2_rn(al, vl[1]);
     if (f.mid) {
-        float vm[4];
-        row_source_at(mid, s_rows[f.H + row], vm);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) r[c] = fmaf(f.a_mid, vm[c], r[c]);
+        float2 vm[2];
+        row_source_at<STAGED>(mid, s_rows[f.H + row], vm);
+        const float2 am = make_float2(f.a_mid, f.a_mid);
+        r[0] = __ffma2_rn(am, vm[0], r[0]);
+        r[1] = __ffma2_rn(am, vm[1], r[1]);
     }
     if (f.hi) {
-        r[0] = fmaf(f.a_hi, hi4.x, r[0]);
-        r[1] = fmaf(f.a_hi, hi4.y, r[1]);
-        r[2] = fmaf(f.a_hi, hi4.z, r[2]);
-        r[3] = fmaf(f.a_hi, hi4.w, r[3]);
+        const float2 ah = make_float2(f.a_hi, f.a_hi);
+        r[0] = __ffma2_rn(ah, make_float2(hi4.x, hi4.y), r[0]);
+        r[1] = __ffma2_rn(ah, make_float2(hi4.z, hi4.w), r[1]);
     }
-    return make_float4(r[0], r[1], r[2], r[3]);
+    return make_float4(r[0].x, r[0].y, r[1].x, r[1].y);
 }
 
 template <bool DECODE>
@@ -395,6 +436,190 @@ static int rows_grid(int n_maps) {
     return n_maps < cap ? n_maps : cap;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Staged shape: the same row walk, but the low-resolution maps are copied into shared memory by the copy
+// engine (cp.async.bulk + mbarrier), double-buffered per block, so refreshing an interpolated row is a
+// handful of shared-memory loads instead of L2 round trips, and the next map's sources arrive while the
+// current one is processed.  No block barrier in the loop: a warp that finishes its strip of a map takes a
+// ticket from a shared counter; the LAST warp of a map merges the four partial argmaxes, scores PCK and
+// re-fills the buffer with the sources of the block's map after next (everybody has read it by then).
+// ---------------------------------------------------------------------------------------------
+struct StagedCtl {
+    unsigned long long full[2];  // mbarriers: sources of buffer b have landed
+    int done[2];                 // warps that have finished the map in buffer b
+    int nan[2];
+    ArgMax am[2][kRowWarps];
+};
+
+template <bool DECODE>
+__global__ void __launch_bounds__(32 * kRowWarps, 4)
+    fuse_staged_kernel(const FuseSrc f, const RowWalk g, int n_maps, float* __restrict__ out, const float* __restrict__ tgt_xy,
+                       int K, double thr, float* __restrict__ pred_xy, float* __restrict__ maxvals,
+                       int32_t* __restrict__ counts_out, double* __restrict__ acc_out, Workspace* __restrict__ ws) {
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    __shared__ StagedCtl ctl;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int HW = f.H * f.W;
+    const int lo_elems = f.hl * f.wl, mid_elems = f.mid ? f.hm * f.wm : 0;
+    const uint32_t lo_bytes = 4u * lo_elems, mid_bytes = 4u * mid_elems, buf_bytes = lo_bytes + mid_bytes;
+    float* s_src = reinterpret_cast<float*>(s_raw);                               // [2][lo | mid]
+    RowTap* s_rows = reinterpret_cast<RowTap*>(s_raw + 2 * static_cast<size_t>(buf_bytes));  // [H] lo taps, [H] mid taps
+    const int n_local = (n_maps - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+    const uint32_t full_u32 = smem_addr(&ctl.full[0]), src_u32 = smem_addr(s_src);
+    const uint64_t pol = l2_evict_first_policy();
+
+    auto request = [&](int j) {  // one thread: sources of the block's j-th map -> buffer j & 1
+        const int b = j & 1;
+        const size_t map = static_cast<size_t>(blockIdx.x) + static_cast<size_t>(j) * gridDim.x;
+        mbar_arrive_expect_tx(full_u32 + 8 * b, buf_bytes);
+        bulk_load(src_u32 + b * buf_bytes, f.lo + map * lo_elems, lo_bytes, full_u32 + 8 * b, pol);
+        if (f.mid) bulk_load(src_u32 + b * buf_bytes + lo_bytes, f.mid + map * mid_elems, mid_bytes, full_u32 + 8 * b, pol);
+    };
+    if (threadIdx.x == 0) {
+        mbar_init(full_u32, 1);
+        mbar_init(full_u32 + 8, 1);
+        mbar_init_fence();
+        ctl.done[0] = ctl.done[1] = 0;
+        ctl.nan[0] = ctl.nan[1] = 0;
+        if (n_local > 0) request(0);
+        if (n_local > 1) request(1);
+    }
+    for (int r = threadIdx.x; r < f.H; r += blockDim.x) {
+        const Tap tl = make_tap(r, f.sy_lo, f.hl, f.H);
+        s_rows[r] = RowTap{tl.i0, tl.i1, tl.l0, tl.l1};
+        if (f.mid) {
+            const Tap tm = make_tap(r, f.sy_mid, f.hm, f.H);
+            s_rows[f.H + r] = RowTap{tm.i0, tm.i1, tm.l0, tm.l1};
+        }
+    }
+    const int x0 = (lane % g.cpr) * 4, ro = lane / g.cpr;
+    RowSource lo, mid;
+    row_source_init(lo, x0, f.sx_lo, f.wl, f.W);
+    row_source_init(mid, x0, f.mid ? f.sx_mid : 1.0f, f.mid ? f.wm : f.W, f.W);
+    const int row_begin = warp * g.strip + ro, row_end = min(f.H, (warp + 1) * g.strip);
+    __syncthreads();  // the only block barrier: control block and tap table are set up
+
+    for (int j = 0; j < n_local; ++j) {
+        const int b = j & 1;
+        const int map = static_cast<int>(blockIdx.x) + j * static_cast<int>(gridDim.x);
+        lo.base_s = src_u32 + b * buf_bytes;
+        mid.base_s = lo.base_s + lo_bytes;
+        lo.cur0 = lo.cur1 = mid.cur0 = mid.cur1 = -1;
+        const float* hi = f.hi ? f.hi + static_cast<size_t>(map) * HW + x0 : nullptr;
+        float* o = DECODE ? nullptr : out + static_cast<size_t>(map) * HW + x0;
+        float best = -INFINITY, witness = 0.0f;
+        int best_row = row_begin;
+        float4 h[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {  // the first rows of the HBM stream are requested before the sources are awaited
+            const int r = row_begin + u * g.rps;
+            h[u] = (hi && r < row_end) ? ldg_stream4(reinterpret_cast<const float4*>(hi + r * f.W)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        mbar_wait(full_u32 + 8 * b, static_cast<uint32_t>(j >> 1) & 1u);
+        for (int row = row_begin; row < row_end; row += 4 * g.rps) {
+            float4 hn[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {  // next step's rows in flight while this step is blended
+                const int r = row + (4 + u) * g.rps;
+                hn[u] = (hi && r < row_end) ? ldg_stream4(reinterpret_cast<const float4*>(hi + r * f.W)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int r = row + u * g.rps;
+                if (r < row_end) {
+                    const float4 v = fused_row4<true>(f, lo, mid, s_rows, r, h[u]);
+                    if (DECODE) {
+                        const float m4 = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+                        best_row = (m4 > best) ? r : best_row;  // strict: the earlier row keeps ties
+                        best = fmaxf(best, m4);
+                        witness += (v.x + v.y) + (v.z + v.w);    // NaN / inf-inf witness
+                    } else {
+                        stg_stream4(reinterpret_cast<float4*>(o + r * f.W), v);
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) h[u] = hn[u];
+        }
+        ArgMax am = am_init();
+        bool bad = false;
+        if (DECODE) {
+            if (row_begin < row_end) {  // the lane's first maximum: recompute its row (same code, same bits)
+                const float4 hb = hi ? ldg_stream4(reinterpret_cast<const float4*>(hi + best_row * f.W)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 v = fused_row4<true>(f, lo, mid, s_rows, best_row, hb);
+                const int comp = (v.x == best) ? 0 : ((v.y == best) ? 1 : ((v.z == best) ? 2 : 3));
+                am.v = best;
+                am.i = best_row * f.W + x0 + comp;
+            }
+            am = warp_argmax_rows(am, lane);
+            bad = __any_sync(0xffffffffu, witness != witness);
+        }
+        // ---- ticket: the last warp of this map closes it and re-fills the buffer ------------------------------
+        __syncwarp();
+        int last = 0;
+        if (lane == 0) {
+            if (DECODE) {
+                ctl.am[b][warp] = am;
+                if (bad) atomicOr(&ctl.nan[b], 1);
+            }
+            __threadfence_block();
+            last = (atomicAdd(&ctl.done[b], 1) == kRowWarps - 1) ? 1 : 0;
+            if (last) __threadfence_block();
+        }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last) {
+            if (DECODE) {
+                ArgMax a = ctl.am[b][0];
+#pragma unroll
+                for (int w = 1; w < kRowWarps; ++w) a = am_merge(a, ctl.am[b][w]);
+                if (*reinterpret_cast<volatile int*>(&ctl.nan[b])) {
+                    // a NaN (or +inf with -inf) somewhere in the fused map: this warp rescans the whole map
+                    // element-wise with numpy's exact rules (the sources are still staged)
+                    ArgMax sx = am_init();
+                    lo.cur0 = lo.cur1 = mid.cur0 = mid.cur1 = -1;
+                    for (int r = ro; r < f.H; r += g.rps) {
+                        const float4 hb = hi ? ldg_stream4(reinterpret_cast<const float4*>(hi + r * f.W)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        am_scan4<true>(sx, fused_row4<true>(f, lo, mid, s_rows, r, hb), r * f.W + x0);
+                    }
+                    a = warp_argmax_rows(sx, lane);
+                }
+                if (lane == 0) {
+                    float px, py;
+                    decode_xy(a, f.W, px, py);
+                    pred_xy[2 * map + 0] = px;
+                    pred_xy[2 * map + 1] = py;
+                    if (maxvals) maxvals[map] = a.v;
+                    int valid, hit;
+                    pck_one(px, py, tgt_xy[2 * map], tgt_xy[2 * map + 1], f.H, f.W, thr, valid, hit);
+                    const int k = map % K;
+                    if (valid) atomicAdd(&ws->counts[K + k], 1);
+                    if (hit) atomicAdd(&ws->counts[k], 1);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) {
+                ctl.done[b] = 0;
+                ctl.nan[b] = 0;
+                __threadfence_block();
+                if (j + 2 < n_local) request(j + 2);  // every warp has finished reading buffer b
+            }
+        }
+    }
+    if (DECODE) {
+        if (last_block_arrives(&ws->counter, gridDim.x)) pck_publish(ws, K, counts_out, acc_out);
+    }
+}
+
+// staged kernel applicable?  rows geometry + bulk-copy alignment + both buffers and the tap table fit
+static bool staged_geometry(const FuseSrc& f, const float* out, RowWalk& g, size_t& smem) {
+    if (!rows_geometry(f, out, g)) return false;
+    const size_t lo_b = 4ull * f.hl * f.wl, mid_b = f.mid ? 4ull * f.hm * f.wm : 0;
+    if (lo_b % 16 != 0 || mid_b % 16 != 0 || !aligned16(f.lo) || (f.mid && !aligned16(f.mid))) return false;
+    smem = 2 * (lo_b + mid_b) + sizeof(RowTap) * 2 * static_cast<size_t>(f.H);
+    return smem <= 48 * 1024;  // 4 blocks per SM
+}
+
 struct FuseDecodeLaunch {
     FuseSrc f;
     const float* tgt_xy;
@@ -445,6 +670,12 @@ extern "C" HP_API int hp_fuse_multiscale(const float* lo, int hl, int wl, float 
     if (n_maps == 0) return HP_OK;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     RowWalk g;
+    size_t staged_smem = 0;
+    if (staged_geometry(f, out, g, staged_smem)) {
+        fuse_staged_kernel<false><<<rows_grid(n_maps), 32 * kRowWarps, staged_smem, s>>>(f, g, n_maps, out, nullptr, 0, 0.0, nullptr,
+                                                                                       nullptr, nullptr, nullptr, nullptr);
+        return launch_status("hp_fuse_multiscale");
+    }
     if (rows_geometry(f, out, g)) {
         const size_t smem = sizeof(RowTap) * 2 * static_cast<size_t>(H);
         fuse_rows_kernel<false><<<rows_grid(n_maps), 32 * kRowWarps, smem, s>>>(f, g, n_maps, out, nullptr, 0, 0.0, nullptr,
@@ -470,6 +701,12 @@ extern "C" HP_API int hp_fuse_decode_pck(const float* lo, int hl, int wl, float 
     HP_REQUIRE(tgt_xy && pred_xy && acc_out && workspace, HP_ERR_NULL, "hp_fuse_decode_pck: null pointer");
     HP_REQUIRE(B > 0 && K > 0 && K <= HP_MAX_K, HP_ERR_SHAPE, "hp_fuse_decode_pck: bad B=%d K=%d", B, K);
     RowWalk g;
+    size_t staged_smem = 0;
+    if (staged_geometry(f, nullptr, g, staged_smem)) {
+        fuse_staged_kernel<true><<<rows_grid(B * K), 32 * kRowWarps, staged_smem, static_cast<cudaStream_t>(stream)>>>(
+            f, g, B * K, nullptr, tgt_xy, K, thr, pred_xy, maxvals, counts, acc_out, static_cast<Workspace*>(workspace));
+        return launch_status("hp_fuse_decode_pck");
+    }
     if (rows_geometry(f, nullptr, g)) {
         const size_t smem = sizeof(RowTap) * 2 * static_cast<size_t>(H);
         fuse_rows_kernel<true><<<rows_grid(B * K), 32 * kRowWarps, smem, static_cast<cudaStream_t>(stream)>>>(

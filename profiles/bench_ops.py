@@ -7,7 +7,7 @@ the BASELINE.json parity configs C2..C5 measured per GPU, for DESIGN.md / BASELI
 
 Timing: CUDA events around `reps` back-to-back calls on rotating input sets (>= 3 sets, each larger than or
 rotating past the 126 MB L2), after 5 warm-up calls.  bytes = algorithmic bytes per call as listed per row."""
-import argparse, importlib, json, os, sys
+import argparse, importlib, json, os, sys, time
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -33,15 +33,19 @@ def timed(name, fn, n_sets, bytes_per_call, maps_per_call, note=""):
         fn(i % n_sets)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
     e0.record()
     for i in range(args.reps):
         fn(i % n_sets)
     e1.record()
+    host_us = 1e6 * (time.perf_counter() - t0) / args.reps   # host time to ISSUE a call (no synchronisation)
     torch.cuda.synchronize()
     us = 1e3 * e0.elapsed_time(e1) / args.reps
+    if host_us > 0.85 * us:
+        note = (note + "; " if note else "") + f"HOST-BOUND: issuing a call takes {host_us:.0f} us"
     gbs = bytes_per_call / (us * 1e-6) / 1e9
     rows.append({"op": name, "us_per_call": us, "GBps": gbs, "frac_of_measured_hbm": gbs / PEAK,
-                 "heatmaps_per_s": maps_per_call / (us * 1e-6), "algorithmic_bytes": bytes_per_call, "note": note})
+                 "heatmaps_per_s": maps_per_call / (us * 1e-6), "algorithmic_bytes": bytes_per_call, "host_issue_us": host_us, "note": note})
     print(f"{name:58s} {us:9.1f} us  {gbs:8.1f} GB/s  {gbs / PEAK:5.2f} of HBM  {maps_per_call / (us * 1e-6) / 1e6:8.1f} M maps/s  {note}")
 
 
