@@ -155,6 +155,26 @@ __device__ __forceinline__ void am_scan4(ArgMax& a, float4 x, int idx0) {
 // ---------------------------------------------------------------------------------------------
 constexpr float kLog2e = 1.4426950408889634f;
 
+// warp-wide float maximum in one instruction (sm_100a; SASS CREDUX.MAX.F32); NaN inputs are ignored
+__device__ __forceinline__ float warp_max_f32(float x) {
+    float r;
+    asm("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// single MUFU instructions (SASS MUFU.EX2 / MUFU.LG2), ~2^-22 relative error
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+constexpr float kLn2 = 0.6931471805599453f;
+
 __device__ __forceinline__ float exp_diff(float a, float b) {  // exp(a - b), 0 when a == -inf
     return (a == -INFINITY) ? 0.0f : exp2f((a - b) * kLog2e);
 }

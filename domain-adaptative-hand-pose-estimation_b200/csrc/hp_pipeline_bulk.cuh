@@ -36,12 +36,6 @@ struct BulkArgs {
                                 // {globaltimer, clock64} at entry and exit, per warp and map 4 clock64 stamps
 };
 
-__device__ __forceinline__ float warp_max_f32(float x) {
-    float r;
-    asm("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(x));
-    return r;
-}
-
 // trace buffer layout (uint64): block b at b * kTraceBlockWords: [0] globaltimer in, [1] clock in, [2] globaltimer out,
 // [3] clock out, [4] SM id, [5] clock when the block's last warp left the map loop, [6..7] spare, then per warp w
 // (< 16) and map jj (< kTraceMaps): 4 stamps {wait begins, data landed, refill issued, map closed}

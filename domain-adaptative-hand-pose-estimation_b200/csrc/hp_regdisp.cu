@@ -15,43 +15,16 @@
 //   x5    g = clip(1 - 10 gt);               [fused f given]  g = clip((g + f) - 100 gt);  g / max(g)
 //   x6    g = clip(clip(sum_j gt_j) - 10 gt); [fused f given] g = clip((g + f) - 100 gt);  g / max(g)
 // Roofline: HBM.  Bytes per map: y (H*W*4) + y_adv (oh*ow*4) [+ fused oh*ow*4]; backward adds a write.
+#include <cstdlib>
+
 #include "hp_common.cuh"
 #include "hp_internal.cuh"
+#include "hp_regdisp_staged.cuh"
 
 namespace hp {
 
 constexpr int kRDThreads = 256;
 constexpr int kRDNV = 4;
-
-enum RDTask { RD_FWD = 0, RD_BWD = 1, RD_MATERIALIZE = 2 };
-
-struct RDArgs {
-    const float* y_adv;
-    const float* fused;
-    const float* weight;
-    int variant, mode;
-    float eps;
-    int B, K, oh, ow, tmp;
-    const float* tab;
-    const int32_t* centres;
-    int splits;
-    FastDiv wdiv;
-    // forward
-    float* per_map;
-    float* per_sample;
-    float* mean;
-    float* stats;  // [B*K,3] lse, S, M
-    Workspace* ws;
-    // backward
-    const float* grad_out;
-    int grad_kind;
-    float* grad_in;
-    // materialise
-    float* gt;
-    float* gf;
-};
-
-__device__ __forceinline__ float clip01(float x) { return (x != x) ? x : fminf(fmaxf(x, 0.0f), 1.0f); }
 
 // un-normalised ground-false value of joint k at pixel (x, y) / flat idx
 __device__ __forceinline__ float ground_false_value(int variant, bool has_fused, int k, int K, int x, int y, int idx,
@@ -307,6 +280,12 @@ static int launch_regdisp(RDArgs a, bool vec, cudaStream_t stream, const char* w
     return launch_status(who);
 }
 
+// HP_RD_SHAPE=g forces the guarded generic kernel (A/B comparisons; the staged kernel is the default)
+static bool generic_forced() {
+    const char* e = getenv("HP_RD_SHAPE");
+    return e != nullptr && e[0] == 'g';
+}
+
 static int check_rd(const char* who, int variant, int mode, int B, int K, int oh, int ow, int tmp) {
     HP_REQUIRE(variant >= HP_RD_BASE && variant <= HP_RD_X6, HP_ERR_ARG, "%s: variant %d", who, variant);
     HP_REQUIRE(mode == HP_MODE_MIN || mode == HP_MODE_MAX, HP_ERR_ARG, "%s: mode %d", who, mode);
@@ -337,6 +316,10 @@ extern "C" HP_API int hp_regdisp_fwd(const float* y, const float* y_adv, const f
     a.per_map = per_map; a.per_sample = per_sample; a.mean = mean; a.stats = stats;
     a.ws = static_cast<Workspace*>(workspace);
     const bool vec = (ow % 4 == 0) && aligned16(y_adv) && (!fused || aligned16(fused));
+    if (vec && !generic_forced()) {
+        const int rc = launch_regdisp_staged<RD_FWD>(a, s, "hp_regdisp_fwd");
+        if (rc != 1) return rc;
+    }
     return launch_regdisp<RD_FWD>(a, vec, s, "hp_regdisp_fwd");
 }
 
@@ -353,6 +336,10 @@ extern "C" HP_API int hp_regdisp_bwd(const float* y_adv, const float* fused, con
     a.B = B; a.K = K; a.oh = oh; a.ow = ow; a.tmp = tmp; a.tab = tab; a.centres = centres; a.stats = const_cast<float*>(stats);
     a.grad_out = grad_out; a.grad_kind = grad_kind; a.grad_in = grad_in;
     const bool vec = (ow % 4 == 0) && aligned16(y_adv) && aligned16(grad_in) && (!fused || aligned16(fused));
+    if (vec && !generic_forced()) {
+        const int rc = launch_regdisp_staged<RD_BWD>(a, static_cast<cudaStream_t>(stream), "hp_regdisp_bwd");
+        if (rc != 1) return rc;
+    }
     return launch_regdisp<RD_BWD>(a, vec, static_cast<cudaStream_t>(stream), "hp_regdisp_bwd");
 }
 

@@ -316,6 +316,56 @@ def test_three_scale_fuse_decode_pck_matches_unfused_and_oracle():
     assert np.array_equal(c[:K], hits) and np.array_equal(c[K:], valid)
 
 
+@pytest.mark.parametrize("variant,mode,fused", [
+    ("base", "min", False), ("base", "max", False), ("x1", "min", False), ("x1", "max", False),
+    ("x5", "min", False), ("x5", "max", False), ("x5", "max", True),
+    ("x6", "min", False), ("x6", "max", False), ("x6", "max", True)])
+def test_disparity_long_map_ranges(variant, mode, fused, monkeypatch):
+    """The staged disparity kernels give each block a contiguous range of maps.  B=2 cases keep every range to
+    one map; here 17 samples run on the full grid AND on 5 blocks (ranges of ~71 maps across 4-5 samples:
+    sample hand-over, ring wrap-around) and must agree bit-for-bit with each other, to 1e-5 with the guarded
+    generic kernel (HP_RD_SHAPE=g) and with the live oracle, for the loss ('none' reduction) and the gradient."""
+    B = 17
+    d = hp.synth.make_host_batch(911, B, 21, 64, 64)
+    adv64 = hp.synth.make_host_batch(912, B, 21, 64, 64)["pred"]
+    adv32, adv16 = hp.synth.make_lowres_heads(913, adv64, (32, 16))
+    rs = np.random.RandomState(914)
+    w_h = (rs.uniform(size=(B, 21, 1)) < 0.85).astype(np.float32)
+    side = {"base": 64, "x1": 16, "x5": 32, "x6": 64}[variant]
+    adv_h = {64: adv64, 32: adv32, 16: adv16}[side]
+    f_h = np.clip(hp.synth.make_host_batch(915, B, 21, side, side)["pred"], -0.2, 1.2).astype(np.float32) if fused else None
+    go_h = rs.uniform(0.5, 1.5, size=(B,)).astype(np.float32)
+
+    def run(ns, device):
+        kl = ns.JointsKLLoss(reduction="none", epsilon=1e-7)
+        rd = {"base": lambda: ns.RegressionDisparity(ns.PseudoLabelGenerator(21, 64, 64), kl),
+              "x1": lambda: ns.RegressionDisparityx1(ns.PseudoLabelGenerator01(21), kl),
+              "x5": lambda: ns.RegressionDisparityx5(ns.PseudoLabelGenerator03(21), kl),
+              "x6": lambda: ns.RegressionDisparityx6(ns.PseudoLabelGenerator(21, 64, 64), kl)}[variant]()
+        y = torch.from_numpy(d["pred"]).to(device)
+        adv = torch.from_numpy(adv_h).to(device).requires_grad_(True)
+        w = torch.from_numpy(w_h).to(device)
+        f = None if f_h is None else torch.from_numpy(f_h).to(device)
+        l = rd(y, adv, w, mode) if variant in ("base", "x1") else rd(y, adv, f, w, mode)
+        l.backward(torch.from_numpy(go_h).to(device))
+        return l.detach().cpu().numpy(), adv.grad.cpu().numpy()
+
+    ns = _ns()
+    l_full, g_full = run(ns, "cuda")
+    monkeypatch.setenv("HP_RD_GRID", "5")
+    l_few, g_few = run(ns, "cuda")
+    monkeypatch.delenv("HP_RD_GRID")
+    monkeypatch.setenv("HP_RD_SHAPE", "g")
+    l_gen, g_gen = run(ns, "cuda")
+    monkeypatch.delenv("HP_RD_SHAPE")
+    l_ref, g_ref = run(api.namespace(), "cpu")
+    assert np.array_equal(l_full, l_few) and np.array_equal(g_full, g_few), "results depend on the grid"
+    scale = 1e-5 * float(np.abs(g_ref).max())
+    for l_o, g_o, what in ((l_gen, g_gen, "generic kernel"), (l_ref, g_ref, "oracle")):
+        np.testing.assert_allclose(l_full, l_o, rtol=1e-5, err_msg=what)
+        np.testing.assert_allclose(g_full, g_o, rtol=1e-5, atol=scale, err_msg=what)
+
+
 def test_foreign_criterion_gets_materialised_maps():
     I = cases.disparity_inputs()
     y, adv, w = (torch.from_numpy(I[k]).cuda() for k in ("y", "adv64", "w"))
