@@ -435,6 +435,62 @@ __device__ __forceinline__ bool last_block_arrives(unsigned int* counter, unsign
     return s_last;
 }
 
+// ---- reductions over per-map values written by OTHER blocks (read after the last-block ticket) -----------------
+// L2 loads (ld.global.cg; the writers fenced before their tickets), issued eight at a time so that their
+// latencies overlap: a dependent chain of ~40 single volatile loads per thread costs tens of microseconds.
+// Summation order is fixed (ascending index per thread): deterministic.
+__device__ __forceinline__ double strided_sum_f64(const float* x, int n, int first, int stride) {
+    double acc = 0.0;
+    for (int i0 = first; i0 < n; i0 += 8 * stride) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = (i0 + u * stride < n) ? __ldcg(x + i0 + u * stride) : 0.0f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (i0 + u * stride < n) acc += static_cast<double>(v[u]);
+    }
+    return acc;
+}
+// per_sample[b] = mean over the K joints of per_map[b*K + k]   (loss.py:158, 'none' reduction of the KL loss)
+__device__ __forceinline__ void per_sample_means(const float* per_map, int B, int K, float* per_sample, int t, int nt) {
+    for (int b = t; b < B; b += nt)
+        per_sample[b] = static_cast<float>(strided_sum_f64(per_map + static_cast<size_t>(b) * K, K, 0, 1) / static_cast<double>(K));
+}
+
+// Exact, order-free accumulation of per-map float losses as 64-bit integers: acc[0] += round(v * 2^40), acc[4] +=
+// round(residual * 2^23) (so values down to 2^-63 still count exactly), acc[1..3] count NaN / +inf / -inf.
+// Integer sums make the 'mean' independent of the grid and of the schedule, and the last block reads FIVE numbers
+// instead of walking every per-map value.
+constexpr float kFxAccLimit = 2097152.0f;  // |per-map loss| >= 2^21 counts as infinite
+constexpr int kFxAccWords = 5;
+__device__ __forceinline__ void fx_acc_add(unsigned long long* acc, float v) {
+    if (fabsf(v) < kFxAccLimit) {
+        const double d = static_cast<double>(v) * 1099511627776.0;  // exact
+        const long long hi = __double2ll_rn(d);
+        const long long lo = __double2ll_rn((d - static_cast<double>(hi)) * 8388608.0);
+        atomicAdd(&acc[0], static_cast<unsigned long long>(hi));
+        if (lo != 0) atomicAdd(&acc[4], static_cast<unsigned long long>(lo));
+    } else {
+        atomicAdd(&acc[(v != v) ? 1 : (v > 0.0f ? 2 : 3)], 1ull);
+    }
+}
+__device__ __forceinline__ float fx_mean(const long long (&v)[kFxAccWords], int n) {
+    if (v[1] != 0 || (v[2] != 0 && v[3] != 0)) return __int_as_float(0x7fc00000);
+    if (v[2] != 0) return INFINITY;
+    if (v[3] != 0) return -INFINITY;
+    const double total = ldexp(static_cast<double>(v[0]), -40) + ldexp(static_cast<double>(v[4]), -63);
+    return static_cast<float>(total / static_cast<double>(n));
+}
+// last block, one thread: read the workspace accumulators, restore their zero state, return the mean
+__device__ __forceinline__ float fx_mean_from_workspace(unsigned long long* acc, int n) {
+    long long v[kFxAccWords];
+    for (int i = 0; i < kFxAccWords; ++i) {
+        v[i] = static_cast<long long>(*reinterpret_cast<volatile unsigned long long*>(&acc[i]));
+        acc[i] = 0ull;
+    }
+    return fx_mean(v, n);
+}
+
 // deterministic block-wide float64 sum of a float array (fixed shape tree, independent of timing)
 template <int NT>
 __device__ __forceinline__ double block_sum_f32_as_f64(const float* __restrict__ x, int n, double* s_buf) {

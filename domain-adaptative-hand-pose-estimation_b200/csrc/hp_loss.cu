@@ -23,7 +23,6 @@ __global__ void __launch_bounds__(TPM* MPB)
                     float* __restrict__ mean, float* __restrict__ stats, Workspace* __restrict__ ws) {
     constexpr int NS = 3;
     __shared__ Stats<NS> scratch[TPM > 32 ? TPM / 32 + 1 : 1];
-    __shared__ double s_red[TPM * MPB];
     const int g = threadIdx.x / TPM, t = threadIdx.x % TPM;
     const int map = blockIdx.x * MPB + g;
     if (map < n_maps) {
@@ -59,41 +58,28 @@ __global__ void __launch_bounds__(TPM* MPB)
             if (IS_KL) {
                 float lse;
                 const double L = kl_finish(st.m, st.s, st.sum[0], st.sum[1], st.sum[2], lse);
-                per_map[map] = static_cast<float>(L * static_cast<double>(w));
+                const float Lw = static_cast<float>(L * static_cast<double>(w));
+                per_map[map] = Lw;
+                if (mean) fx_acc_add(ws->acc, Lw);
                 if (stats) {
                     stats[2 * map + 0] = lse;
                     stats[2 * map + 1] = st.sum[0];
                 }
             } else {
                 // mean over HW of 0.5*w*(p-t)^2  (loss.py:59-65)
-                per_map[map] = static_cast<float>(0.5 * static_cast<double>(w) * static_cast<double>(st.sum[0]) /
-                                                  static_cast<double>(HW));
+                const float Lw = static_cast<float>(0.5 * static_cast<double>(w) * static_cast<double>(st.sum[0]) /
+                                                   static_cast<double>(HW));
+                per_map[map] = Lw;
+                if (mean) fx_acc_add(ws->acc, Lw);
             }
         }
     }
     if (mean == nullptr && per_sample == nullptr) return;
     if (last_block_arrives(&ws->counter, gridDim.x)) {
-        // fixed-order float64 reductions over the per-map values: deterministic
-        const volatile float* pmv = per_map;
-        if (per_sample) {  // KL 'none': mean over joints (loss.py:158)
-            const int B = n_maps / K;
-            for (int b = threadIdx.x; b < B; b += TPM * MPB) {
-                double a = 0.0;
-                for (int k = 0; k < K; ++k) a += static_cast<double>(pmv[b * K + k]);
-                per_sample[b] = static_cast<float>(a / static_cast<double>(K));
-            }
-        }
-        if (mean) {
-            double acc = 0.0;
-            for (int i = threadIdx.x; i < n_maps; i += TPM * MPB) acc += static_cast<double>(pmv[i]);
-            s_red[threadIdx.x] = acc;
-            __syncthreads();
-            for (int o = (TPM * MPB) / 2; o > 0; o >>= 1) {
-                if (threadIdx.x < o) s_red[threadIdx.x] += s_red[threadIdx.x + o];
-                __syncthreads();
-            }
+        if (per_sample) per_sample_means(per_map, n_maps / K, K, per_sample, threadIdx.x, TPM * MPB);  // KL 'none'
+        if (mean && threadIdx.x == 0) {
             // MSE 'mean' = mean over all elements = mean over maps of the per-map means (equal HW)
-            if (threadIdx.x == 0) *mean = static_cast<float>(s_red[0] / static_cast<double>(n_maps));
+            *mean = fx_mean_from_workspace(ws->acc, n_maps);
         }
         if (threadIdx.x == 0) ws->counter = 0;
     }

@@ -225,17 +225,9 @@ __global__ void __launch_bounds__(kRDThreads) regdisp_kernel(const RDArgs a) {
         if (a.mean == nullptr && a.per_sample == nullptr) return;
         if (last_block_arrives(&a.ws->counter, gridDim.x)) {
             const int n_maps = a.B * a.K;
-            const volatile float* pmv = a.per_map;
-            if (a.per_sample) {
-                for (int s = t; s < a.B; s += kRDThreads) {
-                    double acc = 0.0;
-                    for (int k = 0; k < a.K; ++k) acc += static_cast<double>(pmv[s * a.K + k]);
-                    a.per_sample[s] = static_cast<float>(acc / static_cast<double>(a.K));
-                }
-            }
+            if (a.per_sample) per_sample_means(a.per_map, a.B, a.K, a.per_sample, t, kRDThreads);
             if (a.mean) {
-                double acc = 0.0;
-                for (int i = t; i < n_maps; i += kRDThreads) acc += static_cast<double>(pmv[i]);
+                const double acc = strided_sum_f64(a.per_map, n_maps, t, kRDThreads);
                 s_red[t] = acc;
                 __syncthreads();
                 for (int o = kRDThreads / 2; o > 0; o >>= 1) {

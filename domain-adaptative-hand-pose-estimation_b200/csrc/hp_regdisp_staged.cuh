@@ -56,7 +56,12 @@ struct RDArgs {
     float* gf;
 };
 
-__device__ __forceinline__ float clip01(float x) { return (x != x) ? x : fminf(fmaxf(x, 0.0f), 1.0f); }
+// clamp to [0, 1], NaN propagates (torch.clamp); two FMNMX.NAN
+__device__ __forceinline__ float clip01(float x) {
+    float y;
+    asm("max.NaN.f32 %0, %1, 0f00000000;\n\tmin.NaN.f32 %0, %0, 0f3F800000;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 // un-normalised ground-false value of joint k at pixel (x, y).  `all` = clip01(sum over
 // ALL joints of their Gaussians at this pixel) (base / x6 only), gt = joint k's own Gaussian, f = fused map.
@@ -77,345 +82,381 @@ __device__ __forceinline__ float ground_false_pixel(int variant, bool use_fused,
 }
 
 constexpr int kRDSMaxStages = 8;
+constexpr int kRDSBatch = 16;  // maps per closure batch
+constexpr int kRDSSlots = 4;   // samples whose per-joint inputs are resident in shared memory
 struct RDSMeta {
     float a, b, c, d;  // forward: {weight}; backward: {coef, -lse*log2e, 1/S, M}
 };
 template <int NT>
 struct RDSShared {
-    uint64_t bars[kRDSMaxStages];
-    Centre c[2][HP_MAX_K];
-    RDSMeta meta[2][HP_MAX_K];
-    float p1[2][NT / 32][2];  // per-warp {max p, max g} of the map in flight
-    float p2[2][NT / 32][6];  // per-warp {sum exp, sum u, sum u p, sum u lg2 u, sum p over the closed-form pixels}
+    uint64_t full[kRDSMaxStages];   // copy landed (armed with the byte count by the producer)
+    uint64_t empty[kRDSMaxStages];  // every consumer warp has read the stage out
+    Centre c[kRDSSlots][HP_MAX_K];
+    RDSMeta meta[kRDSSlots][HP_MAX_K];
+    float mx[2][NT / 32];                       // normalised recipes: per-warp max of the un-normalised target
+    float cl[2][kRDSBatch][NT / 32][8];         // per map and warp {max p, sum exp, sum u, sum u p, sum u lg2 u, sum p (bg)}
+    float4 clm[2][kRDSBatch];                   // per map {centre x, centre y (bits), weight, M}
+    unsigned long long acc[kFxAccWords];        // block sums of the per-map losses (fx_acc_add)
 };
+
+
 
 __device__ __forceinline__ float max4(float4 v) { return fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)); }
 __device__ __forceinline__ float4 clip01_4(float4 v) { return make_float4(clip01(v.x), clip01(v.y), clip01(v.z), clip01(v.w)); }
 __device__ __forceinline__ float4 add4(float4 a, float4 b) {
     return make_float4(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z), __fadd_rn(a.w, b.w));
 }
-__device__ __forceinline__ float warp_sum_f32(float x) {
+// Sum 8 per-lane values over the warp in 9 shuffles (transpose-reduce): every lane of the group of four with
+// index i = lane >> 2 returns the total of v[4*bit4(lane) + 2*bit3(lane) + bit2(lane)], i.e. v[rds_sum_index(lane)].
+__device__ __forceinline__ float warp_sum8_scattered(const float (&v)[8], int lane) {
+    const bool h16 = (lane & 16) != 0, h8 = (lane & 8) != 0, h4 = (lane & 4) != 0;
+    float w[4], x[2];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-    return x;
+    for (int i = 0; i < 4; ++i) w[i] = (h16 ? v[i + 4] : v[i]) + __shfl_xor_sync(0xffffffffu, h16 ? v[i] : v[i + 4], 16);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) x[i] = (h8 ? w[i + 2] : w[i]) + __shfl_xor_sync(0xffffffffu, h8 ? w[i] : w[i + 2], 8);
+    float y = (h4 ? x[1] : x[0]) + __shfl_xor_sync(0xffffffffu, h4 ? x[0] : x[1], 4);
+    y += __shfl_xor_sync(0xffffffffu, y, 2);
+    y += __shfl_xor_sync(0xffffffffu, y, 1);
+    return y;
 }
+__device__ __forceinline__ int rds_sum_index(int lane) { return ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1); }
 // u / M of the normalised recipes: exact division (bit-equal to the materialised maps), skipped when M == 1
 __device__ __forceinline__ float rds_norm(float g, float M, bool divide) { return divide ? __fdiv_rn(g, M) : g; }
 
-// NT threads per block, NV float4 per thread and map (NT * NV * 4 >= oh * ow), 512 / NT blocks per SM.
-template <int NT, int NV, int TASK>
-__global__ void __launch_bounds__(NT, 512 / NT) regdisp_staged_kernel(const RDArgs a, const int kst) {
+// NT consumer threads + one producer warp per block, NV float4 per consumer thread and map (NT * NV * 4 == oh * ow),
+// 512 / NT blocks per SM.  DENSE: the target outside the own patch depends on the pixel (x6 / base 'max', fused map);
+// otherwise it is a constant there ('min': 0; x1 / x5 'max': 1) and the sums over those pixels are closed forms.
+template <int NT, int NV, int TASK, bool DENSE, bool FUSED>
+__global__ void __launch_bounds__(NT + 32, 512 / NT) regdisp_staged_kernel(const RDArgs a, const int kst) {
     extern __shared__ __align__(128) unsigned char s_rds[];
     __shared__ RDSShared<NT> sh;
-    __shared__ double s_red[TASK == RD_FWD ? NT : 1];
     constexpr int NW = NT / 32;
+    constexpr int n4 = NT * NV, ohw = 4 * n4;
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-    const int ohw = a.oh * a.ow, n4 = ohw >> 2, K = a.K, tmp = a.tmp;
+    const int K = a.K, tmp = a.tmp;
     const bool want_gf = a.mode == HP_MODE_MAX;
-    const bool use_fused = want_gf && a.fused != nullptr && a.variant != HP_RD_X1;
-    const bool needs_all = want_gf && (a.variant == HP_RD_BASE || a.variant == HP_RD_X6);
-    const bool normalise = want_gf && (a.variant == HP_RD_X5 || a.variant == HP_RD_X6);
-    const bool dense = needs_all || use_fused;  // the target outside the own patch depends on the pixel
-    const float bg = want_gf ? 1.0f : 0.0f;     // ... or is this constant (before normalisation and epsilon)
-    const int nbuf = use_fused ? 2 : 1;
-    const uint32_t stage_bytes = static_cast<uint32_t>(nbuf) * static_cast<uint32_t>(ohw) * 4u;
+    const bool needs_all = DENSE && (a.variant == HP_RD_BASE || a.variant == HP_RD_X6);
+    const bool normalise = DENSE && (a.variant == HP_RD_X5 || a.variant == HP_RD_X6);  // sparse recipes: M == 1 (host)
+    const float bg = want_gf ? 1.0f : 0.0f;  // the constant target outside the patch of the sparse recipes
+    constexpr uint32_t stage_bytes = (FUSED ? 2u : 1u) * static_cast<uint32_t>(ohw) * 4u;
     const int ntab = 2 * tmp * tmp + 1;
     float* s_tab = reinterpret_cast<float*>(s_rds + static_cast<size_t>(kst) * stage_bytes);
-    const uint32_t stage_u32 = smem_addr(s_rds), bar_u32 = smem_addr(sh.bars);
+    const uint32_t stage_u32 = smem_addr(s_rds), full_u32 = smem_addr(sh.full), empty_u32 = smem_addr(sh.empty);
 
     // this block's maps: [m0, m1)
     const int n_maps = a.B * K;
     const int m0 = static_cast<int>((static_cast<long long>(blockIdx.x) * n_maps) / gridDim.x);
     const int m1 = static_cast<int>((static_cast<long long>(blockIdx.x + 1) * n_maps) / gridDim.x);
     const int q_total = m1 - m0;
-    int sample = m0 / K, k = m0 - sample * K, spar = 0;
+    const int sample0 = m0 / K, k0 = m0 - sample0 * K;
 
-    // the pixels of this thread: float4 number t + j*NT of every map
-    int gx[NV], gy[NV];
+    if (warp == NW) {
+        // =================================== producer warp ==========================================================
+        // lane l holds the per-sample inputs of joints l and l + 32 of the NEXT sample to be published; the loads
+        // are issued a whole sample ahead (a plain load behind ~100 KB of queued bulk copies waits microseconds)
+        Centre c[2];
+        RDSMeta mt[2];
+        auto load_meta = [&](int s) {
 #pragma unroll
-    for (int j = 0; j < NV; ++j) {
-        const int v = t + j * NT;
-        uint32_t yy, xx;
-        a.wdiv.divmod(static_cast<uint32_t>(v < n4 ? 4 * v : 0), yy, xx);
-        gx[j] = static_cast<int>(xx);
-        gy[j] = static_cast<int>(yy);
-    }
-
-    // per-sample inputs, one sample ahead (thread kk < K holds joint kk)
-    auto load_meta = [&](int s, Centre& c, RDSMeta& mt) {
-        if (t < K && s < a.B) {
-            const int map = s * K + t;
-            c.x = a.centres[2 * map + 0];
-            c.y = a.centres[2 * map + 1];
-            const float w = a.weight ? a.weight[map] : 1.0f;
-            if (TASK == RD_FWD) {
-                mt.a = w;
-            } else {
-                float go, denom;
-                if (a.grad_kind == HP_GRAD_SCALAR) {
-                    go = a.grad_out[0];
-                    denom = static_cast<float>(a.B) * static_cast<float>(K);
-                } else {
-                    go = a.grad_out[s];
-                    denom = static_cast<float>(K);
-                }
-                mt.a = go * w / denom;
-                mt.b = -a.stats[3 * map + 0] * kLog2e;
-                mt.c = 1.0f / a.stats[3 * map + 1];
-                mt.d = a.stats[3 * map + 2];
-            }
-        }
-    };
-    auto request = [&](int q) {  // thread 0: arm stage q % kst and request map m0 + q
-        const int s = q % kst;
-        const size_t off = static_cast<size_t>(m0 + q) * ohw;
-        mbar_arrive_expect_tx(bar_u32 + 8 * s, stage_bytes);
-        const uint64_t pol = l2_evict_first_policy();
-        bulk_load(stage_u32 + s * stage_bytes, a.y_adv + off, static_cast<uint32_t>(ohw) * 4u, bar_u32 + 8 * s, pol);
-        if (use_fused)
-            bulk_load(stage_u32 + s * stage_bytes + static_cast<uint32_t>(ohw) * 4u, a.fused + off,
-                      static_cast<uint32_t>(ohw) * 4u, bar_u32 + 8 * s, pol);
-    };
-
-    // ---- prologue: small loads are ISSUED before the bulk copies are requested -------------------------------------
-    Centre c_cur{0, 0}, c_nxt{0, 0};
-    RDSMeta m_cur{0.f, 0.f, 0.f, 0.f}, m_nxt{0.f, 0.f, 0.f, 0.f};
-    load_meta(sample, c_cur, m_cur);
-    load_meta(sample + 1, c_nxt, m_nxt);
-    const float tab0 = (t < ntab) ? a.tab[t] : 0.0f;
-    if (t == 0) {
-        for (int s = 0; s < kst; ++s) mbar_init(bar_u32 + 8 * s, 1);
-        mbar_init_fence();
-        for (int q = 0; q < kst && q < q_total; ++q) request(q);
-    }
-    if (t < ntab) s_tab[t] = tab0;
-    for (int i = t + NT; i < ntab; i += NT) s_tab[i] = a.tab[i];
-    if (t < K) {
-        sh.c[0][t] = c_cur;
-        sh.meta[0][t] = m_cur;
-    }
-    __syncthreads();
-
-    float4 all[NV];  // clip01(sum over the sample's joints) at this thread's pixels
-#pragma unroll
-    for (int j = 0; j < NV; ++j) all[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-    bool new_sample = true;
-    // the map whose closure is pending (forward)
-    int prev_map = -1;
-    float prev_w = 0.f, prev_M = 1.f, prev_Mp = 0.f;
-    Centre prev_c{0, 0};
-
-    auto closure = [&](int pp) {  // ONE thread: per-map loss and the statistics the backward pass needs
-        float Sexp = 0.f, Su = 0.f, Sup = 0.f, Sulg = 0.f, Spbg = 0.f;
-        for (int w = 0; w < NW; ++w) {
-            Sexp += sh.p2[pp][w][0];
-            Su += sh.p2[pp][w][1];
-            Sup += sh.p2[pp][w][2];
-            Sulg += sh.p2[pp][w][3];
-            Spbg += sh.p2[pp][w][4];
-        }
-        float Sulogu = Sulg * kLn2;
-        if (!dense) {  // the pixels outside the float4s that touch the patch, in closed form
-            const int r0 = max(prev_c.y - tmp, 0), r1 = min(prev_c.y + tmp, a.oh - 1);
-            const int c0 = max(prev_c.x - tmp, 0) >> 2, c1 = min(prev_c.x + tmp, a.ow - 1) >> 2;
-            const float nb = static_cast<float>(ohw - 4 * (r1 - r0 + 1) * (c1 - c0 + 1));
-            const float ubg = rds_norm(bg, prev_M, normalise && prev_M != 1.0f) + a.eps;
-            Su = fmaf(nb, ubg, Su);
-            Sup = fmaf(ubg, Spbg, Sup);
-            if (ubg != 0.0f) Sulogu = fmaf(nb, ubg * logf(ubg), Sulogu);
-        }
-        // L = (sum u ln u - sum u p)/S - ln S + lse,  lse = Mp + ln(sum exp)   (loss.py:145-158)
-        const float lse = prev_Mp + logf(Sexp);
-        const double L = static_cast<double>((Sulogu - Sup) / Su) + static_cast<double>(prev_Mp) +
-                         static_cast<double>(logf(Sexp / Su));
-        a.per_map[prev_map] = static_cast<float>(L * static_cast<double>(prev_w));
-        a.stats[3 * prev_map + 0] = lse;
-        a.stats[3 * prev_map + 1] = Su;
-        a.stats[3 * prev_map + 2] = prev_M;
-    };
-
-    for (int q = 0; q < q_total; ++q) {
-        const int map = m0 + q, par = q & 1, s = q % kst;
-        const uint32_t phase = static_cast<uint32_t>(q / kst) & 1u;
-        const Centre* s_c = sh.c[spar];
-        if (new_sample) {
-            new_sample = false;
-            if (needs_all) {
-#pragma unroll
-                for (int j = 0; j < NV; ++j) {
-                    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (t + j * NT < n4) {
-                        for (int jj = 0; jj < K; ++jj) {
-                            const Centre cj = s_c[jj];
-                            if (static_cast<unsigned>(gy[j] - cj.y + tmp) <= 2u * static_cast<unsigned>(tmp) &&
-                                gx[j] + 3 >= cj.x - tmp && gx[j] <= cj.x + tmp)
-                                sum = add4(sum, patch_at4(s_tab, tmp, cj, gx[j], gy[j]));
+            for (int h = 0; h < 2; ++h) {
+                const int kk = lane + 32 * h;
+                c[h] = Centre{0, 0};
+                mt[h] = RDSMeta{0.f, 0.f, 0.f, 0.f};
+                if (kk < K && s < a.B) {
+                    const int map = s * K + kk;
+                    c[h].x = a.centres[2 * map + 0];
+                    c[h].y = a.centres[2 * map + 1];
+                    const float w = a.weight ? a.weight[map] : 1.0f;
+                    if (TASK == RD_FWD) {
+                        mt[h].a = w;
+                    } else {
+                        float go, denom;
+                        if (a.grad_kind == HP_GRAD_SCALAR) {
+                            go = a.grad_out[0];
+                            denom = static_cast<float>(a.B) * static_cast<float>(K);
+                        } else {
+                            go = a.grad_out[s];
+                            denom = static_cast<float>(K);
                         }
+                        mt[h].a = go * w / denom;
+                        mt[h].b = -a.stats[3 * map + 0] * kLog2e;
+                        mt[h].c = 1.0f / a.stats[3 * map + 1];
+                        mt[h].d = a.stats[3 * map + 2];
                     }
-                    all[j] = clip01_4(sum);
                 }
             }
+        };
+        auto publish = [&](int slot) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int kk = lane + 32 * h;
+                if (kk < K) {
+                    sh.c[slot][kk] = c[h];
+                    sh.meta[slot][kk] = mt[h];
+                }
+            }
+        };
+        const uint64_t pol = l2_evict_first_policy();
+        auto request = [&](int q) {  // lane 0: arm stage q % kst and request map m0 + q
+            const int s = q % kst;
+            const size_t off = static_cast<size_t>(m0 + q) * ohw;
+            mbar_arrive_expect_tx(full_u32 + 8 * s, stage_bytes);
+            bulk_load(stage_u32 + s * stage_bytes, a.y_adv + off, static_cast<uint32_t>(ohw) * 4u, full_u32 + 8 * s, pol);
+            if (FUSED)
+                bulk_load(stage_u32 + s * stage_bytes + static_cast<uint32_t>(ohw) * 4u, a.fused + off,
+                          static_cast<uint32_t>(ohw) * 4u, full_u32 + 8 * s, pol);
+        };
+        // prologue: small loads first, then the first sample's maps, then its inputs
+        load_meta(sample0);
+        int q = min(min(kst, K - k0), q_total);
+        if (lane == 0) {
+            for (int s = 0; s < kst; ++s) {
+                mbar_init(full_u32 + 8 * s, 1);
+                mbar_init(empty_u32 + 8 * s, NW);
+            }
+            mbar_init_fence();
+            for (int i = 0; i < q; ++i) request(i);
         }
-        if (k == K - 1 && t < K) {  // hand the next sample's inputs over (visible after this map's barrier)
-            sh.c[spar ^ 1][t] = c_nxt;
-            sh.meta[spar ^ 1][t] = m_nxt;
+        publish(0);
+        load_meta(sample0 + 1);
+        __syncthreads();
+        int kq = k0 + q, smp = sample0;
+        if (kq == K) {
+            kq = 0;
+            ++smp;
         }
-        const Centre ck = s_c[k];
-        const RDSMeta meta = sh.meta[spar][k];
-        const float4* st_adv = reinterpret_cast<const float4*>(s_rds + static_cast<size_t>(s) * stage_bytes);
-        const float4* st_fz = st_adv + n4;
-
-        mbar_wait(bar_u32 + 8 * s, phase);
-        // ---- pass A: the map into registers, the target's un-normalised values, the two maxima ----------------------
-        float4 p[NV], g[NV];
-        unsigned hit = 0;
-        float lmp = -INFINITY, lmg = -INFINITY;
+        for (; q < q_total; ++q) {
+            if (kq == 0) {  // first map of a sample: its inputs become visible with the arm of the map's barrier
+                publish((smp - sample0) & (kRDSSlots - 1));
+                __syncwarp();
+                load_meta(smp + 1);
+            }
+            if (lane == 0) {
+                if (q >= kst) mbar_wait(empty_u32 + 8 * (q % kst), static_cast<uint32_t>(q / kst - 1) & 1u);
+                request(q);
+            }
+            __syncwarp();
+            if (++kq == K) {
+                kq = 0;
+                ++smp;
+            }
+        }
+    } else {
+        // =================================== consumer warps =========================================================
+        for (int i = t; i < ntab; i += NT) s_tab[i] = a.tab[i];
+        if (t < kFxAccWords) sh.acc[t] = 0ull;
+        __syncthreads();  // barriers initialised, table and the first sample's inputs in shared memory
+        // the pixels of this thread: float4 number t + j*NT of every map
+        int gx[NV], gy[NV];
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
-            const int v = t + j * NT;
-            p[j] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-            g[j] = make_float4(bg, bg, bg, bg);
-            if (v < n4) {
-                p[j] = st_adv[v];
-                float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (use_fused) f = st_fz[v];
-                if (dense) {
-                    g[j] = needs_all ? all[j] : make_float4(1.f, 1.f, 1.f, 1.f);
-                    if (use_fused) g[j] = clip01_4(add4(g[j], f));
+            uint32_t yy, xx;
+            a.wdiv.divmod(static_cast<uint32_t>(4 * (t + j * NT)), yy, xx);
+            gx[j] = static_cast<int>(xx);
+            gy[j] = static_cast<int>(yy);
+        }
+        float4 all[DENSE ? NV : 1];  // clip01(sum over the sample's joints) at this thread's pixels (1 when not needed)
+#pragma unroll
+        for (int j = 0; j < (DENSE ? NV : 1); ++j) all[j] = make_float4(1.f, 1.f, 1.f, 1.f);
+        bool new_sample = true;
+        int k = k0, smp = sample0, s = 0;
+        uint32_t phase = 0;
+        const unsigned rspan = 2u * static_cast<unsigned>(tmp), cspan = rspan + 3u;
+        const float2 l2 = make_float2(kLog2e, kLog2e);
+
+        auto close_batch = [&](int buf, int count, int first_map) {  // thread (warp i % NW, lane i / NW) closes slot i
+            named_barrier<1, NT>();
+            const int i = lane * NW + warp;
+            if (i < count) {
+                const float4 cm = sh.clm[buf][i];
+                const int cx = __float_as_int(cm.x), cy = __float_as_int(cm.y);
+                const float w = cm.z, M = cm.w;
+                float Mp = -INFINITY;
+                for (int ww = 0; ww < NW; ++ww) Mp = fmaxf(Mp, sh.cl[buf][i][ww][5]);
+                float Sexp = 0.f, Su = 0.f, Sup = 0.f, Sulg = 0.f, Spbg = 0.f;
+                for (int ww = 0; ww < NW; ++ww) {
+                    const float* r = sh.cl[buf][i][ww];
+                    Sexp = fmaf(r[0], exp_diff(r[5], Mp), Sexp);
+                    Su += r[1];
+                    Sup += r[2];
+                    Sulg += r[3];
+                    Spbg += r[4];
                 }
-                const bool touches = static_cast<unsigned>(gy[j] - ck.y + tmp) <= 2u * static_cast<unsigned>(tmp) &&
-                                     gx[j] + 3 >= ck.x - tmp && gx[j] <= ck.x + tmp;
-                if (touches) {  // exact per-pixel recipe
-                    hit |= 1u << j;
-                    const float4 gt = patch_at4(s_tab, tmp, ck, gx[j], gy[j]);
-                    if (want_gf) {
-                        g[j].x = ground_false_pixel(a.variant, use_fused, k, K, gx[j] + 0, gy[j], gt.x, f.x, all[j].x, s_tab, tmp, s_c);
-                        g[j].y = ground_false_pixel(a.variant, use_fused, k, K, gx[j] + 1, gy[j], gt.y, f.y, all[j].y, s_tab, tmp, s_c);
-                        g[j].z = ground_false_pixel(a.variant, use_fused, k, K, gx[j] + 2, gy[j], gt.z, f.z, all[j].z, s_tab, tmp, s_c);
-                        g[j].w = ground_false_pixel(a.variant, use_fused, k, K, gx[j] + 3, gy[j], gt.w, f.w, all[j].w, s_tab, tmp, s_c);
-                    } else {
-                        g[j] = gt;
+                float Sulogu = Sulg * kLn2;
+                if (!DENSE) {  // the pixels outside the float4s that touch the patch, in closed form
+                    const int r0 = max(cy - tmp, 0), r1 = min(cy + tmp, a.oh - 1);
+                    const int c0 = max(cx - tmp, 0) >> 2, c1 = min(cx + tmp, a.ow - 1) >> 2;
+                    const float nb = static_cast<float>(ohw - 4 * (r1 - r0 + 1) * (c1 - c0 + 1));
+                    const float ubg = bg + a.eps;
+                    Su = fmaf(nb, ubg, Su);
+                    Sup = fmaf(ubg, Spbg, Sup);
+                    if (ubg != 0.0f) Sulogu = fmaf(nb, ubg * logf(ubg), Sulogu);
+                }
+                // L = (sum u ln u - sum u p)/S - ln S + lse,  lse = Mp + ln(sum exp)   (loss.py:145-158)
+                const float lse = Mp + logf(Sexp);
+                const double L = static_cast<double>((Sulogu - Sup) / Su) + static_cast<double>(Mp) +
+                                 static_cast<double>(logf(Sexp / Su));
+                const int map = first_map + i;
+                const float Lw = static_cast<float>(L * static_cast<double>(w));
+                a.per_map[map] = Lw;
+                if (a.mean) fx_acc_add(sh.acc, Lw);
+                a.stats[3 * map + 0] = lse;
+                a.stats[3 * map + 1] = Su;
+                a.stats[3 * map + 2] = M;
+            }
+        };
+        // exact per-pixel target (before normalisation and epsilon) of a float4 that touches the own patch
+        auto exact4 = [&](int j, const Centre ck, const Centre* s_c, float4 f, float4 al) {
+            const float4 gt = patch_at4(s_tab, tmp, ck, gx[j], gy[j]);
+            if (!want_gf) return gt;
+            float4 r;
+            r.x = ground_false_pixel(a.variant, FUSED, k, K, gx[j] + 0, gy[j], gt.x, f.x, al.x, s_tab, tmp, s_c);
+            r.y = ground_false_pixel(a.variant, FUSED, k, K, gx[j] + 1, gy[j], gt.y, f.y, al.y, s_tab, tmp, s_c);
+            r.z = ground_false_pixel(a.variant, FUSED, k, K, gx[j] + 2, gy[j], gt.z, f.z, al.z, s_tab, tmp, s_c);
+            r.w = ground_false_pixel(a.variant, FUSED, k, K, gx[j] + 3, gy[j], gt.w, f.w, al.w, s_tab, tmp, s_c);
+            return r;
+        };
+
+        for (int q = 0; q < q_total; ++q) {
+            const int map = m0 + q, slot = (smp - sample0) & (kRDSSlots - 1);
+            const Centre* s_c = sh.c[slot];
+            const float4* st_adv = reinterpret_cast<const float4*>(s_rds + static_cast<size_t>(s) * stage_bytes);
+            mbar_wait(full_u32 + 8 * s, phase);
+            if (new_sample) {
+                new_sample = false;
+                if (needs_all) {
+#pragma unroll
+                    for (int j = 0; j < (DENSE ? NV : 1); ++j) {
+                        float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+                        for (int jj = 0; jj < K; ++jj) {
+                            const Centre cj = s_c[jj];
+                            if (static_cast<unsigned>(gy[j] - cj.y + tmp) <= rspan &&
+                                static_cast<unsigned>(gx[j] - cj.x + tmp + 3) <= cspan)
+                                sum = add4(sum, patch_at4(s_tab, tmp, cj, gx[j], gy[j]));
+                        }
+                        all[j] = clip01_4(sum);
                     }
+                }
+            }
+            const Centre ck = s_c[k];
+            const RDSMeta meta = sh.meta[slot][k];
+            const int r0 = ck.y - tmp, c0 = ck.x - tmp - 3;
+            // ---- pass A: the map into registers, the target's un-normalised values (dense recipes), the maxima ------
+            float4 p[NV], g[DENSE ? NV : 1];
+            unsigned hit = 0;
+            float lmp = -INFINITY, lmg = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < NV; ++j) {
+                p[j] = st_adv[t + j * NT];
+                const bool touches = static_cast<unsigned>(gy[j] - r0) <= rspan && static_cast<unsigned>(gx[j] - c0) <= cspan;
+                if (touches) hit |= 1u << j;
+                if (DENSE) {
+                    float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (FUSED) f = st_adv[n4 + t + j * NT];
+                    g[j] = all[j];
+                    if (FUSED) g[j] = clip01_4(add4(g[j], f));
+                    if (touches) g[j] = exact4(j, ck, s_c, f, all[j]);
+                    lmg = fmaxf(lmg, max4(g[j]));
                 }
                 lmp = fmaxf(lmp, max4(p[j]));
-                lmg = fmaxf(lmg, max4(g[j]));
             }
-        }
-        if (TASK == RD_FWD) {
-            const float wmp = warp_max_f32(lmp);
-            const float wmg = normalise ? warp_max_f32(lmg) : 1.0f;
-            if (lane == 0) {
-                sh.p1[par][warp][0] = wmp;
-                sh.p1[par][warp][1] = wmg;
+            // every lane holds its pixels: this warp is done with the stage
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty_u32 + 8 * s);
+            if (++s == kst) {
+                s = 0;
+                phase ^= 1u;
             }
-        }
-        __syncthreads();  // every thread holds its pixels: the stage is free; the warp maxima are visible
-        if (t == 0 && q + kst < q_total) request(q + kst);
 
-        if (TASK == RD_FWD) {
-            if (prev_map >= 0 && t == 32 * ((q - 1) % NW)) closure(par ^ 1);
-            float Mp = -INFINITY, M = -INFINITY;
+            float M = 1.0f;
+            if (TASK == RD_FWD) {
+                if (DENSE && normalise) {  // the one cross-warp dependency of a map: the normaliser
+                    const float wmg = warp_max_f32(lmg);
+                    if (lane == 0) sh.mx[q & 1][warp] = wmg;
+                    named_barrier<1, NT>();
+                    M = -INFINITY;
 #pragma unroll
-            for (int w = 0; w < NW; ++w) {
-                Mp = fmaxf(Mp, sh.p1[par][w][0]);
-                M = fmaxf(M, sh.p1[par][w][1]);
-            }
-            if (!normalise) M = 1.0f;
-            const bool divide = normalise && M != 1.0f;
-            // ---- pass B: the sums, against the true maximum -----------------------------------------------------------
-            const float ms = (Mp == -INFINITY) ? 0.0f : Mp;
-            const float mb = -ms * kLog2e;
-            float sexp = 0.f, su = 0.f, sup = 0.f, sulg = 0.f, spbg = 0.f;
+                    for (int ww = 0; ww < NW; ++ww) M = fmaxf(M, sh.mx[q & 1][ww]);
+                    if (M != 1.0f) {
 #pragma unroll
-            for (int j = 0; j < NV; ++j) {
-                if (t + j * NT < n4) {
-                    sexp += ex2_approx(fmaf(p[j].x, kLog2e, mb)) + ex2_approx(fmaf(p[j].y, kLog2e, mb));
-                    sexp += ex2_approx(fmaf(p[j].z, kLog2e, mb)) + ex2_approx(fmaf(p[j].w, kLog2e, mb));
-                    if (dense || ((hit >> j) & 1u)) {
+                        for (int j = 0; j < (DENSE ? NV : 1); ++j)
+                            g[j] = make_float4(__fdiv_rn(g[j].x, M), __fdiv_rn(g[j].y, M), __fdiv_rn(g[j].z, M), __fdiv_rn(g[j].w, M));
+                    }
+                }
+                // ---- pass B: the sums; the softmax sum against the WARP's maximum (re-based at the closure) ----------
+                const float wmp = warp_max_f32(lmp);
+                const float ms = (wmp == -INFINITY) ? 0.0f : wmp;
+                const float2 mb2 = make_float2(-ms * kLog2e, -ms * kLog2e);
+                float2 sexp2 = make_float2(0.f, 0.f), spbg2 = make_float2(0.f, 0.f);
+                float su = 0.f, sup = 0.f, sulg = 0.f;
+#pragma unroll
+                for (int j = 0; j < NV; ++j) {
+                    const float2 lo = make_float2(p[j].x, p[j].y), hi = make_float2(p[j].z, p[j].w);
+                    const float2 a0 = __ffma2_rn(lo, l2, mb2), a1 = __ffma2_rn(hi, l2, mb2);
+                    sexp2 = __fadd2_rn(sexp2, __fadd2_rn(make_float2(ex2_approx(a0.x), ex2_approx(a0.y)),
+                                                         make_float2(ex2_approx(a1.x), ex2_approx(a1.y))));
+                    if (DENSE || ((hit >> j) & 1u)) {
+                        const float4 gv = DENSE ? g[j] : exact4(j, ck, s_c, make_float4(0.f, 0.f, 0.f, 0.f), make_float4(1.f, 1.f, 1.f, 1.f));
 #pragma unroll
                         for (int c = 0; c < 4; ++c) {
-                            const float u = rds_norm(f4_get(g[j], c), M, divide) + a.eps;
-                            const float pv = f4_get(p[j], c);
+                            const float u = f4_get(gv, c) + a.eps;
                             su += u;
-                            sup = fmaf(u, pv, sup);
-                            if (u != 0.0f) sulg = fmaf(u, lg2_approx(u), sulg);  // xlogy: 0 at u == 0, NaN for u < 0
+                            sup = fmaf(u, f4_get(p[j], c), sup);
+                            // xlogy: the term is 0 at u == 0 (lg2 of the clamp is finite), NaN propagates through u
+                            sulg = fmaf(u, lg2_approx(fmaxf(u, 1.17549435e-38f)), sulg);
                         }
                     } else {
-                        spbg += (p[j].x + p[j].y) + (p[j].z + p[j].w);
+                        spbg2 = __fadd2_rn(spbg2, __fadd2_rn(lo, hi));
                     }
                 }
-            }
-            sexp = warp_sum_f32(sexp);
-            su = warp_sum_f32(su);
-            sup = warp_sum_f32(sup);
-            sulg = warp_sum_f32(sulg);
-            spbg = warp_sum_f32(spbg);
-            if (lane == 0) {
-                float* o = sh.p2[par][warp];
-                o[0] = sexp;
-                o[1] = su;
-                o[2] = sup;
-                o[3] = sulg;
-                o[4] = spbg;
-            }
-            prev_map = map;
-            prev_w = meta.a;
-            prev_M = M;
-            prev_Mp = Mp;
-            prev_c = ck;
-        } else {
-            // ---- backward: d/dp = coef * (softmax(p) - u / S)    ----------------------------
-            const float coef = meta.a, lb = meta.b, invS = meta.c, M = meta.d;
-            const bool divide = normalise && M != 1.0f;
-            const float ubg = rds_norm(bg, M, divide) + a.eps;
-            float4* out = reinterpret_cast<float4*>(a.grad_in + static_cast<size_t>(map) * ohw);
+                const float v8[8] = {sexp2.x + sexp2.y, su, sup, sulg, spbg2.x + spbg2.y, 0.f, 0.f, 0.f};
+                const float tot = warp_sum8_scattered(v8, lane);
+                const int buf = (q / kRDSBatch) & 1, i = q % kRDSBatch;
+                if ((lane & 3) == 0) {
+                    const int idx = rds_sum_index(lane);
+                    if (idx < 6) sh.cl[buf][i][warp][idx] = (idx == 5) ? wmp : tot;
+                }
+                if (t == 0) sh.clm[buf][i] = make_float4(__int_as_float(ck.x), __int_as_float(ck.y), meta.a, M);
+                if (i == kRDSBatch - 1 || q == q_total - 1) close_batch(buf, i + 1, map - i);
+            } else {
+                // ---- backward: d/dp = coef * (softmax(p) - u / S)    --------------------------
+                const float coef = meta.a, lb = meta.b, invS = meta.c;
+                M = meta.d;
+                const bool divide = DENSE && normalise && M != 1.0f;
+                const float qbg = (bg + a.eps) * invS;
+                float4* out = reinterpret_cast<float4*>(a.grad_in + static_cast<size_t>(map) * ohw);
 #pragma unroll
-            for (int j = 0; j < NV; ++j) {
-                const int v = t + j * NT;
-                if (v < n4) {
+                for (int j = 0; j < NV; ++j) {
                     float r[4];
-                    const bool exact = dense || ((hit >> j) & 1u);
+                    float4 gv = make_float4(bg, bg, bg, bg);
+                    if (DENSE) gv = g[j];
+                    else if ((hit >> j) & 1u) gv = exact4(j, ck, s_c, make_float4(0.f, 0.f, 0.f, 0.f), make_float4(1.f, 1.f, 1.f, 1.f));
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
-                        const float u = exact ? rds_norm(f4_get(g[j], c), M, divide) + a.eps : ubg;
-                        r[c] = coef * (ex2_approx(fmaf(f4_get(p[j], c), kLog2e, lb)) - u * invS);
+                        float qv = qbg;
+                        if (DENSE || ((hit >> j) & 1u)) qv = (rds_norm(f4_get(gv, c), M, divide) + a.eps) * invS;
+                        r[c] = coef * (ex2_approx(fmaf(f4_get(p[j], c), kLog2e, lb)) - qv);
                     }
-                    stg_stream4(out + v, make_float4(r[0], r[1], r[2], r[3]));
+                    stg_stream4(out + t + j * NT, make_float4(r[0], r[1], r[2], r[3]));
                 }
             }
-        }
-        if (++k == K) {
-            k = 0;
-            ++sample;
-            spar ^= 1;
-            new_sample = true;
-            load_meta(sample + 1, c_nxt, m_nxt);
+            if (++k == K) {
+                k = 0;
+                ++smp;
+                new_sample = true;
+            }
         }
     }
 
     if (TASK == RD_FWD) {
-        __syncthreads();
-        if (prev_map >= 0 && t == 0) closure((q_total - 1) & 1);
         if (a.mean == nullptr && a.per_sample == nullptr) return;
+        __syncthreads();  // the block's closures are done (shared accumulators final)
+        if (a.mean && t < kFxAccWords && sh.acc[t] != 0ull) atomicAdd(&a.ws->acc[t], sh.acc[t]);
         if (last_block_arrives(&a.ws->counter, gridDim.x)) {
-            const volatile float* pmv = a.per_map;
-            if (a.per_sample) {
-                for (int s = t; s < a.B; s += NT) {
-                    double acc = 0.0;
-                    for (int kk = 0; kk < K; ++kk) acc += static_cast<double>(pmv[s * K + kk]);
-                    a.per_sample[s] = static_cast<float>(acc / static_cast<double>(K));
-                }
-            }
-            if (a.mean) {
-                double acc = 0.0;
-                for (int i = t; i < n_maps; i += NT) acc += static_cast<double>(pmv[i]);
-                s_red[t] = acc;
-                __syncthreads();
-                for (int o = NT / 2; o > 0; o >>= 1) {
-                    if (t < o) s_red[t] += s_red[t + o];
-                    __syncthreads();
-                }
-                if (t == 0) *a.mean = static_cast<float>(s_red[0] / static_cast<double>(n_maps));
+            if (a.per_sample) per_sample_means(a.per_map, a.B, K, a.per_sample, t, NT + 32);
+            if (a.mean && t == 0) {
+                *a.mean = fx_mean_from_workspace(a.ws->acc, n_maps);
             }
             if (t == 0) a.ws->counter = 0;
         }
@@ -424,16 +465,16 @@ __global__ void __launch_bounds__(NT, 512 / NT) regdisp_staged_kernel(const RDAr
 
 // host side: pick the block shape, the stage count and the grid; returns 1 when the shape is not covered
 // (the caller then takes the guarded generic kernel), 0 when launched, < 0 / > 0 on errors.
-template <int NT, int NV, int TASK>
-static int launch_rds_shape(const RDArgs& a, int nbuf, int sms, cudaStream_t stream, const char* who) {
+template <int NT, int NV, int TASK, bool DENSE, bool FUSED>
+static int launch_rds_shape(const RDArgs& a, int sms, cudaStream_t stream, const char* who) {
     constexpr int BPS = 512 / NT;
-    const int ohw = a.oh * a.ow;
-    const size_t stage = static_cast<size_t>(nbuf) * ohw * 4;
+    const size_t stage = static_cast<size_t>(FUSED ? 2 : 1) * NT * NV * 16;
     const size_t tab = ((table_bytes(a.tmp) + 15) / 16) * 16;
-    const size_t budget = (227 * 1024) / BPS - 1024 - sizeof(RDSShared<NT>) - (TASK == RD_FWD ? NT * 8 : 8) - 256;
+    const size_t budget = (227 * 1024) / BPS - 1024 - sizeof(RDSShared<NT>) - 256;
     if (budget < tab + 2 * stage) return 1;
     int kst = static_cast<int>((budget - tab) / stage);
     if (kst > kRDSMaxStages) kst = kRDSMaxStages;
+    if (kst > 2 * a.K) kst = 2 * a.K;  // the producer never runs more than two samples ahead (kRDSSlots)
     const size_t smem = static_cast<size_t>(kst) * stage + tab;
     const int n_maps = a.B * a.K;
     int grid = sms * BPS;
@@ -447,30 +488,44 @@ static int launch_rds_shape(const RDArgs& a, int nbuf, int sms, cudaStream_t str
     cudaGetDevice(&dev);
     bool& attr_done = attr_done_dev[dev & 63];
     if (!attr_done) {
-        const cudaError_t e = cudaFuncSetAttribute(regdisp_staged_kernel<NT, NV, TASK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                   static_cast<int>((227 * 1024) / BPS - 1024 - 4096));
+        const cudaError_t e = cudaFuncSetAttribute(regdisp_staged_kernel<NT, NV, TASK, DENSE, FUSED>,
+                                                   cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(budget));
         if (e != cudaSuccess) return fail(static_cast<int>(e), "%s: %s", who, cudaGetErrorString(e));
         attr_done = true;
     }
-    regdisp_staged_kernel<NT, NV, TASK><<<grid, NT, smem, stream>>>(a, kst);
+    regdisp_staged_kernel<NT, NV, TASK, DENSE, FUSED><<<grid, NT + 32, smem, stream>>>(a, kst);
     return launch_status(who);
+}
+
+template <int NT, int NV, int TASK>
+static int launch_rds_recipe(const RDArgs& a, bool dense, bool fused, int sms, cudaStream_t stream, const char* who) {
+    if (fused) return launch_rds_shape<NT, NV, TASK, true, true>(a, sms, stream, who);
+    if (dense) return launch_rds_shape<NT, NV, TASK, true, false>(a, sms, stream, who);
+    return launch_rds_shape<NT, NV, TASK, false, false>(a, sms, stream, who);
 }
 
 template <int TASK>
 static int launch_regdisp_staged(RDArgs a, cudaStream_t stream, const char* who) {
-    const int ohw = a.oh * a.ow, n4 = ohw / 4;
-    if (n4 > 1024) return 1;
+    const int ohw = a.oh * a.ow;
+    if (ohw != 256 && ohw != 1024 && ohw != 4096) return 1;  // 16^2, 32^2, 64^2 maps (any oh x ow with ow % 4 == 0)
     static int sms = 0;
     if (sms == 0) {
         sms = hp_device_sm_count();
         if (sms <= 0) sms = 148;
     }
     a.wdiv = FastDiv(static_cast<uint32_t>(a.ow));
-    const bool use_fused = a.mode == HP_MODE_MAX && a.fused != nullptr && a.variant != HP_RD_X1;
-    const int nbuf = use_fused ? 2 : 1;
-    if (n4 <= 64) return launch_rds_shape<64, 1, TASK>(a, nbuf, sms, stream, who);
-    if (n4 <= 256) return launch_rds_shape<128, 2, TASK>(a, nbuf, sms, stream, who);
-    return launch_rds_shape<256, 4, TASK>(a, nbuf, sms, stream, who);
+    const bool want_gf = a.mode == HP_MODE_MAX;
+    const bool fused = want_gf && a.fused != nullptr && a.variant != HP_RD_X1;
+    const bool dense = fused || (want_gf && (a.variant == HP_RD_BASE || a.variant == HP_RD_X6));
+    if (!dense) {
+        // sparse recipes take M == 1 for granted: some float4 of the map must lie outside every possible patch
+        const int side = 2 * a.tmp + 1;
+        const long long touched = static_cast<long long>(side < a.oh ? side : a.oh) * ((side + 2) / 4 + 1);
+        if (touched >= ohw / 4) return 1;
+    }
+    if (ohw == 256) return launch_rds_recipe<64, 1, TASK>(a, dense, fused, sms, stream, who);
+    if (ohw == 1024) return launch_rds_recipe<128, 2, TASK>(a, dense, fused, sms, stream, who);
+    return launch_rds_recipe<256, 4, TASK>(a, dense, fused, sms, stream, who);
 }
 
 }  // namespace hp
