@@ -112,12 +112,18 @@ def load():
     return _lib
 
 
+_fn_cache = {}
+
+
 def call(name, *args):
-    """Invoke an ``int``-returning entry point and raise ``RuntimeError(hp_last_error())`` on failure."""
-    lib = load()
-    rc = getattr(lib, name)(*args)
+    """Invoke an ``int``-returning entry point and raise ``RuntimeError(hp_last_error())`` on failure.
+    (Bound functions are cached: attribute lookup on a CDLL costs about as much as a small kernel launch.)"""
+    fn = _fn_cache.get(name)
+    if fn is None:
+        fn = _fn_cache[name] = getattr(load(), name)
+    rc = fn(*args)
     if rc != 0:
-        raise RuntimeError(f"{name} failed (rc={rc}): {lib.hp_last_error().decode(errors='replace')}")
+        raise RuntimeError(f"{name} failed (rc={rc}): {load().hp_last_error().decode(errors='replace')}")
 
 
 # ------------------------------------------------------------------------------------------
@@ -125,11 +131,36 @@ def call(name, *args):
 # ------------------------------------------------------------------------------------------
 
 def ptr(t):
-    return None if t is None else C.c_void_p(t.data_ptr())
+    """Device address as a plain int (ctypes converts it through the prototype's c_void_p), None -> NULL."""
+    return None if t is None else t.data_ptr()
 
 
 def stream_ptr(device=None):
-    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class on_device:
+    """``with on_device(dev):`` - make ``dev`` current for the launches inside; free when it already is
+    (the common one-process-per-GPU case), unlike ``torch.cuda.device`` which always round-trips the driver."""
+    __slots__ = ("idx", "prev")
+
+    def __init__(self, device):
+        self.idx = device.index
+        self.prev = -1
+
+    def __enter__(self):
+        if self.idx is not None:
+            cur = torch.cuda.current_device()
+            if cur != self.idx:
+                self.prev = cur
+                torch.cuda.set_device(self.idx)
+        return self
+
+    def __exit__(self, *exc):
+        if self.prev >= 0:
+            torch.cuda.set_device(self.prev)
+            self.prev = -1
+        return False
 
 
 def require_cuda(t: torch.Tensor, what: str, dtype=torch.float32) -> torch.Tensor:
@@ -148,12 +179,16 @@ def require_cuda(t: torch.Tensor, what: str, dtype=torch.float32) -> torch.Tenso
 
 
 _ws_cache = {}
+_ws_need = None
 
 
 def workspace(device: torch.device, n_maps: int, K: int) -> torch.Tensor:
     """Zero-initialised scratch (block counter, PCK counters, per-map partials) per (device, stream).
     Kernels restore the zero state before they exit, so it is reused without a memset."""
-    need = int(load().hp_workspace_bytes(int(n_maps), int(K)))
+    global _ws_need
+    if _ws_need is None:
+        _ws_need = int(load().hp_workspace_bytes(int(n_maps), int(K)))   # a constant of the library (header + slack)
+    need = _ws_need
     key = (device.index if device.index is not None else torch.cuda.current_device(),
            torch.cuda.current_stream(device).cuda_stream)
     ws = _ws_cache.get(key)

@@ -51,7 +51,7 @@ class PeerExchange:
         self.world = dist.get_world_size(group)
         self.device = torch.device(device)
         self._mapped = []
-        with torch.cuda.device(self.device):
+        with _lib.on_device(self.device):
             own = C.c_void_p()
             _lib.call("hp_peer_alloc", self.world, C.byref(own))
             self._own = own
@@ -88,7 +88,7 @@ class PeerExchange:
             torch.cuda.synchronize(self.device)
             if dist.is_initialized():
                 dist.barrier(group=self.group)     # nobody unmaps while a peer may still write
-            with torch.cuda.device(self.device):
+            with _lib.on_device(self.device):
                 for m in self._mapped:
                     self._lib.call("hp_peer_close", m)
                 self._lib.call("hp_peer_free", self._own)

@@ -27,7 +27,7 @@ def _fuse(lo, a_lo, mid, a_mid, hi, a_hi, size):
         if tuple(hi.shape) != (B, K, H, W):
             raise ValueError(f"fuse: hi is {tuple(hi.shape)}, expected {(B, K, H, W)}")
     out = torch.empty((B, K, H, W), dtype=torch.float32, device=lo.device)
-    with torch.cuda.device(lo.device):
+    with _lib.on_device(lo.device):
         _lib.call("hp_fuse_multiscale", _lib.ptr(lo), hl, wl, C.c_float(a_lo), _lib.ptr(mid), hm, wm, C.c_float(a_mid),
                   _lib.ptr(hi), C.c_float(a_hi), B * K, H, W, _lib.ptr(out), _lib.stream_ptr(lo.device))
     return out

@@ -45,7 +45,7 @@ def decode(heat: torch.Tensor):
         raise ValueError("attempt to get argmax of an empty sequence")
     preds = torch.empty((B, K, 2), dtype=torch.float32, device=heat.device)
     maxvals = torch.empty((B, K, 1), dtype=torch.float32, device=heat.device)
-    with torch.cuda.device(heat.device):
+    with _lib.on_device(heat.device):
         _lib.call("hp_argmax_decode", _lib.ptr(heat), B * K, H, W, _lib.ptr(preds), _lib.ptr(maxvals), None,
                   _lib.stream_ptr(heat.device))
     return preds, maxvals
@@ -77,7 +77,7 @@ def pck(output: torch.Tensor, target: torch.Tensor, thr: float = 0.5):
     pred_xy = torch.empty((B, K, 2), dtype=torch.float32, device=dev)
     counts = torch.empty((2 * K,), dtype=torch.int32, device=dev)
     acc = torch.empty((K + 2,), dtype=torch.float64, device=dev)
-    with torch.cuda.device(dev):
+    with _lib.on_device(dev):
         ws = _lib.workspace(dev, B * K, K)
         _lib.call("hp_accuracy", _lib.ptr(output), _lib.ptr(target), B, K, H, W, C.c_double(thr), _lib.ptr(pred_xy),
                   _lib.ptr(counts), _lib.ptr(acc), _lib.ptr(ws), _lib.stream_ptr(dev))

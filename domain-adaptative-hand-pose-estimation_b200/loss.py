@@ -23,6 +23,19 @@ def _flat_weight(w, B, K, device):
     return w.reshape(B * K)
 
 
+class _NoCtx:
+    """Stand-in for the autograd context when no gradient is wanted: the forward bodies below run as plain
+    functions then (``torch.autograd.Function.apply`` alone costs more host time than the kernel takes)."""
+    __slots__ = ("reduction", "epsilon", "cfg", "fz", "w")
+
+    def save_for_backward(self, *tensors):
+        pass
+
+
+def _wants_grad(t):
+    return torch.is_grad_enabled() and isinstance(t, torch.Tensor) and t.requires_grad
+
+
 class _MSE(torch.autograd.Function):
     @staticmethod
     def forward(ctx, output, target, weight, reduction):
@@ -35,25 +48,23 @@ class _MSE(torch.autograd.Function):
         w = _flat_weight(weight, B, K, dev)
         per_map = torch.empty((B, K), dtype=torch.float32, device=dev)
         mean = torch.empty((), dtype=torch.float32, device=dev) if reduction == "mean" else None
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             ws = _lib.workspace(dev, B * K, K)
             _lib.call("hp_mse_fwd", _lib.ptr(out), _lib.ptr(tgt), _lib.ptr(w), B, K, H * W, _lib.ptr(per_map),
                       _lib.ptr(mean), _lib.ptr(ws), _lib.stream_ptr(dev))
-        ctx.save_for_backward(out, tgt, w if w is not None else torch.empty(0, device=dev))
-        ctx.has_w = w is not None
+        ctx.save_for_backward(out, tgt, w)
         ctx.reduction = reduction
         return mean if reduction == "mean" else per_map
 
     @staticmethod
     def backward(ctx, grad_out):
         out, tgt, w = ctx.saved_tensors
-        w = w if ctx.has_w else None
         B, K, H, W = out.shape
         dev = out.device
         go = grad_out.detach().to(torch.float32).contiguous()
         kind = _lib.GRAD_SCALAR if ctx.reduction == "mean" else _lib.GRAD_PER_MAP
         grad_in = torch.empty_like(out)
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             _lib.call("hp_mse_bwd", _lib.ptr(out), _lib.ptr(tgt), _lib.ptr(w), _lib.ptr(go), kind, B, K, H * W,
                       _lib.ptr(grad_in), _lib.stream_ptr(dev))
         return grad_in, None, None, None
@@ -73,13 +84,12 @@ class _KL(torch.autograd.Function):
         stats = torch.empty((B * K, 2), dtype=torch.float32, device=dev)
         mean = torch.empty((), dtype=torch.float32, device=dev) if reduction == "mean" else None
         per_sample = torch.empty((B,), dtype=torch.float32, device=dev) if reduction == "none" else None
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             ws = _lib.workspace(dev, B * K, K)
             _lib.call("hp_kl_fwd", _lib.ptr(out), _lib.ptr(tgt), _lib.ptr(w), C.c_float(epsilon), B, K, H * W,
                       _lib.ptr(per_map), _lib.ptr(per_sample), _lib.ptr(mean), _lib.ptr(stats), _lib.ptr(ws),
                       _lib.stream_ptr(dev))
-        ctx.save_for_backward(out, tgt, w if w is not None else torch.empty(0, device=dev), stats)
-        ctx.has_w = w is not None
+        ctx.save_for_backward(out, tgt, w, stats)
         ctx.reduction = reduction
         ctx.epsilon = float(epsilon)
         return mean if reduction == "mean" else per_sample
@@ -87,13 +97,12 @@ class _KL(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out):
         out, tgt, w, stats = ctx.saved_tensors
-        w = w if ctx.has_w else None
         B, K, H, W = out.shape
         dev = out.device
         go = grad_out.detach().to(torch.float32).contiguous()
         kind = _lib.GRAD_SCALAR if ctx.reduction == "mean" else _lib.GRAD_PER_SAMPLE
         grad_in = torch.empty_like(out)
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             _lib.call("hp_kl_bwd", _lib.ptr(out), _lib.ptr(tgt), _lib.ptr(w), C.c_float(ctx.epsilon), _lib.ptr(stats),
                       _lib.ptr(go), kind, B, K, H * W, _lib.ptr(grad_in), _lib.stream_ptr(dev))
         return grad_in, None, None, None, None
@@ -110,6 +119,8 @@ class JointsMSELoss(nn.Module):
     def forward(self, output, target, target_weight=None):
         if self.reduction not in ("mean", "none"):
             return None                       # the reference falls off the if/elif (loss.py:62-65)
+        if not _wants_grad(output):
+            return _MSE.forward(_NoCtx(), output, target, target_weight, self.reduction)
         return _MSE.apply(output, target, target_weight, self.reduction)
 
 
@@ -126,4 +137,6 @@ class JointsKLLoss(nn.Module):
     def forward(self, output, target, target_weight=None):
         if self.reduction not in ("mean", "none"):
             return None
+        if not _wants_grad(output):
+            return _KL.forward(_NoCtx(), output, target, target_weight, self.reduction, float(self.epsilon))
         return _KL.apply(output, target, target_weight, self.reduction, float(self.epsilon))

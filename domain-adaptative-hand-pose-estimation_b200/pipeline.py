@@ -88,7 +88,7 @@ class HeatmapPipeline:
             self.loss_mask |= _LOSS_BITS[name]
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.group = group
-        with torch.cuda.device(self.device):
+        with _lib.on_device(self.device):
             self.tab = _lib.gaussian_table(sigma, self.tmp, self.device)
         self._host_state = None
         self._ws = None
@@ -178,7 +178,7 @@ class HeatmapPipeline:
         """One zero-initialised workspace per pipeline object (a pipeline is used on one stream at a time)."""
         need = int(_lib.load().hp_workspace_bytes(int(n_maps), self.K))
         if self._ws is None or self._ws.numel() < need:
-            with torch.cuda.device(self.device):
+            with _lib.on_device(self.device):
                 self._ws = torch.zeros(max(need, 1 << 16), dtype=torch.uint8, device=self.device)
         return self._ws
 
@@ -278,7 +278,7 @@ class HeatmapPipeline:
         slab = max(1, min(int(slab), B))
         st = self._host_buffers(B, slab)
         dev = self.device
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             ws = self._workspace(B * K)
             _lib.call("hp_pipeline_fused_host", _lib.ptr(hp), _lib.ptr(hj), _lib.ptr(hv), B, K, H, W,
                       C.c_double(self.stride[0]), C.c_double(self.stride[1]), self.tmp, _lib.ptr(self.tab),
@@ -356,7 +356,7 @@ class MultiscaleEval:
         maxvals = torch.empty((B, K, 1), dtype=torch.float32, device=dev)
         counts = torch.empty((2 * K,), dtype=torch.int32, device=dev)
         acc = torch.empty((K + 2,), dtype=torch.float64, device=dev)
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             ws = _lib.workspace(dev, B * K, K)
             _lib.call("hp_fuse_decode_pck", _lib.ptr(lo), lo.shape[2], lo.shape[3], C.c_float(self.coef[0]),
                       _lib.ptr(mid), mid.shape[2], mid.shape[3], C.c_float(self.coef[1]), _lib.ptr(hi),

@@ -28,7 +28,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .loss import JointsKLLoss
+from .loss import JointsKLLoss, _NoCtx, _wants_grad
 
 _VARIANT_CODE = {"base": _lib.RD_BASE, "x1": _lib.RD_X1, "x5": _lib.RD_X5, "x6": _lib.RD_X6}
 
@@ -72,7 +72,7 @@ class _PLGBase(nn.Module):
         gt = torch.empty((B, K, oh, ow), dtype=torch.float32, device=dev)
         gf = torch.empty_like(gt)
         centres = torch.empty((B * K, 2), dtype=torch.int32, device=dev)
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             tab = _lib.gaussian_table(self.sigma, tmp, dev)
             _lib.call("hp_pseudo_label", _lib.ptr(y), B, K, H, W, kind, oh, ow, shift, tmp, _lib.ptr(tab), _lib.ptr(gt),
                       _lib.ptr(gf), _lib.ptr(centres), _lib.stream_ptr(dev))
@@ -126,7 +126,7 @@ class _RegDisp(torch.autograd.Function):
         centres = torch.empty((B * K, 2), dtype=torch.int32, device=dev)
         mean = torch.empty((), dtype=torch.float32, device=dev) if reduction == "mean" else None
         per_sample = torch.empty((B,), dtype=torch.float32, device=dev) if reduction == "none" else None
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             tab = _lib.gaussian_table(plg.sigma, tmp, dev)
             ws = _lib.workspace(dev, B * K, K)
             _lib.call("hp_regdisp_fwd", _lib.ptr(yd), _lib.ptr(adv), _lib.ptr(fz), _lib.ptr(w), variant, mode,
@@ -147,7 +147,7 @@ class _RegDisp(torch.autograd.Function):
         go = grad_out.detach().to(torch.float32).contiguous()
         kind = _lib.GRAD_SCALAR if reduction == "mean" else _lib.GRAD_PER_SAMPLE
         grad_in = torch.empty_like(adv)
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             _lib.call("hp_regdisp_bwd", _lib.ptr(adv), _lib.ptr(ctx.fz), _lib.ptr(ctx.w), variant, mode, C.c_float(eps),
                       B, K, oh, ow, tmp, _lib.ptr(tab), _lib.ptr(centres), _lib.ptr(stats), _lib.ptr(go), kind,
                       _lib.ptr(grad_in), _lib.stream_ptr(dev))
@@ -178,7 +178,7 @@ class _RDBase(nn.Module):
             dev = centres.device
             gt = torch.empty((B, K, oh, ow), dtype=torch.float32, device=dev)
             gf = torch.empty_like(gt)
-            with torch.cuda.device(dev):
+            with _lib.on_device(dev):
                 _lib.call("hp_regdisp_materialize", _lib.ptr(fused), variant, B, K, oh, ow, tmp, _lib.ptr(tab),
                           _lib.ptr(centres), _lib.ptr(gt), _lib.ptr(gf), _lib.stream_ptr(dev))
             self._gt, self._gf = gt, gf
@@ -202,8 +202,10 @@ class _RDBase(nn.Module):
         mode_code = _lib.MODE_MIN if mode == "min" else _lib.MODE_MAX
         crit = self.criterion
         if isinstance(crit, JointsKLLoss) and crit.reduction in ("mean", "none"):
-            return _RegDisp.apply(y_adv, y, y_adv2, weight, variant, mode_code, float(crit.epsilon), crit.reduction,
-                                  plg, self)
+            args = (y_adv, y, y_adv2, weight, variant, mode_code, float(crit.epsilon), crit.reduction, plg, self)
+            if not _wants_grad(y_adv):
+                return _RegDisp.forward(_NoCtx(), *args)
+            return _RegDisp.apply(*args)
         # foreign criterion: materialise the maps on the GPU and call it like the reference does
         from .keypoint_detection import decode
         yd, (B, K, H, W), (oh, ow, shift, tmp, _) = plg._check_input(y)
@@ -211,7 +213,7 @@ class _RDBase(nn.Module):
         fz = None if y_adv2 is None else _lib.require_cuda(y_adv2.detach(), "y_adv2")
         preds, _ = decode(yd)
         centres = (preds.reshape(-1, 2).to(torch.int32) >> shift).contiguous()
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             tab = _lib.gaussian_table(plg.sigma, tmp, dev)
         self._remember(variant, fz, centres, tab, (B, K, oh, ow, tmp))
         gt, gf = self._materialise()

@@ -37,7 +37,7 @@ def generate_target_batch(joints, joints_vis, heatmap_size, sigma, image_size, d
     stride = np.array(image_size) / np.array(heatmap_size)              # util.py:36 (float64)
     target = torch.empty((B, K, H, W), dtype=torch.float32, device=device)
     weight = torch.empty((B, K, 1), dtype=torch.float32, device=device)
-    with torch.cuda.device(device):
+    with _lib.on_device(device):
         tab = _lib.gaussian_table(sigma, tmp, device)
         _lib.call("hp_gaussian_target", _lib.ptr(j), _lib.ptr(v), B * K, H, W, C.c_double(float(stride[0])),
                   C.c_double(float(stride[1])), tmp, _lib.ptr(tab), _lib.ptr(target), _lib.ptr(weight),
