@@ -127,8 +127,13 @@ __device__ __forceinline__ float rds_norm(float g, float M, bool divide) { retur
 // NT consumer threads + one producer warp per block, NV float4 per consumer thread and map (NT * NV * 4 == oh * ow),
 // 512 / NT blocks per SM.  DENSE: the target outside the own patch depends on the pixel (x6 / base 'max', fused map);
 // otherwise it is a constant there ('min': 0; x1 / x5 'max': 1) and the sums over those pixels are closed forms.
+// blocks per SM: the sparse recipes are light in registers and take a third block of 256 threads (the kernels are
+// issue-latency bound: more resident warps, not more bytes in flight, is what they lack)
+template <int NT, bool DENSE>
+constexpr int rds_blocks_per_sm() { return (NT == 256 && !DENSE) ? 3 : 512 / NT; }
+
 template <int NT, int NV, int TASK, bool DENSE, bool FUSED>
-__global__ void __launch_bounds__(NT + 32, 512 / NT) regdisp_staged_kernel(const RDArgs a, const int kst) {
+__global__ void __launch_bounds__(NT + 32, rds_blocks_per_sm<NT, DENSE>()) regdisp_staged_kernel(const RDArgs a, const int kst) {
     extern __shared__ __align__(128) unsigned char s_rds[];
     __shared__ RDSShared<NT> sh;
     constexpr int NW = NT / 32;
@@ -467,7 +472,7 @@ __global__ void __launch_bounds__(NT + 32, 512 / NT) regdisp_staged_kernel(const
 // (the caller then takes the guarded generic kernel), 0 when launched, < 0 / > 0 on errors.
 template <int NT, int NV, int TASK, bool DENSE, bool FUSED>
 static int launch_rds_shape(const RDArgs& a, int sms, cudaStream_t stream, const char* who) {
-    constexpr int BPS = 512 / NT;
+    constexpr int BPS = rds_blocks_per_sm<NT, DENSE>();
     const size_t stage = static_cast<size_t>(FUSED ? 2 : 1) * NT * NV * 16;
     const size_t tab = ((table_bytes(a.tmp) + 15) / 16) * 16;
     const size_t budget = (227 * 1024) / BPS - 1024 - sizeof(RDSShared<NT>) - 256;

@@ -21,7 +21,7 @@ for r in csv.reader(io.StringIO(sass)):
     if r and r[0] == "Kernel Name": cur = {'rows': []}; blocks.append(cur); continue
     if r and r[0] == "Address": cur['hdr'] = r; continue
     if cur is not None and len(r) > 5: cur['rows'].append(r)
-b = blocks[0]; h = b['hdr']; iA = h.index('Address'); iI = h.index('Instructions Executed'); iS = h.index('# Samples')
+b = blocks[int(os.environ.get("NCU_BLOCK", "0"))]; h = b['hdr']; iA = h.index('Address'); iI = h.index('Instructions Executed'); iS = h.index('# Samples')
 base = int(b['rows'][0][iA], 16)
 agg = collections.Counter(); smp = collections.Counter(); ops = collections.defaultdict(collections.Counter)
 for r in b['rows']:
