@@ -136,7 +136,10 @@ def ptr(t):
 
 
 def stream_ptr(device=None):
-    return torch.cuda.current_stream(device).cuda_stream
+    """Raw handle of PyTorch's current stream on ``device`` (one C call; ``torch.cuda.current_stream`` builds a
+    Stream object and costs several microseconds per launch)."""
+    idx = device.index if device is not None and device.index is not None else torch.cuda.current_device()
+    return torch._C._cuda_getCurrentRawStream(idx)
 
 
 class on_device:
@@ -189,8 +192,8 @@ def workspace(device: torch.device, n_maps: int, K: int) -> torch.Tensor:
     if _ws_need is None:
         _ws_need = int(load().hp_workspace_bytes(int(n_maps), int(K)))   # a constant of the library (header + slack)
     need = _ws_need
-    key = (device.index if device.index is not None else torch.cuda.current_device(),
-           torch.cuda.current_stream(device).cuda_stream)
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    key = (idx, torch._C._cuda_getCurrentRawStream(idx))
     ws = _ws_cache.get(key)
     if ws is None or ws.numel() < need:
         ws = torch.zeros(max(need, 1 << 16), dtype=torch.uint8, device=device)
