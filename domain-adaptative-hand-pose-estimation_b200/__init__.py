@@ -36,7 +36,7 @@ _LAZY = {
     "RegressionDisparity": "regda", "RegressionDisparityx1": "regda",
     "RegressionDisparityx5": "regda", "RegressionDisparityx6": "regda",
     "generate_target": "target", "generate_target_batch": "target",
-    "fuse_multiscale": "fusion", "fuse_three_scales": "fusion",
+    "fuse_multiscale": "fusion", "fuse_three_scales": "fusion", "upsample_bilinear": "fusion",
     "HeatmapPipeline": "pipeline", "PipelineResult": "pipeline",
     "MultiscaleEval": "pipeline",
 }

@@ -9,6 +9,8 @@
 // 4-tap gathers from the small maps (L1-resident: 1-16 KB per map) and the blend happen in
 // registers and the fused map is written once - or, for hp_fuse_decode_pck, never written.
 // Roofline: HBM.  Bytes per map: sum of the source maps read [+ H*W*4 written].
+#include <cstdlib>
+
 #include "hp_common.cuh"
 #include "hp_decode.cuh"
 #include "hp_dispatch.cuh"
@@ -620,6 +622,16 @@ static bool staged_geometry(const FuseSrc& f, const float* out, RowWalk& g, size
     return smem <= 48 * 1024;  // 4 blocks per SM
 }
 
+}  // namespace hp
+#include "hp_fusion_block.cuh"
+namespace hp {
+
+// HP_FUSE_SHAPE=r forces the row-walking kernels (A/B comparisons; the block kernel is the default for exact scales)
+static bool fuse_rows_forced() {
+    const char* e = getenv("HP_FUSE_SHAPE");
+    return e != nullptr && e[0] == 'r';
+}
+
 struct FuseDecodeLaunch {
     FuseSrc f;
     const float* tgt_xy;
@@ -669,6 +681,16 @@ extern "C" HP_API int hp_fuse_multiscale(const float* lo, int hl, int wl, float 
     HP_REQUIRE(n_maps >= 0, HP_ERR_SHAPE, "hp_fuse_multiscale: n_maps=%d", n_maps);
     if (n_maps == 0) return HP_OK;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    {
+        BlockWalk bg;
+        int sl = 0, sm = 0, n_warps = 0;
+        size_t smem = 0;
+        if (!fuse_rows_forced() && block_geometry(f, out, bg, sl, sm, n_warps, smem)) {
+            launch_fuse_block<false>(f, bg, sl, sm, n_warps, smem, n_maps, out, nullptr, 0, 0.0, nullptr, nullptr, nullptr, nullptr,
+                                     nullptr, s);
+            return launch_status("hp_fuse_multiscale");
+        }
+    }
     RowWalk g;
     size_t staged_smem = 0;
     if (staged_geometry(f, out, g, staged_smem)) {
@@ -700,6 +722,16 @@ extern "C" HP_API int hp_fuse_decode_pck(const float* lo, int hl, int wl, float 
     if (int rc = make_src("hp_fuse_decode_pck", lo, hl, wl, a_lo, mid, hm, wm, a_mid, hi, a_hi, H, W, f)) return rc;
     HP_REQUIRE(tgt_xy && pred_xy && acc_out && workspace, HP_ERR_NULL, "hp_fuse_decode_pck: null pointer");
     HP_REQUIRE(B > 0 && K > 0 && K <= HP_MAX_K, HP_ERR_SHAPE, "hp_fuse_decode_pck: bad B=%d K=%d", B, K);
+    {
+        BlockWalk bg;
+        int sl = 0, sm = 0, n_warps = 0;
+        size_t smem = 0;
+        if (!fuse_rows_forced() && block_geometry(f, nullptr, bg, sl, sm, n_warps, smem)) {
+            launch_fuse_block<true>(f, bg, sl, sm, n_warps, smem, B * K, nullptr, tgt_xy, K, thr, pred_xy, maxvals, counts, acc_out,
+                                    static_cast<Workspace*>(workspace), static_cast<cudaStream_t>(stream));
+            return launch_status("hp_fuse_decode_pck");
+        }
+    }
     RowWalk g;
     size_t staged_smem = 0;
     if (staged_geometry(f, nullptr, g, staged_smem)) {

@@ -1,0 +1,424 @@
+// hp_fusion_block.cuh - multiscale fusion for the EXACT x2 / x4 scales (train1.py:410-424: 16 -> 64, 32 -> 64, 16 -> 32;
+// BASELINE.json configs[3]: 32 / 64 / 128), the production shape of hp_fuse_multiscale and hp_fuse_decode_pck.
+//
+// nn.Upsample(mode='bilinear') is align_corners=False: src = scale*(dst+0.5)-0.5 clamped at 0.  At an integer factor S
+// the taps of four consecutive outputs 4m..4m+3 are a STATIC pattern over three (S=4) or four (S=2) consecutive source
+// positions with constant weights; only the first block of an axis (clamp at 0: weights (1, 0), taps (0, 1)) and the
+// last one (second tap clamped to in-1) differ, and both fit the pattern with one select and two clamped offsets:
+//   S=2: sources A=max(2m-1,0) B=2m C=2m+1 D=min(2m+2,in-1);  outputs (A,B') (B,C) (B,C) (C,D), l1 = .75 .25 .75 .25
+//   S=4: sources A=max(m-1,0)  B=m  C=min(m+1,in-1);          outputs (A,B') (A,B') (B,C) (B,C), l1 = .625 .875 .125 .375
+//   B' = B, except in the first block where the clamp makes the taps (0, 1): B' = C (S=2: index 1 = 2m+1; S=4: m+1)
+//   and the weights of the clamped outputs (1, 0).
+// So a lane owns a column of 4x4 output blocks: per block it interpolates the two / one NEW source rows horizontally
+// (the others are carried in registers from the block above), blends vertically with immediate weights and streams
+// its four float4 of `hi` - no cached-row bookkeeping, no tap table, ~40 instructions per output float4 instead of
+// ~150 (the row-walking kernels in hp_fusion.cu, which remain the path for every other geometry and serve the
+// NaN rescan here).  Arithmetic and operation order are those of fused_row4 (fmul + ffma horizontally, fmul + ffma
+// vertically, fmul / ffma / ffma over the sources), so the results are bit-identical to the row-walking kernels.
+// The low-resolution maps are staged in shared memory by the copy engine, double-buffered per block, exactly as in
+// fuse_staged_kernel (ticket hand-over, no block barrier in the loop).
+#pragma once
+
+namespace hp {
+
+__device__ __forceinline__ float2 lds_f32x2(uint32_t addr) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+    return v;
+}
+
+template <int S>
+struct BlockAxis {           // one axis of one source as seen by a lane / a block row
+    float2 l0a, l1a;         // weights of outputs 0, 1 (first-block clamp folded in)
+    float2 l0b, l1b;         // weights of outputs 2, 3
+    bool first;
+};
+template <int S>
+__device__ __forceinline__ BlockAxis<S> block_axis(int m) {
+    BlockAxis<S> ax;
+    ax.first = (m == 0);
+    if (S == 2) {
+        ax.l1a = make_float2(ax.first ? 0.0f : 0.75f, 0.25f);
+        ax.l1b = make_float2(0.75f, 0.25f);
+    } else {
+        ax.l1a = ax.first ? make_float2(0.0f, 0.0f) : make_float2(0.625f, 0.875f);
+        ax.l1b = make_float2(0.125f, 0.375f);
+    }
+    ax.l0a = make_float2(1.0f - ax.l1a.x, 1.0f - ax.l1a.y);
+    ax.l0b = make_float2(1.0f - ax.l1b.x, 1.0f - ax.l1b.y);
+    return ax;
+}
+// debug guard: the pattern above must reproduce make_tap for outputs 4m..4m+3 (exact in fp32 for S in {2, 4})
+template <int S>
+__device__ __forceinline__ bool block_axis_matches(int m, int in_size) {
+    const BlockAxis<S> ax = block_axis<S>(m);
+    const float l1[4] = {ax.l1a.x, ax.l1a.y, ax.l1b.x, ax.l1b.y};
+    bool ok = true;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const Tap t = make_tap(4 * m + c, 1.0f / static_cast<float>(S), in_size, in_size * S);
+        int i0, i1;
+        if (S == 2) {
+            const int A = max(2 * m - 1, 0), B = 2 * m, Cc = 2 * m + 1, D = min(2 * m + 2, in_size - 1);
+            i0 = c == 0 ? A : (c == 3 ? Cc : B);
+            i1 = c == 0 ? (m == 0 ? Cc : B) : (c == 3 ? D : Cc);
+        } else {
+            const int A = max(m - 1, 0), B = m, Cc = min(m + 1, in_size - 1);
+            i0 = c < 2 ? A : B;
+            i1 = c < 2 ? (m == 0 ? Cc : B) : Cc;
+        }
+        ok = ok && t.i0 == i0 && t.i1 == i1 && t.l1 == l1[c] && t.l0 == 1.0f - l1[c];
+    }
+    return ok;
+}
+
+// byte offsets of a lane's distinct source columns inside a source row
+template <int S>
+struct BlockCols {
+    uint32_t a, b, d;  // S=2: A, (B,C) as one 8-byte load, D;  S=4: A, B, C (d)
+};
+template <int S>
+__device__ __forceinline__ BlockCols<S> block_cols(int n, int w) {
+    BlockCols<S> c;
+    if (S == 2) {
+        c.a = 4u * static_cast<uint32_t>(max(2 * n - 1, 0));
+        c.b = 8u * static_cast<uint32_t>(n);
+        c.d = 4u * static_cast<uint32_t>(min(2 * n + 2, w - 1));
+    } else {
+        c.a = 4u * static_cast<uint32_t>(max(n - 1, 0));
+        c.b = 4u * static_cast<uint32_t>(n);
+        c.d = 4u * static_cast<uint32_t>(min(n + 1, w - 1));
+    }
+    return c;
+}
+// one source row (shared-memory byte address) interpolated to the lane's four output columns
+template <int S>
+__device__ __forceinline__ void block_hrow(uint32_t row, const BlockCols<S>& c, const BlockAxis<S>& ax, float2 (&t)[2]) {
+    float2 a01, b01, a23, b23;
+    if (S == 2) {
+        const float vA = lds_f32(row + c.a);
+        const float2 vBC = lds_f32x2(row + c.b);
+        const float vD = lds_f32(row + c.d);
+        a01 = make_float2(vA, vBC.x);
+        b01 = make_float2(ax.first ? vBC.y : vBC.x, vBC.y);
+        a23 = make_float2(vBC.x, vBC.y);
+        b23 = make_float2(vBC.y, vD);
+    } else {
+        const float vA = lds_f32(row + c.a), vB = lds_f32(row + c.b), vC = lds_f32(row + c.d);
+        const float dup = ax.first ? vC : vB;
+        a01 = make_float2(vA, vA);
+        b01 = make_float2(dup, dup);
+        a23 = make_float2(vB, vB);
+        b23 = make_float2(vC, vC);
+    }
+    t[0] = __ffma2_rn(ax.l1a, b01, __fmul2_rn(ax.l0a, a01));
+    t[1] = __ffma2_rn(ax.l1b, b23, __fmul2_rn(ax.l0b, a23));
+}
+
+// the interpolated source rows a lane carries down its column of blocks, and the vertical blend of a block
+template <int S>
+struct BlockRows {
+    float2 A[2], B[2], C[2], D[2];  // D unused for S=4
+};
+template <int S>
+__device__ __forceinline__ void block_rows_start(BlockRows<S>& R, uint32_t base, int w, int in_h, int m, const BlockCols<S>& c,
+                                                 const BlockAxis<S>& ax) {
+    const uint32_t stride = 4u * static_cast<uint32_t>(w);
+    if (S == 2) {
+        block_hrow<S>(base + stride * static_cast<uint32_t>(max(2 * m - 1, 0)), c, ax, R.A);
+        block_hrow<S>(base + stride * static_cast<uint32_t>(2 * m), c, ax, R.B);
+    } else {
+        block_hrow<S>(base + stride * static_cast<uint32_t>(max(m - 1, 0)), c, ax, R.A);
+        block_hrow<S>(base + stride * static_cast<uint32_t>(m), c, ax, R.B);
+    }
+    (void)in_h;
+}
+// block m: load the new rows, produce the four blended output rows v[r][0..1] (columns (0,1), (2,3))
+template <int S>
+__device__ __forceinline__ void block_rows_blend(BlockRows<S>& R, uint32_t base, int w, int in_h, int m, const BlockCols<S>& c,
+                                                 const BlockAxis<S>& ax, float2 (&v)[4][2]) {
+    const uint32_t stride = 4u * static_cast<uint32_t>(w);
+    const bool first = (m == 0);
+    if (S == 2) {
+        block_hrow<S>(base + stride * static_cast<uint32_t>(2 * m + 1), c, ax, R.C);
+        block_hrow<S>(base + stride * static_cast<uint32_t>(min(2 * m + 2, in_h - 1)), c, ax, R.D);
+        const float l1r0 = first ? 0.0f : 0.75f, l0r0 = 1.0f - l1r0;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const float2 dup = first ? R.C[h] : R.B[h];
+            v[0][h] = __ffma2_rn(make_float2(l1r0, l1r0), dup, __fmul2_rn(make_float2(l0r0, l0r0), R.A[h]));
+            v[1][h] = __ffma2_rn(make_float2(0.25f, 0.25f), R.C[h], __fmul2_rn(make_float2(0.75f, 0.75f), R.B[h]));
+            v[2][h] = __ffma2_rn(make_float2(0.75f, 0.75f), R.C[h], __fmul2_rn(make_float2(0.25f, 0.25f), R.B[h]));
+            v[3][h] = __ffma2_rn(make_float2(0.25f, 0.25f), R.D[h], __fmul2_rn(make_float2(0.75f, 0.75f), R.C[h]));
+            R.A[h] = R.C[h];  // carried into block m + 1
+            R.B[h] = R.D[h];
+        }
+    } else {
+        block_hrow<S>(base + stride * static_cast<uint32_t>(min(m + 1, in_h - 1)), c, ax, R.C);
+        const float l1r0 = first ? 0.0f : 0.625f, l1r1 = first ? 0.0f : 0.875f;
+        const float l0r0 = 1.0f - l1r0, l0r1 = 1.0f - l1r1;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const float2 dup = first ? R.C[h] : R.B[h];
+            v[0][h] = __ffma2_rn(make_float2(l1r0, l1r0), dup, __fmul2_rn(make_float2(l0r0, l0r0), R.A[h]));
+            v[1][h] = __ffma2_rn(make_float2(l1r1, l1r1), dup, __fmul2_rn(make_float2(l0r1, l0r1), R.A[h]));
+            v[2][h] = __ffma2_rn(make_float2(0.125f, 0.125f), R.C[h], __fmul2_rn(make_float2(0.875f, 0.875f), R.B[h]));
+            v[3][h] = __ffma2_rn(make_float2(0.375f, 0.375f), R.C[h], __fmul2_rn(make_float2(0.625f, 0.625f), R.B[h]));
+            R.A[h] = R.B[h];
+            R.B[h] = R.C[h];
+        }
+    }
+}
+
+struct BlockWalk {
+    int cb;     // 4-column blocks per output row (W / 4)
+    int rps;    // block rows walked side by side by one warp (32 / cb)
+    int strip;  // consecutive block rows per lane
+};
+
+// the whole-map NaN rescan of the closing warp (rare): the row-walking code with numpy's exact argmax rules
+static __device__ __noinline__ ArgMax block_nan_rescan(const FuseSrc& f, uint32_t lo_s, uint32_t mid_s, const RowTap* s_rows,
+                                                       const float* hi_map, int lane) {
+    const int cpr = f.W / 4, rps = 32 / cpr;
+    const int x0 = (lane % cpr) * 4, ro = lane / cpr;
+    RowSource lo, mid;
+    row_source_init(lo, x0, f.sx_lo, f.wl, f.W);
+    row_source_init(mid, x0, f.mid ? f.sx_mid : 1.0f, f.mid ? f.wm : f.W, f.W);
+    lo.base_s = lo_s;
+    mid.base_s = mid_s;
+    ArgMax sx = am_init();
+    for (int r = ro; r < f.H; r += rps) {
+        const float4 hb = hi_map ? ldg_stream4(reinterpret_cast<const float4*>(hi_map + r * f.W + x0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        am_scan4<true>(sx, fused_row4<true>(f, lo, mid, s_rows, r, hb), r * f.W + x0);
+    }
+    return warp_argmax_rows(sx, lane);
+}
+
+constexpr int kBlockMaxWarps = 4;
+struct BlockCtl {
+    unsigned long long full[2];  // mbarriers: sources of buffer b have landed
+    int done[2];                 // warps that have finished the map in buffer b
+    int nan[2];
+    int bad_geometry;
+    ArgMax am[2][kBlockMaxWarps];
+};
+
+// SL: scale of `lo` (2 or 4);  SM: scale of `mid` (2, or 0 = no mid source)
+template <int SL, int SM, bool DECODE>
+__global__ void __launch_bounds__(32 * kBlockMaxWarps, 4)
+    fuse_block_kernel(const FuseSrc f, const BlockWalk g, int n_maps, float* __restrict__ out, const float* __restrict__ tgt_xy,
+                      int K, double thr, float* __restrict__ pred_xy, float* __restrict__ maxvals,
+                      int32_t* __restrict__ counts_out, double* __restrict__ acc_out, Workspace* __restrict__ ws) {
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    __shared__ BlockCtl ctl;
+    constexpr int SMX = SM == 0 ? 2 : SM;  // (template argument of the unused mid helpers)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
+    const int HW = f.H * f.W;
+    const int lo_elems = f.hl * f.wl, mid_elems = SM ? f.hm * f.wm : 0;
+    const uint32_t lo_bytes = 4u * lo_elems, mid_bytes = 4u * mid_elems, buf_bytes = lo_bytes + mid_bytes;
+    RowTap* s_rows = reinterpret_cast<RowTap*>(s_raw + 2 * static_cast<size_t>(buf_bytes));  // NaN rescan only
+    const int n_local = (n_maps - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+    const uint32_t full_u32 = smem_addr(&ctl.full[0]), src_u32 = smem_addr(s_raw);
+    const uint64_t pol = l2_evict_first_policy();
+
+    auto request = [&](int j) {  // one thread: sources of the block's j-th map -> buffer j & 1
+        const int b = j & 1;
+        const size_t map = static_cast<size_t>(blockIdx.x) + static_cast<size_t>(j) * gridDim.x;
+        mbar_arrive_expect_tx(full_u32 + 8 * b, buf_bytes);
+        bulk_load(src_u32 + b * buf_bytes, f.lo + map * lo_elems, lo_bytes, full_u32 + 8 * b, pol);
+        if (SM) bulk_load(src_u32 + b * buf_bytes + lo_bytes, f.mid + map * mid_elems, mid_bytes, full_u32 + 8 * b, pol);
+    };
+    if (threadIdx.x == 0) {
+        mbar_init(full_u32, 1);
+        mbar_init(full_u32 + 8, 1);
+        mbar_init_fence();
+        ctl.done[0] = ctl.done[1] = 0;
+        ctl.nan[0] = ctl.nan[1] = 0;
+        ctl.bad_geometry = 0;
+        if (n_local > 0) request(0);
+        if (n_local > 1) request(1);
+    }
+    if (DECODE) {
+        for (int r = threadIdx.x; r < f.H; r += blockDim.x) {
+            const Tap tl = make_tap(r, f.sy_lo, f.hl, f.H);
+            s_rows[r] = RowTap{tl.i0, tl.i1, tl.l0, tl.l1};
+            if (SM) {
+                const Tap tm = make_tap(r, f.sy_mid, f.hm, f.H);
+                s_rows[f.H + r] = RowTap{tm.i0, tm.i1, tm.l0, tm.l1};
+            }
+        }
+    }
+    // this lane: column block n, block rows [m_begin, m_end)
+    const int n = lane % g.cb, sub = lane / g.cb;
+    const int m_begin = (warp * g.rps + sub) * g.strip, m_end = m_begin + g.strip;
+    const int x0 = 4 * n;
+    const BlockAxis<SL> lo_x = block_axis<SL>(n);
+    const BlockCols<SL> lo_c = block_cols<SL>(n, f.wl);
+    const BlockAxis<SMX> mid_x = block_axis<SMX>(n);
+    const BlockCols<SMX> mid_c = block_cols<SMX>(n, SM ? f.wm : 2);
+    __syncthreads();  // the only block barrier: control block (and tap table) are set up
+    {
+        bool ok = block_axis_matches<SL>(n, f.wl);
+        if (SM) ok = ok && block_axis_matches<SMX>(n, f.wm);
+        for (int m = m_begin; m < m_end; ++m) {
+            ok = ok && block_axis_matches<SL>(m, f.hl);
+            if (SM) ok = ok && block_axis_matches<SMX>(m, f.hm);
+        }
+        if (!ok) __trap();  // the host only selects this kernel for exact scales; never silently wrong
+    }
+
+    const float2 al = make_float2(f.a_lo, f.a_lo), am2 = make_float2(f.a_mid, f.a_mid), ah = make_float2(f.a_hi, f.a_hi);
+    for (int j = 0; j < n_local; ++j) {
+        const int b = j & 1;
+        const int map = static_cast<int>(blockIdx.x) + j * static_cast<int>(gridDim.x);
+        const uint32_t lo_s = src_u32 + b * buf_bytes, mid_s = lo_s + lo_bytes;
+        const float* hi = f.hi ? f.hi + static_cast<size_t>(map) * HW + x0 : nullptr;
+        float* o = DECODE ? nullptr : out + static_cast<size_t>(map) * HW + x0;
+        float best = -INFINITY;
+        float2 witness = make_float2(0.f, 0.f);
+        int best_idx = 4 * m_begin * f.W + x0;  // (an all -inf map decodes to its first element)
+        float4 h[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)  // the first rows of the HBM stream are requested before the sources are awaited
+            h[u] = hi ? ldg_stream4(reinterpret_cast<const float4*>(hi + (4 * m_begin + u) * f.W)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        mbar_wait(full_u32 + 8 * b, static_cast<uint32_t>(j >> 1) & 1u);
+        BlockRows<SL> RL;
+        BlockRows<SMX> RM;
+        block_rows_start<SL>(RL, lo_s, f.wl, f.hl, m_begin, lo_c, lo_x);
+        if (SM) block_rows_start<SMX>(RM, mid_s, f.wm, f.hm, m_begin, mid_c, mid_x);
+        for (int m = m_begin; m < m_end; ++m) {
+            float4 hn[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)  // the next block's rows in flight while this block is blended
+                hn[u] = (hi && m + 1 < m_end) ? ldg_stream4(reinterpret_cast<const float4*>(hi + (4 * (m + 1) + u) * f.W))
+                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+            float2 vl[4][2], vm[4][2];
+            block_rows_blend<SL>(RL, lo_s, f.wl, f.hl, m, lo_c, lo_x, vl);
+            if (SM) block_rows_blend<SMX>(RM, mid_s, f.wm, f.hm, m, mid_c, mid_x, vm);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                float2 r0 = __fmul2_rn(al, vl[u][0]), r1 = __fmul2_rn(al, vl[u][1]);
+                if (SM) {
+                    r0 = __ffma2_rn(am2, vm[u][0], r0);
+                    r1 = __ffma2_rn(am2, vm[u][1], r1);
+                }
+                if (f.hi) {
+                    r0 = __ffma2_rn(ah, make_float2(h[u].x, h[u].y), r0);
+                    r1 = __ffma2_rn(ah, make_float2(h[u].z, h[u].w), r1);
+                }
+                const int row = 4 * m + u;
+                if (DECODE) {
+                    const float m4 = fmaxf(fmaxf(r0.x, r0.y), fmaxf(r1.x, r1.y));
+                    if (m4 > best) {  // strict: the earlier (lower-index) element keeps ties; rare after the first rows
+                        best = m4;
+                        const int comp = (r0.x == m4) ? 0 : ((r0.y == m4) ? 1 : ((r1.x == m4) ? 2 : 3));
+                        best_idx = row * f.W + x0 + comp;
+                    }
+                    witness = __fadd2_rn(witness, __fadd2_rn(r0, r1));  // NaN / inf-inf witness
+                } else {
+                    stg_stream4(reinterpret_cast<float4*>(o + row * f.W), make_float4(r0.x, r0.y, r1.x, r1.y));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) h[u] = hn[u];
+        }
+        ArgMax am = am_init();
+        bool bad = false;
+        if (DECODE) {
+            am.v = best;
+            am.i = best_idx;
+            am = warp_argmax_rows(am, lane);
+            const float w = witness.x + witness.y;
+            bad = __any_sync(0xffffffffu, w != w);
+        }
+        // ---- ticket: the last warp of this map closes it and re-fills the buffer ------------------------------
+        __syncwarp();
+        int last = 0;
+        if (lane == 0) {
+            if (DECODE) {
+                ctl.am[b][warp] = am;
+                if (bad) atomicOr(&ctl.nan[b], 1);
+            }
+            __threadfence_block();
+            last = (atomicAdd(&ctl.done[b], 1) == n_warps - 1) ? 1 : 0;
+            if (last) __threadfence_block();
+        }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last) {
+            if (DECODE) {
+                ArgMax a = ctl.am[b][0];
+                for (int w = 1; w < n_warps; ++w) a = am_merge(a, ctl.am[b][w]);
+                if (*reinterpret_cast<volatile int*>(&ctl.nan[b]))
+                    a = block_nan_rescan(f, lo_s, mid_s, s_rows, f.hi ? f.hi + static_cast<size_t>(map) * HW : nullptr, lane);
+                if (lane == 0) {
+                    float px, py;
+                    decode_xy(a, f.W, px, py);
+                    pred_xy[2 * map + 0] = px;
+                    pred_xy[2 * map + 1] = py;
+                    if (maxvals) maxvals[map] = a.v;
+                    int valid, hit;
+                    pck_one(px, py, tgt_xy[2 * map], tgt_xy[2 * map + 1], f.H, f.W, thr, valid, hit);
+                    const int k = map % K;
+                    if (valid) atomicAdd(&ws->counts[K + k], 1);
+                    if (hit) atomicAdd(&ws->counts[k], 1);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) {
+                ctl.done[b] = 0;
+                ctl.nan[b] = 0;
+                __threadfence_block();
+                if (j + 2 < n_local) request(j + 2);  // every warp has finished reading buffer b
+            }
+        }
+    }
+    if (DECODE) {
+        if (last_block_arrives(&ws->counter, gridDim.x)) pck_publish(ws, K, counts_out, acc_out);
+    }
+}
+
+// block kernel applicable?  exact x2 / x4 scales, W/4 in {8, 16, 32}, bulk-copy alignment, everything fits
+static bool block_geometry(const FuseSrc& f, const float* out, BlockWalk& g, int& sl, int& sm, int& n_warps, size_t& smem) {
+    if (f.W % 4 != 0 || f.H % 4 != 0) return false;
+    const int cb = f.W / 4;
+    if (cb != 8 && cb != 16 && cb != 32) return false;
+    if (f.hl < 2 || f.wl < 2) return false;
+    if (f.hl * 4 == f.H && f.wl * 4 == f.W) sl = 4;
+    else if (f.hl * 2 == f.H && f.wl * 2 == f.W) sl = 2;
+    else return false;
+    sm = 0;
+    if (f.mid) {
+        if (f.hm < 2 || f.wm < 2 || f.hm * 2 != f.H || f.wm * 2 != f.W) return false;
+        sm = 2;
+    }
+    if (f.hi && !aligned16(f.hi)) return false;
+    if (out && !aligned16(out)) return false;
+    const size_t lo_b = 4ull * f.hl * f.wl, mid_b = f.mid ? 4ull * f.hm * f.wm : 0;
+    if (lo_b % 16 != 0 || mid_b % 16 != 0 || !aligned16(f.lo) || (f.mid && !aligned16(f.mid))) return false;
+    g.cb = cb;
+    g.rps = 32 / cb;
+    const int mb = f.H / 4;  // block rows
+    n_warps = mb / g.rps;
+    if (n_warps > kBlockMaxWarps) n_warps = kBlockMaxWarps;
+    if (n_warps < 1 || mb % (n_warps * g.rps) != 0) return false;
+    g.strip = mb / (n_warps * g.rps);
+    smem = 2 * (lo_b + mid_b) + sizeof(RowTap) * 2 * static_cast<size_t>(f.H);
+    return smem <= 48 * 1024;  // 4 blocks per SM
+}
+
+template <bool DECODE>
+static void launch_fuse_block(const FuseSrc& f, const BlockWalk& g, int sl, int sm, int n_warps, size_t smem, int n_maps, float* out,
+                              const float* tgt_xy, int K, double thr, float* pred_xy, float* maxvals, int32_t* counts,
+                              double* acc_out, Workspace* ws, cudaStream_t s) {
+    const int grid = rows_grid(n_maps);
+    const int nt = 32 * n_warps;
+#define HP_FUSE_BLOCK(SL, SM) \
+    fuse_block_kernel<SL, SM, DECODE><<<grid, nt, smem, s>>>(f, g, n_maps, out, tgt_xy, K, thr, pred_xy, maxvals, counts, acc_out, ws)
+    if (sl == 4 && sm == 2) HP_FUSE_BLOCK(4, 2);
+    else if (sl == 4) HP_FUSE_BLOCK(4, 0);
+    else if (sm == 2) HP_FUSE_BLOCK(2, 2);
+    else HP_FUSE_BLOCK(2, 0);
+#undef HP_FUSE_BLOCK
+}
+
+}  // namespace hp

@@ -366,6 +366,52 @@ def test_disparity_long_map_ranges(variant, mode, fused, monkeypatch):
         np.testing.assert_allclose(g_full, g_o, rtol=1e-5, atol=scale, err_msg=what)
 
 
+@pytest.mark.parametrize("sizes", [(16, 32, 64), (32, 64, 128), (8, 16, 32)])
+def test_block_fusion_kernel_equals_row_walking_kernels_bit_for_bit(sizes, monkeypatch):
+    """The static-pattern kernel for exact x2 / x4 scales (hp_fusion_block.cuh) against the row-walking kernels
+    (HP_FUSE_SHAPE=r) and the oracle: materialised maps bit-identical (same arithmetic, incl. the clamped first / last
+    taps where 0 * inf must still be NaN), decoded coordinates and PCK counts identical, on inputs that hold NaN, +inf and
+    -inf, an all -inf map and an exact tie."""
+    lo_s, mid_s, hi_s = sizes
+    B, K = 3, 7
+    rs = np.random.RandomState(4100 + hi_s)
+    hi = rs.standard_normal((B, K, hi_s, hi_s)).astype(np.float32)
+    mid = rs.standard_normal((B, K, mid_s, mid_s)).astype(np.float32)
+    lo = rs.standard_normal((B, K, lo_s, lo_s)).astype(np.float32)
+    lo[0, 1, 1, :] = np.inf                 # 0 * inf at the clamped first row / column
+    mid[0, 2, -1, -1] = -np.inf
+    mid[0, 3, 0, 1] = np.nan
+    hi[1, 0] = -np.inf                      # all -inf map -> element 0
+    lo[1, 0] = 0.0
+    mid[1, 0] = 0.0
+    hi[1, 1], lo[1, 1], mid[1, 1] = 0.0, 0.0, 0.0
+    hi[1, 1, 5, 9] = hi[1, 1, 5, 3] = 2.0   # exact tie -> lower index
+    tgt = rs.randint(0, hi_s, size=(B, K, 2)).astype(np.float32)
+    t = lambda a: torch.from_numpy(a).cuda()
+
+    def run():
+        ev = hp.MultiscaleEval(K)
+        acc, pred_xy, counts = ev(t(lo), t(mid), t(hi), t(tgt))
+        return dict(three=hp.fuse_three_scales(t(lo), t(mid), t(hi)).cpu().numpy(),
+                    two=hp.fuse_multiscale(t(lo), t(mid), hi_s, mid_s)[0].cpu().numpy(),
+                    up2=hp.upsample_bilinear(t(lo), mid_s).cpu().numpy(),
+                    up4=hp.upsample_bilinear(t(lo), hi_s).cpu().numpy(),
+                    pred=pred_xy.cpu().numpy(), counts=counts.cpu().numpy(), acc=acc.cpu().numpy())
+
+    got = run()
+    monkeypatch.setenv("HP_FUSE_SHAPE", "r")
+    ref = run()
+    monkeypatch.delenv("HP_FUSE_SHAPE")
+    for k in got:
+        assert np.array_equal(got[k], ref[k], equal_nan=True), f"{k}: block kernel differs from the row-walking kernel"
+    want = O.fuse_three_scales(torch.from_numpy(lo), torch.from_numpy(mid), torch.from_numpy(hi)).numpy()
+    finite = np.isfinite(want) & np.isfinite(got["three"])
+    assert np.array_equal(np.isnan(want), np.isnan(got["three"]))
+    np.testing.assert_allclose(got["three"][finite], want[finite], rtol=1e-5, atol=1e-6)
+    p_o, _ = O.get_max_preds(got["three"])
+    assert np.array_equal(got["pred"], p_o)
+
+
 def test_foreign_criterion_gets_materialised_maps():
     I = cases.disparity_inputs()
     y, adv, w = (torch.from_numpy(I[k]).cuda() for k in ("y", "adv64", "w"))
