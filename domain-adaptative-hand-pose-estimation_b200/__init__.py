@@ -9,6 +9,7 @@ Public names mirror the reference:
 this package                           reference
 =====================================  ====================================================
 ``get_max_preds``, ``accuracy``        utils/keypoint_detection.py:7-35, 63-92
+``compute_uv_from_heatmaps{,2,3}``     utils/keypoint_detection.py:139-239 (resize+argmax, soft-argmax)
 ``JointsMSELoss``, ``JointsKLLoss``    uda/model/loss.py:27-65, 115-158
 ``PseudoLabelGenerator{,01,02,03}``    uda/model/regda_4.py:17-86, regda_7.py:2956-3201
 ``RegressionDisparity{,x1,x5,x6}``     uda/model/regda_4.py:89-143, regda_7.py:3206-3632
@@ -30,6 +31,8 @@ __version__ = "0.1.0"
 _LAZY = {
     "get_max_preds": "keypoint_detection", "accuracy": "keypoint_detection",
     "decode": "keypoint_detection", "pck": "keypoint_detection",
+    "find_keypoints_max": "keypoint_detection", "compute_uv_from_heatmaps": "keypoint_detection",
+    "compute_uv_from_heatmaps2": "keypoint_detection", "compute_uv_from_heatmaps3": "keypoint_detection",
     "JointsMSELoss": "loss", "JointsKLLoss": "loss",
     "PseudoLabelGenerator": "regda", "PseudoLabelGenerator01": "regda",
     "PseudoLabelGenerator02": "regda", "PseudoLabelGenerator03": "regda",

@@ -47,6 +47,7 @@ PROTOTYPES = {
     "hp_device_sm_count": (_i, []),
     "hp_workspace_bytes": (_sz, [_i, _i]),
     "hp_argmax_decode": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "hp_soft_argmax": (_i, [_vp, _i, _i, _i, _f, _f, _vp, _vp]),
     "hp_pck_accumulate": (_i, [_vp, _vp, _i, _i, _i, _i, _d, _vp, _vp]),
     "hp_pck_finalize": (_i, [_vp, _i, _vp, _vp]),
     "hp_accuracy": (_i, [_vp, _vp, _i, _i, _i, _i, _d, _vp, _vp, _vp, _vp, _vp]),

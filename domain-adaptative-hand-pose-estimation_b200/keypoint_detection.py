@@ -102,3 +102,76 @@ def accuracy(output, target, hm_type="gaussian", thr=0.5):
     avg_acc = float(host[K]) if cnt != 0 else 0
     pred = pred_xy.cpu().numpy() if was_numpy else pred_xy
     return acc, avg_acc, cnt, pred
+
+
+# ------------------------------------------------------------------------------------------
+# the decode helpers next to get_max_preds (utils/keypoint_detection.py:139-239)
+# ------------------------------------------------------------------------------------------
+
+def _argmax_idx(heat):
+    """CUDA [N,K,H,W] -> (flat argmax int32 [N*K], maxvals float32 [N*K]) with the decode kernel's rules
+    (first index on ties, NaN wins - what torch.max / torch.argmax do on the reference's side)."""
+    heat = _lib.require_cuda(heat, "argmax")
+    B, K, H, W = heat.shape
+    dev = heat.device
+    preds = torch.empty((B * K, 2), dtype=torch.float32, device=dev)
+    maxvals = torch.empty((B * K,), dtype=torch.float32, device=dev)
+    idx = torch.empty((B * K,), dtype=torch.int32, device=dev)
+    with _lib.on_device(dev):
+        _lib.call("hp_argmax_decode", _lib.ptr(heat), B * K, H, W, _lib.ptr(preds), _lib.ptr(maxvals), _lib.ptr(idx),
+                  _lib.stream_ptr(dev))
+    return idx, maxvals
+
+
+def find_keypoints_max(heatmaps):
+    """utils/keypoint_detection.py:139-154.  [C,H,W] -> [C,3] = (u, v, max) with the reference's index arithmetic
+    (``v = floor(ind / size(1))``, ``u = fmod(ind, size(2))``)."""
+    hm = _lib.require_cuda(heatmaps.detach(), "find_keypoints_max")
+    if hm.ndim != 3:
+        raise ValueError("find_keypoints_max: heatmaps must be [C,H,W]")
+    C_, H, W = hm.shape
+    idx, maxvals = _argmax_idx(hm.reshape(1, C_, H, W))
+    ind = idx.to(torch.float32)
+    v = torch.floor(torch.div(ind, H))
+    u = torch.fmod(ind, W)
+    return torch.cat((u.view(-1, 1), v.view(-1, 1), maxvals.view(-1, 1)), 1)
+
+
+def _resized(hm, resize_dim):
+    from .fusion import upsample_bilinear
+    size = (resize_dim, resize_dim) if isinstance(resize_dim, int) else (int(resize_dim[0]), int(resize_dim[1]))
+    return upsample_bilinear(hm, size), size
+
+
+def compute_uv_from_heatmaps(hm, resize_dim):
+    """utils/keypoint_detection.py:156-171: bilinear resize (CUDA fusion kernel), argmax -> float [B,K,2] (u, v),
+    NOT masked by the maximum."""
+    resized, (H, W) = _resized(hm, resize_dim)
+    B, K = resized.shape[:2]
+    uvc = find_keypoints_max(resized.view(-1, H, W))
+    return uvc.view(-1, K, 3)[:, :, :2]
+
+
+def compute_uv_from_heatmaps2(hm, resize_dim):
+    """utils/keypoint_detection.py:174-205: bilinear resize, argmax -> int64 [B,K,2] (x, y) zeroed where max <= 0."""
+    resized, (H, W) = _resized(hm, resize_dim)
+    B, K = resized.shape[:2]
+    idx, maxvals = _argmax_idx(resized)
+    idx = idx.to(torch.int64).view(B, K, 1)
+    preds = idx.repeat(1, 1, 2)
+    preds[:, :, 0] = preds[:, :, 0] % W
+    preds[:, :, 1] = torch.div(preds[:, :, 1], W, rounding_mode="floor")
+    preds *= torch.greater(maxvals.view(B, K, 1), 0.0).repeat(1, 1, 2)
+    return preds
+
+
+def compute_uv_from_heatmaps3(heatmap, beta=100.0, scale=4.0):
+    """utils/keypoint_detection.py:209-239: soft-argmax, ``softmax(100*h)``-weighted mean of the pixel coordinates,
+    -> float32 [B,K,2] = 4 * (E[col], E[row]).  One CUDA pass, nothing materialised."""
+    hm = _lib.require_cuda(heatmap.detach(), "compute_uv_from_heatmaps3")
+    B, K, H, W = hm.shape
+    out = torch.empty((B, K, 2), dtype=torch.float32, device=hm.device)
+    with _lib.on_device(hm.device):
+        _lib.call("hp_soft_argmax", _lib.ptr(hm), B * K, H, W, float(beta), float(scale), _lib.ptr(out),
+                  _lib.stream_ptr(hm.device))
+    return out

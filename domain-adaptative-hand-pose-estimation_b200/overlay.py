@@ -28,6 +28,7 @@ import types
 #: hot-path name -> attribute of this package
 REPLACED = (
     "get_max_preds", "accuracy",                                    # utils/keypoint_detection.py
+    "find_keypoints_max", "compute_uv_from_heatmaps", "compute_uv_from_heatmaps2", "compute_uv_from_heatmaps3",
     "JointsMSELoss", "JointsKLLoss",                                # uda/model/loss.py
     "PseudoLabelGenerator", "PseudoLabelGenerator01", "PseudoLabelGenerator02", "PseudoLabelGenerator03",
     "RegressionDisparity", "RegressionDisparityx1", "RegressionDisparityx5", "RegressionDisparityx6",

@@ -84,6 +84,12 @@ size_t      hp_workspace_bytes(int n_maps, int K);
 int hp_argmax_decode(const float* heat, int n_maps, int H, int W,
                      float* preds, float* maxvals, int32_t* idx, hp_stream_t stream);
 
+/* ---- f4: soft-argmax.  utils/keypoint_detection.py:209-239 (compute_uv_from_heatmaps3) ---- */
+/* out_uv [n_maps,2] = scale * (E[col], E[row]) under softmax(beta * heat) over H*W
+ * (the reference: beta = 100, scale = 4). */
+int hp_soft_argmax(const float* heat, int n_maps, int H, int W, float beta, float scale,
+                   float* out_uv, hp_stream_t stream);
+
 /* ---- a2: PCK.  utils/keypoint_detection.py:38-92 (calc_dists, dist_acc, accuracy) ---- */
 /* From decoded coordinates: counts[0..K) += hits, counts[K..2K) += valid (int32). */
 int hp_pck_accumulate(const float* pred_xy, const float* tgt_xy, int B, int K, int H, int W,

@@ -110,6 +110,8 @@ class RegressionDisparityx6(_RD):                    # uda/model/regda_7.py:3564
 def namespace():
     return types.SimpleNamespace(
         get_max_preds=O.get_max_preds, accuracy=O.accuracy, generate_target=O.generate_target,
+        find_keypoints_max=O.find_keypoints_max, compute_uv_from_heatmaps=O.compute_uv_from_heatmaps,
+        compute_uv_from_heatmaps2=O.compute_uv_from_heatmaps2, compute_uv_from_heatmaps3=O.compute_uv_from_heatmaps3,
         JointsMSELoss=JointsMSELoss, JointsKLLoss=JointsKLLoss,
         PseudoLabelGenerator=PseudoLabelGenerator, PseudoLabelGenerator01=PseudoLabelGenerator01,
         PseudoLabelGenerator02=PseudoLabelGenerator02, PseudoLabelGenerator03=PseudoLabelGenerator03,

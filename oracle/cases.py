@@ -299,6 +299,33 @@ def case_fusion(ns, device="cpu"):
     return {"c:target5": _np(t5), "c:target0": _np(t0)}
 
 
+# ---------------------------------------------------------------------------------- f4
+
+def case_soft_decode(ns, device="cpu"):
+    """Decode helpers of utils/keypoint_detection.py:139-239 (row f4).  The resize of (1)/(2) is ATen's on the
+    reference side and the fusion kernel's on the CUDA side (<= 4.8e-7 apart), so the argmax
+    outputs are bit-exact only while the top-2 margin of a resized map exceeds that; the seeded maps below have
+    clear peaks."""
+    out = {}
+    d = synth.make_host_batch(1201, 2, K, 64, 64)
+    hm = d["pred"]
+    hm[0, 0] = -np.abs(hm[0, 0]) - 0.1                                              # all negative: (2) masks it
+    lo = synth.make_lowres_heads(1202, hm, (32, 16))
+    t64, t32 = _t(hm, device), _t(lo[0], device)
+    out["x:uv1_64to128"] = _np(ns.compute_uv_from_heatmaps(t64, (128, 128)))
+    out["x:uv1_32to64"] = _np(ns.compute_uv_from_heatmaps(t32, (64, 64)))
+    out["x:uv2_32to64"] = _np(ns.compute_uv_from_heatmaps2(t32, (64, 64)))
+    out["x:uv2_64to128"] = _np(ns.compute_uv_from_heatmaps2(t64, (128, 128)))
+    fk = _np(ns.find_keypoints_max(_t(hm[1], device)))
+    out["x:fkm_uv"], out["x:fkm_max"] = fk[:, :2], fk[:, 2]
+    out["c:uv3_64"] = _np(ns.compute_uv_from_heatmaps3(t64))
+    out["c:uv3_32"] = _np(ns.compute_uv_from_heatmaps3(t32))
+    rs = np.random.RandomState(1203)
+    flat = (0.02 * rs.standard_normal((2, 5, 30, 42))).astype(np.float32)            # broad soft-argmax, odd size
+    out["c:uv3_30x42"] = _np(ns.compute_uv_from_heatmaps3(_t(flat, device)))
+    return out
+
+
 CASES = {
     "decode": case_decode,
     "target": case_target,
@@ -307,6 +334,7 @@ CASES = {
     "pseudo_label": case_pseudo_label,
     "disparity": case_disparity,
     "fusion": case_fusion,
+    "soft_decode": case_soft_decode,
 }
 
 

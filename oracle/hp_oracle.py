@@ -354,6 +354,60 @@ def fuse_three_scales(lo, mid, hi):
 
 
 # ----------------------------------------------------------------------------------------
+# f4  decode helpers next to get_max_preds          utils/keypoint_detection.py:139-239
+# ----------------------------------------------------------------------------------------
+
+def find_keypoints_max(heatmaps: torch.Tensor) -> torch.Tensor:
+    """[C,H,W] -> [C,3] (u, v, max).  utils/keypoint_detection.py:139-154: per-channel max over the flattened map;
+    ``v = floor(ind / size(1))``, ``u = fmod(ind, size(2))`` in float32."""
+    flat = heatmaps.reshape(heatmaps.size(0), -1)
+    peak, where = flat.max(1)                                                # :148
+    where = where.float()                                                    # :149
+    v = torch.floor(torch.div(where, heatmaps.size(1)))                      # :151
+    u = torch.fmod(where, heatmaps.size(2))                                  # :152
+    return torch.cat((u.view(-1, 1), v.view(-1, 1), peak.view(-1, 1)), 1)    # :153
+
+
+def _resize_bilinear(hm: torch.Tensor, resize_dim):
+    """``nn.Upsample(size=resize_dim, mode='bilinear')`` == interpolate(..., align_corners=False)."""
+    return F.interpolate(hm, size=resize_dim, mode="bilinear", align_corners=False)
+
+
+def compute_uv_from_heatmaps(hm: torch.Tensor, resize_dim):
+    """utils/keypoint_detection.py:156-171: resize, per-map argmax -> float [B,K,2] (u, v); no masking."""
+    resized = _resize_bilinear(hm, resize_dim).view(-1, resize_dim[0], resize_dim[1])   # :163-165
+    uvc = find_keypoints_max(resized).view(-1, hm.size(1), 3)                           # :168-169
+    return uvc[:, :, :2]                                                                # :170
+
+
+def compute_uv_from_heatmaps2(hm: torch.Tensor, resize_dim):
+    """utils/keypoint_detection.py:174-205: resize, argmax / amax per map -> int64 [B,K,2] (x, y), zeroed where
+    max <= 0 (the float quotient ``idx / width`` is truncated by the assignment into the int64 tensor)."""
+    resized = _resize_bilinear(hm, resize_dim)
+    n, k, w = resized.shape[0], resized.shape[1], resized.shape[3]
+    flat = resized.reshape(n, k, -1)
+    where = torch.argmax(flat, 2).reshape(n, k, 1)                           # :188
+    peak = torch.amax(flat, 2).reshape(n, k, 1)                              # :189
+    xy = where.repeat(1, 1, 2)                                               # :195
+    xy[:, :, 0] = xy[:, :, 0] % w                                            # :197
+    xy[:, :, 1] = xy[:, :, 1] / w                                            # :198 (true division, truncated on store)
+    xy *= torch.greater(peak, 0.0).repeat(1, 1, 2)                           # :201-205
+    return xy
+
+
+def compute_uv_from_heatmaps3(heatmap: torch.Tensor) -> torch.Tensor:
+    """utils/keypoint_detection.py:209-239: softmax(100*h) over the map; expectation of the row index (``xx``) and the
+    column index (``yy``); output ``cat([E[col], E[row]]) * 4``."""
+    scaled = heatmap.mul(100)                                                # :214
+    n, k, h, w = scaled.size()
+    p = F.softmax(scaled.view(n, k, h * w), dim=2).view(n, k, h, w)          # :218-220
+    rows, cols = torch.meshgrid(torch.arange(h), torch.arange(w), indexing="ij")   # :222 (xx = row, yy = col)
+    e_row = p.mul(rows.float().to(heatmap.device)).view(n, k, h * w).sum(2).unsqueeze(2)   # :224-229
+    e_col = p.mul(cols.float().to(heatmap.device)).view(n, k, h * w).sum(2).unsqueeze(2)   # :230-235
+    return torch.cat([e_col, e_row], 2) * 4                                  # :237-239
+
+
+# ----------------------------------------------------------------------------------------
 # The benchmarked pipeline: gen + loss + decode + PCK   (BASELINE.json configs[0], configs[1])
 # ----------------------------------------------------------------------------------------
 

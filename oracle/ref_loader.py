@@ -82,6 +82,10 @@ def load():
         accuracy=kd.accuracy,
         calc_dists=kd.calc_dists,
         dist_acc=kd.dist_acc,
+        find_keypoints_max=kd.find_keypoints_max,
+        compute_uv_from_heatmaps=kd.compute_uv_from_heatmaps,
+        compute_uv_from_heatmaps2=kd.compute_uv_from_heatmaps2,
+        compute_uv_from_heatmaps3=kd.compute_uv_from_heatmaps3,
         JointsMSELoss=loss.JointsMSELoss,
         JointsKLLoss=loss.JointsKLLoss,
         PseudoLabelGenerator=r4.PseudoLabelGenerator,

@@ -63,6 +63,10 @@ with torch.no_grad():
     timed("accuracy (2x decode + PCK) 256x21x64x64", lambda i: hp.pck(sets[i]["pred"], tg[i][0]), 4, n * (2 * hw4 + 8), n)
     timed("generate_target_batch 256x21x64x64", lambda i: hp.generate_target_batch(sets[i]["joints"], sets[i]["vis"], (S, S), 2, (4 * S, 4 * S)),
           4, n * (hw4 + 24), n, "write-only")
+    timed("compute_uv_from_heatmaps3 (soft-argmax) 256x21x64x64", lambda i: hp.compute_uv_from_heatmaps3(sets[i]["pred"]), 4, n * (hw4 + 8), n)
+    lo32 = [torch.nn.functional.avg_pool2d(s["pred"], 2) for s in sets]
+    timed("compute_uv_from_heatmaps2 (resize 32->64 + argmax) 256x21", lambda i: hp.compute_uv_from_heatmaps2(lo32[i], (S, S)), 4,
+          n * (4096 + 2 * hw4 + 16), n, "reads 32^2, writes + re-reads 64^2")
     mse, kl = hp.JointsMSELoss(), hp.JointsKLLoss(epsilon=1e-7)
     timed("JointsMSELoss fwd 256x21x64x64", lambda i: mse(sets[i]["pred"], tg[i][0], tg[i][1]), 4, n * 2 * hw4, n)
     timed("JointsKLLoss fwd 256x21x64x64", lambda i: kl(sets[i]["pred"], tg[i][0], tg[i][1]), 4, n * 2 * hw4, n)

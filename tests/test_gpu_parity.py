@@ -21,6 +21,8 @@ def _ns():
     import types
     return types.SimpleNamespace(
         get_max_preds=hp.get_max_preds, accuracy=hp.accuracy, generate_target=hp.generate_target,
+        find_keypoints_max=hp.find_keypoints_max, compute_uv_from_heatmaps=hp.compute_uv_from_heatmaps,
+        compute_uv_from_heatmaps2=hp.compute_uv_from_heatmaps2, compute_uv_from_heatmaps3=hp.compute_uv_from_heatmaps3,
         JointsMSELoss=hp.JointsMSELoss, JointsKLLoss=hp.JointsKLLoss,
         PseudoLabelGenerator=hp.PseudoLabelGenerator, PseudoLabelGenerator01=hp.PseudoLabelGenerator01,
         PseudoLabelGenerator02=hp.PseudoLabelGenerator02, PseudoLabelGenerator03=hp.PseudoLabelGenerator03,
