@@ -38,6 +38,10 @@ _LAZY = {
     "PseudoLabelGenerator02": "regda", "PseudoLabelGenerator03": "regda",
     "RegressionDisparity": "regda", "RegressionDisparityx1": "regda",
     "RegressionDisparityx5": "regda", "RegressionDisparityx6": "regda",
+    "RegressionDisparity2": "regda", "RegressionDisparity3": "regda", "RegressionDisparity4": "regda",
+    "RegressionDisparity5": "regda", "RegressionDisparity6": "regda", "RegressionDisparity7": "regda",
+    "RegressionDisparity8": "regda", "RegressionDisparityx2": "regda", "RegressionDisparityx3": "regda",
+    "RegressionDisparityx4": "regda", "JointsMSELoss0": "loss", "JointsKLLoss5": "loss",
     "generate_target": "target", "generate_target_batch": "target",
     "fuse_multiscale": "fusion", "fuse_three_scales": "fusion", "upsample_bilinear": "fusion",
     "HeatmapPipeline": "pipeline", "PipelineResult": "pipeline",

@@ -33,7 +33,7 @@ def pipe_flags(overlap):
         raise ValueError(f"overlap depth must be 1..8, got {overlap!r}")
     return PIPE_OVERLAP_PREV | (d << 8)
 PLG_BASE, PLG_ONE_MINUS = 0, 1
-RD_BASE, RD_X1, RD_X5, RD_X6 = 0, 1, 2, 3
+RD_BASE, RD_X1, RD_X5, RD_X6, RD_RD4 = 0, 1, 2, 3, 4
 MODE_MIN, MODE_MAX = 0, 1
 GRAD_SCALAR, GRAD_PER_MAP, GRAD_PER_SAMPLE = 0, 1, 2
 MAX_K = 64

@@ -42,9 +42,9 @@ __device__ __forceinline__ float ground_false_value(int variant, bool has_fused,
         }
         return clip01(sum);
     }
-    if (variant == HP_RD_X6) g = clip01(__fsub_rn(clip01(s_all[idx]), __fmul_rn(gt, 10.0f)));
+    if (variant == HP_RD_X6 || variant == HP_RD_RD4) g = clip01(__fsub_rn(clip01(s_all[idx]), __fmul_rn(gt, 10.0f)));
     else g = clip01(__fsub_rn(1.0f, __fmul_rn(gt, 10.0f)));
-    if (has_fused && variant != HP_RD_X1) g = clip01(__fsub_rn(__fadd_rn(g, f), __fmul_rn(gt, 100.0f)));
+    if (has_fused && variant != HP_RD_X1 && variant != HP_RD_RD4) g = clip01(__fsub_rn(__fadd_rn(g, f), __fmul_rn(gt, 100.0f)));
     return g;
 }
 
@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(kRDThreads) regdisp_kernel(const RDArgs a) {
     const int k_begin = (part * a.K) / a.splits, k_end = ((part + 1) * a.K) / a.splits;
     const int t = threadIdx.x;
     const bool want_gf = (TASK == RD_MATERIALIZE) || (a.mode == HP_MODE_MAX);
-    const bool needs_all = want_gf && (a.variant == HP_RD_BASE || a.variant == HP_RD_X6);
+    const bool needs_all = want_gf && (a.variant == HP_RD_BASE || a.variant == HP_RD_X6 || a.variant == HP_RD_RD4);
     const bool normalise = want_gf && (a.variant == HP_RD_X5 || a.variant == HP_RD_X6);
     const bool has_fused = a.fused != nullptr;
 
@@ -245,7 +245,7 @@ template <int TASK>
 static int launch_regdisp(RDArgs a, bool vec, cudaStream_t stream, const char* who) {
     const int ohw = a.oh * a.ow;
     const bool want_gf = (TASK == RD_MATERIALIZE) || (a.mode == HP_MODE_MAX);
-    const bool needs_all = want_gf && (a.variant == HP_RD_BASE || a.variant == HP_RD_X6);
+    const bool needs_all = want_gf && (a.variant == HP_RD_BASE || a.variant == HP_RD_X6 || a.variant == HP_RD_RD4);
     const int ntab = 2 * a.tmp * a.tmp + 1;
     const size_t smem = sizeof(float) * (((ntab + 3) & ~3) + (needs_all ? ohw : 0));
     HP_REQUIRE(smem <= 200 * 1024, HP_ERR_SHAPE, "%s: %dx%d map does not fit the per-sample shared-memory sum", who, a.oh,
@@ -279,7 +279,7 @@ static bool generic_forced() {
 }
 
 static int check_rd(const char* who, int variant, int mode, int B, int K, int oh, int ow, int tmp) {
-    HP_REQUIRE(variant >= HP_RD_BASE && variant <= HP_RD_X6, HP_ERR_ARG, "%s: variant %d", who, variant);
+    HP_REQUIRE(variant >= HP_RD_BASE && variant <= HP_RD_RD4, HP_ERR_ARG, "%s: variant %d", who, variant);
     HP_REQUIRE(mode == HP_MODE_MIN || mode == HP_MODE_MAX, HP_ERR_ARG, "%s: mode %d", who, mode);
     HP_REQUIRE(B > 0 && K > 0 && K <= HP_MAX_K && oh > 0 && ow > 0 && static_cast<long long>(oh) * ow < (1ll << 28),
                HP_ERR_SHAPE, "%s: bad shape B=%d K=%d oh=%d ow=%d", who, B, K, oh, ow);

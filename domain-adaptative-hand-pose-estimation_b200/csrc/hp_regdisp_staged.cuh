@@ -75,7 +75,7 @@ __device__ __forceinline__ float ground_false_pixel(int variant, bool use_fused,
             if (j != k) sum += patch_at(s_tab, tmp, s_c[j], x, y);
         return clip01(sum);
     }
-    if (variant == HP_RD_X6) g = clip01(__fsub_rn(all, __fmul_rn(gt, 10.0f)));
+    if (variant == HP_RD_X6 || variant == HP_RD_RD4) g = clip01(__fsub_rn(all, __fmul_rn(gt, 10.0f)));
     else g = clip01(__fsub_rn(1.0f, __fmul_rn(gt, 10.0f)));
     if (use_fused) g = clip01(__fsub_rn(__fadd_rn(g, f), __fmul_rn(gt, 100.0f)));
     return g;
@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(NT + 32, rds_blocks_per_sm<NT, DENSE>()) regdi
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const int K = a.K, tmp = a.tmp;
     const bool want_gf = a.mode == HP_MODE_MAX;
-    const bool needs_all = DENSE && (a.variant == HP_RD_BASE || a.variant == HP_RD_X6);
+    const bool needs_all = DENSE && (a.variant == HP_RD_BASE || a.variant == HP_RD_X6 || a.variant == HP_RD_RD4);
     const bool normalise = DENSE && (a.variant == HP_RD_X5 || a.variant == HP_RD_X6);  // sparse recipes: M == 1 (host)
     const float bg = want_gf ? 1.0f : 0.0f;  // the constant target outside the patch of the sparse recipes
     constexpr uint32_t stage_bytes = (FUSED ? 2u : 1u) * static_cast<uint32_t>(ohw) * 4u;
@@ -520,8 +520,8 @@ static int launch_regdisp_staged(RDArgs a, cudaStream_t stream, const char* who)
     }
     a.wdiv = FastDiv(static_cast<uint32_t>(a.ow));
     const bool want_gf = a.mode == HP_MODE_MAX;
-    const bool fused = want_gf && a.fused != nullptr && a.variant != HP_RD_X1;
-    const bool dense = fused || (want_gf && (a.variant == HP_RD_BASE || a.variant == HP_RD_X6));
+    const bool fused = want_gf && a.fused != nullptr && a.variant != HP_RD_X1 && a.variant != HP_RD_RD4;
+    const bool dense = fused || (want_gf && (a.variant == HP_RD_BASE || a.variant == HP_RD_X6 || a.variant == HP_RD_RD4));
     if (!dense) {
         // sparse recipes take M == 1 for granted: some float4 of the map must lie outside every possible patch
         const int side = 2 * a.tmp + 1;

@@ -140,3 +140,40 @@ class JointsKLLoss(nn.Module):
         if not _wants_grad(output):
             return _KL.forward(_NoCtx(), output, target, target_weight, self.reduction, float(self.epsilon))
         return _KL.apply(output, target, target_weight, self.reduction, float(self.epsilon))
+
+
+class JointsMSELoss0(nn.Module):
+    """uda/model/loss.py:68-112: prediction and label are each shifted by 1e-7 and normalised to sum 1 per map, then
+    ``0.5*(p-t)^2*w``.  The normalisation is two small elementwise ops on the GPU; the loss itself is the CUDA MSE
+    kernel (autograd flows through both)."""
+
+    def __init__(self, reduction="mean"):
+        super().__init__()
+        self.reduction = reduction
+        self._mse = JointsMSELoss(reduction)
+
+    def forward(self, output, target, target_weight=None):
+        B, K, H, W = output.shape
+        p = output.reshape((B, K, -1)) + 1e-7
+        p = p / p.sum(dim=-1, keepdims=True)
+        t = target.reshape((B, K, -1)) + 1e-7
+        t = t / t.sum(dim=-1, keepdims=True)
+        return self._mse(p.reshape(B, K, H, W), t.reshape(B, K, H, W), target_weight)
+
+
+class JointsKLLoss5(nn.Module):
+    """uda/model/loss.py:160-216: both tensors are rescaled per map by ``w5`` (a detached overlap score of prediction and
+    label, normalised by its global maximum), then the KL loss WITHOUT target weights (the reference ignores them)."""
+
+    def __init__(self, reduction="mean", epsilon=0.):
+        super().__init__()
+        self.reduction = reduction
+        self.epsilon = epsilon
+        self._kl = JointsKLLoss(reduction, epsilon)
+
+    def forward(self, output, target, target_weight=None):
+        f1 = (output / torch.max(output)).detach()
+        f2 = (target / torch.max(target)).detach()
+        w3 = torch.mul(f1, f2).sum(dim=2).sum(dim=2)
+        w5 = (w3 / torch.max(w3)).unsqueeze(-1).unsqueeze(-1)
+        return self._kl(torch.mul(output, w5), torch.mul(target, w5), None)

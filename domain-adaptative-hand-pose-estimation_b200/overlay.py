@@ -32,6 +32,9 @@ REPLACED = (
     "JointsMSELoss", "JointsKLLoss",                                # uda/model/loss.py
     "PseudoLabelGenerator", "PseudoLabelGenerator01", "PseudoLabelGenerator02", "PseudoLabelGenerator03",
     "RegressionDisparity", "RegressionDisparityx1", "RegressionDisparityx5", "RegressionDisparityx6",
+    "RegressionDisparity2", "RegressionDisparity3", "RegressionDisparity4", "RegressionDisparity5",   # row f3
+    "RegressionDisparity6", "RegressionDisparity7", "RegressionDisparity8",
+    "RegressionDisparityx2", "RegressionDisparityx3", "RegressionDisparityx4", "JointsMSELoss0", "JointsKLLoss5",
     "generate_target",                                              # uda/dataset/util.py
 )
 

@@ -30,7 +30,7 @@ import torch.nn as nn
 from . import _lib
 from .loss import JointsKLLoss, _NoCtx, _wants_grad
 
-_VARIANT_CODE = {"base": _lib.RD_BASE, "x1": _lib.RD_X1, "x5": _lib.RD_X5, "x6": _lib.RD_X6}
+_VARIANT_CODE = {"base": _lib.RD_BASE, "x1": _lib.RD_X1, "x5": _lib.RD_X5, "x6": _lib.RD_X6, "rd4": _lib.RD_RD4}
 
 
 class _PLGBase(nn.Module):
@@ -250,3 +250,128 @@ class RegressionDisparityx6(_RDBase):
 
     def forward(self, y, y_adv, y_adv2, weight=None, mode="min"):
         return self._run(y, y_adv, y_adv2, weight, mode)
+
+
+# ------------------------------------------------------------------------------------------
+# the remaining disparity variants (dead code in the reference's drivers, imported at
+# train1.py:19).  Three of them are existing kernel recipes under other names; the label-fusing ones compose the
+# CUDA pseudo-label and loss kernels with a few small elementwise torch ops on the GPU (nothing leaves the device).
+# ------------------------------------------------------------------------------------------
+
+class RegressionDisparity4(_RDBase):
+    """uda/model/regda_4.py:299-356: ``gf = clip(clip(sum_k gt) - 10 gt)`` - the x6 recipe without a fused map and
+    without the per-map normalisation.  One fused kernel (variant HP_RD_RD4)."""
+    _variant = "rd4"
+
+    def forward(self, y, y_adv, weight=None, mode="min"):
+        return self._run(y, y_adv, None, weight, mode)
+
+
+class RegressionDisparityx2(_RDBase):
+    """uda/model/regda_7.py:3272-3337: ``gf = clip(1 - 10 gt)`` (its ``label_p`` is computed and never used)."""
+    _variant = "x1"
+
+    def forward(self, y, y_adv, weight=None, mode="min"):
+        return self._run(y, y_adv, None, weight, mode)
+
+
+class RegressionDisparityx3(RegressionDisparityx2):
+    """uda/model/regda_7.py:3340-3405: the same recipe as x2."""
+
+
+class RegressionDisparityx4(_RDBase):
+    """uda/model/regda_7.py:3408-3482: ``gf = PLG.gf / max(PLG.gf)`` per map; with the generators that produce
+    ``clip(1 - 10 gt)`` the maximum is 1, i.e. the x1 recipe.  A tensor ``y_adv2`` makes the reference raise
+    (``if y_adv2:`` on a multi-element tensor), and so does this."""
+    _variant = "x1"
+
+    def forward(self, y, y_adv, weight=None, y_adv2=None, mode="min"):
+        if y_adv2 is not None and bool(y_adv2):   # raises for multi-element tensors, like the reference
+            raise NameError("RegressionDisparityx4: ground_false is undefined when y_adv2 is given (regda_7.py:3463-3466)")
+        if self.pseudo_label_generator._spec[3] != _lib.PLG_ONE_MINUS:
+            raise NotImplementedError("RegressionDisparityx4 is built for PseudoLabelGenerator01 / 03")
+        return self._run(y, y_adv, None, weight, mode)
+
+
+def _clip01(t):
+    return t.clip(max=1., min=0.)
+
+
+def _per_sample_max_normalise(lp):
+    return lp / lp.reshape(lp.shape[0], -1).max(dim=1).values.view(-1, 1, 1)
+
+
+class _RDLabelFusion(nn.Module):
+    """RegressionDisparity2/3/5/6/7/8 (uda/model/regda_4.py:145-645): ``gf = clip(label_p - 10 gt)`` where the per-sample
+    map ``label_p`` fuses the summed pseudo-labels of ``y`` and of one or two extra predictions."""
+
+    def __init__(self, pseudo_label_generator, criterion: nn.Module):
+        super().__init__()
+        self.criterion = criterion
+        self.pseudo_label_generator = pseudo_label_generator
+        self.reset()
+
+    def reset(self):
+        self.label_x = 0.
+
+    def updata(self, label_x):          # (sic) regda_4.py:197
+        self.label_x = label_x
+
+    def _label_p(self, gt, gt1, gt2):
+        raise NotImplementedError
+
+    def _run(self, y, y_adv, label_1, label_2, weight, mode):
+        assert mode in ["min", "max"]
+        plg = self.pseudo_label_generator
+        gt, _ = plg(y.detach())
+        gt1, _ = plg(label_1.detach())
+        gt2 = plg(label_2.detach())[0] if label_2 is not None else None
+        lp = self._label_p(gt, gt1, gt2)
+        gf = _clip01(lp.unsqueeze(1) - gt * 10)
+        self.ground_truth, self.ground_false = gt, gf
+        return self.criterion(y_adv, gt if mode == "min" else gf, weight)
+
+
+class _RDLabelFusion2(_RDLabelFusion):
+    def forward(self, y, y_adv, label_1, label_2, weight=None, mode="min"):
+        return self._run(y, y_adv, label_1, label_2, weight, mode)
+
+
+class _RDLabelFusion1(_RDLabelFusion):
+    def forward(self, y, y_adv, label_1, weight=None, mode="min"):
+        return self._run(y, y_adv, label_1, None, weight, mode)
+
+
+class RegressionDisparity2(_RDLabelFusion2):     # regda_4.py:145-220
+    def _label_p(self, gt, gt1, gt2):
+        return _per_sample_max_normalise(gt1.sum(1) + gt.sum(1) + gt2.sum(1))
+
+
+class RegressionDisparity3(_RDLabelFusion2):     # regda_4.py:222-297
+    def _label_p(self, gt, gt1, gt2):
+        return _per_sample_max_normalise(_clip01(gt.sum(1)) + _clip01(gt1.sum(1)) + _clip01(gt2.sum(1)))
+
+
+class RegressionDisparity5(_RDLabelFusion2):     # regda_4.py:358-427
+    def _label_p(self, gt, gt1, gt2):
+        p1, p2, p3 = _clip01(gt.sum(1)), _clip01(gt1.sum(1)), _clip01(gt2.sum(1))
+        return _clip01(p1 + _clip01(p2 - p1) + _clip01(p3 - p1))
+
+
+class RegressionDisparity6(_RDLabelFusion1):     # regda_4.py:429-495
+    def _label_p(self, gt, gt1, gt2):
+        p1, p2 = _clip01(gt.sum(1)), _clip01(gt1.sum(1))
+        return _clip01(p1 + _clip01(p2 - p1))
+
+
+class RegressionDisparity7(_RDLabelFusion1):     # regda_4.py:497-572
+    def _label_p(self, gt, gt1, gt2):
+        return _per_sample_max_normalise(_clip01(gt1.sum(1)) + _clip01(gt.sum(1)))
+
+
+class RegressionDisparity8(_RDLabelFusion2):     # regda_4.py:574-645
+    def _label_p(self, gt, gt1, gt2):
+        p1 = _clip01(gt.sum(1))
+        x1 = _clip01(_clip01(gt1 - gt).sum(1))
+        x2 = _clip01(_clip01(gt2 - gt).sum(1))
+        return _clip01(p1 + x1 + x2)

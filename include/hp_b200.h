@@ -62,6 +62,7 @@ typedef void* hp_stream_t; /* cudaStream_t */
 #define HP_RD_X1         1 /* RegressionDisparityx1  uda/model/regda_7.py:3206-3268 */
 #define HP_RD_X5         2 /* RegressionDisparityx5  uda/model/regda_7.py:3485-3561 */
 #define HP_RD_X6         3 /* RegressionDisparityx6  uda/model/regda_7.py:3564-3632 */
+#define HP_RD_RD4        4 /* RegressionDisparity4   uda/model/regda_4.py:299-356: clip(clip(sum gt) - 10 gt), no fused map, no normalisation */
 #define HP_MODE_MIN      0
 #define HP_MODE_MAX      1
 

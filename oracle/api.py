@@ -107,6 +107,81 @@ class RegressionDisparityx6(_RD):                    # uda/model/regda_7.py:3564
         return self._run(y, y_adv, y_adv2, weight, mode)
 
 
+class RegressionDisparity4(_RD):                     # uda/model/regda_4.py:299-356
+    variant = "rd4"
+
+    def forward(self, y, y_adv, weight=None, mode="min"):
+        return self._run(y, y_adv, None, weight, mode)
+
+
+class RegressionDisparityx2(_RD):                    # uda/model/regda_7.py:3272-3337
+    variant = "x2"
+
+    def forward(self, y, y_adv, weight=None, mode="min"):
+        return self._run(y, y_adv, None, weight, mode)
+
+
+class RegressionDisparityx3(RegressionDisparityx2):  # uda/model/regda_7.py:3340-3405
+    variant = "x3"
+
+
+class RegressionDisparityx4(_RD):                    # uda/model/regda_7.py:3408-3482
+    variant = "x4"
+
+    def forward(self, y, y_adv, weight=None, y_adv2=None, mode="min"):
+        return self._run(y, y_adv, None, weight, mode)
+
+
+class _RDF(nn.Module):
+    variant = "rd2"
+
+    def __init__(self, pseudo_label_generator, criterion):
+        super().__init__()
+        self.pseudo_label_generator = pseudo_label_generator
+        self.criterion = criterion
+
+    def _run(self, y, y_adv, label_1, label_2, weight, mode):
+        assert mode in ["min", "max"]
+        gt, gf = O.ground_maps_fusion(self.variant, y.detach(), label_1.detach(),
+                                      None if label_2 is None else label_2.detach())
+        self.ground_truth, self.ground_false = gt, gf
+        return self.criterion(y_adv, gt if mode == "min" else gf, weight)
+
+
+def _rdf(variant, two):
+    if two:
+        def forward(self, y, y_adv, label_1, label_2, weight=None, mode="min"):
+            return self._run(y, y_adv, label_1, label_2, weight, mode)
+    else:
+        def forward(self, y, y_adv, label_1, weight=None, mode="min"):
+            return self._run(y, y_adv, label_1, None, weight, mode)
+    return type("RegressionDisparity" + variant[2:], (_RDF,), {"variant": variant, "forward": forward})
+
+
+RegressionDisparity2, RegressionDisparity3 = _rdf("rd2", True), _rdf("rd3", True)      # regda_4.py:145-297
+RegressionDisparity5, RegressionDisparity8 = _rdf("rd5", True), _rdf("rd8", True)      # regda_4.py:358-427, 574-645
+RegressionDisparity6, RegressionDisparity7 = _rdf("rd6", False), _rdf("rd7", False)    # regda_4.py:429-572
+
+
+class JointsMSELoss0(nn.Module):                     # uda/model/loss.py:68-112
+    def __init__(self, reduction="mean"):
+        super().__init__()
+        self.reduction = reduction
+
+    def forward(self, output, target, target_weight=None):
+        return O.joints_mse_loss0(output, target, target_weight, self.reduction)
+
+
+class JointsKLLoss5(nn.Module):                      # uda/model/loss.py:160-216
+    def __init__(self, reduction="mean", epsilon=0.0):
+        super().__init__()
+        self.reduction = reduction
+        self.epsilon = epsilon
+
+    def forward(self, output, target, target_weight=None):
+        return O.joints_kl_loss5(output, target, target_weight, self.reduction, self.epsilon)
+
+
 def namespace():
     return types.SimpleNamespace(
         get_max_preds=O.get_max_preds, accuracy=O.accuracy, generate_target=O.generate_target,
@@ -117,4 +192,10 @@ def namespace():
         PseudoLabelGenerator02=PseudoLabelGenerator02, PseudoLabelGenerator03=PseudoLabelGenerator03,
         RegressionDisparity=RegressionDisparity, RegressionDisparityx1=RegressionDisparityx1,
         RegressionDisparityx5=RegressionDisparityx5, RegressionDisparityx6=RegressionDisparityx6,
+        RegressionDisparity2=RegressionDisparity2, RegressionDisparity3=RegressionDisparity3,
+        RegressionDisparity4=RegressionDisparity4, RegressionDisparity5=RegressionDisparity5,
+        RegressionDisparity6=RegressionDisparity6, RegressionDisparity7=RegressionDisparity7,
+        RegressionDisparity8=RegressionDisparity8, RegressionDisparityx2=RegressionDisparityx2,
+        RegressionDisparityx3=RegressionDisparityx3, RegressionDisparityx4=RegressionDisparityx4,
+        JointsMSELoss0=JointsMSELoss0, JointsKLLoss5=JointsKLLoss5,
     )

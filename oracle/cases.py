@@ -326,6 +326,61 @@ def case_soft_decode(ns, device="cpu"):
     return out
 
 
+# ---------------------------------------------------------------------------------- f3
+
+def case_variants(ns, device="cpu"):
+    """the disparity variants the drivers import but never call (RegressionDisparity2-8, x2-x4)
+    and the loss weightings JointsMSELoss0 / JointsKLLoss5, every one with loss, gradient and both maps."""
+    out = {}
+    I = disparity_inputs(seed=1301)
+    y, w = _t(I["y"], device), _t(I["w"], device)
+    l1 = _t(synth.make_host_batch(1311, 2, K, 64, 64)["pred"], device)
+    l2 = _t(synth.make_host_batch(1312, 2, K, 64, 64)["pred"], device)
+    kl = lambda: ns.JointsKLLoss(epsilon=1e-7)
+    plg = lambda: ns.PseudoLabelGenerator(K, 64, 64)
+    specs = (
+        ("rd2", lambda: ns.RegressionDisparity2(plg(), kl()), "adv64", (l1, l2)),
+        ("rd3", lambda: ns.RegressionDisparity3(plg(), kl()), "adv64", (l1, l2)),
+        ("rd4", lambda: ns.RegressionDisparity4(plg(), kl()), "adv64", ()),
+        ("rd5", lambda: ns.RegressionDisparity5(plg(), kl()), "adv64", (l1, l2)),
+        ("rd6", lambda: ns.RegressionDisparity6(plg(), kl()), "adv64", (l1,)),
+        ("rd7", lambda: ns.RegressionDisparity7(plg(), kl()), "adv64", (l1,)),
+        ("rd8", lambda: ns.RegressionDisparity8(plg(), kl()), "adv64", (l1, l2)),
+        ("x2", lambda: ns.RegressionDisparityx2(ns.PseudoLabelGenerator02(K, 64, 64), kl()), "adv64", ()),
+        ("x3", lambda: ns.RegressionDisparityx3(ns.PseudoLabelGenerator02(K, 64, 64), kl()), "adv64", ()),
+        ("x4", lambda: ns.RegressionDisparityx4(ns.PseudoLabelGenerator01(K), kl()), "adv16", ()),
+    )
+    for name, make, adv_key, labels in specs:
+        rd = make()
+        for mode in ("min", "max"):
+            adv = _t(I[adv_key], device, grad=True)
+            l = rd(y, adv, *labels, w, mode=mode) if name != "x4" else rd(y, adv, w, None, mode)
+            out[f"c:loss_{name}_{mode}"] = _np(l)
+            l.backward()
+            out[f"c:grad_{name}_{mode}"] = _np(adv.grad)
+            if mode == "max":
+                out[f"c:gt_{name}"] = _np(rd.ground_truth)
+                out[f"c:gf_{name}"] = _np(rd.ground_false)
+    # loss weightings on positive maps (JointsMSELoss0 normalises by the map sum)
+    rs = np.random.RandomState(1320)
+    p = rs.uniform(0.01, 1.0, size=(2, K, 64, 64)).astype(np.float32)
+    t = np.clip(synth.make_host_batch(1321, 2, K, 64, 64)["pred"], 0.0, None).astype(np.float32) + np.float32(1e-3)
+    wt = rs.uniform(0, 1, size=(2, K, 1)).astype(np.float32)
+    for red in ("mean", "none"):
+        for wname, wv in (("w", wt), ("nw", None)):
+            tp = _t(p, device, grad=True)
+            l = ns.JointsMSELoss0(reduction=red)(tp, _t(t, device), None if wv is None else _t(wv, device))
+            out[f"c:mse0_{red}_{wname}"] = _np(l)
+            l.sum().backward()
+            out[f"c:grad_mse0_{red}_{wname}"] = _np(tp.grad)
+            tp = _t(p, device, grad=True)
+            l = ns.JointsKLLoss5(reduction=red, epsilon=1e-7)(tp, _t(t, device), None if wv is None else _t(wv, device))
+            out[f"c:kl5_{red}_{wname}"] = _np(l)
+            l.sum().backward()
+            out[f"c:grad_kl5_{red}_{wname}"] = _np(tp.grad)
+    return out
+
+
 CASES = {
     "decode": case_decode,
     "target": case_target,
@@ -335,6 +390,7 @@ CASES = {
     "disparity": case_disparity,
     "fusion": case_fusion,
     "soft_decode": case_soft_decode,
+    "variants": case_variants,
 }
 
 

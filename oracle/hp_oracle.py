@@ -319,7 +319,90 @@ def ground_maps(variant, y, y_adv2=None):
             gf = gf + y_adv2
             gf = (gf - gt * 100).clip(max=1.0, min=0.0)
         return gt, _per_map_max_normalise(gf)
+    if variant == "rd4":                                                     # regda_4.py:344-356 (RegressionDisparity4)
+        gt, _ = pseudo_label(y, "base")
+        lp = torch.sum(gt, dim=1).clip(max=1.0, min=0.0)
+        lp = lp.unsqueeze(1).repeat(1, gt.shape[1], 1, 1)
+        return gt, (lp - gt * 10).clip(max=1.0, min=0.0)
+    if variant in ("x2", "x3"):                                              # regda_7.py:3317-3337, 3385-3405
+        gt, _ = pseudo_label(y, "base")                                      # (PseudoLabelGenerator02)
+        return gt, (torch.ones_like(gt) - gt * 10).clip(max=1.0, min=0.0)
+    if variant == "x4":                                                      # regda_7.py:3454-3482, y_adv2 = None
+        gt, gf = pseudo_label(y, "01")
+        return gt, _per_map_max_normalise(gf)
     raise ValueError(variant)
+
+
+def _sample_max_normalise(lp):
+    """``[lp[k] / max(lp[k]) for k in range(b)]`` stacked (regda_4.py:208-209)."""
+    return torch.stack([lp[k] / torch.max(lp[k]) for k in range(lp.shape[0])])
+
+
+def ground_maps_fusion(variant, y, label_1, label_2=None):
+    """(gt, gf) of RegressionDisparity2/3/5/6/7/8 (regda_4.py:145-645): ``gf = clip(label_p - 10 gt)`` with the per-sample
+    map ``label_p`` fused from the summed pseudo-labels of y, label_1 (and label_2)."""
+    c01 = lambda t: t.clip(max=1.0, min=0.0)
+    gt, _ = pseudo_label(y, "base")
+    gt1, _ = pseudo_label(label_1, "base")
+    gt2 = pseudo_label(label_2, "base")[0] if label_2 is not None else None
+    if variant == "rd2":                                                     # :203-209
+        lp = _sample_max_normalise(torch.sum(gt1, dim=1) + torch.sum(gt, dim=1) + torch.sum(gt2, dim=1))
+    elif variant == "rd3":                                                   # :280-286
+        lp = _sample_max_normalise(c01(torch.sum(gt, dim=1)) + c01(torch.sum(gt1, dim=1)) + c01(torch.sum(gt2, dim=1)))
+    elif variant == "rd5":                                                   # :409-416
+        p1, p2, p3 = c01(torch.sum(gt, dim=1)), c01(torch.sum(gt1, dim=1)), c01(torch.sum(gt2, dim=1))
+        lp = c01(p1 + c01(p2 - p1) + c01(p3 - p1))
+    elif variant == "rd6":                                                   # :479-484
+        p1, p2 = c01(torch.sum(gt, dim=1)), c01(torch.sum(gt1, dim=1))
+        lp = c01(p1 + c01(p2 - p1))
+    elif variant == "rd7":                                                   # :553-558
+        lp = _sample_max_normalise(c01(torch.sum(gt1, dim=1)) + c01(torch.sum(gt, dim=1)))
+    elif variant == "rd8":                                                   # :625-634
+        p1 = c01(torch.sum(gt, dim=1))
+        x1 = c01(torch.sum(c01(gt1 - gt), dim=1))
+        x2 = c01(torch.sum(c01(gt2 - gt), dim=1))
+        lp = c01(p1 + x1 + x2)
+    else:
+        raise ValueError(variant)
+    lp = lp.unsqueeze(1).repeat(1, gt.shape[1], 1, 1)                        # reference hard-codes 21
+    return gt, (lp - gt * 10).clip(max=1.0, min=0.0)
+
+
+def joints_mse_loss0(output, target, target_weight=None, reduction="mean"):
+    """uda/model/loss.py:96-112: both maps shifted by 1e-7 and normalised to sum 1, then 0.5*(p-t)^2*w."""
+    B, K = output.shape[0], output.shape[1]
+    p = output.reshape((B, K, -1)) + 1e-7
+    p = p / p.sum(dim=-1, keepdims=True)
+    t = target.reshape((B, K, -1)) + 1e-7
+    t = t / t.sum(dim=-1, keepdims=True)
+    loss = F.mse_loss(p, t, reduction="none") * 0.5
+    if target_weight is not None:
+        loss = loss * target_weight.view((B, K, 1))
+    if reduction == "mean":
+        return loss.mean()
+    if reduction == "none":
+        return loss.mean(dim=-1)
+    return None
+
+
+def joints_kl_loss5(output, target, target_weight=None, reduction="mean", epsilon=0.0):
+    """uda/model/loss.py:189-216: per-map rescale by the detached overlap score w5, then KL; target_weight is ignored."""
+    B, K = output.shape[0], output.shape[1]
+    f1 = (output / torch.max(output)).detach()
+    f2 = (target / torch.max(target)).detach()
+    w3 = torch.sum(torch.sum(torch.mul(f1, f2), dim=2), dim=2)
+    w5 = (w3 / torch.max(w3)).unsqueeze(-1).unsqueeze(-1)
+    output = torch.mul(output, w5)
+    target = torch.mul(target, w5)
+    logp = F.log_softmax(output.reshape((B, K, -1)), dim=-1)
+    q = target.reshape((B, K, -1)) + epsilon
+    q = q / q.sum(dim=-1, keepdims=True)
+    loss = F.kl_div(logp, q, reduction="none").sum(dim=-1)
+    if reduction == "mean":
+        return loss.mean()
+    if reduction == "none":
+        return loss.mean(dim=-1)
+    return None
 
 
 def regression_disparity(variant, y, y_adv, y_adv2=None, weight=None, mode="min",

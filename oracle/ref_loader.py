@@ -97,6 +97,12 @@ def load():
         RegressionDisparityx5=r7.RegressionDisparityx5,
         RegressionDisparityx6=r7.RegressionDisparityx6,
         generate_target=du.generate_target,
+        RegressionDisparity2=r4.RegressionDisparity2, RegressionDisparity3=r4.RegressionDisparity3,
+        RegressionDisparity4=r4.RegressionDisparity4, RegressionDisparity5=r4.RegressionDisparity5,
+        RegressionDisparity6=r4.RegressionDisparity6, RegressionDisparity7=r4.RegressionDisparity7,
+        RegressionDisparity8=r4.RegressionDisparity8, RegressionDisparityx2=r7.RegressionDisparityx2,
+        RegressionDisparityx3=r7.RegressionDisparityx3, RegressionDisparityx4=r7.RegressionDisparityx4,
+        JointsMSELoss0=loss.JointsMSELoss0, JointsKLLoss5=loss.JointsKLLoss5,
     )
     _CACHE["ns"] = ns
     return ns

@@ -26,8 +26,13 @@ for obj in (PseudoLabelGenerator, RegressionDisparityx1, RegressionDisparityx5, 
             accuracy, get_max_preds, h3d.generate_target, stb.generate_target, rhd.generate_target,
             r4.get_max_preds, r7.get_max_preds, r4.RegressionDisparity):
     assert obj.__module__.startswith(ours), (obj, obj.__module__)
-# out-of-scope variants stay the reference's own
-assert RegressionDisparity3.__module__ == "uda.model.regda_4" and RegressionDisparity4.__module__ == "uda.model.regda_4"
+# row f3: the variants the drivers import but never call are rebound too
+assert RegressionDisparity3.__module__.startswith(ours) and RegressionDisparity4.__module__.startswith(ours)
+from uda.model.loss import JointsMSELoss0, JointsKLLoss5
+assert JointsMSELoss0.__module__.startswith(ours) and JointsKLLoss5.__module__.startswith(ours)
+# models and everything else stay the reference's own
+from uda.model.regda_4 import PoseResNet3
+assert PoseResNet3.__module__ == "uda.model.regda_4"
 import sys
 assert sys.argv[1:] == ["data/H3D", "-t", "Hand3DStudio"], sys.argv
 print("overlay-ok")
