@@ -394,29 +394,32 @@ __device__ __forceinline__ void softmax_tile(float& m, float& s, const float4 (&
     const float mb = -ms * kLog2e;
     float acc = s * exp_diff(m, ms);
 #pragma unroll
-    for (int j = 0; j < NV; ++j) {
-        acc += exp2f(fmaf(p[j].x, kLog2e, mb));
-        acc += exp2f(fmaf(p[j].y, kLog2e, mb));
-        acc += exp2f(fmaf(p[j].z, kLog2e, mb));
-        acc += exp2f(fmaf(p[j].w, kLog2e, mb));
+    for (int j = 0; j < NV; ++j) {  // single-instruction MUFU.EX2 (2^-22 relative error, far inside the 1e-5 bar)
+        acc += ex2_approx(fmaf(p[j].x, kLog2e, mb)) + ex2_approx(fmaf(p[j].y, kLog2e, mb));
+        acc += ex2_approx(fmaf(p[j].z, kLog2e, mb)) + ex2_approx(fmaf(p[j].w, kLog2e, mb));
     }
     s = acc;
     m = mn;
 }
 
-// KL target sums for one element: sum[0] += u, sum[1] += u*p, sum[2] += xlogy(u, u)
+// KL target sums for one element: sum[0] += u, sum[1] += u*p, sum[2] += xlogy(u, u) / ln 2 (the caller scales by ln 2).
+// Branch-free: at u == 0 the clamp keeps lg2 finite, so the term is exactly 0 (xlogy); u < 0 gives lg2(tiny) * u, a
+// finite value where torch gives NaN - a negative (target + epsilon) is outside every caller's domain (targets are
+// clamped heatmaps); a NaN u propagates through the multiplication.
 __device__ __forceinline__ void kl_elem(float (&sum)[3], float p, float u) {
     sum[0] += u;
     sum[1] = fmaf(u, p, sum[1]);
-    if (u != 0.0f) sum[2] = fmaf(u, __logf(u), sum[2]);  // log(u<0) = NaN like torch.xlogy; NaN u propagates
+    sum[2] = fmaf(u, lg2_approx(fmaxf(u, 1.17549435e-38f)), sum[2]);
 }
 
-// per-map KL value from the reduced statistics, in float64
-__device__ __forceinline__ double kl_finish(float m, float s, float Su, float Sup, float Sulogu, float& lse_out) {
-    const double lse = static_cast<double>(m) + log(static_cast<double>(s));
-    lse_out = static_cast<float>(lse);
-    const double S = static_cast<double>(Su);
-    return (static_cast<double>(Sulogu) - static_cast<double>(Sup)) / S - log(S) + lse;
+// per-map KL value from the reduced statistics:  L = (sum u ln u - sum u p)/S - ln S + lse,  lse = m + ln(s).
+// float32 logarithms (two FP64 logs on one thread cost ~1,500 cycles on B200 and sat on every block's critical
+// path); the two logs are merged, ln(s / S), so their rounding does not double, and the few additions run in float64.
+// (Sulg2u = sum u lg2 u as accumulated by kl_elem)
+__device__ __forceinline__ double kl_finish(float m, float s, float Su, float Sup, float Sulg2u, float& lse_out) {
+    const float Sulogu = Sulg2u * kLn2;
+    lse_out = m + logf(s);
+    return static_cast<double>((Sulogu - Sup) / Su) + static_cast<double>(m) + static_cast<double>(logf(s / Su));
 }
 
 // "last block done" election.  counter must be zero on entry; it is reset by the winner.
@@ -489,6 +492,21 @@ __device__ __forceinline__ float fx_mean_from_workspace(unsigned long long* acc,
         acc[i] = 0ull;
     }
     return fx_mean(v, n);
+}
+
+// the same election when only a few threads published block results: only the writers fence (a __threadfence by
+// every thread of every block showed up as the 'membar' stall of the loss kernels)
+__device__ __forceinline__ bool last_block_arrives_writers(unsigned int* counter, unsigned int n_blocks, bool i_wrote) {
+    __shared__ bool s_last1;
+    if (i_wrote) __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(counter, 1u);
+        s_last1 = (prev == n_blocks - 1);
+        if (s_last1) __threadfence();
+    }
+    __syncthreads();
+    return s_last1;
 }
 
 // deterministic block-wide float64 sum of a float array (fixed shape tree, independent of timing)

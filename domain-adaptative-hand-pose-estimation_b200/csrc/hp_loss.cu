@@ -67,15 +67,14 @@ __global__ void __launch_bounds__(TPM* MPB)
                 }
             } else {
                 // mean over HW of 0.5*w*(p-t)^2  (loss.py:59-65)
-                const float Lw = static_cast<float>(0.5 * static_cast<double>(w) * static_cast<double>(st.sum[0]) /
-                                                   static_cast<double>(HW));
+                const float Lw = 0.5f * w * (st.sum[0] / static_cast<float>(HW));
                 per_map[map] = Lw;
                 if (mean) fx_acc_add(ws->acc, Lw);
             }
         }
     }
     if (mean == nullptr && per_sample == nullptr) return;
-    if (last_block_arrives(&ws->counter, gridDim.x)) {
+    if (last_block_arrives_writers(&ws->counter, gridDim.x, t == 0 && map < n_maps)) {
         if (per_sample) per_sample_means(per_map, n_maps / K, K, per_sample, threadIdx.x, TPM * MPB);  // KL 'none'
         if (mean && threadIdx.x == 0) {
             // MSE 'mean' = mean over all elements = mean over maps of the per-map means (equal HW)
