@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(TPM* MPB)
             if (hit) atomicAdd(&ws->counts[k], 1);
         }
     }
-    if (last_block_arrives(&ws->counter, gridDim.x)) pck_publish(ws, K, counts_out, acc_out);
+    if (last_block_arrives_writers(&ws->counter, gridDim.x, t == 0 && map < n_maps)) pck_publish(ws, K, counts_out, acc_out);
 }
 
 __global__ void pck_accumulate_kernel(const float* __restrict__ pred_xy, const float* __restrict__ tgt_xy, int n_maps,
