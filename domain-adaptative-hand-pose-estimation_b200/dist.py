@@ -88,7 +88,7 @@ class PeerExchange:
             torch.cuda.synchronize(self.device)
             if dist.is_initialized():
                 dist.barrier(group=self.group)     # nobody unmaps while a peer may still write
-            with _lib.on_device(self.device):
+            with self._lib.on_device(self.device):
                 for m in self._mapped:
                     self._lib.call("hp_peer_close", m)
                 self._lib.call("hp_peer_free", self._own)
