@@ -363,8 +363,7 @@ class MultiscaleEval:
                       C.c_float(self.coef[2]), _lib.ptr(tgt), B, K, H, W, C.c_double(self.thr), _lib.ptr(pred_xy),
                       _lib.ptr(maxvals), _lib.ptr(counts), _lib.ptr(acc), _lib.ptr(ws), _lib.stream_ptr(dev))
             if hpdist.is_distributed(self.group):
-                c64 = counts.to(torch.float64)
-                hpdist.allreduce_partial(c64, self.group)
-                counts = c64.to(torch.int32)
+                # the path's one collective: integer sum of the 2K hit / valid counts (exact, order-free)
+                torch.distributed.all_reduce(counts, op=torch.distributed.ReduceOp.SUM, group=self.group)
                 _lib.call("hp_pck_finalize", _lib.ptr(counts), K, _lib.ptr(acc), _lib.stream_ptr(dev))
         return acc, pred_xy, counts

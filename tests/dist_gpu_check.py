@@ -55,6 +55,16 @@ def main():
     torch.cuda.synchronize()
     for o in nouts:
         assert np.array_equal(o.partial.cpu().numpy(), part), ("nccl", o.partial.cpu().numpy(), part)
+    # configs[3]: sharded fuse + decode + PCK; the all-reduced counts and accuracies must equal the unsharded ones
+    Bm = 10
+    dm = hp.synth.make_host_batch(9100, Bm, 21, 128, 128, image_size=512)
+    mid_h, lo_h = hp.synth.make_lowres_heads(9101, dm["pred"], (64, 32))
+    tgt_h = np.random.RandomState(9102).randint(0, 128, size=(Bm, 21, 2)).astype(np.float32)
+    lo_m, hi_m = hp.dist.shard_bounds(Bm, rank, world)
+    tm = lambda a, sl: torch.from_numpy(a[sl]).to(dev)
+    sl = slice(lo_m, hi_m)
+    acc_s, _, counts_s = hp.MultiscaleEval(21)(tm(lo_h, sl), tm(mid_h, sl), tm(dm["pred"], sl), tm(tgt_h, sl))
+    acc_s, counts_s = acc_s.cpu().numpy(), counts_s.cpu().numpy()
     # single-GPU reference on the whole batch (group of one rank)
     solo_group = dist.new_group(ranks=[rank]) if False else None
     dist.barrier()
@@ -68,6 +78,9 @@ def main():
     for g in got:
         assert g["mse"] == want["mse"] and g["kl"] == want["kl"], (g, want)
         assert np.array_equal(g["acc"], want["acc"]) and g["cnt"] == want["cnt"] and g["avg_acc"] == want["avg_acc"]
+    full = slice(0, Bm)
+    acc_f, _, counts_f = hp.MultiscaleEval(21)(tm(lo_h, full), tm(mid_h, full), tm(dm["pred"], full), tm(tgt_h, full))
+    assert np.array_equal(counts_s, counts_f.cpu().numpy()) and np.array_equal(acc_s, acc_f.cpu().numpy()), "sharded C4 differs"
     if rank == 0:
         from oracle import hp_oracle as O
         o = O.pipeline(d["pred"], d["joints"], d["vis"], kl_epsilon=1e-7)
