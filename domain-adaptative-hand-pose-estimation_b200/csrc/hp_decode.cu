@@ -11,6 +11,7 @@
 #include "hp_decode.cuh"
 #include "hp_dispatch.cuh"
 #include "hp_internal.cuh"
+#include "hp_decode_staged.cuh"
 
 namespace hp {
 
@@ -174,6 +175,11 @@ extern "C" HP_API int hp_accuracy(const float* output, const float* target, int 
     HP_REQUIRE(B > 0 && K > 0 && K <= HP_MAX_K && H > 0 && W > 0 && static_cast<long long>(H) * W < (1ll << 30),
                HP_ERR_SHAPE, "hp_accuracy: bad shape B=%d K=%d H=%d W=%d", B, K, H, W);
     HP_REQUIRE(aligned8(acc_out) && aligned8(workspace), HP_ERR_ALIGN, "hp_accuracy: misaligned output");
+    {   // 64x64 maps: warp-private copy-engine stages (hp_decode_staged.cuh); everything else: block per map
+        const int rc = launch_accuracy_staged(output, target, B * K, K, H, W, thr, pred_xy, counts, acc_out,
+                                              static_cast<Workspace*>(workspace), static_cast<cudaStream_t>(stream));
+        if (rc != 1) return rc;
+    }
     AccuracyLaunch l{output, target, B * K, K, H, W, thr, pred_xy, counts, acc_out,
                      static_cast<Workspace*>(workspace), static_cast<cudaStream_t>(stream)};
     dispatch_map_walk(H * W, aligned16(output) && aligned16(target), l);

@@ -10,6 +10,7 @@
 // Roofline: HBM.  Algorithmic bytes per map: forward 2*HW*4 read; backward 2*HW*4 read + HW*4 written.
 #include "hp_common.cuh"
 #include "hp_dispatch.cuh"
+#include "hp_loss_staged.cuh"
 
 namespace hp {
 
@@ -193,6 +194,11 @@ extern "C" HP_API int hp_mse_fwd(const float* output, const float* target, const
                                  float* per_map, float* mean, void* workspace, hp_stream_t stream) {
     if (int rc = check_loss_args("hp_mse_fwd", output, target, B, K, HW)) return rc;
     HP_REQUIRE(per_map && workspace, HP_ERR_NULL, "hp_mse_fwd: null output");
+    {   // 64x64 maps: warp-private copy-engine stages (hp_loss_staged.cuh); everything else: block per map
+        const LossStagedArgs sa{output, target, weight, 0.f, B * K, K, per_map, nullptr, mean, nullptr, static_cast<Workspace*>(workspace)};
+        const int rc = launch_loss_fwd_staged<false>(sa, HW, static_cast<cudaStream_t>(stream), "hp_mse_fwd");
+        if (rc != 1) return rc;
+    }
     LossFwdLaunch<false> l{output, target, weight, 0.f, B * K, K, HW, per_map, nullptr, mean, nullptr,
                            static_cast<Workspace*>(workspace), static_cast<cudaStream_t>(stream)};
     dispatch_map_walk<true>(HW, aligned16(output) && aligned16(target), l);
@@ -216,6 +222,11 @@ extern "C" HP_API int hp_kl_fwd(const float* output, const float* target, const 
                                 void* workspace, hp_stream_t stream) {
     if (int rc = check_loss_args("hp_kl_fwd", output, target, B, K, HW)) return rc;
     HP_REQUIRE(per_map && workspace, HP_ERR_NULL, "hp_kl_fwd: null output");
+    {
+        const LossStagedArgs sa{output, target, weight, epsilon, B * K, K, per_map, per_sample, mean, stats, static_cast<Workspace*>(workspace)};
+        const int rc = launch_loss_fwd_staged<true>(sa, HW, static_cast<cudaStream_t>(stream), "hp_kl_fwd");
+        if (rc != 1) return rc;
+    }
     LossFwdLaunch<true> l{output, target, weight, epsilon, B * K, K, HW, per_map, per_sample, mean, stats,
                           static_cast<Workspace*>(workspace), static_cast<cudaStream_t>(stream)};
     dispatch_map_walk<true>(HW, aligned16(output) && aligned16(target), l);

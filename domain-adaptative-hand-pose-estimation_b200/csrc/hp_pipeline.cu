@@ -296,6 +296,7 @@ static int launch_pipeline(const float* pred, const double* joints, const float*
     a.thr = thr;
     const double t2 = thr * thr;
     a.thr2_lo = static_cast<float>(t2 * (1.0 - 1e-4)); a.thr2_hi = static_cast<float>(t2 * (1.0 + 1e-4));
+    if (thr <= 0.0) a.thr2_lo = a.thr2_hi = -1.0f;  // d < thr never holds (the fp32 pre-test must not see thr^2)
     a.inv_nx = static_cast<float>(10.0 / H); a.inv_ny = static_cast<float>(10.0 / W);  // norm = (H/10, W/10) on (x, y)
     a.loss_mask = loss_mask; a.pred_xy = pred_xy; a.maxvals = maxvals; a.weight_out = weight_out;
     a.partial = partial; a.accumulate = accumulate; a.result = result; a.ws = static_cast<Workspace*>(workspace);

@@ -41,6 +41,7 @@ struct RDArgs {
     const int32_t* centres;
     int splits;
     FastDiv wdiv;
+    unsigned producer_sleep_ns;  // staged kernels: back-off of the producer warp's poll on an empty-barrier
     // forward
     float* per_map;
     float* per_sample;
@@ -238,7 +239,7 @@ __global__ void __launch_bounds__(NT + 32, rds_blocks_per_sm<NT, DENSE>()) regdi
                 load_meta(smp + 1);
             }
             if (lane == 0) {
-                if (q >= kst) mbar_wait(empty_u32 + 8 * (q % kst), static_cast<uint32_t>(q / kst - 1) & 1u);
+                if (q >= kst) mbar_wait_backoff(empty_u32 + 8 * (q % kst), static_cast<uint32_t>(q / kst - 1) & 1u, a.producer_sleep_ns);
                 request(q);
             }
             __syncwarp();
@@ -519,6 +520,8 @@ static int launch_regdisp_staged(RDArgs a, cudaStream_t stream, const char* who)
         if (sms <= 0) sms = 148;
     }
     a.wdiv = FastDiv(static_cast<uint32_t>(a.ow));
+    a.producer_sleep_ns = 200;
+    if (const char* e = getenv("HP_RD_SLEEP")) a.producer_sleep_ns = static_cast<unsigned>(atoi(e));  // comparison runs
     const bool want_gf = a.mode == HP_MODE_MAX;
     const bool fused = want_gf && a.fused != nullptr && a.variant != HP_RD_X1 && a.variant != HP_RD_RD4;
     const bool dense = fused || (want_gf && (a.variant == HP_RD_BASE || a.variant == HP_RD_X6 || a.variant == HP_RD_RD4));

@@ -29,6 +29,14 @@ template <int ID, int NTHREADS>
 __device__ __forceinline__ void named_barrier() {
     asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(NTHREADS) : "memory");
 }
+// the pair barrier of stage `st` (< 4) of a block whose warp pairs share one stage each: ids 1..4 as immediates, so
+// that the kernel reserves five hardware barriers, not all sixteen (0 is __syncthreads)
+__device__ __forceinline__ void pair_barrier(int st) {
+    if (st == 0) named_barrier<1, 64>();
+    else if (st == 1) named_barrier<2, 64>();
+    else if (st == 2) named_barrier<3, 64>();
+    else named_barrier<4, 64>();
+}
 __device__ __forceinline__ uint64_t l2_evict_first_policy() {
     uint64_t pol;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
@@ -60,6 +68,18 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     unsigned int spins = 0;
     while (!mbar_try_wait(bar, parity))
         if (++spins > (1u << 24)) __trap();
+}
+
+// the same wait for a warp whose only job is to wait (a producer warp on an empty-barrier): sleep between the polls so
+// that the spin loop does not take issue slots from the computing warps of its scheduler (ncu: 8 % of all executed
+// warp-instructions of the dense disparity kernel were this loop)
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity, unsigned ns) {
+    if (mbar_try_wait(bar, parity)) return;
+    unsigned int spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (ns) __nanosleep(ns);
+        if (++spins > (1u << 24)) __trap();
+    }
 }
 
 __device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }

@@ -7,7 +7,7 @@ the BASELINE.json parity configs C2..C5 measured per GPU, for DESIGN.md / BASELI
 
 Timing: CUDA events around `reps` back-to-back calls on rotating input sets (>= 3 sets, each larger than or
 rotating past the 126 MB L2), after 5 warm-up calls.  bytes = algorithmic bytes per call as listed per row."""
-import argparse, importlib, json, os, sys, time
+import argparse, importlib, json, os, re, sys, time
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -17,6 +17,7 @@ hp = importlib.import_module("domain-adaptative-hand-pose-estimation_b200")
 ap = argparse.ArgumentParser()
 ap.add_argument("--out", default=None)
 ap.add_argument("--reps", type=int, default=30)
+ap.add_argument("--only", default=None, help="regular expression: time only the rows whose name matches")
 args = ap.parse_args()
 dev = torch.device("cuda", 0)
 PEAK = 6450.3
@@ -29,6 +30,8 @@ rows = []
 
 
 def timed(name, fn, n_sets, bytes_per_call, maps_per_call, note=""):
+    if args.only and not re.search(args.only, name):
+        return
     for i in range(5):
         fn(i % n_sets)
     torch.cuda.synchronize()

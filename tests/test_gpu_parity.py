@@ -418,6 +418,80 @@ def test_block_fusion_kernel_equals_row_walking_kernels_bit_for_bit(sizes, monke
     assert np.array_equal(got["pred"], p_o)
 
 
+@pytest.mark.parametrize("B", [3, 256])
+def test_staged_loss_and_accuracy_kernels_equal_block_kernels(B, monkeypatch):
+    """64x64 maps take the warp-private copy-engine kernels (hp_loss_staged.cuh, hp_decode_staged.cuh); the block-per-map
+    kernels (HP_LOSS_SHAPE=b / HP_ACC_SHAPE=b) and the oracle are the witnesses for both staged shapes (one warp or a
+    warp pair per stage): decoded coordinates, PCK counts and
+    accuracies bit-identical, losses / gradients 1e-5 - at the BASELINE.json batch (warps own 6-7 maps each, the
+    stage phases alternate) and on a tiny batch, on inputs holding NaN, +-inf, an all -inf map, exact ties, an all-zero
+    target and zero weights."""
+    K, S = 21, 64
+    d = hp.synth.make_host_batch(7300 + B, B, K, S, S, image_size=4 * S)
+    pred = d["pred"].copy()
+    tg = hp.generate_target_batch(torch.from_numpy(d["joints"]).cuda(), torch.from_numpy(d["vis"]).cuda(), (S, S), 2,
+                                  (4 * S, 4 * S))
+    tgt = np.ascontiguousarray(tg[0].cpu().numpy(), dtype=np.float32).reshape(B, K, S, S)
+    w = np.ascontiguousarray(tg[1].cpu().numpy(), dtype=np.float32).reshape(B, K, 1)
+    pred_edge = pred.copy()
+    pred_edge[0, 0, 3, 5] = np.nan
+    pred_edge[0, 1, 7, 7] = np.inf
+    pred_edge[0, 2, 1, 1], pred_edge[0, 2, 9, 9] = np.inf, -np.inf
+    pred_edge[0, 3] = -np.inf
+    pred_edge[0, 4] = 0.0
+    pred_edge[0, 4, 5, 9] = pred_edge[0, 4, 5, 3] = 2.0
+    pred_edge[0, 5] = -0.0
+    pred_edge[0, 5, 2, 2] = 0.0
+    t = lambda a: torch.from_numpy(a).cuda()
+
+    def run(p_np):
+        out = {}
+        acc, avg, cnt, xy = hp.accuracy(t(p_np), t(tgt))
+        out["acc"], out["avg"], out["cnt"], out["xy"] = acc, np.float64(avg), np.int64(cnt), xy.cpu().numpy()
+        for name, crit in (("mse", hp.JointsMSELoss()), ("mse_none", hp.JointsMSELoss("none")),
+                           ("kl", hp.JointsKLLoss(epsilon=1e-7)), ("kl_none", hp.JointsKLLoss("none", 1e-7)),
+                           ("kl_eps0", hp.JointsKLLoss(epsilon=0.0))):
+            x = t(p_np).requires_grad_(True)
+            l = crit(x, t(tgt), t(w))
+            out[name] = l.detach().cpu().numpy()
+            if p_np is pred:
+                l.sum().backward()
+                out[name + "_grad"] = x.grad.cpu().numpy()
+        out["kl_now"] = hp.JointsKLLoss(epsilon=1e-7)(t(p_np), t(tgt)).cpu().numpy()
+        return out
+
+    for p_np, what0 in ((pred, "synthetic"), (pred_edge, "edge maps")):
+        monkeypatch.setenv("HP_LOSS_SHAPE", "b")
+        monkeypatch.setenv("HP_ACC_SHAPE", "b")
+        ref = run(p_np)
+        runs = {}
+        for shape in ("1", "2"):        # one warp / a warp pair per stage, for every operator
+            monkeypatch.setenv("HP_LOSS_SHAPE", shape)
+            monkeypatch.setenv("HP_ACC_SHAPE", shape)
+            runs[f"{shape} warp(s) per stage"] = run(p_np)
+        monkeypatch.delenv("HP_LOSS_SHAPE")
+        monkeypatch.delenv("HP_ACC_SHAPE")
+        runs["production shapes"] = got = run(p_np)
+        for shape, res in runs.items():
+            what = f"{what0}, {shape}"
+            for k in ("acc", "avg", "cnt", "xy"):
+                assert np.array_equal(res[k], ref[k], equal_nan=True), f"{what}: {k} differs between the staged and block kernels"
+            for k in res:
+                if k in ("acc", "avg", "cnt", "xy"):
+                    continue
+                assert np.array_equal(np.isnan(res[k]), np.isnan(ref[k])), f"{what}: {k} NaN pattern"
+                scale = 1e-9 + (1e-6 * np.nanmax(np.abs(ref[k])) if k.endswith("_grad") else 0.0)
+                np.testing.assert_allclose(res[k], ref[k], rtol=1e-5, atol=scale, equal_nan=True, err_msg=f"{what}: {k}")
+        what = what0
+        # the oracle on the same inputs
+        a_o, avg_o, cnt_o, xy_o = O.accuracy(p_np, tgt)
+        assert np.array_equal(got["xy"], xy_o) and np.array_equal(got["acc"], a_o) and got["cnt"] == cnt_o, what
+        kl_o = O.joints_kl_loss(torch.from_numpy(p_np), torch.from_numpy(tgt), torch.from_numpy(w), "mean", 1e-7).numpy()
+        mse_o = O.joints_mse_loss(torch.from_numpy(p_np), torch.from_numpy(tgt), torch.from_numpy(w), "mean").numpy()
+        np.testing.assert_allclose(got["kl"], kl_o, rtol=1e-5, equal_nan=True, err_msg=what)
+        np.testing.assert_allclose(got["mse"], mse_o, rtol=1e-5, equal_nan=True, err_msg=what)
+
+
 def test_foreign_criterion_gets_materialised_maps():
     I = cases.disparity_inputs()
     y, adv, w = (torch.from_numpy(I[k]).cuda() for k in ("y", "adv64", "w"))
