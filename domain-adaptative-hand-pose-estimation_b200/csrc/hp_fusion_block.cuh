@@ -207,8 +207,8 @@ struct BlockCtl {
 // time (0 = g.strip at run time) - with a known even trip count the loop is unrolled by two and the rows carried from
 // one block to the next (and the prefetched `hi` rows) are renamed instead of moved (ncu attributed 9 % of all
 // executed instructions to those loop-edge moves).  Measured on B200: strips of 2 (64x64 outputs) gain 6 %
-// (66.4 -> 62.3 us); strips of 8 (128x128) spill at the 128-register bound of four blocks per SM and lose 6 %, so
-// they keep the run-time loop.
+// (66.4 -> 62.3 us); strips of 8 (128x128) spill at the 128-register bound of four blocks per SM and lose 6 %
+// (three blocks per SM with 164 registers: 109.8 vs 104.6 us - the kernel needs its 16 warps), so they keep the run-time loop.
 template <int SL, int SM, bool DECODE, int STRIP>
 __global__ void __launch_bounds__(32 * kBlockMaxWarps, 4)
     fuse_block_kernel(const FuseSrc f, const BlockWalk g, int n_maps, float* __restrict__ out, const float* __restrict__ tgt_xy,
