@@ -152,17 +152,39 @@ def compute_uv_from_heatmaps(hm, resize_dim):
     return uvc.view(-1, K, 3)[:, :, :2]
 
 
+_MAX_K = 64   # HP_MAX_K of include/hp_b200.h (per-joint counters of the fused decode kernel)
+
+
 def compute_uv_from_heatmaps2(hm, resize_dim):
-    """utils/keypoint_detection.py:174-205: bilinear resize, argmax -> int64 [B,K,2] (x, y) zeroed where max <= 0."""
-    resized, (H, W) = _resized(hm, resize_dim)
-    B, K = resized.shape[:2]
-    idx, maxvals = _argmax_idx(resized)
-    idx = idx.to(torch.int64).view(B, K, 1)
-    preds = idx.repeat(1, 1, 2)
-    preds[:, :, 0] = preds[:, :, 0] % W
-    preds[:, :, 1] = torch.div(preds[:, :, 1], W, rounding_mode="floor")
-    preds *= torch.greater(maxvals.view(B, K, 1), 0.0).repeat(1, 1, 2)
-    return preds
+    """utils/keypoint_detection.py:174-205: bilinear resize, argmax -> int64 [B,K,2] (x, y) zeroed where max <= 0.
+
+    One launch: the resized map is decoded in registers and never written (``hp_fuse_decode_pck`` with a single
+    source and weight 1 - the arithmetic of :func:`fusion.upsample_bilinear`, so the same map bit for bit); the
+    kernel's coordinates are already ``idx % W``, ``idx // W`` masked by ``max > 0``."""
+    hm = _lib.require_cuda(hm.detach(), "compute_uv_from_heatmaps2")
+    size = (resize_dim, resize_dim) if isinstance(resize_dim, int) else (int(resize_dim[0]), int(resize_dim[1]))
+    B, K = hm.shape[:2]
+    H, W = size
+    if K > _MAX_K:   # the two-launch composition (materialised resize, then the decode kernel)
+        resized, _ = _resized(hm, resize_dim)
+        idx, maxvals = _argmax_idx(resized)
+        idx = idx.to(torch.int64).view(B, K, 1)
+        preds = idx.repeat(1, 1, 2)
+        preds[:, :, 0] = preds[:, :, 0] % W
+        preds[:, :, 1] = torch.div(preds[:, :, 1], W, rounding_mode="floor")
+        preds *= torch.greater(maxvals.view(B, K, 1), 0.0).repeat(1, 1, 2)
+        return preds
+    dev = hm.device
+    pred_xy = torch.empty((B, K, 2), dtype=torch.float32, device=dev)
+    maxvals = torch.empty((B, K, 1), dtype=torch.float32, device=dev)
+    tgt = torch.zeros((B * K, 2), dtype=torch.float32, device=dev)      # the kernel also scores PCK; unused here
+    acc = torch.empty((K + 2,), dtype=torch.float64, device=dev)
+    with _lib.on_device(dev):
+        ws = _lib.workspace(dev, B * K, K)
+        _lib.call("hp_fuse_decode_pck", _lib.ptr(hm), hm.shape[2], hm.shape[3], C.c_float(1.0), None, 0, 0, C.c_float(0.0),
+                  None, C.c_float(0.0), _lib.ptr(tgt), B, K, H, W, C.c_double(0.5), _lib.ptr(pred_xy), _lib.ptr(maxvals),
+                  None, _lib.ptr(acc), _lib.ptr(ws), _lib.stream_ptr(dev))
+    return pred_xy.to(torch.int64)
 
 
 def compute_uv_from_heatmaps3(heatmap, beta=100.0, scale=4.0):
