@@ -7,9 +7,9 @@ checker / the timed CPU baseline.  The product path (the package next to this di
 never imports it and fails loudly when the CUDA library is missing.
 
 Parity status: PINNED.  The reference ships no tests or golden vectors, so
-the pin is (i) ``oracle/validate_against_reference.py`` / ``tests/test_oracle_vs_reference.py``
-which execute the real reference from ``/root/reference`` (via ``oracle/ref_loader.py``) next
-to this restatement on seeded inputs and demand bit-equality, and (ii) the committed
+the pin is (i) ``tests/test_oracle_vs_reference.py``,
+which executes the real reference from ``/root/reference`` (via ``oracle/ref_loader.py``) next
+to this restatement on seeded inputs and demands bit-equality, and (ii) the committed
 fixtures in ``tests/golden/`` that ``oracle/gen_golden.py`` produced FROM THE REAL REFERENCE.
 
 The restatement keeps the reference's *algorithmic structure* (host numpy argmax, the
