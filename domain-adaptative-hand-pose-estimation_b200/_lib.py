@@ -37,6 +37,7 @@ RD_BASE, RD_X1, RD_X5, RD_X6, RD_RD4 = 0, 1, 2, 3, 4
 MODE_MIN, MODE_MAX = 0, 1
 GRAD_SCALAR, GRAD_PER_MAP, GRAD_PER_SAMPLE = 0, 1, 2
 MAX_K = 64
+PEER_MAX_K = 27                 # sharded with collective='peer': 2*(4+2K+6) <= 128 mailbox entries per source
 
 _vp, _i, _f, _d, _sz = C.c_void_p, C.c_int, C.c_float, C.c_double, C.c_size_t
 

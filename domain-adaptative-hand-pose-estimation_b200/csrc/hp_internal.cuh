@@ -45,6 +45,13 @@ __device__ __forceinline__ unsigned long long peer_load(const unsigned long long
     return v;
 }
 constexpr int kPeerScratchWords = kPeerMaxWorld * (kPeerSlotEntries / 2);  // int64 words of shared-memory scratch
+// what the exchange can carry: a K-joint partial vector is n = 4+2K+6 int64 = 2n tagged entries per source slot, and
+// the receiver tracks world*n (source, word) pairs in 32 lanes x 32 pending bits.  Every entry point that accepts a
+// PeerLink with world > 1 checks this (K <= 27; the slots are NOT sized from HP_MAX_K).
+inline bool peer_shape_ok(int K, int world) {
+    const int n = 4 + 2 * K + 6;
+    return world <= 1 || (world <= kPeerMaxWorld && 2 * n <= kPeerSlotEntries && world * n <= 1024);
+}
 // ONE warp: vec[0..n) (shared memory; this rank's int64 vector) -> sum over all ranks, in rank order, in place.
 // `scratch`: kPeerScratchWords int64 of shared memory.  The (source, word) pairs are spread over the lanes and
 // polled eight at a time, so a pass over all sources costs one or two memory round trips however many ranks

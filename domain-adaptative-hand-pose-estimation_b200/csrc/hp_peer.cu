@@ -104,7 +104,7 @@ int launch_finalize_peer(const long long* partial, void* const* mailboxes, int r
                          long long* partial_out, double* result, int overlap, cudaStream_t stream) {
     HP_REQUIRE(partial && mailboxes && result, HP_ERR_NULL, "hp_pipeline_finalize_peer: null pointer");
     HP_REQUIRE(world > 0 && world <= kPeerMaxWorld && rank >= 0 && rank < world && K > 0 && K <= HP_MAX_K && seq >= 0 &&
-                   2 * (4 + 2 * K + 6) <= kPeerSlotEntries,
+                   peer_shape_ok(K, world),
                HP_ERR_ARG, "hp_pipeline_finalize_peer: rank=%d world=%d K=%d seq=%lld", rank, world, K, seq);
     HP_REQUIRE(seq == 0, HP_ERR_ARG, "hp_pipeline_finalize_peer: seq=%lld (the step is counted on the device: pass 0)", seq);
     PeerArgs a{};

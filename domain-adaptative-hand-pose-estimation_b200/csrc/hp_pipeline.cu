@@ -270,7 +270,7 @@ static int pipeline_shape_choice() {
         const char* e = std::getenv("HP_PIPE_SHAPE");
         if (!e) return 1;
         if (e[0] == 't' || e[0] == 'T') return 0;       // "tiles": the register-tile kernels
-        if (e[0] >= '1' && e[0] <= '4') return e[0] - '0';
+        if (e[0] >= '1' && e[0] <= '6') return e[0] - '0';
         return 1;
     }();
     return choice;
@@ -326,6 +326,9 @@ static int launch_pipeline(const float* pred, const double* joints, const float*
             t.overlap = pipeline_grid_div_override() ? pipeline_grid_div_override() : (depth ? depth : 4);
         }
         if (link && link->world > 1 && accumulate == 0) {  // the kernel's last block does the exchange itself
+            HP_REQUIRE(peer_shape_ok(K, link->world), HP_ERR_SHAPE,
+                       "hp_pipeline_fused: K=%d world=%d exceeds the peer mailbox (2*(4+2K+6) <= %d entries per source, "
+                       "world*(4+2K+6) <= 1024)", K, link->world, kPeerSlotEntries);
             t.link = *link;
             if (exchanged) *exchanged = true;
         }
@@ -344,6 +347,10 @@ static int launch_pipeline(const float* pred, const double* joints, const float*
                 case 2: e = launch_bulk<32, false, 6, 1, 2>(t, sms, stream); break;
                 case 3: e = launch_bulk<32, false, 12, 1, 1>(t, sms, stream); break;
                 case 4: e = launch_bulk<32, false, 3, 1, 4>(t, sms, stream); break;
+                // experiments: the map in 4 KB / 8 KB chunks with their own barriers and an online-softmax merge, so that
+                // the arithmetic on the first chunks overlaps the flight of the last one (shorter start-up and drain)
+                case 5: t.n_chunks = 4; e = launch_bulk<8, true, 4, 4, 3>(t, sms, stream); break;
+                case 6: t.n_chunks = 2; e = launch_bulk<16, true, 4, 2, 3>(t, sms, stream); break;
                 default: e = launch_bulk<32, false, 4, 1, 3>(t, sms, stream); break;
             }
         }
@@ -460,6 +467,8 @@ extern "C" HP_API int hp_pipeline_fused_peer(const float* pred, const double* jo
     HP_REQUIRE(world > 0 && world <= kPeerMaxWorld && rank >= 0 && rank < world && seq == 0, HP_ERR_ARG,
                "hp_pipeline_fused_peer: rank=%d world=%d seq=%lld (the step is counted on the device: pass 0)", rank,
                world, static_cast<long long>(seq));
+    HP_REQUIRE(peer_shape_ok(K, world), HP_ERR_SHAPE,
+               "hp_pipeline_fused_peer: K=%d world=%d exceeds the peer mailbox (K <= 27 when sharded)", K, world);
     PeerLink link{};
     for (int r = 0; r < world; ++r) {
         HP_REQUIRE(mailboxes[r], HP_ERR_NULL, "hp_pipeline_fused_peer: mailbox %d is null", r);
@@ -509,6 +518,8 @@ extern "C" HP_API int hp_pipeline_plan_create(const float* pred, const double* j
     HP_REQUIRE(world >= 0 && world <= kPeerMaxWorld && (world <= 1 || (mailboxes && rank >= 0 && rank < world && result &&
                                                                       accumulate == 0)),
                HP_ERR_ARG, "hp_pipeline_plan_create: rank=%d world=%d", rank, world);
+    HP_REQUIRE(peer_shape_ok(K, world), HP_ERR_SHAPE,
+               "hp_pipeline_plan_create: K=%d world=%d exceeds the peer mailbox (K <= 27 when sharded)", K, world);
     hp_plan* p = new (std::nothrow) hp_plan{};
     HP_REQUIRE(p, HP_ERR_ARG, "hp_pipeline_plan_create: out of host memory");
     p->pred = pred; p->joints = joints; p->vis = vis; p->B = B; p->K = K; p->H = H; p->W = W;

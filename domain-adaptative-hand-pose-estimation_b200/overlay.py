@@ -2,6 +2,10 @@
 
     python hpb200.py --ref /path/to/reference train1.py data/H3D -t Hand3DStudio ...
     python hpb200.py --ref /path/to/reference test.py  data/H3D -t Hand3DStudio --checkpoint ...
+    options before the driver: --verbose | --device-targets (rebind the per-sample generate_target too; needs
+    --workers 0) | --plugin FILE.py (run FILE after the overlay is installed and before the driver, e.g. to register a
+    synthetic dataset class in ``uda.dataset`` or a stand-in backbone in ``uda.model`` under a name the driver's
+    ``-s/-t/-a`` flags can select)
 
 The reference has no plugin registry: its hot-path callables are plain names imported at
 ``train1.py:18-32`` from modules that also hold the models.  So the drop-in is an overlay
@@ -35,8 +39,13 @@ REPLACED = (
     "RegressionDisparity2", "RegressionDisparity3", "RegressionDisparity4", "RegressionDisparity5",   # row f3
     "RegressionDisparity6", "RegressionDisparity7", "RegressionDisparity8",
     "RegressionDisparityx2", "RegressionDisparityx3", "RegressionDisparityx4", "JointsMSELoss0", "JointsKLLoss5",
-    "generate_target",                                              # uda/dataset/util.py
 )
+#: rebound only with ``--device-targets``: the datasets call ``generate_target`` per sample from ``__getitem__``
+#: inside DataLoader WORKER processes (train1.py defaults to ``--workers 4``, fork start method), where the parent's
+#: CUDA context cannot be used - so by default the dataset side keeps the reference's numpy version and the batched
+#: CUDA generator is an explicit choice (``generate_target_batch`` / ``target.DeviceTargetCollate``; needs
+#: ``--workers 0`` when rebound per sample)
+OPT_IN = ("generate_target",)                                       # uda/dataset/util.py
 
 #: reference modules that define the names above (imported before rebinding)
 DEFINING_MODULES = ("utils.keypoint_detection", "uda.model.loss", "uda.model.regda_4", "uda.model.regda_7",
@@ -103,8 +112,11 @@ def install_shims():
             pass
 
 
-def install(ref_root: str, verbose: bool = False):
-    """Shim, import and rebind.  Returns ``{module_name: [rebound names]}``."""
+def install(ref_root: str, verbose: bool = False, device_targets: bool = False, route_upsample: bool = True):
+    """Shim, import and rebind.  Returns ``{module_name: [rebound names]}``.
+    ``device_targets``: also rebind the per-sample ``generate_target`` (see OPT_IN).
+    ``route_upsample``: send ``nn.Upsample(mode='bilinear')`` of detached CUDA fp32 heatmaps (train1.py:410-417) to
+    ``hp_fuse_multiscale`` (row a12)."""
     ref_root = os.path.abspath(ref_root)
     if not os.path.isfile(os.path.join(ref_root, "utils", "keypoint_detection.py")):
         raise FileNotFoundError(f"{ref_root} does not look like the reference tree")
@@ -116,7 +128,7 @@ def install(ref_root: str, verbose: bool = False):
     originals = {}
     for modname in DEFINING_MODULES:
         mod = importlib.import_module(modname)
-        for name in REPLACED:
+        for name in REPLACED + (OPT_IN if device_targets else ()):
             if hasattr(mod, name) and getattr(mod, name).__module__ == mod.__name__:
                 originals.setdefault(name, []).append(getattr(mod, name))   # regda_4 and regda_7 both define some
     rebound = {}
@@ -128,20 +140,60 @@ def install(ref_root: str, verbose: bool = False):
             if any(mod.__dict__.get(name) is o for o in origs):
                 setattr(mod, name, getattr(pkg, name))
                 rebound.setdefault(modname, []).append(name)
+    if route_upsample:
+        install_upsample_route()
     if verbose:
         for m in sorted(rebound):
             print(f"[hpb200 overlay] {m}: {', '.join(sorted(rebound[m]))}", file=sys.stderr)
     return rebound
 
 
+_UPSAMPLE_ROUTED = False
+
+
+def install_upsample_route():
+    """train1.py:410-417 / test.py:362-369 build ``nn.Upsample(size=64|32, mode='bilinear')`` inline and apply them
+    to DETACHED adversarial heatmaps.  The drivers must stay unchanged, so the route is on ``nn.Upsample.forward``:
+    a bilinear, align_corners-free upsample of a CUDA fp32 4-D tensor that carries no autograd history goes to the
+    gather+blend kernel (``fusion.upsample_bilinear`` -> ``hp_fuse_multiscale``); everything else (other modes,
+    tensors that need gradients - e.g. inside a model -, CPU tensors, scale_factor forms) takes torch's own path."""
+    global _UPSAMPLE_ROUTED
+    if _UPSAMPLE_ROUTED:
+        return
+    import torch
+    import torch.nn as nn
+    fusion = importlib.import_module(__package__ + ".fusion")
+    stock = nn.Upsample.forward
+
+    def forward(self, input):
+        size = self.size
+        if (self.mode == "bilinear" and not self.align_corners and size is not None and isinstance(input, torch.Tensor)
+                and input.is_cuda and input.dtype == torch.float32 and input.dim() == 4
+                and not (input.requires_grad and torch.is_grad_enabled())):
+            hw = (size, size) if isinstance(size, int) else tuple(int(v) for v in size)
+            if len(hw) == 2 and hw[0] >= input.shape[2] and hw[1] >= input.shape[3]:
+                return fusion.upsample_bilinear(input, hw)
+        return stock(self, input)
+
+    nn.Upsample.forward = forward
+    _UPSAMPLE_ROUTED = True
+
+
 def main(argv=None):
     argv = list(sys.argv[1:] if argv is None else argv)
     ref = os.environ.get("HP_REF_DIR")
-    verbose = False
+    verbose = device_targets = False
+    plugins = []
     while argv and argv[0].startswith("--"):
         if argv[0] == "--ref" and len(argv) > 1:
             ref = argv[1]
             argv = argv[2:]
+        elif argv[0] == "--plugin" and len(argv) > 1:
+            plugins.append(argv[1])
+            argv = argv[2:]
+        elif argv[0] == "--device-targets":
+            device_targets = True
+            argv = argv[1:]
         elif argv[0] == "--verbose":
             verbose = True
             argv = argv[1:]
@@ -152,7 +204,9 @@ def main(argv=None):
         print("error: give the reference tree with --ref DIR or HP_REF_DIR", file=sys.stderr)
         return 2
     script = argv[0] if os.path.isabs(argv[0]) else os.path.join(ref, argv[0])
-    install(ref, verbose=verbose)
+    install(ref, verbose=verbose, device_targets=device_targets)
+    for path in plugins:       # launcher-side registrations (e.g. a synthetic dataset / a stand-in backbone by name)
+        runpy.run_path(path, run_name="__hpb200_plugin__")
     sys.argv = [script] + argv[1:]
     runpy.run_path(script, run_name="__main__")
     return 0

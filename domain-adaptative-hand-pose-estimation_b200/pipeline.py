@@ -12,6 +12,7 @@ dataset-side ``generate_target``)::
 """
 from __future__ import annotations
 
+import collections
 import ctypes as C
 from dataclasses import dataclass
 
@@ -51,7 +52,9 @@ class PipelineResult:
 
 
 class _Plan:
-    """Owner of one C-side plan handle (``hp_plan_t``) and of the tensors whose pointers it stores."""
+    """Owner of one C-side plan handle (``hp_plan_t``) and of the library-side tensors whose pointers it stores
+    (outputs, workspace, table, mailboxes).  ``keep`` holds the caller's input tensors only for plans made through
+    the explicit :meth:`HeatmapPipeline.plan`; the implicit per-call cache never pins inputs."""
 
     def __init__(self, handle, keep):
         self.handle, self.keep = handle, keep
@@ -92,26 +95,21 @@ class HeatmapPipeline:
             self.tab = _lib.gaussian_table(sigma, self.tmp, self.device)
         self._host_state = None
         self._ws = None
-        self._plans = {}
-        self._fast = {}
+        self._plans = collections.OrderedDict()     # small LRU of pre-bound launches (see _cached_plan)
         self._comm_stream = None
         if collective not in ("nccl", "peer"):
             raise ValueError("collective must be 'nccl' or 'peer'")
         self.collective = collective      # how the sharded path sums the partial vectors (dist.PeerExchange / NCCL)
+        if collective == "peer" and hpdist.is_distributed(group) and self.K > _lib.PEER_MAX_K:
+            raise ValueError(f"num_keypoints={self.K} exceeds what the peer mailboxes carry (K <= {_lib.PEER_MAX_K}); "
+                             "use collective='nccl'")
         self._peer = None
         _lib.load()
 
     # ------------------------------------------------------------------------------ device path
-    def plan(self, pred, joints, vis, out=None, finalize=True, overlap=False):
-        """Validate once and return ``(launch, out)``: ``launch()`` enqueues the fused kernel on the
-        current stream with pre-bound arguments (a ~15 us kernel leaves no room for per-call Python
-        argument checking; this is also what gets captured into CUDA graphs).
-
-        ``overlap`` (HP_PIPE_OVERLAP_PREV): ``True`` or a depth 1..8 - the launch is part of a train of
-        launches over batches that are already resident and may run concurrently with the previous
-        ``depth - 1`` launches on the stream (it writes nothing before they have completed; results are
-        bit-identical).  ``pred``, ``joints`` and ``vis`` must not be written by the kernel launched right
-        before this one, and consecutive launches need different ``out`` buffers."""
+    def _check(self, pred, joints, vis):
+        """-> contiguous CUDA (pred fp32, joints fp64, vis fp32) of the pipeline's shape; converts fp16/bf16 and
+        non-contiguous views (fresh copies: such calls are never cached)."""
         pred = _lib.require_cuda(pred, "HeatmapPipeline(pred)")
         joints = _lib.require_cuda(joints, "HeatmapPipeline(joints)", torch.float64)
         vis = _lib.require_cuda(vis, "HeatmapPipeline(vis)")
@@ -120,15 +118,28 @@ class HeatmapPipeline:
             raise ValueError(f"pred is {tuple(pred.shape)}, pipeline was built for K={self.K} H={self.H} W={self.W}")
         if joints.numel() != 2 * B * K or vis.numel() != B * K:
             raise ValueError("joints must be [B,K,2] and vis [B,K,1]")
-        dev = pred.device
-        if dev != self.device:
-            raise ValueError(f"inputs are on {dev}, the pipeline was built for {self.device}")
-        if out is None:
-            out = self.alloc_outputs(B, dev)
-        ws = self._workspace(B * K)
-        return self._bind(pred, joints, vis, out, ws, finalize, overlap, None), out
+        if pred.device != self.device:
+            raise ValueError(f"inputs are on {pred.device}, the pipeline was built for {self.device}")
+        return pred, joints, vis
 
-    def _bind(self, pred, joints, vis, out, ws, finalize, overlap, peer):
+    def plan(self, pred, joints, vis, out=None, finalize=True, overlap=False):
+        """Validate once and return ``(launch, out)``: ``launch()`` enqueues the fused kernel on the
+        current stream with pre-bound arguments (a ~15 us kernel leaves no room for per-call Python
+        argument checking; this is also what gets captured into CUDA graphs).  The plan keeps the three
+        input tensors alive; write new batches INTO them (``pred.copy_(...)``) between launches.
+
+        ``overlap`` (HP_PIPE_OVERLAP_PREV): ``True`` or a depth 1..8 - the launch is part of a train of
+        launches over batches that are already resident and may run concurrently with the previous
+        ``depth - 1`` launches on the stream (it writes nothing before they have completed; results are
+        bit-identical).  ``pred``, ``joints`` and ``vis`` must not be written by the kernel launched right
+        before this one, and consecutive launches need different ``out`` buffers."""
+        pred, joints, vis = self._check(pred, joints, vis)
+        if out is None:
+            out = self.alloc_outputs(pred.shape[0], pred.device)
+        ws = self._workspace(pred.shape[0] * self.K)
+        return self._bind(pred, joints, vis, out, ws, finalize, overlap, None, True), out
+
+    def _bind(self, pred, joints, vis, out, ws, finalize, overlap, peer, keep_inputs):
         """Arguments validated and stored once on the C side (``hp_pipeline_plan_create``); the returned ``launch()``
         is a two-argument FFI call (a step is a ~12 us kernel: per-call marshalling of 25 arguments costs as much)."""
         lib = _lib.load()
@@ -142,13 +153,15 @@ class HeatmapPipeline:
                   _lib.ptr(out.result) if finalize else None, _lib.ptr(ws),
                   peer._table if peer is not None else None, peer.rank if peer is not None else 0,
                   peer.world if peer is not None else 1, C.c_uint(_lib.pipe_flags(overlap)), C.byref(handle))
-        plan = _Plan(handle, (pred, joints, vis, out, ws, peer, self.tab))   # the plan owns references: pointers stay valid
+        # the plan owns references to what the LIBRARY side allocated; the caller's inputs only on request
+        plan = _Plan(handle, (out, ws, peer, self.tab) + ((pred, joints, vis) if keep_inputs else ()))
         fn = lib.hp_pipeline_plan_launch
-        current_stream = torch.cuda.current_stream
+        raw_stream = torch._C._cuda_getCurrentRawStream
+        dev_index = dev.index if dev.index is not None else torch.cuda.current_device()
         last_error = lib.hp_last_error
 
         def launch(_plan=plan, _h=handle):
-            rc = fn(_h, current_stream(dev).cuda_stream)
+            rc = fn(_h, raw_stream(dev_index))
             if rc != 0:
                 raise RuntimeError(f"hp_pipeline_plan_launch failed (rc={rc}): {last_error().decode(errors='replace')}")
         return launch
@@ -156,23 +169,19 @@ class HeatmapPipeline:
     def plan_peer(self, pred, joints, vis, out=None, overlap=False):
         """Sharded step with the peer-memory exchange as ONE call (``hp_pipeline_fused_peer``): the fused kernel on
         this rank's slice, then the exchange + finalise kernel, both on the current stream."""
-        pred = _lib.require_cuda(pred, "HeatmapPipeline(pred)")
-        joints = _lib.require_cuda(joints, "HeatmapPipeline(joints)", torch.float64)
-        vis = _lib.require_cuda(vis, "HeatmapPipeline(vis)")
-        B, K, H, W = pred.shape
-        if (K, H, W) != (self.K, self.H, self.W):
-            raise ValueError(f"pred is {tuple(pred.shape)}, pipeline was built for K={self.K} H={self.H} W={self.W}")
-        if joints.numel() != 2 * B * K or vis.numel() != B * K:
-            raise ValueError("joints must be [B,K,2] and vis [B,K,1]")
-        dev = pred.device
-        if dev != self.device:
-            raise ValueError(f"inputs are on {dev}, the pipeline was built for {self.device}")
+        pred, joints, vis = self._check(pred, joints, vis)
         if out is None:
-            out = self.alloc_outputs(B, dev)
+            out = self.alloc_outputs(pred.shape[0], pred.device)
+        ws = self._workspace(pred.shape[0] * self.K)
+        return self._bind(pred, joints, vis, out, ws, True, overlap, self._peer_link(), True), out
+
+    def _peer_link(self):
         if self._peer is None:
+            if self.K > _lib.PEER_MAX_K:
+                raise ValueError(f"num_keypoints={self.K} exceeds what the peer mailboxes carry "
+                                 f"(K <= {_lib.PEER_MAX_K}); use collective='nccl'")
             self._peer = hpdist.PeerExchange(self.device, self.group)
-        ws = self._workspace(B * K)
-        return self._bind(pred, joints, vis, out, ws, True, overlap, self._peer), out
+        return self._peer
 
     def _workspace(self, n_maps):
         """One zero-initialised workspace per pipeline object (a pipeline is used on one stream at a time)."""
@@ -180,21 +189,45 @@ class HeatmapPipeline:
         if self._ws is None or self._ws.numel() < need:
             with _lib.on_device(self.device):
                 self._ws = torch.zeros(max(need, 1 << 16), dtype=torch.uint8, device=self.device)
+            self._plans.clear()          # plans hold the old workspace pointer
         return self._ws
 
-    def _cached_plan(self, pred, joints, vis, out, finalize, overlap=False):
-        key = (pred.data_ptr(), joints.data_ptr(), vis.data_ptr(), id(out), pred.shape[0], finalize, int(overlap))
-        hit = self._plans.get(key)
-        if hit is None:
-            if len(self._plans) > 256:
-                self._plans.clear()
-            hit = self.plan(pred, joints, vis, out, finalize, overlap)
-            self._plans[key] = hit
-        return hit
+    _PLAN_CACHE = 32
+
+    def _launcher(self, pred, joints, vis, out, finalize, overlap, peer):
+        """``(launch, out)`` for one call.  Pre-bound launches are cached ONLY when the caller's tensors are used in
+        place (CUDA, right dtype, contiguous: no private copy that could go stale) and the caller supplied ``out``;
+        the key is the set of device addresses + the batch size, the cache holds no reference to the inputs (an
+        entry whose memory was freed can only be hit again by tensors that own the same addresses) and is a
+        32-entry LRU.  Anything else - fp16/bf16 or strided inputs, ``out=None`` - is validated, converted and
+        bound per call."""
+        cacheable = (out is not None and isinstance(pred, torch.Tensor) and pred.is_cuda and pred.dtype == torch.float32
+                     and pred.is_contiguous() and isinstance(joints, torch.Tensor) and joints.is_cuda
+                     and joints.dtype == torch.float64 and joints.is_contiguous() and isinstance(vis, torch.Tensor)
+                     and vis.is_cuda and vis.dtype == torch.float32 and vis.is_contiguous())
+        if cacheable:
+            key = (pred.data_ptr(), joints.data_ptr(), vis.data_ptr(), out.result.data_ptr(), out.pred_xy.data_ptr(),
+                   out.partial.data_ptr(), pred.shape[0], finalize, int(overlap), peer)
+            plans = self._plans
+            hit = plans.get(key)
+            if hit is not None:
+                plans.move_to_end(key)
+                return hit, out
+        pred, joints, vis = self._check(pred, joints, vis)
+        if out is None:
+            out = self.alloc_outputs(pred.shape[0], pred.device)
+        ws = self._workspace(pred.shape[0] * self.K)
+        launch = self._bind(pred, joints, vis, out, ws, finalize, overlap, self._peer_link() if peer else None,
+                            not cacheable)
+        if cacheable:
+            self._plans[key] = launch
+            while len(self._plans) > self._PLAN_CACHE:
+                self._plans.popitem(last=False)
+        return launch, out
 
     def launch_local(self, pred, joints, vis, out=None, overlap=False) -> PipelineResult:
         """This rank's kernel only (finalised locally, no collective)."""
-        launch, out = self._cached_plan(pred, joints, vis, out, True, overlap)
+        launch, out = self._launcher(pred, joints, vis, out, True, overlap, False)
         launch()
         return out
 
@@ -204,45 +237,35 @@ class HeatmapPipeline:
         one kernel.  Sharded (torch.distributed initialised): kernel -> all-reduce of the 4+2K partial
         doubles (the path's only collective) -> finalise kernel; with ``collective="peer"`` the exchange over
         NVLink peer memory happens inside the kernel's last block instead (one kernel per step, no NCCL)."""
-        fkey = (id(pred), id(joints), id(vis), id(out), overlap)
-        fast = self._fast.get(fkey)
-        if fast is not None:             # same tensors as an earlier call: the pre-bound launch, nothing else
-            fast[0]()
-            return fast[1]
         sharded = hpdist.is_distributed(self.group)
         if not sharded or self.collective == "peer":
-            hit = self.plan_peer(pred, joints, vis, out, overlap) if sharded else self.plan(pred, joints, vis, out, True, overlap)
-            if len(self._fast) > 256:
-                self._fast.clear()
-            self._fast[fkey] = (hit[0], hit[1], (pred, joints, vis, out))   # the tensors stay alive: ids stay unique
-            hit[0]()
-            return hit[1]
+            launch, out = self._launcher(pred, joints, vis, out, True, overlap, sharded)
+            launch()
+            return out
         # NCCL collective: kernel on this stream, all-reduce + finalise on a side stream
-        launch, out = self._cached_plan(pred, joints, vis, out, not sharded, overlap)
-        if sharded and out.ready is not None:
+        launch, out = self._launcher(pred, joints, vis, out, False, overlap, False)
+        if out.ready is not None:
             # `out` is being reused: its previous collective (side stream) must have consumed it first
             torch.cuda.current_stream(self.device).wait_event(out.ready)
         launch()
-        if sharded:
-            # NCCL: the collective and the finalise run on a side stream so that they overlap the NEXT step's
-            # kernel (steps are independent; `out.ready` / `out.wait()` order consumers after them).
-            main = torch.cuda.current_stream(self.device)
-            if self._comm_stream is None:
-                self._comm_stream = torch.cuda.Stream(device=self.device)
-            comm = self._comm_stream
-            comm.wait_stream(main)
-            with torch.cuda.stream(comm):
-                hpdist.allreduce_partial(out.partial, self.group)
-                _lib.call("hp_pipeline_finalize", _lib.ptr(out.partial), self.K, _lib.ptr(out.result),
-                          C.c_void_p(comm.cuda_stream))
-                if out.ready is None:
-                    out.ready = torch.cuda.Event()
-                out.ready.record(comm)
+        # NCCL: the collective and the finalise run on a side stream so that they overlap the NEXT step's
+        # kernel (steps are independent; `out.ready` / `out.wait()` order consumers after them).
+        main = torch.cuda.current_stream(self.device)
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream(device=self.device)
+        comm = self._comm_stream
+        comm.wait_stream(main)
+        with torch.cuda.stream(comm):
+            hpdist.allreduce_partial(out.partial, self.group)
+            _lib.call("hp_pipeline_finalize", _lib.ptr(out.partial), self.K, _lib.ptr(out.result),
+                      C.c_void_p(comm.cuda_stream))
+            if out.ready is None:
+                out.ready = torch.cuda.Event()
+            out.ready.record(comm)
         return out
 
     def close(self):
         """Release the peer mailboxes (collective; call on every rank before destroying the process group)."""
-        self._fast.clear()
         self._plans.clear()
         if self._peer is not None:
             self.join()

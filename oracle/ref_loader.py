@@ -2,7 +2,8 @@
 
 This file is part of the oracle: only ``tests/``, ``oracle/gen_golden.py`` and the
 oracle-validation script may import it.  It never ships with the product path and it
-only works where the reference tree exists (this container; NOT the GPU box).
+only works where the reference tree exists: /root/reference in this container, or the copy of its *.py files
+that oracle/ship_reference.py leaves under oracle/_ref/reference/ (git-ignored; travels to the GPU box).
 
 The reference does not import on a modern stack as shipped:
   * ``np.int`` / ``np.float`` were removed from numpy   (regda_4.py:80, regda_7.py:75,3033,3108,3195)
@@ -22,7 +23,8 @@ _CACHE = {}
 
 
 def reference_root():
-    for cand in (os.environ.get("HP_REF_DIR"), "/root/reference"):
+    shipped = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "reference")   # oracle/ship_reference.py
+    for cand in (os.environ.get("HP_REF_DIR"), "/root/reference", shipped):
         if cand and os.path.isfile(os.path.join(cand, "utils", "keypoint_detection.py")):
             return cand
     return None

@@ -195,3 +195,40 @@ def test_two_rank_gloo_sharding_reproduces_full_batch(tmp_path):
     outs = [p.communicate(timeout=300)[0] for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
+
+
+def test_peer_exchange_rejects_more_joints_than_the_mailboxes_carry(built_lib):
+    """K <= HP_MAX_K = 64 is fine on one GPU, but the peer mailboxes carry 2*(4+2K+6) <= 128
+    tagged entries per source -> K <= 27.  Every entry point that binds a PeerLink with world > 1 must refuse
+    K = 28..64 with a clean error instead of overrunning a (remote) mailbox.  Argument validation only: the fake
+    pointers are never dereferenced and nothing is launched."""
+    lib = L.load()
+    C = ctypes
+    fake = 0x10000                                   # non-null, 16-byte aligned
+    boxes = (C.c_void_p * 2)(fake, fake)
+    plan = C.c_void_p()
+
+    def create(K, world):
+        return lib.hp_pipeline_plan_create(fake, fake, fake, 4, K, 64, 64, C.c_double(4.0), C.c_double(4.0), 6, fake,
+                                           C.c_float(1e-7), C.c_double(0.5), 3, fake, fake, fake, fake, 0, fake, fake,
+                                           boxes, 0, world, C.c_uint(0), C.byref(plan))
+    assert create(32, 2) != 0 and b"peer mailbox" in lib.hp_last_error()
+    assert create(28, 2) != 0
+    assert create(27, 2) == 0 and plan.value
+    lib.hp_pipeline_plan_destroy(plan)
+    assert create(64, 1) == 0 and plan.value          # unsharded: up to HP_MAX_K
+    lib.hp_pipeline_plan_destroy(plan)
+    rc = lib.hp_pipeline_fused_peer(fake, fake, fake, 4, 32, 64, 64, C.c_double(4.0), C.c_double(4.0), 6, fake,
+                                    C.c_float(1e-7), C.c_double(0.5), 3, fake, fake, fake, fake, fake, fake, boxes, 0, 2,
+                                    C.c_int64(0), C.c_uint(0), None)
+    assert rc != 0 and b"peer mailbox" in lib.hp_last_error()
+    assert L.PEER_MAX_K == 27
+
+
+def test_generate_target_refuses_to_run_inside_a_loader_worker(monkeypatch):
+    """the per-sample CUDA generate_target must not be reached from a forked DataLoader worker."""
+    import torch.utils.data
+    T = importlib.import_module("domain-adaptative-hand-pose-estimation_b200.target")
+    monkeypatch.setattr(torch.utils.data, "get_worker_info", lambda: object())
+    with pytest.raises(RuntimeError, match="DataLoader worker"):
+        T.generate_target(np.zeros((21, 2)), np.ones((21, 1), np.float32), (64, 64), 2, (256, 256))

@@ -23,9 +23,20 @@ h3d, stb, rhd = (sys.modules["uda.dataset." + m] for m in ("hand_3d_studio", "ST
 ours = "domain-adaptative-hand-pose-estimation_b200"
 for obj in (PseudoLabelGenerator, RegressionDisparityx1, RegressionDisparityx5, PseudoLabelGenerator03,
             PseudoLabelGenerator01, RegressionDisparity, RegressionDisparityx6, JointsKLLoss, JointsMSELoss,
-            accuracy, get_max_preds, h3d.generate_target, stb.generate_target, rhd.generate_target,
-            r4.get_max_preds, r7.get_max_preds, r4.RegressionDisparity):
+            accuracy, get_max_preds, r4.get_max_preds, r7.get_max_preds, r4.RegressionDisparity):
     assert obj.__module__.startswith(ours), (obj, obj.__module__)
+# the dataset side (DataLoader workers) keeps the reference's numpy generate_target unless --device-targets is given
+import os
+for m in (h3d, stb, rhd):
+    if os.environ.get("HP_EXPECT_DEVICE_TARGETS") == "1":
+        assert m.generate_target.__module__.startswith(ours), m.generate_target.__module__
+    else:
+        assert m.generate_target.__module__ == "uda.dataset.util", m.generate_target.__module__
+# nn.Upsample(mode='bilinear') is routed (train1.py:410-417); on CPU tensors it must stay torch's own
+import torch, torch.nn as nn
+assert nn.Upsample.forward.__module__.startswith(ours)
+x = torch.arange(16.0).reshape(1, 1, 4, 4)
+assert torch.equal(nn.Upsample(size=8, mode="bilinear")(x), torch.nn.functional.interpolate(x, size=8, mode="bilinear"))
 # row f3: the variants the drivers import but never call are rebound too
 assert RegressionDisparity3.__module__.startswith(ours) and RegressionDisparity4.__module__.startswith(ours)
 from uda.model.loss import JointsMSELoss0, JointsKLLoss5
@@ -39,9 +50,12 @@ print("overlay-ok")
 '''
 
 
-def test_overlay_rebinds_every_driver_import(tmp_path):
+@pytest.mark.parametrize("device_targets", [False, True])
+def test_overlay_rebinds_every_driver_import(tmp_path, device_targets):
     probe = tmp_path / "driver_probe.py"
     probe.write_text(PROBE)
-    p = subprocess.run([sys.executable, "-W", "ignore", os.path.join(ROOT, "hpb200.py"), "--ref", ref_loader.reference_root(),
-                        str(probe), "data/H3D", "-t", "Hand3DStudio"], capture_output=True, text=True, timeout=300)
+    env = dict(os.environ, HP_EXPECT_DEVICE_TARGETS="1" if device_targets else "0")
+    p = subprocess.run([sys.executable, "-W", "ignore", os.path.join(ROOT, "hpb200.py"), "--ref", ref_loader.reference_root()]
+                       + (["--device-targets"] if device_targets else []) +
+                       [str(probe), "data/H3D", "-t", "Hand3DStudio"], capture_output=True, text=True, timeout=300, env=env)
     assert p.returncode == 0 and "overlay-ok" in p.stdout, p.stdout + p.stderr
