@@ -19,19 +19,21 @@ LIB_PATH = os.path.join(_HERE, "libhp_b200.so")
 # enums of include/hp_b200.h
 LOSS_MSE, LOSS_KL = 1, 2
 PIPE_OVERLAP_PREV = 1          # HP_PIPE_OVERLAP_PREV (include/hp_b200.h)
+PIPE_DEFER_EXCHANGE = 2        # HP_PIPE_DEFER_EXCHANGE
 
 
-def pipe_flags(overlap):
+def pipe_flags(overlap, defer=False):
     """False/0 -> serialised launch; True -> overlapped at the library's default depth; int d in 1..8 ->
-    HP_PIPE_OVERLAP_PREV | HP_PIPE_DEPTH(d)."""
+    HP_PIPE_OVERLAP_PREV | HP_PIPE_DEPTH(d).  ``defer`` adds HP_PIPE_DEFER_EXCHANGE (sharded steps)."""
+    extra = PIPE_DEFER_EXCHANGE if defer else 0
     if overlap is True:
-        return PIPE_OVERLAP_PREV
+        return PIPE_OVERLAP_PREV | extra
     d = int(overlap or 0)
     if d == 0:
-        return 0
+        return extra
     if not 1 <= d <= 8:
         raise ValueError(f"overlap depth must be 1..8, got {overlap!r}")
-    return PIPE_OVERLAP_PREV | (d << 8)
+    return PIPE_OVERLAP_PREV | (d << 8) | extra
 PLG_BASE, PLG_ONE_MINUS = 0, 1
 RD_BASE, RD_X1, RD_X5, RD_X6, RD_RD4 = 0, 1, 2, 3, 4
 MODE_MIN, MODE_MAX = 0, 1
@@ -85,8 +87,10 @@ PROTOTYPES = {
     "hp_peer_import": (_i, [_vp, _vp]),
     "hp_peer_close": (_i, [_vp]),
     "hp_pipeline_finalize_peer": (_i, [_vp, _vp, _i, _i, _i, C.c_int64, _vp, _vp, _vp]),
+    "hp_pipeline_flush_peer": (_i, [_vp, _vp, _i, _i, _vp]),
+    "hp_pck_finalize_peer": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "hp_pipeline_fused_host": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _d, _d, _i, _vp, _f, _d, _i, _i,
-                                    _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+                                    _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),
 }
 
 _lib = None

@@ -10,23 +10,26 @@ int launch_decode(const float* heat, int n_maps, int H, int W, float* preds, flo
                   int32_t* centres, int shift, cudaStream_t stream);
 
 // ---- peer mailboxes (hp_peer.cu) ---------------------------------------------------------------------------------
-// Layout (uint64 entries): slots[2 parities][world sources][kPeerSlotEntries], then 8 entries (entry 0: step counter).
+// Layout (uint64 entries): slots[kPeerRing steps][world sources][kPeerSlotEntries], then 8 entries (entry 0: step counter).
 // Protocol ("low latency", like NCCL's LL): every 8-byte entry carries 32 bits of payload and the 32-bit step
 // tag, and an aligned 8-byte store is single-copy atomic - so the sender just fires its stores (no fence, no
-// separate flag, one NVLink hop) and the receiver polls each entry until its tag is the current step.  An int64
-// of the partial vector travels as two entries.  Parity double-buffering: a rank can be at most one step ahead of
-// the slowest rank (it cannot finish step s+1 before it has received everybody's step-(s+1) vector).
+// separate flag, one NVLink hop) and the receiver polls each entry until its tag is the step it waits for.  An int64
+// of the partial vector travels as two entries.  Step q uses ring position q % kPeerRing.  A rank is never more than
+// two steps ahead of the slowest rank's SEND (synchronous exchange: it cannot finish step q before everybody has sent
+// step q; deferred exchange: step q+1 is only finished once everybody has sent step q), so a ring position is rewritten
+// long after every reader has consumed it.
 constexpr int kPeerSlotEntries = 128;   // >= 2 * (4 + 2K + 6)  ->  K <= 27
+constexpr int kPeerRing = 16;
 constexpr int kPeerMaxWorld = 16;
 struct PeerLink {                       // passed by value to kernels that do the exchange themselves
     unsigned long long* mailbox[kPeerMaxWorld];  // base of every rank's mailbox as mapped in this process
     int rank, world;                             // world <= 1: no exchange
 };
-__device__ __forceinline__ unsigned long long* peer_slot(unsigned long long* base, int world, int parity, int src) {
-    return base + (static_cast<size_t>(parity) * world + src) * kPeerSlotEntries;
+__device__ __forceinline__ unsigned long long* peer_slot(unsigned long long* base, int world, unsigned long long step, int src) {
+    return base + (static_cast<size_t>(step % kPeerRing) * world + src) * kPeerSlotEntries;
 }
 __device__ __forceinline__ unsigned long long* peer_counter(unsigned long long* base, int world) {
-    return base + static_cast<size_t>(2) * world * kPeerSlotEntries;
+    return base + static_cast<size_t>(kPeerRing) * world * kPeerSlotEntries;
 }
 __device__ __forceinline__ void peer_store2(unsigned long long* p, unsigned long long a, unsigned long long b) {
     asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
@@ -44,7 +47,8 @@ __device__ __forceinline__ unsigned long long peer_load(const unsigned long long
     asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-constexpr int kPeerScratchWords = kPeerMaxWorld * (kPeerSlotEntries / 2);  // int64 words of shared-memory scratch
+constexpr int kPeerRecvWords = kPeerMaxWorld * (kPeerSlotEntries / 2);  // landing area of peer_recv_sum (world * n words)
+constexpr int kPeerScratchWords = kPeerRecvWords + 144;                 // + one partial vector (4 + 2*HP_MAX_K + 6 <= 144): int64 words of shared-memory scratch
 // what the exchange can carry: a K-joint partial vector is n = 4+2K+6 int64 = 2n tagged entries per source slot, and
 // the receiver tracks world*n (source, word) pairs in 32 lanes x 32 pending bits.  Every entry point that accepts a
 // PeerLink with world > 1 checks this (K <= 27; the slots are NOT sized from HP_MAX_K).
@@ -52,34 +56,34 @@ inline bool peer_shape_ok(int K, int world) {
     const int n = 4 + 2 * K + 6;
     return world <= 1 || (world <= kPeerMaxWorld && 2 * n <= kPeerSlotEntries && world * n <= 1024);
 }
-// ONE warp: vec[0..n) (shared memory; this rank's int64 vector) -> sum over all ranks, in rank order, in place.
-// `scratch`: kPeerScratchWords int64 of shared memory.  The (source, word) pairs are spread over the lanes and
-// polled eight at a time, so a pass over all sources costs one or two memory round trips however many ranks
-// there are (polling source after source cost a round trip per rank: 5.6 us at 8 GPUs).
-// The step number is counted on the device (the rank's own mailbox), so captured graphs of steps replay.
-// Returns non-zero in every lane if a peer did not arrive within ~2 s.
-__device__ __forceinline__ int peer_exchange_warp(const PeerLink& link, long long* vec, long long* scratch, int n, int lane) {
-    const int world = link.world, rank = link.rank;
-    unsigned long long* counter = peer_counter(link.mailbox[rank], world);
-    const unsigned long long seq = peer_load(counter) + 1ull;
+// ONE warp: this rank's vector of step `seq` -> every rank's mailbox (its own included): a word travels as two tagged
+// 8-byte entries, written with one 16-byte store.  Fire and forget.
+__device__ __forceinline__ void peer_send(const PeerLink& link, const long long* vec, int n, unsigned long long seq, int lane) {
     const unsigned long long tag = (seq & 0xffffffffull) << 32;
-    const unsigned long long tag_mask = 0xffffffff00000000ull;
-    const int parity = static_cast<int>(seq & 1ull);
-    // ---- send: a word travels as two tagged 8-byte entries, written with one 16-byte store ---------------------
-    for (int dst = 0; dst < world; ++dst) {
-        unsigned long long* slot = peer_slot(link.mailbox[dst], world, parity, rank);
+    for (int dst = 0; dst < link.world; ++dst) {
+        unsigned long long* slot = peer_slot(link.mailbox[dst], link.world, seq, link.rank);
         for (int w = lane; w < n; w += 32) {
             const unsigned long long v = static_cast<unsigned long long>(vec[w]);
             peer_store2(slot + 2 * w, tag | (v & 0xffffffffull), tag | (v >> 32));
         }
     }
-    // ---- receive: pair p = src * n + w lives in lane p % 32, bit p / 32 of `pending` ------------------------------
+}
+// ONE warp: wait (bounded, ~2 s) until every rank's vector of step `seq` sits in this rank's mailbox and write the sum
+// over the ranks, in rank order, to out[0..n) (shared memory).  `scratch`: kPeerScratchWords int64 of shared memory.
+// The (source, word) pairs are spread over the lanes and polled eight at a time, so a pass over all sources costs one
+// or two memory round trips however many ranks there are (polling source after source cost a round trip per rank:
+// 5.6 us at 8 GPUs).  Returns non-zero in every lane on a timeout (missing contributions count as zero).
+__device__ __forceinline__ int peer_recv_sum(const PeerLink& link, long long* out, long long* scratch, int n,
+                                             unsigned long long seq, int lane) {
+    const int world = link.world;
+    const unsigned long long tag = (seq & 0xffffffffull) << 32;
+    const unsigned long long tag_mask = 0xffffffff00000000ull;
     const int total = world * n;
     const int kcount = (total + 31) >> 5;  // <= 32
     unsigned pending = 0;
     for (int k = 0; k < kcount; ++k)
         if (lane + 32 * k < total) pending |= 1u << k;
-    const unsigned long long* mine = peer_slot(link.mailbox[rank], world, parity, 0);
+    const unsigned long long* mine = peer_slot(link.mailbox[link.rank], world, seq, 0);
     int timeout = 0;
     const long long t0 = clock64();
     while (__any_sync(0xffffffffu, pending != 0)) {
@@ -114,15 +118,47 @@ __device__ __forceinline__ int peer_exchange_warp(const PeerLink& link, long lon
     for (int w = lane; w < n; w += 32) {
         long long tot = 0;
         for (int src = 0; src < world; ++src) tot += scratch[src * n + w];  // rank order
-        vec[w] = tot;
+        out[w] = tot;
     }
-    if (lane == 0) peer_store(counter, seq);
+    __syncwarp();
+    return timeout;
+}
+// The synchronous exchange of one step: vec[0..n) (shared memory; this rank's vector) -> totals over the ranks, in
+// place.  The step number is counted on the device (the rank's own mailbox), so captured graphs of steps replay.
+// A timed-out step is NOT counted: the next step re-uses its number, so ranks that did complete it and ranks that did
+// not cannot drift apart silently (the caller sees the poisoned result and stops).
+__device__ __forceinline__ int peer_exchange_warp(const PeerLink& link, long long* vec, long long* scratch, int n, int lane) {
+    unsigned long long* counter = peer_counter(link.mailbox[link.rank], link.world);
+    const unsigned long long seq = peer_load(counter) + 1ull;
+    peer_send(link, vec, n, seq, lane);
+    const int timeout = peer_recv_sum(link, vec, scratch, n, seq, lane);
+    if (lane == 0 && !timeout) peer_store(counter, seq);
     __syncwarp();
     return timeout;
 }
 
-// the per-step exchange + finalise over peer mailboxes (hp_peer.cu); `overlap` != 0: programmatic dependent launch
+// ---- deferred exchange (HP_PIPE_DEFER_EXCHANGE) --------------------------------------------------------------------
+// In a train of sharded steps the synchronous exchange puts an NVLink round trip - and the slowest rank's jitter - on
+// every step's critical path (SCALE_r01: 16.2 -> 18.7 us per step from 1 to 8 GPUs).  Deferred: step q only SENDS its
+// vector; the totals of step q-1, which every rank sent a whole step ago, are collected and finalised into step q-1's
+// OWN output buffers (remembered in the workspace) by step q's publisher, and the last step of a train by a one-warp
+// flush kernel (hp_pipeline_flush_peer).  Nothing on the step path waits for a peer that is less than a step late.
+struct PeerPending {
+    long long* partial;        // output buffers of the step whose totals are still outstanding
+    double* result;
+    unsigned long long seq;    // its step number
+    int K;
+    int valid;
+};
+constexpr size_t kPendOffsetBytes = 1024;  // of the PeerPending record inside the workspace (zero-initialised: invalid)
+__device__ __forceinline__ PeerPending* peer_pending(Workspace* ws) {
+    return reinterpret_cast<PeerPending*>(reinterpret_cast<unsigned char*>(ws) + kPendOffsetBytes);
+}
+
+// the per-step exchange + finalise over peer mailboxes (hp_peer.cu); `overlap` != 0: programmatic dependent launch;
+// `workspace` (nullable unless defer): where a deferred step is remembered; `defer`: see "deferred exchange" above
 int launch_finalize_peer(const long long* partial, void* const* mailboxes, int rank, int world, int K, long long seq,
-                         long long* partial_out, double* result, int overlap, cudaStream_t stream);
+                         long long* partial_out, double* result, int overlap, void* workspace, int defer,
+                         cudaStream_t stream);
 
 }  // namespace hp

@@ -18,6 +18,7 @@
 #include "hp_common.cuh"
 #include "hp_internal.cuh"
 #include "hp_pipeline_common.cuh"
+#include "hp_peer_step.cuh"
 
 namespace hp {
 
@@ -27,25 +28,65 @@ struct PeerArgs {
     int K;
     long long* partial_out;             // nullable: the reduced vector
     double* result;                     // [4+K]
+    Workspace* ws;                      // where a deferred step is remembered (a private dummy when the caller gave none)
+    int defer;
+    // hp_pck_finalize_peer: integer PCK counts instead of a partial vector
+    const int* counts;                  // [2K] hits, valid of this rank
+    int* counts_out;                    // [2K] totals
+    double* acc_out;                    // [K+2] acc[K], avg_acc, cnt
 };
 
-// one warp, a few registers, 9 KB of shared memory: always fits beside the resident pipeline blocks of a train
+// one warp, a few registers, ~11 KB of shared memory: always fits beside the resident pipeline blocks of a train
 __global__ void __launch_bounds__(32) pipeline_finalize_peer_kernel(const PeerArgs a) {
     __shared__ long long s_total[4 + 2 * HP_MAX_K + 6];
     __shared__ long long s_scratch[kPeerScratchWords];
+    __shared__ double s_acc[HP_MAX_K];
+    __shared__ Workspace s_dummy_ws[4];  // >= kPendOffsetBytes + sizeof(PeerPending): a pending record that is never valid
     const int n = 4 + 2 * a.K + 6, lane = threadIdx.x;
     // Programmatic dependent launch (no-ops without the launch attribute): the next pipeline launch of the train
     // may start right away; this kernel reads `partial` only once the pipeline launch before it has completed.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    Workspace* ws = a.ws;
+    if (!ws) {
+        for (int i = lane; i < static_cast<int>(sizeof(s_dummy_ws) / 8); i += 32) reinterpret_cast<long long*>(s_dummy_ws)[i] = 0;
+        __syncwarp();
+        ws = s_dummy_ws;
+    }
     for (int w = lane; w < n; w += 32) s_total[w] = a.partial[w];
     __syncwarp();
-    const int timeout = peer_exchange_warp(a.link, s_total, s_scratch, n, lane);
-    if (a.partial_out)
-        for (int w = lane; w < n; w += 32) a.partial_out[w] = s_total[w];
+    peer_step_warp(a.link, ws, s_total, s_scratch, s_acc, a.K, a.partial_out, a.result, a.ws ? a.defer : 0, lane);
+}
+
+// the last step of a deferred train: collect and finalise what is still outstanding
+__global__ void __launch_bounds__(32) pipeline_flush_peer_kernel(const PeerArgs a) {
+    __shared__ long long s_scratch[kPeerScratchWords];
+    __shared__ double s_acc[HP_MAX_K];
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    peer_flush_warp(a.link, a.ws, s_scratch, s_acc, threadIdx.x);
+}
+
+// configs[3]: sum of the 2K integer PCK counts over the ranks + the accuracy closure (keypoint_detection.py:80-90)
+__global__ void __launch_bounds__(32) pck_finalize_peer_kernel(const PeerArgs a) {
+    __shared__ long long s_total[4 + 2 * HP_MAX_K + 6];
+    __shared__ long long s_scratch[kPeerScratchWords];
+    __shared__ double s_acc[HP_MAX_K];
+    __shared__ double s_result[4 + HP_MAX_K];
+    __shared__ Workspace s_dummy_ws[4];
+    const int K = a.K, n = 4 + 2 * K + 6, lane = threadIdx.x;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    for (int i = lane; i < static_cast<int>(sizeof(s_dummy_ws) / 8); i += 32) reinterpret_cast<long long*>(s_dummy_ws)[i] = 0;
+    for (int w = lane; w < n; w += 32) s_total[w] = (w >= 4 && w < 4 + 2 * K) ? a.counts[w - 4] : 0;
+    __syncwarp();
+    peer_step_warp(a.link, s_dummy_ws, s_total, s_scratch, s_acc, K, nullptr, s_result, 0, lane);
+    const bool bad = s_result[3] != s_result[3];  // poisoned by a timeout
+    for (int i = lane; i < 2 * K; i += 32) a.counts_out[i] = bad ? -1 : static_cast<int>(s_total[4 + i]);
+    for (int k = lane; k < K; k += 32) a.acc_out[k] = s_result[4 + k];
     if (lane == 0) {
-        pipeline_result_from_partial(s_total, a.K, a.result);
-        if (timeout) a.result[0] = a.result[1] = __longlong_as_double(0x7ff8000000000000ll);
+        a.acc_out[K] = s_result[2];
+        a.acc_out[K + 1] = s_result[3];
     }
 }
 
@@ -55,7 +96,7 @@ using namespace hp;
 
 // ---- setup-time helpers (the only entry points of the library that own memory) -------------------------------
 extern "C" HP_API size_t hp_peer_mailbox_bytes(int world) {
-    return sizeof(unsigned long long) * (2 * static_cast<size_t>(world > 0 ? world : 1) * kPeerSlotEntries + 8);  // + step counter
+    return sizeof(unsigned long long) * (static_cast<size_t>(kPeerRing) * (world > 0 ? world : 1) * kPeerSlotEntries + 8);  // + step counter
 }
 
 extern "C" HP_API int hp_peer_alloc(int world, void** mailbox) {
@@ -100,21 +141,21 @@ extern "C" HP_API int hp_peer_close(void* mapped) {
 
 // ---- per step -----------------------------------------------------------------------------------------------------
 namespace hp {
-int launch_finalize_peer(const long long* partial, void* const* mailboxes, int rank, int world, int K, long long seq,
-                         long long* partial_out, double* result, int overlap, cudaStream_t stream) {
-    HP_REQUIRE(partial && mailboxes && result, HP_ERR_NULL, "hp_pipeline_finalize_peer: null pointer");
-    HP_REQUIRE(world > 0 && world <= kPeerMaxWorld && rank >= 0 && rank < world && K > 0 && K <= HP_MAX_K && seq >= 0 &&
+static int fill_link(const char* who, PeerLink& link, void* const* mailboxes, int rank, int world, int K) {
+    HP_REQUIRE(mailboxes, HP_ERR_NULL, "%s: null mailbox table", who);
+    HP_REQUIRE(world > 0 && world <= kPeerMaxWorld && rank >= 0 && rank < world && K > 0 && K <= HP_MAX_K &&
                    peer_shape_ok(K, world),
-               HP_ERR_ARG, "hp_pipeline_finalize_peer: rank=%d world=%d K=%d seq=%lld", rank, world, K, seq);
-    HP_REQUIRE(seq == 0, HP_ERR_ARG, "hp_pipeline_finalize_peer: seq=%lld (the step is counted on the device: pass 0)", seq);
-    PeerArgs a{};
-    a.partial = partial;
+               HP_ERR_ARG, "%s: rank=%d world=%d K=%d (K <= 27 when sharded)", who, rank, world, K);
     for (int r = 0; r < world; ++r) {
-        HP_REQUIRE(mailboxes[r], HP_ERR_NULL, "hp_pipeline_finalize_peer: mailbox %d is null", r);
-        a.link.mailbox[r] = static_cast<unsigned long long*>(mailboxes[r]);
+        HP_REQUIRE(mailboxes[r], HP_ERR_NULL, "%s: mailbox %d is null", who, r);
+        link.mailbox[r] = static_cast<unsigned long long*>(mailboxes[r]);
     }
-    a.link.rank = rank; a.link.world = world; a.K = K;
-    a.partial_out = partial_out; a.result = result;
+    link.rank = rank;
+    link.world = world;
+    return HP_OK;
+}
+template <typename Kernel>
+static int launch_one_warp(const char* who, Kernel kernel, const PeerArgs& a, int overlap, cudaStream_t stream) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(1);
     cfg.blockDim = dim3(32);
@@ -125,9 +166,22 @@ int launch_finalize_peer(const long long* partial, void* const* mailboxes, int r
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = overlap ? 1 : 0;
-    const cudaError_t e = cudaLaunchKernelEx(&cfg, pipeline_finalize_peer_kernel, a);
-    if (e != cudaSuccess) return fail(static_cast<int>(e), "hp_pipeline_finalize_peer: %s", cudaGetErrorString(e));
-    return launch_status("hp_pipeline_finalize_peer");
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, a);
+    if (e != cudaSuccess) return fail(static_cast<int>(e), "%s: %s", who, cudaGetErrorString(e));
+    return launch_status(who);
+}
+
+int launch_finalize_peer(const long long* partial, void* const* mailboxes, int rank, int world, int K, long long seq,
+                         long long* partial_out, double* result, int overlap, void* workspace, int defer,
+                         cudaStream_t stream) {
+    HP_REQUIRE(partial && result, HP_ERR_NULL, "hp_pipeline_finalize_peer: null pointer");
+    HP_REQUIRE(seq == 0, HP_ERR_ARG, "hp_pipeline_finalize_peer: seq=%lld (the step is counted on the device: pass 0)", seq);
+    HP_REQUIRE(!defer || workspace, HP_ERR_NULL, "hp_pipeline_finalize_peer: a deferred step needs the workspace");
+    PeerArgs a{};
+    if (int rc = fill_link("hp_pipeline_finalize_peer", a.link, mailboxes, rank, world, K)) return rc;
+    a.partial = partial; a.K = K; a.partial_out = partial_out; a.result = result;
+    a.ws = static_cast<Workspace*>(workspace); a.defer = defer;
+    return launch_one_warp("hp_pipeline_finalize_peer", pipeline_finalize_peer_kernel, a, overlap, stream);
 }
 }  // namespace hp
 
@@ -135,6 +189,24 @@ extern "C" HP_API int hp_pipeline_finalize_peer(const int64_t* partial, void* co
                                                 int K, int64_t seq, int64_t* partial_out, double* result,
                                                 hp_stream_t stream) {
     return launch_finalize_peer(reinterpret_cast<const long long*>(partial), mailboxes, rank, world, K,
-                                static_cast<long long>(seq), reinterpret_cast<long long*>(partial_out), result, 0,
+                                static_cast<long long>(seq), reinterpret_cast<long long*>(partial_out), result, 0, nullptr, 0,
                                 static_cast<cudaStream_t>(stream));
+}
+
+extern "C" HP_API int hp_pipeline_flush_peer(void* workspace, void* const* mailboxes, int rank, int world,
+                                             hp_stream_t stream) {
+    HP_REQUIRE(workspace, HP_ERR_NULL, "hp_pipeline_flush_peer: null workspace");
+    PeerArgs a{};
+    if (int rc = fill_link("hp_pipeline_flush_peer", a.link, mailboxes, rank, world, 1)) return rc;
+    a.ws = static_cast<Workspace*>(workspace);
+    return launch_one_warp("hp_pipeline_flush_peer", pipeline_flush_peer_kernel, a, 1, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" HP_API int hp_pck_finalize_peer(const int32_t* counts, void* const* mailboxes, int rank, int world, int K,
+                                           int32_t* counts_out, double* acc_out, hp_stream_t stream) {
+    HP_REQUIRE(counts && counts_out && acc_out, HP_ERR_NULL, "hp_pck_finalize_peer: null pointer");
+    PeerArgs a{};
+    if (int rc = fill_link("hp_pck_finalize_peer", a.link, mailboxes, rank, world, K)) return rc;
+    a.K = K; a.counts = counts; a.counts_out = counts_out; a.acc_out = acc_out;
+    return launch_one_warp("hp_pck_finalize_peer", pck_finalize_peer_kernel, a, 1, static_cast<cudaStream_t>(stream));
 }

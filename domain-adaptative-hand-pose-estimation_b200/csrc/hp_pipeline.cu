@@ -14,8 +14,10 @@
 // Algorithmic bytes per map: H*W*4 (pred) + 24 (joint, vis, weight) + 8 (coords) = 16,416 at 64x64.
 // Roofline: HBM.  Per element: 1 compare-select pair (argmax), 1 FFMA+MUFU+FADD (softmax),
 // 1 FADD (sum p), 1 FFMA (squared error); target terms only on the 13 rows the patch touches.
+#include <atomic>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 #include <new>
 
 #include "hp_common.cuh"
@@ -219,8 +221,26 @@ static int pipeline_grid_div_override() {
     return div;
 }
 // ---- TMA-staged shape (hp_pipeline_bulk.cuh) ---------------------------------------------------------------------
+// experiments: HP_PIPE_EPILOGUE=atomics keeps the workspace-atomics + ticket epilogue; HP_PIPE_STRICT_PDL=0 launches a
+// serialised step without the programmatic attribute (the next launch is then not even scheduled before this one ends)
+static bool pipeline_slots_enabled() {
+    static const bool on = []() {
+        const char* e = std::getenv("HP_PIPE_EPILOGUE");
+        return !(e && (e[0] == 'a' || e[0] == 'A'));
+    }();
+    return on;
+}
+static bool pipeline_strict_pdl() {
+    static const bool on = []() {
+        const char* e = std::getenv("HP_PIPE_STRICT_PDL");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+static std::atomic<unsigned int> g_launch_seq{0};
+
 template <int NITC, int LOSS, bool MULTI, int W, int KST, int BPS>
-static cudaError_t launch_bulk_one(const BulkArgs& t, int grid, cudaStream_t stream) {
+static cudaError_t launch_bulk_one(BulkArgs& t, int grid, cudaStream_t stream) {
     constexpr size_t smem = static_cast<size_t>(W) * KST * NITC * 512 + sizeof(uint64_t) * W * KST;
     static bool configured[16] = {};  // per device: opt in to > 48 KB of dynamic shared memory once
     int dev = 0;
@@ -231,6 +251,28 @@ static cudaError_t launch_bulk_one(const BulkArgs& t, int grid, cudaStream_t str
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < 16) configured[dev] = true;
     }
+    // ---- how the blocks hand their sums to the publisher: tagged slots when they fit, else atomics + ticket -----------
+    t.slot_bits = 0;
+    t.slots = reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(t.p.ws) + kSlotOffsetBytes);
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess) cap = cudaStreamCaptureStatusActive;
+    // (a captured launch replays with the SAME tag: stale slots of the previous replay would look fresh)
+    if (pipeline_slots_enabled() && cap == cudaStreamCaptureStatusNone && grid <= kSlotMaxBlocks) {
+        const int n_local = (t.p.n_maps + grid - 1) / grid;  // most maps any block owns = bound of every counter
+        const int bits = n_local <= 15 ? 4 : (n_local <= 255 ? 8 : (n_local <= 65535 ? 16 : 0));
+        if (bits != 0) {
+            const int n_counts = 2 * t.p.K + 6;
+            const int n_cent = (n_counts * bits + 31) / 32, n_ent = n_cent + 4, n_pairs = (n_ent + 1) / 2;
+            if (n_ent <= kSlotEntries && static_cast<long long>(grid) * n_pairs <= 128ll * 32 * W) {
+                unsigned int seq = ++g_launch_seq;
+                if (seq == 0) seq = ++g_launch_seq;
+                t.slot_bits = bits; t.n_cent = n_cent; t.n_pairs = n_pairs;
+                t.pdiv = FastDiv(static_cast<uint32_t>(n_pairs));
+                t.seq = seq;
+            }
+        }
+    }
+    t.strict = (t.overlap == 0 && pipeline_strict_pdl()) ? 1 : 0;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(static_cast<unsigned>(grid));
     cfg.blockDim = dim3(32 * W);
@@ -240,11 +282,11 @@ static cudaError_t launch_bulk_one(const BulkArgs& t, int grid, cudaStream_t str
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = t.overlap > 0 ? 1 : 0;
+    cfg.numAttrs = (t.overlap > 0 || t.strict) ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, pipeline_bulk_kernel<NITC, LOSS, MULTI, W, KST, BPS>, t);
 }
 template <int NITC, bool MULTI, int W, int KST, int BPS>
-static cudaError_t launch_bulk(const BulkArgs& t, int sms, cudaStream_t stream) {
+static cudaError_t launch_bulk(BulkArgs& t, int sms, cudaStream_t stream) {
     // persistent: BPS blocks per SM.  An overlapped launch may take only 1/div of the slots so that `div`
     // consecutive launches are resident at once, out of phase (their start-up and drain bubbles interleave).
     // The depth only pays while a launch is a few rounds long (its start-up and drain are then a third of its
@@ -330,6 +372,7 @@ static int launch_pipeline(const float* pred, const double* joints, const float*
                        "hp_pipeline_fused: K=%d world=%d exceeds the peer mailbox (2*(4+2K+6) <= %d entries per source, "
                        "world*(4+2K+6) <= 1024)", K, link->world, kPeerSlotEntries);
             t.link = *link;
+            t.defer = (flags & HP_PIPE_DEFER_EXCHANGE) ? 1 : 0;
             if (exchanged) *exchanged = true;
         }
         const size_t trace_words = static_cast<size_t>(kTraceBlockWords) * kTraceMaxBlocksPerSM * static_cast<size_t>(g_sm_count);
@@ -461,8 +504,8 @@ extern "C" HP_API int hp_pipeline_fused_peer(const float* pred, const double* jo
     if (int rc = check_pipeline("hp_pipeline_fused_peer", pred, joints, vis, B, K, H, W, stride_x, stride_y, tmp, tab,
                                 pred_xy, partial, workspace, loss_mask))
         return rc;
-    HP_REQUIRE((flags & ~(HP_PIPE_OVERLAP_PREV | HP_PIPE_DEPTH(15u))) == 0 && ((flags >> 8) & 15u) <= 8u, HP_ERR_ARG,
-               "hp_pipeline_fused_peer: bad flags 0x%x", flags);
+    HP_REQUIRE((flags & ~(HP_PIPE_OVERLAP_PREV | HP_PIPE_DEFER_EXCHANGE | HP_PIPE_DEPTH(15u))) == 0 && ((flags >> 8) & 15u) <= 8u,
+               HP_ERR_ARG, "hp_pipeline_fused_peer: bad flags 0x%x", flags);
     HP_REQUIRE(result && mailboxes, HP_ERR_NULL, "hp_pipeline_fused_peer: null pointer");
     HP_REQUIRE(world > 0 && world <= kPeerMaxWorld && rank >= 0 && rank < world && seq == 0, HP_ERR_ARG,
                "hp_pipeline_fused_peer: rank=%d world=%d seq=%lld (the step is counted on the device: pass 0)", rank,
@@ -486,7 +529,8 @@ extern "C" HP_API int hp_pipeline_fused_peer(const float* pred, const double* jo
     // other shapes: the separate exchange + finalise kernel
     return launch_finalize_peer(reinterpret_cast<const long long*>(partial), mailboxes, rank, world, K, 0,
                                 reinterpret_cast<long long*>(partial), result,
-                                (flags & HP_PIPE_OVERLAP_PREV) ? 1 : 0, static_cast<cudaStream_t>(stream));
+                                (flags & HP_PIPE_OVERLAP_PREV) ? 1 : 0, workspace, (flags & HP_PIPE_DEFER_EXCHANGE) ? 1 : 0,
+                                static_cast<cudaStream_t>(stream));
 }
 
 /* ---- pre-bound steps -------------------------------------------------------------------------------------------
@@ -513,8 +557,10 @@ extern "C" HP_API int hp_pipeline_plan_create(const float* pred, const double* j
     if (int rc = check_pipeline("hp_pipeline_plan_create", pred, joints, vis, B, K, H, W, stride_x, stride_y, tmp, tab,
                                 pred_xy, partial, workspace, loss_mask))
         return rc;
-    HP_REQUIRE((flags & ~(HP_PIPE_OVERLAP_PREV | HP_PIPE_DEPTH(15u))) == 0 && ((flags >> 8) & 15u) <= 8u, HP_ERR_ARG,
-               "hp_pipeline_plan_create: bad flags 0x%x", flags);
+    HP_REQUIRE((flags & ~(HP_PIPE_OVERLAP_PREV | HP_PIPE_DEFER_EXCHANGE | HP_PIPE_DEPTH(15u))) == 0 && ((flags >> 8) & 15u) <= 8u,
+               HP_ERR_ARG, "hp_pipeline_plan_create: bad flags 0x%x", flags);
+    HP_REQUIRE(!(flags & HP_PIPE_DEFER_EXCHANGE) || world > 1, HP_ERR_ARG,
+               "hp_pipeline_plan_create: HP_PIPE_DEFER_EXCHANGE needs a sharded step (world > 1)");
     HP_REQUIRE(world >= 0 && world <= kPeerMaxWorld && (world <= 1 || (mailboxes && rank >= 0 && rank < world && result &&
                                                                       accumulate == 0)),
                HP_ERR_ARG, "hp_pipeline_plan_create: rank=%d world=%d", rank, world);
@@ -554,7 +600,8 @@ extern "C" HP_API int hp_pipeline_plan_launch(const hp_plan* p, hp_stream_t stre
         return rc;
     if (exchanged) return HP_OK;
     return launch_finalize_peer(p->partial, p->mailboxes, p->link.rank, p->link.world, p->K, 0, p->partial, p->result,
-                                (p->flags & HP_PIPE_OVERLAP_PREV) ? 1 : 0, st);
+                                (p->flags & HP_PIPE_OVERLAP_PREV) ? 1 : 0, p->workspace,
+                                (p->flags & HP_PIPE_DEFER_EXCHANGE) ? 1 : 0, st);
 }
 
 extern "C" HP_API int hp_pipeline_plan_destroy(hp_plan* p) {
@@ -591,13 +638,17 @@ extern "C" HP_API int hp_pipeline_fused_host(const float* h_pred, const double* 
                                              const float* tab, float kl_epsilon, double thr, int loss_mask, int slab_B,
                                              float* d_pred, double* d_joints, float* d_vis, float* d_pred_xy,
                                              float* d_maxvals, float* d_weight, int64_t* d_partial, double* d_result,
-                                             void* workspace, float* h_pred_xy, double* h_result, hp_stream_t stream,
+                                             void* workspace, float* h_pred_xy, double* h_result,
+                                             void* const* mailboxes, int rank, int world, hp_stream_t stream,
                                              hp_stream_t copy_stream) {
     if (int rc = check_pipeline("hp_pipeline_fused_host", h_pred, h_joints, h_vis, B, K, H, W, stride_x, stride_y, tmp,
                                 tab, d_pred_xy, d_partial, workspace, loss_mask))
         return rc;
     HP_REQUIRE(d_pred && d_joints && d_vis && d_result && h_result, HP_ERR_NULL, "hp_pipeline_fused_host: null pointer");
     HP_REQUIRE(slab_B > 0, HP_ERR_ARG, "hp_pipeline_fused_host: slab_B=%d", slab_B);
+    const bool sharded = world > 1;
+    HP_REQUIRE(!sharded || (mailboxes && rank >= 0 && rank < world && world <= kPeerMaxWorld && peer_shape_ok(K, world)),
+               HP_ERR_ARG, "hp_pipeline_fused_host: rank=%d world=%d K=%d (K <= 27 when sharded)", rank, world, K);
     cudaStream_t cs = static_cast<cudaStream_t>(stream), xs = static_cast<cudaStream_t>(copy_stream);
     const size_t map_elems = static_cast<size_t>(H) * W;
     const int n_slabs = (B + slab_B - 1) / slab_B;
@@ -631,10 +682,13 @@ extern "C" HP_API int hp_pipeline_fused_host(const float* h_pred, const double* 
                              d_pred_xy + 2 * static_cast<size_t>(b0) * K,
                              d_maxvals ? d_maxvals + static_cast<size_t>(b0) * K : nullptr,
                              d_weight ? d_weight + static_cast<size_t>(b0) * K : nullptr,
-                             reinterpret_cast<long long*>(d_partial), s > 0 ? 1 : 0, last ? d_result : nullptr, workspace,
-                             cs);
+                             reinterpret_cast<long long*>(d_partial), s > 0 ? 1 : 0, (last && !sharded) ? d_result : nullptr,
+                             workspace, cs);
         if (rc == HP_OK) e = cudaEventRecord(drained[slot], cs);
     }
+    if (e == cudaSuccess && rc == HP_OK && sharded)  // the path's one collective: this rank's totals -> totals over the ranks
+        rc = launch_finalize_peer(reinterpret_cast<const long long*>(d_partial), mailboxes, rank, world, K, 0,
+                                  reinterpret_cast<long long*>(d_partial), d_result, 0, nullptr, 0, cs);
     if (e == cudaSuccess && rc == HP_OK)
         e = cudaMemcpyAsync(h_result, d_result, sizeof(double) * (4 + K), cudaMemcpyDeviceToHost, cs);
     if (e == cudaSuccess && rc == HP_OK && h_pred_xy)

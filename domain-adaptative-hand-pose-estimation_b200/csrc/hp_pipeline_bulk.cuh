@@ -20,6 +20,7 @@
 #pragma once
 #include "hp_internal.cuh"
 #include "hp_pipeline_common.cuh"
+#include "hp_peer_step.cuh"
 #include "hp_tma.cuh"
 #include "hp_pipeline_tiles.cuh"  // PatchSlot, WarpLoss, warp_sum3_scattered, kTileMaxPatch
 
@@ -32,6 +33,16 @@ struct BulkArgs {
     int overlap;    // 0: serialised launch; d >= 1: programmatic dependent launch on 1/d of the block slots, so that
                     // d consecutive launches are resident at once (HP_PIPE_OVERLAP_PREV | HP_PIPE_DEPTH(d))
     PeerLink link;  // world > 1: the last block sums the partial vector over the ranks itself (NVLink peer memory)
+    int defer;      // world > 1: deferred exchange (HP_PIPE_DEFER_EXCHANGE): this step only sends, and completes the previous one
+    // ---- block results through tagged slots (see "epilogue" below); slot_bits == 0: the atomics + ticket epilogue ----
+    int strict;           // serialised launch: wait for the previous grid BEFORE the first global read (the launch carries
+                          // the programmatic attribute only so that block scheduling and the prologue hide the launch gap)
+    unsigned int seq;     // tag of this launch (never 0, unique per process)
+    int slot_bits;        // bits per packed counter: 4 / 8 / 16 (every counter of a block is < 2^slot_bits); 0 = off
+    int n_cent;           // slot entries that carry packed counters; then 4 entries with the two fixed-point loss sums
+    int n_pairs;          // 16-byte entry pairs per slot
+    FastDiv pdiv;         // by n_pairs
+    unsigned long long* slots;  // [gridDim.x][kSlotEntries] in the workspace
     unsigned long long* trace;  // nullable profiling buffer (hp_debug_pipeline_trace): per block a header
                                 // {globaltimer, clock64} at entry and exit, per warp and map 4 clock64 stamps
 };
@@ -149,7 +160,125 @@ struct BulkShared {
     float4 out[kBulkOutCap];        // {x, y, maxval, weight} of the block's first maps
     long long pub[4 + 2 * HP_MAX_K + 6];
     double pub_acc[HP_MAX_K];
+    int tot_counts[2 * HP_MAX_K + 6];      // publisher block (slot epilogue): sums over the blocks' slots
+    unsigned long long tot_fx[4];          // low / high 32-bit halves of the two fixed-point loss sums, summed separately
 };
+
+// ---- block results through tagged slots ------------------------------------------------------------------------------
+// The classic "REDs into a workspace, __threadfence, atomic ticket, last block reads the workspace back" epilogue costs
+// every block two dependent L2 round trips (the fence waits for the REDs, the ticket for the fence) and the last block
+// a third one - 2-4.5 us of a ~20 us launch (profiles/r1_trace_serial.json: exit_after_barrier).  Here a block instead
+// PACKS its contribution (2K PCK counters + 6 non-finite counters at 4/8/16 bits each, two 64-bit fixed-point sums)
+// into <= 32 tagged 8-byte entries {payload:32, launch tag:32} and stores them into ITS slot with plain 16-byte stores:
+// data and "ready" travel together, so there is no fence, no ticket and nothing to zero afterwards.  The publisher
+// (the last block index: it owns the fewest maps) polls all slots with every thread, sums them in shared memory with
+// integer atomics (exact, order-free), and finalises.  One one-way store + one poll on the critical path.
+constexpr int kSlotEntries = 32;            // uint64 entries per block slot (256 B)
+constexpr int kSlotMaxBlocks = 1024;
+constexpr size_t kSlotOffsetBytes = 2048;   // of the slot array inside the workspace (after the Workspace header)
+__device__ __forceinline__ void slot_store2(unsigned long long* p, unsigned long long a, unsigned long long b) {
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+}
+__device__ __forceinline__ ulonglong2 slot_load2(const unsigned long long* p) {
+    ulonglong2 v;
+    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
+    return v;
+}
+// payload of slot entry e of THIS block (sh.counts / sh.acc are final: called after the block barrier)
+__device__ __forceinline__ unsigned int slot_entry_payload(const BulkArgs& t, const BulkShared& sh, int e) {
+    const int K = t.p.K, n_counts = 2 * K + 6, cb = t.slot_bits, per = 32 / cb;
+    if (e < t.n_cent) {
+        unsigned int w = 0;
+        for (int j = 0; j < per; ++j) {
+            const int idx = e * per + j;
+            if (idx < n_counts) {
+                const unsigned int c = idx < 2 * K ? static_cast<unsigned int>(sh.counts[idx])
+                                                   : static_cast<unsigned int>(sh.acc[2 + idx - 2 * K]);
+                w |= c << (j * cb);
+            }
+        }
+        return w;
+    }
+    const int f = e - t.n_cent;  // 0..3: lo(mse), hi(mse), lo(kl), hi(kl)
+    if (f >= 4) return 0u;       // padding of an odd entry count
+    const unsigned long long v = sh.acc[f >> 1];
+    return static_cast<unsigned int>((f & 1) ? (v >> 32) : (v & 0xffffffffull));
+}
+// warp 0 of every block: pack + store the block's slot (lane l writes entries 2l, 2l+1)
+__device__ __forceinline__ void slot_publish_block(const BulkArgs& t, const BulkShared& sh, int lane) {
+    if (lane < t.n_pairs) {
+        const unsigned long long tag = static_cast<unsigned long long>(t.seq) << 32;
+        unsigned long long* slot = t.slots + static_cast<size_t>(blockIdx.x) * kSlotEntries;
+        slot_store2(slot + 2 * lane, tag | slot_entry_payload(t, sh, 2 * lane), tag | slot_entry_payload(t, sh, 2 * lane + 1));
+    }
+}
+// publisher block, ALL threads: poll every block's slot until it carries this launch's tag, sum into sh.tot_*.
+// Pair p = block * n_pairs + pr is owned by thread p % blockDim.x (bit p / blockDim.x of its pending mask).
+template <int NTHREADS>
+__device__ __forceinline__ void slot_collect(const BulkArgs& t, BulkShared& sh) {
+    constexpr int kWords = 4;  // 128 pairs per thread
+    const int tid = threadIdx.x;
+    const int total = static_cast<int>(gridDim.x) * t.n_pairs;
+    const int K = t.p.K, n_counts = 2 * K + 6, cb = t.slot_bits, per = 32 / cb;
+    const unsigned int cmask = (cb == 32) ? 0xffffffffu : ((1u << cb) - 1u);
+    const unsigned long long tag = static_cast<unsigned long long>(t.seq) << 32, tag_mask = 0xffffffff00000000ull;
+    unsigned int pending[kWords];
+#pragma unroll
+    for (int w = 0; w < kWords; ++w) {
+        pending[w] = 0;
+        for (int b = 0; b < 32; ++b)
+            if (tid + (w * 32 + b) * NTHREADS < total) pending[w] |= 1u << b;
+    }
+    auto consume = [&](int e, unsigned int payload) {
+        if (e < t.n_cent) {
+            for (int j = 0; j < per; ++j) {
+                const unsigned int c = (payload >> (j * cb)) & cmask;
+                const int idx = e * per + j;
+                if (c != 0 && idx < n_counts) atomicAdd(&sh.tot_counts[idx], static_cast<int>(c));
+            }
+        } else if (e - t.n_cent < 4) {
+            if (payload != 0) atomicAdd(&sh.tot_fx[e - t.n_cent], static_cast<unsigned long long>(payload));
+        }
+    };
+    const long long t0 = clock64();
+    bool any = true;
+    while (any) {
+        any = false;
+#pragma unroll
+        for (int w = 0; w < kWords; ++w) {
+            unsigned int m = pending[w];
+            while (m != 0) {  // up to 4 loads in flight per thread
+                int bit[4];
+                ulonglong2 v[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    bit[j] = -1;
+                    if (m != 0) {
+                        bit[j] = __ffs(m) - 1;
+                        m &= m - 1;
+                        const int p = tid + (w * 32 + bit[j]) * NTHREADS;
+                        const uint32_t b = t.pdiv.div(static_cast<uint32_t>(p));
+                        v[j] = slot_load2(t.slots + static_cast<size_t>(b) * kSlotEntries + 2 * (p - b * t.n_pairs));
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (bit[j] < 0) continue;
+                    if ((v[j].x & tag_mask) == tag && (v[j].y & tag_mask) == tag) {
+                        const int p = tid + (w * 32 + bit[j]) * NTHREADS;
+                        const uint32_t b = t.pdiv.div(static_cast<uint32_t>(p));
+                        const int pr = p - static_cast<int>(b) * t.n_pairs;
+                        consume(2 * pr, static_cast<unsigned int>(v[j].x));
+                        consume(2 * pr + 1, static_cast<unsigned int>(v[j].y));
+                        pending[w] &= ~(1u << bit[j]);
+                    }
+                }
+            }
+            any |= pending[w] != 0;
+        }
+        if (any && clock64() - t0 > 4000000000ll) __trap();  // ~2 s: a block of this grid never published (it faulted)
+    }
+}
 
 // last block, ONE warp: workspace -> partial (= or +=), workspace back to zero, optional finalise
 // (same results as pipeline_publish, without block barriers)
@@ -158,21 +287,26 @@ struct BulkShared {
 // (bounded) for the other ranks' vectors of the same step and sums them in rank order - compute and collective
 // in ONE kernel, no NCCL launch and no second kernel on the step path.  All entries are integers, so every rank
 // ends with bit-identical totals.
-__device__ __forceinline__ void bulk_publish_warp(const PipeArgs& a, const PeerLink& link, BulkShared& sh,
-                                                  long long* scratch, int lane) {
+__device__ __forceinline__ void bulk_publish_warp(const BulkArgs& t, BulkShared& sh, long long* scratch, int lane) {
+    const PipeArgs& a = t.p;
+    const PeerLink& link = t.link;
     const int K = a.K, n = 4 + 2 * K + 6;
     const bool add = a.accumulate != 0;
     const bool exchange = link.world > 1;
-    int timeout = 0;
+    const bool from_slots = t.slot_bits != 0;  // totals already summed in shared memory (slot_collect)
     for (int i = lane; i < n; i += 32) {
         long long v;
-        if (i < 2) {
-            v = static_cast<long long>(*reinterpret_cast<volatile unsigned long long*>(&a.ws->acc[i]));
-            a.ws->acc[i] = 0;
-        } else if (i == 2) {
+        if (i == 2) {
             v = a.n_maps;
         } else if (i == 3) {
             v = static_cast<long long>(a.n_maps) * a.HW;
+        } else if (from_slots) {
+            if (i < 2) v = static_cast<long long>((sh.tot_fx[2 * i + 1] << 32) + sh.tot_fx[2 * i]);
+            else if (i < 4 + 2 * K) v = sh.tot_counts[i - 4];
+            else v = sh.tot_counts[2 * K + (i - 4 - 2 * K)];
+        } else if (i < 2) {
+            v = static_cast<long long>(*reinterpret_cast<volatile unsigned long long*>(&a.ws->acc[i]));
+            a.ws->acc[i] = 0;
         } else if (i < 4 + 2 * K) {
             v = *reinterpret_cast<volatile int*>(&a.ws->counts[i - 4]);
             a.ws->counts[i - 4] = 0;
@@ -187,35 +321,12 @@ __device__ __forceinline__ void bulk_publish_warp(const PipeArgs& a, const PeerL
     }
     __syncwarp();
     if (exchange) {
-        timeout = peer_exchange_warp(link, sh.pub, scratch, n, lane);  // sh.pub: this rank's vector -> totals over the ranks
-        for (int i = lane; i < n; i += 32) a.partial[i] = sh.pub[i];
-        __syncwarp();
+        // sh.pub = this rank's vector: send it, and collect / finalise this step (synchronous) or the previous one (deferred)
+        peer_step_warp(link, a.ws, sh.pub, scratch, sh.pub_acc, K, a.partial, a.result, t.defer, lane);
+    } else if (a.result) {
+        warp_result_from_partial(sh.pub, K, a.result, sh.pub_acc, lane);
     }
-    if (a.result) {
-        for (int k = lane; k < K; k += 32) {
-            const long long h = sh.pub[4 + k], v = sh.pub[4 + K + k];
-            const double acc = v > 0 ? __ddiv_rn(static_cast<double>(h) * 1.0, static_cast<double>(v)) : -1.0;
-            sh.pub_acc[k] = acc;
-            a.result[4 + k] = acc;
-        }
-        __syncwarp();
-        if (lane == 0) {
-            double total = 0.0;
-            int cnt = 0;
-            for (int k = 0; k < K; ++k)
-                if (sh.pub_acc[k] >= 0.0) {
-                    total = __dadd_rn(total, sh.pub_acc[k]);
-                    ++cnt;
-                }
-            const long long* cls = sh.pub + 4 + 2 * K;
-            a.result[0] = loss_from_fx(sh.pub[0], cls[0], cls[1], cls[2], sh.pub[2]);
-            a.result[1] = loss_from_fx(sh.pub[1], cls[3], cls[4], cls[5], sh.pub[2]);
-            a.result[2] = cnt != 0 ? __ddiv_rn(total, static_cast<double>(cnt)) : 0.0;
-            a.result[3] = static_cast<double>(cnt);
-            if (timeout) a.result[0] = a.result[1] = __longlong_as_double(0x7ff8000000000000ll);
-        }
-    }
-    if (lane == 0) a.ws->counter = 0;
+    if (lane == 0 && !from_slots) a.ws->counter = 0;
 }
 
 // NITC: iterations (of 128 elements) per chunk;  MULTI: maps span several chunks;
@@ -247,6 +358,9 @@ __global__ void __launch_bounds__(32 * W, BPS) pipeline_bulk_kernel(const BulkAr
     // global memory (and the shared workspace is not touched) before griddep_wait() has seen the previous grid
     // complete - per-map outputs wait in shared memory until then.
     griddep_launch_dependents();
+    // serialised launch: nothing of this launch is read or written before the previous grid has completed and flushed;
+    // only block scheduling and the barrier set-up above the first global access overlap its tail
+    if (t.strict) griddep_wait();
     unsigned long long* trace = t.trace ? t.trace + static_cast<size_t>(blockIdx.x) * kTraceBlockWords : nullptr;
     if (trace && threadIdx.x == 0) {
         trace[0] = global_timer_ns();
@@ -347,7 +461,7 @@ __global__ void __launch_bounds__(32 * W, BPS) pipeline_bulk_kernel(const BulkAr
 
     WarpLoss* wl = &s_wl[warp];
     const float inv_hw = 1.0f / static_cast<float>(a.HW);
-    bool dep_ok = false;  // griddep_wait() already executed by this warp
+    bool dep_ok = t.strict != 0;  // griddep_wait() already executed by this warp
     int q = 0;            // chunk being consumed
     for (int jj = 0; jj < n_mine; ++jj) {
         const int j = warp + jj * W;
@@ -496,7 +610,32 @@ __global__ void __launch_bounds__(32 * W, BPS) pipeline_bulk_kernel(const BulkAr
     __syncthreads();
     if (trace && threadIdx.x == 0) trace[5] = static_cast<unsigned long long>(clock64());
     if (!dep_ok) griddep_wait();  // (warps without maps) previous grid complete: outputs and workspace may be written
-    if (warp == 0) {
+    if (t.slot_bits != 0) {
+        // ---- tagged slots: one one-way store per block, the publisher polls --------------------------------------------
+        const bool publisher = blockIdx.x == gridDim.x - 1;
+        if (publisher) {
+            for (int i = threadIdx.x; i < 2 * HP_MAX_K + 6; i += blockDim.x) sh.tot_counts[i] = 0;
+            if (threadIdx.x < 4) sh.tot_fx[threadIdx.x] = 0;
+        }
+        if (warp == 0) slot_publish_block(t, sh, lane);
+        {   // every warp delivers its share of the buffered per-map outputs
+            const int n_buf = n_local < kBulkOutCap ? n_local : kBulkOutCap;
+            for (int jb = static_cast<int>(threadIdx.x); jb < n_buf; jb += 32 * W) {
+                const int map = static_cast<int>(blockIdx.x) + jb * static_cast<int>(gridDim.x);
+                const float4 o = sh.out[jb];
+                *reinterpret_cast<float2*>(a.pred_xy + 2 * static_cast<size_t>(map)) = make_float2(o.x, o.y);
+                if (a.maxvals) a.maxvals[map] = o.z;
+                if (a.weight_out) a.weight_out[map] = o.w;
+            }
+        }
+        if (publisher) {
+            __syncthreads();  // totals zeroed
+            slot_collect<32 * W>(t, sh);
+            __syncthreads();
+            // (the block's stages are idle by now and serve as the exchange's scratch space)
+            if (warp == 0) bulk_publish_warp(t, sh, reinterpret_cast<long long*>(s_dyn), lane);
+        }
+    } else if (warp == 0) {
         for (int i = lane; i < 8 + 2 * a.K; i += 32) {
             if (i < 8) {
                 const unsigned long long v = sh.acc[i];
@@ -516,7 +655,7 @@ __global__ void __launch_bounds__(32 * W, BPS) pipeline_bulk_kernel(const BulkAr
         last = __shfl_sync(0xffffffffu, last, 0);
         // (the block's stages are idle by now - every copy was consumed before the barrier above - and serve as the
         // exchange's scratch space)
-        if (last) bulk_publish_warp(a, t.link, sh, reinterpret_cast<long long*>(s_dyn), lane);
+        if (last) bulk_publish_warp(t, sh, reinterpret_cast<long long*>(s_dyn), lane);
     } else {
         // the other warps deliver the buffered per-map outputs meanwhile
         const int n_buf = n_local < kBulkOutCap ? n_local : kBulkOutCap;

@@ -81,7 +81,21 @@ class PeerExchange:
         _lib.call("hp_pipeline_finalize_peer", _lib.ptr(partial), self._table, self.rank, self.world, int(K),
                   C.c_int64(0), _lib.ptr(partial_out), _lib.ptr(result), st)      # 0: step counted on the device
 
+    def flush(self, workspace, stream=None):
+        """Complete the outstanding step of a train of deferred exchanges that used ``workspace``."""
+        C, _lib = self._C, self._lib
+        st = C.c_void_p(stream.cuda_stream) if stream is not None else _lib.stream_ptr(self.device)
+        _lib.call("hp_pipeline_flush_peer", _lib.ptr(workspace), self._table, self.rank, self.world, st)
+
+    def pck_finalize(self, counts, K, counts_out, acc_out, stream=None):
+        """configs[3]: integer PCK counts int32 [2K] of this rank -> totals + accuracies, one small kernel."""
+        C, _lib = self._C, self._lib
+        st = C.c_void_p(stream.cuda_stream) if stream is not None else _lib.stream_ptr(self.device)
+        _lib.call("hp_pck_finalize_peer", _lib.ptr(counts), self._table, self.rank, self.world, int(K),
+                  _lib.ptr(counts_out), _lib.ptr(acc_out), st)
+
     def close(self):
+        _SHARED.pop((self.device.index, id(self.group)), None)
         if self._own is None:
             return
         try:
@@ -94,6 +108,20 @@ class PeerExchange:
                 self._lib.call("hp_peer_free", self._own)
         finally:
             self._mapped, self._own = [], None
+
+
+_SHARED = {}
+
+
+def shared_peer_exchange(device, group=None) -> PeerExchange:
+    """One mailbox per (device, process group), shared by everything that exchanges on it (the step number is counted
+    in the mailbox, so all users must issue their exchanges in the same order on every rank - SPMD)."""
+    device = torch.device(device)
+    key = (device.index if device.index is not None else torch.cuda.current_device(), id(group))
+    px = _SHARED.get(key)
+    if px is None:
+        px = _SHARED[key] = PeerExchange(device, group)
+    return px
 
 
 FX_SHIFT = 40                    # HP_LOSS_FX_SHIFT of include/hp_b200.h

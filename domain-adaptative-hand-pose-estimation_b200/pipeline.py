@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import collections
 import ctypes as C
+import weakref
 from dataclasses import dataclass
 
 import numpy as np
@@ -36,9 +37,14 @@ class PipelineResult:
     weight: torch.Tensor      # float32 [B,K,1]  (target_weight of generate_target)
     K: int
     ready: object = None      # CUDA event recorded after the last op that writes `result` (sharded path)
+    owner: object = None      # weakref to the pipeline while this step's totals are still outstanding (deferred exchange)
 
     def wait(self):
-        """Make the current stream wait for `result` (only needed when the collective ran on a side stream)."""
+        """Make the current stream wait for `result`: completes a deferred exchange that still has this step
+        outstanding, and orders the stream after a collective that ran on a side stream."""
+        pipe = self.owner() if self.owner is not None else None
+        if pipe is not None and pipe._pending is self:
+            pipe.join()
         if self.ready is not None:
             torch.cuda.current_stream(self.result.device).wait_event(self.ready)
         return self
@@ -47,6 +53,9 @@ class PipelineResult:
         self.wait()
         r = self.result.cpu().numpy() if isinstance(self.result, torch.Tensor) else np.asarray(self.result)
         K = self.K
+        if np.isnan(r[3]):          # cnt is never NaN in a completed step: the kernels poison it on an exchange timeout
+            raise RuntimeError("HeatmapPipeline: the cross-GPU exchange of this step timed out (a rank never delivered "
+                               "its partial vector); the totals are incomplete")
         return dict(mse=float(r[0]), kl=float(r[1]), avg_acc=float(r[2]) if int(r[3]) else 0, cnt=int(r[3]),
                     acc=r[4:4 + K].copy())
 
@@ -73,7 +82,7 @@ class HeatmapPipeline:
     all-reduce when the batch is sharded over several GPUs)."""
 
     def __init__(self, num_keypoints=21, heatmap_size=(64, 64), image_size=(256, 256), sigma=2, kl_epsilon=0.0,
-                 thr=0.5, losses=("mse", "kl"), device=None, group=None, collective="nccl"):
+                 thr=0.5, losses=("mse", "kl"), device=None, group=None, collective="nccl", defer_exchange=True):
         if not torch.cuda.is_available():
             raise RuntimeError("no CUDA device: the B200 heatmap path has no CPU fallback")
         self.K = int(num_keypoints)
@@ -104,6 +113,11 @@ class HeatmapPipeline:
             raise ValueError(f"num_keypoints={self.K} exceeds what the peer mailboxes carry (K <= {_lib.PEER_MAX_K}); "
                              "use collective='nccl'")
         self._peer = None
+        # collective="peer": overlapped steps (a train) only SEND their partial vector; the totals of step s are
+        # completed by step s+1's kernel - or by join() / PipelineResult.wait() / host() for the last one - so no step
+        # waits for a peer that is less than a whole step late (HP_PIPE_DEFER_EXCHANGE).  Serialised steps exchange at once.
+        self.defer_exchange = bool(defer_exchange)
+        self._pending = None              # the PipelineResult whose totals are still outstanding
         _lib.load()
 
     # ------------------------------------------------------------------------------ device path
@@ -139,7 +153,7 @@ class HeatmapPipeline:
         ws = self._workspace(pred.shape[0] * self.K)
         return self._bind(pred, joints, vis, out, ws, finalize, overlap, None, True), out
 
-    def _bind(self, pred, joints, vis, out, ws, finalize, overlap, peer, keep_inputs):
+    def _bind(self, pred, joints, vis, out, ws, finalize, overlap, peer, keep_inputs, defer=False):
         """Arguments validated and stored once on the C side (``hp_pipeline_plan_create``); the returned ``launch()``
         is a two-argument FFI call (a step is a ~12 us kernel: per-call marshalling of 25 arguments costs as much)."""
         lib = _lib.load()
@@ -152,7 +166,7 @@ class HeatmapPipeline:
                   _lib.ptr(out.maxvals), _lib.ptr(out.weight), _lib.ptr(out.partial), 0,
                   _lib.ptr(out.result) if finalize else None, _lib.ptr(ws),
                   peer._table if peer is not None else None, peer.rank if peer is not None else 0,
-                  peer.world if peer is not None else 1, C.c_uint(_lib.pipe_flags(overlap)), C.byref(handle))
+                  peer.world if peer is not None else 1, C.c_uint(_lib.pipe_flags(overlap, defer)), C.byref(handle))
         # the plan owns references to what the LIBRARY side allocated; the caller's inputs only on request
         plan = _Plan(handle, (out, ws, peer, self.tab) + ((pred, joints, vis) if keep_inputs else ()))
         fn = lib.hp_pipeline_plan_launch
@@ -160,11 +174,23 @@ class HeatmapPipeline:
         dev_index = dev.index if dev.index is not None else torch.cuda.current_device()
         last_error = lib.hp_last_error
 
-        def launch(_plan=plan, _h=handle):
+        if peer is None:
+            def launch(_plan=plan, _h=handle):
+                rc = fn(_h, raw_stream(dev_index))
+                if rc != 0:
+                    raise RuntimeError(f"hp_pipeline_plan_launch failed (rc={rc}): {last_error().decode(errors='replace')}")
+            return launch
+        owner = weakref.ref(self)
+        pending = out if defer else None     # a sharded step completes whatever was outstanding; a deferred one leaves itself
+
+        def launch_sharded(_plan=plan, _h=handle):
             rc = fn(_h, raw_stream(dev_index))
             if rc != 0:
                 raise RuntimeError(f"hp_pipeline_plan_launch failed (rc={rc}): {last_error().decode(errors='replace')}")
-        return launch
+            self._pending = pending
+            if pending is not None:
+                pending.owner = owner
+        return launch_sharded
 
     def plan_peer(self, pred, joints, vis, out=None, overlap=False):
         """Sharded step with the peer-memory exchange as ONE call (``hp_pipeline_fused_peer``): the fused kernel on
@@ -173,14 +199,15 @@ class HeatmapPipeline:
         if out is None:
             out = self.alloc_outputs(pred.shape[0], pred.device)
         ws = self._workspace(pred.shape[0] * self.K)
-        return self._bind(pred, joints, vis, out, ws, True, overlap, self._peer_link(), True), out
+        return self._bind(pred, joints, vis, out, ws, True, overlap, self._peer_link(), True,
+                          self.defer_exchange and bool(overlap)), out
 
     def _peer_link(self):
         if self._peer is None:
             if self.K > _lib.PEER_MAX_K:
                 raise ValueError(f"num_keypoints={self.K} exceeds what the peer mailboxes carry "
                                  f"(K <= {_lib.PEER_MAX_K}); use collective='nccl'")
-            self._peer = hpdist.PeerExchange(self.device, self.group)
+            self._peer = hpdist.shared_peer_exchange(self.device, self.group)
         return self._peer
 
     def _workspace(self, n_maps):
@@ -218,7 +245,7 @@ class HeatmapPipeline:
             out = self.alloc_outputs(pred.shape[0], pred.device)
         ws = self._workspace(pred.shape[0] * self.K)
         launch = self._bind(pred, joints, vis, out, ws, finalize, overlap, self._peer_link() if peer else None,
-                            not cacheable)
+                            not cacheable, bool(peer) and self.defer_exchange and bool(overlap))
         if cacheable:
             self._plans[key] = launch
             while len(self._plans) > self._PLAN_CACHE:
@@ -266,14 +293,19 @@ class HeatmapPipeline:
 
     def close(self):
         """Release the peer mailboxes (collective; call on every rank before destroying the process group)."""
+        self.join()
         self._plans.clear()
         if self._peer is not None:
-            self.join()
             self._peer.close()
             self._peer = None
 
     def join(self):
-        """Order the current stream after every outstanding collective of this pipeline."""
+        """Order the current stream after every outstanding collective of this pipeline: completes the last step of
+        a train of deferred exchanges (one-warp flush kernel) and waits for the NCCL side stream."""
+        if self._pending is not None:
+            self._pending = None
+            with _lib.on_device(self.device):
+                self._peer.flush(self._ws)
         if self._comm_stream is not None:
             torch.cuda.current_stream(self.device).wait_stream(self._comm_stream)
 
@@ -291,6 +323,9 @@ class HeatmapPipeline:
     def run_host(self, pred, joints, vis, slab=64, want_pred_xy=True):
         """End-to-end form for HOST inputs (what a caller holding numpy / CPU tensors uses):
         pinned host buffers -> slabbed H2D copies overlapped with the kernel -> one small D2H.
+        Sharded (torch.distributed initialised, ``collective="peer"``): the inputs are THIS rank's slice; the ranks'
+        partial vectors are exchanged over the peer mailboxes before the result is copied back, so every rank returns the
+        losses / PCK of the whole batch (``pred_xy`` stays the rank's slice).
         ``pred`` float32 [B,K,H,W], ``joints`` float64 [B,K,2], ``vis`` float32 [B,K,1] (numpy arrays or
         CPU tensors; pinned tensors are used in place, anything else is staged through pinned memory).
         Returns ``dict(mse, kl, avg_acc, cnt, acc[K], pred_xy[B,K,2] numpy)`` after synchronising."""
@@ -301,6 +336,12 @@ class HeatmapPipeline:
         slab = max(1, min(int(slab), B))
         st = self._host_buffers(B, slab)
         dev = self.device
+        sharded = hpdist.is_distributed(self.group)
+        peer = self._peer_link() if (sharded and self.collective == "peer") else None
+        if sharded and peer is None:
+            raise RuntimeError("run_host on a sharded batch needs collective='peer' (the exchange runs on the step's "
+                               "stream between the last slab's kernel and the device->host copy of the result)")
+        self.join()
         with _lib.on_device(dev):
             ws = self._workspace(B * K)
             _lib.call("hp_pipeline_fused_host", _lib.ptr(hp), _lib.ptr(hj), _lib.ptr(hv), B, K, H, W,
@@ -309,6 +350,8 @@ class HeatmapPipeline:
                       _lib.ptr(st["d_joints"]), _lib.ptr(st["d_vis"]), _lib.ptr(st["d_xy"]), _lib.ptr(st["d_max"]),
                       _lib.ptr(st["d_w"]), _lib.ptr(st["d_partial"]), _lib.ptr(st["d_result"]), _lib.ptr(ws),
                       _lib.ptr(st["h_xy"]) if want_pred_xy else None, _lib.ptr(st["h_result"]),
+                      peer._table if peer is not None else None, peer.rank if peer is not None else 0,
+                      peer.world if peer is not None else 1,
                       _lib.stream_ptr(dev), C.c_void_p(st["copy_stream"].cuda_stream))
         r = st["h_result"].numpy()
         out = dict(mse=float(r[0]), kl=float(r[1]), avg_acc=float(r[2]) if int(r[3]) else 0, cnt=int(r[3]),
@@ -359,11 +402,16 @@ class MultiscaleEval:
     train1.py:410-424 scaled up), decode the fused map and score PCK against label coordinates - the
     fused map lives in registers only.  Batch-sharded like :class:`HeatmapPipeline`."""
 
-    def __init__(self, num_keypoints=21, thr=0.5, a_lo=0.5, a_mid=1.0, a_hi=1.0, group=None):
+    def __init__(self, num_keypoints=21, thr=0.5, a_lo=0.5, a_mid=1.0, a_hi=1.0, group=None, collective="peer"):
         self.K = int(num_keypoints)
         self.thr = float(thr)
         self.coef = (float(a_lo), float(a_mid), float(a_hi))
         self.group = group
+        if collective not in ("nccl", "peer"):
+            raise ValueError("collective must be 'nccl' or 'peer'")
+        # how the sharded path sums the 2K integer counts: one-warp kernel over the NVLink peer mailboxes (stream-ordered
+        # right behind the fuse kernel, no NCCL launch) or torch.distributed.all_reduce + hp_pck_finalize
+        self.collective = collective if self.K <= _lib.PEER_MAX_K else "nccl"
         _lib.load()
 
     def __call__(self, lo, mid, hi, target_xy):
@@ -387,6 +435,9 @@ class MultiscaleEval:
                       _lib.ptr(maxvals), _lib.ptr(counts), _lib.ptr(acc), _lib.ptr(ws), _lib.stream_ptr(dev))
             if hpdist.is_distributed(self.group):
                 # the path's one collective: integer sum of the 2K hit / valid counts (exact, order-free)
-                torch.distributed.all_reduce(counts, op=torch.distributed.ReduceOp.SUM, group=self.group)
-                _lib.call("hp_pck_finalize", _lib.ptr(counts), K, _lib.ptr(acc), _lib.stream_ptr(dev))
+                if self.collective == "peer":
+                    hpdist.shared_peer_exchange(dev, self.group).pck_finalize(counts, K, counts, acc)
+                else:
+                    torch.distributed.all_reduce(counts, op=torch.distributed.ReduceOp.SUM, group=self.group)
+                    _lib.call("hp_pck_finalize", _lib.ptr(counts), K, _lib.ptr(acc), _lib.stream_ptr(dev))
         return acc, pred_xy, counts

@@ -198,8 +198,17 @@ int hp_pipeline_fused(const float* pred, const double* joints, const float* vis,
  *   completed - results are bit-identical to serialised launches.
  *   Contract: pred, joints, vis and tab must NOT be produced by the kernel launched right before this one
  *   on `stream`; consecutive launches of a train use different output buffers.
- *   HP_PIPE_DEPTH(d), d = 1..8: launches resident at once (1 = hand-over only); 0/absent = library default. */
+ *   HP_PIPE_DEPTH(d), d = 1..8: launches resident at once (1 = hand-over only); 0/absent = library default.
+ *   Without HP_PIPE_OVERLAP_PREV a launch is fully serialised: it reads nothing and writes nothing before the
+ *   previous kernel on the stream has completed (it still carries the programmatic-launch attribute, so that block
+ *   scheduling and barrier set-up hide the launch gap behind the previous kernel's tail - nothing else overlaps).
+ *   HP_PIPE_DEFER_EXCHANGE (sharded steps only: hp_pipeline_fused_peer / plans with world > 1): the step sends its
+ *   partial vector to the other ranks but does not wait for theirs; `partial` / `result` of step s are completed by
+ *   the next sharded step on the same workspace (or by hp_pipeline_flush_peer after the last one) - nothing on the
+ *   step path then waits for a peer that is less than a whole step late.  Keep step s's output buffers alive and
+ *   unread until then. */
 #define HP_PIPE_OVERLAP_PREV 1u
+#define HP_PIPE_DEFER_EXCHANGE 2u
 #define HP_PIPE_DEPTH(d) (((unsigned int)(d) & 15u) << 8)
 int hp_pipeline_fused_ex(const float* pred, const double* joints, const float* vis,
                          int B, int K, int H, int W, double stride_x, double stride_y, int tmp,
@@ -223,8 +232,13 @@ int hp_pipeline_finalize(const int64_t* partial, int K, double* result, hp_strea
  * it writes this rank's partial into every mailbox, waits (bounded) for all ranks' step `seq`, sums in
  * rank order and finalises.  mailboxes[r] = rank r's mailbox as mapped here (own pointer for r == rank).
  * `seq` = 1, 2, 3, ... identical on all ranks, or 0: the step number is counted on the device (in the rank's own
- * mailbox), which makes a captured CUDA graph of steps replayable.  Do not mix the two on one mailbox.
- * On a timeout result[0] and result[1] are NaN. */
+ * mailbox), which makes a captured CUDA graph of steps replayable.  Only 0 is accepted by this version.
+ * On a timeout (a rank did not deliver within ~2 s) every entry of `result` is NaN and every entry of the reduced
+ * partial vector is -1; the step is not counted.
+ * hp_pipeline_flush_peer completes the outstanding step of a train of HP_PIPE_DEFER_EXCHANGE steps that used
+ * `workspace`; a no-op when nothing is outstanding.
+ * hp_pck_finalize_peer is the same exchange for configs[3]: counts int32 [2K] (hits, valid) of this rank -> totals in
+ * counts_out and acc_out[K+2] = acc[K], avg_acc, cnt (replaces [all-reduce(counts) ; hp_pck_finalize]). */
 size_t hp_peer_mailbox_bytes(int world);
 int hp_peer_alloc(int world, void** mailbox);
 int hp_peer_free(void* mailbox);
@@ -233,6 +247,9 @@ int hp_peer_import(const void* handle64, void** mapped);
 int hp_peer_close(void* mapped);
 int hp_pipeline_finalize_peer(const int64_t* partial, void* const* mailboxes, int rank, int world, int K,
                               int64_t seq, int64_t* partial_out, double* result, hp_stream_t stream);
+int hp_pipeline_flush_peer(void* workspace, void* const* mailboxes, int rank, int world, hp_stream_t stream);
+int hp_pck_finalize_peer(const int32_t* counts, void* const* mailboxes, int rank, int world, int K,
+                         int32_t* counts_out, double* acc_out, hp_stream_t stream);
 
 /* One batch-sharded step in a single call and - for the shapes served by the TMA-staged kernel (H*W = 256,
  * 1024 or a multiple of 4096 floats, aligned) - in a single KERNEL: the last block of the fused kernel stores
@@ -265,7 +282,10 @@ int hp_pipeline_plan_destroy(hp_plan_t* plan);
 
 /* Host-buffer form (end-to-end path): h_* are pinned host arrays; the batch is cut into slabs
  * of slab_B samples whose H2D copies (copy_stream) overlap the kernels (stream); device
- * staging d_pred holds 2 slabs [2*slab_B,K,H,W]; returns after h_result is valid. */
+ * staging d_pred holds 2 slabs [2*slab_B,K,H,W]; returns after h_result is valid.
+ * Sharded (world > 1, mailboxes as for hp_pipeline_fused_peer; else NULL, 0, 1): h_pred .. are THIS rank's slice; after
+ * the last slab the ranks' partial vectors are exchanged over the peer mailboxes, so d_partial / h_result hold the
+ * totals over all ranks (h_pred_xy stays this rank's slice). */
 int hp_pipeline_fused_host(const float* h_pred, const double* h_joints, const float* h_vis,
                            int B, int K, int H, int W, double stride_x, double stride_y, int tmp,
                            const float* tab, float kl_epsilon, double thr, int loss_mask,
@@ -273,6 +293,7 @@ int hp_pipeline_fused_host(const float* h_pred, const double* h_joints, const fl
                            float* d_pred_xy, float* d_maxvals, float* d_weight,
                            int64_t* d_partial, double* d_result, void* workspace,
                            float* h_pred_xy /*nullable*/, double* h_result,
+                           void* const* mailboxes /*nullable*/, int rank, int world,
                            hp_stream_t stream, hp_stream_t copy_stream);
 
 #ifdef __cplusplus

@@ -46,7 +46,26 @@ def main():
         for o in pouts:
             assert np.array_equal(o.partial.cpu().numpy(), part), (overlap, o.partial.cpu().numpy(), part)
             assert torch.equal(o.result, outs[-1].result), (overlap, o.result, outs[-1].result)
-    peer.close()
+    # deferred exchange made visible: right after a train WITHOUT join() the last step's totals are still outstanding;
+    # reading them through PipelineResult.host() must complete the exchange first
+    for rep in range(5):
+        last = peer(x[0], x[1], x[2], out=pouts[rep % 8], overlap=True)
+    assert peer._pending is last
+    h_last = last.host()
+    assert peer._pending is None and h_last["mse"] == got[-1]["mse"] and h_last["kl"] == got[-1]["kl"] and h_last["cnt"] == got[-1]["cnt"]
+    # synchronous steps (no overlap) right after deferred ones complete what is outstanding themselves
+    for o in pouts:
+        o.partial.zero_(); o.result.zero_()
+    peer(x[0], x[1], x[2], out=pouts[0], overlap=True)
+    peer(x[0], x[1], x[2], out=pouts[1], overlap=False)
+    assert peer._pending is None
+    torch.cuda.synchronize()
+    for o in pouts[:2]:
+        assert np.array_equal(o.partial.cpu().numpy(), part) and torch.equal(o.result, outs[-1].result)
+    # the host-buffer entry point, sharded: every rank gets the totals of the whole batch
+    hr = peer.run_host(d["pred"][lo:hi], d["joints"][lo:hi], d["vis"][lo:hi], slab=8)
+    assert hr["mse"] == got[-1]["mse"] and hr["kl"] == got[-1]["kl"] and hr["cnt"] == got[-1]["cnt"], (hr, got[-1])
+    assert np.array_equal(hr["acc"], got[-1]["acc"]) and np.array_equal(hr["pred_xy"], pouts[0].pred_xy.cpu().numpy())
     # NCCL path with reused outputs and overlapped launches
     nouts = [pipe.alloc_outputs(hi - lo, dev) for _ in range(3)]
     for rep in range(30):
@@ -63,8 +82,11 @@ def main():
     lo_m, hi_m = hp.dist.shard_bounds(Bm, rank, world)
     tm = lambda a, sl: torch.from_numpy(a[sl]).to(dev)
     sl = slice(lo_m, hi_m)
-    acc_s, _, counts_s = hp.MultiscaleEval(21)(tm(lo_h, sl), tm(mid_h, sl), tm(dm["pred"], sl), tm(tgt_h, sl))
+    acc_s, _, counts_s = hp.MultiscaleEval(21)(tm(lo_h, sl), tm(mid_h, sl), tm(dm["pred"], sl), tm(tgt_h, sl))   # peer exchange
+    acc_n, _, counts_n = hp.MultiscaleEval(21, collective="nccl")(tm(lo_h, sl), tm(mid_h, sl), tm(dm["pred"], sl), tm(tgt_h, sl))
+    assert torch.equal(acc_s, acc_n) and torch.equal(counts_s, counts_n), "peer and NCCL sums of the PCK counts differ"
     acc_s, counts_s = acc_s.cpu().numpy(), counts_s.cpu().numpy()
+    peer.close()                    # the shared mailboxes: collective, before the process group goes away
     # single-GPU reference on the whole batch (group of one rank)
     solo_group = dist.new_group(ranks=[rank]) if False else None
     dist.barrier()

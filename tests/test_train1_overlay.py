@@ -1,0 +1,61 @@
+"""Row f1: the reference's OWN train1.py, unchanged, runs training iterations on a GPU on top of the
+CUDA path - through the overlay launcher (hpb200.py), with a synthetic dataset and a small stand-in backbone registered
+by a launcher plugin (tests/train1_synthetic_plugin.py).  The reference tree is /root/reference in the build container
+and the copy under oracle/_ref/reference (oracle/ship_reference.py) on the GPU box.
+
+Asserts: exit code 0; the three steps of train() (train1.py:371-450) and validate() ran with finite losses; the
+heatmap work went through the C ABI (KL loss fwd+bwd, fused regression disparity fwd+bwd at 64/32/16, accuracy, and
+the nn.Upsample route into hp_fuse_multiscale); checkpoints were written by the driver."""
+import json
+import math
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from oracle import ref_loader
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not ref_loader.available(), reason="reference tree not present")]
+
+
+@pytest.mark.parametrize("device_targets", [False, True])
+def test_unchanged_train1_runs_three_iterations_on_the_cuda_path(tmp_path, device_targets):
+    ckpt = tmp_path / "pretrain_stub.pth"
+    torch.save({"model": {}}, ckpt)                       # train1.py:186-191 loads it with strict=False
+    stats = tmp_path / "stats.json"
+    log = tmp_path / "log"
+    env = dict(os.environ, HP_OVERLAY_STATS=str(stats), PYTHONWARNINGS="ignore")
+    cmd = [sys.executable, os.path.join(ROOT, "hpb200.py"), "--ref", ref_loader.reference_root(),
+           "--plugin", os.path.join(ROOT, "tests", "train1_synthetic_plugin.py")]
+    if device_targets:
+        cmd.append("--device-targets")
+    cmd += ["train1.py", str(tmp_path / "data"), "--source_root", str(tmp_path / "data"), "-s", "SyntheticHands",
+            "-t", "SyntheticHands", "-a", "tinynet", "--pretrain", str(ckpt), "-b", "4", "-j", "0", "--epochs", "1",
+            "-i", "3", "-p", "1", "--log", str(log), "--seed", "0"]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env, cwd=str(tmp_path))
+    out = p.stdout + p.stderr
+    assert p.returncode == 0, out[-4000:]
+    # ProgressMeter lines of train(): "Epoch: [0][2/3] ... Loss (s) 1.23e+00 (...) Loss (t, false) ... Loss (t, truth) ..."
+    rows = [l for l in out.splitlines() if l.startswith("Epoch: [0][")]
+    assert len(rows) == 3, out[-3000:]
+    for l in rows:
+        for name in ("Loss (s)", "Loss (t, false)", "Loss (t, truth)"):
+            m = re.search(re.escape(name) + r"\s+([-+0-9.eEnaif]+)", l)
+            assert m and math.isfinite(float(m.group(1))), l
+    assert "Test: [0/2]" in out or "Test: [" in out, out[-2000:]                    # validate() ran
+    assert re.search(r"Source: [0-9.]+ Target: [0-9.]+ Target\(best\)", out), out[-2000:]
+    assert os.path.isfile(log / "checkpoints" / "0.pth") and os.path.isfile(log / "checkpoints" / "best.pth")
+    calls = json.loads(stats.read_text())
+    # step A/B/C: 2 + 3 + 2 fused disparity forwards per iteration, each with a backward
+    assert calls.get("hp_regdisp_fwd", 0) >= 3 * 7 and calls.get("hp_regdisp_bwd", 0) >= 3 * 7, calls
+    assert calls.get("hp_kl_fwd", 0) >= 3 and calls.get("hp_kl_bwd", 0) >= 3, calls        # criterion(y_s, label_s, weight_s)
+    assert calls.get("hp_accuracy", 0) >= 3 * 4 + 4, calls                                  # 4 per iteration + validate
+    assert calls.get("hp_fuse_multiscale", 0) >= 3 * 3, calls                               # the three nn.Upsample of step B
+    if device_targets:
+        assert calls.get("hp_gaussian_target", 0) >= 16, calls
+    else:
+        assert calls.get("hp_gaussian_target", 0) == 0, calls
