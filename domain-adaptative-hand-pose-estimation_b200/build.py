@@ -10,6 +10,7 @@ from __future__ import annotations
 import concurrent.futures as cf
 import glob
 import os
+import re
 import shutil
 import subprocess
 import sys
@@ -41,16 +42,31 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+_INCLUDE = re.compile(r'^\s*#\s*include\s+"([^"]+)"', re.M)
+
+
+def _deps(path, seen=None):
+    """The quoted includes of `path`, transitively (one object per .cu: only what it really includes makes it stale)."""
+    seen = set() if seen is None else seen
+    path = os.path.normpath(path)
+    if path in seen or not os.path.exists(path):
+        return seen
+    seen.add(path)
+    with open(path) as f:
+        text = f.read()
+    for inc in _INCLUDE.findall(text):
+        _deps(os.path.join(os.path.dirname(path), inc), seen)
+    return seen
+
+
 def build(force=False, verbose=False):
     nvcc = _nvcc()
     os.makedirs(OBJ, exist_ok=True)
     sources = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
-    headers = sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + [os.path.join(HERE, "..", "include", "hp_b200.h"),
-                                                               os.path.abspath(__file__)]
     jobs = []
     for src in sources:
         obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
-        if force or _stale(obj, [src] + headers):
+        if force or _stale(obj, sorted(_deps(src)) + [os.path.abspath(__file__)]):
             cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
             jobs.append((src, cmd))
 

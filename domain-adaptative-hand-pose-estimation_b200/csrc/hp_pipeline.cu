@@ -223,12 +223,16 @@ static int pipeline_grid_div_override() {
 // ---- TMA-staged shape (hp_pipeline_bulk.cuh) ---------------------------------------------------------------------
 // experiments: HP_PIPE_EPILOGUE=atomics keeps the workspace-atomics + ticket epilogue; HP_PIPE_STRICT_PDL=0 launches a
 // serialised step without the programmatic attribute (the next launch is then not even scheduled before this one ends)
-static bool pipeline_slots_enabled() {
-    static const bool on = []() {
+// 0: never (atomics + ticket), 1: serialised launches only (default: in a train the epilogue is hidden behind the next
+// launches' streaming and the proven atomics path stays), 2: every launch
+static int pipeline_slots_mode() {
+    static const int mode = []() {
         const char* e = std::getenv("HP_PIPE_EPILOGUE");
-        return !(e && (e[0] == 'a' || e[0] == 'A'));
+        if (e && (e[0] == 'a' || e[0] == 'A')) return 0;
+        if (e && (e[0] == 's' || e[0] == 'S')) return 2;
+        return 1;
     }();
-    return on;
+    return mode;
 }
 static bool pipeline_strict_pdl() {
     static const bool on = []() {
@@ -257,7 +261,8 @@ static cudaError_t launch_bulk_one(BulkArgs& t, int grid, cudaStream_t stream) {
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess) cap = cudaStreamCaptureStatusActive;
     // (a captured launch replays with the SAME tag: stale slots of the previous replay would look fresh)
-    if (pipeline_slots_enabled() && cap == cudaStreamCaptureStatusNone && grid <= kSlotMaxBlocks) {
+    const bool want_slots = pipeline_slots_mode() == 2 || (pipeline_slots_mode() == 1 && t.overlap == 0);
+    if (want_slots && cap == cudaStreamCaptureStatusNone && grid <= kSlotMaxBlocks) {
         const int n_local = (t.p.n_maps + grid - 1) / grid;  // most maps any block owns = bound of every counter
         const int bits = n_local <= 15 ? 4 : (n_local <= 255 ? 8 : (n_local <= 65535 ? 16 : 0));
         if (bits != 0) {

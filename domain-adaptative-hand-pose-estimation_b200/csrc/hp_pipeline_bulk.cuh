@@ -213,22 +213,28 @@ __device__ __forceinline__ void slot_publish_block(const BulkArgs& t, const Bulk
     }
 }
 // publisher block, ALL threads: poll every block's slot until it carries this launch's tag, sum into sh.tot_*.
-// Pair p = block * n_pairs + pr is owned by thread p % blockDim.x (bit p / blockDim.x of its pending mask).
+// Pair p = block * n_pairs + pr is owned by thread p % NTHREADS (bit p / NTHREADS of its pending mask).  The loads of a
+// pass go out kBatch at a time per thread (a pass over all slots is one or two L2 round trips, not one per slot); PCK
+// counters are summed with 32-bit shared-memory atomics, the 32-bit halves of the fixed-point loss sums in registers
+// (64-bit shared-memory atomics are compare-and-swap loops: 4 hot addresses x hundreds of blocks).
 template <int NTHREADS>
 __device__ __forceinline__ void slot_collect(const BulkArgs& t, BulkShared& sh) {
-    constexpr int kWords = 4;  // 128 pairs per thread
+    constexpr int kWords = 4;   // 128 pairs per thread
+    constexpr int kBatch = 8;   // loads in flight per thread
     const int tid = threadIdx.x;
     const int total = static_cast<int>(gridDim.x) * t.n_pairs;
     const int K = t.p.K, n_counts = 2 * K + 6, cb = t.slot_bits, per = 32 / cb;
-    const unsigned int cmask = (cb == 32) ? 0xffffffffu : ((1u << cb) - 1u);
+    const unsigned int cmask = (1u << cb) - 1u;
     const unsigned long long tag = static_cast<unsigned long long>(t.seq) << 32, tag_mask = 0xffffffff00000000ull;
     unsigned int pending[kWords];
 #pragma unroll
     for (int w = 0; w < kWords; ++w) {
-        pending[w] = 0;
-        for (int b = 0; b < 32; ++b)
-            if (tid + (w * 32 + b) * NTHREADS < total) pending[w] |= 1u << b;
+        const int first = tid + w * 32 * NTHREADS;  // pairs tid + (32 w + b) * NTHREADS, b = 0..31
+        const int left = total - first;
+        const int nb = left <= 0 ? 0 : (left + NTHREADS - 1) / NTHREADS;
+        pending[w] = nb >= 32 ? 0xffffffffu : ((1u << nb) - 1u);
     }
+    unsigned long long fx[4] = {0ull, 0ull, 0ull, 0ull};
     auto consume = [&](int e, unsigned int payload) {
         if (e < t.n_cent) {
             for (int j = 0; j < per; ++j) {
@@ -236,8 +242,12 @@ __device__ __forceinline__ void slot_collect(const BulkArgs& t, BulkShared& sh) 
                 const int idx = e * per + j;
                 if (c != 0 && idx < n_counts) atomicAdd(&sh.tot_counts[idx], static_cast<int>(c));
             }
-        } else if (e - t.n_cent < 4) {
-            if (payload != 0) atomicAdd(&sh.tot_fx[e - t.n_cent], static_cast<unsigned long long>(payload));
+        } else {
+            const int f = e - t.n_cent;
+            fx[0] += (f == 0) ? payload : 0u;
+            fx[1] += (f == 1) ? payload : 0u;
+            fx[2] += (f == 2) ? payload : 0u;
+            fx[3] += (f == 3) ? payload : 0u;
         }
     };
     const long long t0 = clock64();
@@ -247,11 +257,11 @@ __device__ __forceinline__ void slot_collect(const BulkArgs& t, BulkShared& sh) 
 #pragma unroll
         for (int w = 0; w < kWords; ++w) {
             unsigned int m = pending[w];
-            while (m != 0) {  // up to 4 loads in flight per thread
-                int bit[4];
-                ulonglong2 v[4];
+            while (m != 0) {
+                int bit[kBatch];
+                ulonglong2 v[kBatch];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < kBatch; ++j) {
                     bit[j] = -1;
                     if (m != 0) {
                         bit[j] = __ffs(m) - 1;
@@ -262,7 +272,7 @@ __device__ __forceinline__ void slot_collect(const BulkArgs& t, BulkShared& sh) 
                     }
                 }
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < kBatch; ++j) {
                     if (bit[j] < 0) continue;
                     if ((v[j].x & tag_mask) == tag && (v[j].y & tag_mask) == tag) {
                         const int p = tid + (w * 32 + bit[j]) * NTHREADS;
@@ -277,6 +287,14 @@ __device__ __forceinline__ void slot_collect(const BulkArgs& t, BulkShared& sh) 
             any |= pending[w] != 0;
         }
         if (any && clock64() - t0 > 4000000000ll) __trap();  // ~2 s: a block of this grid never published (it faulted)
+    }
+    // the loss-sum halves: warp shuffle tree, then one 64-bit shared-memory atomic per warp and half
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+        unsigned long long x = fx[f];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if ((tid & 31) == 0 && x != 0ull) atomicAdd(&sh.tot_fx[f], x);
     }
 }
 

@@ -222,6 +222,17 @@ int hp_pipeline_fused_ex(const float* pred, const double* joints, const float* v
  * uint64 words.  buf = NULL switches it off.  Read by profiles/trace_pipeline.py. */
 size_t hp_debug_pipeline_trace_words(void);
 int hp_debug_pipeline_trace(void* buf, size_t words);
+/* ---- small boundary operators around the decode (csrc/hp_extras.cu) ----
+ * hp_argmax_decode_f64: get_max_preds for float64 heatmaps (utils/keypoint_detection.py:7-35 takes any ndarray dtype);
+ *   preds float32 [n_maps,2], maxvals float64 [n_maps] (the reference returns maxvals in the input dtype).
+ * hp_refine_quarter: OPT-IN quarter-pixel refinement of decoded coordinates, in place (not in the reference - SURVEY.md
+ *   row a13): preds += 0.25 * sign(hm[y][x+1]-hm[y][x-1], hm[y+1][x]-hm[y-1][x]) for maxima with 1 < x < W-1, 1 < y < H-1.
+ * hp_group_accuracy: uda/dataset/keypoint_dataset.py:58-71 on the device: out[g] = mean of acc[index[offsets[g]:offsets[g+1]]],
+ *   summed left to right like Python's sum() (bit-equal float64). */
+int hp_argmax_decode_f64(const double* heat, int n_maps, int H, int W, float* preds, double* maxvals, hp_stream_t stream);
+int hp_refine_quarter(const float* heat, int n_maps, int H, int W, float* preds, hp_stream_t stream);
+int hp_group_accuracy(const double* acc, const int32_t* offsets, const int32_t* index, int n_groups, double* out,
+                      hp_stream_t stream);
 /* partial (e.g. after an NCCL all-reduce over ranks) -> result, on device */
 int hp_pipeline_finalize(const int64_t* partial, int K, double* result, hp_stream_t stream);
 
