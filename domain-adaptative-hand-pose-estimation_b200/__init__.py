@@ -30,7 +30,7 @@ __version__ = "0.1.0"
 
 _LAZY = {
     "get_max_preds": "keypoint_detection", "accuracy": "keypoint_detection",
-    "decode": "keypoint_detection", "pck": "keypoint_detection",
+    "decode": "keypoint_detection", "pck": "keypoint_detection", "group_accuracy": "keypoint_detection",
     "find_keypoints_max": "keypoint_detection", "compute_uv_from_heatmaps": "keypoint_detection",
     "compute_uv_from_heatmaps2": "keypoint_detection", "compute_uv_from_heatmaps3": "keypoint_detection",
     "JointsMSELoss": "loss", "JointsKLLoss": "loss",
@@ -42,7 +42,7 @@ _LAZY = {
     "RegressionDisparity5": "regda", "RegressionDisparity6": "regda", "RegressionDisparity7": "regda",
     "RegressionDisparity8": "regda", "RegressionDisparityx2": "regda", "RegressionDisparityx3": "regda",
     "RegressionDisparityx4": "regda", "JointsMSELoss0": "loss", "JointsKLLoss5": "loss",
-    "generate_target": "target", "generate_target_batch": "target",
+    "generate_target": "target", "generate_target_batch": "target", "DeviceTargetCollate": "target",
     "fuse_multiscale": "fusion", "fuse_three_scales": "fusion", "upsample_bilinear": "fusion",
     "HeatmapPipeline": "pipeline", "PipelineResult": "pipeline",
     "MultiscaleEval": "pipeline",

@@ -45,7 +45,7 @@ extern "C" HP_API size_t hp_workspace_bytes(int n_maps, int K) {
     // Workspace header (block counter, PCK counters, 64-bit loss accumulators) + slack; kernels that need
     // per-map scratch keep it in shared memory
     (void)n_maps;
-    // + the per-block result slots of the fused pipeline kernel (hp_pipeline_bulk.cuh: 1024 blocks x 32 tagged entries
-    // at byte offset 2048; never needs zeroing - entries carry the tag of the launch that wrote them)
-    return 2048 + static_cast<size_t>(1024) * 32 * sizeof(unsigned long long);
+    // + at byte 1024 the record of a deferred cross-GPU exchange (hp_internal.cuh) and at byte 2048 the self-certifying
+    // accumulators of the fused pipeline kernel (hp_pipeline_bulk.cuh: 2K + 14 <= 142 words); all zero between launches
+    return 2048 + 2048;
 }

@@ -24,7 +24,7 @@
 #include "hp_dispatch.cuh"
 #include "hp_internal.cuh"
 #include "hp_pipeline_common.cuh"
-#include "hp_pipeline_tiles.cuh"
+#include "hp_pipeline_parts.cuh"
 #include "hp_pipeline_bulk.cuh"
 #include "hp_pipeline_stream.cuh"
 
@@ -223,16 +223,13 @@ static int pipeline_grid_div_override() {
 // ---- TMA-staged shape (hp_pipeline_bulk.cuh) ---------------------------------------------------------------------
 // experiments: HP_PIPE_EPILOGUE=atomics keeps the workspace-atomics + ticket epilogue; HP_PIPE_STRICT_PDL=0 launches a
 // serialised step without the programmatic attribute (the next launch is then not even scheduled before this one ends)
-// 0: never (atomics + ticket), 1: serialised launches only (default: in a train the epilogue is hidden behind the next
-// launches' streaming and the proven atomics path stays), 2: every launch
-static int pipeline_slots_mode() {
-    static const int mode = []() {
+// HP_PIPE_EPILOGUE=atomics keeps the workspace-atomics + fence + ticket epilogue (comparison runs)
+static bool pipeline_cert_enabled() {
+    static const bool on = []() {
         const char* e = std::getenv("HP_PIPE_EPILOGUE");
-        if (e && (e[0] == 'a' || e[0] == 'A')) return 0;
-        if (e && (e[0] == 's' || e[0] == 'S')) return 2;
-        return 1;
+        return !(e && (e[0] == 'a' || e[0] == 'A'));
     }();
-    return mode;
+    return on;
 }
 static bool pipeline_strict_pdl() {
     static const bool on = []() {
@@ -241,7 +238,6 @@ static bool pipeline_strict_pdl() {
     }();
     return on;
 }
-static std::atomic<unsigned int> g_launch_seq{0};
 
 template <int NITC, int LOSS, bool MULTI, int W, int KST, int BPS>
 static cudaError_t launch_bulk_one(BulkArgs& t, int grid, cudaStream_t stream) {
@@ -255,28 +251,9 @@ static cudaError_t launch_bulk_one(BulkArgs& t, int grid, cudaStream_t stream) {
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < 16) configured[dev] = true;
     }
-    // ---- how the blocks hand their sums to the publisher: tagged slots when they fit, else atomics + ticket -----------
-    t.slot_bits = 0;
-    t.slots = reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(t.p.ws) + kSlotOffsetBytes);
-    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-    if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess) cap = cudaStreamCaptureStatusActive;
-    // (a captured launch replays with the SAME tag: stale slots of the previous replay would look fresh)
-    const bool want_slots = pipeline_slots_mode() == 2 || (pipeline_slots_mode() == 1 && t.overlap == 0);
-    if (want_slots && cap == cudaStreamCaptureStatusNone && grid <= kSlotMaxBlocks) {
-        const int n_local = (t.p.n_maps + grid - 1) / grid;  // most maps any block owns = bound of every counter
-        const int bits = n_local <= 15 ? 4 : (n_local <= 255 ? 8 : (n_local <= 65535 ? 16 : 0));
-        if (bits != 0) {
-            const int n_counts = 2 * t.p.K + 6;
-            const int n_cent = (n_counts * bits + 31) / 32, n_ent = n_cent + 4, n_pairs = (n_ent + 1) / 2;
-            if (n_ent <= kSlotEntries && static_cast<long long>(grid) * n_pairs <= 128ll * 32 * W) {
-                unsigned int seq = ++g_launch_seq;
-                if (seq == 0) seq = ++g_launch_seq;
-                t.slot_bits = bits; t.n_cent = n_cent; t.n_pairs = n_pairs;
-                t.pdiv = FastDiv(static_cast<uint32_t>(n_pairs));
-                t.seq = seq;
-            }
-        }
-    }
+    // ---- how the blocks hand their sums to the publisher (hp_pipeline_bulk.cuh "self-certifying accumulators") --------
+    t.certs = reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(t.p.ws) + kCertOffsetBytes);
+    t.cert = (pipeline_cert_enabled() && grid <= 65535) ? 1 : 0;
     t.strict = (t.overlap == 0 && pipeline_strict_pdl()) ? 1 : 0;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(static_cast<unsigned>(grid));
@@ -311,13 +288,13 @@ static cudaError_t launch_bulk(BulkArgs& t, int sms, cudaStream_t stream) {
         default: return launch_bulk_one<NITC, 3, MULTI, W, KST, BPS>(t, grid, stream);
     }
 }
-// 0 = tiles/stream shapes, 1.. = bulk shape with (warps, stages per warp) variants for 64x64
+// experiments: HP_PIPE_SHAPE = 0 / "stream": never the TMA-staged kernel; 3: one block of 12 warps per SM for 64x64 maps
 static int pipeline_shape_choice() {
     static const int choice = []() {
         const char* e = std::getenv("HP_PIPE_SHAPE");
         if (!e) return 1;
-        if (e[0] == 't' || e[0] == 'T') return 0;       // "tiles": the register-tile kernels
-        if (e[0] >= '1' && e[0] <= '6') return e[0] - '0';
+        if (e[0] == '0' || e[0] == 's' || e[0] == 'S') return 0;
+        if (e[0] == '3') return 3;
         return 1;
     }();
     return choice;
@@ -387,63 +364,19 @@ static int launch_pipeline(const float* pred, const double* joints, const float*
         // default: 3 blocks of 4 warps per SM, one 16 KB stage per warp (12 stages = 192 KB in flight per SM)
         if (HW == 256) e = launch_bulk<2, false, 4, 8, 3>(t, sms, stream);
         else if (HW == 1024) e = launch_bulk<8, false, 4, 4, 3>(t, sms, stream);
-        else if (HW > 4096) {
-            if (pipeline_shape_choice() == 2) e = launch_bulk<32, true, 3, 2, 2>(t, sms, stream);
-            else e = launch_bulk<32, true, 4, 1, 3>(t, sms, stream);
-        } else {
-            switch (pipeline_shape_choice()) {
-                case 2: e = launch_bulk<32, false, 6, 1, 2>(t, sms, stream); break;
-                case 3: e = launch_bulk<32, false, 12, 1, 1>(t, sms, stream); break;
-                case 4: e = launch_bulk<32, false, 3, 1, 4>(t, sms, stream); break;
-                // experiments: the map in 4 KB / 8 KB chunks with their own barriers and an online-softmax merge, so that
-                // the arithmetic on the first chunks overlaps the flight of the last one (shorter start-up and drain)
-                case 5: t.n_chunks = 4; e = launch_bulk<8, true, 4, 4, 3>(t, sms, stream); break;
-                case 6: t.n_chunks = 2; e = launch_bulk<16, true, 4, 2, 3>(t, sms, stream); break;
-                default: e = launch_bulk<32, false, 4, 1, 3>(t, sms, stream); break;
-            }
-        }
+        else if (HW > 4096) e = launch_bulk<32, true, 4, 1, 3>(t, sms, stream);
+        else if (pipeline_shape_choice() == 3) e = launch_bulk<32, false, 12, 1, 1>(t, sms, stream);
+        else e = launch_bulk<32, false, 4, 1, 3>(t, sms, stream);
         if (e != cudaSuccess) return fail(static_cast<int>(e), "hp_pipeline_fused: %s", cudaGetErrorString(e));
         return launch_status("hp_pipeline_fused");
     }
     const int tile_elems = (HW % 1024 == 0) ? 1024 : ((HW % 256 == 0) ? 256 : 0);
     if (fast_ok && tile_elems != 0) {
-        const int tpm = HW / tile_elems;
-        if (tpm == 1 || tpm == 2 || tpm == 4) {
-            // tile-granular persistent shape: 4 blocks of 4 warps per SM, static stride over the tiles
-            if (g_sm_count == 0) {
-                g_sm_count = hp_device_sm_count();
-                if (g_sm_count <= 0) g_sm_count = 148;
-            }
-            TileArgs t{};
-            t.p = a;
-            t.tiles_per_map = tpm;
-            t.n_tiles = a.n_maps * tpm;
-            t.tdiv = FastDiv(static_cast<uint32_t>(tpm));
-            t.kdiv = FastDiv(static_cast<uint32_t>(K));
-            // static stride n_warps = 4*grid over the tiles: with tpm | 4 the warps of a block always hold the
-            // tiles of the same map(s) in the same iteration, which the shared-memory ring relies on
-            static const int variant = []() {
-                const char* e = std::getenv("HP_TILES_VARIANT");  // tuning knob: A = 2 buffers x 4 blocks/SM, B = 1 x 6
-                if (e && (e[0] == 'B' || e[0] == 'b')) return 1;
-                if (e && (e[0] == 'C' || e[0] == 'c')) return 2;
-                return 0;
-            }();
-            int grid = g_sm_count * (variant == 1 ? 6 : (variant == 2 ? 5 : 4));
-            const int need = (t.n_tiles + kTileWarps - 1) / kTileWarps;
-            if (grid > need) grid = need;
-            if (variant == 1) {
-                if (tile_elems == 1024) { HP_BY_LOSS(pipeline_tiles1_kernel, grid, t, 8) } else { HP_BY_LOSS(pipeline_tiles1_kernel, grid, t, 2) }
-            } else if (variant == 2) {
-                if (tile_elems == 1024) { HP_BY_LOSS(pipeline_tiles1c_kernel, grid, t, 8) } else { HP_BY_LOSS(pipeline_tiles1c_kernel, grid, t, 2) }
-            } else {
-                if (tile_elems == 1024) { HP_BY_LOSS(pipeline_tiles_kernel, grid, t, 8) } else { HP_BY_LOSS(pipeline_tiles_kernel, grid, t, 2) }
-            }
-        } else {
-            // many tiles per map (128x128 ...): one warp streams a whole map
-            const int grid = (a.n_maps + kStreamWarps - 1) / kStreamWarps;
-            a.ntiles = tpm;
-            if (tile_elems == 1024) { HP_BY_LOSS(pipeline_stream_kernel, grid, a, 8) } else { HP_BY_LOSS(pipeline_stream_kernel, grid, a, 2) }
-        }
+        // aligned maps of whole 1 KB / 4 KB tiles that the TMA-staged kernel does not take (e.g. 32x64, 48x64): one warp
+        // streams a whole map through register tiles
+        const int grid = (a.n_maps + kStreamWarps - 1) / kStreamWarps;
+        a.ntiles = HW / tile_elems;
+        if (tile_elems == 1024) { HP_BY_LOSS(pipeline_stream_kernel, grid, a, 8) } else { HP_BY_LOSS(pipeline_stream_kernel, grid, a, 2) }
         return launch_status("hp_pipeline_fused");
     }
 #undef HP_BY_LOSS

@@ -22,7 +22,7 @@
 #include "hp_pipeline_common.cuh"
 #include "hp_peer_step.cuh"
 #include "hp_tma.cuh"
-#include "hp_pipeline_tiles.cuh"  // PatchSlot, WarpLoss, warp_sum3_scattered, kTileMaxPatch
+#include "hp_pipeline_parts.cuh"  // PatchSlot, WarpLoss, warp_sum3_scattered, kTileMaxPatch
 
 namespace hp {
 
@@ -34,15 +34,10 @@ struct BulkArgs {
                     // d consecutive launches are resident at once (HP_PIPE_OVERLAP_PREV | HP_PIPE_DEPTH(d))
     PeerLink link;  // world > 1: the last block sums the partial vector over the ranks itself (NVLink peer memory)
     int defer;      // world > 1: deferred exchange (HP_PIPE_DEFER_EXCHANGE): this step only sends, and completes the previous one
-    // ---- block results through tagged slots (see "epilogue" below); slot_bits == 0: the atomics + ticket epilogue ----
-    int strict;           // serialised launch: wait for the previous grid BEFORE the first global read (the launch carries
-                          // the programmatic attribute only so that block scheduling and the prologue hide the launch gap)
-    unsigned int seq;     // tag of this launch (never 0, unique per process)
-    int slot_bits;        // bits per packed counter: 4 / 8 / 16 (every counter of a block is < 2^slot_bits); 0 = off
-    int n_cent;           // slot entries that carry packed counters; then 4 entries with the two fixed-point loss sums
-    int n_pairs;          // 16-byte entry pairs per slot
-    FastDiv pdiv;         // by n_pairs
-    unsigned long long* slots;  // [gridDim.x][kSlotEntries] in the workspace
+    int strict;     // serialised launch: wait for the previous grid BEFORE the first global read (the launch carries the
+                    // programmatic attribute only so that block scheduling and the prologue hide the launch gap)
+    int cert;       // block sums through self-certifying accumulators (see below); 0: the atomics + fence + ticket epilogue
+    unsigned long long* certs;  // [2K + 6 + 8] 64-bit accumulators in the workspace (zero between launches)
     unsigned long long* trace;  // nullable profiling buffer (hp_debug_pipeline_trace): per block a header
                                 // {globaltimer, clock64} at entry and exit, per warp and map 4 clock64 stamps
 };
@@ -160,142 +155,26 @@ struct BulkShared {
     float4 out[kBulkOutCap];        // {x, y, maxval, weight} of the block's first maps
     long long pub[4 + 2 * HP_MAX_K + 6];
     double pub_acc[HP_MAX_K];
-    int tot_counts[2 * HP_MAX_K + 6];      // publisher block (slot epilogue): sums over the blocks' slots
-    unsigned long long tot_fx[4];          // low / high 32-bit halves of the two fixed-point loss sums, summed separately
 };
 
-// ---- block results through tagged slots ------------------------------------------------------------------------------
-// The classic "REDs into a workspace, __threadfence, atomic ticket, last block reads the workspace back" epilogue costs
-// every block two dependent L2 round trips (the fence waits for the REDs, the ticket for the fence) and the last block
-// a third one - 2-4.5 us of a ~20 us launch (profiles/r1_trace_serial.json: exit_after_barrier).  Here a block instead
-// PACKS its contribution (2K PCK counters + 6 non-finite counters at 4/8/16 bits each, two 64-bit fixed-point sums)
-// into <= 32 tagged 8-byte entries {payload:32, launch tag:32} and stores them into ITS slot with plain 16-byte stores:
-// data and "ready" travel together, so there is no fence, no ticket and nothing to zero afterwards.  The publisher
-// (the last block index: it owns the fewest maps) polls all slots with every thread, sums them in shared memory with
-// integer atomics (exact, order-free), and finalises.  One one-way store + one poll on the critical path.
-constexpr int kSlotEntries = 32;            // uint64 entries per block slot (256 B)
-constexpr int kSlotMaxBlocks = 1024;
-constexpr size_t kSlotOffsetBytes = 2048;   // of the slot array inside the workspace (after the Workspace header)
-__device__ __forceinline__ void slot_store2(unsigned long long* p, unsigned long long a, unsigned long long b) {
-    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
-}
-__device__ __forceinline__ ulonglong2 slot_load2(const unsigned long long* p) {
-    ulonglong2 v;
-    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
+// ---- block sums through self-certifying accumulators ---------------------------------------------------------------
+// The classic "REDs into a workspace, __threadfence, atomic ticket, last block reads the workspace back" epilogue puts
+// three dependent L2 round trips between the last map and the end of the launch (the fence waits for the REDs, the
+// ticket for the fence, the read-back for the ticket): 2-4.5 us of a ~20 us launch (profiles/r1_trace_serial.json).
+// Here every accumulator certifies ITSELF: it is a 64-bit word {contributors:32 | value:32}, and every block adds
+// (1 << 32 | its value) to EVERY accumulator with one fire-and-forget 64-bit RED - zeros included.  A word whose high
+// half equals the grid size is complete, whatever order the REDs arrived in: no fence, no ticket, no read-back after a
+// flag.  The publisher (the last block index: it owns the fewest maps) polls the 2K + 14 words with one warp - a single
+// L2 round trip per poll -, zeroes them for the next launch and finalises.  One hop + one poll on the critical path.
+// Layout: [0, 2K) PCK hits / valid, [2K, 2K+6) non-finite loss counters, then the two 64-bit fixed-point loss sums as
+// 4 + 4 limbs of 16 bits (a limb summed over <= 65535 blocks fits the 32-bit value field; sum_i limb_i << 16 i
+// reproduces the two's-complement total mod 2^64).
+constexpr size_t kCertOffsetBytes = 2048;   // of the accumulators inside the workspace (after the Workspace header)
+__device__ __forceinline__ int cert_words(int K) { return 2 * K + 6 + 8; }
+__device__ __forceinline__ unsigned long long cert_load(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
-}
-// payload of slot entry e of THIS block (sh.counts / sh.acc are final: called after the block barrier)
-__device__ __forceinline__ unsigned int slot_entry_payload(const BulkArgs& t, const BulkShared& sh, int e) {
-    const int K = t.p.K, n_counts = 2 * K + 6, cb = t.slot_bits, per = 32 / cb;
-    if (e < t.n_cent) {
-        unsigned int w = 0;
-        for (int j = 0; j < per; ++j) {
-            const int idx = e * per + j;
-            if (idx < n_counts) {
-                const unsigned int c = idx < 2 * K ? static_cast<unsigned int>(sh.counts[idx])
-                                                   : static_cast<unsigned int>(sh.acc[2 + idx - 2 * K]);
-                w |= c << (j * cb);
-            }
-        }
-        return w;
-    }
-    const int f = e - t.n_cent;  // 0..3: lo(mse), hi(mse), lo(kl), hi(kl)
-    if (f >= 4) return 0u;       // padding of an odd entry count
-    const unsigned long long v = sh.acc[f >> 1];
-    return static_cast<unsigned int>((f & 1) ? (v >> 32) : (v & 0xffffffffull));
-}
-// warp 0 of every block: pack + store the block's slot (lane l writes entries 2l, 2l+1)
-__device__ __forceinline__ void slot_publish_block(const BulkArgs& t, const BulkShared& sh, int lane) {
-    if (lane < t.n_pairs) {
-        const unsigned long long tag = static_cast<unsigned long long>(t.seq) << 32;
-        unsigned long long* slot = t.slots + static_cast<size_t>(blockIdx.x) * kSlotEntries;
-        slot_store2(slot + 2 * lane, tag | slot_entry_payload(t, sh, 2 * lane), tag | slot_entry_payload(t, sh, 2 * lane + 1));
-    }
-}
-// publisher block, ALL threads: poll every block's slot until it carries this launch's tag, sum into sh.tot_*.
-// Pair p = block * n_pairs + pr is owned by thread p % NTHREADS (bit p / NTHREADS of its pending mask).  The loads of a
-// pass go out kBatch at a time per thread (a pass over all slots is one or two L2 round trips, not one per slot); PCK
-// counters are summed with 32-bit shared-memory atomics, the 32-bit halves of the fixed-point loss sums in registers
-// (64-bit shared-memory atomics are compare-and-swap loops: 4 hot addresses x hundreds of blocks).
-template <int NTHREADS>
-__device__ __forceinline__ void slot_collect(const BulkArgs& t, BulkShared& sh) {
-    constexpr int kWords = 4;   // 128 pairs per thread
-    constexpr int kBatch = 8;   // loads in flight per thread
-    const int tid = threadIdx.x;
-    const int total = static_cast<int>(gridDim.x) * t.n_pairs;
-    const int K = t.p.K, n_counts = 2 * K + 6, cb = t.slot_bits, per = 32 / cb;
-    const unsigned int cmask = (1u << cb) - 1u;
-    const unsigned long long tag = static_cast<unsigned long long>(t.seq) << 32, tag_mask = 0xffffffff00000000ull;
-    unsigned int pending[kWords];
-#pragma unroll
-    for (int w = 0; w < kWords; ++w) {
-        const int first = tid + w * 32 * NTHREADS;  // pairs tid + (32 w + b) * NTHREADS, b = 0..31
-        const int left = total - first;
-        const int nb = left <= 0 ? 0 : (left + NTHREADS - 1) / NTHREADS;
-        pending[w] = nb >= 32 ? 0xffffffffu : ((1u << nb) - 1u);
-    }
-    unsigned long long fx[4] = {0ull, 0ull, 0ull, 0ull};
-    auto consume = [&](int e, unsigned int payload) {
-        if (e < t.n_cent) {
-            for (int j = 0; j < per; ++j) {
-                const unsigned int c = (payload >> (j * cb)) & cmask;
-                const int idx = e * per + j;
-                if (c != 0 && idx < n_counts) atomicAdd(&sh.tot_counts[idx], static_cast<int>(c));
-            }
-        } else {
-            const int f = e - t.n_cent;
-            fx[0] += (f == 0) ? payload : 0u;
-            fx[1] += (f == 1) ? payload : 0u;
-            fx[2] += (f == 2) ? payload : 0u;
-            fx[3] += (f == 3) ? payload : 0u;
-        }
-    };
-    const long long t0 = clock64();
-    bool any = true;
-    while (any) {
-        any = false;
-#pragma unroll
-        for (int w = 0; w < kWords; ++w) {
-            unsigned int m = pending[w];
-            while (m != 0) {
-                int bit[kBatch];
-                ulonglong2 v[kBatch];
-#pragma unroll
-                for (int j = 0; j < kBatch; ++j) {
-                    bit[j] = -1;
-                    if (m != 0) {
-                        bit[j] = __ffs(m) - 1;
-                        m &= m - 1;
-                        const int p = tid + (w * 32 + bit[j]) * NTHREADS;
-                        const uint32_t b = t.pdiv.div(static_cast<uint32_t>(p));
-                        v[j] = slot_load2(t.slots + static_cast<size_t>(b) * kSlotEntries + 2 * (p - b * t.n_pairs));
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < kBatch; ++j) {
-                    if (bit[j] < 0) continue;
-                    if ((v[j].x & tag_mask) == tag && (v[j].y & tag_mask) == tag) {
-                        const int p = tid + (w * 32 + bit[j]) * NTHREADS;
-                        const uint32_t b = t.pdiv.div(static_cast<uint32_t>(p));
-                        const int pr = p - static_cast<int>(b) * t.n_pairs;
-                        consume(2 * pr, static_cast<unsigned int>(v[j].x));
-                        consume(2 * pr + 1, static_cast<unsigned int>(v[j].y));
-                        pending[w] &= ~(1u << bit[j]);
-                    }
-                }
-            }
-            any |= pending[w] != 0;
-        }
-        if (any && clock64() - t0 > 4000000000ll) __trap();  // ~2 s: a block of this grid never published (it faulted)
-    }
-    // the loss-sum halves: warp shuffle tree, then one 64-bit shared-memory atomic per warp and half
-#pragma unroll
-    for (int f = 0; f < 4; ++f) {
-        unsigned long long x = fx[f];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-        if ((tid & 31) == 0 && x != 0ull) atomicAdd(&sh.tot_fx[f], x);
-    }
 }
 
 // last block, ONE warp: workspace -> partial (= or +=), workspace back to zero, optional finalise
@@ -311,17 +190,15 @@ __device__ __forceinline__ void bulk_publish_warp(const BulkArgs& t, BulkShared&
     const int K = a.K, n = 4 + 2 * K + 6;
     const bool add = a.accumulate != 0;
     const bool exchange = link.world > 1;
-    const bool from_slots = t.slot_bits != 0;  // totals already summed in shared memory (slot_collect)
+    const bool from_cert = t.cert != 0;  // raw totals already in sh.pub (cert_collect_warp)
     for (int i = lane; i < n; i += 32) {
         long long v;
         if (i == 2) {
             v = a.n_maps;
         } else if (i == 3) {
             v = static_cast<long long>(a.n_maps) * a.HW;
-        } else if (from_slots) {
-            if (i < 2) v = static_cast<long long>((sh.tot_fx[2 * i + 1] << 32) + sh.tot_fx[2 * i]);
-            else if (i < 4 + 2 * K) v = sh.tot_counts[i - 4];
-            else v = sh.tot_counts[2 * K + (i - 4 - 2 * K)];
+        } else if (from_cert) {
+            v = sh.pub[i];
         } else if (i < 2) {
             v = static_cast<long long>(*reinterpret_cast<volatile unsigned long long*>(&a.ws->acc[i]));
             a.ws->acc[i] = 0;
@@ -344,7 +221,7 @@ __device__ __forceinline__ void bulk_publish_warp(const BulkArgs& t, BulkShared&
     } else if (a.result) {
         warp_result_from_partial(sh.pub, K, a.result, sh.pub_acc, lane);
     }
-    if (lane == 0 && !from_slots) a.ws->counter = 0;
+    if (lane == 0 && !from_cert) a.ws->counter = 0;
 }
 
 // NITC: iterations (of 128 elements) per chunk;  MULTI: maps span several chunks;
@@ -628,30 +505,71 @@ __global__ void __launch_bounds__(32 * W, BPS) pipeline_bulk_kernel(const BulkAr
     __syncthreads();
     if (trace && threadIdx.x == 0) trace[5] = static_cast<unsigned long long>(clock64());
     if (!dep_ok) griddep_wait();  // (warps without maps) previous grid complete: outputs and workspace may be written
-    if (t.slot_bits != 0) {
-        // ---- tagged slots: one one-way store per block, the publisher polls --------------------------------------------
+    if (t.cert != 0) {
+        // ---- self-certifying accumulators: one fire-and-forget RED per accumulator and block, the publisher polls ------
         const bool publisher = blockIdx.x == gridDim.x - 1;
-        if (publisher) {
-            for (int i = threadIdx.x; i < 2 * HP_MAX_K + 6; i += blockDim.x) sh.tot_counts[i] = 0;
-            if (threadIdx.x < 4) sh.tot_fx[threadIdx.x] = 0;
+        const int K = a.K, nw = cert_words(K);
+        if (warp == 0) {
+            for (int i = lane; i < nw; i += 32) {
+                unsigned int v;
+                if (i < 2 * K) {
+                    v = static_cast<unsigned int>(sh.counts[i]);
+                } else if (i < 2 * K + 6) {
+                    v = static_cast<unsigned int>(sh.acc[2 + i - 2 * K]);
+                } else {
+                    const int f = i - 2 * K - 6;  // limb f & 3 of loss sum f >> 2
+                    v = static_cast<unsigned int>((sh.acc[f >> 2] >> (16 * (f & 3))) & 0xffffull);
+                }
+                atomicAdd(&t.certs[i], (1ull << 32) | static_cast<unsigned long long>(v));  // RED.E.ADD.64, no return
+            }
         }
-        if (warp == 0) slot_publish_block(t, sh, lane);
-        {   // every warp delivers its share of the buffered per-map outputs
+        if (!(publisher && warp == 0)) {  // the other warps deliver the buffered per-map outputs meanwhile
             const int n_buf = n_local < kBulkOutCap ? n_local : kBulkOutCap;
-            for (int jb = static_cast<int>(threadIdx.x); jb < n_buf; jb += 32 * W) {
+            const int first = publisher ? static_cast<int>(threadIdx.x) - 32 : static_cast<int>(threadIdx.x);
+            const int step = publisher ? 32 * (W - 1) : 32 * W;
+            for (int jb = first; jb < n_buf; jb += step) {
                 const int map = static_cast<int>(blockIdx.x) + jb * static_cast<int>(gridDim.x);
                 const float4 o = sh.out[jb];
                 *reinterpret_cast<float2*>(a.pred_xy + 2 * static_cast<size_t>(map)) = make_float2(o.x, o.y);
                 if (a.maxvals) a.maxvals[map] = o.z;
                 if (a.weight_out) a.weight_out[map] = o.w;
             }
-        }
-        if (publisher) {
-            __syncthreads();  // totals zeroed
-            slot_collect<32 * W>(t, sh);
-            __syncthreads();
+        } else {
+            // ONE warp: poll until every accumulator has heard from every block, take the totals, zero the words
+            const unsigned int want = gridDim.x;
+            const long long t0 = clock64();
+            unsigned long long w0 = 0ull, w1 = 0ull, w2 = 0ull;  // words lane, lane + 32, lane + 64 (2K + 14 <= 142 -> 5 max)
+            unsigned long long w3 = 0ull, w4 = 0ull;
+            bool done = false;
+            while (!done) {
+                bool ok = true;
+                if (lane < nw) { w0 = cert_load(t.certs + lane); ok &= static_cast<unsigned int>(w0 >> 32) == want; }
+                if (lane + 32 < nw) { w1 = cert_load(t.certs + lane + 32); ok &= static_cast<unsigned int>(w1 >> 32) == want; }
+                if (lane + 64 < nw) { w2 = cert_load(t.certs + lane + 64); ok &= static_cast<unsigned int>(w2 >> 32) == want; }
+                if (lane + 96 < nw) { w3 = cert_load(t.certs + lane + 96); ok &= static_cast<unsigned int>(w3 >> 32) == want; }
+                if (lane + 128 < nw) { w4 = cert_load(t.certs + lane + 128); ok &= static_cast<unsigned int>(w4 >> 32) == want; }
+                done = __all_sync(0xffffffffu, ok);
+                if (!done && clock64() - t0 > 4000000000ll) __trap();  // ~2 s: a block of this grid never reported (it faulted)
+            }
+            // raw partial vector in sh.pub: [0,1] loss sums, [4, 4+2K) counts, [4+2K, 4+2K+6) non-finite counters
+            unsigned long long* limb = reinterpret_cast<unsigned long long*>(sh.pub_acc);  // 8 words of scratch
+            auto take = [&](int i, unsigned long long w) {
+                if (i >= nw) return;
+                const unsigned long long v = w & 0xffffffffull;
+                if (i < 2 * K + 6) sh.pub[4 + i] = static_cast<long long>(v);
+                else limb[i - 2 * K - 6] = v;
+                t.certs[i] = 0ull;  // ready for the next launch (ordered before it by the grid's completion)
+            };
+            take(lane, w0); take(lane + 32, w1); take(lane + 64, w2); take(lane + 96, w3); take(lane + 128, w4);
+            __syncwarp();
+            if (lane < 2) {
+                unsigned long long tot = 0ull;
+                for (int i = 0; i < 4; ++i) tot += limb[4 * lane + i] << (16 * i);
+                sh.pub[lane] = static_cast<long long>(tot);
+            }
+            __syncwarp();
             // (the block's stages are idle by now and serve as the exchange's scratch space)
-            if (warp == 0) bulk_publish_warp(t, sh, reinterpret_cast<long long*>(s_dyn), lane);
+            bulk_publish_warp(t, sh, reinterpret_cast<long long*>(s_dyn), lane);
         }
     } else if (warp == 0) {
         for (int i = lane; i < 8 + 2 * a.K; i += 32) {

@@ -3,7 +3,7 @@
 // One WARP streams a whole map through double-buffered register tiles (8 x 128-bit loads per lane),
 // no block barrier on the data path.  Used where a map is large or tiny relative to a block's share:
 // 128x128 (16 tiles per map, many waves) and 16x16 (one quarter-size tile).  For 64x64 / 32x32 the
-// tile-granular shape (hp_pipeline_tiles.cuh) is faster: there a whole-map-per-warp work item is so long
+// TMA-staged shape (hp_pipeline_bulk.cuh) is faster: there a whole-map-per-warp work item is so long
 // (~10 us) that the tail of a 2.3-wave grid idles the SMs 47 % of the time (profiles/r1_pipeline_v2.md).
 // The instruction diet is the same: target-free hot loop (FMNMX3 max, ==max index scan, packed
 // FFMA2/FADD2, MUFU.EX2), patch terms from an up-front re-read of the <=169 patch pixels.

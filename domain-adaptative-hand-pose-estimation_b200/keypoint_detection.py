@@ -22,45 +22,101 @@ def _device():
 
 
 def _as_cuda_heatmaps(x, what):
-    """-> (cuda float32 contiguous tensor, was_numpy, numpy dtype or None)"""
+    """-> (cuda contiguous tensor, was_numpy, numpy dtype or None).  float32 / float16 / bfloat16 become float32 (exact
+    widening); float64 stays float64 and is decoded by the float64 kernel - a cast to float32 could merge two distinct
+    maxima into a tie and move the argmax (utils/keypoint_detection.py:12-21 accepts any ndarray dtype)."""
     if isinstance(x, np.ndarray):
-        if x.dtype == np.float64:
-            raise TypeError(f"{what}: float64 heatmaps are not supported (argmax ties would change "
-                            "under a cast); pass float32 like train1.py/test.py do")
-        if x.dtype not in (np.float32, np.float16):
+        if x.dtype not in (np.float32, np.float16, np.float64):
             raise TypeError(f"{what}: unsupported dtype {x.dtype}")
         t = torch.from_numpy(np.ascontiguousarray(x)).to(_device(), non_blocking=False)
+        if x.dtype == np.float64:
+            return t.contiguous(), True, x.dtype
         return _lib.require_cuda(t, what), True, x.dtype
     if isinstance(x, torch.Tensor):
+        if x.dtype == torch.float64:
+            if not x.is_cuda:
+                raise RuntimeError(f"{what}: tensor is on {x.device}; the B200 heatmap path runs on CUDA only "
+                                   "(there is no CPU fallback)")
+            return x.detach().contiguous(), False, None
         return _lib.require_cuda(x.detach(), what), False, None
     raise AssertionError("batch_heatmaps should be numpy.ndarray")  # keypoint_detection.py:12-13
 
 
-def decode(heat: torch.Tensor):
-    """CUDA tensor [B,K,H,W] -> (preds float32 [B,K,2] as (x,y), maxvals float32 [B,K,1]) on device.
-    utils/keypoint_detection.py:16-35 semantics (first index on ties, NaN wins, masked by max>0)."""
-    heat = _lib.require_cuda(heat, "decode")
+def decode(heat: torch.Tensor, refine=None):
+    """CUDA tensor [B,K,H,W] (float32, or float64) -> (preds float32 [B,K,2] as (x,y), maxvals [B,K,1] in the input's
+    precision) on device.  utils/keypoint_detection.py:16-35 semantics (first index on ties, NaN wins, masked by max>0).
+
+    ``refine="quarter"`` (opt-in; NOT in the reference, whose ``get_max_preds`` has no refinement - SURVEY.md row a13):
+    shifts each interior maximum by a quarter pixel towards its higher neighbour,
+    ``coord += 0.25 * sign(hm[y][x+1] - hm[y][x-1])`` (resp. y) for ``1 < x < W-1, 1 < y < H-1``."""
+    if refine not in (None, "quarter"):
+        raise ValueError("refine must be None or 'quarter'")
+    f64 = isinstance(heat, torch.Tensor) and heat.dtype == torch.float64
+    if f64:
+        if not heat.is_cuda:
+            raise RuntimeError("decode: tensor is on cpu; the B200 heatmap path runs on CUDA only (there is no CPU fallback)")
+        heat = heat.contiguous()
+    else:
+        heat = _lib.require_cuda(heat, "decode")
     B, K, H, W = heat.shape
     if H * W == 0:
         raise ValueError("attempt to get argmax of an empty sequence")
     preds = torch.empty((B, K, 2), dtype=torch.float32, device=heat.device)
-    maxvals = torch.empty((B, K, 1), dtype=torch.float32, device=heat.device)
+    maxvals = torch.empty((B, K, 1), dtype=heat.dtype if f64 else torch.float32, device=heat.device)
     with _lib.on_device(heat.device):
-        _lib.call("hp_argmax_decode", _lib.ptr(heat), B * K, H, W, _lib.ptr(preds), _lib.ptr(maxvals), None,
-                  _lib.stream_ptr(heat.device))
+        st = _lib.stream_ptr(heat.device)
+        if f64:
+            _lib.call("hp_argmax_decode_f64", _lib.ptr(heat), B * K, H, W, _lib.ptr(preds), _lib.ptr(maxvals), st)
+            if refine == "quarter":
+                _lib.call("hp_refine_quarter", _lib.ptr(heat.float()), B * K, H, W, _lib.ptr(preds), st)
+        else:
+            _lib.call("hp_argmax_decode", _lib.ptr(heat), B * K, H, W, _lib.ptr(preds), _lib.ptr(maxvals), None, st)
+            if refine == "quarter":
+                _lib.call("hp_refine_quarter", _lib.ptr(heat), B * K, H, W, _lib.ptr(preds), st)
     return preds, maxvals
 
 
-def get_max_preds(batch_heatmaps):
-    """utils/keypoint_detection.py:7-35.  numpy [B,K,H,W] -> (preds float32 [B,K,2], maxvals [B,K,1])."""
+def get_max_preds(batch_heatmaps, refine=None):
+    """utils/keypoint_detection.py:7-35.  numpy [B,K,H,W] -> (preds float32 [B,K,2], maxvals [B,K,1] in the input dtype).
+    ``refine``: see :func:`decode` (opt-in extension, default off = the reference)."""
     if not isinstance(batch_heatmaps, (np.ndarray, torch.Tensor)):
         raise AssertionError("batch_heatmaps should be numpy.ndarray")
     assert batch_heatmaps.ndim == 4, "batch_images should be 4-ndim"
     heat, was_numpy, np_dtype = _as_cuda_heatmaps(batch_heatmaps, "get_max_preds")
-    preds, maxvals = decode(heat)
+    preds, maxvals = decode(heat, refine)
     if was_numpy:
         return preds.cpu().numpy(), maxvals.cpu().numpy().astype(np_dtype, copy=False)
     return preds, maxvals
+
+
+def group_accuracy(accuracies, keypoints_group):
+    """uda/dataset/keypoint_dataset.py:58-71 on the device: per-group means of the per-joint accuracies.
+    ``accuracies``: float64 [K] CUDA tensor (e.g. ``pck(...)[0][:K]``) or anything ``torch.as_tensor`` takes;
+    ``keypoints_group``: ``{name: indices}``.  -> ``{name: float}`` (one small device->host read), summed left to right
+    like the reference's ``sum(...) / len(...)`` so the float64 values are bit-equal."""
+    acc = torch.as_tensor(accuracies, dtype=torch.float64)
+    if not acc.is_cuda:
+        acc = acc.to(_device())
+    acc = acc.contiguous()
+    names = list(keypoints_group)
+    offsets, index = [0], []
+    for n in names:
+        idx = [int(i) for i in keypoints_group[n]]
+        if not idx:
+            raise ZeroDivisionError("division by zero")          # what the reference's sum(...)/len(...) raises
+        if max(idx) >= acc.numel() or min(idx) < -acc.numel():
+            raise IndexError("index out of range")
+        index += [i % acc.numel() for i in idx]
+        offsets.append(len(index))
+    dev = acc.device
+    off_t = torch.tensor(offsets, dtype=torch.int32, device=dev)
+    idx_t = torch.tensor(index, dtype=torch.int32, device=dev)
+    out = torch.empty((len(names),), dtype=torch.float64, device=dev)
+    with _lib.on_device(dev):
+        _lib.call("hp_group_accuracy", _lib.ptr(acc), _lib.ptr(off_t), _lib.ptr(idx_t), len(names), _lib.ptr(out),
+                  _lib.stream_ptr(dev))
+    host = out.cpu().numpy()
+    return {n: float(host[i]) for i, n in enumerate(names)}
 
 
 def pck(output: torch.Tensor, target: torch.Tensor, thr: float = 0.5):
@@ -84,6 +140,26 @@ def pck(output: torch.Tensor, target: torch.Tensor, thr: float = 0.5):
     return acc, pred_xy, counts
 
 
+def _pck_from_decodes(output, target, thr):
+    """accuracy() for inputs the fused kernel does not take (float64 heatmaps): decode both, then the PCK count and
+    finalise kernels on the coordinates.  Same integer counts / float64 ratios."""
+    if output.shape != target.shape or output.ndim != 4:
+        raise ValueError(f"accuracy: output {tuple(output.shape)} vs target {tuple(target.shape)}")
+    B, K, H, W = output.shape
+    if K > _lib.MAX_K:
+        raise ValueError(f"accuracy: K={K} exceeds HP_MAX_K={_lib.MAX_K}")
+    pred_xy, _ = decode(output)
+    tgt_xy, _ = decode(target)
+    dev = output.device
+    counts = torch.zeros((2 * K,), dtype=torch.int32, device=dev)
+    acc = torch.empty((K + 2,), dtype=torch.float64, device=dev)
+    with _lib.on_device(dev):
+        _lib.call("hp_pck_accumulate", _lib.ptr(pred_xy), _lib.ptr(tgt_xy), B, K, H, W, C.c_double(thr), _lib.ptr(counts),
+                  _lib.stream_ptr(dev))
+        _lib.call("hp_pck_finalize", _lib.ptr(counts), K, _lib.ptr(acc), _lib.stream_ptr(dev))
+    return acc, pred_xy
+
+
 def accuracy(output, target, hm_type="gaussian", thr=0.5):
     """utils/keypoint_detection.py:63-92.  -> (acc float64[K], avg_acc, cnt, pred [B,K,2]).
 
@@ -94,7 +170,10 @@ def accuracy(output, target, hm_type="gaussian", thr=0.5):
         raise NameError("accuracy: only hm_type='gaussian' is defined by the reference")
     out_t, was_numpy, _ = _as_cuda_heatmaps(output, "accuracy(output)")
     tgt_t, _, _ = _as_cuda_heatmaps(target, "accuracy(target)")
-    acc_vec, pred_xy, _ = pck(out_t, tgt_t, thr)
+    if out_t.dtype == torch.float64 or tgt_t.dtype == torch.float64:
+        acc_vec, pred_xy = _pck_from_decodes(out_t, tgt_t, thr)     # float64 heatmaps: two decodes + the count kernels
+    else:
+        acc_vec, pred_xy, _ = pck(out_t, tgt_t, thr)
     host = acc_vec.cpu().numpy()
     K = out_t.shape[1]
     acc = host[:K].copy()

@@ -123,3 +123,22 @@ def test_config3_multiscale_eval_256x21_32_64_128_vs_oracle():
         h2, v2 = O.pck_counts(got_xy, txy, side, side)
         c = counts.cpu().numpy()
         assert np.array_equal(c[:K], h2) and np.array_equal(c[K:], v2)
+
+
+@pytest.mark.parametrize("H,W", [(32, 64), (16, 32), (48, 64), (8, 32)])
+def test_pipeline_aligned_shapes_outside_the_staged_kernel_vs_oracle(H, W):
+    """Maps of whole 1 KB / 4 KB tiles that are not 16^2 / 32^2 / n x 4096: served by the warp-per-map stream kernel
+    (they went to the retired register-tile kernels in round 1)."""
+    B = 6
+    d = hp.synth.make_host_batch(2400 + H, B, K, H, W, image_size=4 * W)
+    # make_host_batch draws square images: rescale y so that joints/stride land inside the H x W map
+    d["joints"][..., 1] *= H / W
+    want = O.pipeline(d["pred"], d["joints"], d["vis"], kl_epsilon=1e-7, image_size=(4 * W, 4 * H))
+    dev = torch.device("cuda", 0)
+    pipe = hp.HeatmapPipeline(num_keypoints=K, heatmap_size=(W, H), image_size=(4 * W, 4 * H), kl_epsilon=1e-7, device=dev)
+    out = pipe(*(torch.from_numpy(d[k]).to(dev) for k in ("pred", "joints", "vis")))
+    got = out.host()
+    assert np.array_equal(out.pred_xy.cpu().numpy(), want["pred_xy"])
+    assert np.array_equal(got["acc"], want["acc"]) and got["cnt"] == want["cnt"]
+    np.testing.assert_allclose(got["mse"], want["mse"], rtol=1e-5)
+    np.testing.assert_allclose(got["kl"], want["kl"], rtol=1e-5)
