@@ -46,6 +46,6 @@ extern "C" HP_API size_t hp_workspace_bytes(int n_maps, int K) {
     // per-map scratch keep it in shared memory
     (void)n_maps;
     // + at byte 1024 the record of a deferred cross-GPU exchange (hp_internal.cuh) and at byte 2048 the self-certifying
-    // accumulators of the fused pipeline kernel (hp_pipeline_bulk.cuh: 2K + 14 <= 142 words); all zero between launches
-    return 2048 + 2048;
+    // accumulators of the fused pipeline kernel (hp_pipeline_bulk.cuh: 4 copies of 160 words); all zero between launches
+    return 2048 + 4 * 160 * sizeof(unsigned long long);
 }

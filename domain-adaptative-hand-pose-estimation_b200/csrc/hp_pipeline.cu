@@ -211,6 +211,15 @@ static unsigned long long* g_trace = nullptr;
 static size_t g_trace_words = 0;
 static unsigned long long g_trace_seq = 0;
 
+// experiments: HP_PIPE_GRID overrides the number of blocks of the TMA-staged kernel
+static int pipeline_grid_override() {
+    static const int v = []() {
+        const char* e = std::getenv("HP_PIPE_GRID");
+        const int g = e ? std::atoi(e) : 0;
+        return g > 0 ? g : 0;
+    }();
+    return v;
+}
 // experiments: HP_PIPE_GRID_DIV overrides the depth requested through the flags (0 = no override)
 static int pipeline_grid_div_override() {
     static const int div = []() {
@@ -253,7 +262,7 @@ static cudaError_t launch_bulk_one(BulkArgs& t, int grid, cudaStream_t stream) {
     }
     // ---- how the blocks hand their sums to the publisher (hp_pipeline_bulk.cuh "self-certifying accumulators") --------
     t.certs = reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(t.p.ws) + kCertOffsetBytes);
-    t.cert = (pipeline_cert_enabled() && grid <= 65535) ? 1 : 0;
+    t.cert = (pipeline_cert_enabled() && grid <= 65535 && t.p.n_maps <= 65535) ? 1 : 0;  // 16-bit count fields
     t.strict = (t.overlap == 0 && pipeline_strict_pdl()) ? 1 : 0;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(static_cast<unsigned>(grid));
@@ -280,7 +289,10 @@ static cudaError_t launch_bulk(BulkArgs& t, int sms, cudaStream_t stream) {
         const int depth = fit < 1 ? 1 : (fit < t.overlap ? static_cast<int>(fit) : t.overlap);
         slots = (slots + depth - 1) / depth;
     }
-    const int grid = t.p.n_maps < slots ? t.p.n_maps : slots;
+    // (a smaller grid that gives every warp the same number of maps - 112 x 12 x 4 rounds for 256 x 21 maps - was measured
+    // SLOWER: with fewer blocks the copy engines no longer saturate HBM, profiles/r2_pipeline_history.md)
+    int grid = t.p.n_maps < slots ? t.p.n_maps : slots;
+    if (const int g = pipeline_grid_override()) grid = g < t.p.n_maps ? g : t.p.n_maps;
     switch (t.p.loss_mask) {
         case 0: return launch_bulk_one<NITC, 0, MULTI, W, KST, BPS>(t, grid, stream);
         case HP_LOSS_MSE: return launch_bulk_one<NITC, 1, MULTI, W, KST, BPS>(t, grid, stream);
@@ -289,6 +301,7 @@ static cudaError_t launch_bulk(BulkArgs& t, int sms, cudaStream_t stream) {
     }
 }
 // experiments: HP_PIPE_SHAPE = 0 / "stream": never the TMA-staged kernel; 3: one block of 12 warps per SM for 64x64 maps
+static bool pipeline_shape_forced() { return std::getenv("HP_PIPE_SHAPE") != nullptr; }
 static int pipeline_shape_choice() {
     static const int choice = []() {
         const char* e = std::getenv("HP_PIPE_SHAPE");
@@ -365,7 +378,11 @@ static int launch_pipeline(const float* pred, const double* joints, const float*
         if (HW == 256) e = launch_bulk<2, false, 4, 8, 3>(t, sms, stream);
         else if (HW == 1024) e = launch_bulk<8, false, 4, 4, 3>(t, sms, stream);
         else if (HW > 4096) e = launch_bulk<32, true, 4, 1, 3>(t, sms, stream);
-        else if (pipeline_shape_choice() == 3) e = launch_bulk<32, false, 12, 1, 1>(t, sms, stream);
+        // 64x64: a train of launches takes 3 blocks of 4 warps per SM (the next launch takes an SM over block by block);
+        // a serialised launch one block of 12 warps per SM - the same 12 stages in flight, a third of the blocks in the
+        // epilogue (21.4 vs 22.3-24 us per launch, profiles/r2_pipeline_history.md).  HP_PIPE_SHAPE=1 / 3 force one.
+        else if (pipeline_shape_choice() == 3 || (pipeline_shape_choice() == 1 && t.overlap == 0 && !pipeline_shape_forced()))
+            e = launch_bulk<32, false, 12, 1, 1>(t, sms, stream);
         else e = launch_bulk<32, false, 4, 1, 3>(t, sms, stream);
         if (e != cudaSuccess) return fail(static_cast<int>(e), "hp_pipeline_fused: %s", cudaGetErrorString(e));
         return launch_status("hp_pipeline_fused");

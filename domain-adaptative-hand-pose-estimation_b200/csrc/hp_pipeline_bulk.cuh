@@ -37,7 +37,7 @@ struct BulkArgs {
     int strict;     // serialised launch: wait for the previous grid BEFORE the first global read (the launch carries the
                     // programmatic attribute only so that block scheduling and the prologue hide the launch gap)
     int cert;       // block sums through self-certifying accumulators (see below); 0: the atomics + fence + ticket epilogue
-    unsigned long long* certs;  // [2K + 6 + 8] 64-bit accumulators in the workspace (zero between launches)
+    unsigned long long* certs;  // [kCertReplicas][kCertStride] 64-bit accumulators in the workspace (zero between launches)
     unsigned long long* trace;  // nullable profiling buffer (hp_debug_pipeline_trace): per block a header
                                 // {globaltimer, clock64} at entry and exit, per warp and map 4 clock64 stamps
 };
@@ -166,11 +166,17 @@ struct BulkShared {
 // half equals the grid size is complete, whatever order the REDs arrived in: no fence, no ticket, no read-back after a
 // flag.  The publisher (the last block index: it owns the fewest maps) polls the 2K + 14 words with one warp - a single
 // L2 round trip per poll -, zeroes them for the next launch and finalises.  One hop + one poll on the critical path.
-// Layout: [0, 2K) PCK hits / valid, [2K, 2K+6) non-finite loss counters, then the two 64-bit fixed-point loss sums as
-// 4 + 4 limbs of 16 bits (a limb summed over <= 65535 blocks fits the 32-bit value field; sum_i limb_i << 16 i
-// reproduces the two's-complement total mod 2^64).
+// Layout (value field = two 16-bit halves where noted; every count is <= n_maps <= 65535, checked on the host):
+// [0, K) {valid[k] : hits[k]}, [K, K+3) the six non-finite loss counters two per word, then the two 64-bit fixed-point
+// loss sums as 4 + 4 limbs of 16 bits (a limb summed over <= 65535 blocks fits the 32-bit value field; sum_i limb_i << 16 i
+// reproduces the two's-complement total mod 2^64).  K = 21: 32 words - one per lane of the polling warp.
+// Same-address REDs serialise in the L2 slice that owns the word, so the accumulators exist in kCertReplicas copies
+// (block b adds to copy b % kCertReplicas) and the publisher sums the copies: a word is complete when the contributor
+// counts of its copies add up to the grid size.
 constexpr size_t kCertOffsetBytes = 2048;   // of the accumulators inside the workspace (after the Workspace header)
-__device__ __forceinline__ int cert_words(int K) { return 2 * K + 6 + 8; }
+constexpr int kCertReplicas = 4;
+constexpr int kCertStride = 80;             // words per copy (>= HP_MAX_K + 11 = 75), 640 B: copies start on new lines
+__device__ __forceinline__ int cert_words(int K) { return K + 3 + 8; }
 __device__ __forceinline__ unsigned long long cert_load(const unsigned long long* p) {
     unsigned long long v;
     asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -512,15 +518,17 @@ __global__ void __launch_bounds__(32 * W, BPS) pipeline_bulk_kernel(const BulkAr
         if (warp == 0) {
             for (int i = lane; i < nw; i += 32) {
                 unsigned int v;
-                if (i < 2 * K) {
-                    v = static_cast<unsigned int>(sh.counts[i]);
-                } else if (i < 2 * K + 6) {
-                    v = static_cast<unsigned int>(sh.acc[2 + i - 2 * K]);
+                if (i < K) {
+                    v = static_cast<unsigned int>(sh.counts[i]) | (static_cast<unsigned int>(sh.counts[K + i]) << 16);
+                } else if (i < K + 3) {
+                    const int c = 2 * (i - K);
+                    v = static_cast<unsigned int>(sh.acc[2 + c]) | (static_cast<unsigned int>(sh.acc[3 + c]) << 16);
                 } else {
-                    const int f = i - 2 * K - 6;  // limb f & 3 of loss sum f >> 2
+                    const int f = i - K - 3;  // limb f & 3 of loss sum f >> 2
                     v = static_cast<unsigned int>((sh.acc[f >> 2] >> (16 * (f & 3))) & 0xffffull);
                 }
-                atomicAdd(&t.certs[i], (1ull << 32) | static_cast<unsigned long long>(v));  // RED.E.ADD.64, no return
+                atomicAdd(&t.certs[(blockIdx.x % kCertReplicas) * kCertStride + i],
+                          (1ull << 32) | static_cast<unsigned long long>(v));  // RED.E.ADD.64, no return
             }
         }
         if (!(publisher && warp == 0)) {  // the other warps deliver the buffered per-map outputs meanwhile
@@ -538,29 +546,45 @@ __global__ void __launch_bounds__(32 * W, BPS) pipeline_bulk_kernel(const BulkAr
             // ONE warp: poll until every accumulator has heard from every block, take the totals, zero the words
             const unsigned int want = gridDim.x;
             const long long t0 = clock64();
-            unsigned long long w0 = 0ull, w1 = 0ull, w2 = 0ull;  // words lane, lane + 32, lane + 64 (2K + 14 <= 142 -> 5 max)
-            unsigned long long w3 = 0ull, w4 = 0ull;
+            unsigned long long w0 = 0ull, w1 = 0ull, w2 = 0ull;  // words lane, lane + 32, lane + 64 (K + 11 <= 75)
             bool done = false;
+            auto word = [&](int i) {  // sum of the copies of word i (all kCertReplicas loads in flight)
+                unsigned long long c[kCertReplicas];
+#pragma unroll
+                for (int r = 0; r < kCertReplicas; ++r) c[r] = cert_load(t.certs + r * kCertStride + i);
+                unsigned long long tot = 0ull;
+#pragma unroll
+                for (int r = 0; r < kCertReplicas; ++r) tot += c[r];
+                return tot;
+            };
             while (!done) {
                 bool ok = true;
-                if (lane < nw) { w0 = cert_load(t.certs + lane); ok &= static_cast<unsigned int>(w0 >> 32) == want; }
-                if (lane + 32 < nw) { w1 = cert_load(t.certs + lane + 32); ok &= static_cast<unsigned int>(w1 >> 32) == want; }
-                if (lane + 64 < nw) { w2 = cert_load(t.certs + lane + 64); ok &= static_cast<unsigned int>(w2 >> 32) == want; }
-                if (lane + 96 < nw) { w3 = cert_load(t.certs + lane + 96); ok &= static_cast<unsigned int>(w3 >> 32) == want; }
-                if (lane + 128 < nw) { w4 = cert_load(t.certs + lane + 128); ok &= static_cast<unsigned int>(w4 >> 32) == want; }
+                if (lane < nw) { w0 = word(lane); ok &= static_cast<unsigned int>(w0 >> 32) == want; }
+                if (lane + 32 < nw) { w1 = word(lane + 32); ok &= static_cast<unsigned int>(w1 >> 32) == want; }
+                if (lane + 64 < nw) { w2 = word(lane + 64); ok &= static_cast<unsigned int>(w2 >> 32) == want; }
                 done = __all_sync(0xffffffffu, ok);
                 if (!done && clock64() - t0 > 4000000000ll) __trap();  // ~2 s: a block of this grid never reported (it faulted)
             }
             // raw partial vector in sh.pub: [0,1] loss sums, [4, 4+2K) counts, [4+2K, 4+2K+6) non-finite counters
+            // (the 16-bit halves of a word were summed over the blocks without carries: each total is <= n_maps <= 65535)
             unsigned long long* limb = reinterpret_cast<unsigned long long*>(sh.pub_acc);  // 8 words of scratch
             auto take = [&](int i, unsigned long long w) {
                 if (i >= nw) return;
                 const unsigned long long v = w & 0xffffffffull;
-                if (i < 2 * K + 6) sh.pub[4 + i] = static_cast<long long>(v);
-                else limb[i - 2 * K - 6] = v;
-                t.certs[i] = 0ull;  // ready for the next launch (ordered before it by the grid's completion)
+                if (i < K) {
+                    sh.pub[4 + i] = static_cast<long long>(v & 0xffffull);
+                    sh.pub[4 + K + i] = static_cast<long long>(v >> 16);
+                } else if (i < K + 3) {
+                    sh.pub[4 + 2 * K + 2 * (i - K)] = static_cast<long long>(v & 0xffffull);
+                    sh.pub[4 + 2 * K + 2 * (i - K) + 1] = static_cast<long long>(v >> 16);
+                } else {
+                    limb[i - K - 3] = v;
+                }
+#pragma unroll
+                for (int r = 0; r < kCertReplicas; ++r)  // ready for the next launch (ordered before it by the grid's completion)
+                    t.certs[r * kCertStride + i] = 0ull;
             };
-            take(lane, w0); take(lane + 32, w1); take(lane + 64, w2); take(lane + 96, w3); take(lane + 128, w4);
+            take(lane, w0); take(lane + 32, w1); take(lane + 64, w2);
             __syncwarp();
             if (lane < 2) {
                 unsigned long long tot = 0ull;

@@ -15,11 +15,13 @@
 //   x5    g = clip(1 - 10 gt);               [fused f given]  g = clip((g + f) - 100 gt);  g / max(g)
 //   x6    g = clip(clip(sum_j gt_j) - 10 gt); [fused f given] g = clip((g + f) - 100 gt);  g / max(g)
 // Roofline: HBM.  Bytes per map: y (H*W*4) + y_adv (oh*ow*4) [+ fused oh*ow*4]; backward adds a write.
+#include <cmath>
 #include <cstdlib>
 
 #include "hp_common.cuh"
 #include "hp_internal.cuh"
 #include "hp_regdisp_staged.cuh"
+#include "hp_regdisp_min.cuh"
 
 namespace hp {
 
@@ -50,15 +52,15 @@ __device__ __forceinline__ float ground_false_value(int variant, bool has_fused,
 
 template <int MODE, int TASK>
 __global__ void __launch_bounds__(kRDThreads) regdisp_kernel(const RDArgs a) {
-    extern __shared__ float s_dyn[];
+    extern __shared__ float s_rdg[];
     __shared__ Centre s_c[HP_MAX_K];
     __shared__ Stats<3> scratch[kRDThreads / 32 + 1];
     __shared__ double s_red[kRDThreads];
 
     const int ohw = a.oh * a.ow;
     const int ntab = 2 * a.tmp * a.tmp + 1;
-    float* s_tab = s_dyn;
-    float* s_all = s_dyn + ((ntab + 3) & ~3);
+    float* s_tab = s_rdg;
+    float* s_all = s_rdg + ((ntab + 3) & ~3);
     const int b = blockIdx.x / a.splits, part = blockIdx.x - b * a.splits;
     const int k_begin = (part * a.K) / a.splits, k_end = ((part + 1) * a.K) / a.splits;
     const int t = threadIdx.x;
@@ -291,6 +293,15 @@ static int check_rd(const char* who, int variant, int mode, int B, int K, int oh
 
 using namespace hp;
 
+// comparison runs: HP_RD_MIN_FUSED=0 keeps the two-launch path (decode, then the staged loss kernel) for 'min'
+static bool rd_min_fused_enabled() {
+    static const bool on = []() {
+        const char* e = std::getenv("HP_RD_MIN_FUSED");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+
 extern "C" HP_API int hp_regdisp_fwd(const float* y, const float* y_adv, const float* fused, const float* weight,
                                      int variant, int mode, float epsilon, int B, int K, int H, int W, int oh, int ow,
                                      int shift, int tmp, const float* tab, float* per_map, float* per_sample,
@@ -301,6 +312,19 @@ extern "C" HP_API int hp_regdisp_fwd(const float* y, const float* y_adv, const f
     HP_REQUIRE(H > 0 && W > 0 && shift >= 0 && shift < 16 && ((H - 1) >> shift) < oh && ((W - 1) >> shift) < ow,
                HP_ERR_SHAPE, "hp_regdisp_fwd: decoded %dx%d >> %d does not fit %dx%d", H, W, shift, oh, ow);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    // 'min' at full resolution needs nothing but the map's own argmax: decode + loss in ONE kernel (hp_regdisp_min.cuh)
+    if (mode == HP_MODE_MIN && H == oh && W == ow && shift == 0 && H * W == 4096 && W % 4 == 0 && aligned16(y) &&
+        aligned16(y_adv) && (2 * tmp + 1) * (2 * tmp + 1) <= 32 * kTileMaxPatch && !generic_forced() && rd_min_fused_enabled()) {
+        RDMinArgs m{};
+        m.y = y; m.y_adv = y_adv; m.weight = weight; m.n_maps = B * K; m.B = B; m.K = K; m.H = H; m.W = W; m.HW = H * W;
+        m.tmp = tmp; m.wdiv = FastDiv(static_cast<uint32_t>(W)); m.sdiv = FastDiv(static_cast<uint32_t>(2 * tmp + 1));
+        m.tab = tab; m.eps = epsilon;
+        m.eps_log_eps = epsilon > 0.0f ? static_cast<float>(static_cast<double>(epsilon) * std::log(static_cast<double>(epsilon))) : 0.0f;
+        m.per_map = per_map; m.per_sample = per_sample; m.mean = mean; m.stats = stats; m.centres = centres;
+        m.ws = static_cast<Workspace*>(workspace);
+        const int rc = launch_regdisp_min(m, s, "hp_regdisp_fwd");
+        if (rc != 1) return rc;
+    }
     if (int rc = launch_decode(y, B * K, H, W, nullptr, nullptr, nullptr, centres, shift, s)) return rc;
     RDArgs a{};
     a.y_adv = y_adv; a.fused = fused; a.weight = weight; a.variant = variant; a.mode = mode; a.eps = epsilon;

@@ -47,6 +47,16 @@ def bench(overlap, n):
 
 ls_t, train = bench(True, args.launches)
 ls_s, serial = bench(False, max(200, args.launches // 4))
+serial40 = []
+for rep in range(15):      # short serialised bursts: is the long-burst figure a clock / power effect?
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(40):
+        ls_s[i % 8]()
+    e1.record()
+    torch.cuda.synchronize()
+    serial40.append(1e3 * e0.elapsed_time(e1) / 40)
 short = []
 for rep in range(9):       # the driver's shape: 20-launch trains
     torch.cuda.synchronize()
@@ -71,6 +81,7 @@ alg = (S * S * 4 + 32) * B * 21
 f = lambda us: alg / (us * 1e-6) / 1e9 / 6450.3
 print(json.dumps({"tag": args.tag, "env": {k: v for k, v in os.environ.items() if k.startswith("HP_")},
                   "train_us": round(statistics.median(train), 3), "train20_us": round(statistics.median(short), 3),
-                  "serial_us": round(statistics.median(serial), 3), "isolated_us": round(statistics.median(iso), 3),
+                  "serial_us": round(statistics.median(serial), 3), "serial_all": [round(v, 2) for v in serial],
+                  "serial40_us": round(statistics.median(serial40), 3), "isolated_us": round(statistics.median(iso), 3),
                   "frac_train": round(f(statistics.median(train)), 3), "frac_serial": round(f(statistics.median(serial)), 3),
                   "frac_isolated": round(f(statistics.median(iso)), 3), "mse": r["mse"], "kl": r["kl"], "avg_acc": r["avg_acc"]}))
