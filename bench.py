@@ -341,6 +341,11 @@ class Harness:
             raise RuntimeError("bench.py needs CUDA: the heatmap path has no CPU fallback (use --impl reference for the CPU arm)")
         torch.cuda.set_device(self.local)
         self.dev = torch.device("cuda", self.local)
+        # one process per GPU: run (and first-touch the pinned staging buffers) on the GPU's own NUMA node
+        self._affinity0 = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
+        self.numa_node = None
+        if not args.no_numa_bind:
+            self.numa_node = importlib.import_module(PKG + ".dist").bind_to_gpu_numa(self.local)
         if self.world > 1:
             if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
                 os.environ["NCCL_DEBUG"] = "WARN"      # the version banner goes to stdout and would precede the JSON line
@@ -397,6 +402,11 @@ class Harness:
 
     def finish(self):
         self.sampler.stop()
+        if self._affinity0 is not None:          # the CPU baseline that may follow uses every host core again
+            try:
+                os.sched_setaffinity(0, self._affinity0)
+            except OSError:
+                pass
         return self.sampler.summary(self.windows)
 
     def shutdown(self):
@@ -563,7 +573,7 @@ def run_pipeline_arm(args, wl):
     e2e_maps = e2e_B * K * n_gpus
     e2e = {"value": e2e_maps * e2e_steps / e2e_dt, "unit": UNIT, "h2d_bytes_per_step": h2d * n_gpus,
            "d2h_bytes_per_step": d2h * n_gpus, "steps": e2e_steps, "ms_per_step": 1e3 * e2e_dt / e2e_steps,
-           "per_gpu_batch": e2e_B,
+           "per_gpu_batch": e2e_B, "host_numa_node": h.numa_node,
            "api": "HeatmapPipeline.run_host -> hp_pipeline_fused_host (pinned host buffers, slabbed H2D overlapped "
                   "with the kernel, D2H of the 25-double result and the decoded coordinates"
                   + ("; the ranks' partial vectors are exchanged, every rank returns the all-rank totals)" if sharded else ")"),
@@ -832,6 +842,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
                     help="N>1: how the ranks' partial vectors are summed each step")
+    ap.add_argument("--no-numa-bind", action="store_true",
+                    help="do not pin the process to the CPUs of the GPU's NUMA node (affects the end-to-end host path only)")
     ap.add_argument("--no-overlap", action="store_true",
                     help="launch every step fully serialised after the previous one (no programmatic dependent launch)")
     args = ap.parse_args()
