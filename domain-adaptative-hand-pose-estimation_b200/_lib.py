@@ -79,6 +79,7 @@ PROTOTYPES = {
     "hp_pipeline_plan_destroy": (_i, [_vp]),
     "hp_debug_pipeline_trace_words": (_sz, []),
     "hp_debug_pipeline_trace": (_i, [_vp, _sz]),
+    "hp_label_fusion": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "hp_argmax_decode_f64": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
     "hp_refine_quarter": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "hp_group_accuracy": (_i, [_vp, _vp, _vp, _i, _vp, _vp]),

@@ -73,6 +73,7 @@ __device__ __forceinline__ void peer_send(const PeerLink& link, const long long*
 // The (source, word) pairs are spread over the lanes and polled eight at a time, so a pass over all sources costs one
 // or two memory round trips however many ranks there are (polling source after source cost a round trip per rank:
 // 5.6 us at 8 GPUs).  Returns non-zero in every lane on a timeout (missing contributions count as zero).
+template <int kBatch = 8>
 __device__ __forceinline__ int peer_recv_sum(const PeerLink& link, long long* out, long long* scratch, int n,
                                              unsigned long long seq, int lane) {
     const int world = link.world;
@@ -87,10 +88,10 @@ __device__ __forceinline__ int peer_recv_sum(const PeerLink& link, long long* ou
     int timeout = 0;
     const long long t0 = clock64();
     while (__any_sync(0xffffffffu, pending != 0)) {
-        for (int kb = 0; kb < kcount; kb += 8) {
-            ulonglong2 v[8];
+        for (int kb = 0; kb < kcount; kb += kBatch) {
+            ulonglong2 v[kBatch];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < kBatch; ++j) {
                 const int k = kb + j, p = lane + 32 * k;
                 if ((pending >> k) & 1u) {
                     const int src = p / n, w = p - src * n;
@@ -98,7 +99,7 @@ __device__ __forceinline__ int peer_recv_sum(const PeerLink& link, long long* ou
                 }
             }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < kBatch; ++j) {
                 const int k = kb + j, p = lane + 32 * k;
                 if (((pending >> k) & 1u) && (v[j].x & tag_mask) == tag && (v[j].y & tag_mask) == tag) {
                     scratch[p] = static_cast<long long>((v[j].y << 32) | (v[j].x & 0xffffffffull));

@@ -190,7 +190,10 @@ __device__ __forceinline__ unsigned long long cert_load(const unsigned long long
 // (bounded) for the other ranks' vectors of the same step and sums them in rank order - compute and collective
 // in ONE kernel, no NCCL launch and no second kernel on the step path.  All entries are integers, so every rank
 // ends with bit-identical totals.
-__device__ __forceinline__ void bulk_publish_warp(const BulkArgs& t, BulkShared& sh, long long* scratch, int lane) {
+// `split_done` != ~0: the pending step is being completed by another warp of this block (peer_pending_warp); this warp
+// meets it at named barrier 1 (64 threads) and only sends (peer_send_warp) with the step counter it was given.
+__device__ __forceinline__ void bulk_publish_warp(const BulkArgs& t, BulkShared& sh, long long* scratch, int lane,
+                                                  unsigned long long split_done = ~0ull) {
     const PipeArgs& a = t.p;
     const PeerLink& link = t.link;
     const int K = a.K, n = 4 + 2 * K + 6;
@@ -223,7 +226,12 @@ __device__ __forceinline__ void bulk_publish_warp(const BulkArgs& t, BulkShared&
     __syncwarp();
     if (exchange) {
         // sh.pub = this rank's vector: send it, and collect / finalise this step (synchronous) or the previous one (deferred)
-        peer_step_warp(link, a.ws, sh.pub, scratch, sh.pub_acc, K, a.partial, a.result, t.defer, lane);
+        if (split_done != ~0ull) {
+            named_barrier<1, 64>();  // the other warp has read (and completed) the pending record
+            peer_send_warp(link, a.ws, sh.pub, scratch, sh.pub_acc, K, a.partial, a.result, t.defer, split_done, lane);
+        } else {
+            peer_step_warp(link, a.ws, sh.pub, scratch, sh.pub_acc, K, a.partial, a.result, t.defer, lane);
+        }
     } else if (a.result) {
         warp_result_from_partial(sh.pub, K, a.result, sh.pub_acc, lane);
     }
@@ -531,6 +539,7 @@ __global__ void __launch_bounds__(32 * W, BPS) pipeline_bulk_kernel(const BulkAr
                           (1ull << 32) | static_cast<unsigned long long>(v));  // RED.E.ADD.64, no return
             }
         }
+        const bool exchange = t.link.world > 1;
         if (!(publisher && warp == 0)) {  // the other warps deliver the buffered per-map outputs meanwhile
             const int n_buf = n_local < kBulkOutCap ? n_local : kBulkOutCap;
             const int first = publisher ? static_cast<int>(threadIdx.x) - 32 : static_cast<int>(threadIdx.x);
@@ -542,8 +551,17 @@ __global__ void __launch_bounds__(32 * W, BPS) pipeline_bulk_kernel(const BulkAr
                 if (a.maxvals) a.maxvals[map] = o.z;
                 if (a.weight_out) a.weight_out[map] = o.w;
             }
+            if (publisher && warp == 1 && exchange) {
+                // the step that is still outstanding from the previous launch: collected and finalised by THIS warp while
+                // warp 0 waits for the blocks' sums (scratch: the idle stages behind warp 0's area)
+                long long* scratch1 = reinterpret_cast<long long*>(s_dyn) + kPeerScratchWords + HP_MAX_K;
+                peer_pending_warp(t.link, a.ws, scratch1, reinterpret_cast<double*>(scratch1 + kPeerScratchWords), lane);
+                named_barrier<1, 64>();
+            }
         } else {
             // ONE warp: poll until every accumulator has heard from every block, take the totals, zero the words
+            unsigned long long done = ~0ull;
+            if (exchange) done = peer_load(peer_counter(t.link.mailbox[t.link.rank], t.link.world));  // final: the previous grid is complete
             const unsigned int want = gridDim.x;
             const long long t0 = clock64();
             unsigned long long w0 = 0ull, w1 = 0ull, w2 = 0ull;  // words lane, lane + 32, lane + 64 (K + 11 <= 75)
@@ -593,7 +611,7 @@ __global__ void __launch_bounds__(32 * W, BPS) pipeline_bulk_kernel(const BulkAr
             }
             __syncwarp();
             // (the block's stages are idle by now and serve as the exchange's scratch space)
-            bulk_publish_warp(t, sh, reinterpret_cast<long long*>(s_dyn), lane);
+            bulk_publish_warp(t, sh, reinterpret_cast<long long*>(s_dyn), lane, done);
         }
     } else if (warp == 0) {
         for (int i = lane; i < 8 + 2 * a.K; i += 32) {

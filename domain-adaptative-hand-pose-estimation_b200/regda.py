@@ -293,17 +293,16 @@ class RegressionDisparityx4(_RDBase):
         return self._run(y, y_adv, None, weight, mode)
 
 
-def _clip01(t):
-    return t.clip(max=1., min=0.)
-
-
-def _per_sample_max_normalise(lp):
-    return lp / lp.reshape(lp.shape[0], -1).max(dim=1).values.view(-1, 1, 1)
-
-
 class _RDLabelFusion(nn.Module):
     """RegressionDisparity2/3/5/6/7/8 (uda/model/regda_4.py:145-645): ``gf = clip(label_p - 10 gt)`` where the per-sample
-    map ``label_p`` fuses the summed pseudo-labels of ``y`` and of one or two extra predictions."""
+    map ``label_p`` fuses the summed pseudo-labels of ``y`` and of one or two extra predictions.
+
+    Three decode launches (one per prediction) + ONE kernel (``hp_label_fusion``, csrc/hp_variants.cu: a block per sample
+    rebuilds the per-sample sums from the 3K centres, applies the variant's rule and writes gt / gf), then the criterion on
+    the materialised target - no elementwise ATen chain, no [B,K,H,W] temporaries besides the two maps the reference itself
+    exposes as ``ground_truth`` / ``ground_false``."""
+
+    _rule = 0
 
     def __init__(self, pseudo_label_generator, criterion: nn.Module):
         super().__init__()
@@ -317,17 +316,30 @@ class _RDLabelFusion(nn.Module):
     def updata(self, label_x):          # (sic) regda_4.py:197
         self.label_x = label_x
 
-    def _label_p(self, gt, gt1, gt2):
-        raise NotImplementedError
-
     def _run(self, y, y_adv, label_1, label_2, weight, mode):
         assert mode in ["min", "max"]
+        from .keypoint_detection import decode
         plg = self.pseudo_label_generator
-        gt, _ = plg(y.detach())
-        gt1, _ = plg(label_1.detach())
-        gt2 = plg(label_2.detach())[0] if label_2 is not None else None
-        lp = self._label_p(gt, gt1, gt2)
-        gf = _clip01(lp.unsqueeze(1) - gt * 10)
+        if not isinstance(plg, _PLGBase):
+            raise TypeError("pseudo_label_generator must be one of this package's PseudoLabelGenerator classes")
+        yd, (B, K, H, W), (oh, ow, shift, tmp, _) = plg._check_input(y)
+        dev = yd.device
+
+        def centres(t):
+            td = plg._check_input(t)[0]
+            if tuple(td.shape) != (B, K, H, W):
+                raise ValueError(f"label is {tuple(td.shape)}, expected {(B, K, H, W)}")
+            preds, _ = decode(td)                                   # masked (x, y) like get_max_preds (regda_4.py:79-81)
+            return (preds.reshape(-1, 2).to(torch.int32) >> shift).contiguous()
+
+        c0, c1 = centres(y), centres(label_1)
+        c2 = centres(label_2) if label_2 is not None else None
+        gt = torch.empty((B, K, oh, ow), dtype=torch.float32, device=dev)
+        gf = torch.empty_like(gt)
+        with _lib.on_device(dev):
+            tab = _lib.gaussian_table(plg.sigma, tmp, dev)
+            _lib.call("hp_label_fusion", _lib.ptr(c0), _lib.ptr(c1), _lib.ptr(c2), self._rule, B, K, oh, ow, tmp,
+                      _lib.ptr(tab), _lib.ptr(gt), _lib.ptr(gf), None, _lib.stream_ptr(dev))
         self.ground_truth, self.ground_false = gt, gf
         return self.criterion(y_adv, gt if mode == "min" else gf, weight)
 
@@ -342,36 +354,25 @@ class _RDLabelFusion1(_RDLabelFusion):
         return self._run(y, y_adv, label_1, None, weight, mode)
 
 
-class RegressionDisparity2(_RDLabelFusion2):     # regda_4.py:145-220
-    def _label_p(self, gt, gt1, gt2):
-        return _per_sample_max_normalise(gt1.sum(1) + gt.sum(1) + gt2.sum(1))
+class RegressionDisparity2(_RDLabelFusion2):     # regda_4.py:145-220: lp = (sum gt1 + sum gt + sum gt2) / max
+    _rule = 2
 
 
-class RegressionDisparity3(_RDLabelFusion2):     # regda_4.py:222-297
-    def _label_p(self, gt, gt1, gt2):
-        return _per_sample_max_normalise(_clip01(gt.sum(1)) + _clip01(gt1.sum(1)) + _clip01(gt2.sum(1)))
+class RegressionDisparity3(_RDLabelFusion2):     # regda_4.py:222-297: lp = (c(sum gt) + c(sum gt1) + c(sum gt2)) / max
+    _rule = 3
 
 
-class RegressionDisparity5(_RDLabelFusion2):     # regda_4.py:358-427
-    def _label_p(self, gt, gt1, gt2):
-        p1, p2, p3 = _clip01(gt.sum(1)), _clip01(gt1.sum(1)), _clip01(gt2.sum(1))
-        return _clip01(p1 + _clip01(p2 - p1) + _clip01(p3 - p1))
+class RegressionDisparity5(_RDLabelFusion2):     # regda_4.py:358-427: lp = c(p1 + c(p2 - p1) + c(p3 - p1))
+    _rule = 5
 
 
-class RegressionDisparity6(_RDLabelFusion1):     # regda_4.py:429-495
-    def _label_p(self, gt, gt1, gt2):
-        p1, p2 = _clip01(gt.sum(1)), _clip01(gt1.sum(1))
-        return _clip01(p1 + _clip01(p2 - p1))
+class RegressionDisparity6(_RDLabelFusion1):     # regda_4.py:429-495: lp = c(p1 + c(p2 - p1))
+    _rule = 6
 
 
-class RegressionDisparity7(_RDLabelFusion1):     # regda_4.py:497-572
-    def _label_p(self, gt, gt1, gt2):
-        return _per_sample_max_normalise(_clip01(gt1.sum(1)) + _clip01(gt.sum(1)))
+class RegressionDisparity7(_RDLabelFusion1):     # regda_4.py:497-572: lp = (c(sum gt1) + c(sum gt)) / max
+    _rule = 7
 
 
-class RegressionDisparity8(_RDLabelFusion2):     # regda_4.py:574-645
-    def _label_p(self, gt, gt1, gt2):
-        p1 = _clip01(gt.sum(1))
-        x1 = _clip01(_clip01(gt1 - gt).sum(1))
-        x2 = _clip01(_clip01(gt2 - gt).sum(1))
-        return _clip01(p1 + x1 + x2)
+class RegressionDisparity8(_RDLabelFusion2):     # regda_4.py:574-645: lp = c(p1 + c(sum c(gt1 - gt)) + c(sum c(gt2 - gt)))
+    _rule = 8

@@ -222,6 +222,20 @@ int hp_pipeline_fused_ex(const float* pred, const double* joints, const float* v
  * uint64 words.  buf = NULL switches it off.  Read by profiles/trace_pipeline.py. */
 size_t hp_debug_pipeline_trace_words(void);
 int hp_debug_pipeline_trace(void* buf, size_t words);
+/* ---- row f3: the label-fusing disparity variants RegressionDisparity2/3/5/6/7/8 (uda/model/regda_4.py:145-645) ----
+ * centres_* int32 [B*K,2]: decoded pseudo-label centres of y, label_1, label_2 (hp_argmax_decode / hp_pseudo_label);
+ * writes gt [B,K,H,W] (Gaussian at centres_y), gf = clip(label_p - 10 gt) and/or the per-sample label_p [B,H,W]
+ * (any of the three may be NULL).  One block per sample, H*W <= 4096. */
+#define HP_LF_RD2 2
+#define HP_LF_RD3 3
+#define HP_LF_RD5 5
+#define HP_LF_RD6 6
+#define HP_LF_RD7 7
+#define HP_LF_RD8 8
+int hp_label_fusion(const int32_t* centres_y, const int32_t* centres_1, const int32_t* centres_2 /*nullable*/,
+                    int rule, int B, int K, int H, int W, int tmp, const float* tab,
+                    float* gt, float* gf, float* label_p, hp_stream_t stream);
+
 /* ---- small boundary operators around the decode (csrc/hp_extras.cu) ----
  * hp_argmax_decode_f64: get_max_preds for float64 heatmaps (utils/keypoint_detection.py:7-35 takes any ndarray dtype);
  *   preds float32 [n_maps,2], maxvals float64 [n_maps] (the reference returns maxvals in the input dtype).
