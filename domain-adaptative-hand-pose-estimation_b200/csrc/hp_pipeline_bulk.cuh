@@ -560,8 +560,8 @@ __global__ void __launch_bounds__(32 * W, BPS) pipeline_bulk_kernel(const BulkAr
             }
         } else {
             // ONE warp: poll until every accumulator has heard from every block, take the totals, zero the words
-            unsigned long long done = ~0ull;
-            if (exchange) done = peer_load(peer_counter(t.link.mailbox[t.link.rank], t.link.world));  // final: the previous grid is complete
+            unsigned long long steps_done = ~0ull;
+            if (exchange) steps_done = peer_load(peer_counter(t.link.mailbox[t.link.rank], t.link.world));  // final: the previous grid is complete
             const unsigned int want = gridDim.x;
             const long long t0 = clock64();
             unsigned long long w0 = 0ull, w1 = 0ull, w2 = 0ull;  // words lane, lane + 32, lane + 64 (K + 11 <= 75)
@@ -611,7 +611,7 @@ __global__ void __launch_bounds__(32 * W, BPS) pipeline_bulk_kernel(const BulkAr
             }
             __syncwarp();
             // (the block's stages are idle by now and serve as the exchange's scratch space)
-            bulk_publish_warp(t, sh, reinterpret_cast<long long*>(s_dyn), lane, done);
+            bulk_publish_warp(t, sh, reinterpret_cast<long long*>(s_dyn), lane, steps_done);
         }
     } else if (warp == 0) {
         for (int i = lane; i < 8 + 2 * a.K; i += 32) {
