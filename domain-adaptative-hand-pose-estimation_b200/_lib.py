@@ -79,6 +79,10 @@ PROTOTYPES = {
     "hp_pipeline_plan_destroy": (_i, [_vp]),
     "hp_debug_pipeline_trace_words": (_sz, []),
     "hp_debug_pipeline_trace": (_i, [_vp, _sz]),
+    "hp_mse0_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "hp_mse0_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "hp_kl5_fwd": (_i, [_vp, _vp, _f, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "hp_kl5_bwd": (_i, [_vp, _vp, _f, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "hp_label_fusion": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "hp_argmax_decode_f64": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
     "hp_refine_quarter": (_i, [_vp, _i, _i, _i, _vp, _vp]),

@@ -222,6 +222,22 @@ int hp_pipeline_fused_ex(const float* pred, const double* joints, const float* v
  * uint64 words.  buf = NULL switches it off.  Read by profiles/trace_pipeline.py. */
 size_t hp_debug_pipeline_trace_words(void);
 int hp_debug_pipeline_trace(void* buf, size_t words);
+/* ---- row f3: the loss weightings JointsMSELoss0 / JointsKLLoss5 (uda/model/loss.py:68-112, :160-216) ----
+ * hp_mse0_*: both maps shifted by 1e-7 and normalised to sum 1 per map, then 0.5*w*(p-t)^2; per_map [B*K] = mean over HW
+ *   ('none'), *mean (nullable) = mean over all elements.  grad_kind HP_GRAD_SCALAR ('mean') / HP_GRAD_PER_MAP ('none').
+ * hp_kl5_*: per-map scale s = w3 / max(w3), w3 = sum (out/max(out)) (tgt/max(tgt)) (global maxima, no gradient), then the KL
+ *   loss of s*out against s*tgt without target weights; per_sample [B] = mean over K ('none'), *mean = mean over B*K.
+ *   scratch: float [4*B*K] (the per-map scale lands at scratch + 3*B*K and is what hp_kl5_bwd takes); stats [B*K,2]. */
+int hp_mse0_fwd(const float* out, const float* tgt, const float* weight /*nullable*/, int B, int K, int HW,
+                float* per_map, float* mean /*nullable*/, void* workspace, hp_stream_t stream);
+int hp_mse0_bwd(const float* out, const float* tgt, const float* weight /*nullable*/, const float* grad_out, int grad_kind,
+                int B, int K, int HW, float* grad_in, hp_stream_t stream);
+int hp_kl5_fwd(const float* out, const float* tgt, float epsilon, int B, int K, int HW, float* scratch,
+               float* per_map, float* per_sample /*nullable*/, float* mean /*nullable*/, float* stats, void* workspace,
+               hp_stream_t stream);
+int hp_kl5_bwd(const float* out, const float* tgt, float epsilon, const float* scale, const float* stats,
+               const float* grad_out, int grad_kind, int B, int K, int HW, float* grad_in, hp_stream_t stream);
+
 /* ---- row f3: the label-fusing disparity variants RegressionDisparity2/3/5/6/7/8 (uda/model/regda_4.py:145-645) ----
  * centres_* int32 [B*K,2]: decoded pseudo-label centres of y, label_1, label_2 (hp_argmax_decode / hp_pseudo_label);
  * writes gt [B,K,H,W] (Gaussian at centres_y), gf = clip(label_p - 10 gt) and/or the per-sample label_p [B,H,W]
