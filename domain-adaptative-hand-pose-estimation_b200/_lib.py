@@ -79,6 +79,8 @@ PROTOTYPES = {
     "hp_pipeline_plan_destroy": (_i, [_vp]),
     "hp_debug_pipeline_trace_words": (_sz, []),
     "hp_debug_pipeline_trace": (_i, [_vp, _sz]),
+    "hp_debug_regdisp_trace_words": (_sz, []),
+    "hp_debug_regdisp_trace": (_i, [_vp, _sz]),
     "hp_mse0_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "hp_mse0_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "hp_kl5_fwd": (_i, [_vp, _vp, _f, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -22,6 +22,7 @@
 #include "hp_internal.cuh"
 #include "hp_regdisp_staged.cuh"
 #include "hp_regdisp_min.cuh"
+#include "hp_regdisp_dense.cuh"
 
 namespace hp {
 
@@ -333,10 +334,25 @@ extern "C" HP_API int hp_regdisp_fwd(const float* y, const float* y_adv, const f
     a.ws = static_cast<Workspace*>(workspace);
     const bool vec = (ow % 4 == 0) && aligned16(y_adv) && (!fused || aligned16(fused));
     if (vec && !generic_forced()) {
-        const int rc = launch_regdisp_staged<RD_FWD>(a, s, "hp_regdisp_fwd");
+        int rc = launch_regdisp_dense(a, s, "hp_regdisp_fwd");  // x6 / rd4 'max' on 4096-pixel maps
+        if (rc != 1) return rc;
+        rc = launch_regdisp_staged<RD_FWD>(a, s, "hp_regdisp_fwd");
         if (rc != 1) return rc;
     }
     return launch_regdisp<RD_FWD>(a, vec, s, "hp_regdisp_fwd");
+}
+
+/* profiling aid: the blocks of the dense 'max' disparity kernel stamp their timeline (globaltimer ns) into `buf`
+ * (device memory, hp_debug_regdisp_trace_words() uint64 words).  NULL switches it off.  Read by profiles/trace_regdisp.py. */
+extern "C" HP_API size_t hp_debug_regdisp_trace_words(void) {
+    int sms = hp_device_sm_count();
+    if (sms <= 0) sms = 148;
+    return static_cast<size_t>(sms) * kRDDTraceBlockWords;
+}
+extern "C" HP_API int hp_debug_regdisp_trace(void* buf, size_t words) {
+    g_rdd_trace = static_cast<unsigned long long*>(buf);
+    g_rdd_trace_words = buf ? words : 0;
+    return HP_OK;
 }
 
 extern "C" HP_API int hp_regdisp_bwd(const float* y_adv, const float* fused, const float* weight, int variant, int mode,

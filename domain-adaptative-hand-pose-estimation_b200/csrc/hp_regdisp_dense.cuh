@@ -1,0 +1,688 @@
+// hp_regdisp_dense.cuh - RegressionDisparityx6 / RegressionDisparity4 forward with mode='max' on 4096-pixel maps
+// (configs[2] of BASELINE.json: 512 x 21 x 64 x 64; regda_7.py:3609-3632, regda_4.py RD4), with or without the fused
+// map y_adv2 (train1.py:419-421).  The ground-false label of joint k,
+//     lp   = clip(sum_j G_j)                      per SAMPLE (G_j = Gaussian at joint j's decoded centre)
+//     g_k  = clip(lp - 10 G_k)                    [+ fused map f_k:  g_k = clip((g_k + f_k) - 100 G_k)]
+//     gf_k = g_k / max(g_k),  u = gf_k + eps,     KL(y_adv_k, u)  (loss.py:145-158)
+// depends on the pixel everywhere ("dense"), which made the register-slice kernel (hp_regdisp_staged.cuh) issue-bound:
+// 5,000 warp-instructions per map, 0.47 / 0.60 of the HBM roofline.  This kernel splits the label into what is shared
+// and what is not:
+//   * outside joint k's own (2 tmp + 1)^2 patch G_k = 0, so g_k = lp (no fused map) or clip(lp + f_k): `lp` is built
+//     ONCE per sample, in shared memory, by a builder warp running a sample ahead of the consumers (scatter of the K
+//     patches, joints ascending -> deterministic; two slots, full/empty mbarriers);
+//   * the own patch (<= 192 pixels) is a per-lane correction: the exact recipe is evaluated there from `lp`, the fused map
+//     and the tabulated Gaussian, and the generic contribution of those pixels is taken back out;
+//   * without a fused map the max of g_k (x6; rd4 does not normalise at all) is 1 whenever some other joint's centre lies
+//     outside k's patch (lp = 1 there, G_k = 0); then sum(u) and sum(u lg u) are PER-SAMPLE constants plus the patch
+//     correction, and the only per-pixel work of a map is the softmax sum and sum(lp * p).  Maps where every other centre
+//     falls inside the own patch take an exact per-pixel path (rare; tested);
+//   * with a fused map a first pass writes g = clip(lp + f) over f in the slot and finds the max, the second pass
+//     accumulates the sums of u = g / M + eps.
+// Shape: one block per SM; NG groups of G consumer warps, a group owns NS slots of one map (16 KB) each, filled by the copy
+// engine (cp.async.bulk -> mbarrier complete_tx) - the group's load sequence (y_adv of its maps, or fused map / y_adv
+// alternating) goes round the slots, so the next unit is in flight while the current map is computed.  The G warps of
+// a group split the map's 32 iterations (and the patch slots) and meet at named barriers: one per map without a fused
+// map (each warp runs the softmax against its own maximum, the leader re-bases), three with one (patch pixels marked,
+// maxima exchanged, sums exchanged).  The leader role rotates over the group's warps.  No fused map: 6 groups x 2 warps x
+// 2 slots; fused: 4 groups x 4 warps x 3 slots; + 2 x 16 KB of `lp`; contiguous map ranges per block (balanced to one
+// map; ranges cross samples).  History (profiles/r2_regdisp_dense_history.md): one warp per map ran at 0.3 instructions
+// per cycle and warp - 2.8 us (no fused map) / 3.7 us (fused) per map whatever the copies did.
+// Algorithmic bytes per map: 16,384 (y_adv) [+ 16,384 fused] here + 16,384 (y) in the decode launch that precedes it.
+// Roofline: HBM.
+#pragma once
+#include "hp_pipeline_parts.cuh"
+#include "hp_regdisp_staged.cuh"
+
+namespace hp {
+
+constexpr int kRDDMaxK = 32;     // joints per sample (lane j of the builder holds joint j)
+constexpr int kRDDMaxTab = 80;   // 2 tmp^2 + 1 <= 73 table entries (tmp <= 6)
+constexpr int kRDDPixels = 4096;
+// profiling: per block 8 header words {entry, exit, first lp built, n_samples, q_total, ...} (globaltimer ns), then per
+// consumer warp (<= 16) and map (first 16) eight stamps {wait begins, data landed, lp seen, patch done, passes done,
+// sums reduced + next units requested, map closed, -}, then per sample
+// (first 8) two builder stamps {build begins, lp published}
+constexpr int kRDDTraceMaps = 16;
+constexpr int kRDDTraceBlockWords = 8 + 16 * kRDDTraceMaps * 8 + 8 * 2;
+__device__ __forceinline__ unsigned long long rdd_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+template <bool FUSED, int GW>
+struct RDDShape {
+    static constexpr int NG = FUSED ? 4 : 6;                 // groups = maps being computed at once
+    static constexpr int G = GW;                             // warps per group
+    static constexpr int W = NG * G;                         // consumer warps
+    static_assert(NG * GW <= 16, "RDDShared::xch / xmx hold 16 consumer warps");
+    static constexpr int NS = FUSED ? 3 : 2;                 // slots per group
+    static constexpr int UPM = FUSED ? 2 : 1;                // units per map
+    static constexpr int IT = 32 / G;                        // iterations per warp and pass
+    static constexpr int NSL = (kTileMaxPatch + G - 1) / G;  // patch slots per lane of a consumer warp
+    static constexpr size_t kSmem = static_cast<size_t>(NG) * NS * kRDDPixels * 4 + 2 * kRDDPixels * 4;
+};
+
+struct RDDShared {
+    uint64_t full[12];        // slot s of group g landed: full[g * NS + s]
+    uint64_t lp_full[2];      // lp slot built (count 1: the builder)
+    uint64_t lp_empty[2];     // lp slot released (count W: every consumer warp, once per sample)
+    Centre c[2][kRDDMaxK];
+    float w[2][kRDDMaxK];
+    float cu[2], culg[2];     // per sample: sum (lp + eps), sum (lp + eps) lg2 (lp + eps)
+    float tab[kRDDMaxTab];
+    float xch[2][16][8];      // [map parity][consumer warp]: the warp's partial sums of a map
+    float xmx[2][16];         // fused: max g of the warp's part
+    unsigned long long acc[kFxAccWords];
+};
+
+// per-warp exact accumulation of the per-map losses (lane 0's registers; fx_acc_add's arithmetic, one set of shared
+// atomics per warp at the end instead of per map)
+struct FxReg {
+    long long hi, lo;
+    int n_nan, n_pinf, n_ninf;
+};
+__device__ __forceinline__ void fx_reg_add(FxReg& r, float v) {
+    if (fabsf(v) < kFxAccLimit) {
+        const double d = static_cast<double>(v) * 1099511627776.0;  // exact
+        const long long hi = __double2ll_rn(d);
+        r.hi += hi;
+        r.lo += __double2ll_rn((d - static_cast<double>(hi)) * 8388608.0);
+    } else if (v != v) {
+        r.n_nan += 1;
+    } else if (v > 0.0f) {
+        r.n_pinf += 1;
+    } else {
+        r.n_ninf += 1;
+    }
+}
+__device__ __forceinline__ void fx_reg_flush(const FxReg& r, unsigned long long* acc) {
+    if (r.hi != 0) atomicAdd(&acc[0], static_cast<unsigned long long>(r.hi));
+    if (r.lo != 0) atomicAdd(&acc[4], static_cast<unsigned long long>(r.lo));
+    if (r.n_nan != 0) atomicAdd(&acc[1], static_cast<unsigned long long>(r.n_nan));
+    if (r.n_pinf != 0) atomicAdd(&acc[2], static_cast<unsigned long long>(r.n_pinf));
+    if (r.n_ninf != 0) atomicAdd(&acc[3], static_cast<unsigned long long>(r.n_ninf));
+}
+__device__ __forceinline__ void group_barrier(int id, int n_threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n_threads) : "memory");
+}
+
+__device__ __forceinline__ float ulg2(float u) { return u * lg2_approx(fmaxf(u, 1.17549435e-38f)); }  // xlogy / ln 2
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// per-lane patch slots, lane-constant for the whole kernel: offset from the centre (dx = 1 << 20: unused) and value
+// slot j of a warp that takes every `stride`-th slot row starting at `first` is patch pixel (first + j * stride) * 32 + lane
+template <int N>
+struct RDDSlots {
+    int dx[N], dy[N];
+    float t[N];
+};
+template <int N>
+__device__ __forceinline__ void rdd_slots_init(RDDSlots<N>& s, const float* __restrict__ tab, int tmp, int lane, int first, int stride) {
+    const int side = 2 * tmp + 1, n_patch = side * side;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        const int i = (first + k * stride) * 32 + lane;
+        s.dx[k] = 1 << 20;
+        s.dy[k] = 0;
+        s.t[k] = 0.0f;
+        if (i < n_patch) {
+            const int ry = i / side, rx = i - ry * side;
+            s.dx[k] = rx - tmp;
+            s.dy[k] = ry - tmp;
+            s.t[k] = tab[s.dx[k] * s.dx[k] + s.dy[k] * s.dy[k]];
+        }
+    }
+}
+
+// Exact per-pixel evaluation of a map without a fused map (every other centre lies inside the own patch, so the
+// maximum of g is not known in closed form).  Returns the sums of u = g / M + eps (sum u, sum u (p - ref) log2 e with
+// mb = -ref log2 e, sum u lg2 u) and M; two passes over lp.
+__device__ __noinline__ void rdd_exact_map(const float4* __restrict__ P, const float4* __restrict__ LP, const float* s_tab,
+                                           int tmp, Centre ck, FastDiv wdiv, float eps, float mb, int lane, float& Su,
+                                           float& Sua, float& Sulg, float& M_out) {
+    float mg = -INFINITY;
+    for (int it = 0; it < 32; ++it) {
+        const int i4 = it * 32 + lane;
+        uint32_t yy, xx;
+        wdiv.divmod(static_cast<uint32_t>(4 * i4), yy, xx);
+        const float4 gt = patch_at4(s_tab, tmp, ck, static_cast<int>(xx), static_cast<int>(yy));
+        const float4 l = LP[i4];
+        mg = fmaxf(mg, fmaxf(fmaxf(clip01(__fsub_rn(l.x, __fmul_rn(gt.x, 10.0f))), clip01(__fsub_rn(l.y, __fmul_rn(gt.y, 10.0f)))),
+                             fmaxf(clip01(__fsub_rn(l.z, __fmul_rn(gt.z, 10.0f))), clip01(__fsub_rn(l.w, __fmul_rn(gt.w, 10.0f))))));
+    }
+    const float M = warp_max_f32(mg);
+    float su = 0.f, sup = 0.f, sulg = 0.f;
+    for (int it = 0; it < 32; ++it) {
+        const int i4 = it * 32 + lane;
+        uint32_t yy, xx;
+        wdiv.divmod(static_cast<uint32_t>(4 * i4), yy, xx);
+        const float4 gt = patch_at4(s_tab, tmp, ck, static_cast<int>(xx), static_cast<int>(yy));
+        const float4 l = LP[i4], p = P[i4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const float g = clip01(__fsub_rn(f4_get(l, c), __fmul_rn(f4_get(gt, c), 10.0f)));
+            const float u = rds_norm(g, M, M != 1.0f) + eps;
+            su += u;
+            sup = fmaf(u, fmaf(f4_get(p, c), kLog2e, mb), sup);  // u * (p - ref) * log2 e
+            sulg += ulg2(u);
+        }
+    }
+    const float r = warp_sum3_scattered(su, sup, sulg, lane);
+    Su = __shfl_sync(0xffffffffu, r, 0);
+    Sua = __shfl_sync(0xffffffffu, r, 8);
+    Sulg = __shfl_sync(0xffffffffu, r, 16);
+    M_out = M;
+}
+
+// Softmax sum of iterations [it0, it1) of a map in shared memory against their TRUE maximum (two passes).  The passes
+// of the kernel run against a sampled reference value instead (the maximum of the part's first iteration: the sum is
+// the same number up to rounding whatever the reference, as long as nothing overflows) and come here when their sum is
+// not a positive finite number.
+__device__ __noinline__ void rdd_softmax_exact(const float4* __restrict__ P4, int it0, int it1, int lane, float& m_out, float& s_out) {
+    float run = -INFINITY;
+    for (int it = it0; it < it1; ++it) run = fmaxf(run, max4(P4[it * 32 + lane]));
+    const float m = warp_max_f32(run);
+    const float mb = -((m == -INFINITY) ? 0.0f : m) * kLog2e;
+    float acc = 0.0f;
+    for (int it = it0; it < it1; ++it) {
+        const float4 v = P4[it * 32 + lane];
+        acc += ex2_approx(fmaf(v.x, kLog2e, mb)) + ex2_approx(fmaf(v.y, kLog2e, mb));
+        acc += ex2_approx(fmaf(v.z, kLog2e, mb)) + ex2_approx(fmaf(v.w, kLog2e, mb));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    m_out = m;
+    s_out = acc;
+}
+
+template <bool FUSED, int GW>
+__global__ void __launch_bounds__(32 * (RDDShape<FUSED, GW>::W + 1), 1) regdisp_dense_kernel(const RDArgs a) {
+    extern __shared__ __align__(128) unsigned char s_rdd[];
+    __shared__ RDDShared sh;
+    using S = RDDShape<FUSED, GW>;
+    constexpr int W = S::W, G = S::G, NG = S::NG, NS = S::NS, UPM = S::UPM, IT = S::IT, NSL = S::NSL;
+    constexpr int kMapBytes = kRDDPixels * 4;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int K = a.K, tmp = a.tmp, ow = a.ow, oh = a.oh;
+    const float eps = a.eps;
+    float* lp_base = reinterpret_cast<float*>(s_rdd + static_cast<size_t>(NG) * NS * kMapBytes);
+
+    // this block's maps: [m0, m1), its samples: [sample0, sample0 + n_samples)
+    const int n_maps = a.B * K;
+    const int m0 = static_cast<int>((static_cast<long long>(blockIdx.x) * n_maps) / gridDim.x);
+    const int m1 = static_cast<int>((static_cast<long long>(blockIdx.x + 1) * n_maps) / gridDim.x);
+    const int q_total = m1 - m0;
+    const int sample0 = m0 / K;
+    const int n_samples = (q_total > 0) ? (m1 - 1) / K - sample0 + 1 : 0;
+    unsigned long long* trace = a.trace ? a.trace + static_cast<size_t>(blockIdx.x) * kRDDTraceBlockWords : nullptr;
+    if (trace && threadIdx.x == 0) {
+        trace[0] = rdd_now();
+        trace[3] = static_cast<unsigned long long>(n_samples);
+        trace[4] = static_cast<unsigned long long>(q_total);
+    }
+
+    // the builder's first loads go out before any bulk copy is queued (a plain load behind ~200 KB of queued copies
+    // per SM waits microseconds, and the first lp is on every consumer's critical path)
+    Centre cn = Centre{0, 0};
+    float wn = 1.0f;
+    auto load_sample = [&](int s) {
+        if (lane < K && s < a.B) {
+            const int map = s * K + lane;
+            cn.x = a.centres[2 * map + 0];
+            cn.y = a.centres[2 * map + 1];
+            wn = a.weight ? a.weight[map] : 1.0f;
+        }
+    };
+    if (warp == W && n_samples > 0) load_sample(sample0);
+
+    const uint32_t lpf_u32 = smem_addr(sh.lp_full), lpe_u32 = smem_addr(sh.lp_empty);
+    const uint64_t pol = l2_evict_first_policy();
+    const int grp = warp < W ? warp / G : 0, h = warp < W ? warp % G : 0;  // group, warp of the group
+    unsigned char* my_slots = s_rdd + static_cast<size_t>(grp) * NS * kMapBytes;
+    const uint32_t slots_u32 = smem_addr(my_slots), bars_u32 = smem_addr(sh.full) + 8 * grp * NS;
+    const int n_my = (q_total > grp) ? (q_total - grp + NG - 1) / NG : 0;  // maps of this group
+    const int n_units = n_my * UPM;
+    // one lane of a group: request unit u of the group's load sequence into slot `slot` (= u % NS)
+    auto request = [&](int u, int slot) {
+        const int i = grp + (u / UPM) * NG;  // block-local map
+        const size_t off = static_cast<size_t>(m0 + i) * kRDDPixels;
+        const float* src = (FUSED && (u % UPM) == 0) ? a.fused + off : a.y_adv + off;
+        mbar_arrive_expect_tx(bars_u32 + 8 * slot, kMapBytes);
+        bulk_load(slots_u32 + slot * kMapBytes, src, kMapBytes, bars_u32 + 8 * slot, pol);
+    };
+
+    // ---- prologue: every group requests its first NS units before anything else --------------------------------------
+    if (warp < W) {
+        if (h == 0 && lane == 0) {
+            for (int s = 0; s < NS; ++s) mbar_init(bars_u32 + 8 * s, 1);
+            mbar_init_fence();
+            for (int u = 0; u < NS && u < n_units; ++u) request(u, u);
+        }
+    } else if (lane == 0) {
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(lpf_u32 + 8 * s, 1);
+            mbar_init(lpe_u32 + 8 * s, W);
+        }
+        mbar_init_fence();
+    }
+    for (int i = threadIdx.x; i < 2 * tmp * tmp + 1; i += blockDim.x) sh.tab[i] = a.tab[i];
+    if (threadIdx.x < kFxAccWords) sh.acc[threadIdx.x] = 0ull;
+    __syncthreads();
+
+    if (warp == W) {
+        // =================================== builder warp: lp of every sample of the block, one ahead ==================
+        RDDSlots<kTileMaxPatch> sl;
+        rdd_slots_init(sl, sh.tab, tmp, lane, 0, 1);
+        for (int r = 0; r < n_samples; ++r) {
+            const int slot = r & 1;
+            const Centre cc = cn;
+            const float ww = wn;
+            if (r + 1 < n_samples) load_sample(sample0 + r + 1);
+            if (r >= 2) mbar_wait_backoff(lpe_u32 + 8 * slot, static_cast<uint32_t>((r >> 1) - 1) & 1u, 100);
+            if (trace && lane == 0 && r < 8) trace[8 + 16 * kRDDTraceMaps * 8 + 2 * r] = rdd_now();
+            float* lp = lp_base + slot * kRDDPixels;
+            float4* lp4 = reinterpret_cast<float4*>(lp);
+#pragma unroll 8
+            for (int it = 0; it < 32; ++it) lp4[it * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+            __syncwarp();
+            for (int j = 0; j < K; ++j) {  // joints ascending: the summation order of every pixel is fixed
+                const int cx = __shfl_sync(0xffffffffu, cc.x, j), cy = __shfl_sync(0xffffffffu, cc.y, j);
+                // the patch pixels of one joint are distinct: all loads, then all stores (no false dependencies)
+                int off[kTileMaxPatch];
+                float v[kTileMaxPatch];
+#pragma unroll
+                for (int k = 0; k < kTileMaxPatch; ++k) {
+                    const int x = cx + sl.dx[k], y = cy + sl.dy[k];
+                    const bool in = static_cast<unsigned>(x) < static_cast<unsigned>(ow) && static_cast<unsigned>(y) < static_cast<unsigned>(oh);
+                    off[k] = in ? y * ow + x : -1;
+                    v[k] = in ? lp[off[k]] : 0.0f;
+                }
+#pragma unroll
+                for (int k = 0; k < kTileMaxPatch; ++k)
+                    if (off[k] >= 0) lp[off[k]] = v[k] + sl.t[k];
+                __syncwarp();
+            }
+            float2 su2 = make_float2(0.f, 0.f), sulg2 = make_float2(0.f, 0.f);
+#pragma unroll 4
+            for (int it = 0; it < 32; ++it) {
+                const float4 v = clip01_4(lp4[it * 32 + lane]);
+                lp4[it * 32 + lane] = v;
+                if (!FUSED) {
+                    const float2 u0 = make_float2(v.x + eps, v.y + eps), u1 = make_float2(v.z + eps, v.w + eps);
+                    su2 = __fadd2_rn(su2, __fadd2_rn(u0, u1));
+                    sulg2 = __fadd2_rn(sulg2, __fadd2_rn(make_float2(ulg2(u0.x), ulg2(u0.y)), make_float2(ulg2(u1.x), ulg2(u1.y))));
+                }
+            }
+            if (!FUSED) {
+                const float rr = warp_sum3_scattered(su2.x + su2.y, sulg2.x + sulg2.y, 0.0f, lane);
+                if (lane == 0) sh.cu[slot] = rr;
+                if (lane == 8) sh.culg[slot] = rr;
+            }
+            if (lane < K) {
+                sh.c[slot][lane] = cc;
+                sh.w[slot][lane] = ww;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(lpf_u32 + 8 * slot);
+            if (trace && lane == 0 && r < 8) trace[8 + 16 * kRDDTraceMaps * 8 + 2 * r + 1] = rdd_now();
+        }
+    } else {
+        // =================================== consumer warps: G warps per map ===========================================
+        RDDSlots<NSL> sl;  // this warp's share of the patch: slot rows h, h + G, ...
+        rdd_slots_init(sl, sh.tab, tmp, lane, h, G);
+        const float2 l2e = make_float2(kLog2e, kLog2e);
+        const int bar_id = 1 + grp;
+        uint32_t par_mask = 0;        // bit s: parity of slot s's next completion
+        int slot_c = 0;               // slot of the next unit to consume
+        int u_load = (n_units < NS) ? n_units : NS;   // next unit to request (its slot is the one consumed NS units before)
+        auto wait_unit = [&]() {      // the next unit of the sequence has landed; returns its slot
+            const int s = slot_c;
+            mbar_wait(bars_u32 + 8 * s, (par_mask >> s) & 1u);
+            par_mask ^= 1u << s;
+            slot_c = (s + 1 == NS) ? 0 : s + 1;
+            return s;
+        };
+        int r_done = 0;  // samples [0, r_done) of the block have been released by this warp
+        int k = m0 + grp - sample0 * K, r = 0;  // joint and block-relative sample of the current map
+        // wait for a sample's lp; the samples before it are released in order, each only after ITS lp has been seen
+        // complete (so that the empty-barrier of a slot never receives arrivals of two phases at once)
+        auto advance_to = [&](int r_want) {
+            while (r_done < r_want) {
+                mbar_wait_backoff(lpf_u32 + 8 * (r_done & 1), static_cast<uint32_t>(r_done >> 1) & 1u, 50);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(lpe_u32 + 8 * (r_done & 1));
+                ++r_done;
+            }
+            if (r_want < n_samples) mbar_wait(lpf_u32 + 8 * (r_want & 1), static_cast<uint32_t>(r_want >> 1) & 1u);
+        };
+        FxReg fx{0, 0, 0, 0, 0};
+        int jj = 0;  // the group's map counter
+        for (int i = grp; i < q_total; i += NG, ++jj) {
+            while (k >= K) {
+                k -= K;
+                ++r;
+            }
+            const int map = m0 + i, slot = r & 1, xb = jj & 1;
+            const bool leader = (jj % G) == h;
+            const float* lp = lp_base + slot * kRDDPixels;
+            const float4* LP4 = reinterpret_cast<const float4*>(lp);
+            float* xch = sh.xch[xb][warp];
+            int freed0;  // first slot freed by this map (UPM consecutive slots)
+            unsigned long long* wt = (trace && lane == 0 && jj < kRDDTraceMaps) ? trace + 8 + (warp * kRDDTraceMaps + jj) * 8 : nullptr;
+            if (wt) wt[0] = rdd_now();
+            if (!FUSED) {
+                const int sp = wait_unit();
+                freed0 = sp;
+                const float4* P4 = reinterpret_cast<const float4*>(my_slots + sp * kMapBytes);
+                const float* P = reinterpret_cast<const float*>(P4);
+                // ---- the softmax reference: the maximum of the map's first iteration (no pass over the map; every warp of
+                //      the group reads the same 32 float4) -------------------------------------------------------------------
+                float Mp = warp_max_f32(max4(P4[lane]));
+                const float ms = (Mp == -INFINITY) ? 0.0f : Mp;
+                const float mb = -ms * kLog2e;
+                if (wt) wt[1] = rdd_now();
+                advance_to(r);
+                if (wt) wt[2] = rdd_now();
+                const Centre ck = sh.c[slot][k];
+                // M = 1 iff some other centre lies outside the own patch (lp = 1 there, own Gaussian 0)
+                bool outside = false;
+                if (lane < K) {
+                    const Centre cj = sh.c[slot][lane];
+                    outside = abs(cj.x - ck.x) > tmp || abs(cj.y - ck.y) > tmp;
+                }
+                const bool fast = __any_sync(0xffffffffu, outside) || a.variant == HP_RD_RD4;  // rd4 does not normalise
+                // ---- own patch (this warp's slots): exact recipe minus the generic term --------------------------------
+                float c_u = 0.f, c_up = 0.f, c_ulg = 0.f;
+#pragma unroll
+                for (int kk = 0; kk < NSL; ++kk) {
+                    const int x = ck.x + sl.dx[kk], y = ck.y + sl.dy[kk];
+                    const bool in = static_cast<unsigned>(x) < static_cast<unsigned>(ow) && static_cast<unsigned>(y) < static_cast<unsigned>(oh);
+                    const int off = in ? y * ow + x : 0;
+                    const float lpv = lp[off], pk = P[off];
+                    const float gex = clip01(__fsub_rn(lpv, __fmul_rn(sl.t[kk], 10.0f)));
+                    const float du = in ? gex - lpv : 0.0f;
+                    const float dl = ulg2(gex + eps) - ulg2(lpv + eps);
+                    c_u += du;
+                    c_up = in ? fmaf(du, fmaf(pk, kLog2e, mb), c_up) : c_up;
+                    c_ulg += in ? dl : 0.0f;
+                }
+                if (wt) wt[3] = rdd_now();
+                // ---- pass B: softmax sum against the reference, sum u a with u = lp + eps, a = (p - ref) log2 e ---------------
+                const float2 mb2 = make_float2(mb, mb), e2 = make_float2(eps, eps);
+                float2 s2 = make_float2(0.f, 0.f), slp2 = make_float2(0.f, 0.f), slq2 = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int it = h * IT; it < (h + 1) * IT; ++it) {
+                    const float4 v = P4[it * 32 + lane];
+                    const float4 l = LP4[it * 32 + lane];
+                    const float2 lo = make_float2(v.x, v.y), hi = make_float2(v.z, v.w);
+                    const float2 a0 = __ffma2_rn(lo, l2e, mb2), a1 = __ffma2_rn(hi, l2e, mb2);
+                    s2 = __fadd2_rn(s2, __fadd2_rn(make_float2(ex2_approx(a0.x), ex2_approx(a0.y)),
+                                                   make_float2(ex2_approx(a1.x), ex2_approx(a1.y))));
+                    slp2 = __ffma2_rn(__fadd2_rn(make_float2(l.x, l.y), e2), a0, slp2);
+                    slq2 = __ffma2_rn(__fadd2_rn(make_float2(l.z, l.w), e2), a1, slq2);
+                }
+                if (wt) wt[4] = rdd_now();
+                {
+                    const float rr = warp_sum3_scattered(s2.x + s2.y, slp2.x + slp2.y + slq2.x + slq2.y, 0.0f, lane);
+                    const float r2 = warp_sum3_scattered(c_u, c_up, c_ulg, lane);
+                    // lanes 0 / 8 / 16 hold the three sums of each reduction
+                    if ((lane & 7) == 0 && lane < 16) xch[lane >> 3] = rr;
+                    if ((lane & 7) == 0 && lane < 24) xch[2 + (lane >> 3)] = r2;
+                }
+                group_barrier(bar_id, 32 * G);
+                if (leader) {
+                    float Sexp = 0.f, Sua = 0.f, cu = 0.f, culg = 0.f;
+#pragma unroll
+                    for (int g = 0; g < G; ++g) {
+                        const float* x = sh.xch[xb][grp * G + g];
+                        Sexp += x[0];
+                        Sua += x[1] + x[3];
+                        cu += x[2];
+                        culg += x[4];
+                    }
+                    float Su = sh.cu[slot] + cu, Sulg = sh.culg[slot] + culg, M = 1.0f;
+                    if (!fast) rdd_exact_map(P4, LP4, sh.tab, tmp, ck, a.wdiv, eps, mb, lane, Su, Sua, Sulg, M);  // the slot is still intact
+                    if (Sexp == INFINITY || Sexp == 0.0f) {
+                        // the sampled reference lies too far below the map's maximum (or is -inf): the exact two-pass sum,
+                        // and sum u a re-based to the true maximum
+                        float mx, sx;
+                        rdd_softmax_exact(P4, 0, 32, lane, mx, sx);
+                        const float msx = (mx == -INFINITY) ? 0.0f : mx;
+                        Sua = fmaf((ms - msx) * kLog2e, Su, Sua);
+                        Mp = mx;
+                        Sexp = sx;
+                    }
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (u_load < n_units) request(u_load, freed0);
+                        if (wt) wt[5] = rdd_now();
+                        // ---- closure: L = (sum u ln u - sum u p)/S - ln S + lse   (loss.py:145-158), in log2 units against
+                        //      the softmax reference: L = ln 2 ((sum u lg u - sum u a)/S - lg S + lg sum 2^a) ---------------------
+                        const float lg_se = lg2_approx(Sexp);
+                        const float lse = fmaf(lg_se, kLn2, (Mp == -INFINITY) ? 0.0f : Mp);
+                        const float L = kLn2 * (__fdividef(Sulg - Sua, Su) - lg2_approx(Su) + lg_se);
+                        const float Lw = L * sh.w[slot][k];
+                        a.per_map[map] = Lw;
+                        if (a.mean) fx_reg_add(fx, Lw);
+                        a.stats[3 * map + 0] = lse;
+                        a.stats[3 * map + 1] = Su;
+                        a.stats[3 * map + 2] = M;
+                    }
+                }
+                u_load += UPM;
+            } else {
+                const int sf = wait_unit(), sp = wait_unit();
+                freed0 = sf;
+                const float4* P4 = reinterpret_cast<const float4*>(my_slots + sp * kMapBytes);
+                const float* P = reinterpret_cast<const float*>(P4);
+                float4* F4 = reinterpret_cast<float4*>(my_slots + sf * kMapBytes);
+                float* F = reinterpret_cast<float*>(F4);
+                if (wt) wt[1] = rdd_now();
+                advance_to(r);
+                if (wt) wt[2] = rdd_now();
+                const Centre ck = sh.c[slot][k];
+                // ---- own patch (this warp's slots): exact un-normalised values into registers, -inf into the fused map
+                //      (the passes then see g = 0 there) -------------------------------------------------------------------
+                float gex[NSL], pk[NSL];
+                int poff[NSL];
+                float mg = -INFINITY;
+#pragma unroll
+                for (int kk = 0; kk < NSL; ++kk) {
+                    const int x = ck.x + sl.dx[kk], y = ck.y + sl.dy[kk];
+                    const bool in = static_cast<unsigned>(x) < static_cast<unsigned>(ow) && static_cast<unsigned>(y) < static_cast<unsigned>(oh);
+                    const int off = in ? y * ow + x : 0;
+                    const float lpv = lp[off], fv = F[off];
+                    pk[kk] = P[off];
+                    float g = clip01(__fsub_rn(lpv, __fmul_rn(sl.t[kk], 10.0f)));
+                    g = clip01(__fsub_rn(__fadd_rn(g, fv), __fmul_rn(sl.t[kk], 100.0f)));
+                    gex[kk] = g;
+                    poff[kk] = in ? off : -1;
+                    mg = in ? fmaxf(mg, g) : mg;
+                }
+#pragma unroll
+                for (int kk = 0; kk < NSL; ++kk)
+                    if (poff[kk] >= 0) F[poff[kk]] = -INFINITY;   // a patch pixel belongs to exactly one lane of the group
+                group_barrier(bar_id, 32 * G);
+                if (wt) wt[3] = rdd_now();
+                // ---- pass 1: g = clip(lp + f) written over f, its maximum; the softmax reference is sampled ------------
+#pragma unroll
+                for (int it = h * IT; it < (h + 1) * IT; ++it) {
+                    const float4 f = F4[it * 32 + lane], l = LP4[it * 32 + lane];
+                    const float4 g = clip01_4(add4(l, f));
+                    F4[it * 32 + lane] = g;
+                    mg = fmaxf(mg, max4(g));
+                }
+                {
+                    const float wmg = warp_max_f32(mg);
+                    if (lane == 0) sh.xmx[xb][warp] = wmg;
+                }
+                float Mp = warp_max_f32(max4(P4[lane]));  // the softmax reference: sampled from the map's first iteration
+                group_barrier(bar_id, 32 * G);
+                float M = -INFINITY;
+#pragma unroll
+                for (int g = 0; g < G; ++g) M = fmaxf(M, sh.xmx[xb][grp * G + g]);
+                const float invM = (M == 1.0f) ? 1.0f : __frcp_rn(M);
+                // ---- pass 2: the sums of u = g / M + eps ----------------------------------------------------------------
+                const float ms = (Mp == -INFINITY) ? 0.0f : Mp;
+                const float mb = -ms * kLog2e;
+                const float2 mb2 = make_float2(mb, mb), im2 = make_float2(invM, invM), e2 = make_float2(eps, eps);
+                float2 s2 = make_float2(0.f, 0.f), su2 = make_float2(0.f, 0.f), sup2 = make_float2(0.f, 0.f), suq2 = make_float2(0.f, 0.f);
+                float2 sulg2 = make_float2(0.f, 0.f), sulh2 = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int it = h * IT; it < (h + 1) * IT; ++it) {
+                    const float4 v = P4[it * 32 + lane], g = F4[it * 32 + lane];
+                    const float2 lo = make_float2(v.x, v.y), hi = make_float2(v.z, v.w);
+                    const float2 a0 = __ffma2_rn(lo, l2e, mb2), a1 = __ffma2_rn(hi, l2e, mb2);
+                    s2 = __fadd2_rn(s2, __fadd2_rn(make_float2(ex2_approx(a0.x), ex2_approx(a0.y)),
+                                                   make_float2(ex2_approx(a1.x), ex2_approx(a1.y))));
+                    const float2 u0 = __ffma2_rn(make_float2(g.x, g.y), im2, e2), u1 = __ffma2_rn(make_float2(g.z, g.w), im2, e2);
+                    su2 = __fadd2_rn(su2, __fadd2_rn(u0, u1));
+                    sup2 = __ffma2_rn(u0, a0, sup2);
+                    suq2 = __ffma2_rn(u1, a1, suq2);
+                    const float2 q0 = make_float2(lg2_approx(fmaxf(u0.x, 1.17549435e-38f)), lg2_approx(fmaxf(u0.y, 1.17549435e-38f)));
+                    const float2 q1 = make_float2(lg2_approx(fmaxf(u1.x, 1.17549435e-38f)), lg2_approx(fmaxf(u1.y, 1.17549435e-38f)));
+                    sulg2 = __ffma2_rn(u0, q0, sulg2);
+                    sulh2 = __ffma2_rn(u1, q1, sulh2);
+                }
+                if (wt) wt[4] = rdd_now();
+                // this warp's patch pixels went through the passes as g = 0 (u = eps): replace by the exact values
+                float c_u = 0.f, c_up = 0.f, c_ulg = 0.f;
+                const float u_bg = fmaf(0.0f, invM, eps), bg_ulg = ulg2(u_bg);
+#pragma unroll
+                for (int kk = 0; kk < NSL; ++kk) {
+                    const float uex = fmaf(gex[kk], invM, eps);
+                    const float du = uex - u_bg, dl = ulg2(uex) - bg_ulg;
+                    const bool in = poff[kk] >= 0;
+                    c_u += in ? du : 0.0f;
+                    c_up = in ? fmaf(du, fmaf(pk[kk], kLog2e, mb), c_up) : c_up;
+                    c_ulg += in ? dl : 0.0f;
+                }
+                {
+                    const float rr = warp_sum3_scattered(s2.x + s2.y, su2.x + su2.y + c_u, sup2.x + sup2.y + suq2.x + suq2.y + c_up, lane);
+                    float t = sulg2.x + sulg2.y + sulh2.x + sulh2.y + c_ulg;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+                    if ((lane & 7) == 0 && lane < 24) xch[lane >> 3] = rr;
+                    if (lane == 24) xch[3] = t;
+                }
+                fence_proxy_async_smem();  // this lane's writes to the slot precede the copy engine's next write
+                group_barrier(bar_id, 32 * G);
+                if (leader) {
+                    float Sexp = 0.f, Su = 0.f, Sup = 0.f, Sulg = 0.f;
+#pragma unroll
+                    for (int g = 0; g < G; ++g) {
+                        const float* x = sh.xch[xb][grp * G + g];
+                        Sexp += x[0];
+                        Su += x[1];
+                        Sup += x[2];
+                        Sulg += x[3];
+                    }
+                    if (Sexp == INFINITY || Sexp == 0.0f) {  // see the branch without a fused map; the slot is still intact
+                        float mx, sx;
+                        rdd_softmax_exact(P4, 0, 32, lane, mx, sx);
+                        const float msx = (mx == -INFINITY) ? 0.0f : mx;
+                        Sup = fmaf((ms - msx) * kLog2e, Su, Sup);
+                        Mp = mx;
+                        Sexp = sx;
+                    }
+                    __syncwarp();
+                    if (lane == 0) {
+                        int s = freed0;
+                        for (int c = 0; c < UPM; ++c) {
+                            if (u_load + c < n_units) request(u_load + c, s);
+                            s = (s + 1 == NS) ? 0 : s + 1;
+                        }
+                        if (wt) wt[5] = rdd_now();
+                        const float lg_se = lg2_approx(Sexp);
+                        const float lse = fmaf(lg_se, kLn2, (Mp == -INFINITY) ? 0.0f : Mp);
+                        const float L = kLn2 * (__fdividef(Sulg - Sup, Su) - lg2_approx(Su) + lg_se);
+                        const float Lw = L * sh.w[slot][k];
+                        a.per_map[map] = Lw;
+                        if (a.mean) fx_reg_add(fx, Lw);
+                        a.stats[3 * map + 0] = lse;
+                        a.stats[3 * map + 1] = Su;
+                        a.stats[3 * map + 2] = M;
+                    }
+                }
+                u_load += UPM;
+            }
+            if (wt) wt[6] = rdd_now();
+            k += NG;
+        }
+        advance_to(n_samples);  // release the remaining samples (keeps the arrival counts of the empty barriers whole)
+        if (lane == 0 && a.mean) fx_reg_flush(fx, sh.acc);
+    }
+
+    // ---- epilogue: block sum -> workspace, the last block finalises 'mean' / the per-sample means ----------------------
+    if (trace) {
+        __syncthreads();
+        if (threadIdx.x == 0) trace[1] = rdd_now();
+    }
+    if (a.mean == nullptr && a.per_sample == nullptr) return;
+    __syncthreads();
+    if (a.mean && threadIdx.x < kFxAccWords && sh.acc[threadIdx.x] != 0ull) atomicAdd(&a.ws->acc[threadIdx.x], sh.acc[threadIdx.x]);
+    if (last_block_arrives(&a.ws->counter, gridDim.x)) {
+        if (a.per_sample) per_sample_means(a.per_map, a.B, K, a.per_sample, threadIdx.x, 32 * (W + 1));
+        if (a.mean && threadIdx.x == 0) *a.mean = fx_mean_from_workspace(a.ws->acc, n_maps);
+        if (threadIdx.x == 0) a.ws->counter = 0;
+    }
+}
+
+template <bool FUSED, int GW>
+static int launch_rdd_shape(const RDArgs& a, int sms, cudaStream_t stream, const char* who) {
+    constexpr size_t smem = RDDShape<FUSED, GW>::kSmem;
+    static bool attr_done_dev[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    bool& attr_done = attr_done_dev[dev & 63];
+    if (!attr_done) {
+        const cudaError_t e = cudaFuncSetAttribute(regdisp_dense_kernel<FUSED, GW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   static_cast<int>(smem));
+        if (e != cudaSuccess) return fail(static_cast<int>(e), "%s: %s", who, cudaGetErrorString(e));
+        attr_done = true;
+    }
+    const int n_maps = a.B * a.K;
+    int grid = sms;
+    if (const char* e = getenv("HP_RD_GRID")) {  // tests: few blocks -> long map ranges spanning many samples
+        const int g = atoi(e);
+        if (g > 0) grid = g;
+    }
+    if (grid > n_maps) grid = n_maps;
+    regdisp_dense_kernel<FUSED, GW><<<grid, 32 * (RDDShape<FUSED, GW>::W + 1), smem, stream>>>(a);
+    return launch_status(who);
+}
+
+// profiling only (hp_debug_regdisp_trace)
+static unsigned long long* g_rdd_trace = nullptr;
+static size_t g_rdd_trace_words = 0;
+
+// forward, mode 'max', x6 / rd4 recipes on 4096-pixel maps; returns 1 when the case is not covered (the caller takes
+// the register-slice kernel), 0 when launched.  HP_RD_DENSE=0 keeps the old kernel (comparison runs).
+static int launch_regdisp_dense(RDArgs a, cudaStream_t stream, const char* who) {
+    static const bool on = []() {
+        const char* e = getenv("HP_RD_DENSE");
+        return !(e && e[0] == '0');
+    }();
+    if (!on) return 1;
+    if (a.mode != HP_MODE_MAX || (a.variant != HP_RD_X6 && a.variant != HP_RD_RD4)) return 1;
+    if (a.oh * a.ow != kRDDPixels || a.ow % 4 != 0 || a.K > kRDDMaxK || a.tmp > 6) return 1;
+    if ((2 * a.tmp + 1) * (2 * a.tmp + 1) > 32 * kTileMaxPatch) return 1;
+    static int sms = 0;
+    if (sms == 0) {
+        sms = hp_device_sm_count();
+        if (sms <= 0) sms = 148;
+    }
+    a.wdiv = FastDiv(static_cast<uint32_t>(a.ow));
+    a.trace = (g_rdd_trace && g_rdd_trace_words >= static_cast<size_t>(sms) * kRDDTraceBlockWords) ? g_rdd_trace : nullptr;
+    const bool fused = a.fused != nullptr && a.variant == HP_RD_X6;
+    // warps per map with a fused map: HP_RDD_G=2|4 overrides the default (comparison runs)
+    static const int g_env = []() {
+        const char* e = getenv("HP_RDD_G");
+        return e ? atoi(e) : 0;
+    }();
+    if (fused) return g_env == 2 ? launch_rdd_shape<true, 2>(a, sms, stream, who) : launch_rdd_shape<true, 4>(a, sms, stream, who);
+    return launch_rdd_shape<false, 2>(a, sms, stream, who);  // (4 warps per map measured slower: 82 vs 75 us with the decode)
+}
+
+}  // namespace hp

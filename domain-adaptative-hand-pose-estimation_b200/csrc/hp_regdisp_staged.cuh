@@ -55,6 +55,8 @@ struct RDArgs {
     // materialise
     float* gt;
     float* gf;
+    // profiling (hp_debug_regdisp_trace): per block kRDDTraceBlockWords stamps of the dense kernel, or null
+    unsigned long long* trace;
 };
 
 // clamp to [0, 1], NaN propagates (torch.clamp); two FMNMX.NAN

@@ -222,6 +222,11 @@ int hp_pipeline_fused_ex(const float* pred, const double* joints, const float* v
  * uint64 words.  buf = NULL switches it off.  Read by profiles/trace_pipeline.py. */
 size_t hp_debug_pipeline_trace_words(void);
 int hp_debug_pipeline_trace(void* buf, size_t words);
+/* The same aid for the dense 'max' disparity kernel (csrc/hp_regdisp_dense.cuh): per block entry / exit, per consumer warp
+ * and map {wait begins, data landed, per-sample label seen, map done}, per sample the builder's {begin, published}
+ * (globaltimer ns).  Read by profiles/trace_regdisp.py. */
+size_t hp_debug_regdisp_trace_words(void);
+int hp_debug_regdisp_trace(void* buf, size_t words);
 /* ---- row f3: the loss weightings JointsMSELoss0 / JointsKLLoss5 (uda/model/loss.py:68-112, :160-216) ----
  * hp_mse0_*: both maps shifted by 1e-7 and normalised to sum 1 per map, then 0.5*w*(p-t)^2; per_map [B*K] = mean over HW
  *   ('none'), *mean (nullable) = mean over all elements.  grad_kind HP_GRAD_SCALAR ('mean') / HP_GRAD_PER_MAP ('none').

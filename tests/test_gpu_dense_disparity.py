@@ -1,0 +1,157 @@
+"""GPU parity of the dense 'max' disparity kernel (csrc/hp_regdisp_dense.cuh: RegressionDisparityx6 / RegressionDisparity4,
+regda_7.py:3609-3632, regda_4.py) on the cases its shortcuts have to get right:
+
+  * every other joint's centre INSIDE the own patch (the maximum of the ground-false map is not 1 in closed form: the exact
+    per-pixel path), incl. all 21 maps non-positive (all centres (0, 0)) and centres in the map's corners;
+  * fused maps that push the ground-false label to all-zero (0 / 0 = NaN in the reference), NaN / +-inf in the fused map
+    or the prediction, fused values that make the maximum anything between 0 and 1;
+  * few blocks (map ranges over many samples: slot hand-over of the per-sample label) == the full grid, bit for bit;
+  * loss ('none' and 'mean'), the saved statistics through the backward kernel (gradient), against the live oracle and
+    against the register-slice kernel it replaced (HP_RD_DENSE=0 in a subprocess is not needed: HP_RD_SHAPE=g takes the
+    guarded generic kernel).
+Tolerances: loss rtol 1e-5; gradient rtol 1e-5 with the absolute slack scaled to the tensor (see test_gpu_parity.py)."""
+import importlib
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import api
+
+pytestmark = pytest.mark.gpu
+
+hp = importlib.import_module("domain-adaptative-hand-pose-estimation_b200")
+K = 21
+
+
+def _peaks(rs, B, centres, amp=1.0, noise=0.02):
+    """y[b,k]: a single clear peak at centres[b,k] = (x, y) plus small noise."""
+    y = (noise * rs.standard_normal((B, K, 64, 64))).astype(np.float32)
+    for b in range(B):
+        for k in range(K):
+            cx, cy = centres[b, k]
+            y[b, k, cy, cx] = amp + rs.uniform(0.1, 0.5)
+    return y
+
+
+def _run(ns, device, y_h, adv_h, f_h, w_h, go_h, mode="max", cls="RegressionDisparityx6"):
+    kl = ns.JointsKLLoss(reduction="none", epsilon=1e-7)
+    rd = getattr(ns, cls)(ns.PseudoLabelGenerator(K, 64, 64), kl)
+    y = torch.from_numpy(y_h).to(device)
+    adv = torch.from_numpy(adv_h).to(device).requires_grad_(True)
+    w = None if w_h is None else torch.from_numpy(w_h).to(device)
+    f = None if f_h is None else torch.from_numpy(f_h).to(device)
+    l = rd(y, adv, f, w, mode) if cls == "RegressionDisparityx6" else rd(y, adv, w, mode)
+    l.backward(torch.from_numpy(go_h).to(device))
+    klm = ns.JointsKLLoss(epsilon=1e-7)
+    rdm = getattr(ns, cls)(ns.PseudoLabelGenerator(K, 64, 64), klm)
+    with torch.no_grad():
+        lm = rdm(y, adv.detach(), f, w, mode) if cls == "RegressionDisparityx6" else rdm(y, adv.detach(), w, mode)
+    return l.detach().cpu().numpy(), adv.grad.cpu().numpy(), float(lm)
+
+
+def _compare(y_h, adv_h, f_h, w_h, seed, cls="RegressionDisparityx6", monkeypatch=None):
+    B = y_h.shape[0]
+    go_h = np.random.RandomState(seed).uniform(0.5, 1.5, size=(B,)).astype(np.float32)
+    ns = hp
+    l_gpu, g_gpu, m_gpu = _run(ns, "cuda", y_h, adv_h, f_h, w_h, go_h, cls=cls)
+    l_ref, g_ref, m_ref = _run(api.namespace(), "cpu", y_h, adv_h, f_h, w_h, go_h, cls=cls)
+    np.testing.assert_allclose(l_gpu, l_ref, rtol=1e-5, atol=1e-7, equal_nan=True)
+    np.testing.assert_allclose(m_gpu, m_ref, rtol=1e-5, equal_nan=True)
+    ok = np.isfinite(g_ref)
+    scale = 1e-5 * float(np.abs(g_ref[ok]).max()) if ok.any() else 0.0
+    assert np.array_equal(np.isnan(g_gpu), np.isnan(g_ref))
+    np.testing.assert_allclose(g_gpu[ok], g_ref[ok], rtol=1e-5, atol=scale)
+    if monkeypatch is not None:
+        monkeypatch.setenv("HP_RD_GRID", "3")
+        l_few, g_few, m_few = _run(ns, "cuda", y_h, adv_h, f_h, w_h, go_h, cls=cls)
+        monkeypatch.delenv("HP_RD_GRID")
+        assert np.array_equal(l_gpu, l_few, equal_nan=True) and np.array_equal(g_gpu, g_few, equal_nan=True)
+        assert m_gpu == m_few or (np.isnan(m_gpu) and np.isnan(m_few))
+    return l_gpu
+
+
+@pytest.mark.parametrize("cls", ["RegressionDisparityx6", "RegressionDisparity4"])
+def test_clustered_centres_take_the_exact_path(cls, monkeypatch):
+    """Samples whose 21 decoded centres all lie within each other's 13x13 patches: max(gf) has no closed form."""
+    rs = np.random.RandomState(4101)
+    B = 9
+    centres = np.zeros((B, K, 2), dtype=np.int64)
+    centres[0] = rs.randint(30, 34, size=(K, 2))            # tight cluster in the middle
+    centres[1] = rs.randint(0, 5, size=(K, 2))              # cluster in the top-left corner (truncated patches)
+    centres[2] = rs.randint(59, 64, size=(K, 2))            # bottom-right corner
+    centres[3] = np.array([17, 40])                         # all on ONE pixel
+    centres[4] = rs.randint(20, 27, size=(K, 2))            # 7x7 cluster: all inside every patch (|d| <= 6)
+    centres[5] = rs.randint(0, 64, size=(K, 2))             # ordinary sample (closed-form path)
+    centres[6] = rs.randint(20, 27, size=(K, 2))
+    centres[6, 20] = (40, 40)                               # one joint far away: maps 0..19 closed form, map 20 exact
+    centres[7] = rs.randint(0, 64, size=(K, 2))
+    centres[8] = rs.randint(10, 17, size=(K, 2))
+    y_h = _peaks(rs, B, centres)
+    y_h[7] = -np.abs(y_h[7])                                # every map non-positive: all centres (0, 0)
+    adv_h = hp.synth.make_host_batch(4102, B, K, 64, 64)["pred"]
+    w_h = (rs.uniform(size=(B, K, 1)) < 0.85).astype(np.float32)
+    _compare(y_h, adv_h, None, w_h, 4103, cls=cls, monkeypatch=monkeypatch)
+
+
+def test_fused_map_edge_values(monkeypatch):
+    """x6 'max' with a fused map: maxima anywhere in (0, 1], an all-zero label (0/0 -> NaN like the reference), NaN and
+    +-inf in the fused map, a clustered sample, weights None."""
+    rs = np.random.RandomState(4201)
+    B = 8
+    y_h = hp.synth.make_host_batch(4202, B, K, 64, 64)["pred"]
+    adv_h = hp.synth.make_host_batch(4203, B, K, 64, 64)["pred"]
+    f_h = rs.uniform(-0.3, 0.6, size=(B, K, 64, 64)).astype(np.float32)
+    f_h[1] = -3.0                                           # label all zero: NaN losses for the sample
+    f_h[2, :, :, :] = rs.uniform(-1.2, -0.6, size=(K, 64, 64)).astype(np.float32)   # max(gf) in (0, 0.4)
+    f_h[3, 4, 10, 11] = np.nan
+    f_h[3, 5, 0, 0] = np.inf
+    f_h[3, 6, 63, 63] = -np.inf
+    f_h[4] = 0.0                                            # the fused map adds nothing
+    centres = np.tile(rs.randint(28, 34, size=(1, K, 2)), (1, 1, 1))
+    y_h[5] = _peaks(rs, 1, centres)[0]                      # clustered centres + fused map
+    adv_h[6, 3, 20, 20] = np.nan                            # NaN in the prediction
+    l = _compare(y_h, adv_h, f_h, None, 4204, monkeypatch=monkeypatch)
+    assert np.isnan(l[1]) and np.isnan(l[3]) and np.isnan(l[6]) and np.isfinite(l[0]) and np.isfinite(l[2])
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_large_logits_take_the_exact_softmax(fused, monkeypatch):
+    """The passes run the softmax against a SAMPLED reference value; predictions whose maximum lies far above (or whose
+    sampled pixels lie far above the rest of) the map overflow / underflow that sum and must come back through the exact
+    two-pass path: logits of +-300, a single +200 spike, +inf (NaN like torch), a constant offset of -500 (the sums
+    run against the reference, so the offset does not cost precision).  Not covered: -inf logits - torch gives +inf, the
+    patch-correction algebra of this kernel (and of the headline pipeline kernel) gives NaN (inf - inf)."""
+    rs = np.random.RandomState(4401)
+    B = 6
+    y_h = hp.synth.make_host_batch(4402, B, K, 64, 64)["pred"]
+    adv_h = hp.synth.make_host_batch(4403, B, K, 64, 64)["pred"]
+    adv_h[0] *= 300.0
+    adv_h[1, :, 40, 17] += 200.0
+    adv_h[2, :, :2, :] += 150.0                             # the sampled rows far ABOVE the rest
+    adv_h[3] += 500.0
+    adv_h[4, 7, 50, 50] = np.inf
+    adv_h[5] -= 500.0
+    f_h = rs.uniform(-0.3, 0.6, size=(B, K, 64, 64)).astype(np.float32) if fused else None
+    l = _compare(y_h, adv_h, f_h, None, 4404, monkeypatch=monkeypatch)
+    assert np.isfinite(l[0]) and np.isfinite(l[1]) and np.isfinite(l[2]) and np.isfinite(l[3]) and np.isnan(l[4]) and np.isfinite(l[5])
+
+
+def test_mean_matches_generic_kernel_at_scale(monkeypatch):
+    """150 samples (more than one map range per SM boundary), 'mean': dense kernel == guarded generic kernel to 1e-6."""
+    B = 150
+    y = torch.from_numpy(hp.synth.make_host_batch(4301, B, K, 64, 64)["pred"]).cuda()
+    adv = torch.from_numpy(hp.synth.make_host_batch(4302, B, K, 64, 64)["pred"]).cuda()
+    f = torch.from_numpy(np.random.RandomState(4303).uniform(-0.3, 0.6, size=(B, K, 64, 64)).astype(np.float32)).cuda()
+    rd = hp.RegressionDisparityx6(hp.PseudoLabelGenerator(K, 64, 64), hp.JointsKLLoss(epsilon=1e-7))
+    rdn = hp.RegressionDisparityx6(hp.PseudoLabelGenerator(K, 64, 64), hp.JointsKLLoss(reduction="none", epsilon=1e-7))
+    with torch.no_grad():
+        got = [float(rd(y, adv, ff, None, "max")) for ff in (None, f)]
+        got_n = [rdn(y, adv, ff, None, "max").cpu().numpy() for ff in (None, f)]
+        monkeypatch.setenv("HP_RD_SHAPE", "g")
+        want = [float(rd(y, adv, ff, None, "max")) for ff in (None, f)]
+        want_n = [rdn(y, adv, ff, None, "max").cpu().numpy() for ff in (None, f)]
+        monkeypatch.delenv("HP_RD_SHAPE")
+    np.testing.assert_allclose(got, want, rtol=2e-6)
+    for a, b in zip(got_n, want_n):
+        np.testing.assert_allclose(a, b, rtol=1e-5)
