@@ -21,6 +21,10 @@ __global__ void __launch_bounds__(TPM* MPB)
                   float* __restrict__ maxvals, int32_t* __restrict__ idx_out, int32_t* __restrict__ centres,
                   int shift) {
     __shared__ Stats<0> scratch[TPM > 32 ? TPM / 32 + 1 : 1];
+    // a kernel launched behind this one with the programmatic-serialisation attribute (the dense disparity kernel,
+    // hp_regdisp_dense.cuh) may become resident as soon as every block of this grid has started; it reads this kernel's
+    // output only after its own griddepcontrol.wait.  No effect on ordinary launches.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int g = threadIdx.x / TPM, t = threadIdx.x % TPM;
     const int map = blockIdx.x * MPB + g;
     if (map >= n_maps) return;  // TPM == 32 groups are whole warps; TPM > 32 implies MPB == 1

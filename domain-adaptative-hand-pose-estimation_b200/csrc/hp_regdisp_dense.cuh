@@ -110,6 +110,14 @@ __device__ __forceinline__ void group_barrier(int id, int n_threads) {
 __device__ __forceinline__ float ulg2(float u) { return u * lg2_approx(fmaxf(u, 1.17549435e-38f)); }  // xlogy / ln 2
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// the per-sample constants sum (lp + eps), sum (lp + eps) lg2 (lp + eps) are summed in ONE order whichever path built
+// the sample (builder warp alone, or all warps for a block's first sample): per lane over the iterations ascending, then
+// the fixed shuffle tree - these are the per-(iteration, lane) terms
+__device__ __forceinline__ float rdd_term_u(float4 v, float eps) { return ((v.x + eps) + (v.y + eps)) + ((v.z + eps) + (v.w + eps)); }
+__device__ __forceinline__ float rdd_term_ulg(float4 v, float eps) {
+    return (ulg2(v.x + eps) + ulg2(v.y + eps)) + (ulg2(v.z + eps) + ulg2(v.w + eps));
+}
+
 // per-lane patch slots, lane-constant for the whole kernel: offset from the centre (dx = 1 << 20: unused) and value
 // slot j of a warp that takes every `stride`-th slot row starting at `first` is patch pixel (first + j * stride) * 32 + lane
 template <int N>
@@ -118,7 +126,7 @@ struct RDDSlots {
     float t[N];
 };
 template <int N>
-__device__ __forceinline__ void rdd_slots_init(RDDSlots<N>& s, const float* __restrict__ tab, int tmp, int lane, int first, int stride) {
+__device__ __forceinline__ void rdd_slots_init(RDDSlots<N>& s, const float* __restrict__ tab, int tmp, FastDiv sdiv, int lane, int first, int stride) {
     const int side = 2 * tmp + 1, n_patch = side * side;
 #pragma unroll
     for (int k = 0; k < N; ++k) {
@@ -127,7 +135,9 @@ __device__ __forceinline__ void rdd_slots_init(RDDSlots<N>& s, const float* __re
         s.dy[k] = 0;
         s.t[k] = 0.0f;
         if (i < n_patch) {
-            const int ry = i / side, rx = i - ry * side;
+            uint32_t qy, qx;
+            sdiv.divmod(static_cast<uint32_t>(i), qy, qx);
+            const int ry = static_cast<int>(qy), rx = static_cast<int>(qx);
             s.dx[k] = rx - tmp;
             s.dy[k] = ry - tmp;
             s.t[k] = tab[s.dx[k] * s.dx[k] + s.dy[k] * s.dy[k]];
@@ -234,8 +244,6 @@ __global__ void __launch_bounds__(32 * (RDDShape<FUSED, GW>::W + 1), 1) regdisp_
             wn = a.weight ? a.weight[map] : 1.0f;
         }
     };
-    if (warp == W && n_samples > 0) load_sample(sample0);
-
     const uint32_t lpf_u32 = smem_addr(sh.lp_full), lpe_u32 = smem_addr(sh.lp_empty);
     const uint64_t pol = l2_evict_first_policy();
     const int grp = warp < W ? warp / G : 0, h = warp < W ? warp % G : 0;  // group, warp of the group
@@ -251,15 +259,25 @@ __global__ void __launch_bounds__(32 * (RDDShape<FUSED, GW>::W + 1), 1) regdisp_
         mbar_arrive_expect_tx(bars_u32 + 8 * slot, kMapBytes);
         bulk_load(slots_u32 + slot * kMapBytes, src, kMapBytes, bars_u32 + 8 * slot, pol);
     };
-
-    // ---- prologue: every group requests its first NS units before anything else --------------------------------------
+    // The kernel is launched as a PROGRAMMATIC DEPENDENT of the decode launch (hp_decode.cu): its blocks become resident
+    // while the decode grid drains.  The first units (inputs the decode does not write) are requested at once; the
+    // builder warp alone waits for the decode to complete before it touches the centres, everybody else meets it at the
+    // block barrier below.  Nothing is written to global memory before that barrier.
     if (warp < W) {
         if (h == 0 && lane == 0) {
             for (int s = 0; s < NS; ++s) mbar_init(bars_u32 + 8 * s, 1);
             mbar_init_fence();
             for (int u = 0; u < NS && u < n_units; ++u) request(u, u);
         }
-    } else if (lane == 0) {
+    } else {
+        griddep_wait();
+        if (n_samples > 0) load_sample(sample0);
+    }
+
+    // ---- prologue ------------------------------------------------------------------------------------------------------
+    // The first sample's label is on every consumer's critical path: it is built by ALL warps, each a band of the map
+    // (a single warp needs 3.5-6 us for a sample; the first map of a block used to close 9 us after kernel entry).
+    if (warp == W && lane == 0) {
         for (int s = 0; s < 2; ++s) {
             mbar_init(lpf_u32 + 8 * s, 1);
             mbar_init(lpe_u32 + 8 * s, W);
@@ -268,13 +286,95 @@ __global__ void __launch_bounds__(32 * (RDDShape<FUSED, GW>::W + 1), 1) regdisp_
     }
     for (int i = threadIdx.x; i < 2 * tmp * tmp + 1; i += blockDim.x) sh.tab[i] = a.tab[i];
     if (threadIdx.x < kFxAccWords) sh.acc[threadIdx.x] = 0ull;
+    // everything that does not need the centres happens before the barrier (in the shadow of the decode's tail): the
+    // slot tables (from the table in global memory), the band's zeroes
+    constexpr int NWARPS = W + 1;
+    const int it0 = warp * 32 / NWARPS, it1 = (warp + 1) * 32 / NWARPS;  // this warp's band of the first label: float4 [32 it0, 32 it1)
+    RDDSlots<kTileMaxPatch> s6;  // the whole patch (cooperative build, builder)
+    rdd_slots_init(s6, a.tab, tmp, a.sdiv, lane, 0, 1);
+    RDDSlots<NSL> sl;            // a consumer warp's share of the patch: slot rows h, h + G, ...
+    rdd_slots_init(sl, a.tab, tmp, a.sdiv, lane, h, G);
+    for (int it = it0; it < it1; ++it) reinterpret_cast<float4*>(lp_base)[it * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (warp == W && lane < K) {  // waits for the loads issued at kernel entry
+        sh.c[0][lane] = cn;
+        sh.w[0][lane] = wn;
+    }
     __syncthreads();
+    if (trace && warp == W && lane == 0) trace[8 + 16 * kRDDTraceMaps * 8] = rdd_now();
+    if (n_samples > 0) {
+        const int p0 = it0 * 128, p1 = it1 * 128;                            // the band = pixels [p0, p1)
+        float* lp = lp_base;
+        float4* lp4 = reinterpret_cast<float4*>(lp);
+        float* scratch = lp_base + kRDDPixels;  // the second lp slot is free until the builder starts the second sample
+        if (trace && threadIdx.x == 0) trace[5] = rdd_now();
+        // lane j holds joint j; only the joints whose patch meets the band are visited - ascending, like the builder: the
+        // same sums bit for bit
+        Centre cl = Centre{0, 0};
+        bool meets = false;
+        if (lane < K) {
+            cl = sh.c[0][lane];
+            meets = (cl.y + tmp + 1) * ow > p0 && (cl.y - tmp) * ow < p1;
+        }
+        unsigned todo = __ballot_sync(0xffffffffu, meets);
+        while (todo != 0u) {
+            const int j = __ffs(todo) - 1;
+            todo &= todo - 1u;
+            Centre cj;
+            cj.x = __shfl_sync(0xffffffffu, cl.x, j);
+            cj.y = __shfl_sync(0xffffffffu, cl.y, j);
+            int off[kTileMaxPatch];
+            float v[kTileMaxPatch];
+#pragma unroll
+            for (int k = 0; k < kTileMaxPatch; ++k) {
+                const int x = cj.x + s6.dx[k], y = cj.y + s6.dy[k];
+                const int o = y * ow + x;
+                const bool in = static_cast<unsigned>(x) < static_cast<unsigned>(ow) && o >= p0 && o < p1;
+                off[k] = in ? o : -1;
+                v[k] = in ? lp[o] : 0.0f;
+            }
+#pragma unroll
+            for (int k = 0; k < kTileMaxPatch; ++k)
+                if (off[k] >= 0) lp[off[k]] = v[k] + s6.t[k];
+            __syncwarp();
+        }
+        if (trace && threadIdx.x == 0) trace[6] = rdd_now();
+        for (int it = it0; it < it1; ++it) {
+            const float4 v = clip01_4(lp4[it * 32 + lane]);
+            lp4[it * 32 + lane] = v;
+            if (!FUSED) {
+                scratch[it * 32 + lane] = rdd_term_u(v, eps);
+                scratch[1024 + it * 32 + lane] = rdd_term_ulg(v, eps);
+            }
+        }
+    }
+    if (trace && threadIdx.x == 0) trace[7] = rdd_now();
+    __syncthreads();
+    if (trace && threadIdx.x == 0) trace[2] = rdd_now();
 
     if (warp == W) {
         // =================================== builder warp: lp of every sample of the block, one ahead ==================
-        RDDSlots<kTileMaxPatch> sl;
-        rdd_slots_init(sl, sh.tab, tmp, lane, 0, 1);
-        for (int r = 0; r < n_samples; ++r) {
+        // (the second sample's loads only now: queued behind the first bulk copies they take microseconds, and a wait
+        // for them inside the cooperative build would hold every warp at its barrier)
+        if (n_samples > 1) load_sample(sample0 + 1);
+        const RDDSlots<kTileMaxPatch>& sl = s6;
+        if (n_samples > 0) {  // the first sample: built by all warps above; its constants in the canonical order
+            if (!FUSED) {
+                const float* scratch = lp_base + kRDDPixels;
+                float su = 0.f, sulg = 0.f;
+#pragma unroll 8
+                for (int it = 0; it < 32; ++it) {
+                    su += scratch[it * 32 + lane];
+                    sulg += scratch[1024 + it * 32 + lane];
+                }
+                const float rr = warp_sum3_scattered(su, sulg, 0.0f, lane);
+                if (lane == 0) sh.cu[0] = rr;
+                if (lane == 8) sh.culg[0] = rr;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(lpf_u32);
+            if (trace && lane == 0) trace[8 + 16 * kRDDTraceMaps * 8 + 1] = rdd_now();
+        }
+        for (int r = 1; r < n_samples; ++r) {
             const int slot = r & 1;
             const Centre cc = cn;
             const float ww = wn;
@@ -303,19 +403,18 @@ __global__ void __launch_bounds__(32 * (RDDShape<FUSED, GW>::W + 1), 1) regdisp_
                     if (off[k] >= 0) lp[off[k]] = v[k] + sl.t[k];
                 __syncwarp();
             }
-            float2 su2 = make_float2(0.f, 0.f), sulg2 = make_float2(0.f, 0.f);
+            float su = 0.f, sulg = 0.f;
 #pragma unroll 4
             for (int it = 0; it < 32; ++it) {
                 const float4 v = clip01_4(lp4[it * 32 + lane]);
                 lp4[it * 32 + lane] = v;
                 if (!FUSED) {
-                    const float2 u0 = make_float2(v.x + eps, v.y + eps), u1 = make_float2(v.z + eps, v.w + eps);
-                    su2 = __fadd2_rn(su2, __fadd2_rn(u0, u1));
-                    sulg2 = __fadd2_rn(sulg2, __fadd2_rn(make_float2(ulg2(u0.x), ulg2(u0.y)), make_float2(ulg2(u1.x), ulg2(u1.y))));
+                    su += rdd_term_u(v, eps);
+                    sulg += rdd_term_ulg(v, eps);
                 }
             }
             if (!FUSED) {
-                const float rr = warp_sum3_scattered(su2.x + su2.y, sulg2.x + sulg2.y, 0.0f, lane);
+                const float rr = warp_sum3_scattered(su, sulg, 0.0f, lane);
                 if (lane == 0) sh.cu[slot] = rr;
                 if (lane == 8) sh.culg[slot] = rr;
             }
@@ -329,8 +428,6 @@ __global__ void __launch_bounds__(32 * (RDDShape<FUSED, GW>::W + 1), 1) regdisp_
         }
     } else {
         // =================================== consumer warps: G warps per map ===========================================
-        RDDSlots<NSL> sl;  // this warp's share of the patch: slot rows h, h + G, ...
-        rdd_slots_init(sl, sh.tab, tmp, lane, h, G);
         const float2 l2e = make_float2(kLog2e, kLog2e);
         const int bar_id = 1 + grp;
         uint32_t par_mask = 0;        // bit s: parity of slot s's next completion
@@ -649,7 +746,18 @@ static int launch_rdd_shape(const RDArgs& a, int sms, cudaStream_t stream, const
         if (g > 0) grid = g;
     }
     if (grid > n_maps) grid = n_maps;
-    regdisp_dense_kernel<FUSED, GW><<<grid, 32 * (RDDShape<FUSED, GW>::W + 1), smem, stream>>>(a);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(32 * (RDDShape<FUSED, GW>::W + 1));
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // behind the decode launch of hp_regdisp_fwd
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, regdisp_dense_kernel<FUSED, GW>, a);
+    if (e != cudaSuccess) return fail(static_cast<int>(e), "%s: %s", who, cudaGetErrorString(e));
     return launch_status(who);
 }
 
@@ -674,6 +782,7 @@ static int launch_regdisp_dense(RDArgs a, cudaStream_t stream, const char* who) 
         if (sms <= 0) sms = 148;
     }
     a.wdiv = FastDiv(static_cast<uint32_t>(a.ow));
+    a.sdiv = FastDiv(static_cast<uint32_t>(2 * a.tmp + 1));
     a.trace = (g_rdd_trace && g_rdd_trace_words >= static_cast<size_t>(sms) * kRDDTraceBlockWords) ? g_rdd_trace : nullptr;
     const bool fused = a.fused != nullptr && a.variant == HP_RD_X6;
     // warps per map with a fused map: HP_RDD_G=2|4 overrides the default (comparison runs)

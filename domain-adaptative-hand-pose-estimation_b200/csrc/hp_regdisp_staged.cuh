@@ -41,6 +41,7 @@ struct RDArgs {
     const int32_t* centres;
     int splits;
     FastDiv wdiv;
+    FastDiv sdiv;  // by the patch side (dense kernel)
     unsigned producer_sleep_ns;  // staged kernels: back-off of the producer warp's poll on an empty-barrier
     // forward
     float* per_map;

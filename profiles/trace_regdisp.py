@@ -89,6 +89,8 @@ res = {
                    "reduce_request": q((rel[..., 5] - rel[..., 4])[later]), "closure": q((rel[..., 6] - rel[..., 5])[later])},
     "maps_done_at_by_index_ns": [q(rel[..., j, 6][used[..., j]]) for j in range(NM) if used[..., j].any()],
     "maps_per_warp": q(used.sum(axis=2).ravel()),
+    "prologue_warp0_ns": {"slots_ready": q(t[:, 5] - t0), "joints_done": q(t[:, 6] - t0), "clip_done": q(t[:, 7] - t0),
+                          "barrier_passed": q(t[:, 2] - t0)},
 }
 print(json.dumps(res, indent=1))
 if args.out:
