@@ -701,11 +701,13 @@ def run_regdisp_arm(args, wl):
         for name, (fn, bytes_per_map, note) in variants.items():
             for i in range(max(args.warmup, 3)):
                 fn(i)
-            reg = h.regions(fn, args.steps, min_total_ms=MIN_TIMED_MS / 2, profile_first=(name == "min"))
+            reg = h.regions(fn, args.steps, min_total_ms=MIN_TIMED_MS / 2, profile_first=True)
             ms = statistics.median(reg) / args.steps
             gbs = n * bytes_per_map / (ms * 1e-3) / 1e9
             rows[name] = {"ms_per_step": ms, "heatmaps_per_s": n * world / (ms * 1e-3), "algorithmic_bytes_per_map": bytes_per_map,
-                          "achieved_GBps": gbs, "frac": gbs / peak, "regions": region_stats(reg, args.steps), "note": note}
+                          "achieved_GBps": gbs, "frac": gbs / peak, "regions": region_stats(reg, args.steps), "note": note,
+                          "launches_per_step": 1 if name == "min" else 2,
+                          "traffic": recorded_traffic(args.workload + ("" if name == "min" else "_" + name))}
         # e2e: host heatmaps in, scalar loss out
         hy = [y.cpu().pin_memory() for y in ys[:2]]
         ha = [a.cpu().pin_memory() for a in advs[:2]]
@@ -737,18 +739,18 @@ def run_regdisp_arm(args, wl):
                 "scaling": wl["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": wl["desc"], "per_gpu_batch": B, "joints": K, "heatmap": [side, side],
                            "step": "RegressionDisparityx6(PseudoLabelGenerator, JointsKLLoss(1e-7)) forward, mode='min' "
-                                   "(decode launch + staged loss launch); 'max' variants in `variants`",
+                                   "(decode + loss in ONE launch); 'max' variants (decode launch + dense loss launch) in `variants`",
                            "l2": f"{n_sets} rotating input sets of {2 * n * hw4 / 1e6:.0f} MB",
                            "parallelism": f"batch-sharded dp{world}, no collective (per-rank mean)" if world > 1 else "single GPU"},
                 "roofline": {"bound": "hbm", "achieved": head["achieved_GBps"], "peak": peak, "unit": "GB/s", "frac": head["frac"],
-                             "traffic": recorded_traffic(args.workload), "kernel": "hp::decode_kernel + hp::regdisp_staged_kernel",
+                             "traffic": recorded_traffic(args.workload), "kernel": "hp::regdisp_min_kernel ('min': decode + loss in one launch); 'max' variants: hp::decode_kernel + hp::regdisp_dense_kernel",
                              "algorithmic_bytes_per_launch": n * 2 * hw4, "kernel_ms": head["ms_per_step"], "peak_source": peak_src},
                 "variants": rows, "cpu_baseline": cpu_baseline,
                 "e2e": {"value": n * world * e2e_steps / float(dt_t.item()), "unit": UNIT, "h2d_bytes_per_step": 2 * n * hw4 * world,
                         "d2h_bytes_per_step": 4 * world, "steps": e2e_steps, "ms_per_step": 1e3 * float(dt_t.item()) / e2e_steps,
                         "api": "pinned host y, y_adv -> .to(device) -> RegressionDisparityx6(...,'min') -> loss.item()",
                         "check_loss": last},
-                "clocks": clocks, "gpu_launches": 2 * args.steps}
+                "clocks": clocks, "gpu_launches": args.steps}
         sys.stdout.write(json.dumps(line) + "\n")
         sys.stdout.flush()
     h.shutdown()
