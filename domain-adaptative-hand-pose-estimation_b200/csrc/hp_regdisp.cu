@@ -23,6 +23,7 @@
 #include "hp_regdisp_staged.cuh"
 #include "hp_regdisp_min.cuh"
 #include "hp_regdisp_dense.cuh"
+#include "hp_regdisp_sparse.cuh"
 
 namespace hp {
 
@@ -324,6 +325,25 @@ extern "C" HP_API int hp_regdisp_fwd(const float* y, const float* y_adv, const f
         m.per_map = per_map; m.per_sample = per_sample; m.mean = mean; m.stats = stats; m.centres = centres;
         m.ws = static_cast<Workspace*>(workspace);
         const int rc = launch_regdisp_min(m, s, "hp_regdisp_fwd");
+        if (rc != 1) return rc;
+    }
+    // x1 / x5 recipes (constant target outside the own patch) on 32x32 / 16x16 heads, both modes, no fused map: decode +
+    // loss in ONE kernel as well (hp_regdisp_sparse.cuh)
+    if ((variant == HP_RD_X1 || variant == HP_RD_X5) && fused == nullptr && H * W == 4096 && W % 4 == 0 &&
+        (oh * ow == 1024 || oh * ow == 256) && ow % 4 == 0 && aligned16(y) && aligned16(y_adv) &&
+        (2 * tmp + 1) * (2 * tmp + 1) <= 32 * kTileMaxPatch && (2 * tmp + 1) * (2 * tmp + 1) < oh * ow && !generic_forced() &&
+        rd_min_fused_enabled()) {
+        RDSparseArgs sp{};
+        RDMinArgs& m = sp.m;
+        m.y = y; m.y_adv = y_adv; m.weight = weight; m.n_maps = B * K; m.B = B; m.K = K; m.H = H; m.W = W; m.HW = H * W;
+        m.tmp = tmp; m.wdiv = FastDiv(static_cast<uint32_t>(W)); m.sdiv = FastDiv(static_cast<uint32_t>(2 * tmp + 1));
+        m.tab = tab; m.eps = epsilon;
+        m.per_map = per_map; m.per_sample = per_sample; m.mean = mean; m.stats = stats; m.centres = centres;
+        m.ws = static_cast<Workspace*>(workspace);
+        sp.oh = oh; sp.ow = ow; sp.shift = shift; sp.want_gf = (mode == HP_MODE_MAX) ? 1 : 0; sp.bg = sp.want_gf ? 1.0f : 0.0f;
+        sp.ubg = sp.bg + epsilon;
+        sp.ubg_log_ubg = sp.ubg > 0.0f ? sp.ubg * std::log(sp.ubg) : 0.0f;
+        const int rc = launch_regdisp_sparse(sp, s, "hp_regdisp_fwd");
         if (rc != 1) return rc;
     }
     if (int rc = launch_decode(y, B * K, H, W, nullptr, nullptr, nullptr, centres, shift, s)) return rc;

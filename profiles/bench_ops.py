@@ -108,6 +108,8 @@ with torch.no_grad():
     rd1 = hp.RegressionDisparityx1(hp.PseudoLabelGenerator01(K), hp.JointsKLLoss(epsilon=1e-7))
     timed("RegressionDisparityx5 'min' (32x32 head)", lambda i: rd5(ys[i], f32[i], None, None, "min"), 3, n * (hw4 + 4096), n)
     timed("RegressionDisparityx1 'min' (16x16 head)", lambda i: rd1(ys[i], f16[i], None, "min"), 3, n * (hw4 + 1024), n)
+    timed("RegressionDisparityx5 'max' (32x32 head, no fused map)", lambda i: rd5(ys[i], f32[i], None, None, "max"), 3, n * (hw4 + 4096), n)
+    timed("RegressionDisparityx1 'max' (16x16 head)", lambda i: rd1(ys[i], f16[i], None, "max"), 3, n * (hw4 + 1024), n)
     del ys, advs, f32, f16, t5
     torch.cuda.empty_cache()
 
