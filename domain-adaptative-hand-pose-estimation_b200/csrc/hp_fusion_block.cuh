@@ -392,6 +392,233 @@ __global__ void __launch_bounds__(32 * kBlockMaxWarps, 4)
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// The same walk with the HIGH-RESOLUTION map staged by the copy engine too (configs[3]: 32 / 64 / 128, fuse + decode +
+// PCK).  In fuse_block_kernel a lane streams its four float4 of `hi` per block row with plain loads, one block row
+// ahead: ncu (profiles/r1_final_kernels_summary.txt) shows the warps waiting on exactly those loads (long-scoreboard
+// 2.1 per issued instruction at 57 % issue utilisation) and 16 register moves per block row that hand the prefetched
+// rows on.  Here a block is 8 warps (2 blocks per SM, the same 16 warps), a warp owns 16 output rows = 8 KB of `hi`,
+// split into two 4 KB halves with their own mbarriers: the half a warp has finished is re-requested for the block's
+// NEXT map at once, so each half has half a map of lead time and the blend never waits on global memory.
+constexpr int kBlockHsWarps = 8;
+struct BlockHsCtl {
+    unsigned long long full[2];               // lo / mid sources of buffer b have landed
+    unsigned long long hfull[kBlockHsWarps][2];  // half h of warp w's rows of `hi` has landed
+    int done[2];
+    int nan[2];
+    ArgMax am[2][kBlockHsWarps];
+};
+
+template <int SL, int SM, bool DECODE>
+__global__ void __launch_bounds__(32 * kBlockHsWarps, 2)
+    fuse_block_hs_kernel(const FuseSrc f, int n_maps, float* __restrict__ out, const float* __restrict__ tgt_xy, int K, double thr,
+                         float* __restrict__ pred_xy, float* __restrict__ maxvals, int32_t* __restrict__ counts_out,
+                         double* __restrict__ acc_out, Workspace* __restrict__ ws) {
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    __shared__ BlockHsCtl ctl;
+    constexpr int SMX = SM == 0 ? 2 : SM;
+    constexpr int STRIP = 4, SUB = 2;  // block rows per lane, per half
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int HW = f.H * f.W;
+    const int lo_elems = f.hl * f.wl, mid_elems = SM ? f.hm * f.wm : 0;
+    const uint32_t lo_bytes = 4u * lo_elems, mid_bytes = 4u * mid_elems, buf_bytes = lo_bytes + mid_bytes;
+    RowTap* s_rows = reinterpret_cast<RowTap*>(s_raw + 2 * static_cast<size_t>(buf_bytes));  // NaN rescan only
+    const uint32_t rows_bytes = ((static_cast<uint32_t>(sizeof(RowTap)) * 2u * f.H + 127u) / 128u) * 128u;
+    const uint32_t half_bytes = static_cast<uint32_t>(SUB * 4 * f.W) * 4u;  // 8 rows of `hi`
+    const int n_local = (n_maps - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+    const uint32_t full_u32 = smem_addr(&ctl.full[0]), src_u32 = smem_addr(s_raw);
+    const uint32_t hbar_u32 = smem_addr(&ctl.hfull[warp][0]);
+    const uint32_t hs_u32 = src_u32 + 2u * buf_bytes + rows_bytes + static_cast<uint32_t>(warp) * 2u * half_bytes;
+    const uint64_t pol = l2_evict_first_policy();
+    const int m_begin = warp * STRIP;  // one block row per warp pass (W / 4 == 32 column blocks)
+
+    auto request = [&](int j) {  // one thread: lo / mid of the block's j-th map -> buffer j & 1
+        const int b = j & 1;
+        const size_t map = static_cast<size_t>(blockIdx.x) + static_cast<size_t>(j) * gridDim.x;
+        mbar_arrive_expect_tx(full_u32 + 8 * b, buf_bytes);
+        bulk_load(src_u32 + b * buf_bytes, f.lo + map * lo_elems, lo_bytes, full_u32 + 8 * b, pol);
+        if (SM) bulk_load(src_u32 + b * buf_bytes + lo_bytes, f.mid + map * mid_elems, mid_bytes, full_u32 + 8 * b, pol);
+    };
+    auto request_hi = [&](int j, int half) {  // lane 0 of a warp: its rows [16 warp + 8 half, + 8) of the block's j-th map
+        const size_t map = static_cast<size_t>(blockIdx.x) + static_cast<size_t>(j) * gridDim.x;
+        const float* src = f.hi + map * HW + static_cast<size_t>(4 * (m_begin + half * SUB)) * f.W;
+        mbar_arrive_expect_tx(hbar_u32 + 8 * half, half_bytes);
+        bulk_load(hs_u32 + half * half_bytes, src, half_bytes, hbar_u32 + 8 * half, pol);
+    };
+    if (lane == 0) {
+        mbar_init(hbar_u32, 1);
+        mbar_init(hbar_u32 + 8, 1);
+        if (warp == 0) {
+            mbar_init(full_u32, 1);
+            mbar_init(full_u32 + 8, 1);
+        }
+        mbar_init_fence();
+        if (n_local > 0) {
+            request_hi(0, 0);
+            request_hi(0, 1);
+        }
+        if (warp == 0) {
+            ctl.done[0] = ctl.done[1] = 0;
+            ctl.nan[0] = ctl.nan[1] = 0;
+            if (n_local > 0) request(0);
+            if (n_local > 1) request(1);
+        }
+    }
+    if (DECODE) {
+        for (int r = threadIdx.x; r < f.H; r += blockDim.x) {
+            const Tap tl = make_tap(r, f.sy_lo, f.hl, f.H);
+            s_rows[r] = RowTap{tl.i0, tl.i1, tl.l0, tl.l1};
+            if (SM) {
+                const Tap tm = make_tap(r, f.sy_mid, f.hm, f.H);
+                s_rows[f.H + r] = RowTap{tm.i0, tm.i1, tm.l0, tm.l1};
+            }
+        }
+    }
+    const int n = lane, x0 = 4 * n;
+    const BlockAxis<SL> lo_x = block_axis<SL>(n);
+    const BlockCols<SL> lo_c = block_cols<SL>(n, f.wl);
+    const BlockAxis<SMX> mid_x = block_axis<SMX>(n);
+    const BlockCols<SMX> mid_c = block_cols<SMX>(n, SM ? f.wm : 2);
+    __syncthreads();  // the only block barrier: control block (and tap table) are set up
+    {
+        bool ok = block_axis_matches<SL>(n, f.wl);
+        if (SM) ok = ok && block_axis_matches<SMX>(n, f.wm);
+        for (int m = m_begin; m < m_begin + STRIP; ++m) {
+            ok = ok && block_axis_matches<SL>(m, f.hl);
+            if (SM) ok = ok && block_axis_matches<SMX>(m, f.hm);
+        }
+        if (!ok) __trap();  // the host only selects this kernel for exact scales; never silently wrong
+    }
+
+    const float2 al = make_float2(f.a_lo, f.a_lo), am2 = make_float2(f.a_mid, f.a_mid), ah = make_float2(f.a_hi, f.a_hi);
+    const uint32_t my_hi = hs_u32 + 16u * static_cast<uint32_t>(lane);  // this lane's float4 of a staged row
+    const uint32_t row_bytes = 4u * static_cast<uint32_t>(f.W);
+    for (int j = 0; j < n_local; ++j) {
+        const int b = j & 1;
+        const int map = static_cast<int>(blockIdx.x) + j * static_cast<int>(gridDim.x);
+        const uint32_t lo_s = src_u32 + b * buf_bytes, mid_s = lo_s + lo_bytes;
+        float* o = DECODE ? nullptr : out + static_cast<size_t>(map) * HW + x0;
+        float best = -INFINITY;
+        int best_row = 4 * m_begin;
+        float4 best_v = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        float2 witness = make_float2(0.f, 0.f);
+        mbar_wait(full_u32 + 8 * b, static_cast<uint32_t>(j >> 1) & 1u);
+        BlockRows<SL> RL;
+        BlockRows<SMX> RM;
+        block_rows_start<SL>(RL, lo_s, f.wl, f.hl, m_begin, lo_c, lo_x);
+        if (SM) block_rows_start<SMX>(RM, mid_s, f.wm, f.hm, m_begin, mid_c, mid_x);
+#pragma unroll
+        for (int i = 0; i < STRIP; ++i) {
+            const int m = m_begin + i;
+            const int half = i / SUB;
+            if (i % SUB == 0) mbar_wait(hbar_u32 + 8 * half, static_cast<uint32_t>(j) & 1u);
+            float4 h[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t addr = my_hi + half * half_bytes + static_cast<uint32_t>((i % SUB) * 4 + u) * row_bytes;
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(h[u].x), "=f"(h[u].y), "=f"(h[u].z), "=f"(h[u].w) : "r"(addr));
+            }
+            if (i % SUB == SUB - 1) {  // this half has been read out: the block's next map takes its place
+                __syncwarp();
+                if (lane == 0 && j + 1 < n_local) request_hi(j + 1, half);
+            }
+            float2 vl[4][2], vm[4][2];
+            block_rows_blend<SL>(RL, lo_s, f.wl, f.hl, m, lo_c, lo_x, vl);
+            if (SM) block_rows_blend<SMX>(RM, mid_s, f.wm, f.hm, m, mid_c, mid_x, vm);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                float2 r0 = __fmul2_rn(al, vl[u][0]), r1 = __fmul2_rn(al, vl[u][1]);
+                if (SM) {
+                    r0 = __ffma2_rn(am2, vm[u][0], r0);
+                    r1 = __ffma2_rn(am2, vm[u][1], r1);
+                }
+                r0 = __ffma2_rn(ah, make_float2(h[u].x, h[u].y), r0);
+                r1 = __ffma2_rn(ah, make_float2(h[u].z, h[u].w), r1);
+                const int row = 4 * m + u;
+                if (DECODE) {
+                    const float m4 = fmaxf(fmaxf(r0.x, r0.y), fmaxf(r1.x, r1.y));
+                    const bool up = m4 > best;  // strict; a NaN row never improves (the witness sends the map to the rescan)
+                    best = up ? m4 : best;
+                    best_row = up ? row : best_row;
+                    best_v.x = up ? r0.x : best_v.x;
+                    best_v.y = up ? r0.y : best_v.y;
+                    best_v.z = up ? r1.x : best_v.z;
+                    best_v.w = up ? r1.y : best_v.w;
+                    witness = __fadd2_rn(witness, __fadd2_rn(r0, r1));  // NaN / inf-inf witness
+                } else {
+                    stg_stream4(reinterpret_cast<float4*>(o + row * f.W), make_float4(r0.x, r0.y, r1.x, r1.y));
+                }
+            }
+        }
+        ArgMax am = am_init();
+        bool bad = false;
+        if (DECODE) {
+            const int comp = (best_v.x == best) ? 0 : ((best_v.y == best) ? 1 : ((best_v.z == best) ? 2 : 3));
+            am.v = best;
+            am.i = best_row * f.W + x0 + comp;
+            am = warp_argmax_rows(am, lane);
+            const float w = witness.x + witness.y;
+            bad = __any_sync(0xffffffffu, w != w);
+        }
+        // ---- ticket: the last warp of this map closes it and re-fills the lo / mid buffer ------------------------
+        __syncwarp();
+        int last = 0;
+        if (lane == 0) {
+            if (DECODE) {
+                ctl.am[b][warp] = am;
+                if (bad) atomicOr(&ctl.nan[b], 1);
+            }
+            __threadfence_block();
+            last = (atomicAdd(&ctl.done[b], 1) == kBlockHsWarps - 1) ? 1 : 0;
+            if (last) __threadfence_block();
+        }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last) {
+            if (DECODE) {
+                ArgMax a = ctl.am[b][0];
+                for (int w = 1; w < kBlockHsWarps; ++w) a = am_merge(a, ctl.am[b][w]);
+                if (*reinterpret_cast<volatile int*>(&ctl.nan[b]))
+                    a = block_nan_rescan(f, lo_s, mid_s, s_rows, f.hi + static_cast<size_t>(map) * HW, lane);
+                if (lane == 0) {
+                    float px, py;
+                    decode_xy(a, f.W, px, py);
+                    pred_xy[2 * map + 0] = px;
+                    pred_xy[2 * map + 1] = py;
+                    if (maxvals) maxvals[map] = a.v;
+                    int valid, hit;
+                    pck_one(px, py, tgt_xy[2 * map], tgt_xy[2 * map + 1], f.H, f.W, thr, valid, hit);
+                    const int k = map % K;
+                    if (valid) atomicAdd(&ws->counts[K + k], 1);
+                    if (hit) atomicAdd(&ws->counts[k], 1);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) {
+                ctl.done[b] = 0;
+                ctl.nan[b] = 0;
+                __threadfence_block();
+                if (j + 2 < n_local) request(j + 2);  // every warp has finished reading buffer b
+            }
+        }
+    }
+    if (DECODE) {
+        if (last_block_arrives(&ws->counter, gridDim.x)) pck_publish(ws, K, counts_out, acc_out);
+    }
+}
+
+// the staged-hi kernel covers: a high-resolution source, 32 column blocks (W == 128), 32 block rows (H == 128)
+static bool block_hs_geometry(const FuseSrc& f, const BlockWalk& g, size_t& smem) {
+    static const bool on = []() {
+        const char* e = getenv("HP_FUSE_HS");
+        return !(e && e[0] == '0');
+    }();
+    if (!on || f.hi == nullptr || g.cb != 32 || f.H != 4 * kBlockHsWarps * 4) return false;
+    const size_t lo_b = 4ull * f.hl * f.wl, mid_b = f.mid ? 4ull * f.hm * f.wm : 0;
+    const size_t rows_b = ((sizeof(RowTap) * 2 * static_cast<size_t>(f.H) + 127) / 128) * 128;
+    smem = 2 * (lo_b + mid_b) + rows_b + static_cast<size_t>(kBlockHsWarps) * 2 * (2 * 4 * f.W * 4);
+    return (2 * (lo_b + mid_b)) % 128 == 0 && smem <= 110 * 1024;  // 2 blocks per SM
+}
+
 // block kernel applicable?  exact x2 / x4 scales, W/4 in {8, 16, 32}, bulk-copy alignment, everything fits
 static bool block_geometry(const FuseSrc& f, const float* out, BlockWalk& g, int& sl, int& sm, int& n_warps, size_t& smem) {
     if (f.W % 4 != 0 || f.H % 4 != 0) return false;
@@ -425,6 +652,24 @@ template <bool DECODE>
 static void launch_fuse_block(const FuseSrc& f, const BlockWalk& g, int sl, int sm, int n_warps, size_t smem, int n_maps, float* out,
                               const float* tgt_xy, int K, double thr, float* pred_xy, float* maxvals, int32_t* counts,
                               double* acc_out, Workspace* ws, cudaStream_t s) {
+    {
+        size_t smem_hs = 0;
+        if (sl == 4 && sm == 2 && block_hs_geometry(f, g, smem_hs)) {  // configs[3]: 32 / 64 / 128
+            static bool configured[16] = {};
+            int dev = 0;
+            cudaGetDevice(&dev);
+            if (dev < 0 || dev >= 16 || !configured[dev]) {
+                cudaFuncSetAttribute(fuse_block_hs_kernel<4, 2, DECODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_hs));
+                if (dev >= 0 && dev < 16) configured[dev] = true;
+            }
+            int sms = hp_device_sm_count();
+            if (sms <= 0) sms = 148;
+            const int grid_hs = n_maps < 2 * sms ? n_maps : 2 * sms;
+            fuse_block_hs_kernel<4, 2, DECODE><<<grid_hs, 32 * kBlockHsWarps, smem_hs, s>>>(f, n_maps, out, tgt_xy, K, thr, pred_xy, maxvals,
+                                                                                       counts, acc_out, ws);
+            return;
+        }
+    }
     const int grid = rows_grid(n_maps);
     const int nt = 32 * n_warps;
     const char* shape = getenv("HP_FUSE_SHAPE");
