@@ -354,7 +354,7 @@ extern "C" HP_API int hp_regdisp_fwd(const float* y, const float* y_adv, const f
     a.ws = static_cast<Workspace*>(workspace);
     const bool vec = (ow % 4 == 0) && aligned16(y_adv) && (!fused || aligned16(fused));
     if (vec && !generic_forced()) {
-        int rc = launch_regdisp_dense(a, s, "hp_regdisp_fwd");  // x6 / rd4 'max' on 4096-pixel maps
+        int rc = launch_regdisp_dense<RD_FWD>(a, s, "hp_regdisp_fwd");  // x6 / rd4 'max' on 4096-pixel maps
         if (rc != 1) return rc;
         rc = launch_regdisp_staged<RD_FWD>(a, s, "hp_regdisp_fwd");
         if (rc != 1) return rc;
@@ -389,7 +389,9 @@ extern "C" HP_API int hp_regdisp_bwd(const float* y_adv, const float* fused, con
     a.grad_out = grad_out; a.grad_kind = grad_kind; a.grad_in = grad_in;
     const bool vec = (ow % 4 == 0) && aligned16(y_adv) && aligned16(grad_in) && (!fused || aligned16(fused));
     if (vec && !generic_forced()) {
-        const int rc = launch_regdisp_staged<RD_BWD>(a, static_cast<cudaStream_t>(stream), "hp_regdisp_bwd");
+        int rc = launch_regdisp_dense<RD_BWD>(a, static_cast<cudaStream_t>(stream), "hp_regdisp_bwd");  // x6 / rd4 'max', 4096-pixel maps
+        if (rc != 1) return rc;
+        rc = launch_regdisp_staged<RD_BWD>(a, static_cast<cudaStream_t>(stream), "hp_regdisp_bwd");
         if (rc != 1) return rc;
     }
     return launch_regdisp<RD_BWD>(a, vec, static_cast<cudaStream_t>(stream), "hp_regdisp_bwd");

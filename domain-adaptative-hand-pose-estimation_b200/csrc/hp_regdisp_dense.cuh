@@ -71,7 +71,10 @@ struct RDDShared {
     float w[2][kRDDMaxK];
     float cu[2], culg[2];     // per sample: sum (lp + eps), sum (lp + eps) lg2 (lp + eps)
     float tab[kRDDMaxTab];
-    float xch[2][16][8];      // [map parity][consumer warp]: the warp's partial sums of a map
+    union {
+        float xch[2][16][8];          // forward: [map parity][consumer warp]: the warp's partial sums of a map
+        RDSMeta meta[2][kRDDMaxK];    // backward: per sample slot and joint {coef, -lse log2 e, 1 / S, M}
+    };
     float xmx[2][16];         // fused: max g of the warp's part
     unsigned long long acc[kFxAccWords];
 };
@@ -206,7 +209,7 @@ __device__ __noinline__ void rdd_softmax_exact(const float4* __restrict__ P4, in
     s_out = acc;
 }
 
-template <bool FUSED, int GW>
+template <bool FUSED, int GW, int TASK>
 __global__ void __launch_bounds__(32 * (RDDShape<FUSED, GW>::W + 1), 1) regdisp_dense_kernel(const RDArgs a) {
     extern __shared__ __align__(128) unsigned char s_rdd[];
     __shared__ RDDShared sh;
@@ -236,12 +239,22 @@ __global__ void __launch_bounds__(32 * (RDDShape<FUSED, GW>::W + 1), 1) regdisp_
     // per SM waits microseconds, and the first lp is on every consumer's critical path)
     Centre cn = Centre{0, 0};
     float wn = 1.0f;
+    RDSMeta mn = RDSMeta{0.f, 0.f, 0.f, 1.f};  // backward only
     auto load_sample = [&](int s) {
         if (lane < K && s < a.B) {
             const int map = s * K + lane;
             cn.x = a.centres[2 * map + 0];
             cn.y = a.centres[2 * map + 1];
             wn = a.weight ? a.weight[map] : 1.0f;
+            if (TASK == RD_BWD) {  // d/dp = coef (softmax(p) - u / S), coef = grad_out w / (B K) resp. / K   (appendix A6)
+                const bool scalar = a.grad_kind == HP_GRAD_SCALAR;
+                const float go = scalar ? a.grad_out[0] : a.grad_out[s];
+                const float denom = scalar ? static_cast<float>(a.B) * static_cast<float>(K) : static_cast<float>(K);
+                mn.a = go * wn / denom;
+                mn.b = -a.stats[3 * map + 0] * kLog2e;
+                mn.c = 1.0f / a.stats[3 * map + 1];
+                mn.d = a.stats[3 * map + 2];
+            }
         }
     };
     const uint32_t lpf_u32 = smem_addr(sh.lp_full), lpe_u32 = smem_addr(sh.lp_empty);
@@ -298,6 +311,7 @@ __global__ void __launch_bounds__(32 * (RDDShape<FUSED, GW>::W + 1), 1) regdisp_
     if (warp == W && lane < K) {  // waits for the loads issued at kernel entry
         sh.c[0][lane] = cn;
         sh.w[0][lane] = wn;
+        if (TASK == RD_BWD) sh.meta[0][lane] = mn;
     }
     __syncthreads();
     if (trace && warp == W && lane == 0) trace[8 + 16 * kRDDTraceMaps * 8] = rdd_now();
@@ -341,7 +355,7 @@ __global__ void __launch_bounds__(32 * (RDDShape<FUSED, GW>::W + 1), 1) regdisp_
         for (int it = it0; it < it1; ++it) {
             const float4 v = clip01_4(lp4[it * 32 + lane]);
             lp4[it * 32 + lane] = v;
-            if (!FUSED) {
+            if (!FUSED && TASK == RD_FWD) {
                 scratch[it * 32 + lane] = rdd_term_u(v, eps);
                 scratch[1024 + it * 32 + lane] = rdd_term_ulg(v, eps);
             }
@@ -358,7 +372,7 @@ __global__ void __launch_bounds__(32 * (RDDShape<FUSED, GW>::W + 1), 1) regdisp_
         if (n_samples > 1) load_sample(sample0 + 1);
         const RDDSlots<kTileMaxPatch>& sl = s6;
         if (n_samples > 0) {  // the first sample: built by all warps above; its constants in the canonical order
-            if (!FUSED) {
+            if (!FUSED && TASK == RD_FWD) {
                 const float* scratch = lp_base + kRDDPixels;
                 float su = 0.f, sulg = 0.f;
 #pragma unroll 8
@@ -378,6 +392,7 @@ __global__ void __launch_bounds__(32 * (RDDShape<FUSED, GW>::W + 1), 1) regdisp_
             const int slot = r & 1;
             const Centre cc = cn;
             const float ww = wn;
+            const RDSMeta mm = mn;
             if (r + 1 < n_samples) load_sample(sample0 + r + 1);
             if (r >= 2) mbar_wait_backoff(lpe_u32 + 8 * slot, static_cast<uint32_t>((r >> 1) - 1) & 1u, 100);
             if (trace && lane == 0 && r < 8) trace[8 + 16 * kRDDTraceMaps * 8 + 2 * r] = rdd_now();
@@ -408,12 +423,12 @@ __global__ void __launch_bounds__(32 * (RDDShape<FUSED, GW>::W + 1), 1) regdisp_
             for (int it = 0; it < 32; ++it) {
                 const float4 v = clip01_4(lp4[it * 32 + lane]);
                 lp4[it * 32 + lane] = v;
-                if (!FUSED) {
+                if (!FUSED && TASK == RD_FWD) {
                     su += rdd_term_u(v, eps);
                     sulg += rdd_term_ulg(v, eps);
                 }
             }
-            if (!FUSED) {
+            if (!FUSED && TASK == RD_FWD) {
                 const float rr = warp_sum3_scattered(su, sulg, 0.0f, lane);
                 if (lane == 0) sh.cu[slot] = rr;
                 if (lane == 8) sh.culg[slot] = rr;
@@ -421,6 +436,7 @@ __global__ void __launch_bounds__(32 * (RDDShape<FUSED, GW>::W + 1), 1) regdisp_
             if (lane < K) {
                 sh.c[slot][lane] = cc;
                 sh.w[slot][lane] = ww;
+                if (TASK == RD_BWD) sh.meta[slot][lane] = mm;
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(lpf_u32 + 8 * slot);
@@ -468,7 +484,67 @@ __global__ void __launch_bounds__(32 * (RDDShape<FUSED, GW>::W + 1), 1) regdisp_
             int freed0;  // first slot freed by this map (UPM consecutive slots)
             unsigned long long* wt = (trace && lane == 0 && jj < kRDDTraceMaps) ? trace + 8 + (warp * kRDDTraceMaps + jj) * 8 : nullptr;
             if (wt) wt[0] = rdd_now();
-            if (!FUSED) {
+            if (TASK == RD_BWD) {
+                // ---- backward: d/dp = coef (softmax(p) - u / S),  u = g / M + eps   -----------------
+                const int sf = FUSED ? wait_unit() : 0, sp = wait_unit();
+                freed0 = FUSED ? sf : sp;
+                const float4* P4 = reinterpret_cast<const float4*>(my_slots + sp * kMapBytes);
+                const float* P = reinterpret_cast<const float*>(P4);
+                const float4* F4 = reinterpret_cast<const float4*>(my_slots + sf * kMapBytes);  // FUSED only
+                const float* F = reinterpret_cast<const float*>(F4);
+                if (wt) wt[1] = rdd_now();
+                advance_to(r);
+                if (wt) wt[2] = rdd_now();
+                const Centre ck = sh.c[slot][k];
+                const RDSMeta meta = sh.meta[slot][k];
+                const float coef = meta.a, lb = meta.b, invS = meta.c, M = meta.d;
+                const float invM = (M == 1.0f) ? 1.0f : __frcp_rn(M);
+                const float k1 = -coef * (invM * invS), k0 = -coef * (eps * invS);  // -coef u / S = k1 g + k0
+                float* gout = a.grad_in + static_cast<size_t>(map) * kRDDPixels;
+                // the own patch (this warp's slots): exact values, written after the generic pass
+                float gk[NSL];
+                int poff[NSL];
+#pragma unroll
+                for (int kk = 0; kk < NSL; ++kk) {
+                    const int x = ck.x + sl.dx[kk], y = ck.y + sl.dy[kk];
+                    const bool in = static_cast<unsigned>(x) < static_cast<unsigned>(ow) && static_cast<unsigned>(y) < static_cast<unsigned>(oh);
+                    const int off = in ? y * ow + x : 0;
+                    float g = clip01(__fsub_rn(lp[off], __fmul_rn(sl.t[kk], 10.0f)));
+                    if (FUSED) g = clip01(__fsub_rn(__fadd_rn(g, F[off]), __fmul_rn(sl.t[kk], 100.0f)));
+                    gk[kk] = fmaf(coef, ex2_approx(fmaf(P[off], kLog2e, lb)), fmaf(g, k1, k0));
+                    poff[kk] = in ? off : -1;
+                }
+                if (wt) wt[3] = rdd_now();
+                const float2 lb2 = make_float2(lb, lb), k12 = make_float2(k1, k1), k02 = make_float2(k0, k0), c2 = make_float2(coef, coef);
+                float4* out4 = reinterpret_cast<float4*>(gout);
+#pragma unroll
+                for (int it = h * IT; it < (h + 1) * IT; ++it) {
+                    const float4 v = P4[it * 32 + lane];
+                    float4 g = LP4[it * 32 + lane];
+                    if (FUSED) g = clip01_4(add4(g, F4[it * 32 + lane]));
+                    const float2 a0 = __ffma2_rn(make_float2(v.x, v.y), l2e, lb2), a1 = __ffma2_rn(make_float2(v.z, v.w), l2e, lb2);
+                    const float2 q0 = __ffma2_rn(make_float2(g.x, g.y), k12, k02), q1 = __ffma2_rn(make_float2(g.z, g.w), k12, k02);
+                    const float2 r0 = __ffma2_rn(c2, make_float2(ex2_approx(a0.x), ex2_approx(a0.y)), q0);
+                    const float2 r1 = __ffma2_rn(c2, make_float2(ex2_approx(a1.x), ex2_approx(a1.y)), q1);
+                    stg_stream4(out4 + it * 32 + lane, make_float4(r0.x, r0.y, r1.x, r1.y));
+                }
+                if (wt) wt[4] = rdd_now();
+                // every warp of the group has issued its stores of the map (and read the slots out): the patch pixels are
+                // overwritten with their exact values (ordered behind the generic stores by the barrier)
+                group_barrier(bar_id, 32 * G);
+#pragma unroll
+                for (int kk = 0; kk < NSL; ++kk)
+                    if (poff[kk] >= 0) gout[poff[kk]] = gk[kk];
+                if (leader && lane == 0) {
+                    int s = freed0;
+                    for (int c = 0; c < UPM; ++c) {
+                        if (u_load + c < n_units) request(u_load + c, s);
+                        s = (s + 1 == NS) ? 0 : s + 1;
+                    }
+                }
+                if (wt) wt[5] = rdd_now();
+                u_load += UPM;
+            } else if (!FUSED) {
                 const int sp = wait_unit();
                 freed0 = sp;
                 const float4* P4 = reinterpret_cast<const float4*>(my_slots + sp * kMapBytes);
@@ -708,7 +784,7 @@ __global__ void __launch_bounds__(32 * (RDDShape<FUSED, GW>::W + 1), 1) regdisp_
             k += NG;
         }
         advance_to(n_samples);  // release the remaining samples (keeps the arrival counts of the empty barriers whole)
-        if (lane == 0 && a.mean) fx_reg_flush(fx, sh.acc);
+        if (TASK == RD_FWD && lane == 0 && a.mean) fx_reg_flush(fx, sh.acc);
     }
 
     // ---- epilogue: block sum -> workspace, the last block finalises 'mean' / the per-sample means ----------------------
@@ -716,7 +792,7 @@ __global__ void __launch_bounds__(32 * (RDDShape<FUSED, GW>::W + 1), 1) regdisp_
         __syncthreads();
         if (threadIdx.x == 0) trace[1] = rdd_now();
     }
-    if (a.mean == nullptr && a.per_sample == nullptr) return;
+    if (TASK != RD_FWD || (a.mean == nullptr && a.per_sample == nullptr)) return;
     __syncthreads();
     if (a.mean && threadIdx.x < kFxAccWords && sh.acc[threadIdx.x] != 0ull) atomicAdd(&a.ws->acc[threadIdx.x], sh.acc[threadIdx.x]);
     if (last_block_arrives(&a.ws->counter, gridDim.x)) {
@@ -726,7 +802,7 @@ __global__ void __launch_bounds__(32 * (RDDShape<FUSED, GW>::W + 1), 1) regdisp_
     }
 }
 
-template <bool FUSED, int GW>
+template <bool FUSED, int GW, int TASK>
 static int launch_rdd_shape(const RDArgs& a, int sms, cudaStream_t stream, const char* who) {
     constexpr size_t smem = RDDShape<FUSED, GW>::kSmem;
     static bool attr_done_dev[64] = {};
@@ -734,7 +810,7 @@ static int launch_rdd_shape(const RDArgs& a, int sms, cudaStream_t stream, const
     cudaGetDevice(&dev);
     bool& attr_done = attr_done_dev[dev & 63];
     if (!attr_done) {
-        const cudaError_t e = cudaFuncSetAttribute(regdisp_dense_kernel<FUSED, GW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        const cudaError_t e = cudaFuncSetAttribute(regdisp_dense_kernel<FUSED, GW, TASK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                    static_cast<int>(smem));
         if (e != cudaSuccess) return fail(static_cast<int>(e), "%s: %s", who, cudaGetErrorString(e));
         attr_done = true;
@@ -755,8 +831,8 @@ static int launch_rdd_shape(const RDArgs& a, int sms, cudaStream_t stream, const
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // behind the decode launch of hp_regdisp_fwd
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    const cudaError_t e = cudaLaunchKernelEx(&cfg, regdisp_dense_kernel<FUSED, GW>, a);
+    cfg.numAttrs = (TASK == RD_FWD) ? 1 : 0;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, regdisp_dense_kernel<FUSED, GW, TASK>, a);
     if (e != cudaSuccess) return fail(static_cast<int>(e), "%s: %s", who, cudaGetErrorString(e));
     return launch_status(who);
 }
@@ -765,8 +841,9 @@ static int launch_rdd_shape(const RDArgs& a, int sms, cudaStream_t stream, const
 static unsigned long long* g_rdd_trace = nullptr;
 static size_t g_rdd_trace_words = 0;
 
-// forward, mode 'max', x6 / rd4 recipes on 4096-pixel maps; returns 1 when the case is not covered (the caller takes
+// forward / backward, mode 'max', x6 / rd4 recipes on 4096-pixel maps; returns 1 when the case is not covered (the caller takes
 // the register-slice kernel), 0 when launched.  HP_RD_DENSE=0 keeps the old kernel (comparison runs).
+template <int TASK>
 static int launch_regdisp_dense(RDArgs a, cudaStream_t stream, const char* who) {
     static const bool on = []() {
         const char* e = getenv("HP_RD_DENSE");
@@ -790,8 +867,8 @@ static int launch_regdisp_dense(RDArgs a, cudaStream_t stream, const char* who) 
         const char* e = getenv("HP_RDD_G");
         return e ? atoi(e) : 0;
     }();
-    if (fused) return g_env == 2 ? launch_rdd_shape<true, 2>(a, sms, stream, who) : launch_rdd_shape<true, 4>(a, sms, stream, who);
-    return launch_rdd_shape<false, 2>(a, sms, stream, who);  // (4 warps per map measured slower: 82 vs 75 us with the decode)
+    if (fused) return g_env == 2 ? launch_rdd_shape<true, 2, TASK>(a, sms, stream, who) : launch_rdd_shape<true, 4, TASK>(a, sms, stream, who);
+    return launch_rdd_shape<false, 2, TASK>(a, sms, stream, who);  // (4 warps per map measured slower: 82 vs 75 us with the decode)
 }
 
 }  // namespace hp
