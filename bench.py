@@ -802,6 +802,7 @@ def run_fuse_arm(args, wl):
     dt_t = torch.tensor([dt], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(dt_t, op=dist.ReduceOp.MAX)
+    parity = fuse_parity_check(h, hp, ev, lo[0], mid[0], hi[0], tgt[0]) if world > 1 else None
     clocks = h.finish()
     peak, peak_src = measured_hbm_peak()
     gbs = n * bytes_map / (ms * 1e-3) / 1e9
@@ -817,7 +818,7 @@ def run_fuse_arm(args, wl):
                                           if world > 1 else "single GPU, no collective"},
                 "regions": region_stats(reg, args.steps),
                 "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
-                             "traffic": recorded_traffic(args.workload), "kernel": "hp::fuse_block_kernel (fuse + decode + PCK)",
+                             "traffic": recorded_traffic(args.workload), "kernel": "hp::fuse_block_hs_kernel (fuse + decode + PCK; the three sources staged by the copy engine)",
                              "algorithmic_bytes_per_launch": n * bytes_map, "kernel_ms": ms, "peak_source": peak_src},
                 "cpu_baseline": cpu_baseline,
                 "e2e": {"value": maps * e2e_steps / float(dt_t.item()), "unit": UNIT,
@@ -825,11 +826,50 @@ def run_fuse_arm(args, wl):
                         "steps": e2e_steps, "ms_per_step": 1e3 * float(dt_t.item()) / e2e_steps,
                         "api": "pinned host lo/mid/hi/target_xy -> .to(device) -> MultiscaleEval -> acc, pred_xy .cpu()",
                         "check_avg_acc": float(acc_h[K].item())},
+                "parity_check": parity,
                 "clocks": clocks, "gpu_launches": args.steps * (2 if world > 1 else 1)}
         sys.stdout.write(json.dumps(line) + "\n")
         sys.stdout.flush()
     h.shutdown()
     return 0
+
+
+def fuse_parity_check(h, hp, ev, lo, mid, hi, tgt):
+    """Untimed, N > 1: the sharded fuse + decode + PCK step (counts summed over the ranks) on a slice of every rank's
+    inputs against rank 0's single-GPU step on the gathered slices: integer hit / valid counts, the float64 accuracy
+    vector and the decoded coordinates of rank 0's slice, bit for bit (keypoint_detection.py:63-92 on the whole batch)."""
+    torch, dist, dev, world, rank = h.torch, h.dist, h.dev, h.world, h.rank
+    cB = min(lo.shape[0], 64)
+    parts = [t[:cB].contiguous() for t in (lo, mid, hi, tgt)]
+    with torch.no_grad():
+        acc, xy, counts = ev(*parts)
+        torch.cuda.synchronize()
+        gathered = []
+        for t in parts:
+            g = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(g, t)
+            gathered.append(torch.cat(g, 0))
+        ok, detail = True, {}
+        if rank == 0:
+            acc1, xy1, counts1 = ev(*gathered, local=True)
+            torch.cuda.synchronize()
+            detail["counts_bit_equal"] = bool(torch.equal(counts, counts1))
+            detail["acc_bit_equal"] = bool(torch.equal(acc.view(torch.int64), acc1.view(torch.int64)))
+            detail["pred_xy_bit_equal"] = bool(torch.equal(xy, xy1[:cB]))
+            ok = all(detail.values())
+            detail["avg_acc"] = float(acc1[ev.K].item())
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    tot = counts.clone()
+    dist.broadcast(tot, 0)
+    same = torch.tensor([1 if torch.equal(tot, counts) else 0], device=dev)
+    dist.all_reduce(same, op=dist.ReduceOp.MIN)
+    detail.update({"ok": bool(flag.item()) and bool(same.item()), "all_ranks_hold_rank0_totals": bool(same.item()),
+                   "ranks": world, "samples": world * cB,
+                   "what": f"sharded fuse + decode + PCK over {world} ranks x {cB} samples vs rank 0's single-GPU step on the "
+                           f"gathered {world * cB}-sample batch: int32 hit / valid counts, float64 accuracy vector bits, "
+                           f"decoded coordinates of rank 0's slice"})
+    return detail
 
 
 def main():

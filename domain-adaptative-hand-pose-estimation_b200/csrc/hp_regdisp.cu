@@ -329,7 +329,8 @@ extern "C" HP_API int hp_regdisp_fwd(const float* y, const float* y_adv, const f
     }
     // x1 / x5 recipes (constant target outside the own patch) on 32x32 / 16x16 heads, both modes, no fused map: decode +
     // loss in ONE kernel as well (hp_regdisp_sparse.cuh)
-    if ((variant == HP_RD_X1 || variant == HP_RD_X5) && fused == nullptr && H * W == 4096 && W % 4 == 0 &&
+    const float* fused_used = (mode == HP_MODE_MAX && variant == HP_RD_X5) ? fused : nullptr;  // ('min' / x1 ignore y_adv2)
+    if ((variant == HP_RD_X1 || variant == HP_RD_X5) && (fused_used == nullptr || aligned16(fused_used)) && H * W == 4096 && W % 4 == 0 &&
         (oh * ow == 1024 || oh * ow == 256) && ow % 4 == 0 && aligned16(y) && aligned16(y_adv) &&
         (2 * tmp + 1) * (2 * tmp + 1) <= 32 * kTileMaxPatch && (2 * tmp + 1) * (2 * tmp + 1) < oh * ow && !generic_forced() &&
         rd_min_fused_enabled()) {
@@ -341,6 +342,7 @@ extern "C" HP_API int hp_regdisp_fwd(const float* y, const float* y_adv, const f
         m.per_map = per_map; m.per_sample = per_sample; m.mean = mean; m.stats = stats; m.centres = centres;
         m.ws = static_cast<Workspace*>(workspace);
         sp.oh = oh; sp.ow = ow; sp.shift = shift; sp.want_gf = (mode == HP_MODE_MAX) ? 1 : 0; sp.bg = sp.want_gf ? 1.0f : 0.0f;
+        sp.fused = fused_used;
         sp.ubg = sp.bg + epsilon;
         sp.ubg_log_ubg = sp.ubg > 0.0f ? sp.ubg * std::log(sp.ubg) : 0.0f;
         const int rc = launch_regdisp_sparse(sp, s, "hp_regdisp_fwd");

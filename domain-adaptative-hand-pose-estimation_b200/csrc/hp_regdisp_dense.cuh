@@ -1,4 +1,5 @@
-// hp_regdisp_dense.cuh - RegressionDisparityx6 / RegressionDisparity4 forward with mode='max' on 4096-pixel maps
+// hp_regdisp_dense.cuh - RegressionDisparityx6 / RegressionDisparity4 / RegressionDisparity (base) with mode='max' on
+// 4096-pixel maps, forward and backward
 // (configs[2] of BASELINE.json: 512 x 21 x 64 x 64; regda_7.py:3609-3632, regda_4.py RD4), with or without the fused
 // map y_adv2 (train1.py:419-421).  The ground-false label of joint k,
 //     lp   = clip(sum_j G_j)                      per SAMPLE (G_j = Gaussian at joint j's decoded centre)
@@ -119,6 +120,19 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 __device__ __forceinline__ float rdd_term_u(float4 v, float eps) { return ((v.x + eps) + (v.y + eps)) + ((v.z + eps) + (v.w + eps)); }
 __device__ __forceinline__ float rdd_term_ulg(float4 v, float eps) {
     return (ulg2(v.x + eps) + ulg2(v.y + eps)) + (ulg2(v.z + eps) + ulg2(v.w + eps));
+}
+
+// un-normalised ground-false value of joint k at an own-patch pixel, no fused map: x6 / rd4 clip(lp - 10 t); base
+// clip(sum_{j != k} G_j) with the own Gaussian left out explicitly (no cancellation; regda_4.py:83-84)
+__device__ __forceinline__ float rdd_patch_value(int variant, float lpv, float t, int k, int K, int x, int y, const float* s_tab, int tmp,
+                                                 const Centre* s_c) {
+    if (variant == HP_RD_BASE) {
+        float sum = 0.0f;
+        for (int j = 0; j < K; ++j)
+            if (j != k) sum += patch_at(s_tab, tmp, s_c[j], x, y);
+        return clip01(sum);
+    }
+    return clip01(__fsub_rn(lpv, __fmul_rn(t, 10.0f)));
 }
 
 // per-lane patch slots, lane-constant for the whole kernel: offset from the centre (dx = 1 << 20: unused) and value
@@ -509,7 +523,7 @@ __global__ void __launch_bounds__(32 * (RDDShape<FUSED, GW>::W + 1), 1) regdisp_
                     const int x = ck.x + sl.dx[kk], y = ck.y + sl.dy[kk];
                     const bool in = static_cast<unsigned>(x) < static_cast<unsigned>(ow) && static_cast<unsigned>(y) < static_cast<unsigned>(oh);
                     const int off = in ? y * ow + x : 0;
-                    float g = clip01(__fsub_rn(lp[off], __fmul_rn(sl.t[kk], 10.0f)));
+                    float g = rdd_patch_value(a.variant, lp[off], sl.t[kk], k, K, x, y, sh.tab, tmp, sh.c[slot]);
                     if (FUSED) g = clip01(__fsub_rn(__fadd_rn(g, F[off]), __fmul_rn(sl.t[kk], 100.0f)));
                     gk[kk] = fmaf(coef, ex2_approx(fmaf(P[off], kLog2e, lb)), fmaf(g, k1, k0));
                     poff[kk] = in ? off : -1;
@@ -564,7 +578,7 @@ __global__ void __launch_bounds__(32 * (RDDShape<FUSED, GW>::W + 1), 1) regdisp_
                     const Centre cj = sh.c[slot][lane];
                     outside = abs(cj.x - ck.x) > tmp || abs(cj.y - ck.y) > tmp;
                 }
-                const bool fast = __any_sync(0xffffffffu, outside) || a.variant == HP_RD_RD4;  // rd4 does not normalise
+                const bool fast = __any_sync(0xffffffffu, outside) || a.variant != HP_RD_X6;  // rd4 and base do not normalise
                 // ---- own patch (this warp's slots): exact recipe minus the generic term --------------------------------
                 float c_u = 0.f, c_up = 0.f, c_ulg = 0.f;
 #pragma unroll
@@ -573,7 +587,7 @@ __global__ void __launch_bounds__(32 * (RDDShape<FUSED, GW>::W + 1), 1) regdisp_
                     const bool in = static_cast<unsigned>(x) < static_cast<unsigned>(ow) && static_cast<unsigned>(y) < static_cast<unsigned>(oh);
                     const int off = in ? y * ow + x : 0;
                     const float lpv = lp[off], pk = P[off];
-                    const float gex = clip01(__fsub_rn(lpv, __fmul_rn(sl.t[kk], 10.0f)));
+                    const float gex = rdd_patch_value(a.variant, lpv, sl.t[kk], k, K, x, y, sh.tab, tmp, sh.c[slot]);
                     const float du = in ? gex - lpv : 0.0f;
                     const float dl = ulg2(gex + eps) - ulg2(lpv + eps);
                     c_u += du;
@@ -850,7 +864,7 @@ static int launch_regdisp_dense(RDArgs a, cudaStream_t stream, const char* who) 
         return !(e && e[0] == '0');
     }();
     if (!on) return 1;
-    if (a.mode != HP_MODE_MAX || (a.variant != HP_RD_X6 && a.variant != HP_RD_RD4)) return 1;
+    if (a.mode != HP_MODE_MAX || (a.variant != HP_RD_X6 && a.variant != HP_RD_RD4 && a.variant != HP_RD_BASE)) return 1;
     if (a.oh * a.ow != kRDDPixels || a.ow % 4 != 0 || a.K > kRDDMaxK || a.tmp > 6) return 1;
     if ((2 * a.tmp + 1) * (2 * a.tmp + 1) > 32 * kTileMaxPatch) return 1;
     static int sms = 0;

@@ -1,5 +1,5 @@
-// hp_regdisp_sparse.cuh - RegressionDisparityx1 / x5 (and x2 / x3 / x4, which share the x1 recipe) forward, both modes,
-// without a fused map, as ONE kernel: the pseudo-label decode of y[b,k] (64x64 or any 4096-pixel map) and the KL loss of
+// hp_regdisp_sparse.cuh - RegressionDisparityx1 / x5 (and x2 / x3 / x4, which share the x1 recipe) forward, both modes
+// (x5 'max' also WITH the fused map y_adv2, see the FUSED instantiation below), as ONE kernel: the pseudo-label decode of y[b,k] (64x64 or any 4096-pixel map) and the KL loss of
 // the LOW-RESOLUTION head y_adv[b,k] (32x32: x5, PseudoLabelGenerator03; 16x16: x1, PseudoLabelGenerator01) against
 //   'min':  gt = Gaussian at (decoded centre >> shift)                          regda_7.py:3250-3268, 3529-3561
 //   'max':  gf = clip(1 - 10 gt)  (its maximum is 1: no normalisation needed)   regda_7.py:3036-3037, 3198-3199
@@ -19,18 +19,22 @@ struct RDSparseArgs {
     int oh, ow, shift;  // the head's size, centre = decoded coordinate >> shift
     float bg;           // the target outside the own patch: 0 ('min') or 1 ('max')
     int want_gf;        // 'max': the patch holds clip(1 - 10 t)
+    const float* fused; // x5 'max' with the fused map y_adv2 (train1.py:421 `target0`): g = clip(clip(1 - 10 t) + f - 100 t),
+                        // divided by its maximum (regda_7.py:3548-3553) - FUSED instantiation only
     float ubg, ubg_log_ubg;  // bg + eps, (bg + eps) ln (bg + eps)
 };
 
-// NITA: iterations (of 32 float4) over the head: oh*ow / 128
-template <int W, int BPS, int NITA>
+// NITA: iterations (of 32 float4) over the head: oh*ow / 128.  FUSED: a third buffer receives the fused map; the target
+// then depends on the pixel everywhere (clip(1 + f) outside the patch), so the head takes two passes: g (written over f)
+// and its maximum, then the sums of u = g / M + eps - the recipe of hp_regdisp_dense.cuh with a per-sample label of 1.
+template <int W, int BPS, int NITA, bool FUSED>
 __global__ void __launch_bounds__(32 * W, BPS) regdisp_sparse_kernel(const RDSparseArgs s) {
     extern __shared__ __align__(128) unsigned char s_rds2[];
     __shared__ PatchSlot s_patch[kTileMaxPatch * 32];
     __shared__ unsigned long long s_acc[kFxAccWords];
     const RDMinArgs& a = s.m;
     constexpr int NITC = 32;
-    constexpr uint32_t kYBytes = NITC * 512, kABytes = NITA * 512, kStage = kYBytes + kABytes;
+    constexpr uint32_t kYBytes = NITC * 512, kABytes = NITA * 512, kStage = kYBytes + (FUSED ? 2 : 1) * kABytes;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_local = (a.n_maps - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
     const int n_mine = (n_local > warp) ? (n_local - warp + W - 1) / W : 0;
@@ -45,6 +49,7 @@ __global__ void __launch_bounds__(32 * W, BPS) regdisp_sparse_kernel(const RDSpa
         mbar_arrive_expect_tx(bar_u32, kStage);
         bulk_load(stage_u32, a.y + map * a.HW, kYBytes, bar_u32, pol);
         bulk_load(stage_u32 + kYBytes, a.y_adv + map * ohw, kABytes, bar_u32, pol);
+        if (FUSED) bulk_load(stage_u32 + kYBytes + kABytes, s.fused + map * ohw, kABytes, bar_u32, pol);
     };
 
     // ---- prologue: barrier, the small loads, the first copies, then the patch table (order: see hp_pipeline_bulk.cuh) ----
@@ -71,7 +76,7 @@ __global__ void __launch_bounds__(32 * W, BPS) regdisp_sparse_kernel(const RDSpa
             sl.dy = static_cast<int>(ry) - a.tmp;
             const float t = a.tab[sl.dx * sl.dx + sl.dy * sl.dy];
             // the patch's target value: the Gaussian ('min') or clip(1 - 10 t) ('max'; regda_7.py:3036, :3198)
-            sl.t = s.want_gf ? clip01(__fsub_rn(1.0f, __fmul_rn(t, 10.0f))) : t;
+            sl.t = (s.want_gf && !FUSED) ? clip01(__fsub_rn(1.0f, __fmul_rn(t, 10.0f))) : t;
             const float u = sl.t + a.eps;
             sl.ulogu = (u != 0.0f) ? u * logf(u) : 0.0f;
         }
@@ -127,6 +132,92 @@ __global__ void __launch_bounds__(32 * W, BPS) regdisp_sparse_kernel(const RDSpa
         a.wdiv.divmod(static_cast<uint32_t>(am.i), qy, qx);
         const bool keep = am.v > 0.0f;  // NaN -> (0, 0)  (keypoint_detection.py:31-34)
         const int cx = keep ? static_cast<int>(qx) >> s.shift : 0, cy = keep ? static_cast<int>(qy) >> s.shift : 0;
+        if (FUSED) {
+            float* F = reinterpret_cast<float*>(my_stage + kYBytes + kABytes);
+            float4* F4 = reinterpret_cast<float4*>(F);
+            const float* P = reinterpret_cast<const float*>(abuf);
+            // ---- own patch: exact un-normalised values into registers, -inf into the fused map (the passes see g = 0) ----
+            float gex[kTileMaxPatch], pk[kTileMaxPatch];
+            int poff[kTileMaxPatch];
+            float mg = -INFINITY;
+#pragma unroll
+            for (int k = 0; k < kTileMaxPatch; ++k) {
+                const PatchSlot sl = s_patch[k * 32 + lane];
+                const int x = cx + sl.dx, yy = cy + sl.dy;
+                const bool in = static_cast<unsigned>(x) < static_cast<unsigned>(s.ow) && static_cast<unsigned>(yy) < static_cast<unsigned>(s.oh);
+                const int off = in ? yy * s.ow + x : 0;
+                float g = clip01(__fsub_rn(1.0f, __fmul_rn(sl.t, 10.0f)));
+                g = clip01(__fsub_rn(__fadd_rn(g, F[off]), __fmul_rn(sl.t, 100.0f)));
+                gex[k] = g;
+                pk[k] = P[off];
+                poff[k] = in ? off : -1;
+                mg = in ? fmaxf(mg, g) : mg;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < kTileMaxPatch; ++k)
+                if (poff[k] >= 0) F[poff[k]] = -INFINITY;
+            __syncwarp();
+            // ---- pass 1: g = clip(1 + f) written over f, its maximum, the softmax maximum ------------------------------------
+            float run = -INFINITY;
+#pragma unroll
+            for (int it = 0; it < NITA; ++it) {
+                const float4 f = F4[it * 32 + lane], v = abuf[it * 32 + lane];
+                const float4 g = clip01_4(add4(make_float4(1.f, 1.f, 1.f, 1.f), f));
+                F4[it * 32 + lane] = g;
+                mg = fmaxf(mg, max4(g));
+                run = fmaxf(run, max4(v));
+            }
+            const float Mp = warp_max_f32(run), M = warp_max_f32(mg);
+            const float invM = (M == 1.0f) ? 1.0f : __frcp_rn(M);
+            const float ms = (Mp == -INFINITY) ? 0.0f : Mp, mb = -ms * kLog2e;
+            // ---- pass 2: the sums of u = g / M + eps, against the softmax maximum in log2 units -----------------------------
+            float sexp = 0.f, su = 0.f, sua = 0.f, sulg = 0.f;
+#pragma unroll
+            for (int it = 0; it < NITA; ++it) {
+                const float4 v = abuf[it * 32 + lane], g = F4[it * 32 + lane];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const float av = fmaf(f4_get(v, c), kLog2e, mb);
+                    const float u = fmaf(f4_get(g, c), invM, a.eps);
+                    sexp += ex2_approx(av);
+                    su += u;
+                    sua = fmaf(u, av, sua);
+                    sulg = fmaf(u, lg2_approx(fmaxf(u, 1.17549435e-38f)), sulg);
+                }
+            }
+            const float u_bg = fmaf(0.0f, invM, a.eps);
+            const float bg_ulg = u_bg * lg2_approx(fmaxf(u_bg, 1.17549435e-38f));
+#pragma unroll
+            for (int k = 0; k < kTileMaxPatch; ++k) {
+                const float uex = fmaf(gex[k], invM, a.eps);
+                const float du = uex - u_bg;
+                if (poff[k] >= 0) {
+                    su += du;
+                    sua = fmaf(du, fmaf(pk[k], kLog2e, mb), sua);
+                    sulg += uex * lg2_approx(fmaxf(uex, 1.17549435e-38f)) - bg_ulg;
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // this lane's writes to the buffer precede the next copy
+            __syncwarp();
+            if (lane == 0 && jj + 1 < n_mine) request(map_l + map_step);
+            const float r = warp_sum3_scattered(sexp, su, sua, lane);
+            const float Sexp = __shfl_sync(0xffffffffu, r, 0), Su = __shfl_sync(0xffffffffu, r, 8), Sua = __shfl_sync(0xffffffffu, r, 16);
+            const float Sulg = warp_sum(sulg);
+            if (lane == 0) {
+                const float lg_se = lg2_approx(Sexp);
+                const float lse = fmaf(lg_se, kLn2, ms);
+                const float L = kLn2 * (__fdividef(Sulg - Sua, Su) - lg2_approx(Su) + lg_se);
+                const float Lw = L * weight;
+                a.per_map[map] = Lw;
+                a.stats[3 * map + 0] = lse;
+                a.stats[3 * map + 1] = Su;
+                a.stats[3 * map + 2] = M;
+                *reinterpret_cast<int2*>(a.centres + 2 * static_cast<size_t>(map)) = make_int2(cx, cy);
+                if (a.mean) fx_acc_add(s_acc, Lw);
+            }
+            continue;
+        }
         PatchSums ps{0.f, 0.f, 0.f, 0.f, 0.f};
         const float* fbuf = reinterpret_cast<const float*>(abuf);
 #pragma unroll
@@ -192,21 +283,21 @@ __global__ void __launch_bounds__(32 * W, BPS) regdisp_sparse_kernel(const RDSpa
     }
 }
 
-template <int W, int BPS, int NITA>
+template <int W, int BPS, int NITA, bool FUSED>
 static int launch_rds2_shape(const RDSparseArgs& s, int sms, cudaStream_t stream, const char* who) {
-    constexpr size_t smem = static_cast<size_t>(W) * (32 * 512 + NITA * 512) + sizeof(uint64_t) * W;
+    constexpr size_t smem = static_cast<size_t>(W) * (32 * 512 + (FUSED ? 2 : 1) * NITA * 512) + sizeof(uint64_t) * W;
     static bool configured[16] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 16 || !configured[dev]) {
-        const cudaError_t e = cudaFuncSetAttribute(regdisp_sparse_kernel<W, BPS, NITA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        const cudaError_t e = cudaFuncSetAttribute(regdisp_sparse_kernel<W, BPS, NITA, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                    static_cast<int>(smem));
         if (e != cudaSuccess) return fail(static_cast<int>(e), "%s: %s", who, cudaGetErrorString(e));
         if (dev >= 0 && dev < 16) configured[dev] = true;
     }
     int grid = sms * BPS;
     if (grid > s.m.n_maps) grid = s.m.n_maps;
-    regdisp_sparse_kernel<W, BPS, NITA><<<grid, 32 * W, smem, stream>>>(s);
+    regdisp_sparse_kernel<W, BPS, NITA, FUSED><<<grid, 32 * W, smem, stream>>>(s);
     return launch_status(who);
 }
 
@@ -218,8 +309,9 @@ static int launch_regdisp_sparse(const RDSparseArgs& s, cudaStream_t stream, con
         if (sms <= 0) sms = 148;
     }
     const int ohw = s.oh * s.ow;
-    if (ohw == 1024) return launch_rds2_shape<5, 2, 8>(s, sms, stream, who);   // 2 x 5 x 20 KB per SM
-    if (ohw == 256) return launch_rds2_shape<4, 3, 2>(s, sms, stream, who);    // 3 x 4 x 17 KB per SM
+    if (s.fused) return ohw == 1024 ? launch_rds2_shape<4, 2, 8, true>(s, sms, stream, who) : 1;  // 2 x 4 x 24 KB per SM
+    if (ohw == 1024) return launch_rds2_shape<5, 2, 8, false>(s, sms, stream, who);   // 2 x 5 x 20 KB per SM
+    if (ohw == 256) return launch_rds2_shape<4, 3, 2, false>(s, sms, stream, who);    // 3 x 4 x 17 KB per SM
     return 1;
 }
 

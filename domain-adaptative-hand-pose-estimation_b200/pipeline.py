@@ -414,9 +414,10 @@ class MultiscaleEval:
         self.collective = collective if self.K <= _lib.PEER_MAX_K else "nccl"
         _lib.load()
 
-    def __call__(self, lo, mid, hi, target_xy):
+    def __call__(self, lo, mid, hi, target_xy, local=False):
         """lo/mid/hi float32 [B,K,h,w] CUDA tensors (hi may be None -> output size = 2x mid); target_xy
-        float32 [B,K,2].  -> (acc_vec float64 [K+2] = acc[K], avg_acc, cnt ; pred_xy [B,K,2] ; counts int32 [2K])."""
+        float32 [B,K,2].  -> (acc_vec float64 [K+2] = acc[K], avg_acc, cnt ; pred_xy [B,K,2] ; counts int32 [2K]).
+        ``local=True``: this rank's batch only, no exchange (the single-GPU reference of a sharded run)."""
         lo = _lib.require_cuda(lo, "MultiscaleEval(lo)")
         mid = _lib.require_cuda(mid, "MultiscaleEval(mid)")
         hi = _lib.require_cuda(hi, "MultiscaleEval(hi)")
@@ -433,7 +434,7 @@ class MultiscaleEval:
                       _lib.ptr(mid), mid.shape[2], mid.shape[3], C.c_float(self.coef[1]), _lib.ptr(hi),
                       C.c_float(self.coef[2]), _lib.ptr(tgt), B, K, H, W, C.c_double(self.thr), _lib.ptr(pred_xy),
                       _lib.ptr(maxvals), _lib.ptr(counts), _lib.ptr(acc), _lib.ptr(ws), _lib.stream_ptr(dev))
-            if hpdist.is_distributed(self.group):
+            if not local and hpdist.is_distributed(self.group):
                 # the path's one collective: integer sum of the 2K hit / valid counts (exact, order-free)
                 if self.collective == "peer":
                     hpdist.shared_peer_exchange(dev, self.group).pck_finalize(counts, K, counts, acc)

@@ -71,7 +71,7 @@ def _compare(y_h, adv_h, f_h, w_h, seed, cls="RegressionDisparityx6", monkeypatc
     return l_gpu
 
 
-@pytest.mark.parametrize("cls", ["RegressionDisparityx6", "RegressionDisparity4"])
+@pytest.mark.parametrize("cls", ["RegressionDisparityx6", "RegressionDisparity4", "RegressionDisparity"])
 def test_clustered_centres_take_the_exact_path(cls, monkeypatch):
     """Samples whose 21 decoded centres all lie within each other's 13x13 patches: max(gf) has no closed form."""
     rs = np.random.RandomState(4101)
@@ -135,6 +135,47 @@ def test_large_logits_take_the_exact_softmax(fused, monkeypatch):
     f_h = rs.uniform(-0.3, 0.6, size=(B, K, 64, 64)).astype(np.float32) if fused else None
     l = _compare(y_h, adv_h, f_h, None, 4404, monkeypatch=monkeypatch)
     assert np.isfinite(l[0]) and np.isfinite(l[1]) and np.isfinite(l[2]) and np.isfinite(l[3]) and np.isnan(l[4]) and np.isfinite(l[5])
+
+
+def test_x5_fused_map_edge_values():
+    """x5 'max' with the fused map on the 32x32 head (train1.py:421; one fused decode+loss kernel): maxima anywhere in
+    (0, 1], an all-zero label (NaN like the reference), NaN / +-inf in the fused map, NaN in the prediction; loss, 'mean'
+    and gradient against the oracle."""
+    rs = np.random.RandomState(4501)
+    B = 7
+    y_h = hp.synth.make_host_batch(4502, B, K, 64, 64)["pred"]
+    adv64 = hp.synth.make_host_batch(4503, B, K, 64, 64)["pred"]
+    adv_h = hp.synth.make_lowres_heads(4504, adv64, (32,))[0]
+    f_h = rs.uniform(-0.9, 0.6, size=(B, K, 32, 32)).astype(np.float32)
+    f_h[1] = -3.0
+    f_h[2] = rs.uniform(-0.9, -0.5, size=(K, 32, 32)).astype(np.float32)    # max(gf) in (0.1, 0.5)
+    f_h[3, 4, 10, 11] = np.nan
+    f_h[3, 5, 0, 0] = np.inf
+    f_h[3, 6, 31, 31] = -np.inf
+    f_h[4] = 0.0
+    adv_h[5, 3, 20, 20] = np.nan
+    w_h = (rs.uniform(size=(B, K, 1)) < 0.85).astype(np.float32)
+    go_h = rs.uniform(0.5, 1.5, size=(B,)).astype(np.float32)
+
+    def run(ns, device):
+        rd = ns.RegressionDisparityx5(ns.PseudoLabelGenerator03(K), ns.JointsKLLoss(reduction="none", epsilon=1e-7))
+        rdm = ns.RegressionDisparityx5(ns.PseudoLabelGenerator03(K), ns.JointsKLLoss(epsilon=1e-7))
+        y, f, w = (torch.from_numpy(a).to(device) for a in (y_h, f_h, w_h))
+        adv = torch.from_numpy(adv_h).to(device).requires_grad_(True)
+        l = rd(y, adv, f, w, "max")
+        l.backward(torch.from_numpy(go_h).to(device))
+        with torch.no_grad():
+            m = float(rdm(y, adv.detach(), f, w, "max"))
+        return l.detach().cpu().numpy(), adv.grad.cpu().numpy(), m
+
+    l_gpu, g_gpu, m_gpu = run(hp, "cuda")
+    l_ref, g_ref, m_ref = run(api.namespace(), "cpu")
+    np.testing.assert_allclose(l_gpu, l_ref, rtol=1e-5, atol=1e-7, equal_nan=True)
+    np.testing.assert_allclose(m_gpu, m_ref, rtol=1e-5, equal_nan=True)
+    assert np.isnan(l_gpu[1]) and np.isnan(l_gpu[3]) and np.isnan(l_gpu[5]) and np.isfinite(l_gpu[0]) and np.isfinite(l_gpu[2])
+    ok = np.isfinite(g_ref)
+    assert np.array_equal(np.isnan(g_gpu), np.isnan(g_ref))
+    np.testing.assert_allclose(g_gpu[ok], g_ref[ok], rtol=1e-5, atol=1e-5 * float(np.abs(g_ref[ok]).max()))
 
 
 def test_mean_matches_generic_kernel_at_scale(monkeypatch):
