@@ -6,7 +6,11 @@
 // temporaries); here a block of 128 threads holds a map in registers (one HBM read), takes the maximum, then the three
 // sums (sum e, sum e*col, sum e*row) against it.  Maps larger than one register tile are walked twice (the second
 // pass is served by L2).  Roofline: HBM, H*W*4 + 8 bytes per map.
+#include <cstdlib>
+
 #include "hp_common.cuh"
+#include "hp_tma.cuh"
+#include "hp_pipeline_parts.cuh"  // warp_sum3_scattered
 
 namespace hp {
 
@@ -84,6 +88,87 @@ __global__ void __launch_bounds__(kSATPM)
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// 4096-pixel maps (64x64): the shape of the fused pipeline kernel (hp_pipeline_bulk.cuh) - persistent blocks of 4 warps,
+// 3 per SM; every warp owns one map at a time in a PRIVATE 16 KB shared-memory stage filled by the copy engine
+// (cp.async.bulk -> mbarrier complete_tx) and re-armed by the warp that drained it; two passes over shared memory
+// (maximum of beta * h, then sum e, sum e * col, sum e * row against it).  The block-per-map kernel above keeps HBM busy
+// only through its own loads (0.59 of the roofline); here 192 KB per SM are requested whatever the warps are doing.
+constexpr int kSAStageWarps = 4, kSAStageBlocks = 3;
+__global__ void __launch_bounds__(32 * kSAStageWarps, kSAStageBlocks)
+    soft_argmax_staged_kernel(const float* __restrict__ heat, int n_maps, FastDiv wdiv, float beta, float scale,
+                              float* __restrict__ out_uv) {
+    extern __shared__ __align__(128) unsigned char s_sa[];
+    constexpr int W = kSAStageWarps, NITC = 32;
+    constexpr uint32_t kBytes = NITC * 512;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_local = (n_maps - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+    const int n_mine = (n_local > warp) ? (n_local - warp + W - 1) / W : 0;
+    unsigned char* my_stage = s_sa + static_cast<size_t>(warp) * kBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_sa + static_cast<size_t>(W) * kBytes) + warp;
+    const uint32_t stage_u32 = smem_addr(my_stage), bar_u32 = smem_addr(bars);
+    const size_t first_map = static_cast<size_t>(blockIdx.x) + static_cast<size_t>(warp) * gridDim.x;
+    const size_t map_step = static_cast<size_t>(gridDim.x) * W;
+    const uint64_t pol = l2_evict_first_policy();
+    if (lane == 0) {
+        mbar_init(bar_u32, 1);
+        mbar_init_fence();
+        if (n_mine > 0) {
+            mbar_arrive_expect_tx(bar_u32, kBytes);
+            bulk_load(stage_u32, heat + first_map * 4096, kBytes, bar_u32, pol);
+        }
+    }
+    __syncwarp();
+    // this lane's pixel coordinates: float4 number it * 32 + lane starts at flat index idx0 = 128 it + 4 lane
+    const float bl = beta * kLog2e;
+    const float4* buf = reinterpret_cast<const float4*>(my_stage);
+    uint32_t parity = 0;
+    for (int jj = 0; jj < n_mine; ++jj) {
+        const size_t map = first_map + static_cast<size_t>(jj) * map_step;
+        mbar_wait(bar_u32, parity);
+        parity ^= 1u;
+        // ---- pass 1: maximum of beta * h -------------------------------------------------------------------------------
+        float lm = -INFINITY;
+#pragma unroll 8
+        for (int it = 0; it < NITC; ++it) {
+            const float4 v = buf[it * 32 + lane];
+            lm = fmaxf(lm, fmaxf(fmaxf(beta * v.x, beta * v.y), fmaxf(beta * v.z, beta * v.w)));
+        }
+        const float M = warp_max_f32(lm);
+        const float ms = (M == -INFINITY) ? 0.0f : M;
+        const float mb = -ms * kLog2e;
+        // ---- pass 2: sum e, sum e * col, sum e * row with e = exp(beta * h - M) -----------------------------------------
+        float s = 0.f, sc = 0.f, sr = 0.f;
+#pragma unroll 4
+        for (int it = 0; it < NITC; ++it) {
+            const float4 v = buf[it * 32 + lane];
+            uint32_t row, col;
+            wdiv.divmod(static_cast<uint32_t>(128 * it + 4 * lane), row, col);
+            const float fr = static_cast<float>(row), fc = static_cast<float>(col);
+            const float e0 = exp2f(fmaf(v.x, bl, mb)), e1 = exp2f(fmaf(v.y, bl, mb));
+            const float e2 = exp2f(fmaf(v.z, bl, mb)), e3 = exp2f(fmaf(v.w, bl, mb));
+            const float es = (e0 + e1) + (e2 + e3);
+            s += es;
+            sr = fmaf(es, fr, sr);
+            sc = fmaf(e0, fc, sc);
+            sc = fmaf(e1, fc + 1.0f, sc);
+            sc = fmaf(e2, fc + 2.0f, sc);
+            sc = fmaf(e3, fc + 3.0f, sc);
+        }
+        __syncwarp();
+        if (lane == 0 && jj + 1 < n_mine) {  // the stage has been read out: the warp's next map
+            mbar_arrive_expect_tx(bar_u32, kBytes);
+            bulk_load(stage_u32, heat + (map + map_step) * 4096, kBytes, bar_u32, pol);
+        }
+        const float r = warp_sum3_scattered(s, sc, sr, lane);
+        const float S = __shfl_sync(0xffffffffu, r, 0), SC = __shfl_sync(0xffffffffu, r, 8), SR = __shfl_sync(0xffffffffu, r, 16);
+        if (lane == 0) {
+            out_uv[2 * map + 0] = scale * __fdiv_rn(SC, S);
+            out_uv[2 * map + 1] = scale * __fdiv_rn(SR, S);
+        }
+    }
+}
+
 }  // namespace hp
 
 using namespace hp;
@@ -101,6 +186,25 @@ extern "C" HP_API int hp_soft_argmax(const float* heat, int n_maps, int H, int W
     const int grid = n_maps < sms * 16 ? n_maps : sms * 16;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const FastDiv wdiv(static_cast<uint32_t>(W));
+    // HP_SA_SHAPE=b keeps the block-per-map kernel at 64x64 (comparison runs)
+    static const bool staged_on = []() {
+        const char* e = getenv("HP_SA_SHAPE");
+        return !(e && e[0] == 'b');
+    }();
+    if (aligned16(heat) && W % 4 == 0 && HW == 4096 && staged_on) {
+        constexpr size_t smem = static_cast<size_t>(kSAStageWarps) * 32 * 512 + sizeof(uint64_t) * kSAStageWarps;
+        static bool configured[16] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev < 0 || dev >= 16 || !configured[dev]) {
+            const cudaError_t e = cudaFuncSetAttribute(soft_argmax_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+            if (e != cudaSuccess) return fail(static_cast<int>(e), "hp_soft_argmax: %s", cudaGetErrorString(e));
+            if (dev >= 0 && dev < 16) configured[dev] = true;
+        }
+        const int g = n_maps < sms * kSAStageBlocks ? n_maps : sms * kSAStageBlocks;
+        soft_argmax_staged_kernel<<<g, 32 * kSAStageWarps, smem, s>>>(heat, n_maps, wdiv, beta, scale, out_uv);
+        return launch_status("hp_soft_argmax");
+    }
     if (aligned16(heat) && W % 4 == 0) {
         if (HW == kSATPM * kSANV * 4) soft_argmax_kernel<WALK_EXACT><<<grid, kSATPM, 0, s>>>(heat, n_maps, HW, wdiv, beta, scale, out_uv);
         else soft_argmax_kernel<WALK_VEC><<<grid, kSATPM, 0, s>>>(heat, n_maps, HW, wdiv, beta, scale, out_uv);
