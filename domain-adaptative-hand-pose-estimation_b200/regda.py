@@ -121,35 +121,41 @@ class _RegDisp(torch.autograd.Function):
             w = _lib.require_cuda(weight.detach(), "weight").reshape(-1)
             if w.numel() != B * K:
                 raise ValueError(f"weight has {w.numel()} elements, expected {B}*{K}")
-        per_map = torch.empty((B, K), dtype=torch.float32, device=dev)
-        stats = torch.empty((B * K, 3), dtype=torch.float32, device=dev)
-        centres = torch.empty((B * K, 2), dtype=torch.int32, device=dev)
+        # one allocation for the per-map outputs: per_map [B*K] | stats [B*K, 3] | centres [B*K, 2] (int32 bits) - 4-byte words
+        n = B * K
+        pack = torch.empty((6 * n,), dtype=torch.float32, device=dev)
+        base = pack.data_ptr()
+        p_per_map, p_stats, p_centres = base, base + 4 * n, base + 16 * n
         mean = torch.empty((), dtype=torch.float32, device=dev) if reduction == "mean" else None
         per_sample = torch.empty((B,), dtype=torch.float32, device=dev) if reduction == "none" else None
         with _lib.on_device(dev):
             tab = _lib.gaussian_table(plg.sigma, tmp, dev)
             ws = _lib.workspace(dev, B * K, K)
             _lib.call("hp_regdisp_fwd", _lib.ptr(yd), _lib.ptr(adv), _lib.ptr(fz), _lib.ptr(w), variant, mode,
-                      C.c_float(epsilon), B, K, H, W, oh, ow, shift, tmp, _lib.ptr(tab), _lib.ptr(per_map),
-                      _lib.ptr(per_sample), _lib.ptr(mean), _lib.ptr(stats), _lib.ptr(centres), _lib.ptr(ws),
+                      C.c_float(epsilon), B, K, H, W, oh, ow, shift, tmp, _lib.ptr(tab), p_per_map,
+                      _lib.ptr(per_sample), _lib.ptr(mean), p_stats, p_centres, _lib.ptr(ws),
                       _lib.stream_ptr(dev))
-        ctx.save_for_backward(adv, centres, stats, tab)
+        ctx.save_for_backward(adv, pack, tab)
         ctx.fz, ctx.w = fz, w
         ctx.cfg = (variant, mode, float(epsilon), reduction, B, K, oh, ow, tmp)
-        holder._remember(variant, fz, centres, tab, (B, K, oh, ow, tmp))
+        holder._remember(variant, fz, pack, tab, (B, K, oh, ow, tmp))
         return mean if reduction == "mean" else per_sample
 
     @staticmethod
     def backward(ctx, grad_out):
-        adv, centres, stats, tab = ctx.saved_tensors
+        adv, pack, tab = ctx.saved_tensors
         variant, mode, eps, reduction, B, K, oh, ow, tmp = ctx.cfg
         dev = adv.device
-        go = grad_out.detach().to(torch.float32).contiguous()
+        base = pack.data_ptr()
+        p_stats, p_centres = base + 4 * B * K, base + 16 * B * K
+        go = grad_out.detach()
+        if go.dtype != torch.float32 or not go.is_contiguous():
+            go = go.to(torch.float32).contiguous()
         kind = _lib.GRAD_SCALAR if reduction == "mean" else _lib.GRAD_PER_SAMPLE
         grad_in = torch.empty_like(adv)
         with _lib.on_device(dev):
             _lib.call("hp_regdisp_bwd", _lib.ptr(adv), _lib.ptr(ctx.fz), _lib.ptr(ctx.w), variant, mode, C.c_float(eps),
-                      B, K, oh, ow, tmp, _lib.ptr(tab), _lib.ptr(centres), _lib.ptr(stats), _lib.ptr(go), kind,
+                      B, K, oh, ow, tmp, _lib.ptr(tab), p_centres, p_stats, _lib.ptr(go), kind,
                       _lib.ptr(grad_in), _lib.stream_ptr(dev))
         return (grad_in,) + (None,) * 9
 
@@ -167,8 +173,10 @@ class _RDBase(nn.Module):
 
     # -- lazily materialised attributes the reference sets eagerly (regda_4.py:136-137) ------
     def _remember(self, variant, fused, centres, tab, dims):
-        self._lazy = (variant, fused, centres, tab, dims)
-        self._gt = self._gf = None
+        # (object.__setattr__: nn.Module.__setattr__ costs ~3 us per assignment - it was a third of a forward call's host time)
+        object.__setattr__(self, "_lazy", (variant, fused, centres, tab, dims))
+        object.__setattr__(self, "_gt", None)
+        object.__setattr__(self, "_gf", None)
 
     def _materialise(self):
         if self._gt is None:
@@ -179,9 +187,13 @@ class _RDBase(nn.Module):
             gt = torch.empty((B, K, oh, ow), dtype=torch.float32, device=dev)
             gf = torch.empty_like(gt)
             with _lib.on_device(dev):
+                # `centres` is either an int32 [B*K, 2] tensor or the forward's packed float32 output buffer
+                # (per_map | stats | centres), whose centres start 16 * B * K bytes in
+                c_ptr = centres.data_ptr() + (16 * B * K if centres.dtype == torch.float32 else 0)
                 _lib.call("hp_regdisp_materialize", _lib.ptr(fused), variant, B, K, oh, ow, tmp, _lib.ptr(tab),
-                          _lib.ptr(centres), _lib.ptr(gt), _lib.ptr(gf), _lib.stream_ptr(dev))
-            self._gt, self._gf = gt, gf
+                          c_ptr, _lib.ptr(gt), _lib.ptr(gf), _lib.stream_ptr(dev))
+            object.__setattr__(self, "_gt", gt)
+            object.__setattr__(self, "_gf", gf)
         return self._gt, self._gf
 
     @property
