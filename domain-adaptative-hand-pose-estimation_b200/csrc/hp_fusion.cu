@@ -15,6 +15,7 @@
 #include "hp_decode.cuh"
 #include "hp_dispatch.cuh"
 #include "hp_tma.cuh"
+#include "hp_peer_step.cuh"
 
 namespace hp {
 
@@ -714,10 +715,51 @@ extern "C" HP_API int hp_fuse_multiscale(const float* lo, int hl, int wl, float 
     return launch_status("hp_fuse_multiscale");
 }
 
+// link != nullptr: a sharded call; *exchanged tells whether the kernel summed the counts over the ranks itself
+static int fuse_decode_pck_impl(const float* lo, int hl, int wl, float a_lo, const float* mid, int hm, int wm,
+                                float a_mid, const float* hi, float a_hi, const float* tgt_xy, int B, int K,
+                                int H, int W, double thr, float* pred_xy, float* maxvals, int32_t* counts,
+                                double* acc_out, void* workspace, hp_stream_t stream, const PeerLink* link, bool* exchanged);
+
 extern "C" HP_API int hp_fuse_decode_pck(const float* lo, int hl, int wl, float a_lo, const float* mid, int hm, int wm,
                                          float a_mid, const float* hi, float a_hi, const float* tgt_xy, int B, int K,
                                          int H, int W, double thr, float* pred_xy, float* maxvals, int32_t* counts,
                                          double* acc_out, void* workspace, hp_stream_t stream) {
+    return fuse_decode_pck_impl(lo, hl, wl, a_lo, mid, hm, wm, a_mid, hi, a_hi, tgt_xy, B, K, H, W, thr, pred_xy, maxvals, counts,
+                                acc_out, workspace, stream, nullptr, nullptr);
+}
+
+/* The sharded form (configs[3] on the GPUs of one node): the same step on this rank's samples; `counts` / `acc_out` then hold
+ * the totals over ALL ranks (keypoint_detection.py:63-92 on the concatenated batch).  Where the staged kernel applies
+ * (32 / 64 / 128) its last block exchanges the 2K integer counts over the peer mailboxes itself; otherwise a one-warp
+ * hp_pck_finalize_peer launch follows.  `mailboxes`: as for hp_pipeline_fused_peer. */
+extern "C" HP_API int hp_fuse_decode_pck_peer(const float* lo, int hl, int wl, float a_lo, const float* mid, int hm, int wm,
+                                              float a_mid, const float* hi, float a_hi, const float* tgt_xy, int B, int K,
+                                              int H, int W, double thr, float* pred_xy, float* maxvals, int32_t* counts,
+                                              double* acc_out, void* workspace, void* const* mailboxes, int rank, int world,
+                                              hp_stream_t stream) {
+    HP_REQUIRE(counts && mailboxes, HP_ERR_NULL, "hp_fuse_decode_pck_peer: null pointer");
+    HP_REQUIRE(world > 0 && world <= kPeerMaxWorld && rank >= 0 && rank < world && K > 0 && K <= HP_MAX_K && peer_shape_ok(K, world),
+               HP_ERR_ARG, "hp_fuse_decode_pck_peer: rank=%d world=%d K=%d (K <= 27 when sharded)", rank, world, K);
+    PeerLink link{};
+    for (int r = 0; r < world; ++r) {
+        HP_REQUIRE(mailboxes[r], HP_ERR_NULL, "hp_fuse_decode_pck_peer: mailbox %d is null", r);
+        link.mailbox[r] = static_cast<unsigned long long*>(mailboxes[r]);
+    }
+    link.rank = rank;
+    link.world = world;
+    bool exchanged = false;
+    if (int rc = fuse_decode_pck_impl(lo, hl, wl, a_lo, mid, hm, wm, a_mid, hi, a_hi, tgt_xy, B, K, H, W, thr, pred_xy, maxvals,
+                                      counts, acc_out, workspace, stream, world > 1 ? &link : nullptr, &exchanged))
+        return rc;
+    if (world > 1 && !exchanged) return hp_pck_finalize_peer(counts, mailboxes, rank, world, K, counts, acc_out, stream);
+    return HP_OK;
+}
+
+static int fuse_decode_pck_impl(const float* lo, int hl, int wl, float a_lo, const float* mid, int hm, int wm,
+                                float a_mid, const float* hi, float a_hi, const float* tgt_xy, int B, int K,
+                                int H, int W, double thr, float* pred_xy, float* maxvals, int32_t* counts,
+                                double* acc_out, void* workspace, hp_stream_t stream, const PeerLink* link, bool* exchanged) {
     FuseSrc f;
     if (int rc = make_src("hp_fuse_decode_pck", lo, hl, wl, a_lo, mid, hm, wm, a_mid, hi, a_hi, H, W, f)) return rc;
     HP_REQUIRE(tgt_xy && pred_xy && acc_out && workspace, HP_ERR_NULL, "hp_fuse_decode_pck: null pointer");
@@ -727,8 +769,9 @@ extern "C" HP_API int hp_fuse_decode_pck(const float* lo, int hl, int wl, float 
         int sl = 0, sm = 0, n_warps = 0;
         size_t smem = 0;
         if (!fuse_rows_forced() && block_geometry(f, nullptr, bg, sl, sm, n_warps, smem)) {
-            launch_fuse_block<true>(f, bg, sl, sm, n_warps, smem, B * K, nullptr, tgt_xy, K, thr, pred_xy, maxvals, counts, acc_out,
-                                    static_cast<Workspace*>(workspace), static_cast<cudaStream_t>(stream));
+            const bool ex = launch_fuse_block<true>(f, bg, sl, sm, n_warps, smem, B * K, nullptr, tgt_xy, K, thr, pred_xy, maxvals, counts,
+                                                    acc_out, static_cast<Workspace*>(workspace), static_cast<cudaStream_t>(stream), link);
+            if (exchanged) *exchanged = ex;
             return launch_status("hp_fuse_decode_pck");
         }
     }

@@ -416,7 +416,7 @@ template <int SL, int SM, bool DECODE>
 __global__ void __launch_bounds__(32 * kBlockHsWarps, 2)
     fuse_block_hs_kernel(const FuseSrc f, int n_maps, float* __restrict__ out, const float* __restrict__ tgt_xy, int K, double thr,
                          float* __restrict__ pred_xy, float* __restrict__ maxvals, int32_t* __restrict__ counts_out,
-                         double* __restrict__ acc_out, Workspace* __restrict__ ws) {
+                         double* __restrict__ acc_out, Workspace* __restrict__ ws, const PeerLink link) {
     extern __shared__ __align__(128) unsigned char s_raw[];
     __shared__ BlockHsCtl ctl;
     constexpr int SMX = SM == 0 ? 2 : SM;
@@ -602,7 +602,41 @@ __global__ void __launch_bounds__(32 * kBlockHsWarps, 2)
         }
     }
     if (DECODE) {
-        if (last_block_arrives(&ws->counter, gridDim.x)) pck_publish(ws, K, counts_out, acc_out);
+        if (last_block_arrives(&ws->counter, gridDim.x)) {
+            if (link.world > 1) {
+                // sharded (configs[3] on N GPUs): the last block sums the integer counts over the ranks itself - one warp, over
+                // the NVLink peer mailboxes (hp_peer_step.cuh) - instead of a second launch; scratch = the dead source buffers
+                long long* s_total = reinterpret_cast<long long*>(s_raw);
+                long long* s_scratch = s_total + 144;
+                double* s_acc = reinterpret_cast<double*>(s_scratch + kPeerScratchWords);
+                double* s_result = s_acc + HP_MAX_K;
+                Workspace* s_dummy = reinterpret_cast<Workspace*>(s_result + 4 + HP_MAX_K + 2);
+                if (warp == 0) {
+                    const int n = 4 + 2 * K + 6;
+                    for (int i = lane; i < static_cast<int>(4 * sizeof(Workspace) / 8); i += 32) reinterpret_cast<long long*>(s_dummy)[i] = 0;
+                    for (int w = lane; w < n; w += 32) {
+                        long long v = 0;
+                        if (w >= 4 && w < 4 + 2 * K) {
+                            v = *reinterpret_cast<volatile int*>(&ws->counts[w - 4]);
+                            ws->counts[w - 4] = 0;
+                        }
+                        s_total[w] = v;
+                    }
+                    __syncwarp();
+                    peer_step_warp(link, s_dummy, s_total, s_scratch, s_acc, K, nullptr, s_result, 0, lane);
+                    const bool bad = s_result[3] != s_result[3];  // poisoned by a timeout
+                    for (int i = lane; i < 2 * K; i += 32) counts_out[i] = bad ? -1 : static_cast<int>(s_total[4 + i]);
+                    for (int k = lane; k < K; k += 32) acc_out[k] = s_result[4 + k];
+                    if (lane == 0) {
+                        acc_out[K] = s_result[2];
+                        acc_out[K + 1] = s_result[3];
+                        ws->counter = 0;
+                    }
+                }
+            } else {
+                pck_publish(ws, K, counts_out, acc_out);
+            }
+        }
     }
 }
 
@@ -649,9 +683,10 @@ static bool block_geometry(const FuseSrc& f, const float* out, BlockWalk& g, int
 }
 
 template <bool DECODE>
-static void launch_fuse_block(const FuseSrc& f, const BlockWalk& g, int sl, int sm, int n_warps, size_t smem, int n_maps, float* out,
+static bool launch_fuse_block(const FuseSrc& f, const BlockWalk& g, int sl, int sm, int n_warps, size_t smem, int n_maps, float* out,
                               const float* tgt_xy, int K, double thr, float* pred_xy, float* maxvals, int32_t* counts,
-                              double* acc_out, Workspace* ws, cudaStream_t s) {
+                              double* acc_out, Workspace* ws, cudaStream_t s, const PeerLink* link = nullptr) {
+    // -> true when the launched kernel did the cross-GPU exchange of `link` itself (only the staged-hi kernel can)
     {
         size_t smem_hs = 0;
         if (sl == 4 && sm == 2 && block_hs_geometry(f, g, smem_hs)) {  // configs[3]: 32 / 64 / 128
@@ -665,9 +700,12 @@ static void launch_fuse_block(const FuseSrc& f, const BlockWalk& g, int sl, int 
             int sms = hp_device_sm_count();
             if (sms <= 0) sms = 148;
             const int grid_hs = n_maps < 2 * sms ? n_maps : 2 * sms;
+            PeerLink lk{};
+            lk.world = 1;
+            if (link && DECODE) lk = *link;
             fuse_block_hs_kernel<4, 2, DECODE><<<grid_hs, 32 * kBlockHsWarps, smem_hs, s>>>(f, n_maps, out, tgt_xy, K, thr, pred_xy, maxvals,
-                                                                                       counts, acc_out, ws);
-            return;
+                                                                                       counts, acc_out, ws, lk);
+            return link != nullptr && DECODE;
         }
     }
     const int grid = rows_grid(n_maps);
@@ -688,6 +726,7 @@ static void launch_fuse_block(const FuseSrc& f, const BlockWalk& g, int sl, int 
     else HP_FUSE_BLOCK(2, 0);
 #undef HP_FUSE_BLOCK_S
 #undef HP_FUSE_BLOCK
+    return false;
 }
 
 }  // namespace hp

@@ -428,17 +428,21 @@ class MultiscaleEval:
         maxvals = torch.empty((B, K, 1), dtype=torch.float32, device=dev)
         counts = torch.empty((2 * K,), dtype=torch.int32, device=dev)
         acc = torch.empty((K + 2,), dtype=torch.float64, device=dev)
+        sharded = not local and hpdist.is_distributed(self.group)
         with _lib.on_device(dev):
             ws = _lib.workspace(dev, B * K, K)
+            if sharded and self.collective == "peer":
+                # one launch: the kernel's last block sums the 2K integer counts over the NVLink peer mailboxes
+                hpdist.shared_peer_exchange(dev, self.group).fuse_decode_pck(
+                    lo, self.coef[0], mid, self.coef[1], hi, self.coef[2], tgt, B, K, H, W, self.thr, pred_xy, maxvals,
+                    counts, acc, ws)
+                return acc, pred_xy, counts
             _lib.call("hp_fuse_decode_pck", _lib.ptr(lo), lo.shape[2], lo.shape[3], C.c_float(self.coef[0]),
                       _lib.ptr(mid), mid.shape[2], mid.shape[3], C.c_float(self.coef[1]), _lib.ptr(hi),
                       C.c_float(self.coef[2]), _lib.ptr(tgt), B, K, H, W, C.c_double(self.thr), _lib.ptr(pred_xy),
                       _lib.ptr(maxvals), _lib.ptr(counts), _lib.ptr(acc), _lib.ptr(ws), _lib.stream_ptr(dev))
-            if not local and hpdist.is_distributed(self.group):
-                # the path's one collective: integer sum of the 2K hit / valid counts (exact, order-free)
-                if self.collective == "peer":
-                    hpdist.shared_peer_exchange(dev, self.group).pck_finalize(counts, K, counts, acc)
-                else:
-                    torch.distributed.all_reduce(counts, op=torch.distributed.ReduceOp.SUM, group=self.group)
-                    _lib.call("hp_pck_finalize", _lib.ptr(counts), K, _lib.ptr(acc), _lib.stream_ptr(dev))
+            if sharded:
+                # the path's one collective, NCCL form: integer sum of the 2K hit / valid counts (exact, order-free)
+                torch.distributed.all_reduce(counts, op=torch.distributed.ReduceOp.SUM, group=self.group)
+                _lib.call("hp_pck_finalize", _lib.ptr(counts), K, _lib.ptr(acc), _lib.stream_ptr(dev))
         return acc, pred_xy, counts

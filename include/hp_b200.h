@@ -296,6 +296,14 @@ int hp_pipeline_finalize_peer(const int64_t* partial, void* const* mailboxes, in
 int hp_pipeline_flush_peer(void* workspace, void* const* mailboxes, int rank, int world, hp_stream_t stream);
 int hp_pck_finalize_peer(const int32_t* counts, void* const* mailboxes, int rank, int world, int K,
                          int32_t* counts_out, double* acc_out, hp_stream_t stream);
+/* hp_fuse_decode_pck on this rank's samples with the exchange folded in: `counts` / `acc_out` hold the totals over ALL ranks
+ * (keypoint_detection.py:63-92 on the concatenated batch).  For the shapes of the staged kernel (32 / 64 / 128) the kernel's
+ * last block sums the 2K integer counts over the mailboxes itself - one launch per step; for any other geometry a one-warp
+ * hp_pck_finalize_peer launch follows.  world == 1: plain hp_fuse_decode_pck. */
+int hp_fuse_decode_pck_peer(const float* lo, int hl, int wl, float a_lo, const float* mid, int hm, int wm, float a_mid,
+                            const float* hi, float a_hi, const float* tgt_xy, int B, int K, int H, int W, double thr,
+                            float* pred_xy, float* maxvals, int32_t* counts, double* acc_out, void* workspace,
+                            void* const* mailboxes, int rank, int world, hp_stream_t stream);
 
 /* One batch-sharded step in a single call and - for the shapes served by the TMA-staged kernel (H*W = 256,
  * 1024 or a multiple of 4096 floats, aligned) - in a single KERNEL: the last block of the fused kernel stores

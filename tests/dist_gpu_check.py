@@ -86,6 +86,15 @@ def main():
     acc_n, _, counts_n = hp.MultiscaleEval(21, collective="nccl")(tm(lo_h, sl), tm(mid_h, sl), tm(dm["pred"], sl), tm(tgt_h, sl))
     assert torch.equal(acc_s, acc_n) and torch.equal(counts_s, counts_n), "peer and NCCL sums of the PCK counts differ"
     acc_s, counts_s = acc_s.cpu().numpy(), counts_s.cpu().numpy()
+    # a geometry the staged kernel (exchange folded into its last block) does not take - 16 / 32 / 64: the exchange is the
+    # one-warp kernel behind the fuse kernel, inside the same C call
+    d6 = hp.synth.make_host_batch(9110, Bm, 21, 64, 64)
+    mid6, lo6 = hp.synth.make_lowres_heads(9111, d6["pred"], (32, 16))
+    tgt6 = np.random.RandomState(9112).randint(0, 64, size=(Bm, 21, 2)).astype(np.float32)
+    acc6_s, _, counts6_s = hp.MultiscaleEval(21)(tm(lo6, sl), tm(mid6, sl), tm(d6["pred"], sl), tm(tgt6, sl))
+    acc6_n, _, counts6_n = hp.MultiscaleEval(21, collective="nccl")(tm(lo6, sl), tm(mid6, sl), tm(d6["pred"], sl), tm(tgt6, sl))
+    assert torch.equal(acc6_s, acc6_n) and torch.equal(counts6_s, counts6_n), "peer and NCCL sums differ (16/32/64)"
+    acc6_s, counts6_s = acc6_s.cpu().numpy(), counts6_s.cpu().numpy()
     peer.close()                    # the shared mailboxes: collective, before the process group goes away
     # single-GPU reference on the whole batch (group of one rank)
     solo_group = dist.new_group(ranks=[rank]) if False else None
@@ -103,6 +112,8 @@ def main():
     full = slice(0, Bm)
     acc_f, _, counts_f = hp.MultiscaleEval(21)(tm(lo_h, full), tm(mid_h, full), tm(dm["pred"], full), tm(tgt_h, full))
     assert np.array_equal(counts_s, counts_f.cpu().numpy()) and np.array_equal(acc_s, acc_f.cpu().numpy()), "sharded C4 differs"
+    acc6_f, _, counts6_f = hp.MultiscaleEval(21)(tm(lo6, full), tm(mid6, full), tm(d6["pred"], full), tm(tgt6, full))
+    assert np.array_equal(counts6_s, counts6_f.cpu().numpy()) and np.array_equal(acc6_s, acc6_f.cpu().numpy()), "sharded 16/32/64 differs"
     if rank == 0:
         from oracle import hp_oracle as O
         o = O.pipeline(d["pred"], d["joints"], d["vis"], kl_epsilon=1e-7)
