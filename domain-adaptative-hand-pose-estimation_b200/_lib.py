@@ -100,7 +100,7 @@ PROTOTYPES = {
     "hp_pipeline_flush_peer": (_i, [_vp, _vp, _i, _i, _vp]),
     "hp_pck_finalize_peer": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "hp_fuse_decode_pck_peer": (_i, [_vp, _i, _i, _f, _vp, _i, _i, _f, _vp, _f, _vp, _i, _i, _i, _i, _d,
-                                     _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
+                                     _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, C.c_uint, _vp, _vp, _vp]),
     "hp_pipeline_fused_host": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _d, _d, _i, _vp, _f, _d, _i, _i,
                                     _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),
 }

@@ -719,7 +719,8 @@ extern "C" HP_API int hp_fuse_multiscale(const float* lo, int hl, int wl, float 
 static int fuse_decode_pck_impl(const float* lo, int hl, int wl, float a_lo, const float* mid, int hm, int wm,
                                 float a_mid, const float* hi, float a_hi, const float* tgt_xy, int B, int K,
                                 int H, int W, double thr, float* pred_xy, float* maxvals, int32_t* counts,
-                                double* acc_out, void* workspace, hp_stream_t stream, const PeerLink* link, bool* exchanged);
+                                double* acc_out, void* workspace, hp_stream_t stream, const PeerLink* link, bool* exchanged,
+                                int defer = 0, long long* partial_out = nullptr, double* result_out = nullptr);
 
 extern "C" HP_API int hp_fuse_decode_pck(const float* lo, int hl, int wl, float a_lo, const float* mid, int hm, int wm,
                                          float a_mid, const float* hi, float a_hi, const float* tgt_xy, int B, int K,
@@ -737,8 +738,10 @@ extern "C" HP_API int hp_fuse_decode_pck_peer(const float* lo, int hl, int wl, f
                                               float a_mid, const float* hi, float a_hi, const float* tgt_xy, int B, int K,
                                               int H, int W, double thr, float* pred_xy, float* maxvals, int32_t* counts,
                                               double* acc_out, void* workspace, void* const* mailboxes, int rank, int world,
-                                              hp_stream_t stream) {
+                                              unsigned int flags, int64_t* partial_out, double* result_out, hp_stream_t stream) {
     HP_REQUIRE(counts && mailboxes, HP_ERR_NULL, "hp_fuse_decode_pck_peer: null pointer");
+    const int defer = (flags & 2u) != 0 && world > 1;  // HP_PIPE_DEFER_EXCHANGE
+    HP_REQUIRE(!defer || (partial_out && result_out), HP_ERR_NULL, "hp_fuse_decode_pck_peer: a deferred step needs partial_out and result_out");
     HP_REQUIRE(world > 0 && world <= kPeerMaxWorld && rank >= 0 && rank < world && K > 0 && K <= HP_MAX_K && peer_shape_ok(K, world),
                HP_ERR_ARG, "hp_fuse_decode_pck_peer: rank=%d world=%d K=%d (K <= 27 when sharded)", rank, world, K);
     PeerLink link{};
@@ -750,16 +753,21 @@ extern "C" HP_API int hp_fuse_decode_pck_peer(const float* lo, int hl, int wl, f
     link.world = world;
     bool exchanged = false;
     if (int rc = fuse_decode_pck_impl(lo, hl, wl, a_lo, mid, hm, wm, a_mid, hi, a_hi, tgt_xy, B, K, H, W, thr, pred_xy, maxvals,
-                                      counts, acc_out, workspace, stream, world > 1 ? &link : nullptr, &exchanged))
+                                      counts, acc_out, workspace, stream, world > 1 ? &link : nullptr, &exchanged, defer,
+                                      reinterpret_cast<long long*>(partial_out), result_out))
         return rc;
-    if (world > 1 && !exchanged) return hp_pck_finalize_peer(counts, mailboxes, rank, world, K, counts, acc_out, stream);
+    if (world > 1 && !exchanged) {
+        HP_REQUIRE(!defer, HP_ERR_SHAPE, "hp_fuse_decode_pck_peer: only the staged 32/64/128 kernel can defer its exchange");
+        return hp_pck_finalize_peer(counts, mailboxes, rank, world, K, counts, acc_out, stream);
+    }
     return HP_OK;
 }
 
 static int fuse_decode_pck_impl(const float* lo, int hl, int wl, float a_lo, const float* mid, int hm, int wm,
                                 float a_mid, const float* hi, float a_hi, const float* tgt_xy, int B, int K,
                                 int H, int W, double thr, float* pred_xy, float* maxvals, int32_t* counts,
-                                double* acc_out, void* workspace, hp_stream_t stream, const PeerLink* link, bool* exchanged) {
+                                double* acc_out, void* workspace, hp_stream_t stream, const PeerLink* link, bool* exchanged,
+                                int defer, long long* partial_out, double* result_out) {
     FuseSrc f;
     if (int rc = make_src("hp_fuse_decode_pck", lo, hl, wl, a_lo, mid, hm, wm, a_mid, hi, a_hi, H, W, f)) return rc;
     HP_REQUIRE(tgt_xy && pred_xy && acc_out && workspace, HP_ERR_NULL, "hp_fuse_decode_pck: null pointer");
@@ -770,7 +778,8 @@ static int fuse_decode_pck_impl(const float* lo, int hl, int wl, float a_lo, con
         size_t smem = 0;
         if (!fuse_rows_forced() && block_geometry(f, nullptr, bg, sl, sm, n_warps, smem)) {
             const bool ex = launch_fuse_block<true>(f, bg, sl, sm, n_warps, smem, B * K, nullptr, tgt_xy, K, thr, pred_xy, maxvals, counts,
-                                                    acc_out, static_cast<Workspace*>(workspace), static_cast<cudaStream_t>(stream), link);
+                                                    acc_out, static_cast<Workspace*>(workspace), static_cast<cudaStream_t>(stream), link,
+                                                    defer, partial_out, result_out);
             if (exchanged) *exchanged = ex;
             return launch_status("hp_fuse_decode_pck");
         }

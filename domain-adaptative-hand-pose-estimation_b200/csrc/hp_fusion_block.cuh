@@ -416,7 +416,8 @@ template <int SL, int SM, bool DECODE>
 __global__ void __launch_bounds__(32 * kBlockHsWarps, 2)
     fuse_block_hs_kernel(const FuseSrc f, int n_maps, float* __restrict__ out, const float* __restrict__ tgt_xy, int K, double thr,
                          float* __restrict__ pred_xy, float* __restrict__ maxvals, int32_t* __restrict__ counts_out,
-                         double* __restrict__ acc_out, Workspace* __restrict__ ws, const PeerLink link) {
+                         double* __restrict__ acc_out, Workspace* __restrict__ ws, const PeerLink link, const int defer,
+                         long long* __restrict__ partial_out, double* __restrict__ result_out) {
     extern __shared__ __align__(128) unsigned char s_raw[];
     __shared__ BlockHsCtl ctl;
     constexpr int SMX = SM == 0 ? 2 : SM;
@@ -610,10 +611,8 @@ __global__ void __launch_bounds__(32 * kBlockHsWarps, 2)
                 long long* s_scratch = s_total + 144;
                 double* s_acc = reinterpret_cast<double*>(s_scratch + kPeerScratchWords);
                 double* s_result = s_acc + HP_MAX_K;
-                Workspace* s_dummy = reinterpret_cast<Workspace*>(s_result + 4 + HP_MAX_K + 2);
                 if (warp == 0) {
                     const int n = 4 + 2 * K + 6;
-                    for (int i = lane; i < static_cast<int>(4 * sizeof(Workspace) / 8); i += 32) reinterpret_cast<long long*>(s_dummy)[i] = 0;
                     for (int w = lane; w < n; w += 32) {
                         long long v = 0;
                         if (w >= 4 && w < 4 + 2 * K) {
@@ -623,15 +622,21 @@ __global__ void __launch_bounds__(32 * kBlockHsWarps, 2)
                         s_total[w] = v;
                     }
                     __syncwarp();
-                    peer_step_warp(link, s_dummy, s_total, s_scratch, s_acc, K, nullptr, s_result, 0, lane);
-                    const bool bad = s_result[3] != s_result[3];  // poisoned by a timeout
-                    for (int i = lane; i < 2 * K; i += 32) counts_out[i] = bad ? -1 : static_cast<int>(s_total[4 + i]);
-                    for (int k = lane; k < K; k += 32) acc_out[k] = s_result[4 + k];
-                    if (lane == 0) {
-                        acc_out[K] = s_result[2];
-                        acc_out[K + 1] = s_result[3];
-                        ws->counter = 0;
+                    // defer != 0 (a step of a train): only SEND; the totals of this step land in partial_out / result_out
+                    // (the pipeline's vector layout: counts at [4, 4 + 2K), {-, -, avg_acc, cnt, acc[K]}) when the NEXT step's
+                    // last block - or hp_pipeline_flush_peer - collects them; the pending record lives in the workspace
+                    peer_step_warp(link, ws, s_total, s_scratch, s_acc, K, defer ? partial_out : nullptr, defer ? result_out : s_result,
+                                   defer, lane);
+                    if (!defer) {
+                        const bool bad = s_result[3] != s_result[3];  // poisoned by a timeout
+                        for (int i = lane; i < 2 * K; i += 32) counts_out[i] = bad ? -1 : static_cast<int>(s_total[4 + i]);
+                        for (int k = lane; k < K; k += 32) acc_out[k] = s_result[4 + k];
+                        if (lane == 0) {
+                            acc_out[K] = s_result[2];
+                            acc_out[K + 1] = s_result[3];
+                        }
                     }
+                    if (lane == 0) ws->counter = 0;
                 }
             } else {
                 pck_publish(ws, K, counts_out, acc_out);
@@ -685,7 +690,8 @@ static bool block_geometry(const FuseSrc& f, const float* out, BlockWalk& g, int
 template <bool DECODE>
 static bool launch_fuse_block(const FuseSrc& f, const BlockWalk& g, int sl, int sm, int n_warps, size_t smem, int n_maps, float* out,
                               const float* tgt_xy, int K, double thr, float* pred_xy, float* maxvals, int32_t* counts,
-                              double* acc_out, Workspace* ws, cudaStream_t s, const PeerLink* link = nullptr) {
+                              double* acc_out, Workspace* ws, cudaStream_t s, const PeerLink* link = nullptr, int defer = 0,
+                              long long* partial_out = nullptr, double* result_out = nullptr) {
     // -> true when the launched kernel did the cross-GPU exchange of `link` itself (only the staged-hi kernel can)
     {
         size_t smem_hs = 0;
@@ -704,7 +710,8 @@ static bool launch_fuse_block(const FuseSrc& f, const BlockWalk& g, int sl, int 
             lk.world = 1;
             if (link && DECODE) lk = *link;
             fuse_block_hs_kernel<4, 2, DECODE><<<grid_hs, 32 * kBlockHsWarps, smem_hs, s>>>(f, n_maps, out, tgt_xy, K, thr, pred_xy, maxvals,
-                                                                                       counts, acc_out, ws, lk);
+                                                                                       counts, acc_out, ws, lk,
+                                                                                       (link && DECODE) ? defer : 0, partial_out, result_out);
             return link != nullptr && DECODE;
         }
     }

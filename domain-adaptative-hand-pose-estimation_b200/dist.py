@@ -95,15 +95,16 @@ class PeerExchange:
                   _lib.ptr(counts_out), _lib.ptr(acc_out), st)
 
     def fuse_decode_pck(self, lo, a_lo, mid, a_mid, hi, a_hi, tgt, B, K, H, W, thr, pred_xy, maxvals, counts, acc, ws,
-                        stream=None):
+                        stream=None, partial=None, result=None):
         """configs[3], sharded: fuse + decode + PCK of this rank's samples with the counts exchange folded into the kernel's
-        last block (one launch per step; other geometries: the one-warp exchange kernel follows inside the C call)."""
+        last block (one launch per step; other geometries: the one-warp exchange kernel follows inside the C call).
+        ``partial`` / ``result`` given: a DEFERRED step (HP_PIPE_DEFER_EXCHANGE) - see :meth:`MultiscaleEval.step`."""
         C, _lib = self._C, self._lib
         st = C.c_void_p(stream.cuda_stream) if stream is not None else _lib.stream_ptr(self.device)
         _lib.call("hp_fuse_decode_pck_peer", _lib.ptr(lo), lo.shape[2], lo.shape[3], C.c_float(a_lo), _lib.ptr(mid),
                   mid.shape[2], mid.shape[3], C.c_float(a_mid), _lib.ptr(hi), C.c_float(a_hi), _lib.ptr(tgt), B, K, H, W,
                   C.c_double(thr), _lib.ptr(pred_xy), _lib.ptr(maxvals), _lib.ptr(counts), _lib.ptr(acc), _lib.ptr(ws),
-                  self._table, self.rank, self.world, st)
+                  self._table, self.rank, self.world, 2 if partial is not None else 0, _lib.ptr(partial), _lib.ptr(result), st)
 
     def close(self):
         _SHARED.pop((self.device.index, id(self.group)), None)

@@ -80,30 +80,34 @@ class _KL(torch.autograd.Function):
         B, K, H, W = out.shape
         dev = out.device
         w = _flat_weight(weight, B, K, dev)
-        per_map = torch.empty((B, K), dtype=torch.float32, device=dev)
-        stats = torch.empty((B * K, 2), dtype=torch.float32, device=dev)
+        # one allocation for the per-map outputs: per_map [B*K] | stats [B*K, 2] (every torch.empty is ~3 us of host time)
+        n = B * K
+        pack = torch.empty((3 * n,), dtype=torch.float32, device=dev)
+        base = pack.data_ptr()
         mean = torch.empty((), dtype=torch.float32, device=dev) if reduction == "mean" else None
         per_sample = torch.empty((B,), dtype=torch.float32, device=dev) if reduction == "none" else None
         with _lib.on_device(dev):
             ws = _lib.workspace(dev, B * K, K)
             _lib.call("hp_kl_fwd", _lib.ptr(out), _lib.ptr(tgt), _lib.ptr(w), C.c_float(epsilon), B, K, H * W,
-                      _lib.ptr(per_map), _lib.ptr(per_sample), _lib.ptr(mean), _lib.ptr(stats), _lib.ptr(ws),
+                      base, _lib.ptr(per_sample), _lib.ptr(mean), base + 4 * n, _lib.ptr(ws),
                       _lib.stream_ptr(dev))
-        ctx.save_for_backward(out, tgt, w, stats)
+        ctx.save_for_backward(out, tgt, w, pack)
         ctx.reduction = reduction
         ctx.epsilon = float(epsilon)
         return mean if reduction == "mean" else per_sample
 
     @staticmethod
     def backward(ctx, grad_out):
-        out, tgt, w, stats = ctx.saved_tensors
+        out, tgt, w, pack = ctx.saved_tensors
         B, K, H, W = out.shape
         dev = out.device
-        go = grad_out.detach().to(torch.float32).contiguous()
+        go = grad_out.detach()
+        if go.dtype != torch.float32 or not go.is_contiguous():
+            go = go.to(torch.float32).contiguous()
         kind = _lib.GRAD_SCALAR if ctx.reduction == "mean" else _lib.GRAD_PER_SAMPLE
         grad_in = torch.empty_like(out)
         with _lib.on_device(dev):
-            _lib.call("hp_kl_bwd", _lib.ptr(out), _lib.ptr(tgt), _lib.ptr(w), C.c_float(ctx.epsilon), _lib.ptr(stats),
+            _lib.call("hp_kl_bwd", _lib.ptr(out), _lib.ptr(tgt), _lib.ptr(w), C.c_float(ctx.epsilon), pack.data_ptr() + 4 * B * K,
                       _lib.ptr(go), kind, B, K, H * W, _lib.ptr(grad_in), _lib.stream_ptr(dev))
         return grad_in, None, None, None, None
 

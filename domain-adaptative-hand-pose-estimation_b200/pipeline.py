@@ -397,6 +397,28 @@ class HeatmapPipeline:
         return st
 
 
+class MultiscaleStep:
+    """Result of :meth:`MultiscaleEval.step`: ``pred_xy`` at once; ``acc`` (float64 [K+2] = acc[K], avg_acc, cnt) and
+    ``counts`` (int32 [2K] hits, valid) over ALL ranks once the step has been collected (next step / ``flush``)."""
+    __slots__ = ("K", "pred_xy", "partial", "result", "_acc", "_counts")
+
+    def __init__(self, K, pred_xy, partial, result, acc, counts):
+        self.K, self.pred_xy, self.partial, self.result, self._acc, self._counts = K, pred_xy, partial, result, acc, counts
+
+    @property
+    def acc(self):
+        if self._acc is None:
+            K = self.K
+            self._acc = torch.cat([self.result[4:4 + K], self.result[2:4]])
+        return self._acc
+
+    @property
+    def counts(self):
+        if self._counts is None:
+            self._counts = self.partial[4:4 + 2 * self.K].to(torch.int32)
+        return self._counts
+
+
 class MultiscaleEval:
     """BASELINE.json configs[3]: fuse three resolutions (``0.5*up(lo) + up(mid) + hi``, the rule of
     train1.py:410-424 scaled up), decode the fused map and score PCK against label coordinates - the
@@ -413,6 +435,43 @@ class MultiscaleEval:
         # right behind the fuse kernel, no NCCL launch) or torch.distributed.all_reduce + hp_pck_finalize
         self.collective = collective if self.K <= _lib.PEER_MAX_K else "nccl"
         _lib.load()
+
+    def step(self, lo, mid, hi, target_xy):
+        """One step of a TRAIN of sharded evaluations (peer collective, 32 / 64 / 128 geometry): the kernel only sends its
+        counts; the totals over all ranks land in the returned :class:`MultiscaleStep` when the next ``step`` (same
+        stream) or :meth:`flush` collects them - no step waits for a rank that is less than a step late.  Unsharded or
+        with ``collective='nccl'`` it is the synchronous ``__call__``."""
+        if not (hpdist.is_distributed(self.group) and self.collective == "peer"):
+            acc, pred_xy, counts = self(lo, mid, hi, target_xy)
+            return MultiscaleStep(self.K, pred_xy, None, None, acc, counts)
+        lo = _lib.require_cuda(lo, "MultiscaleEval(lo)")
+        mid = _lib.require_cuda(mid, "MultiscaleEval(mid)")
+        hi = _lib.require_cuda(hi, "MultiscaleEval(hi)")
+        tgt = _lib.require_cuda(target_xy, "MultiscaleEval(target_xy)")
+        B, K, H, W = hi.shape
+        dev = hi.device
+        pred_xy = torch.empty((B, K, 2), dtype=torch.float32, device=dev)
+        maxvals = torch.empty((B, K, 1), dtype=torch.float32, device=dev)
+        counts = torch.empty((2 * K,), dtype=torch.int32, device=dev)
+        acc = torch.empty((K + 2,), dtype=torch.float64, device=dev)
+        partial = torch.empty((4 + 2 * K + 6,), dtype=torch.int64, device=dev)
+        result = torch.empty((4 + K,), dtype=torch.float64, device=dev)
+        with _lib.on_device(dev):
+            ws = _lib.workspace(dev, B * K, K)
+            self._pending = (dev, ws)
+            hpdist.shared_peer_exchange(dev, self.group).fuse_decode_pck(
+                lo, self.coef[0], mid, self.coef[1], hi, self.coef[2], tgt, B, K, H, W, self.thr, pred_xy, maxvals,
+                counts, acc, ws, partial=partial, result=result)
+        return MultiscaleStep(K, pred_xy, partial, result, None, None)
+
+    def flush(self):
+        """Complete the outstanding step of a train of :meth:`step` calls (one-warp kernel; a no-op when nothing is pending)."""
+        pend = getattr(self, "_pending", None)
+        if pend is not None:
+            dev, ws = pend
+            with _lib.on_device(dev):
+                hpdist.shared_peer_exchange(dev, self.group).flush(ws)
+            self._pending = None
 
     def __call__(self, lo, mid, hi, target_xy, local=False):
         """lo/mid/hi float32 [B,K,h,w] CUDA tensors (hi may be None -> output size = 2x mid); target_xy

@@ -299,11 +299,16 @@ int hp_pck_finalize_peer(const int32_t* counts, void* const* mailboxes, int rank
 /* hp_fuse_decode_pck on this rank's samples with the exchange folded in: `counts` / `acc_out` hold the totals over ALL ranks
  * (keypoint_detection.py:63-92 on the concatenated batch).  For the shapes of the staged kernel (32 / 64 / 128) the kernel's
  * last block sums the 2K integer counts over the mailboxes itself - one launch per step; for any other geometry a one-warp
- * hp_pck_finalize_peer launch follows.  world == 1: plain hp_fuse_decode_pck. */
+ * hp_pck_finalize_peer launch follows.  world == 1: plain hp_fuse_decode_pck.
+ * flags & HP_PIPE_DEFER_EXCHANGE (a step of a train; staged kernel only): the step only SENDS its counts; its totals land in
+ * partial_out (int64 [4+2K+6], the pipeline's vector: hits / valid at [4, 4+2K)) and result_out (double [4+K]:
+ * -, -, avg_acc, cnt, acc[K]) when the next such step on the same workspace - or hp_pipeline_flush_peer - collects them;
+ * `counts` / `acc_out` are not written then. */
 int hp_fuse_decode_pck_peer(const float* lo, int hl, int wl, float a_lo, const float* mid, int hm, int wm, float a_mid,
                             const float* hi, float a_hi, const float* tgt_xy, int B, int K, int H, int W, double thr,
                             float* pred_xy, float* maxvals, int32_t* counts, double* acc_out, void* workspace,
-                            void* const* mailboxes, int rank, int world, hp_stream_t stream);
+                            void* const* mailboxes, int rank, int world, unsigned int flags, int64_t* partial_out,
+                            double* result_out, hp_stream_t stream);
 
 /* One batch-sharded step in a single call and - for the shapes served by the TMA-staged kernel (H*W = 256,
  * 1024 or a multiple of 4096 floats, aligned) - in a single KERNEL: the last block of the fused kernel stores

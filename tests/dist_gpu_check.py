@@ -85,6 +85,13 @@ def main():
     acc_s, _, counts_s = hp.MultiscaleEval(21)(tm(lo_h, sl), tm(mid_h, sl), tm(dm["pred"], sl), tm(tgt_h, sl))   # peer exchange
     acc_n, _, counts_n = hp.MultiscaleEval(21, collective="nccl")(tm(lo_h, sl), tm(mid_h, sl), tm(dm["pred"], sl), tm(tgt_h, sl))
     assert torch.equal(acc_s, acc_n) and torch.equal(counts_s, counts_n), "peer and NCCL sums of the PCK counts differ"
+    # a TRAIN of deferred steps (each only sends; the next step / flush collects): every step's totals == the synchronous ones
+    ev_d = hp.MultiscaleEval(21)
+    steps_d = [ev_d.step(tm(lo_h, sl), tm(mid_h, sl), tm(dm["pred"], sl), tm(tgt_h, sl)) for _ in range(4)]
+    ev_d.flush()
+    torch.cuda.synchronize()
+    for st in steps_d:
+        assert torch.equal(st.acc, acc_s) and torch.equal(st.counts, counts_s), "deferred fuse step differs from the synchronous one"
     acc_s, counts_s = acc_s.cpu().numpy(), counts_s.cpu().numpy()
     # a geometry the staged kernel (exchange folded into its last block) does not take - 16 / 32 / 64: the exchange is the
     # one-warp kernel behind the fuse kernel, inside the same C call
