@@ -27,6 +27,14 @@ except Exception:
     pass
 K = 21
 rows = []
+# nvidia-smi clocks / throttle reasons sampled every 20 ms over the whole run (bench.py's sampler): every row records the
+# samples that fell into its own timed window (reps are raised so that a window holds at least a few samples)
+import importlib.util
+_spec = importlib.util.spec_from_file_location("hp_bench", os.path.join(ROOT, "bench.py"))
+_bench = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(_bench)
+sampler = _bench.ClockSampler(0)
+sampler.start()
 
 
 def timed(name, fn, n_sets, bytes_per_call, maps_per_call, note=""):
@@ -44,11 +52,19 @@ def timed(name, fn, n_sets, bytes_per_call, maps_per_call, note=""):
     host_us = 1e6 * (time.perf_counter() - t0) / args.reps   # host time to ISSUE a call (no synchronisation)
     torch.cuda.synchronize()
     us = 1e3 * e0.elapsed_time(e1) / args.reps
+    # the same load for >= 120 ms more, untimed, so that the clock sampler sees this operator under load
+    w0 = time.perf_counter()
+    extra = max(args.reps, int(0.12 / max(us * 1e-6, 1e-6)))
+    for i in range(min(extra, 20000)):
+        fn(i % n_sets)
+    torch.cuda.synchronize()
+    clocks = sampler.summary([(w0, time.perf_counter())])
     if host_us > 0.85 * us:
         note = (note + "; " if note else "") + f"HOST-BOUND: issuing a call takes {host_us:.0f} us"
     gbs = bytes_per_call / (us * 1e-6) / 1e9
     rows.append({"op": name, "us_per_call": us, "GBps": gbs, "frac_of_measured_hbm": gbs / PEAK,
-                 "heatmaps_per_s": maps_per_call / (us * 1e-6), "algorithmic_bytes": bytes_per_call, "host_issue_us": host_us, "note": note})
+                 "heatmaps_per_s": maps_per_call / (us * 1e-6), "algorithmic_bytes": bytes_per_call, "host_issue_us": host_us, "note": note,
+                 "clocks": clocks})
     print(f"{name:58s} {us:9.1f} us  {gbs:8.1f} GB/s  {gbs / PEAK:5.2f} of HBM  {maps_per_call / (us * 1e-6) / 1e6:8.1f} M maps/s  {note}")
 
 
@@ -137,6 +153,7 @@ with torch.no_grad():
     timed("HeatmapPipeline 1024x21x128x128 (launch train)",
           lambda i: pipe(p128[i]["pred"], p128[i]["joints"], p128[i]["vis"], out=outs[i], overlap=True), 3, n * (65536 + 32), n)
 
+sampler.stop()
 if args.out:
     with open(args.out, "w") as f:
         json.dump({"hbm_peak_gbs": PEAK, "rows": rows}, f, indent=1)
