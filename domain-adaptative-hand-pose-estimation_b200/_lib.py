@@ -65,6 +65,7 @@ PROTOTYPES = {
     "hp_regdisp_bwd": (_i, [_vp, _vp, _vp, _i, _i, _f, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
     "hp_regdisp_materialize": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "hp_fuse_multiscale": (_i, [_vp, _i, _i, _f, _vp, _i, _i, _f, _vp, _f, _i, _i, _i, _vp, _vp]),
+    "hp_fuse_multiscale_pair": (_i, [_vp, _i, _i, _f, _vp, _i, _i, _f, _i, _i, _i, _vp, _f, _i, _i, _vp, _vp]),
     "hp_fuse_decode_pck": (_i, [_vp, _i, _i, _f, _vp, _i, _i, _f, _vp, _f, _vp, _i, _i, _i, _i, _d,
                                 _vp, _vp, _vp, _vp, _vp, _vp]),
     "hp_pipeline_fused": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _d, _d, _i, _vp, _f, _d, _i,

@@ -715,6 +715,27 @@ extern "C" HP_API int hp_fuse_multiscale(const float* lo, int hl, int wl, float 
     return launch_status("hp_fuse_multiscale");
 }
 
+/* train1.py:410-424 in one call: out [n_maps, H, W] = a_lo * up(lo) + a_mid * up(mid) (`target5`) and
+ * out2 [n_maps, H2, W2] = a_lo2 * up(lo) (`target0`), both nn.Upsample(mode='bilinear').  ONE launch for the driver's geometry
+ * (lo x4 and mid x2 -> H x W, lo x2 -> H2 x W2 = H/2 x W/2); anything else: two hp_fuse_multiscale launches. */
+extern "C" HP_API int hp_fuse_multiscale_pair(const float* lo, int hl, int wl, float a_lo, const float* mid, int hm, int wm, float a_mid,
+                                              int n_maps, int H, int W, float* out, float a_lo2, int H2, int W2, float* out2,
+                                              hp_stream_t stream) {
+    HP_REQUIRE(out && out2, HP_ERR_NULL, "hp_fuse_multiscale_pair: null output");
+    if (n_maps > 0 && mid && H2 * 2 == H && W2 * 2 == W && !fuse_rows_forced()) {
+        FuseSrc f;
+        if (int rc = make_src("hp_fuse_multiscale_pair", lo, hl, wl, a_lo, mid, hm, wm, a_mid, nullptr, 0.0f, H, W, f)) return rc;
+        BlockWalk bg;
+        int sl = 0, sm = 0, n_warps = 0;
+        size_t smem = 0;
+        if (block_geometry(f, out, bg, sl, sm, n_warps, smem) &&
+            launch_fuse_pair(f, bg, sl, sm, n_warps, smem, n_maps, out, out2, a_lo2, static_cast<cudaStream_t>(stream)))
+            return launch_status("hp_fuse_multiscale_pair");
+    }
+    if (int rc = hp_fuse_multiscale(lo, hl, wl, a_lo, mid, hm, wm, a_mid, nullptr, 0.0f, n_maps, H, W, out, stream)) return rc;
+    return hp_fuse_multiscale(lo, hl, wl, a_lo2, nullptr, 0, 0, 0.0f, nullptr, 0.0f, n_maps, H2, W2, out2, stream);
+}
+
 // link != nullptr: a sharded call; *exchanged tells whether the kernel summed the counts over the ranks itself
 static int fuse_decode_pck_impl(const float* lo, int hl, int wl, float a_lo, const float* mid, int hm, int wm,
                                 float a_mid, const float* hi, float a_hi, const float* tgt_xy, int B, int K,

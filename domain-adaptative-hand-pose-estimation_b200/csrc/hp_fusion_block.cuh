@@ -209,11 +209,15 @@ struct BlockCtl {
 // executed instructions to those loop-edge moves).  Measured on B200: strips of 2 (64x64 outputs) gain 6 %
 // (66.4 -> 62.3 us); strips of 8 (128x128) spill at the 128-register bound of four blocks per SM and lose 6 %
 // (three blocks per SM with 164 registers: 109.8 vs 104.6 us - the kernel needs its 16 warps), so they keep the run-time loop.
-template <int SL, int SM, bool DECODE, int STRIP>
+// PAIR (train1.py:410-424 in ONE launch): besides `out` = a_lo up4(lo) + a_mid up2(mid) the block also writes
+// out2 = a2 * up2(lo) at half the size (`target0 = up32(y_adv3)` next to `target5`): 64 of its threads take one 4x4 block of
+// the second map each, from the same staged source - the second launch and its re-read of `lo` disappear.
+template <int SL, int SM, bool DECODE, int STRIP, bool PAIR = false>
 __global__ void __launch_bounds__(32 * kBlockMaxWarps, 4)
     fuse_block_kernel(const FuseSrc f, const BlockWalk g, int n_maps, float* __restrict__ out, const float* __restrict__ tgt_xy,
                       int K, double thr, float* __restrict__ pred_xy, float* __restrict__ maxvals,
-                      int32_t* __restrict__ counts_out, double* __restrict__ acc_out, Workspace* __restrict__ ws) {
+                      int32_t* __restrict__ counts_out, double* __restrict__ acc_out, Workspace* __restrict__ ws,
+                      float* __restrict__ out2 = nullptr, float a2 = 0.0f) {
     extern __shared__ __align__(128) unsigned char s_raw[];
     __shared__ BlockCtl ctl;
     constexpr int SMX = SM == 0 ? 2 : SM;  // (template argument of the unused mid helpers)
@@ -263,10 +267,16 @@ __global__ void __launch_bounds__(32 * kBlockMaxWarps, 4)
     const BlockCols<SL> lo_c = block_cols<SL>(n, f.wl);
     const BlockAxis<SMX> mid_x = block_axis<SMX>(n);
     const BlockCols<SMX> mid_c = block_cols<SMX>(n, SM ? f.wm : 2);
+    // PAIR: thread i < (H/8) * (W/8) owns block (m2, n2) of the half-size map
+    const int cb2 = f.W / 8, nb2 = (f.H / 8) * cb2;
+    const int n2 = PAIR ? static_cast<int>(threadIdx.x) % cb2 : 0, m2 = PAIR ? static_cast<int>(threadIdx.x) / cb2 : 0;
+    const BlockAxis<2> ax2 = block_axis<2>(n2);
+    const BlockCols<2> col2 = block_cols<2>(n2, f.wl);
     __syncthreads();  // the only block barrier: control block (and tap table) are set up
     {
         bool ok = block_axis_matches<SL>(n, f.wl);
         if (SM) ok = ok && block_axis_matches<SMX>(n, f.wm);
+        if (PAIR && static_cast<int>(threadIdx.x) < nb2) ok = ok && block_axis_matches<2>(n2, f.wl) && block_axis_matches<2>(m2, f.hl);
         for (int m = m_begin; m < m_end; ++m) {
             ok = ok && block_axis_matches<SL>(m, f.hl);
             if (SM) ok = ok && block_axis_matches<SMX>(m, f.hm);
@@ -335,6 +345,19 @@ __global__ void __launch_bounds__(32 * kBlockMaxWarps, 4)
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) h[u] = hn[u];
+        }
+        if (PAIR && static_cast<int>(threadIdx.x) < nb2) {  // the half-size map from the same staged `lo` (still valid: before the ticket)
+            BlockRows<2> R2;
+            block_rows_start<2>(R2, lo_s, f.wl, f.hl, m2, col2, ax2);
+            float2 v2[4][2];
+            block_rows_blend<2>(R2, lo_s, f.wl, f.hl, m2, col2, ax2, v2);
+            const float2 aa = make_float2(a2, a2);
+            float* o2 = out2 + static_cast<size_t>(map) * (HW / 4) + (4 * m2) * (f.W / 2) + 4 * n2;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float2 r0 = __fmul2_rn(aa, v2[u][0]), r1 = __fmul2_rn(aa, v2[u][1]);
+                stg_stream4(reinterpret_cast<float4*>(o2 + u * (f.W / 2)), make_float4(r0.x, r0.y, r1.x, r1.y));
+            }
         }
         ArgMax am = am_init();
         bool bad = false;
@@ -658,6 +681,11 @@ static bool block_hs_geometry(const FuseSrc& f, const BlockWalk& g, size_t& smem
     return (2 * (lo_b + mid_b)) % 128 == 0 && smem <= 110 * 1024;  // 2 blocks per SM
 }
 
+// train1.py:410-424 in one launch: out [n, H, W] = a_lo up4(lo) + a_mid up2(mid), out2 [n, H/2, W/2] = a2 up2(lo);
+// -> false when the geometry is not the 16 / 32 -> 64 (+ 32) pattern of the 4-warp block kernel with strips of two
+static bool launch_fuse_pair(const FuseSrc& f, const BlockWalk& g, int sl, int sm, int n_warps, size_t smem, int n_maps, float* out,
+                             float* out2, float a2, cudaStream_t s);
+
 // block kernel applicable?  exact x2 / x4 scales, W/4 in {8, 16, 32}, bulk-copy alignment, everything fits
 static bool block_geometry(const FuseSrc& f, const float* out, BlockWalk& g, int& sl, int& sm, int& n_warps, size_t& smem) {
     if (f.W % 4 != 0 || f.H % 4 != 0) return false;
@@ -734,6 +762,15 @@ static bool launch_fuse_block(const FuseSrc& f, const BlockWalk& g, int sl, int 
 #undef HP_FUSE_BLOCK_S
 #undef HP_FUSE_BLOCK
     return false;
+}
+
+static bool launch_fuse_pair(const FuseSrc& f, const BlockWalk& g, int sl, int sm, int n_warps, size_t smem, int n_maps, float* out,
+                             float* out2, float a2, cudaStream_t s) {
+    if (sl != 4 || sm != 2 || g.strip != 2 || f.hi != nullptr || n_warps != kBlockMaxWarps) return false;
+    if ((f.H / 8) * (f.W / 8) > 32 * n_warps || f.hl * 2 * 2 != f.H || f.wl * 2 * 2 != f.W || !aligned16(out2)) return false;
+    fuse_block_kernel<4, 2, false, 2, true><<<rows_grid(n_maps), 32 * n_warps, smem, s>>>(f, g, n_maps, out, nullptr, 0, 0.0, nullptr, nullptr,
+                                                                                     nullptr, nullptr, nullptr, out2, a2);
+    return true;
 }
 
 }  // namespace hp

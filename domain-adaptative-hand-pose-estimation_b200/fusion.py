@@ -41,6 +41,20 @@ def upsample_bilinear(x, size):
 def fuse_multiscale(y_adv3, y_adv2, size_hi=64, size_mid=32):
     """train1.py:410-424 -> ``(target5, target0)`` with
     ``target5 = 0.5*up_hi(y_adv3) + up_hi(y_adv2)`` and ``target0 = up_mid(y_adv3)`` (inputs detached)."""
+    if isinstance(size_hi, int) and isinstance(size_mid, int) and 2 * size_mid == size_hi:
+        # both maps from ONE launch (hp_fuse_multiscale_pair; any geometry it does not cover falls back to two inside the call)
+        lo = _lib.require_cuda(y_adv3.detach(), "fuse(lo)")
+        mid = _lib.require_cuda(y_adv2.detach(), "fuse(mid)")
+        if mid.shape[:2] != lo.shape[:2]:
+            raise ValueError("fuse: batch/joint dims differ")
+        B, K, hl, wl = lo.shape
+        target5 = torch.empty((B, K, size_hi, size_hi), dtype=torch.float32, device=lo.device)
+        target0 = torch.empty((B, K, size_mid, size_mid), dtype=torch.float32, device=lo.device)
+        with _lib.on_device(lo.device):
+            _lib.call("hp_fuse_multiscale_pair", _lib.ptr(lo), hl, wl, C.c_float(0.5), _lib.ptr(mid), mid.shape[2], mid.shape[3],
+                      C.c_float(1.0), B * K, size_hi, size_hi, _lib.ptr(target5), C.c_float(1.0), size_mid, size_mid,
+                      _lib.ptr(target0), _lib.stream_ptr(lo.device))
+        return target5, target0
     target5 = _fuse(y_adv3, 0.5, y_adv2, 1.0, None, 0.0, size_hi)
     target0 = _fuse(y_adv3, 1.0, None, 0.0, None, 0.0, size_mid)
     return target5, target0

@@ -161,6 +161,13 @@ int hp_fuse_multiscale(const float* lo, int hl, int wl, float a_lo,
                        const float* mid, int hm, int wm, float a_mid,
                        const float* hi, float a_hi, int n_maps, int H, int W, float* out,
                        hp_stream_t stream);
+/* train1.py:410-424 in one call: out [n_maps, H, W] = a_lo * up(lo) + a_mid * up(mid) (`target5`) and
+ * out2 [n_maps, H2, W2] = a_lo2 * up(lo) (`target0 = up32(y_adv3)`), both nn.Upsample(mode='bilinear') (align_corners=False).
+ * One launch for the driver's geometry (lo x4 and mid x2 -> H x W, H2 x W2 = H/2 x W/2, e.g. 16 / 32 -> 64 and 32); any other
+ * geometry: two hp_fuse_multiscale launches.  Results are bit-identical to the two separate calls. */
+int hp_fuse_multiscale_pair(const float* lo, int hl, int wl, float a_lo, const float* mid, int hm, int wm, float a_mid,
+                            int n_maps, int H, int W, float* out, float a_lo2, int H2, int W2, float* out2,
+                            hp_stream_t stream);
 /* fuse (as above, never written to memory) + decode + PCK against target coordinates:
  * BASELINE.json configs[3].  tgt_xy [n_maps,2] ; outputs as hp_accuracy. */
 int hp_fuse_decode_pck(const float* lo, int hl, int wl, float a_lo,

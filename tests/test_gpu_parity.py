@@ -529,3 +529,23 @@ def test_sharded_pipeline_two_gpus():
                         "--master-addr", "127.0.0.1", "--master-port", "29633",
                         os.path.join(root, "tests", "dist_gpu_check.py")], capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
+
+
+def test_fuse_multiscale_pair_equals_two_launches():
+    """train1.py:410-424: target5 (64x64) and target0 (32x32) come from ONE launch (hp_fuse_multiscale_pair); the result is
+    bit-identical to the two separate launches it replaced, on the driver's geometry and on one it does not cover."""
+    fusion = importlib.import_module("domain-adaptative-hand-pose-estimation_b200.fusion")
+    rs = np.random.RandomState(5101)
+    for (s3, s2, hi, mid_out) in ((16, 32, 64, 32), (8, 16, 32, 16), (16, 32, 96, 48)):
+        y3 = torch.from_numpy(rs.standard_normal((5, 21, s3, s3)).astype(np.float32)).cuda()
+        y2 = torch.from_numpy(rs.standard_normal((5, 21, s2, s2)).astype(np.float32)).cuda()
+        t5, t0 = hp.fuse_multiscale(y3, y2, hi, mid_out)
+        w5 = fusion._fuse(y3, 0.5, y2, 1.0, None, 0.0, hi)
+        w0 = fusion._fuse(y3, 1.0, None, 0.0, None, 0.0, mid_out)
+        assert torch.equal(t5, w5) and torch.equal(t0, w0), (s3, s2, hi, mid_out)
+        r5, r0 = O.fuse_multiscale(y3.cpu(), y2.cpu(), hi, mid_out)
+        # exact x2 / x4 scales: the tap weights are dyadic, only the association order differs from ATen's (1e-6).  The x3 / x6
+        # geometry has source indices up to 15.9 computed in fp32 (one ulp = 9.5e-7 of a weight times |v1 - v0| <= 6): 1e-5.
+        atol = 1e-6 if hi % s3 == 0 and (hi // s3) in (2, 4) else 1e-5
+        np.testing.assert_allclose(t5.cpu().numpy(), r5.numpy(), rtol=1e-5, atol=atol)
+        np.testing.assert_allclose(t0.cpu().numpy(), r0.numpy(), rtol=1e-5, atol=atol)
