@@ -694,7 +694,11 @@ def run_regdisp_arm(args, wl):
                 "mode='max', y_adv2=None: ground-false label rebuilt per pixel from the sample's K centres"),
         "max_fused": (lambda i: rd6(ys[i % n_sets], advs[i % n_sets], t5[i % n_sets], None, "max"), 3 * hw4,
                       "mode='max' with the pre-fused target5 map (train1.py:419-421)"),
+        "max_heads": (lambda i: rd6(ys[i % n_sets], advs[i % n_sets], heads[i % n_sets], None, "max"), 2 * hw4 + hw4 // 4 + hw4 // 16,
+                      "mode='max' with target5 left unfused (hp.FusedHeads: the loss kernel interpolates 0.5 up64(y_adv3) + "
+                      "up64(y_adv2) from the staged 16x16 / 32x32 heads; SURVEY.md 8d: 37,888 B per map, no fusion launch)"),
     }
+    heads = [hp.FusedHeads(f16[i], f32[i]) for i in range(n_sets)]
     peak, peak_src = measured_hbm_peak()
     rows = {}
     with torch.no_grad():

@@ -15,6 +15,7 @@ this package                           reference
 ``RegressionDisparity{,x1,x5,x6}``     uda/model/regda_4.py:89-143, regda_7.py:3206-3632
 ``generate_target``                    uda/dataset/util.py:9-68
 ``fuse_multiscale``                    train1.py:410-424 (inline in the reference)
+``FusedHeads``                         the same map left unfused: x6 'max' builds it inside the loss kernel
 ``HeatmapPipeline``                    gen + loss + decode + PCK fused (BASELINE.json metric)
 =====================================  ====================================================
 
@@ -43,7 +44,7 @@ _LAZY = {
     "RegressionDisparity8": "regda", "RegressionDisparityx2": "regda", "RegressionDisparityx3": "regda",
     "RegressionDisparityx4": "regda", "JointsMSELoss0": "loss", "JointsKLLoss5": "loss",
     "generate_target": "target", "generate_target_batch": "target", "DeviceTargetCollate": "target",
-    "fuse_multiscale": "fusion", "fuse_three_scales": "fusion", "upsample_bilinear": "fusion",
+    "fuse_multiscale": "fusion", "fuse_three_scales": "fusion", "upsample_bilinear": "fusion", "FusedHeads": "fusion",
     "HeatmapPipeline": "pipeline", "PipelineResult": "pipeline",
     "MultiscaleEval": "pipeline",
 }

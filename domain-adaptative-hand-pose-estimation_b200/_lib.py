@@ -63,6 +63,10 @@ PROTOTYPES = {
     "hp_regdisp_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _i, _i, _i, _i, _i, _i, _i, _i, _vp,
                             _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "hp_regdisp_bwd": (_i, [_vp, _vp, _vp, _i, _i, _f, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
+    "hp_regdisp_fwd_heads": (_i, [_vp, _vp, _vp, _i, _i, _f, _vp, _i, _i, _f, _vp, _i, _i, _f, _i, _i, _i, _i, _i, _i, _i,
+                                  _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "hp_regdisp_bwd_heads": (_i, [_vp, _vp, _i, _i, _f, _vp, _i, _i, _f, _vp, _i, _i, _f, _i, _i, _i, _i, _i, _vp, _vp, _vp,
+                                  _vp, _i, _vp, _vp]),
     "hp_regdisp_materialize": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "hp_fuse_multiscale": (_i, [_vp, _i, _i, _f, _vp, _i, _i, _f, _vp, _f, _i, _i, _i, _vp, _vp]),
     "hp_fuse_multiscale_pair": (_i, [_vp, _i, _i, _f, _vp, _i, _i, _f, _i, _i, _i, _vp, _f, _i, _i, _vp, _vp]),

@@ -16,6 +16,7 @@
 #include "hp_dispatch.cuh"
 #include "hp_tma.cuh"
 #include "hp_peer_step.cuh"
+#include "hp_bilinear_block.cuh"
 
 namespace hp {
 
@@ -222,11 +223,6 @@ __device__ __forceinline__ void row_source_init(RowSource& s, int x0, float sx, 
     s.cur0 = s.cur1 = -1;
     s.base = nullptr;
     s.base_s = 0;
-}
-__device__ __forceinline__ float lds_f32(uint32_t addr) {
-    float v;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
-    return v;
 }
 template <bool STAGED>
 __device__ __forceinline__ void row_source_load(const RowSource& s, int r, float2 (&t)[2]) {

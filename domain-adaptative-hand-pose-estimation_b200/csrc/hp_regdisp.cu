@@ -399,6 +399,62 @@ extern "C" HP_API int hp_regdisp_bwd(const float* y_adv, const float* fused, con
     return launch_regdisp<RD_BWD>(a, vec, static_cast<cudaStream_t>(stream), "hp_regdisp_bwd");
 }
 
+// ---- x6 'max' with the fused map built IN the kernel from its two heads (train1.py:410-426; SURVEY.md 8d, configs[2] 'max' with
+// in-kernel fusion: 37,888 B per map) -------------------------------------------------------------------------------------------
+static int check_heads(const char* who, const float* f_lo, int hl, int wl, const float* f_mid, int hm, int wm, int variant, int mode,
+                       int oh, int ow, int tmp, int K, const float* y_adv) {
+    HP_REQUIRE(f_lo && f_mid, HP_ERR_NULL, "%s: null head", who);
+    HP_REQUIRE(variant == HP_RD_X6 && mode == HP_MODE_MAX, HP_ERR_ARG,
+               "%s: only RegressionDisparityx6 mode='max' reads a fused map (variant %d, mode %d)", who, variant, mode);
+    HP_REQUIRE(oh == 64 && ow == 64 && hl == kRDDLoSide && wl == kRDDLoSide && hm == kRDDMidSide && wm == kRDDMidSide, HP_ERR_SHAPE,
+               "%s: heads %dx%d / %dx%d -> %dx%d; the in-kernel fusion covers 16x16 / 32x32 -> 64x64 (materialise the map with "
+               "hp_fuse_multiscale and call hp_regdisp_fwd otherwise)", who, hl, wl, hm, wm, oh, ow);
+    HP_REQUIRE(K <= kRDDMaxK && tmp <= 6 && (2 * tmp + 1) * (2 * tmp + 1) <= 32 * kTileMaxPatch, HP_ERR_SHAPE,
+               "%s: K=%d tmp=%d outside the dense kernel's range", who, K, tmp);
+    HP_REQUIRE(aligned16(f_lo) && aligned16(f_mid) && aligned16(y_adv), HP_ERR_ARG, "%s: pointers must be 16-byte aligned", who);
+    return HP_OK;
+}
+
+extern "C" HP_API int hp_regdisp_fwd_heads(const float* y, const float* y_adv, const float* f_lo, int hl, int wl, float a_lo,
+                                           const float* f_mid, int hm, int wm, float a_mid, const float* weight, int variant,
+                                           int mode, float epsilon, int B, int K, int H, int W, int oh, int ow, int tmp,
+                                           const float* tab, float* per_map, float* per_sample, float* mean, float* stats,
+                                           int32_t* centres, void* workspace, hp_stream_t stream) {
+    if (int rc = check_rd("hp_regdisp_fwd_heads", variant, mode, B, K, oh, ow, tmp)) return rc;
+    HP_REQUIRE(y && y_adv && tab && per_map && stats && centres && workspace, HP_ERR_NULL, "hp_regdisp_fwd_heads: null pointer");
+    HP_REQUIRE(H == oh && W == ow, HP_ERR_SHAPE, "hp_regdisp_fwd_heads: y is %dx%d, the label grid %dx%d", H, W, oh, ow);
+    if (int rc = check_heads("hp_regdisp_fwd_heads", f_lo, hl, wl, f_mid, hm, wm, variant, mode, oh, ow, tmp, K, y_adv)) return rc;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (int rc = launch_decode(y, B * K, H, W, nullptr, nullptr, nullptr, centres, 0, s)) return rc;
+    RDArgs a{};
+    a.y_adv = y_adv; a.f_lo = f_lo; a.f_mid = f_mid; a.a_lo = a_lo; a.a_mid = a_mid; a.weight = weight; a.variant = variant;
+    a.mode = mode; a.eps = epsilon; a.B = B; a.K = K; a.oh = oh; a.ow = ow; a.tmp = tmp; a.tab = tab; a.centres = centres;
+    a.per_map = per_map; a.per_sample = per_sample; a.mean = mean; a.stats = stats; a.ws = static_cast<Workspace*>(workspace);
+    const int rc = launch_regdisp_dense<RD_FWD>(a, s, "hp_regdisp_fwd_heads");
+    if (rc == 1) return fail(HP_ERR_ARG, "hp_regdisp_fwd_heads: the dense kernel is switched off (HP_RD_DENSE=0)");
+    return rc;
+}
+
+extern "C" HP_API int hp_regdisp_bwd_heads(const float* y_adv, const float* f_lo, int hl, int wl, float a_lo, const float* f_mid,
+                                           int hm, int wm, float a_mid, const float* weight, int variant, int mode, float epsilon,
+                                           int B, int K, int oh, int ow, int tmp, const float* tab, const int32_t* centres,
+                                           const float* stats, const float* grad_out, int grad_kind, float* grad_in,
+                                           hp_stream_t stream) {
+    if (int rc = check_rd("hp_regdisp_bwd_heads", variant, mode, B, K, oh, ow, tmp)) return rc;
+    HP_REQUIRE(y_adv && tab && centres && stats && grad_out && grad_in, HP_ERR_NULL, "hp_regdisp_bwd_heads: null pointer");
+    HP_REQUIRE(grad_kind == HP_GRAD_SCALAR || grad_kind == HP_GRAD_PER_SAMPLE, HP_ERR_ARG,
+               "hp_regdisp_bwd_heads: grad_kind %d", grad_kind);
+    if (int rc = check_heads("hp_regdisp_bwd_heads", f_lo, hl, wl, f_mid, hm, wm, variant, mode, oh, ow, tmp, K, y_adv)) return rc;
+    HP_REQUIRE(aligned16(grad_in), HP_ERR_ARG, "hp_regdisp_bwd_heads: grad_in must be 16-byte aligned");
+    RDArgs a{};
+    a.y_adv = y_adv; a.f_lo = f_lo; a.f_mid = f_mid; a.a_lo = a_lo; a.a_mid = a_mid; a.weight = weight; a.variant = variant;
+    a.mode = mode; a.eps = epsilon; a.B = B; a.K = K; a.oh = oh; a.ow = ow; a.tmp = tmp; a.tab = tab; a.centres = centres;
+    a.stats = const_cast<float*>(stats); a.grad_out = grad_out; a.grad_kind = grad_kind; a.grad_in = grad_in;
+    const int rc = launch_regdisp_dense<RD_BWD>(a, static_cast<cudaStream_t>(stream), "hp_regdisp_bwd_heads");
+    if (rc == 1) return fail(HP_ERR_ARG, "hp_regdisp_bwd_heads: the dense kernel is switched off (HP_RD_DENSE=0)");
+    return rc;
+}
+
 extern "C" HP_API int hp_regdisp_materialize(const float* fused, int variant, int B, int K, int oh, int ow, int tmp,
                                              const float* tab, const int32_t* centres, float* gt, float* gf,
                                              hp_stream_t stream) {

@@ -33,6 +33,7 @@
 #pragma once
 #include "hp_pipeline_parts.cuh"
 #include "hp_regdisp_staged.cuh"
+#include "hp_bilinear_block.cuh"
 
 namespace hp {
 
@@ -62,10 +63,15 @@ struct RDDShape {
     static constexpr int IT = 32 / G;                        // iterations per warp and pass
     static constexpr int NSL = (kTileMaxPatch + G - 1) / G;  // patch slots per lane of a consumer warp
     static constexpr size_t kSmem = static_cast<size_t>(NG) * NS * kRDDPixels * 4 + 2 * kRDDPixels * 4;
+    // LAZY (the fused map built from its heads): a group owns two 16 KB slots for y_adv and two 5 KB slots for the heads, so
+    // that BOTH units of the group's next map are in flight while the current one is computed (with a pre-fused map the 3 x
+    // 16 KB rotation leaves the next map's y_adv unrequested until the current map closes)
+    static constexpr size_t kLazyGroupBytes = 2 * kRDDPixels * 4 + 2 * (16 * 16 + 32 * 32) * 4;
+    static constexpr size_t kLazySmem = static_cast<size_t>(NG) * kLazyGroupBytes + 2 * kRDDPixels * 4;
 };
 
 struct RDDShared {
-    uint64_t full[12];        // slot s of group g landed: full[g * NS + s]
+    uint64_t full[16];        // slot s of group g landed: full[g * NS + s]  (LAZY: full[4 g + {0, 1}] y_adv, full[4 g + {2, 3}] heads)
     uint64_t lp_full[2];      // lp slot built (count 1: the builder)
     uint64_t lp_empty[2];     // lp slot released (count W: every consumer warp, once per sample)
     Centre c[2][kRDDMaxK];
@@ -223,7 +229,102 @@ __device__ __noinline__ void rdd_softmax_exact(const float4* __restrict__ P4, in
     s_out = acc;
 }
 
-template <bool FUSED, int GW, int TASK>
+// ---- the fused map built in the kernel (LAZY; hp_regdisp_fwd_heads / hp_regdisp_bwd_heads) ---------------------------------------
+// train1.py:410-426 feeds x6 'max' with target5 = a_lo up64(y_adv3) + a_mid up64(y_adv2) (16x16 and 32x32 heads,
+// nn.Upsample(mode='bilinear')).  Pre-fused, that map costs 16 KB written by the fusion kernel and 16 KB read here per
+// map; LAZY launches receive the two heads themselves (1 KB + 4 KB per map, one bulk copy each into the head of the slot the
+// fused map would have occupied) and every lane interpolates the fused values of its two 4x4 output blocks in registers -
+// the static tap pattern of hp_bilinear_block.cuh, same arithmetic and operation order as the fusion kernels, so the values
+// are bit-identical to hp_fuse_multiscale's.  Algorithmic bytes per map: 16,384 (y, decode) + 16,384 (y_adv) + 4,096 + 1,024
+// = 37,888 (SURVEY.md 8d, configs[2] 'max' with in-kernel fusion) instead of 49,152 + the fusion kernel's 5,120 + 16,384.
+constexpr int kRDDLoSide = 16, kRDDMidSide = 32;
+constexpr int kRDDRow4 = 16;  // float4 per row of the 64 x 64 map the heads are fused into
+constexpr int kRDDLoBytes = kRDDLoSide * kRDDLoSide * 4, kRDDMidBytes = kRDDMidSide * kRDDMidSide * 4;
+
+// taps of output coordinate X at the exact scale S (align_corners=False, clamped at 0 and in - 1): the scalar form of BlockAxis
+template <int S>
+__device__ __forceinline__ void rdd_exact_tap(int X, int in, int& i0, int& i1, float& l1) {
+    if (S == 2) {
+        const int j = X >> 1;
+        if (X & 1) {
+            i0 = j; i1 = min(j + 1, in - 1); l1 = 0.25f;
+        } else if (X == 0) {
+            i0 = 0; i1 = 1; l1 = 0.0f;
+        } else {
+            i0 = j - 1; i1 = j; l1 = 0.75f;
+        }
+    } else {
+        const int m = X >> 2, c = X & 3;
+        if (c < 2) {
+            if (m == 0) {
+                i0 = 0; i1 = 1; l1 = 0.0f;
+            } else {
+                i0 = m - 1; i1 = m; l1 = (c == 0) ? 0.625f : 0.875f;
+            }
+        } else {
+            i0 = m; i1 = min(m + 1, in - 1); l1 = (c == 2) ? 0.125f : 0.375f;
+        }
+    }
+}
+template <int S>
+__device__ __forceinline__ float rdd_bilinear_at(const float* __restrict__ src, int in, int x, int y) {
+    int x0, x1, y0, y1;
+    float lx, ly;
+    rdd_exact_tap<S>(x, in, x0, x1, lx);
+    rdd_exact_tap<S>(y, in, y0, y1, ly);
+    const float lx0 = 1.0f - lx, ly0 = 1.0f - ly;
+    const float t0 = __fmaf_rn(lx, src[y0 * in + x1], __fmul_rn(lx0, src[y0 * in + x0]));
+    const float t1 = __fmaf_rn(lx, src[y1 * in + x1], __fmul_rn(lx0, src[y1 * in + x0]));
+    return __fmaf_rn(ly, t1, __fmul_rn(ly0, t0));
+}
+// one pixel of the fused map from the staged heads (own-patch pixels)
+__device__ __forceinline__ float rdd_fused_at(const float* __restrict__ lo, const float* __restrict__ mid, float a_lo, float a_mid, int x, int y) {
+    return __fmaf_rn(a_mid, rdd_bilinear_at<2>(mid, kRDDMidSide, x, y), __fmul_rn(a_lo, rdd_bilinear_at<4>(lo, kRDDLoSide, x, y)));
+}
+// the lane's two 4x4 blocks (column block n, block rows m_begin, m_begin + 1): f[4 i + u] = row 4 (m_begin + i) + u, columns 4n..4n+3
+__device__ __forceinline__ void rdd_fused_blocks(uint32_t lo_s, uint32_t mid_s, float a_lo, float a_mid, int n, int m_begin, float4 (&f)[8]) {
+    const BlockAxis<4> lo_x = block_axis<4>(n);
+    const BlockCols<4> lo_c = block_cols<4>(n, kRDDLoSide);
+    const BlockAxis<2> mid_x = block_axis<2>(n);
+    const BlockCols<2> mid_c = block_cols<2>(n, kRDDMidSide);
+    BlockRows<4> RL;
+    BlockRows<2> RM;
+    block_rows_start<4>(RL, lo_s, kRDDLoSide, kRDDLoSide, m_begin, lo_c, lo_x);
+    block_rows_start<2>(RM, mid_s, kRDDMidSide, kRDDMidSide, m_begin, mid_c, mid_x);
+    const float2 al = make_float2(a_lo, a_lo), am = make_float2(a_mid, a_mid);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        float2 vl[4][2], vm[4][2];
+        block_rows_blend<4>(RL, lo_s, kRDDLoSide, kRDDLoSide, m_begin + i, lo_c, lo_x, vl);
+        block_rows_blend<2>(RM, mid_s, kRDDMidSide, kRDDMidSide, m_begin + i, mid_c, mid_x, vm);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float2 r0 = __ffma2_rn(am, vm[u][0], __fmul2_rn(al, vl[u][0]));
+            const float2 r1 = __ffma2_rn(am, vm[u][1], __fmul2_rn(al, vl[u][1]));
+            f[4 * i + u] = make_float4(r0.x, r0.y, r1.x, r1.y);
+        }
+    }
+}
+
+// the sums of pass 2 with a fused map (u = g / M + eps), one float4 of the prediction and of g at a time
+struct RDDFusedAcc {
+    float2 s2, su2, sup2, suq2, sulg2, sulh2;
+};
+__device__ __forceinline__ void rdd_fused_acc(RDDFusedAcc& A, float4 v, float4 g, float2 l2e, float2 mb2, float2 im2, float2 e2) {
+    const float2 lo = make_float2(v.x, v.y), hi = make_float2(v.z, v.w);
+    const float2 a0 = __ffma2_rn(lo, l2e, mb2), a1 = __ffma2_rn(hi, l2e, mb2);
+    A.s2 = __fadd2_rn(A.s2, __fadd2_rn(make_float2(ex2_approx(a0.x), ex2_approx(a0.y)), make_float2(ex2_approx(a1.x), ex2_approx(a1.y))));
+    const float2 u0 = __ffma2_rn(make_float2(g.x, g.y), im2, e2), u1 = __ffma2_rn(make_float2(g.z, g.w), im2, e2);
+    A.su2 = __fadd2_rn(A.su2, __fadd2_rn(u0, u1));
+    A.sup2 = __ffma2_rn(u0, a0, A.sup2);
+    A.suq2 = __ffma2_rn(u1, a1, A.suq2);
+    const float2 q0 = make_float2(lg2_approx(fmaxf(u0.x, 1.17549435e-38f)), lg2_approx(fmaxf(u0.y, 1.17549435e-38f)));
+    const float2 q1 = make_float2(lg2_approx(fmaxf(u1.x, 1.17549435e-38f)), lg2_approx(fmaxf(u1.y, 1.17549435e-38f)));
+    A.sulg2 = __ffma2_rn(u0, q0, A.sulg2);
+    A.sulh2 = __ffma2_rn(u1, q1, A.sulh2);
+}
+
+template <bool FUSED, int GW, int TASK, bool LAZY = false>
 __global__ void __launch_bounds__(32 * (RDDShape<FUSED, GW>::W + 1), 1) regdisp_dense_kernel(const RDArgs a) {
     extern __shared__ __align__(128) unsigned char s_rdd[];
     __shared__ RDDShared sh;
@@ -233,7 +334,10 @@ __global__ void __launch_bounds__(32 * (RDDShape<FUSED, GW>::W + 1), 1) regdisp_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int K = a.K, tmp = a.tmp, ow = a.ow, oh = a.oh;
     const float eps = a.eps;
-    float* lp_base = reinterpret_cast<float*>(s_rdd + static_cast<size_t>(NG) * NS * kMapBytes);
+    constexpr size_t kGroupBytes = LAZY ? S::kLazyGroupBytes : static_cast<size_t>(NS) * kMapBytes;
+    constexpr int kGroupBars = LAZY ? 4 : NS;
+    constexpr int kHeadBytes = kRDDLoBytes + kRDDMidBytes;
+    float* lp_base = reinterpret_cast<float*>(s_rdd + static_cast<size_t>(NG) * kGroupBytes);
 
     // this block's maps: [m0, m1), its samples: [sample0, sample0 + n_samples)
     const int n_maps = a.B * K;
@@ -274,8 +378,8 @@ __global__ void __launch_bounds__(32 * (RDDShape<FUSED, GW>::W + 1), 1) regdisp_
     const uint32_t lpf_u32 = smem_addr(sh.lp_full), lpe_u32 = smem_addr(sh.lp_empty);
     const uint64_t pol = l2_evict_first_policy();
     const int grp = warp < W ? warp / G : 0, h = warp < W ? warp % G : 0;  // group, warp of the group
-    unsigned char* my_slots = s_rdd + static_cast<size_t>(grp) * NS * kMapBytes;
-    const uint32_t slots_u32 = smem_addr(my_slots), bars_u32 = smem_addr(sh.full) + 8 * grp * NS;
+    unsigned char* my_slots = s_rdd + static_cast<size_t>(grp) * kGroupBytes;
+    const uint32_t slots_u32 = smem_addr(my_slots), bars_u32 = smem_addr(sh.full) + 8 * grp * kGroupBars;
     const int n_my = (q_total > grp) ? (q_total - grp + NG - 1) / NG : 0;  // maps of this group
     const int n_units = n_my * UPM;
     // one lane of a group: request unit u of the group's load sequence into slot `slot` (= u % NS)
@@ -286,15 +390,30 @@ __global__ void __launch_bounds__(32 * (RDDShape<FUSED, GW>::W + 1), 1) regdisp_
         mbar_arrive_expect_tx(bars_u32 + 8 * slot, kMapBytes);
         bulk_load(slots_u32 + slot * kMapBytes, src, kMapBytes, bars_u32 + 8 * slot, pol);
     };
+    // LAZY: both units of the group's map number j (y_adv -> 16 KB slot j & 1, the two heads -> 5 KB slot j & 1)
+    auto request_lazy = [&](int j) {
+        const int b = j & 1;
+        const size_t mp = static_cast<size_t>(m0 + grp + j * NG);
+        const uint32_t hb = slots_u32 + 2 * kMapBytes + b * kHeadBytes;
+        mbar_arrive_expect_tx(bars_u32 + 8 * (2 + b), kHeadBytes);
+        bulk_load(hb, a.f_lo + mp * (kRDDLoBytes / 4), kRDDLoBytes, bars_u32 + 8 * (2 + b), pol);
+        bulk_load(hb + kRDDLoBytes, a.f_mid + mp * (kRDDMidBytes / 4), kRDDMidBytes, bars_u32 + 8 * (2 + b), pol);
+        mbar_arrive_expect_tx(bars_u32 + 8 * b, kMapBytes);
+        bulk_load(slots_u32 + b * kMapBytes, a.y_adv + mp * kRDDPixels, kMapBytes, bars_u32 + 8 * b, pol);
+    };
     // The kernel is launched as a PROGRAMMATIC DEPENDENT of the decode launch (hp_decode.cu): its blocks become resident
     // while the decode grid drains.  The first units (inputs the decode does not write) are requested at once; the
     // builder warp alone waits for the decode to complete before it touches the centres, everybody else meets it at the
     // block barrier below.  Nothing is written to global memory before that barrier.
     if (warp < W) {
         if (h == 0 && lane == 0) {
-            for (int s = 0; s < NS; ++s) mbar_init(bars_u32 + 8 * s, 1);
+            for (int s = 0; s < kGroupBars; ++s) mbar_init(bars_u32 + 8 * s, 1);
             mbar_init_fence();
-            for (int u = 0; u < NS && u < n_units; ++u) request(u, u);
+            if constexpr (LAZY) {
+                for (int j = 0; j < 2 && j < n_my; ++j) request_lazy(j);
+            } else {
+                for (int u = 0; u < NS && u < n_units; ++u) request(u, u);
+            }
         }
     } else {
         griddep_wait();
@@ -470,6 +589,15 @@ __global__ void __launch_bounds__(32 * (RDDShape<FUSED, GW>::W + 1), 1) regdisp_
             slot_c = (s + 1 == NS) ? 0 : s + 1;
             return s;
         };
+        // LAZY: heads and y_adv of the group's map jj have landed; their byte offsets inside the group's slots
+        auto wait_lazy = [&](int j, uint32_t& f_off, uint32_t& p_off) {
+            const int b = j & 1;
+            const uint32_t parity = static_cast<uint32_t>(j >> 1) & 1u;
+            mbar_wait(bars_u32 + 8 * (2 + b), parity);  // the heads; y_adv is awaited (wait_lazy_p) after the fused blocks are built
+            f_off = 2 * kMapBytes + b * kHeadBytes;
+            p_off = b * kMapBytes;
+        };
+        auto wait_lazy_p = [&](int j) { mbar_wait(bars_u32 + 8 * (j & 1), static_cast<uint32_t>(j >> 1) & 1u); };
         int r_done = 0;  // samples [0, r_done) of the block have been released by this warp
         int k = m0 + grp - sample0 * K, r = 0;  // joint and block-relative sample of the current map
         // wait for a sample's lp; the samples before it are released in order, each only after ITS lp has been seen
@@ -483,6 +611,9 @@ __global__ void __launch_bounds__(32 * (RDDShape<FUSED, GW>::W + 1), 1) regdisp_
             }
             if (r_want < n_samples) mbar_wait(lpf_u32 + 8 * (r_want & 1), static_cast<uint32_t>(r_want >> 1) & 1u);
         };
+        // LAZY: this lane's two 4x4 blocks of the fused map - column block bn, block rows bm, bm + 1 (the walk of
+        // fuse_block_kernel<4, 2, ., 2>: warp h of the group covers output rows 16 h .. 16 h + 15)
+        const int bn = lane & 15, bm = (h * 2 + (lane >> 4)) * 2;
         FxReg fx{0, 0, 0, 0, 0};
         int jj = 0;  // the group's map counter
         for (int i = grp; i < q_total; i += NG, ++jj) {
@@ -500,13 +631,27 @@ __global__ void __launch_bounds__(32 * (RDDShape<FUSED, GW>::W + 1), 1) regdisp_
             if (wt) wt[0] = rdd_now();
             if (TASK == RD_BWD) {
                 // ---- backward: d/dp = coef (softmax(p) - u / S),  u = g / M + eps   -----------------
-                const int sf = FUSED ? wait_unit() : 0, sp = wait_unit();
-                freed0 = FUSED ? sf : sp;
-                const float4* P4 = reinterpret_cast<const float4*>(my_slots + sp * kMapBytes);
+                uint32_t f_off = 0, p_off = 0;
+                if constexpr (LAZY) {
+                    wait_lazy(jj, f_off, p_off);
+                    freed0 = 0;
+                } else {
+                    const int sf = FUSED ? wait_unit() : 0, sp = wait_unit();
+                    freed0 = FUSED ? sf : sp;
+                    f_off = sf * kMapBytes;
+                    p_off = sp * kMapBytes;
+                }
+                const float4* P4 = reinterpret_cast<const float4*>(my_slots + p_off);
                 const float* P = reinterpret_cast<const float*>(P4);
-                const float4* F4 = reinterpret_cast<const float4*>(my_slots + sf * kMapBytes);  // FUSED only
-                const float* F = reinterpret_cast<const float*>(F4);
+                const float4* F4 = reinterpret_cast<const float4*>(my_slots + f_off);  // FUSED only
+                const float* F = reinterpret_cast<const float*>(F4);                            // (LAZY: the heads, 16x16 then 32x32)
                 if (wt) wt[1] = rdd_now();
+                float4 fv[LAZY ? 8 : 1];
+                if constexpr (LAZY)  // before the label is awaited: the fused values of this lane's blocks
+                {
+                    rdd_fused_blocks(slots_u32 + f_off, slots_u32 + f_off + kRDDLoBytes, a.a_lo, a.a_mid, bn, bm, fv);
+                    wait_lazy_p(jj);
+                }
                 advance_to(r);
                 if (wt) wt[2] = rdd_now();
                 const Centre ck = sh.c[slot][k];
@@ -524,23 +669,37 @@ __global__ void __launch_bounds__(32 * (RDDShape<FUSED, GW>::W + 1), 1) regdisp_
                     const bool in = static_cast<unsigned>(x) < static_cast<unsigned>(ow) && static_cast<unsigned>(y) < static_cast<unsigned>(oh);
                     const int off = in ? y * ow + x : 0;
                     float g = rdd_patch_value(a.variant, lp[off], sl.t[kk], k, K, x, y, sh.tab, tmp, sh.c[slot]);
-                    if (FUSED) g = clip01(__fsub_rn(__fadd_rn(g, F[off]), __fmul_rn(sl.t[kk], 100.0f)));
+                    if (FUSED) {
+                        const float fval = LAZY ? rdd_fused_at(F, F + kRDDLoBytes / 4, a.a_lo, a.a_mid, in ? x : 0, in ? y : 0) : F[off];
+                        g = clip01(__fsub_rn(__fadd_rn(g, fval), __fmul_rn(sl.t[kk], 100.0f)));
+                    }
                     gk[kk] = fmaf(coef, ex2_approx(fmaf(P[off], kLog2e, lb)), fmaf(g, k1, k0));
                     poff[kk] = in ? off : -1;
                 }
                 if (wt) wt[3] = rdd_now();
                 const float2 lb2 = make_float2(lb, lb), k12 = make_float2(k1, k1), k02 = make_float2(k0, k0), c2 = make_float2(coef, coef);
                 float4* out4 = reinterpret_cast<float4*>(gout);
-#pragma unroll
-                for (int it = h * IT; it < (h + 1) * IT; ++it) {
-                    const float4 v = P4[it * 32 + lane];
-                    float4 g = LP4[it * 32 + lane];
-                    if (FUSED) g = clip01_4(add4(g, F4[it * 32 + lane]));
+                auto grad4 = [&](int i4, float4 g) {  // float4 number i4 of the map: gradient from the prediction and g
+                    const float4 v = P4[i4];
                     const float2 a0 = __ffma2_rn(make_float2(v.x, v.y), l2e, lb2), a1 = __ffma2_rn(make_float2(v.z, v.w), l2e, lb2);
                     const float2 q0 = __ffma2_rn(make_float2(g.x, g.y), k12, k02), q1 = __ffma2_rn(make_float2(g.z, g.w), k12, k02);
                     const float2 r0 = __ffma2_rn(c2, make_float2(ex2_approx(a0.x), ex2_approx(a0.y)), q0);
                     const float2 r1 = __ffma2_rn(c2, make_float2(ex2_approx(a1.x), ex2_approx(a1.y)), q1);
-                    stg_stream4(out4 + it * 32 + lane, make_float4(r0.x, r0.y, r1.x, r1.y));
+                    stg_stream4(out4 + i4, make_float4(r0.x, r0.y, r1.x, r1.y));
+                };
+                if constexpr (LAZY) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {  // the lane's blocks: row 4 bm + q, columns 4 bn .. 4 bn + 3
+                        const int i4 = (4 * bm + q) * kRDDRow4 + bn;
+                        grad4(i4, clip01_4(add4(LP4[i4], fv[q])));
+                    }
+                } else {
+#pragma unroll
+                    for (int it = h * IT; it < (h + 1) * IT; ++it) {
+                        float4 g = LP4[it * 32 + lane];
+                        if (FUSED) g = clip01_4(add4(g, F4[it * 32 + lane]));
+                        grad4(it * 32 + lane, g);
+                    }
                 }
                 if (wt) wt[4] = rdd_now();
                 // every warp of the group has issued its stores of the map (and read the slots out): the patch pixels are
@@ -550,10 +709,14 @@ __global__ void __launch_bounds__(32 * (RDDShape<FUSED, GW>::W + 1), 1) regdisp_
                 for (int kk = 0; kk < NSL; ++kk)
                     if (poff[kk] >= 0) gout[poff[kk]] = gk[kk];
                 if (leader && lane == 0) {
-                    int s = freed0;
-                    for (int c = 0; c < UPM; ++c) {
-                        if (u_load + c < n_units) request(u_load + c, s);
-                        s = (s + 1 == NS) ? 0 : s + 1;
+                    if constexpr (LAZY) {
+                        if (jj + 2 < n_my) request_lazy(jj + 2);
+                    } else {
+                        int s = freed0;
+                        for (int c = 0; c < UPM; ++c) {
+                            if (u_load + c < n_units) request(u_load + c, s);
+                            s = (s + 1 == NS) ? 0 : s + 1;
+                        }
                     }
                 }
                 if (wt) wt[5] = rdd_now();
@@ -659,13 +822,27 @@ __global__ void __launch_bounds__(32 * (RDDShape<FUSED, GW>::W + 1), 1) regdisp_
                 }
                 u_load += UPM;
             } else {
-                const int sf = wait_unit(), sp = wait_unit();
-                freed0 = sf;
-                const float4* P4 = reinterpret_cast<const float4*>(my_slots + sp * kMapBytes);
+                uint32_t f_off = 0, p_off = 0;
+                if constexpr (LAZY) {
+                    wait_lazy(jj, f_off, p_off);
+                    freed0 = 0;
+                } else {
+                    const int sf = wait_unit(), sp = wait_unit();
+                    freed0 = sf;
+                    f_off = sf * kMapBytes;
+                    p_off = sp * kMapBytes;
+                }
+                const float4* P4 = reinterpret_cast<const float4*>(my_slots + p_off);
                 const float* P = reinterpret_cast<const float*>(P4);
-                float4* F4 = reinterpret_cast<float4*>(my_slots + sf * kMapBytes);
-                float* F = reinterpret_cast<float*>(F4);
+                float4* F4 = reinterpret_cast<float4*>(my_slots + f_off);
+                float* F = reinterpret_cast<float*>(F4);  // (LAZY: the heads, 16x16 then 32x32; read only)
                 if (wt) wt[1] = rdd_now();
+                float4 fv[LAZY ? 8 : 1];
+                if constexpr (LAZY)  // before the label is awaited: the fused values of this lane's blocks
+                {
+                    rdd_fused_blocks(slots_u32 + f_off, slots_u32 + f_off + kRDDLoBytes, a.a_lo, a.a_mid, bn, bm, fv);
+                    wait_lazy_p(jj);
+                }
                 advance_to(r);
                 if (wt) wt[2] = rdd_now();
                 const Centre ck = sh.c[slot][k];
@@ -679,26 +856,47 @@ __global__ void __launch_bounds__(32 * (RDDShape<FUSED, GW>::W + 1), 1) regdisp_
                     const int x = ck.x + sl.dx[kk], y = ck.y + sl.dy[kk];
                     const bool in = static_cast<unsigned>(x) < static_cast<unsigned>(ow) && static_cast<unsigned>(y) < static_cast<unsigned>(oh);
                     const int off = in ? y * ow + x : 0;
-                    const float lpv = lp[off], fv = F[off];
+                    const float lpv = lp[off];
+                    const float fval = LAZY ? rdd_fused_at(F, F + kRDDLoBytes / 4, a.a_lo, a.a_mid, in ? x : 0, in ? y : 0) : F[off];
                     pk[kk] = P[off];
                     float g = clip01(__fsub_rn(lpv, __fmul_rn(sl.t[kk], 10.0f)));
-                    g = clip01(__fsub_rn(__fadd_rn(g, fv), __fmul_rn(sl.t[kk], 100.0f)));
+                    g = clip01(__fsub_rn(__fadd_rn(g, fval), __fmul_rn(sl.t[kk], 100.0f)));
                     gex[kk] = g;
                     poff[kk] = in ? off : -1;
                     mg = in ? fmaxf(mg, g) : mg;
                 }
+                if constexpr (LAZY) {
+                    // ---- pass 1 in registers: g = clip(lp + f) of the lane's blocks, 0 on the own patch (its exact values are
+                    //      in gex); nothing is written to the slot, so no barrier separates the patch step from this pass
+                    if (wt) wt[3] = rdd_now();
 #pragma unroll
-                for (int kk = 0; kk < NSL; ++kk)
-                    if (poff[kk] >= 0) F[poff[kk]] = -INFINITY;   // a patch pixel belongs to exactly one lane of the group
-                group_barrier(bar_id, 32 * G);
-                if (wt) wt[3] = rdd_now();
-                // ---- pass 1: g = clip(lp + f) written over f, its maximum; the softmax reference is sampled ------------
+                    for (int q = 0; q < 8; ++q) {
+                        const int Y = 4 * bm + q;
+                        float4 g = clip01_4(add4(LP4[Y * kRDDRow4 + bn], fv[q]));
+                        if (static_cast<unsigned>(Y - ck.y + tmp) <= static_cast<unsigned>(2 * tmp)) {
+                            const int dx0 = 4 * bn - ck.x + tmp;  // column c of the float4 lies in the patch iff 0 <= dx0 + c <= 2 tmp
+                            g.x = (static_cast<unsigned>(dx0 + 0) <= static_cast<unsigned>(2 * tmp)) ? 0.0f : g.x;
+                            g.y = (static_cast<unsigned>(dx0 + 1) <= static_cast<unsigned>(2 * tmp)) ? 0.0f : g.y;
+                            g.z = (static_cast<unsigned>(dx0 + 2) <= static_cast<unsigned>(2 * tmp)) ? 0.0f : g.z;
+                            g.w = (static_cast<unsigned>(dx0 + 3) <= static_cast<unsigned>(2 * tmp)) ? 0.0f : g.w;
+                        }
+                        fv[q] = g;
+                        mg = fmaxf(mg, max4(g));
+                    }
+                } else {
 #pragma unroll
-                for (int it = h * IT; it < (h + 1) * IT; ++it) {
-                    const float4 f = F4[it * 32 + lane], l = LP4[it * 32 + lane];
-                    const float4 g = clip01_4(add4(l, f));
-                    F4[it * 32 + lane] = g;
-                    mg = fmaxf(mg, max4(g));
+                    for (int kk = 0; kk < NSL; ++kk)
+                        if (poff[kk] >= 0) F[poff[kk]] = -INFINITY;   // a patch pixel belongs to exactly one lane of the group
+                    group_barrier(bar_id, 32 * G);
+                    if (wt) wt[3] = rdd_now();
+                    // ---- pass 1: g = clip(lp + f) written over f, its maximum; the softmax reference is sampled ------------
+#pragma unroll
+                    for (int it = h * IT; it < (h + 1) * IT; ++it) {
+                        const float4 f = F4[it * 32 + lane], l = LP4[it * 32 + lane];
+                        const float4 g = clip01_4(add4(l, f));
+                        F4[it * 32 + lane] = g;
+                        mg = fmaxf(mg, max4(g));
+                    }
                 }
                 {
                     const float wmg = warp_max_f32(mg);
@@ -714,24 +912,16 @@ __global__ void __launch_bounds__(32 * (RDDShape<FUSED, GW>::W + 1), 1) regdisp_
                 const float ms = (Mp == -INFINITY) ? 0.0f : Mp;
                 const float mb = -ms * kLog2e;
                 const float2 mb2 = make_float2(mb, mb), im2 = make_float2(invM, invM), e2 = make_float2(eps, eps);
-                float2 s2 = make_float2(0.f, 0.f), su2 = make_float2(0.f, 0.f), sup2 = make_float2(0.f, 0.f), suq2 = make_float2(0.f, 0.f);
-                float2 sulg2 = make_float2(0.f, 0.f), sulh2 = make_float2(0.f, 0.f);
+                const float2 z2 = make_float2(0.f, 0.f);
+                RDDFusedAcc A{z2, z2, z2, z2, z2, z2};
+                if constexpr (LAZY) {
 #pragma unroll
-                for (int it = h * IT; it < (h + 1) * IT; ++it) {
-                    const float4 v = P4[it * 32 + lane], g = F4[it * 32 + lane];
-                    const float2 lo = make_float2(v.x, v.y), hi = make_float2(v.z, v.w);
-                    const float2 a0 = __ffma2_rn(lo, l2e, mb2), a1 = __ffma2_rn(hi, l2e, mb2);
-                    s2 = __fadd2_rn(s2, __fadd2_rn(make_float2(ex2_approx(a0.x), ex2_approx(a0.y)),
-                                                   make_float2(ex2_approx(a1.x), ex2_approx(a1.y))));
-                    const float2 u0 = __ffma2_rn(make_float2(g.x, g.y), im2, e2), u1 = __ffma2_rn(make_float2(g.z, g.w), im2, e2);
-                    su2 = __fadd2_rn(su2, __fadd2_rn(u0, u1));
-                    sup2 = __ffma2_rn(u0, a0, sup2);
-                    suq2 = __ffma2_rn(u1, a1, suq2);
-                    const float2 q0 = make_float2(lg2_approx(fmaxf(u0.x, 1.17549435e-38f)), lg2_approx(fmaxf(u0.y, 1.17549435e-38f)));
-                    const float2 q1 = make_float2(lg2_approx(fmaxf(u1.x, 1.17549435e-38f)), lg2_approx(fmaxf(u1.y, 1.17549435e-38f)));
-                    sulg2 = __ffma2_rn(u0, q0, sulg2);
-                    sulh2 = __ffma2_rn(u1, q1, sulh2);
+                    for (int q = 0; q < 8; ++q) rdd_fused_acc(A, P4[(4 * bm + q) * kRDDRow4 + bn], fv[q], l2e, mb2, im2, e2);
+                } else {
+#pragma unroll
+                    for (int it = h * IT; it < (h + 1) * IT; ++it) rdd_fused_acc(A, P4[it * 32 + lane], F4[it * 32 + lane], l2e, mb2, im2, e2);
                 }
+                const float2 s2 = A.s2, su2 = A.su2, sup2 = A.sup2, suq2 = A.suq2, sulg2 = A.sulg2, sulh2 = A.sulh2;
                 if (wt) wt[4] = rdd_now();
                 // this warp's patch pixels went through the passes as g = 0 (u = eps): replace by the exact values
                 float c_u = 0.f, c_up = 0.f, c_ulg = 0.f;
@@ -775,10 +965,14 @@ __global__ void __launch_bounds__(32 * (RDDShape<FUSED, GW>::W + 1), 1) regdisp_
                     }
                     __syncwarp();
                     if (lane == 0) {
-                        int s = freed0;
-                        for (int c = 0; c < UPM; ++c) {
-                            if (u_load + c < n_units) request(u_load + c, s);
-                            s = (s + 1 == NS) ? 0 : s + 1;
+                        if constexpr (LAZY) {
+                            if (jj + 2 < n_my) request_lazy(jj + 2);
+                        } else {
+                            int s = freed0;
+                            for (int c = 0; c < UPM; ++c) {
+                                if (u_load + c < n_units) request(u_load + c, s);
+                                s = (s + 1 == NS) ? 0 : s + 1;
+                            }
                         }
                         if (wt) wt[5] = rdd_now();
                         const float lg_se = lg2_approx(Sexp);
@@ -816,15 +1010,15 @@ __global__ void __launch_bounds__(32 * (RDDShape<FUSED, GW>::W + 1), 1) regdisp_
     }
 }
 
-template <bool FUSED, int GW, int TASK>
+template <bool FUSED, int GW, int TASK, bool LAZY = false>
 static int launch_rdd_shape(const RDArgs& a, int sms, cudaStream_t stream, const char* who) {
-    constexpr size_t smem = RDDShape<FUSED, GW>::kSmem;
+    constexpr size_t smem = LAZY ? RDDShape<FUSED, GW>::kLazySmem : RDDShape<FUSED, GW>::kSmem;
     static bool attr_done_dev[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     bool& attr_done = attr_done_dev[dev & 63];
     if (!attr_done) {
-        const cudaError_t e = cudaFuncSetAttribute(regdisp_dense_kernel<FUSED, GW, TASK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        const cudaError_t e = cudaFuncSetAttribute(regdisp_dense_kernel<FUSED, GW, TASK, LAZY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                    static_cast<int>(smem));
         if (e != cudaSuccess) return fail(static_cast<int>(e), "%s: %s", who, cudaGetErrorString(e));
         attr_done = true;
@@ -846,7 +1040,7 @@ static int launch_rdd_shape(const RDArgs& a, int sms, cudaStream_t stream, const
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = (TASK == RD_FWD) ? 1 : 0;
-    const cudaError_t e = cudaLaunchKernelEx(&cfg, regdisp_dense_kernel<FUSED, GW, TASK>, a);
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, regdisp_dense_kernel<FUSED, GW, TASK, LAZY>, a);
     if (e != cudaSuccess) return fail(static_cast<int>(e), "%s: %s", who, cudaGetErrorString(e));
     return launch_status(who);
 }
@@ -875,6 +1069,10 @@ static int launch_regdisp_dense(RDArgs a, cudaStream_t stream, const char* who) 
     a.wdiv = FastDiv(static_cast<uint32_t>(a.ow));
     a.sdiv = FastDiv(static_cast<uint32_t>(2 * a.tmp + 1));
     a.trace = (g_rdd_trace && g_rdd_trace_words >= static_cast<size_t>(sms) * kRDDTraceBlockWords) ? g_rdd_trace : nullptr;
+    if (a.f_lo != nullptr) {  // the fused map built in the kernel from its two heads (hp_regdisp_fwd_heads / _bwd_heads): x6 only
+        if (a.variant != HP_RD_X6 || a.f_mid == nullptr || a.fused != nullptr || a.ow != 64 || a.oh != 64) return 1;
+        return launch_rdd_shape<true, 4, TASK, true>(a, sms, stream, who);
+    }
     const bool fused = a.fused != nullptr && a.variant == HP_RD_X6;
     // warps per map with a fused map: HP_RDD_G=2|4 overrides the default (comparison runs)
     static const int g_env = []() {

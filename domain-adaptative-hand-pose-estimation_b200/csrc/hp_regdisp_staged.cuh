@@ -33,6 +33,10 @@ enum RDTask { RD_FWD = 0, RD_BWD = 1, RD_MATERIALIZE = 2 };
 struct RDArgs {
     const float* y_adv;
     const float* fused;
+    // dense kernel only: the fused map as its two heads, fused = a_lo up64(f_lo) + a_mid up64(f_mid) (16x16 / 32x32 per map)
+    const float* f_lo;
+    const float* f_mid;
+    float a_lo, a_mid;
     const float* weight;
     int variant, mode;
     float eps;

@@ -64,3 +64,36 @@ def fuse_three_scales(lo, mid, hi):
     """BASELINE.json configs[3]: the same rule over three resolutions (e.g. 32/64/128):
     ``0.5*up(lo) + up(mid) + hi`` at the resolution of ``hi``."""
     return _fuse(lo, 0.5, mid, 1.0, hi, 1.0, (hi.shape[2], hi.shape[3]))
+
+
+class FusedHeads:
+    """``a_lo * up(lo) + a_mid * up(mid)`` at ``size`` x ``size`` - the ``target5`` of train1.py:410-424 - NOT materialised.
+
+    Pass it where ``RegressionDisparityx6.forward`` takes ``y_adv2``
+    (``regression_disparity(y_t, y_t_adv, FusedHeads(y_t_adv3, y_t_adv2), weight_t, mode='max')`` instead of building
+    ``target5`` first): for the driver's geometry (16x16 and 32x32 heads, 64x64 maps) the loss kernel interpolates the
+    fused values from the two heads itself (``hp_regdisp_fwd_heads``; 5 KB read per map instead of 16 KB written and
+    16 KB read, no fusion launch), bit-identical to the materialised map.  Every other consumer gets :meth:`materialise`
+    (one ``hp_fuse_multiscale`` launch, cached)."""
+
+    def __init__(self, lo, mid, a_lo=0.5, a_mid=1.0, size=64):
+        self.lo = _lib.require_cuda(lo.detach(), "FusedHeads(lo)")
+        self.mid = _lib.require_cuda(mid.detach(), "FusedHeads(mid)")
+        if self.lo.ndim != 4 or self.mid.ndim != 4 or self.mid.shape[:2] != self.lo.shape[:2]:
+            raise ValueError("FusedHeads: lo and mid must be [B,K,h,w] with equal batch / joint dims")
+        self.a_lo, self.a_mid, self.size = float(a_lo), float(a_mid), int(size)
+        self._map = None
+
+    @property
+    def shape(self):
+        return (self.lo.shape[0], self.lo.shape[1], self.size, self.size)
+
+    def in_kernel(self):
+        """True when the dense disparity kernel can build the map itself (16x16 / 32x32 -> 64x64)."""
+        return (self.size == 64 and tuple(self.lo.shape[2:]) == (16, 16) and tuple(self.mid.shape[2:]) == (32, 32)
+                and self.lo.data_ptr() % 16 == 0 and self.mid.data_ptr() % 16 == 0)
+
+    def materialise(self):
+        if self._map is None:
+            self._map = _fuse(self.lo, self.a_lo, self.mid, self.a_mid, None, 0.0, self.size)
+        return self._map

@@ -26,7 +26,7 @@ def _flat_weight(w, B, K, device):
 class _NoCtx:
     """Stand-in for the autograd context when no gradient is wanted: the forward bodies below run as plain
     functions then (``torch.autograd.Function.apply`` alone costs more host time than the kernel takes)."""
-    __slots__ = ("reduction", "epsilon", "cfg", "fz", "w")
+    __slots__ = ("reduction", "epsilon", "cfg", "fz", "w", "heads")
 
     def save_for_backward(self, *tensors):
         pass

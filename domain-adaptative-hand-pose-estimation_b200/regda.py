@@ -28,6 +28,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
+from .fusion import FusedHeads
 from .loss import JointsKLLoss, _NoCtx, _wants_grad
 
 _VARIANT_CODE = {"base": _lib.RD_BASE, "x1": _lib.RD_X1, "x5": _lib.RD_X5, "x6": _lib.RD_X6, "rd4": _lib.RD_RD4}
@@ -111,7 +112,18 @@ class _RegDisp(torch.autograd.Function):
         if tuple(adv.shape) != (B, K, oh, ow):
             raise ValueError(f"y_adv is {tuple(adv.shape)}, the pseudo-label grid is {(B, K, oh, ow)}")
         dev = adv.device
-        fz = None
+        fz = heads = None
+        if isinstance(fused, FusedHeads):
+            # y_adv2 given as its two heads (train1.py:410-424 unfused): x6 'max' on the 64x64 grid builds the map inside the loss
+            # kernel; 'min' never reads y_adv2 (regda_7.py:3614-3631); everything else gets the materialised map
+            if tuple(fused.shape) != (B, K, oh, ow):
+                raise ValueError(f"y_adv2 is {tuple(fused.shape)}, expected {(B, K, oh, ow)}")
+            if mode == _lib.MODE_MIN:
+                fused = None
+            elif variant == _lib.RD_X6 and fused.in_kernel() and (H, W) == (oh, ow) and tmp <= 6 and K <= 32:
+                heads, fused = fused, None
+            else:
+                fused = fused.materialise()
         if fused is not None:
             fz = _lib.require_cuda(fused.detach(), "RegressionDisparity(y_adv2)")
             if tuple(fz.shape) != (B, K, oh, ow):
@@ -131,14 +143,20 @@ class _RegDisp(torch.autograd.Function):
         with _lib.on_device(dev):
             tab = _lib.gaussian_table(plg.sigma, tmp, dev)
             ws = _lib.workspace(dev, B * K, K)
-            _lib.call("hp_regdisp_fwd", _lib.ptr(yd), _lib.ptr(adv), _lib.ptr(fz), _lib.ptr(w), variant, mode,
-                      C.c_float(epsilon), B, K, H, W, oh, ow, shift, tmp, _lib.ptr(tab), p_per_map,
-                      _lib.ptr(per_sample), _lib.ptr(mean), p_stats, p_centres, _lib.ptr(ws),
-                      _lib.stream_ptr(dev))
+            if heads is not None:
+                _lib.call("hp_regdisp_fwd_heads", _lib.ptr(yd), _lib.ptr(adv), _lib.ptr(heads.lo), 16, 16, C.c_float(heads.a_lo),
+                          _lib.ptr(heads.mid), 32, 32, C.c_float(heads.a_mid), _lib.ptr(w), variant, mode, C.c_float(epsilon),
+                          B, K, H, W, oh, ow, tmp, _lib.ptr(tab), p_per_map, _lib.ptr(per_sample), _lib.ptr(mean), p_stats,
+                          p_centres, _lib.ptr(ws), _lib.stream_ptr(dev))
+            else:
+                _lib.call("hp_regdisp_fwd", _lib.ptr(yd), _lib.ptr(adv), _lib.ptr(fz), _lib.ptr(w), variant, mode,
+                          C.c_float(epsilon), B, K, H, W, oh, ow, shift, tmp, _lib.ptr(tab), p_per_map,
+                          _lib.ptr(per_sample), _lib.ptr(mean), p_stats, p_centres, _lib.ptr(ws),
+                          _lib.stream_ptr(dev))
         ctx.save_for_backward(adv, pack, tab)
-        ctx.fz, ctx.w = fz, w
+        ctx.fz, ctx.w, ctx.heads = fz, w, heads
         ctx.cfg = (variant, mode, float(epsilon), reduction, B, K, oh, ow, tmp)
-        holder._remember(variant, fz, pack, tab, (B, K, oh, ow, tmp))
+        holder._remember(variant, heads if heads is not None else fz, pack, tab, (B, K, oh, ow, tmp))
         return mean if reduction == "mean" else per_sample
 
     @staticmethod
@@ -154,9 +172,16 @@ class _RegDisp(torch.autograd.Function):
         kind = _lib.GRAD_SCALAR if reduction == "mean" else _lib.GRAD_PER_SAMPLE
         grad_in = torch.empty_like(adv)
         with _lib.on_device(dev):
-            _lib.call("hp_regdisp_bwd", _lib.ptr(adv), _lib.ptr(ctx.fz), _lib.ptr(ctx.w), variant, mode, C.c_float(eps),
-                      B, K, oh, ow, tmp, _lib.ptr(tab), p_centres, p_stats, _lib.ptr(go), kind,
-                      _lib.ptr(grad_in), _lib.stream_ptr(dev))
+            heads = getattr(ctx, "heads", None)
+            if heads is not None:
+                _lib.call("hp_regdisp_bwd_heads", _lib.ptr(adv), _lib.ptr(heads.lo), 16, 16, C.c_float(heads.a_lo),
+                          _lib.ptr(heads.mid), 32, 32, C.c_float(heads.a_mid), _lib.ptr(ctx.w), variant, mode, C.c_float(eps),
+                          B, K, oh, ow, tmp, _lib.ptr(tab), p_centres, p_stats, _lib.ptr(go), kind, _lib.ptr(grad_in),
+                          _lib.stream_ptr(dev))
+            else:
+                _lib.call("hp_regdisp_bwd", _lib.ptr(adv), _lib.ptr(ctx.fz), _lib.ptr(ctx.w), variant, mode, C.c_float(eps),
+                          B, K, oh, ow, tmp, _lib.ptr(tab), p_centres, p_stats, _lib.ptr(go), kind,
+                          _lib.ptr(grad_in), _lib.stream_ptr(dev))
         return (grad_in,) + (None,) * 9
 
 
@@ -183,6 +208,8 @@ class _RDBase(nn.Module):
             if self._lazy is None:
                 raise AttributeError("ground_truth / ground_false exist only after a forward call")
             variant, fused, centres, tab, (B, K, oh, ow, tmp) = self._lazy
+            if isinstance(fused, FusedHeads):
+                fused = fused.materialise()
             dev = centres.device
             gt = torch.empty((B, K, oh, ow), dtype=torch.float32, device=dev)
             gf = torch.empty_like(gt)
@@ -222,6 +249,8 @@ class _RDBase(nn.Module):
         from .keypoint_detection import decode
         yd, (B, K, H, W), (oh, ow, shift, tmp, _) = plg._check_input(y)
         dev = yd.device
+        if isinstance(y_adv2, FusedHeads):
+            y_adv2 = y_adv2.materialise()
         fz = None if y_adv2 is None else _lib.require_cuda(y_adv2.detach(), "y_adv2")
         preds, _ = decode(yd)
         centres = (preds.reshape(-1, 2).to(torch.int32) >> shift).contiguous()

@@ -149,6 +149,22 @@ int hp_regdisp_bwd(const float* y_adv, const float* fused, const float* weight, 
                    float epsilon, int B, int K, int oh, int ow, int tmp, const float* tab,
                    const int32_t* centres, const float* stats, const float* grad_out, int grad_kind,
                    float* grad_in, hp_stream_t stream);
+/* RegressionDisparityx6 mode='max' with its y_adv2 argument given UNFUSED, as the two heads train1.py:410-424 builds it from:
+ * fused = a_lo * up64(f_lo) + a_mid * up64(f_mid), f_lo [B,K,16,16], f_mid [B,K,32,32] (nn.Upsample bilinear; train1.py:
+ * target5 = 0.5 up(y_adv3) + up(y_adv2) -> a_lo 0.5, a_mid 1).  The fused map is interpolated inside the loss kernel from the
+ * staged heads (values bit-identical to hp_fuse_multiscale) and never exists in memory: 37,888 B per map instead of 49,152 +
+ * the fusion launch (SURVEY.md 8d, configs[2]).  Only x6 / 'max' / 64x64 label grids; anything else -> HP_ERR_ARG /
+ * HP_ERR_SHAPE (materialise with hp_fuse_multiscale and call hp_regdisp_fwd).  Outputs as hp_regdisp_fwd / _bwd. */
+int hp_regdisp_fwd_heads(const float* y, const float* y_adv, const float* f_lo, int hl, int wl, float a_lo,
+                         const float* f_mid, int hm, int wm, float a_mid, const float* weight, int variant,
+                         int mode, float epsilon, int B, int K, int H, int W, int oh, int ow, int tmp,
+                         const float* tab, float* per_map, float* per_sample, float* mean, float* stats,
+                         int32_t* centres, void* workspace, hp_stream_t stream);
+int hp_regdisp_bwd_heads(const float* y_adv, const float* f_lo, int hl, int wl, float a_lo, const float* f_mid,
+                         int hm, int wm, float a_mid, const float* weight, int variant, int mode, float epsilon,
+                         int B, int K, int oh, int ow, int tmp, const float* tab, const int32_t* centres,
+                         const float* stats, const float* grad_out, int grad_kind, float* grad_in,
+                         hp_stream_t stream);
 /* the .ground_truth / .ground_false attributes the reference classes expose, on demand */
 int hp_regdisp_materialize(const float* fused, int variant, int B, int K, int oh, int ow, int tmp,
                            const float* tab, const int32_t* centres, float* gt, float* gf,

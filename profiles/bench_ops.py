@@ -118,6 +118,21 @@ with torch.no_grad():
     timed("RegressionDisparityx6 'max' (no fused map)", lambda i: rd6(ys[i], advs[i], None, None, "max"), 3, n * 2 * hw4, n)
     t5 = [hp.fuse_multiscale(f16[i], f32[i], 64, 32)[0] for i in range(3)]
     timed("RegressionDisparityx6 'max' + pre-fused target5", lambda i: rd6(ys[i], advs[i], t5[i], None, "max"), 3, n * 3 * hw4, n)
+    hd = [hp.FusedHeads(f16[i], f32[i]) for i in range(3)]
+    timed("RegressionDisparityx6 'max' + target5 built in the kernel (FusedHeads)", lambda i: rd6(ys[i], advs[i], hd[i], None, "max"), 3,
+          n * (2 * hw4 + 4096 + 1024), n, "reads y + y_adv + 16^2 + 32^2 heads; target5 never written")
+    adv_g = [a.clone().requires_grad_(True) for a in advs]
+
+    def fb(i, f):
+        with torch.enable_grad():
+            adv_g[i].grad = None
+            rd6(ys[i], adv_g[i], f[i], None, "max").backward()
+
+    timed("RegressionDisparityx6 'max' fwd+bwd, pre-fused target5", lambda i: fb(i, t5), 3, n * (6 * hw4), n,
+          "fwd reads y, y_adv, target5; bwd reads y_adv, target5, writes grad")
+    timed("RegressionDisparityx6 'max' fwd+bwd, FusedHeads", lambda i: fb(i, hd), 3, n * (4 * hw4 + 2 * 5120), n,
+          "fwd reads y, y_adv, heads; bwd reads y_adv, heads, writes grad")
+    del adv_g
     timed("fuse_multiscale 16+32 -> 64 and 16 -> 32 (512x21)", lambda i: hp.fuse_multiscale(f16[i], f32[i], 64, 32), 3,
           n * (1024 + 4096 + hw4 + 4096), n, "reads 16^2 + 32^2, writes 64^2 + 32^2")
     rd5 = hp.RegressionDisparityx5(hp.PseudoLabelGenerator03(K), hp.JointsKLLoss(epsilon=1e-7))

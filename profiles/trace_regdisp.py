@@ -18,6 +18,7 @@ L = importlib.import_module("domain-adaptative-hand-pose-estimation_b200._lib")
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--fused", action="store_true")
+ap.add_argument("--heads", action="store_true", help="with --fused: leave the map unfused (hp.FusedHeads, built inside the kernel)")
 ap.add_argument("--batch", type=int, default=512)
 ap.add_argument("--out", default=None)
 args = ap.parse_args()
@@ -31,7 +32,7 @@ f = None
 if args.fused:
     a32 = torch.nn.functional.avg_pool2d(advs[0], 2)
     a16 = torch.nn.functional.avg_pool2d(advs[0], 4)
-    f = hp.fuse_multiscale(a16, a32, 64, 32)[0]
+    f = hp.FusedHeads(a16, a32) if args.heads else hp.fuse_multiscale(a16, a32, 64, 32)[0]
 rd6 = hp.RegressionDisparityx6(hp.PseudoLabelGenerator(K, 64, 64), hp.JointsKLLoss(epsilon=1e-7))
 words = int(lib.hp_debug_regdisp_trace_words())
 buf = torch.zeros(words, dtype=torch.int64, device=dev)
@@ -76,7 +77,7 @@ def q(x):
 
 bu = bld[..., 1] != 0
 res = {
-    "us_per_step_decode_plus_loss": us_step, "fused": args.fused, "batch": B, "blocks": int(t.shape[0]),
+    "us_per_step_decode_plus_loss": us_step, "fused": args.fused, "heads": args.heads, "batch": B, "blocks": int(t.shape[0]),
     "block_entry_ns": q(entry), "block_exit_ns": q(exit_), "kernel_span_ns": float(exit_.max()),
     "first_lp_published_ns": q((bld[:, 0, 1] - t0)), "builder_build_ns": q((bld[..., 1] - bld[..., 0])[bu]),
     "builder_begin_by_sample_ns": [q((bld[:, r, 0] - t0)[bld[:, r, 1] != 0]) for r in range(6)],

@@ -196,3 +196,118 @@ def test_mean_matches_generic_kernel_at_scale(monkeypatch):
     np.testing.assert_allclose(got, want, rtol=2e-6)
     for a, b in zip(got_n, want_n):
         np.testing.assert_allclose(a, b, rtol=1e-5)
+
+
+# ---- x6 'max' with the fused map left UNFUSED (hp.FusedHeads -> hp_regdisp_fwd_heads / _bwd_heads) ---------------------------------
+
+def _heads_case(seed, B):
+    rs = np.random.RandomState(seed)
+    y_h = hp.synth.make_host_batch(seed + 1, B, K, 64, 64)["pred"]
+    adv_h = hp.synth.make_host_batch(seed + 2, B, K, 64, 64)["pred"]
+    mid_h, lo_h = hp.synth.make_lowres_heads(seed + 3, adv_h, (32, 16))
+    return rs, y_h, adv_h, lo_h, mid_h
+
+
+def _run_heads(device, y_h, adv_h, lo_h, mid_h, w_h, go_h, how, mode="max"):
+    """how: 'heads' (hp.FusedHeads: the map is built inside the loss kernel), 'map' (hp.fuse_multiscale, then the pre-fused
+    kernel), 'oracle' (the reference restatement on the CPU: nn.Upsample x 2 + 0.5 a + b, then RegressionDisparityx6)."""
+    from oracle import hp_oracle as O
+    ns = api.namespace() if how == "oracle" else hp
+    t = lambda a: torch.from_numpy(a).to(device)
+    if how == "heads":
+        f = hp.FusedHeads(t(lo_h), t(mid_h))
+    elif how == "map":
+        f = hp.fuse_multiscale(t(lo_h), t(mid_h), 64, 32)[0]
+    else:
+        f = O.fuse_multiscale(t(lo_h), t(mid_h), 64, 32)[0]
+    rd = ns.RegressionDisparityx6(ns.PseudoLabelGenerator(K, 64, 64), ns.JointsKLLoss(reduction="none", epsilon=1e-7))
+    adv = t(adv_h).requires_grad_(True)
+    w = None if w_h is None else t(w_h)
+    l = rd(t(y_h), adv, f, w, mode)
+    l.backward(t(go_h))
+    M = None
+    if how != "oracle" and mode == "max":  # the per-map maxima the kernel normalised by (stats[:, 2] of the packed forward output)
+        n = y_h.shape[0] * K
+        M = rd._lazy[2][n:4 * n].reshape(n, 3)[:, 2].cpu().numpy()
+    rdm = ns.RegressionDisparityx6(ns.PseudoLabelGenerator(K, 64, 64), ns.JointsKLLoss(epsilon=1e-7))
+    with torch.no_grad():
+        m = float(rdm(t(y_h), adv.detach(), f, w, mode))
+    return l.detach().cpu().numpy(), adv.grad.cpu().numpy(), m, M
+
+
+def _close(got, want, rtol):
+    l_g, g_g, m_g, _ = got
+    l_w, g_w, m_w, _ = want
+    np.testing.assert_allclose(l_g, l_w, rtol=rtol, atol=1e-7, equal_nan=True)
+    np.testing.assert_allclose(m_g, m_w, rtol=rtol, equal_nan=True)
+    ok = np.isfinite(g_w)
+    assert np.array_equal(np.isnan(g_g), np.isnan(g_w))
+    np.testing.assert_allclose(g_g[ok], g_w[ok], rtol=rtol, atol=rtol * float(np.abs(g_w[ok]).max()) if ok.any() else 0.0)
+
+
+def test_fused_heads_in_kernel_equals_prefused_map_and_oracle(monkeypatch):
+    """train1.py:410-426 with target5 never materialised: the loss kernel interpolates 0.5 up64(y_adv3) + up64(y_adv2) from the
+    staged 16x16 / 32x32 heads.  Against (a) the same loss on the materialised map (hp.fuse_multiscale + pre-fused kernel):
+    the per-map maxima M are bit-identical (the fused VALUES are the fusion kernel's, bit for bit), losses / gradients agree
+    to 2e-6 (only the summation order differs); (b) the oracle, 1e-5; (c) few blocks == the full grid, bit for bit.  Edge
+    values: heads that drive the label to all-zero (NaN like the reference), NaN / +-inf inside the heads (incl. the clamped
+    first row / column, where a zero-weight tap on inf must still give NaN), clustered centres, NaN in the prediction."""
+    rs, y_h, adv_h, lo_h, mid_h = _heads_case(4601, 9)
+    B = 9
+    mid_h[1] = -3.0                                          # fused map << 0: label all zero -> NaN for the sample
+    lo_h[2] = rs.uniform(-1.6, -0.9, size=(K, 16, 16)).astype(np.float32)
+    mid_h[2] = rs.uniform(-0.4, 0.1, size=(K, 32, 32)).astype(np.float32)      # max(gf) somewhere in (0, 1)
+    lo_h[3, 4, 7, 9] = np.nan
+    lo_h[3, 5, 1, 1] = np.inf                                # tap (0, 1) of the clamped first block row / column: 0 * inf
+    mid_h[3, 6, 31, 31] = -np.inf
+    mid_h[3, 7, 0, 1] = np.inf
+    lo_h[4] = 0.0
+    mid_h[4] = 0.0                                           # the fused map adds nothing
+    centres = rs.randint(28, 34, size=(1, K, 2))
+    y_h[5] = _peaks(rs, 1, centres)[0]                       # clustered centres: own patches overlap every other centre
+    adv_h[6, 3, 20, 20] = np.nan
+    y_h[7] = -np.abs(y_h[7])                                 # all centres (0, 0): patches truncated by the corner
+    w_h = (rs.uniform(size=(B, K, 1)) < 0.85).astype(np.float32)
+    go_h = rs.uniform(0.5, 1.5, size=(B,)).astype(np.float32)
+    heads = _run_heads("cuda", y_h, adv_h, lo_h, mid_h, w_h, go_h, "heads")
+    pre = _run_heads("cuda", y_h, adv_h, lo_h, mid_h, w_h, go_h, "map")
+    ref = _run_heads("cpu", y_h, adv_h, lo_h, mid_h, w_h, go_h, "oracle")
+    assert np.array_equal(heads[3], pre[3], equal_nan=True), "per-map maxima differ: the in-kernel fused values are not the fusion kernel's"
+    _close(heads, pre, 2e-6)
+    _close(heads, ref, 1e-5)
+    l = heads[0]
+    assert np.isnan(l[1]) and np.isnan(l[3]) and np.isnan(l[6]) and np.isfinite(l[0]) and np.isfinite(l[2]) and np.isfinite(l[5])
+    monkeypatch.setenv("HP_RD_GRID", "3")
+    few = _run_heads("cuda", y_h, adv_h, lo_h, mid_h, w_h, go_h, "heads")
+    monkeypatch.delenv("HP_RD_GRID")
+    assert np.array_equal(heads[0], few[0], equal_nan=True) and np.array_equal(heads[1], few[1], equal_nan=True)
+    # weights None, 'mean' through the same kernel
+    _close(_run_heads("cuda", y_h[:3], adv_h[:3], lo_h[:3], mid_h[:3], None, go_h[:3], "heads"),
+           _run_heads("cpu", y_h[:3], adv_h[:3], lo_h[:3], mid_h[:3], None, go_h[:3], "oracle"), 1e-5)
+
+
+def test_fused_heads_fall_back_to_the_materialised_map():
+    """Where the in-kernel fusion does not apply the unfused argument behaves exactly like the tensor it stands for: mode='min'
+    (x6 never reads y_adv2 there), other head sizes (8x8 / 16x16 -> 64x64: hp_fuse_multiscale + the pre-fused kernel), and the
+    lazily materialised .ground_false."""
+    rs, y_h, adv_h, lo_h, mid_h = _heads_case(4701, 4)
+    go_h = rs.uniform(0.5, 1.5, size=(4,)).astype(np.float32)
+    a = _run_heads("cuda", y_h, adv_h, lo_h, mid_h, None, go_h, "heads", mode="min")
+    b = _run_heads("cuda", y_h, adv_h, lo_h, mid_h, None, go_h, "map", mode="min")
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    t = lambda x: torch.from_numpy(x).cuda()
+    lo8 = np.ascontiguousarray(lo_h[:, :, ::2, ::2])
+    rd = hp.RegressionDisparityx6(hp.PseudoLabelGenerator(K, 64, 64), hp.JointsKLLoss(reduction="none", epsilon=1e-7))
+    fh = hp.FusedHeads(t(lo8), t(lo_h))
+    assert not fh.in_kernel()
+    l1 = rd(t(y_h), t(adv_h), fh, None, "max")
+    gf1 = rd.ground_false.clone()
+    l2 = rd(t(y_h), t(adv_h), fh.materialise(), None, "max")
+    assert torch.equal(l1, l2) and torch.equal(gf1, rd.ground_false)
+    # in-kernel path: .ground_false is built from the materialised map on demand and matches the oracle's
+    rd(t(y_h), t(adv_h), hp.FusedHeads(t(lo_h), t(mid_h)), None, "max")
+    from oracle import hp_oracle as O
+    ns = api.namespace()
+    ro = ns.RegressionDisparityx6(ns.PseudoLabelGenerator(K, 64, 64), ns.JointsKLLoss(reduction="none", epsilon=1e-7))
+    ro(torch.from_numpy(y_h), torch.from_numpy(adv_h), O.fuse_multiscale(torch.from_numpy(lo_h), torch.from_numpy(mid_h), 64, 32)[0], None, "max")
+    np.testing.assert_allclose(rd.ground_false.cpu().numpy(), ro.ground_false.numpy(), rtol=1e-5, atol=1e-6)

@@ -60,7 +60,7 @@ def test_config4_shape_pipeline_48x21x128x128_vs_oracle():
     _pipeline_case(48, 128, 2102, True)
 
 
-@pytest.mark.parametrize("mode,fused", [("min", False), ("max", False), ("max", True)])
+@pytest.mark.parametrize("mode,fused", [("min", False), ("max", False), ("max", True), ("max", "heads")])
 def test_config2_regression_disparity_x6_512x21x64x64_vs_oracle(mode, fused):
     B, side = 512, 64
     y_h = hp.synth.make_host_batch(2201, B, K, side, side)["pred"]
@@ -80,6 +80,8 @@ def test_config2_regression_disparity_x6_512x21x64x64_vs_oracle(mode, fused):
     dev = torch.device("cuda", 0)
     y, adv, w = (torch.from_numpy(a).to(dev) for a in (y_h, adv_h, w_h))
     f = None if f_h is None else torch.from_numpy(f_h).to(dev)
+    if fused == "heads":  # the fused map left to the loss kernel (hp_regdisp_fwd_heads): 37,888 B per map
+        f = hp.FusedHeads(torch.from_numpy(a16).to(dev), torch.from_numpy(a32).to(dev))
     plg = hp.PseudoLabelGenerator(K, side, side)
     got_mean = hp.RegressionDisparityx6(plg, hp.JointsKLLoss(epsilon=1e-7))(y, adv, f, w, mode)
     got_none = hp.RegressionDisparityx6(plg, hp.JointsKLLoss(reduction="none", epsilon=1e-7))(y, adv, f, w, mode)
