@@ -52,21 +52,28 @@ __device__ __forceinline__ unsigned long long rdd_now() {
     return t;
 }
 
-template <bool FUSED, int GW>
+// LZ: 0 = the fused map (if any) arrives pre-fused; 4 / 5 = built in the kernel from its heads (LAZY) with 4 / 5 groups.
+// Measured (B200, 512 x 21 maps, forward incl. the decode launch): 4 groups x 2 head slots 112.1 us; 5 groups x 1 head slot
+// (672 threads: 80 registers, 152 B of spills) 114.2 us - a map takes a group 4.4 instead of 3.6 us - so 4 it is.
+constexpr int kRDDLazyGroups = 4;
+template <bool FUSED, int GW, int LZ = 0>
 struct RDDShape {
-    static constexpr int NG = FUSED ? 4 : 6;                 // groups = maps being computed at once
+    static constexpr int NG = LZ ? LZ : (FUSED ? 4 : 6);     // groups = maps being computed at once
     static constexpr int G = GW;                             // warps per group
     static constexpr int W = NG * G;                         // consumer warps
-    static_assert(NG * GW <= 16, "RDDShared::xch / xmx hold 16 consumer warps");
+    static_assert(NG * GW <= 20, "RDDShared::xch / xmx hold 20 consumer warps");
     static constexpr int NS = FUSED ? 3 : 2;                 // slots per group
     static constexpr int UPM = FUSED ? 2 : 1;                // units per map
     static constexpr int IT = 32 / G;                        // iterations per warp and pass
     static constexpr int NSL = (kTileMaxPatch + G - 1) / G;  // patch slots per lane of a consumer warp
     static constexpr size_t kSmem = static_cast<size_t>(NG) * NS * kRDDPixels * 4 + 2 * kRDDPixels * 4;
-    // LAZY (the fused map built from its heads): a group owns two 16 KB slots for y_adv and two 5 KB slots for the heads, so
-    // that BOTH units of the group's next map are in flight while the current one is computed (with a pre-fused map the 3 x
-    // 16 KB rotation leaves the next map's y_adv unrequested until the current map closes)
-    static constexpr size_t kLazyGroupBytes = 2 * kRDDPixels * 4 + 2 * (16 * 16 + 32 * 32) * 4;
+    // LAZY (the fused map built from its heads): a group owns two 16 KB slots for y_adv and 5 KB slots for the heads, so that
+    // the group's next map is in flight while the current one is computed (with a pre-fused map the 3 x 16 KB rotation leaves
+    // the next map's y_adv unrequested until the current map closes: 1.0 us of every map's 3.1 us is a wait for it, 0.13 us
+    // here).  LZ = 4: two head slots.  LZ = 5 (kept for comparison): the forward's heads are dead after pass 1, ONE head slot
+    // re-requested behind the barrier that follows it, and the shared memory saved holds a fifth group.
+    static constexpr int kHeadSlots = (LZ == 5) ? 1 : 2;
+    static constexpr size_t kLazyGroupBytes = 2 * kRDDPixels * 4 + kHeadSlots * (16 * 16 + 32 * 32) * 4;
     static constexpr size_t kLazySmem = static_cast<size_t>(NG) * kLazyGroupBytes + 2 * kRDDPixels * 4;
 };
 
@@ -79,10 +86,10 @@ struct RDDShared {
     float cu[2], culg[2];     // per sample: sum (lp + eps), sum (lp + eps) lg2 (lp + eps)
     float tab[kRDDMaxTab];
     union {
-        float xch[2][16][8];          // forward: [map parity][consumer warp]: the warp's partial sums of a map
+        float xch[2][20][8];          // forward: [map parity][consumer warp]: the warp's partial sums of a map
         RDSMeta meta[2][kRDDMaxK];    // backward: per sample slot and joint {coef, -lse log2 e, 1 / S, M}
     };
-    float xmx[2][16];         // fused: max g of the warp's part
+    float xmx[2][20];         // fused: max g of the warp's part
     unsigned long long acc[kFxAccWords];
 };
 
@@ -241,30 +248,15 @@ constexpr int kRDDLoSide = 16, kRDDMidSide = 32;
 constexpr int kRDDRow4 = 16;  // float4 per row of the 64 x 64 map the heads are fused into
 constexpr int kRDDLoBytes = kRDDLoSide * kRDDLoSide * 4, kRDDMidBytes = kRDDMidSide * kRDDMidSide * 4;
 
-// taps of output coordinate X at the exact scale S (align_corners=False, clamped at 0 and in - 1): the scalar form of BlockAxis
+// taps of output coordinate X at the exact scale S (align_corners=False: src = max(X / S + 0.5 / S - 0.5, 0), exact in fp32 for
+// S in {2, 4}; i0 = floor(src), i1 = min(i0 + 1, in - 1), l1 = src - i0) - the scalar form of BlockAxis, branch-free so that the
+// patch pixels' four bilinear gathers interleave
 template <int S>
 __device__ __forceinline__ void rdd_exact_tap(int X, int in, int& i0, int& i1, float& l1) {
-    if (S == 2) {
-        const int j = X >> 1;
-        if (X & 1) {
-            i0 = j; i1 = min(j + 1, in - 1); l1 = 0.25f;
-        } else if (X == 0) {
-            i0 = 0; i1 = 1; l1 = 0.0f;
-        } else {
-            i0 = j - 1; i1 = j; l1 = 0.75f;
-        }
-    } else {
-        const int m = X >> 2, c = X & 3;
-        if (c < 2) {
-            if (m == 0) {
-                i0 = 0; i1 = 1; l1 = 0.0f;
-            } else {
-                i0 = m - 1; i1 = m; l1 = (c == 0) ? 0.625f : 0.875f;
-            }
-        } else {
-            i0 = m; i1 = min(m + 1, in - 1); l1 = (c == 2) ? 0.125f : 0.375f;
-        }
-    }
+    const float src = fmaxf(fmaf(static_cast<float>(X), 1.0f / S, 0.5f / S - 0.5f), 0.0f);
+    i0 = __float2int_rz(src);
+    l1 = src - static_cast<float>(i0);
+    i1 = min(i0 + 1, in - 1);
 }
 template <int S>
 __device__ __forceinline__ float rdd_bilinear_at(const float* __restrict__ src, int in, int x, int y) {
@@ -325,17 +317,18 @@ __device__ __forceinline__ void rdd_fused_acc(RDDFusedAcc& A, float4 v, float4 g
 }
 
 template <bool FUSED, int GW, int TASK, bool LAZY = false>
-__global__ void __launch_bounds__(32 * (RDDShape<FUSED, GW>::W + 1), 1) regdisp_dense_kernel(const RDArgs a) {
+__global__ void __launch_bounds__(32 * (RDDShape<FUSED, GW, LAZY ? kRDDLazyGroups : 0>::W + 1), 1) regdisp_dense_kernel(const RDArgs a) {
     extern __shared__ __align__(128) unsigned char s_rdd[];
     __shared__ RDDShared sh;
-    using S = RDDShape<FUSED, GW>;
+    using S = RDDShape<FUSED, GW, LAZY ? kRDDLazyGroups : 0>;
+    constexpr int kHeadSlots = S::kHeadSlots;
     constexpr int W = S::W, G = S::G, NG = S::NG, NS = S::NS, UPM = S::UPM, IT = S::IT, NSL = S::NSL;
     constexpr int kMapBytes = kRDDPixels * 4;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int K = a.K, tmp = a.tmp, ow = a.ow, oh = a.oh;
     const float eps = a.eps;
     constexpr size_t kGroupBytes = LAZY ? S::kLazyGroupBytes : static_cast<size_t>(NS) * kMapBytes;
-    constexpr int kGroupBars = LAZY ? 4 : NS;
+    constexpr int kGroupBars = LAZY ? 2 + kHeadSlots : NS;  // LAZY: y_adv slots 0 / 1, then the head slot(s)
     constexpr int kHeadBytes = kRDDLoBytes + kRDDMidBytes;
     float* lp_base = reinterpret_cast<float*>(s_rdd + static_cast<size_t>(NG) * kGroupBytes);
 
@@ -390,16 +383,20 @@ __global__ void __launch_bounds__(32 * (RDDShape<FUSED, GW>::W + 1), 1) regdisp_
         mbar_arrive_expect_tx(bars_u32 + 8 * slot, kMapBytes);
         bulk_load(slots_u32 + slot * kMapBytes, src, kMapBytes, bars_u32 + 8 * slot, pol);
     };
-    // LAZY: both units of the group's map number j (y_adv -> 16 KB slot j & 1, the two heads -> 5 KB slot j & 1)
-    auto request_lazy = [&](int j) {
+    // LAZY: the units of the group's map number j: y_adv -> 16 KB slot j & 1, the two heads -> 5 KB slot j % kHeadSlots
+    auto request_lazy_p = [&](int j) {
         const int b = j & 1;
+        const size_t mp = static_cast<size_t>(m0 + grp + j * NG);
+        mbar_arrive_expect_tx(bars_u32 + 8 * b, kMapBytes);
+        bulk_load(slots_u32 + b * kMapBytes, a.y_adv + mp * kRDDPixels, kMapBytes, bars_u32 + 8 * b, pol);
+    };
+    auto request_lazy_h = [&](int j) {
+        const int b = j % kHeadSlots;
         const size_t mp = static_cast<size_t>(m0 + grp + j * NG);
         const uint32_t hb = slots_u32 + 2 * kMapBytes + b * kHeadBytes;
         mbar_arrive_expect_tx(bars_u32 + 8 * (2 + b), kHeadBytes);
         bulk_load(hb, a.f_lo + mp * (kRDDLoBytes / 4), kRDDLoBytes, bars_u32 + 8 * (2 + b), pol);
         bulk_load(hb + kRDDLoBytes, a.f_mid + mp * (kRDDMidBytes / 4), kRDDMidBytes, bars_u32 + 8 * (2 + b), pol);
-        mbar_arrive_expect_tx(bars_u32 + 8 * b, kMapBytes);
-        bulk_load(slots_u32 + b * kMapBytes, a.y_adv + mp * kRDDPixels, kMapBytes, bars_u32 + 8 * b, pol);
     };
     // The kernel is launched as a PROGRAMMATIC DEPENDENT of the decode launch (hp_decode.cu): its blocks become resident
     // while the decode grid drains.  The first units (inputs the decode does not write) are requested at once; the
@@ -410,7 +407,8 @@ __global__ void __launch_bounds__(32 * (RDDShape<FUSED, GW>::W + 1), 1) regdisp_
             for (int s = 0; s < kGroupBars; ++s) mbar_init(bars_u32 + 8 * s, 1);
             mbar_init_fence();
             if constexpr (LAZY) {
-                for (int j = 0; j < 2 && j < n_my; ++j) request_lazy(j);
+                for (int j = 0; j < kHeadSlots && j < n_my; ++j) request_lazy_h(j);
+                for (int j = 0; j < 2 && j < n_my; ++j) request_lazy_p(j);
             } else {
                 for (int u = 0; u < NS && u < n_units; ++u) request(u, u);
             }
@@ -591,11 +589,11 @@ __global__ void __launch_bounds__(32 * (RDDShape<FUSED, GW>::W + 1), 1) regdisp_
         };
         // LAZY: heads and y_adv of the group's map jj have landed; their byte offsets inside the group's slots
         auto wait_lazy = [&](int j, uint32_t& f_off, uint32_t& p_off) {
-            const int b = j & 1;
-            const uint32_t parity = static_cast<uint32_t>(j >> 1) & 1u;
+            const int b = j % kHeadSlots;
+            const uint32_t parity = static_cast<uint32_t>(j / kHeadSlots) & 1u;
             mbar_wait(bars_u32 + 8 * (2 + b), parity);  // the heads; y_adv is awaited (wait_lazy_p) after the fused blocks are built
             f_off = 2 * kMapBytes + b * kHeadBytes;
-            p_off = b * kMapBytes;
+            p_off = (j & 1) * kMapBytes;
         };
         auto wait_lazy_p = [&](int j) { mbar_wait(bars_u32 + 8 * (j & 1), static_cast<uint32_t>(j >> 1) & 1u); };
         int r_done = 0;  // samples [0, r_done) of the block have been released by this warp
@@ -627,7 +625,7 @@ __global__ void __launch_bounds__(32 * (RDDShape<FUSED, GW>::W + 1), 1) regdisp_
             const float4* LP4 = reinterpret_cast<const float4*>(lp);
             float* xch = sh.xch[xb][warp];
             int freed0;  // first slot freed by this map (UPM consecutive slots)
-            unsigned long long* wt = (trace && lane == 0 && jj < kRDDTraceMaps) ? trace + 8 + (warp * kRDDTraceMaps + jj) * 8 : nullptr;
+            unsigned long long* wt = (trace && lane == 0 && jj < kRDDTraceMaps && warp < 16) ? trace + 8 + (warp * kRDDTraceMaps + jj) * 8 : nullptr;
             if (wt) wt[0] = rdd_now();
             if (TASK == RD_BWD) {
                 // ---- backward: d/dp = coef (softmax(p) - u / S),  u = g / M + eps   -----------------
@@ -710,7 +708,10 @@ __global__ void __launch_bounds__(32 * (RDDShape<FUSED, GW>::W + 1), 1) regdisp_
                     if (poff[kk] >= 0) gout[poff[kk]] = gk[kk];
                 if (leader && lane == 0) {
                     if constexpr (LAZY) {
-                        if (jj + 2 < n_my) request_lazy(jj + 2);
+                        if (jj + 2 < n_my) {  // (backward: two head slots)
+                            request_lazy_h(jj + 2);
+                            request_lazy_p(jj + 2);
+                        }
                     } else {
                         int s = freed0;
                         for (int c = 0; c < UPM; ++c) {
@@ -904,6 +905,9 @@ __global__ void __launch_bounds__(32 * (RDDShape<FUSED, GW>::W + 1), 1) regdisp_
                 }
                 float Mp = warp_max_f32(max4(P4[lane]));  // the softmax reference: sampled from the map's first iteration
                 group_barrier(bar_id, 32 * G);
+                if constexpr (LAZY && kHeadSlots == 1) {  // every warp of the group has read the heads (blocks and patch): the next map's
+                    if (leader && lane == 0 && jj + 1 < n_my) request_lazy_h(jj + 1);
+                }
                 float M = -INFINITY;
 #pragma unroll
                 for (int g = 0; g < G; ++g) M = fmaxf(M, sh.xmx[xb][grp * G + g]);
@@ -966,7 +970,8 @@ __global__ void __launch_bounds__(32 * (RDDShape<FUSED, GW>::W + 1), 1) regdisp_
                     __syncwarp();
                     if (lane == 0) {
                         if constexpr (LAZY) {
-                            if (jj + 2 < n_my) request_lazy(jj + 2);
+                            if (jj + 2 < n_my) request_lazy_p(jj + 2);
+                            if (kHeadSlots == 2 && jj + 2 < n_my) request_lazy_h(jj + 2);
                         } else {
                             int s = freed0;
                             for (int c = 0; c < UPM; ++c) {
@@ -1012,7 +1017,8 @@ __global__ void __launch_bounds__(32 * (RDDShape<FUSED, GW>::W + 1), 1) regdisp_
 
 template <bool FUSED, int GW, int TASK, bool LAZY = false>
 static int launch_rdd_shape(const RDArgs& a, int sms, cudaStream_t stream, const char* who) {
-    constexpr size_t smem = LAZY ? RDDShape<FUSED, GW>::kLazySmem : RDDShape<FUSED, GW>::kSmem;
+    using Shape = RDDShape<FUSED, GW, LAZY ? kRDDLazyGroups : 0>;
+    constexpr size_t smem = LAZY ? Shape::kLazySmem : Shape::kSmem;
     static bool attr_done_dev[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -1032,7 +1038,7 @@ static int launch_rdd_shape(const RDArgs& a, int sms, cudaStream_t stream, const
     if (grid > n_maps) grid = n_maps;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(32 * (RDDShape<FUSED, GW>::W + 1));
+    cfg.blockDim = dim3(32 * (Shape::W + 1));
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
