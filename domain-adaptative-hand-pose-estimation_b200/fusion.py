@@ -66,7 +66,108 @@ def fuse_three_scales(lo, mid, hi):
     return _fuse(lo, 0.5, mid, 1.0, hi, 1.0, (hi.shape[2], hi.shape[3]))
 
 
-class FusedHeads:
+
+# ---- maps that are NOT built until somebody needs them --------------------------------------------------------------------
+def _unlazy(x):
+    if isinstance(x, _LazyMap):
+        return x.materialise()
+    if isinstance(x, (list, tuple)):
+        return type(x)(_unlazy(v) for v in x)
+    if isinstance(x, dict):
+        return {k: _unlazy(v) for k, v in x.items()}
+    return x
+
+
+class _LazyMap:
+    """Stands for a CUDA float32 tensor that has not been computed.  The consumers that can do better than reading it from
+    memory (``RegressionDisparityx6`` for :class:`FusedHeads`) recognise the type; every other use - a torch function or
+    method, arithmetic, any attribute of a tensor - sees :meth:`materialise` (one ``hp_fuse_multiscale`` launch, cached)."""
+
+    _map = None
+
+    def materialise(self):
+        raise NotImplementedError
+
+    def __getattr__(self, name):                 # only reached for names the lazy object itself does not have
+        if name.startswith("_"):
+            raise AttributeError(name)
+        return getattr(self.materialise(), name)
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        return func(*_unlazy(args), **_unlazy(kwargs or {}))
+
+    def __add__(self, other):
+        return self.materialise() + _unlazy(other)
+
+    def __radd__(self, other):
+        return _unlazy(other) + self.materialise()
+
+    def __sub__(self, other):
+        return self.materialise() - _unlazy(other)
+
+    def __rsub__(self, other):
+        return _unlazy(other) - self.materialise()
+
+    def __mul__(self, other):
+        return self.materialise() * _unlazy(other)
+
+    def __rmul__(self, other):
+        return _unlazy(other) * self.materialise()
+
+    def __truediv__(self, other):
+        return self.materialise() / _unlazy(other)
+
+    def __neg__(self):
+        return -self.materialise()
+
+    def __getitem__(self, idx):
+        return self.materialise()[idx]
+
+    def __len__(self):
+        return self.shape[0]
+
+
+class LazyUpsample(_LazyMap):
+    """``scale * nn.Upsample(size, mode='bilinear')(src)`` of a detached CUDA heatmap, not yet computed (what the overlay's
+    ``nn.Upsample`` route returns for train1.py:410-417).  ``c * lazy`` stays lazy, ``lazy + lazy`` (same output size) becomes
+    :class:`FusedHeads` - so the driver's ``target5 = 0.5 * target + target1`` reaches the loss as its two heads."""
+
+    def __init__(self, src, size, scale=1.0):
+        self.src = _lib.require_cuda(src.detach(), "LazyUpsample(src)")
+        if self.src.ndim != 4:
+            raise ValueError("LazyUpsample: src must be [B,K,h,w]")
+        self.size = (int(size), int(size)) if isinstance(size, int) else (int(size[0]), int(size[1]))
+        self.scale = float(scale)
+
+    @property
+    def shape(self):
+        return torch.Size((self.src.shape[0], self.src.shape[1]) + self.size)
+
+    def materialise(self):
+        if self._map is None:
+            self._map = _fuse(self.src, self.scale, None, 0.0, None, 0.0, self.size)
+        return self._map
+
+    def __mul__(self, other):
+        if isinstance(other, (int, float)) and not isinstance(other, bool):
+            return LazyUpsample(self.src, self.size, self.scale * float(other))
+        return self.materialise() * _unlazy(other)
+
+    __rmul__ = __mul__
+
+    def __add__(self, other):
+        if (isinstance(other, LazyUpsample) and other.size == self.size and self.size[0] == self.size[1]
+                and other.src.shape[:2] == self.src.shape[:2] and other.src.device == self.src.device):
+            lo, mid = (self, other) if self.src.shape[2] <= other.src.shape[2] else (other, self)
+            return FusedHeads(lo.src, mid.src, lo.scale, mid.scale, self.size[0])
+        return self.materialise() + _unlazy(other)
+
+    def __radd__(self, other):
+        return self.__add__(other)
+
+
+class FusedHeads(_LazyMap):
     """``a_lo * up(lo) + a_mid * up(mid)`` at ``size`` x ``size`` - the ``target5`` of train1.py:410-424 - NOT materialised.
 
     Pass it where ``RegressionDisparityx6.forward`` takes ``y_adv2``
@@ -86,7 +187,7 @@ class FusedHeads:
 
     @property
     def shape(self):
-        return (self.lo.shape[0], self.lo.shape[1], self.size, self.size)
+        return torch.Size((self.lo.shape[0], self.lo.shape[1], self.size, self.size))
 
     def in_kernel(self):
         """True when the dense disparity kernel can build the map itself (16x16 / 32x32 -> 64x64)."""

@@ -2,7 +2,7 @@
 
     python hpb200.py --ref /path/to/reference train1.py data/H3D -t Hand3DStudio ...
     python hpb200.py --ref /path/to/reference test.py  data/H3D -t Hand3DStudio --checkpoint ...
-    options before the driver: --verbose | --device-targets (rebind the per-sample generate_target too; needs
+    options before the driver: --verbose | --eager-upsample (see install_upsample_route) | --device-targets (rebind the per-sample generate_target too; needs
     --workers 0) | --plugin FILE.py (run FILE after the overlay is installed and before the driver, e.g. to register a
     synthetic dataset class in ``uda.dataset`` or a stand-in backbone in ``uda.model`` under a name the driver's
     ``-s/-t/-a`` flags can select)
@@ -112,11 +112,14 @@ def install_shims():
             pass
 
 
-def install(ref_root: str, verbose: bool = False, device_targets: bool = False, route_upsample: bool = True):
+def install(ref_root: str, verbose: bool = False, device_targets: bool = False, route_upsample: bool = True,
+            lazy_upsample: bool = True):
     """Shim, import and rebind.  Returns ``{module_name: [rebound names]}``.
     ``device_targets``: also rebind the per-sample ``generate_target`` (see OPT_IN).
     ``route_upsample``: send ``nn.Upsample(mode='bilinear')`` of detached CUDA fp32 heatmaps (train1.py:410-417) to
-    ``hp_fuse_multiscale`` (row a12)."""
+    ``hp_fuse_multiscale`` (row a12).  ``lazy_upsample``: the route returns ``fusion.LazyUpsample`` objects, so that the
+    driver's own ``target5 = 0.5 * target + target1`` reaches ``RegressionDisparityx6`` as its two heads and is built inside
+    the loss kernel (``--eager-upsample`` switches this off)."""
     ref_root = os.path.abspath(ref_root)
     if not os.path.isfile(os.path.join(ref_root, "utils", "keypoint_detection.py")):
         raise FileNotFoundError(f"{ref_root} does not look like the reference tree")
@@ -141,7 +144,7 @@ def install(ref_root: str, verbose: bool = False, device_targets: bool = False, 
                 setattr(mod, name, getattr(pkg, name))
                 rebound.setdefault(modname, []).append(name)
     if route_upsample:
-        install_upsample_route()
+        install_upsample_route(lazy=lazy_upsample)
     if verbose:
         for m in sorted(rebound):
             print(f"[hpb200 overlay] {m}: {', '.join(sorted(rebound[m]))}", file=sys.stderr)
@@ -151,13 +154,23 @@ def install(ref_root: str, verbose: bool = False, device_targets: bool = False, 
 _UPSAMPLE_ROUTED = False
 
 
-def install_upsample_route():
+_UPSAMPLE_LAZY = True
+
+
+def install_upsample_route(lazy=True):
     """train1.py:410-417 / test.py:362-369 build ``nn.Upsample(size=64|32, mode='bilinear')`` inline and apply them
     to DETACHED adversarial heatmaps.  The drivers must stay unchanged, so the route is on ``nn.Upsample.forward``:
     a bilinear, align_corners-free upsample of a CUDA fp32 4-D tensor that carries no autograd history goes to the
     gather+blend kernel (``fusion.upsample_bilinear`` -> ``hp_fuse_multiscale``); everything else (other modes,
-    tensors that need gradients - e.g. inside a model -, CPU tensors, scale_factor forms) takes torch's own path."""
-    global _UPSAMPLE_ROUTED
+    tensors that need gradients - e.g. inside a model -, CPU tensors, scale_factor forms) takes torch's own path.
+
+    ``lazy``: the route returns a ``fusion.LazyUpsample`` (the map is not built yet).  train1.py:424-428 only scales, adds and
+    hands these maps to the disparity losses: ``0.5 * target + target1`` becomes ``fusion.FusedHeads``, which
+    ``RegressionDisparityx6(..., mode='max')`` consumes as two heads (the fused map is interpolated inside the loss kernel and
+    never written); ``target0`` is materialised by ``RegressionDisparityx5`` with one launch.  Any other use of such an object
+    (a torch function, an attribute of a tensor, other arithmetic) materialises it first - same values as the eager route."""
+    global _UPSAMPLE_ROUTED, _UPSAMPLE_LAZY
+    _UPSAMPLE_LAZY = bool(lazy)
     if _UPSAMPLE_ROUTED:
         return
     import torch
@@ -172,7 +185,7 @@ def install_upsample_route():
                 and not (input.requires_grad and torch.is_grad_enabled())):
             hw = (size, size) if isinstance(size, int) else tuple(int(v) for v in size)
             if len(hw) == 2 and hw[0] >= input.shape[2] and hw[1] >= input.shape[3]:
-                return fusion.upsample_bilinear(input, hw)
+                return fusion.LazyUpsample(input, hw) if _UPSAMPLE_LAZY else fusion.upsample_bilinear(input, hw)
         return stock(self, input)
 
     nn.Upsample.forward = forward
@@ -183,6 +196,7 @@ def main(argv=None):
     argv = list(sys.argv[1:] if argv is None else argv)
     ref = os.environ.get("HP_REF_DIR")
     verbose = device_targets = False
+    lazy_upsample = True
     plugins = []
     while argv and argv[0].startswith("--"):
         if argv[0] == "--ref" and len(argv) > 1:
@@ -197,6 +211,9 @@ def main(argv=None):
         elif argv[0] == "--verbose":
             verbose = True
             argv = argv[1:]
+        elif argv[0] == "--eager-upsample":
+            lazy_upsample = False
+            argv = argv[1:]
         else:
             break
     if not argv or ref is None:
@@ -204,7 +221,7 @@ def main(argv=None):
         print("error: give the reference tree with --ref DIR or HP_REF_DIR", file=sys.stderr)
         return 2
     script = argv[0] if os.path.isabs(argv[0]) else os.path.join(ref, argv[0])
-    install(ref, verbose=verbose, device_targets=device_targets)
+    install(ref, verbose=verbose, device_targets=device_targets, lazy_upsample=lazy_upsample)
     for path in plugins:       # launcher-side registrations (e.g. a synthetic dataset / a stand-in backbone by name)
         runpy.run_path(path, run_name="__hpb200_plugin__")
     sys.argv = [script] + argv[1:]

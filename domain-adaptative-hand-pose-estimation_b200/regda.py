@@ -28,7 +28,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .fusion import FusedHeads
+from .fusion import FusedHeads, LazyUpsample
 from .loss import JointsKLLoss, _NoCtx, _wants_grad
 
 _VARIANT_CODE = {"base": _lib.RD_BASE, "x1": _lib.RD_X1, "x5": _lib.RD_X5, "x6": _lib.RD_X6, "rd4": _lib.RD_RD4}
@@ -113,6 +113,8 @@ class _RegDisp(torch.autograd.Function):
             raise ValueError(f"y_adv is {tuple(adv.shape)}, the pseudo-label grid is {(B, K, oh, ow)}")
         dev = adv.device
         fz = heads = None
+        if isinstance(fused, LazyUpsample):      # (the overlay's nn.Upsample route; x5 'max' reads target0 as a map)
+            fused = None if mode == _lib.MODE_MIN else fused.materialise()
         if isinstance(fused, FusedHeads):
             # y_adv2 given as its two heads (train1.py:410-424 unfused): x6 'max' on the 64x64 grid builds the map inside the loss
             # kernel; 'min' never reads y_adv2 (regda_7.py:3614-3631); everything else gets the materialised map
@@ -249,7 +251,7 @@ class _RDBase(nn.Module):
         from .keypoint_detection import decode
         yd, (B, K, H, W), (oh, ow, shift, tmp, _) = plg._check_input(y)
         dev = yd.device
-        if isinstance(y_adv2, FusedHeads):
+        if isinstance(y_adv2, (FusedHeads, LazyUpsample)):
             y_adv2 = y_adv2.materialise()
         fz = None if y_adv2 is None else _lib.require_cuda(y_adv2.detach(), "y_adv2")
         preds, _ = decode(yd)
