@@ -828,7 +828,11 @@ __global__ void __launch_bounds__(32 * (RDDShape<FUSED, GW, LAZY ? kRDDLazyGroup
                     wait_lazy(jj, f_off, p_off);
                     freed0 = 0;
                 } else {
-                    const int sf = wait_unit(), sp = wait_unit();
+                    // the fused map now; y_adv is awaited behind pass 1, which does not read it.  g stays in registers, so the
+                    // fused map's slot is free once every warp of the group has been through pass 1: the NEXT map's y_adv is
+                    // requested into it there (not when this map closes), a whole pass 2 + closure + patch + pass 1 ahead of
+                    // its use (timeline before: 1.0 us of a map's 3.1 us were the wait for y_adv)
+                    const int sf = wait_unit(), sp = slot_c;
                     freed0 = sf;
                     f_off = sf * kMapBytes;
                     p_off = sp * kMapBytes;
@@ -838,7 +842,7 @@ __global__ void __launch_bounds__(32 * (RDDShape<FUSED, GW, LAZY ? kRDDLazyGroup
                 float4* F4 = reinterpret_cast<float4*>(my_slots + f_off);
                 float* F = reinterpret_cast<float*>(F4);  // (LAZY: the heads, 16x16 then 32x32; read only)
                 if (wt) wt[1] = rdd_now();
-                float4 fv[LAZY ? 8 : 1];
+                float4 fv[LAZY ? 8 : IT];  // g of this lane's float4s (LAZY: first the fused values of its two blocks)
                 if constexpr (LAZY)  // before the label is awaited: the fused values of this lane's blocks
                 {
                     rdd_fused_blocks(slots_u32 + f_off, slots_u32 + f_off + kRDDLoBytes, a.a_lo, a.a_mid, bn, bm, fv);
@@ -859,7 +863,7 @@ __global__ void __launch_bounds__(32 * (RDDShape<FUSED, GW, LAZY ? kRDDLazyGroup
                     const int off = in ? y * ow + x : 0;
                     const float lpv = lp[off];
                     const float fval = LAZY ? rdd_fused_at(F, F + kRDDLoBytes / 4, a.a_lo, a.a_mid, in ? x : 0, in ? y : 0) : F[off];
-                    pk[kk] = P[off];
+                    pk[kk] = LAZY ? P[off] : 0.0f;  // (pre-fused: read behind pass 1, once y_adv has been awaited)
                     float g = clip01(__fsub_rn(lpv, __fmul_rn(sl.t[kk], 10.0f)));
                     g = clip01(__fsub_rn(__fadd_rn(g, fval), __fmul_rn(sl.t[kk], 100.0f)));
                     gex[kk] = g;
@@ -895,16 +899,23 @@ __global__ void __launch_bounds__(32 * (RDDShape<FUSED, GW, LAZY ? kRDDLazyGroup
                     for (int it = h * IT; it < (h + 1) * IT; ++it) {
                         const float4 f = F4[it * 32 + lane], l = LP4[it * 32 + lane];
                         const float4 g = clip01_4(add4(l, f));
-                        F4[it * 32 + lane] = g;
+                        fv[LAZY ? 0 : it - h * IT] = g;
                         mg = fmaxf(mg, max4(g));
                     }
+                    wait_unit();  // y_adv (slot sp)
+#pragma unroll
+                    for (int kk = 0; kk < NSL; ++kk) pk[kk] = P[poff[kk] >= 0 ? poff[kk] : 0];
                 }
                 {
                     const float wmg = warp_max_f32(mg);
                     if (lane == 0) sh.xmx[xb][warp] = wmg;
                 }
                 float Mp = warp_max_f32(max4(P4[lane]));  // the softmax reference: sampled from the map's first iteration
+                if constexpr (!LAZY) fence_proxy_async_smem();  // this lane's -inf marks in the slot precede the copy engine's next write
                 group_barrier(bar_id, 32 * G);
+                if constexpr (!LAZY) {  // every warp of the group is through pass 1: the fused map's slot takes the next map's y_adv
+                    if (leader && lane == 0 && u_load < n_units) request(u_load, freed0);
+                }
                 if constexpr (LAZY && kHeadSlots == 1) {  // every warp of the group has read the heads (blocks and patch): the next map's
                     if (leader && lane == 0 && jj + 1 < n_my) request_lazy_h(jj + 1);
                 }
@@ -923,7 +934,7 @@ __global__ void __launch_bounds__(32 * (RDDShape<FUSED, GW, LAZY ? kRDDLazyGroup
                     for (int q = 0; q < 8; ++q) rdd_fused_acc(A, P4[(4 * bm + q) * kRDDRow4 + bn], fv[q], l2e, mb2, im2, e2);
                 } else {
 #pragma unroll
-                    for (int it = h * IT; it < (h + 1) * IT; ++it) rdd_fused_acc(A, P4[it * 32 + lane], F4[it * 32 + lane], l2e, mb2, im2, e2);
+                    for (int it = h * IT; it < (h + 1) * IT; ++it) rdd_fused_acc(A, P4[it * 32 + lane], fv[LAZY ? 0 : it - h * IT], l2e, mb2, im2, e2);
                 }
                 const float2 s2 = A.s2, su2 = A.su2, sup2 = A.sup2, suq2 = A.suq2, sulg2 = A.sulg2, sulh2 = A.sulh2;
                 if (wt) wt[4] = rdd_now();
@@ -972,12 +983,8 @@ __global__ void __launch_bounds__(32 * (RDDShape<FUSED, GW, LAZY ? kRDDLazyGroup
                         if constexpr (LAZY) {
                             if (jj + 2 < n_my) request_lazy_p(jj + 2);
                             if (kHeadSlots == 2 && jj + 2 < n_my) request_lazy_h(jj + 2);
-                        } else {
-                            int s = freed0;
-                            for (int c = 0; c < UPM; ++c) {
-                                if (u_load + c < n_units) request(u_load + c, s);
-                                s = (s + 1 == NS) ? 0 : s + 1;
-                            }
+                        } else {  // (the next map's y_adv, unit u_load, went out behind pass 1) the fused map after it -> y_adv's slot
+                            if (u_load + 1 < n_units) request(u_load + 1, (freed0 + 1 == NS) ? 0 : freed0 + 1);
                         }
                         if (wt) wt[5] = rdd_now();
                         const float lg_se = lg2_approx(Sexp);
