@@ -23,6 +23,7 @@ for _ in range(reps):
     for args, rd in (((y, adv.clone().requires_grad_(True), None, None, "min"), rd6),
                      ((y, adv.clone().requires_grad_(True), None, None, "max"), rd6),
                      ((y, adv.clone().requires_grad_(True), t5, None, "max"), rd6),
+                     ((y, adv.clone().requires_grad_(True), hp.FusedHeads(a16, a32), None, "max"), rd6),
                      ((y, a32.clone().requires_grad_(True), None, None, "min"), rd5),
                      ((y, a32.clone().requires_grad_(True), t0, None, "max"), rd5),
                      ((y, a16.clone().requires_grad_(True), None, "min"), rd1),
