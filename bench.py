@@ -899,7 +899,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="pipeline64", choices=sorted(WORKLOADS))
-    ap.add_argument("--slab", type=int, default=32, help="samples per H2D slab in the end-to-end path")
+    ap.add_argument("--slab", type=int, default=64, help="samples per H2D slab in the end-to-end path")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
                     help="N>1: how the ranks' partial vectors are summed each step")

@@ -127,6 +127,12 @@ class _LazyMap:
     def __len__(self):
         return self.shape[0]
 
+    def __array__(self, *args, **kwargs):         # numpy conversion behaves like the tensor's (a CUDA tensor refuses it)
+        return self.materialise().__array__(*args, **kwargs)
+
+    def __repr__(self):
+        return f"{type(self).__name__}(shape={tuple(self.shape)}, materialised={self._map is not None})"
+
 
 class LazyUpsample(_LazyMap):
     """``scale * nn.Upsample(size, mode='bilinear')(src)`` of a detached CUDA heatmap, not yet computed (what the overlay's
