@@ -891,7 +891,21 @@ def fuse_parity_check(h, hp, ev, lo, mid, hi, tgt):
     return detail
 
 
+def _keep_stdout_for_the_json_line():
+    """The contract is ONE JSON line on stdout.  Native libraries write there too (NCCL's "NCCL version ..." banner at the first
+    communicator, whatever NCCL_DEBUG says once torch has loaded it): file descriptor 1 is pointed at stderr for everything
+    below Python, and sys.stdout keeps the real stdout for the line itself."""
+    try:
+        sys.stdout.flush()
+        real = os.dup(1)
+        os.dup2(2, 1)
+        sys.stdout = os.fdopen(real, "w", buffering=1)
+    except OSError:
+        pass
+
+
 def main():
+    _keep_stdout_for_the_json_line()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=None, help="steps per timed region (default: 2000 for the 64x64 pipeline, "
