@@ -299,6 +299,35 @@ def case_fusion(ns, device="cpu"):
     return {"c:target5": _np(t5), "c:target0": _np(t0)}
 
 
+# ---------------------------------------------------------------------------------- step B of train(), as written
+
+def case_step_b(ns, device="cpu"):
+    """train1.py:405-431 (== test.py:357-383): the three ground-false losses of step B from the adversarial heads - x1 'max' on the
+    16x16 head, x6 'max' against ``target5 = 0.5 * up64(y_adv3) + up64(y_adv2)``, x5 'max' against ``target0 = up32(y_adv3)`` -,
+    their weighted sum (train1.py:430) and its gradients with respect to the three heads.  The reference and the oracle execute
+    the driver's inline ``nn.Upsample`` statements; a namespace that offers ``FusedHeads`` (the CUDA package) hands ``target5``
+    to the loss UNFUSED, so the golden values of this case pin the fusion done inside the loss kernel to the real reference."""
+    I = disparity_inputs(seed=801, B=3)
+    y, w = _t(I["y"], device), _t(I["w"], device)
+    y_adv, y_adv2, y_adv3 = (_t(I[k], device, grad=True) for k in ("adv64", "adv32", "adv16"))
+    kl = lambda: ns.JointsKLLoss(epsilon=1e-7)                                   # train1.py:135-137
+    regression_disparity = ns.RegressionDisparityx6(ns.PseudoLabelGenerator(K, 64, 64), kl())
+    regression_disparity2 = ns.RegressionDisparityx5(ns.PseudoLabelGenerator03(K), kl())
+    regression_disparity1 = ns.RegressionDisparityx1(ns.PseudoLabelGenerator01(K), kl())
+    loss1 = regression_disparity1(y, y_adv3, w, mode="max")                      # train1.py:408
+    if getattr(ns, "FusedHeads", None) is not None:
+        target5 = ns.FusedHeads(y_adv3, y_adv2)
+        target0 = ns.upsample_bilinear(y_adv3.detach(), 32)
+    else:
+        target5, target0 = reference_fusion(y_adv3, y_adv2)                      # train1.py:410-424
+    loss2 = regression_disparity(y, y_adv, target5, w, mode="max")               # train1.py:426
+    loss3 = regression_disparity2(y, y_adv2, target0, w, mode="max")             # train1.py:428
+    total = 0.3 * loss1 + 1 * loss2 + 0.3 * loss3                                # train1.py:430
+    total.backward()
+    return {"c:loss1": _np(loss1), "c:loss2": _np(loss2), "c:loss3": _np(loss3), "c:total": _np(total),
+            "c:grad_y_adv": _np(y_adv.grad), "c:grad_y_adv2": _np(y_adv2.grad), "c:grad_y_adv3": _np(y_adv3.grad)}
+
+
 # ---------------------------------------------------------------------------------- f4
 
 def case_soft_decode(ns, device="cpu"):
@@ -389,6 +418,7 @@ CASES = {
     "pseudo_label": case_pseudo_label,
     "disparity": case_disparity,
     "fusion": case_fusion,
+    "step_b": case_step_b,
     "soft_decode": case_soft_decode,
     "variants": case_variants,
 }

@@ -1,6 +1,7 @@
 """Freeze golden vectors FROM THE REAL REFERENCE  (run here, where /root/reference exists).
 
     python -m oracle.gen_golden            # writes tests/golden/<case>.npz + MANIFEST.json
+    python -m oracle.gen_golden step_b     # only the named cases (a new case is added without touching the other files)
 
 Evaluates every case of ``oracle/cases.py`` on the reference's own code (loaded in place by
 ``oracle/ref_loader.py``) and stores the outputs.  Inputs are regenerated from seeds by the
@@ -52,7 +53,13 @@ def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     manifest = {"source": "real reference executed in place from /root/reference",
                 "numpy": np.__version__, "torch": torch.__version__, "files": {}}
+    only = set(sys.argv[1:])     # python -m oracle.gen_golden [case ...]: freeze only these (the other files and their entries stay)
+    if only:
+        with open(os.path.join(GOLDEN_DIR, "MANIFEST.json")) as f:
+            manifest["files"] = json.load(f)["files"]
     for name, fn in cases.CASES.items():
+        if only and name not in only:
+            continue
         out = digest(fn(ns, "cpu"))
         path = os.path.join(GOLDEN_DIR, f"{name}.npz")
         np.savez_compressed(path, **out)

@@ -28,7 +28,7 @@ def _ns():
         PseudoLabelGenerator02=hp.PseudoLabelGenerator02, PseudoLabelGenerator03=hp.PseudoLabelGenerator03,
         RegressionDisparity=hp.RegressionDisparity, RegressionDisparityx1=hp.RegressionDisparityx1,
         RegressionDisparityx5=hp.RegressionDisparityx5, RegressionDisparityx6=hp.RegressionDisparityx6,
-        fuse_multiscale=hp.fuse_multiscale,
+        fuse_multiscale=hp.fuse_multiscale, FusedHeads=hp.FusedHeads, upsample_bilinear=hp.upsample_bilinear,
         **{n: getattr(hp, n) for n in ("RegressionDisparity2", "RegressionDisparity3", "RegressionDisparity4",
                                        "RegressionDisparity5", "RegressionDisparity6", "RegressionDisparity7",
                                        "RegressionDisparity8", "RegressionDisparityx2", "RegressionDisparityx3",
