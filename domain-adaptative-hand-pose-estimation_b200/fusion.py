@@ -38,9 +38,13 @@ def upsample_bilinear(x, size):
     return _fuse(x, 1.0, None, 0.0, None, 0.0, size)
 
 
-def fuse_multiscale(y_adv3, y_adv2, size_hi=64, size_mid=32):
+def fuse_multiscale(y_adv3, y_adv2, size_hi=64, size_mid=32, lazy=False):
     """train1.py:410-424 -> ``(target5, target0)`` with
-    ``target5 = 0.5*up_hi(y_adv3) + up_hi(y_adv2)`` and ``target0 = up_mid(y_adv3)`` (inputs detached)."""
+    ``target5 = 0.5*up_hi(y_adv3) + up_hi(y_adv2)`` and ``target0 = up_mid(y_adv3)`` (inputs detached).
+    ``lazy=True``: neither map is built - ``(FusedHeads, LazyUpsample)``, which the disparity modules accept as ``y_adv2``
+    (x6 'max' interpolates ``target5`` inside its loss kernel; anything else materialises on first use)."""
+    if lazy:
+        return FusedHeads(y_adv3, y_adv2, 0.5, 1.0, size_hi), LazyUpsample(y_adv3, size_mid)
     if isinstance(size_hi, int) and isinstance(size_mid, int) and 2 * size_mid == size_hi:
         # both maps from ONE launch (hp_fuse_multiscale_pair; any geometry it does not cover falls back to two inside the call)
         lo = _lib.require_cuda(y_adv3.detach(), "fuse(lo)")

@@ -80,3 +80,11 @@ def test_fused_heads_outside_the_kernels_geometry_materialise(cpu_fuse):
     assert isinstance(fh, fusion.FusedHeads) and not fh.in_kernel()
     want = F.interpolate(a8, size=64, mode="bilinear") + F.interpolate(a16, size=64, mode="bilinear")
     assert torch.allclose(fh.materialise(), want, atol=1e-6)
+
+
+def test_fuse_multiscale_lazy_form(cpu_fuse):
+    a16, a32 = _heads()
+    t5, t0 = fusion.fuse_multiscale(a16, a32, 64, 32, lazy=True)
+    assert isinstance(t5, fusion.FusedHeads) and isinstance(t0, fusion.LazyUpsample) and not cpu_fuse
+    assert t5.in_kernel() and tuple(t0.shape) == (2, 21, 32, 32)
+    assert torch.allclose(t0.materialise(), F.interpolate(a16, size=32, mode="bilinear"), atol=1e-6)
