@@ -122,7 +122,8 @@ class _RegDisp(torch.autograd.Function):
                 raise ValueError(f"y_adv2 is {tuple(fused.shape)}, expected {(B, K, oh, ow)}")
             if mode == _lib.MODE_MIN:
                 fused = None
-            elif variant == _lib.RD_X6 and fused.in_kernel() and (H, W) == (oh, ow) and tmp <= 6 and K <= 32:
+            elif (variant == _lib.RD_X6 and fused.in_kernel() and (H, W) == (oh, ow) and tmp <= 6 and K <= 32
+                  and fused.lo.device == dev and fused.mid.device == dev and adv.data_ptr() % 16 == 0):
                 heads, fused = fused, None
             else:
                 fused = fused.materialise()
